@@ -1,0 +1,182 @@
+/*
+ * radiobear_b200 -- C ABI of the B200 (sm_100a) hot paths of RadioBEAR.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.  Each entry
+ * point names the reference interface it replaces (paths relative to david-deboer/radiobear
+ * v2.0.1, radiobear/...).  The reference is pure Python, so the "FFI" a maintainer adds is a
+ * ctypes stub; see INTEGRATION.md.  The Python host in radiobear_b200/ binds exactly these.
+ *
+ * Conventions
+ *   - all floating point arrays are float64 unless stated; frequencies GHz, T in K, P in bar,
+ *     lengths km, absorption in cm^-1 ('invcm') or dB/km.
+ *   - every call returns RB_OK (0) or an error code; rb_last_error() gives the message.
+ *     Nothing is printed from kernels.  No pointer is retained after a call returns.
+ *   - functions without suffix take HOST pointers and copy in/out on the context stream
+ *     (synchronous on return).  "_dev" functions take DEVICE pointers and only enqueue work on
+ *     the context stream (asynchronous; call rb_synchronize or sync the stream yourself).
+ *   - one context per (process, GPU); a context is not thread-safe.
+ */
+#ifndef RADIOBEAR_B200_H
+#define RADIOBEAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+
+/* status codes */
+#define RB_OK 0
+#define RB_ERR_INVALID 1      /* bad argument (Python raises ValueError) */
+#define RB_ERR_CUDA 2         /* CUDA runtime failure (RuntimeError) */
+#define RB_ERR_NOMEM 3        /* device allocation failed (MemoryError) */
+#define RB_ERR_UNSUPPORTED 4  /* formalism / option not built (NotImplementedError) */
+
+typedef struct rb_context rb_context;
+
+/* ---- context --------------------------------------------------------------------------- */
+int rb_abi_version(void);
+/* Create a context on CUDA device `device`.  Fails (RB_ERR_CUDA) when no sm_100 GPU is there:
+ * there is no CPU fallback. */
+int rb_create(int device, rb_context** ctx);
+void rb_destroy(rb_context* ctx);
+const char* rb_last_error(const rb_context* ctx);
+/* Use an existing CUDA stream (cudaStream_t as void*; NULL = the context's own stream). */
+int rb_set_stream(rb_context* ctx, void* cuda_stream);
+int rb_synchronize(rb_context* ctx);
+/* Number of kernel launches issued through this context since creation (bench bookkeeping). */
+int64_t rb_launch_count(const rb_context* ctx);
+/* Device time (ms, CUDA events on the context stream) of the last call of each kernel family;
+ * which: 0 alpha_lines, 1 ray_geometry, 2 rt_integrate.  Valid after rb_synchronize when timing
+ * was enabled with rb_enable_timing(ctx, 1). */
+int rb_enable_timing(rb_context* ctx, int on);
+double rb_last_kernel_ms(rb_context* ctx, int which);
+
+/* ---- line catalogs --------------------------------------------------------------------- *
+ * Replaces the per-plugin npz readers: nh3_hs.py:62-67, nh3_sjs.py:17-23, h2s_ddb.py:14-39,
+ * ph3_jh.py:18-61, co_ddb.py:14-19.  Truncation (truncate_strength / truncate_freq) is applied
+ * by the caller before upload.  cols is row-major [ncols][nlines] (host memory).            */
+#define RB_CAT_NH3_INV 0 /* fo, Io, Eo, gammaNH3o                                  (4 cols) */
+#define RB_CAT_NH3_ROT 1 /* fo_rot, Io_rot, Eo_rot, gNH3_rot, gH2_rot, gHe_rot      (6 cols) */
+#define RB_CAT_NH3_V2 2  /* fo_v2, Io_v2, Eo_v2                                    (3 cols) */
+#define RB_CAT_NH3_SJS 3 /* f0, I0, E, G0                                          (4 cols) */
+#define RB_CAT_H2S 4     /* f0, I0, E, GH2S                                        (4 cols) */
+#define RB_CAT_PH3 5     /* f0, I0, E, WgtI0, WgtFGB, WgtSB                        (6 cols) */
+#define RB_CAT_CO 6      /* f0, I0, E                                              (3 cols) */
+#define RB_CAT_H2O 7     /* f_o, I_o, E_o, w_s, x_s, w_h2, w_he, x_h2, x_he  (9 cols, h2o_bk.py:23-49) */
+#define RB_NUM_CATALOGS 8
+int rb_set_catalog(rb_context* ctx, int catalog, int nlines, int ncols, const double* cols);
+
+/* ---- absorption (hot path A) ----------------------------------------------------------- *
+ * Formalism ids = module names under constituents/<gas>/ (alpha.py:59-68).                  */
+#define RB_F_NONE 0
+#define RB_F_NH3_HS 1      /* nh3/nh3_hs.py:70-312      */
+#define RB_F_NH3_DBS 2     /* nh3/nh3_dbs.py:70-313     */
+#define RB_F_NH3_SJS 3     /* nh3/nh3_sjs.py:26-128     */
+#define RB_F_NH3_HS_SJS 4  /* nh3/nh3_hs_sjs.py:6-26    */
+#define RB_F_NH3_DBS_SJS 5 /* nh3/nh3_dbs_sjs.py:6-26   */
+#define RB_F_H2S_DDB 6     /* h2s/h2s_ddb.py:42-87      */
+#define RB_F_PH3_JH 7      /* ph3/ph3_jh.py:64-108      */
+#define RB_F_H2O_BK 8      /* h2o/h2o_bk.py:65-187      */
+#define RB_F_H2_JJ_DDB 9   /* h2/h2_jj_ddb.py:7-38      */
+#define RB_F_H2_JJ 10      /* h2/h2_jj.py:7-22          */
+#define RB_F_CLOUDS_IDP 11 /* clouds/clouds_idp.py:6-101 */
+#define RB_F_CO_DDB 12     /* co/co_ddb.py:22-99        */
+#define RB_NUM_FORMALISMS 13
+#define RB_MAX_CONSTITUENTS 8
+
+#define RB_UNITS_INVCM 0
+#define RB_UNITS_DBPERKM 1
+
+/* gas rows used by the plugins (P_dict lookups, e.g. nh3_hs.py:101-103) */
+enum { RB_GAS_H2 = 0, RB_GAS_HE, RB_GAS_CH4, RB_GAS_NH3, RB_GAS_H2O, RB_GAS_H2S, RB_GAS_PH3, RB_GAS_CO,
+       RB_NUM_GAS };
+/* cloud rows used by clouds_idp.py:17-47 */
+enum { RB_CLD_H2O = 0, RB_CLD_SOLN, RB_CLD_NH4SH, RB_CLD_NH3, RB_CLD_H2S, RB_CLD_CH4, RB_NUM_CLD };
+
+typedef struct rb_alpha_desc {
+  int32_t n_layers;                        /* L */
+  int32_t n_freqs;                         /* F */
+  int32_t n_constituents;                  /* C <= RB_MAX_CONSTITUENTS, in CALL order = sorted(constituent), alpha.py:83 */
+  int32_t formalism[RB_MAX_CONSTITUENTS];  /* RB_F_* per constituent */
+  const double* freqs;                     /* [F] GHz */
+  const double* T;                         /* [L] K    (atm.gas[C['T']]) */
+  const double* P;                         /* [L] bar  (atm.gas[C['P']]) */
+  const double* gas;                       /* [gas_rows][L] mixing ratios (atm.gas) */
+  int32_t gas_rows;
+  int32_t gas_col[RB_NUM_GAS];             /* row of H2,HE,CH4,NH3,H2O,H2S,PH3,CO in `gas` (P_dict); -1 = absent */
+  const double* cloud;                     /* [cloud_rows][L] cloud densities (atm.cloud) or NULL */
+  int32_t cloud_rows;
+  int32_t cloud_col[RB_NUM_CLD];           /* rows in `cloud` (cloud_dict); -1 = absent */
+  uint32_t cloud_flags;                    /* bit i set <=> other_dict enables species i (clouds_idp.py:17-45),
+                                              bit order: ice_p(H2O) water_p(SOLN) nh4sh_p nh3ice_p h2sice_p ch4 */
+  int32_t h2state;                         /* 0 'e', 1 'n' (h2_jj_ddb.py:17-30) */
+  int32_t coshape;                         /* 0 voigt, 1 vvw, 2 diff, 3 other (co_ddb.py:39-42) */
+  int32_t units;                           /* RB_UNITS_* (parameters.py:4-8) */
+  const double* scale;                     /* [C][L] per-constituent per-layer scale or NULL (alpha.py:151-192, 235-259) */
+} rb_alpha_desc;
+
+/* Alpha.get_layers (alpha.py:261-305): total absorption for every (layer, freq).
+ *   out_total : [L][F]  (layer-major "alpha slab"; Alpha.layers[F][L] is its transpose view)
+ *   out_cube  : [L][F][C] per-constituent absorption after scaling (alpha.py:110-131) or NULL
+ * A single plugin call (constituents/<gas>/<formalism>.alpha, alpha.py:210) is n_layers = 1.   */
+int rb_alpha_layers(rb_context* ctx, const rb_alpha_desc* desc, double* out_total, double* out_cube);
+int rb_alpha_layers_dev(rb_context* ctx, const rb_alpha_desc* desc, double* out_total, double* out_cube);
+
+/* ---- ray geometry + radiative transfer (hot path B) ------------------------------------- */
+#define RB_GTYPE_ELLIPSE 0 /* shape.py:223-274 */
+#define RB_GTYPE_SPHERE 1  /* 'circle' / 'sphere' */
+#define RB_LIMB_SHAPE 0
+#define RB_LIMB_SEC 1      /* raypath.py:218-219 */
+
+typedef struct rb_geometry_desc {
+  int32_t n_layers;         /* L */
+  const double* radius;     /* [L] equatorial radius of each layer, km  (atm.property[LP['R']], raypath.py:124) */
+  double n0, n1;            /* refractive index of the two outermost layers (raypath.py:158) */
+  double Req, Rpol;         /* config.Req / config.Rpol, km */
+  double orientation[2];    /* [position angle, sub-earth latitude] degrees (raypath.py:39-44) */
+  int32_t gtype;            /* RB_GTYPE_* */
+  int32_t limb;             /* RB_LIMB_* */
+} rb_geometry_desc;
+
+/* raypath.compute_ds (raypath.py:108-273) for n_rays impact points b[R][2].
+ *   out_ds   : [R][L-1] path length per layer, km (NaN from the tangent depth on, as in the reference)
+ *   out_nseg : [R] number of valid segments; -1 = ray misses the planet (Ray.ds is None)
+ *   out_aspect: [3] tip, rotate (rad), rNorm (km)                                              */
+int rb_compute_ds(rb_context* ctx, const rb_geometry_desc* geom, int64_t n_rays, const double* b,
+                  double* out_ds, int32_t* out_nseg, double* out_aspect);
+
+typedef struct rb_rt_desc {
+  int32_t n_freqs;          /* F */
+  const double* alpha;      /* [L][F] alpha slab in cm^-1 (rb_alpha_layers out_total) */
+  const double* T;          /* [L] K */
+  int32_t disc_average;     /* 1: W = 2 a E2(tau) (brightness.py:95-96) -- use with b = (0,0) */
+  int32_t out_f32;          /* 1: out_Tb is float32 (Data.Tb dtype, data_handling.py:46-47) else float64 */
+  double tau_cut;           /* stop a ray once tau > tau_cut (exp(-tau) no longer representable in the sums);
+                               <= 0 disables.  The reference integrates every layer. */
+} rb_rt_desc;
+
+/* Brightness.single over a batch of rays (brightness.py:30-126): geometry + tau/W/Tb integration.
+ *   out_Tb          : [R][F] brightness temperature (off-planet rays: 2.725, brightness.py:46-51)
+ *   out_integrated_W: [R][F] or NULL
+ *   profile_ray >= 0 additionally returns for that ray out_tau / out_W / out_Tb_lyr, each [F][L-1]
+ *                    (Brightness.tau / .W / .Tb_lyr, brightness.py:118-120); pass -1 / NULL otherwise. */
+int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* geom, const rb_rt_desc* rt, int64_t n_rays,
+                const double* b, void* out_Tb, double* out_integrated_W, int64_t profile_ray, double* out_tau,
+                double* out_W, double* out_Tb_lyr);
+/* Device-pointer variant: geom->radius, rt->alpha, rt->T, b, out_* are device pointers. */
+int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* geom, const rb_rt_desc* rt, int64_t n_rays,
+                    const double* b, void* out_Tb, double* out_integrated_W);
+
+/* Integration only, for caller-supplied segments (Brightness.single with a given Ray):
+ *   ds : [R][S] km host, nseg[R]; layer4ds is implicit 0..nseg-1 (raypath.py:222-225).          */
+int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int64_t n_rays, int32_t n_seg,
+                    const double* ds, const int32_t* nseg, void* out_Tb, double* out_integrated_W);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADIOBEAR_B200_H */

@@ -1,0 +1,374 @@
+// radiobear_b200 -- the extern "C" boundary (include/radiobear_b200.h): context, catalogs,
+// host<->device staging around the kernels.  No torch, no C++ types in the signatures.
+#include "rb_common.cuh"
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+
+int rb_fail(rb_context* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+int rb_ensure(rb_context* ctx, int which, size_t bytes, void** out) {
+  DevBuf& b = ctx->buf[which];
+  if (bytes == 0) bytes = 16;
+  if (b.cap < bytes) {
+    if (b.p) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(b.p);
+      b.p = nullptr;
+      b.cap = 0;
+    }
+    size_t want = bytes + (bytes >> 3);  // 12.5 % headroom
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&b.p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return rb_fail(ctx, RB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.cap = want;
+  }
+  *out = b.p;
+  return RB_OK;
+}
+
+extern "C" {
+
+int rb_abi_version(void) { return RB_ABI_VERSION; }
+
+int rb_create(int device, rb_context** out) {
+  if (!out) return RB_ERR_INVALID;
+  *out = nullptr;
+  rb_context* ctx = new rb_context();
+  *out = ctx;  // returned even on failure so that rb_last_error works; caller destroys it
+  ctx->device = device;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return rb_fail(ctx, RB_ERR_CUDA, "no CUDA device available (%s): radiobear_b200 has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if (device < 0 || device >= count) return rb_fail(ctx, RB_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
+  RB_CUDA(ctx, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return rb_fail(ctx, RB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                   prop.major, prop.minor);
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 2; ++j) RB_CUDA(ctx, cudaEventCreate(&ctx->ev[i][j]));
+  return RB_OK;
+}
+
+void rb_destroy(rb_context* ctx) {
+  if (!ctx) return;
+  if (ctx->own_stream) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->buf)
+      if (b.p) cudaFree(b.p);
+    for (auto& c : ctx->cat)
+      if (c) cudaFree(c);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 2; ++j)
+        if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
+    cudaStreamDestroy(ctx->own_stream);
+  }
+  delete ctx;
+}
+
+const char* rb_last_error(const rb_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rb_set_stream(rb_context* ctx, void* s) {
+  if (!ctx) return RB_ERR_INVALID;
+  ctx->stream = s ? reinterpret_cast<cudaStream_t>(s) : ctx->own_stream;
+  return RB_OK;
+}
+
+int rb_synchronize(rb_context* ctx) {
+  if (!ctx) return RB_ERR_INVALID;
+  RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RB_OK;
+}
+
+int64_t rb_launch_count(const rb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int rb_enable_timing(rb_context* ctx, int on) {
+  if (!ctx) return RB_ERR_INVALID;
+  ctx->timing = on != 0;
+  return RB_OK;
+}
+
+double rb_last_kernel_ms(rb_context* ctx, int which) {
+  if (!ctx || which < 0 || which > 2 || !ctx->ev_valid[which]) return -1.0;
+  float ms = 0.f;
+  if (cudaEventSynchronize(ctx->ev[which][1]) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, ctx->ev[which][0], ctx->ev[which][1]) != cudaSuccess) return -1.0;
+  return ms;
+}
+
+int rb_set_catalog(rb_context* ctx, int catalog, int nlines, int ncols, const double* cols) {
+  if (!ctx) return RB_ERR_INVALID;
+  static const int want_cols[RB_NUM_CATALOGS] = {4, 6, 3, 4, 4, 6, 3, 9};
+  if (catalog < 0 || catalog >= RB_NUM_CATALOGS) return rb_fail(ctx, RB_ERR_INVALID, "catalog id %d unknown", catalog);
+  if (ncols != want_cols[catalog])
+    return rb_fail(ctx, RB_ERR_INVALID, "catalog %d needs %d columns, got %d", catalog, want_cols[catalog], ncols);
+  if (nlines < 0 || (nlines > 0 && !cols)) return rb_fail(ctx, RB_ERR_INVALID, "catalog %d: bad line count / pointer", catalog);
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->cat[catalog]) {
+    cudaFree(ctx->cat[catalog]);
+    ctx->cat[catalog] = nullptr;
+  }
+  ctx->cat_n[catalog] = nlines;
+  ctx->cat_cols[catalog] = ncols;
+  if (nlines == 0) return RB_OK;
+  const size_t bytes = (size_t)nlines * ncols * sizeof(double);
+  RB_CUDA(ctx, cudaMalloc(&ctx->cat[catalog], bytes));
+  RB_CUDA(ctx, cudaMemcpy(ctx->cat[catalog], cols, bytes, cudaMemcpyHostToDevice));
+  return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int check_alpha_desc(rb_context* ctx, const rb_alpha_desc* d, const double* out_total) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (!d || !out_total) return rb_fail(ctx, RB_ERR_INVALID, "alpha: null descriptor / output");
+  if (d->n_layers <= 0 || d->n_freqs <= 0) return rb_fail(ctx, RB_ERR_INVALID, "alpha: n_layers and n_freqs must be positive");
+  if (!d->freqs || !d->T || !d->P) return rb_fail(ctx, RB_ERR_INVALID, "alpha: freqs / T / P must not be null");
+  if (d->n_constituents <= 0 || d->n_constituents > RB_MAX_CONSTITUENTS)
+    return rb_fail(ctx, RB_ERR_INVALID, "alpha: n_constituents must be 1..%d", RB_MAX_CONSTITUENTS);
+  if (d->units != RB_UNITS_INVCM && d->units != RB_UNITS_DBPERKM) return rb_fail(ctx, RB_ERR_INVALID, "alpha: bad units");
+  return RB_OK;
+}
+
+int rb_alpha_layers_dev(rb_context* ctx, const rb_alpha_desc* d, double* out_total, double* out_cube) {
+  RB_TRY(check_alpha_desc(ctx, d, out_total));
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  // the frequency-class scan needs the (tiny) frequency list on the host
+  std::vector<double> hf(d->n_freqs);
+  RB_CUDA(ctx, cudaMemcpyAsync(hf.data(), d->freqs, sizeof(double) * d->n_freqs, cudaMemcpyDeviceToHost, ctx->stream));
+  RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return rb_launch_alpha(ctx, d, hf.data(), out_total, out_cube);
+}
+
+int rb_alpha_layers(rb_context* ctx, const rb_alpha_desc* d, double* out_total, double* out_cube) {
+  RB_TRY(check_alpha_desc(ctx, d, out_total));
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t L = d->n_layers, F = d->n_freqs, C = d->n_constituents;
+  rb_alpha_desc dd = *d;
+  void *p_f, *p_T, *p_P, *p_gas = nullptr, *p_cloud = nullptr, *p_scale = nullptr, *p_tot, *p_cube = nullptr;
+  RB_TRY(rb_ensure(ctx, RB_BUF_FREQS, F * 8, &p_f));
+  RB_TRY(rb_ensure(ctx, RB_BUF_T, L * 8, &p_T));
+  RB_TRY(rb_ensure(ctx, RB_BUF_P, L * 8, &p_P));
+  RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, L * F * 8, &p_tot));
+  cudaStream_t s = ctx->stream;
+  RB_CUDA(ctx, cudaMemcpyAsync(p_f, d->freqs, F * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_T, d->T, L * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_P, d->P, L * 8, cudaMemcpyHostToDevice, s));
+  if (d->gas && d->gas_rows > 0) {
+    RB_TRY(rb_ensure(ctx, RB_BUF_GAS, (size_t)d->gas_rows * L * 8, &p_gas));
+    RB_CUDA(ctx, cudaMemcpyAsync(p_gas, d->gas, (size_t)d->gas_rows * L * 8, cudaMemcpyHostToDevice, s));
+  }
+  if (d->cloud && d->cloud_rows > 0) {
+    RB_TRY(rb_ensure(ctx, RB_BUF_CLOUD, (size_t)d->cloud_rows * L * 8, &p_cloud));
+    RB_CUDA(ctx, cudaMemcpyAsync(p_cloud, d->cloud, (size_t)d->cloud_rows * L * 8, cudaMemcpyHostToDevice, s));
+  }
+  if (d->scale) {
+    RB_TRY(rb_ensure(ctx, RB_BUF_SCALE, C * L * 8, &p_scale));
+    RB_CUDA(ctx, cudaMemcpyAsync(p_scale, d->scale, C * L * 8, cudaMemcpyHostToDevice, s));
+  }
+  if (out_cube) RB_TRY(rb_ensure(ctx, RB_BUF_CUBE, L * F * C * 8, &p_cube));
+  dd.freqs = (const double*)p_f; dd.T = (const double*)p_T; dd.P = (const double*)p_P;
+  dd.gas = (const double*)p_gas; dd.cloud = (const double*)p_cloud; dd.scale = (const double*)p_scale;
+  RB_TRY(rb_launch_alpha(ctx, &dd, d->freqs, (double*)p_tot, (double*)p_cube));
+  RB_CUDA(ctx, cudaMemcpyAsync(out_total, p_tot, L * F * 8, cudaMemcpyDeviceToHost, s));
+  if (out_cube) RB_CUDA(ctx, cudaMemcpyAsync(out_cube, p_cube, L * F * C * 8, cudaMemcpyDeviceToHost, s));
+  RB_CUDA(ctx, cudaStreamSynchronize(s));
+  return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int make_geometry(rb_context* ctx, const rb_geometry_desc* g, int64_t R, RtLaunch* out) {
+  if (!g) return rb_fail(ctx, RB_ERR_INVALID, "geometry: null descriptor");
+  if (g->n_layers < 2) return rb_fail(ctx, RB_ERR_INVALID, "geometry: need at least 2 layers");
+  if (R <= 0) return rb_fail(ctx, RB_ERR_INVALID, "geometry: n_rays must be positive");
+  if (!(g->Req > 0.0) || !(g->Rpol > 0.0)) return rb_fail(ctx, RB_ERR_INVALID, "geometry: Req / Rpol must be positive");
+  if (g->gtype != RB_GTYPE_ELLIPSE && g->gtype != RB_GTYPE_SPHERE)
+    return rb_fail(ctx, RB_ERR_UNSUPPORTED, "geometry: gtype %d not built (ellipse / sphere only)", g->gtype);
+  out->L = g->n_layers;
+  out->n0 = g->n0; out->n1 = g->n1;
+  out->q = (g->gtype == RB_GTYPE_ELLIPSE) ? g->Rpol / g->Req : 1.0;
+  // computeAspect (raypath.py:39-44): f = 1 - Rpol/Req is used for every gtype
+  const double f = 1.0 - g->Rpol / g->Req;
+  const double tip = -g->orientation[0] * M_PI / 180.0;
+  const double rotate = -atan(tan(g->orientation[1] * M_PI / 180.0) * (1.0 - f) * (1.0 - f));
+  out->rot[0] = cos(tip); out->rot[1] = sin(tip); out->rot[2] = cos(rotate); out->rot[3] = sin(rotate);
+  out->limb = g->limb;
+  out->R = R;
+  out->Rpad = (R + 3) & ~(int64_t)3;
+  return RB_OK;
+}
+
+static void aspect_out(const rb_geometry_desc* g, double rNorm, double* out) {
+  const double f = 1.0 - g->Rpol / g->Req;
+  out[0] = -g->orientation[0] * M_PI / 180.0;
+  out[1] = -atan(tan(g->orientation[1] * M_PI / 180.0) * (1.0 - f) * (1.0 - f));
+  out[2] = rNorm;
+}
+
+int rb_compute_ds(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const double* b, double* out_ds,
+                  int32_t* out_nseg, double* out_aspect) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (!b || !out_ds || !out_nseg || !g || !g->radius) return rb_fail(ctx, RB_ERR_INVALID, "compute_ds: null pointer");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  RtLaunch L{};
+  RB_TRY(make_geometry(ctx, g, R, &L));
+  const size_t S = L.L - 1;
+  void *p_rad, *p_b, *p_ds, *p_n, *p_o;
+  RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, L.L * 8, &p_rad));
+  RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 4, &p_n));
+  RB_TRY(rb_ensure(ctx, RB_BUF_MISC, (size_t)R * S * 8, &p_o));
+  cudaStream_t s = ctx->stream;
+  RB_CUDA(ctx, cudaMemcpyAsync(p_rad, g->radius, L.L * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemsetAsync(p_ds, 0, S * L.Rpad * 8, s));
+  L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n;
+  RB_TRY(rb_launch_geometry(ctx, L));
+  RB_TRY(rb_launch_ds_transpose(ctx, L, (double*)p_o));
+  RB_CUDA(ctx, cudaMemcpyAsync(out_ds, p_o, (size_t)R * S * 8, cudaMemcpyDeviceToHost, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(out_nseg, p_n, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
+  RB_CUDA(ctx, cudaStreamSynchronize(s));
+  if (out_aspect) aspect_out(g, g->radius[0], out_aspect);
+  return RB_OK;
+}
+
+static int check_rt(rb_context* ctx, const rb_rt_desc* rt, const void* out_Tb) {
+  if (!rt || !out_Tb) return rb_fail(ctx, RB_ERR_INVALID, "rt: null descriptor / output");
+  if (rt->n_freqs <= 0) return rb_fail(ctx, RB_ERR_INVALID, "rt: n_freqs must be positive");
+  if (!rt->alpha || !rt->T) return rb_fail(ctx, RB_ERR_INVALID, "rt: alpha / T must not be null");
+  return RB_OK;
+}
+
+int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt, int64_t R, const double* b,
+                    void* out_Tb, double* out_intW) {
+  if (!ctx) return RB_ERR_INVALID;
+  RB_TRY(check_rt(ctx, rt, out_Tb));
+  if (!b || !g || !g->radius) return rb_fail(ctx, RB_ERR_INVALID, "rt: null pointer");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  RtLaunch L{};
+  RB_TRY(make_geometry(ctx, g, R, &L));
+  const size_t S = L.L - 1;
+  void *p_ds, *p_n;
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 4, &p_n));
+  L.radius = g->radius; L.b = b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n;
+  RB_TRY(rb_launch_geometry(ctx, L));
+  return rb_launch_integrate(ctx, L, rt, out_Tb, out_intW, -1, nullptr, nullptr, nullptr);
+}
+
+int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt, int64_t R, const double* b,
+                void* out_Tb, double* out_intW, int64_t profile_ray, double* out_tau, double* out_W,
+                double* out_Tblyr) {
+  if (!ctx) return RB_ERR_INVALID;
+  RB_TRY(check_rt(ctx, rt, out_Tb));
+  if (!b || !g || !g->radius) return rb_fail(ctx, RB_ERR_INVALID, "rt: null pointer");
+  if (profile_ray >= 0 && (!out_tau || !out_W || !out_Tblyr)) return rb_fail(ctx, RB_ERR_INVALID, "rt: profile outputs null");
+  if (profile_ray >= R) return rb_fail(ctx, RB_ERR_INVALID, "rt: profile_ray out of range");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  RtLaunch L{};
+  RB_TRY(make_geometry(ctx, g, R, &L));
+  const size_t nL = L.L, S = nL - 1, F = rt->n_freqs;
+  const size_t esz = rt->out_f32 ? 4 : 8;
+  void *p_rad, *p_b, *p_ds, *p_n, *p_alpha, *p_T, *p_tb, *p_iw = nullptr, *p_prof = nullptr;
+  RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, nL * 8, &p_rad));
+  RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 4, &p_n));
+  RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, nL * F * 8, &p_alpha));
+  RB_TRY(rb_ensure(ctx, RB_BUF_T, nL * 8, &p_T));
+  RB_TRY(rb_ensure(ctx, RB_BUF_TB, (size_t)R * F * esz, &p_tb));
+  if (out_intW) RB_TRY(rb_ensure(ctx, RB_BUF_INTW, (size_t)R * F * 8, &p_iw));
+  cudaStream_t s = ctx->stream;
+  RB_CUDA(ctx, cudaMemcpyAsync(p_rad, g->radius, nL * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_alpha, rt->alpha, nL * F * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_T, rt->T, nL * 8, cudaMemcpyHostToDevice, s));
+  L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n;
+  rb_rt_desc rd = *rt;
+  rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
+  RB_TRY(rb_launch_geometry(ctx, L));
+  RB_TRY(rb_launch_integrate(ctx, L, &rd, p_tb, (double*)p_iw, -1, nullptr, nullptr, nullptr));
+  RB_CUDA(ctx, cudaMemcpyAsync(out_Tb, p_tb, (size_t)R * F * esz, cudaMemcpyDeviceToHost, s));
+  if (out_intW) RB_CUDA(ctx, cudaMemcpyAsync(out_intW, p_iw, (size_t)R * F * 8, cudaMemcpyDeviceToHost, s));
+  if (profile_ray >= 0) {
+    // re-run the selected ray alone with the profile-writing variant (Brightness.tau/.W/.Tb_lyr)
+    RB_TRY(rb_ensure(ctx, RB_BUF_PROFILE, 3 * F * S * 8 + F * 8, &p_prof));
+    RB_CUDA(ctx, cudaMemsetAsync(p_prof, 0, 3 * F * S * 8 + F * 8, s));
+    RtLaunch L1 = L;
+    L1.R = 1; L1.Rpad = L.Rpad;
+    L1.ds = L.ds + profile_ray; L1.nseg = L.nseg + profile_ray; L1.b = L.b + 2 * profile_ray;
+    double* pp = (double*)p_prof;
+    rd.out_f32 = 0;
+    RB_TRY(rb_launch_integrate(ctx, L1, &rd, pp + 3 * F * S, nullptr, 0, pp, pp + F * S, pp + 2 * F * S));
+    RB_CUDA(ctx, cudaMemcpyAsync(out_tau, pp, F * S * 8, cudaMemcpyDeviceToHost, s));
+    RB_CUDA(ctx, cudaMemcpyAsync(out_W, pp + F * S, F * S * 8, cudaMemcpyDeviceToHost, s));
+    RB_CUDA(ctx, cudaMemcpyAsync(out_Tblyr, pp + 2 * F * S, F * S * 8, cudaMemcpyDeviceToHost, s));
+  }
+  RB_CUDA(ctx, cudaStreamSynchronize(s));
+  return RB_OK;
+}
+
+int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int64_t R, int32_t n_seg, const double* ds,
+                    const int32_t* nseg, void* out_Tb, double* out_intW) {
+  if (!ctx) return RB_ERR_INVALID;
+  RB_TRY(check_rt(ctx, rt, out_Tb));
+  if (!ds || !nseg || R <= 0) return rb_fail(ctx, RB_ERR_INVALID, "rt_integrate: null pointer / no rays");
+  if (n_layers < 2 || n_seg != n_layers - 1) return rb_fail(ctx, RB_ERR_INVALID, "rt_integrate: n_seg must be n_layers - 1");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  RtLaunch L{};
+  L.L = n_layers; L.R = R; L.Rpad = (R + 3) & ~(int64_t)3;
+  const size_t nL = n_layers, S = n_seg, F = rt->n_freqs;
+  const size_t esz = rt->out_f32 ? 4 : 8;
+  void *p_in, *p_ds, *p_n, *p_alpha, *p_T, *p_tb, *p_iw = nullptr;
+  RB_TRY(rb_ensure(ctx, RB_BUF_MISC, (size_t)R * S * 8, &p_in));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 4, &p_n));
+  RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, nL * F * 8, &p_alpha));
+  RB_TRY(rb_ensure(ctx, RB_BUF_T, nL * 8, &p_T));
+  RB_TRY(rb_ensure(ctx, RB_BUF_TB, (size_t)R * F * esz, &p_tb));
+  if (out_intW) RB_TRY(rb_ensure(ctx, RB_BUF_INTW, (size_t)R * F * 8, &p_iw));
+  cudaStream_t s = ctx->stream;
+  RB_CUDA(ctx, cudaMemcpyAsync(p_in, ds, (size_t)R * S * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_n, nseg, (size_t)R * 4, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_alpha, rt->alpha, nL * F * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_T, rt->T, nL * 8, cudaMemcpyHostToDevice, s));
+  RB_TRY(rb_launch_ds_to_slab(ctx, (const double*)p_in, R, L.Rpad, (int)S, (double*)p_ds));
+  L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n;
+  rb_rt_desc rd = *rt;
+  rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
+  RB_TRY(rb_launch_integrate(ctx, L, &rd, p_tb, (double*)p_iw, -1, nullptr, nullptr, nullptr));
+  RB_CUDA(ctx, cudaMemcpyAsync(out_Tb, p_tb, (size_t)R * F * esz, cudaMemcpyDeviceToHost, s));
+  if (out_intW) RB_CUDA(ctx, cudaMemcpyAsync(out_intW, p_iw, (size_t)R * F * 8, cudaMemcpyDeviceToHost, s));
+  RB_CUDA(ctx, cudaStreamSynchronize(s));
+  return RB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+// radiobear_b200 -- hot path B: ray geometry (raypath.compute_ds) and the fused
+// optical-depth / weighting-function / brightness-temperature integration (Brightness.single).
+//
+// Data layout in HBM
+//   ds slab   [S = L-1][Rpad]  float64, RAY index fastest: the geometry kernel (one thread per ray)
+//             writes it coalesced; the integration kernel reads 4 consecutive rays per thread with one
+//             32-byte load that the whole warp shares (lanes = frequencies).
+//   alpha slab [L][F] float64, FREQUENCY fastest (written by alpha_lines_kernel): a warp reads one
+//             256-byte row per segment, shared by all rays it carries; 0.5 MB at C4, lives in L2/L1.
+//   Tb        [R][F] float32 or float64, coalesced stores.
+//
+// Geometry is evaluated in an algebraic (trig-free) form of the reference recurrence:
+//   shell radius at parametric latitude lat: r*sqrt(q^2 sin^2 lat + cos^2 lat)    (shape.py:240-244)
+//   sin lat = y/|r| of the current position                                        (raypath.py:231)
+//   ds = -r.s - sqrt((r.s)^2 + rNext^2 - rNow^2)  (NaN below the tangent shell)    (raypath.py:193)
+//   Snell refraction at the first interface only, nratio = 1 afterwards            (raypath.py:158,257)
+// tests/test_ray_geometry.py checks it against the trigonometric oracle and the reference's vectors.
+#include "rb_common.cuh"
+#include <cmath>
+
+namespace {
+
+constexpr double kTcmb = 2.725;   // utils.py:77
+constexpr double kKmToCm = 1.0E5; // brightness.py:66
+
+struct GeoK {
+  int L;
+  const double* radius;
+  double n0, n1, q;
+  double cz, sz, cx, sx;  // rotate2planet = rotX(rotate) . rotZ(tip)   (raypath.py:47-51)
+  int limb;
+  long long R, Rpad;
+  const double* b;
+  double* ds;
+  int* nseg;
+};
+
+__device__ __forceinline__ void rot2planet(const GeoK& g, double x, double y, double z, double& ox, double& oy,
+                                           double& oz) {
+  const double x1 = g.cz * x - g.sz * y, y1 = g.sz * x + g.cz * y;
+  ox = x1;
+  oy = g.cx * y1 - g.sx * z;
+  oz = g.sx * y1 + g.cx * z;
+}
+
+// sin / cos of the (parametric) latitude used by Shape._calcEllipse for a position with y/|r| = v;
+// lat == 0 is replaced by 1e-6 rad (shape.py:231-233)
+__device__ __forceinline__ void lat_sc(double v, double& s, double& c) {
+  if (v == 0.0) {
+    s = 9.99999999999833333e-07;  // sin(1e-6)
+    c = 0.9999999999995;          // cos(1e-6)
+  } else {
+    s = v;
+    c = sqrt(fmax(0.0, 1.0 - v * v));
+    if (v != v) c = v;  // NaN propagates
+  }
+}
+
+// one thread per ray
+__global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant__ GeoK g) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= g.R) return;
+  const int S = g.L - 1;
+  const double bx = g.b[2 * r], by = g.b[2 * r + 1];
+  const double bb = bx * bx + by * by;
+  if (!(bb < 1.0)) {  // raypath.py:126-127 (NaN impact parameters also miss)
+    g.nseg[r] = -1;
+    return;
+  }
+  const double q2 = g.q * g.q;
+  const double rNorm = g.radius[0];
+  const double mu = sqrt(1.0 - bx * bx - by * by);
+
+  // ---- findEdge (raypath.py:60-105): march zQ down by 0.005 until inside the outer shell --------
+  const double z0 = sqrt(1.0 - bb) * 1.01;
+  const int ntrial = (int)ceil(z0 / 0.005);  // len(np.arange(z0, 0, -0.005))
+  double d_prev = 0.0, z_prev = 0.0, zq = 0.0;
+  bool hit = false;
+  for (int t = 0; t < ntrial; ++t) {
+    const double z = z0 + t * (-0.005);
+    double px, py, pz;
+    rot2planet(g, bx, by, z, px, py, pz);
+    const double nb = sqrt(px * px + py * py + pz * pz);
+    const double r1 = nb * rNorm;
+    double s, c;
+    lat_sc(py / nb, s, c);
+    const double r2 = rNorm * sqrt(q2 * s * s + c * c);
+    const double d = r1 - r2;
+    if (r1 < r2) {
+      hit = true;
+      // np.interp(0, [d, d_prev], [z, z_prev]); a first-trial hit returns z itself
+      zq = (t == 0) ? z : ((z_prev - z) / (d_prev - d)) * (0.0 - d) + z;
+      break;
+    }
+    d_prev = d;
+    z_prev = z;
+  }
+  if (!hit) {
+    g.nseg[r] = -1;
+    return;
+  }
+  // edge position, then the shell point / normal the reference starts from (raypath.py:141-156)
+  double ex, ey, ez;
+  rot2planet(g, bx, by, zq, ex, ey, ez);
+  ex *= rNorm; ey *= rNorm; ez *= rNorm;
+  double px, py, pz;  // current position r_i
+  double v, hs, sl, clng;
+  {
+    const double ne = sqrt(ex * ex + ey * ey + ez * ez);
+    v = ey / ne;
+    hs = sqrt(ex * ex + ez * ez);
+    sl = (hs > 0.0) ? ex / hs : 0.0;
+    clng = (hs > 0.0) ? ez / hs : 1.0;
+    double s, c;
+    lat_sc(v, s, c);
+    // geoid.r = rotY(lng, [0, b sin lat, a cos lat])
+    px = rNorm * c * sl;
+    py = g.q * rNorm * s;
+    pz = rNorm * c * clng;
+  }
+  double s_lat, c_lat;
+  lat_sc(v, s_lat, c_lat);
+  double shape = sqrt(q2 * s_lat * s_lat + c_lat * c_lat);  // rmag / req at the current latitude
+  // outward normal n = rotY(lng, [0, a sin, b cos]/norm)
+  double nx, ny, nz;
+  {
+    const double inv = 1.0 / sqrt(s_lat * s_lat + q2 * c_lat * c_lat);
+    nx = g.q * c_lat * sl * inv;
+    ny = s_lat * inv;
+    nz = g.q * c_lat * clng * inv;
+  }
+  // start direction (0,0,-1) rotated into the planet frame
+  double sx, sy, sz;
+  rot2planet(g, 0.0, 0.0, -1.0, sx, sy, sz);
+  // first interface: Snell with nratio = n0/n1 (raypath.py:157-159, 176-177)
+  {
+    const double nratio = g.n0 / g.n1;
+    const double ci = -(sx * nx + sy * ny + sz * nz);      // cos(t_inc)
+    const double st = nratio * sqrt(fmax(0.0, 1.0 - ci * ci));
+    double ct = sqrt(1.0 - st * st);                        // cos(asin(st)); NaN if st > 1
+    if (fabs(ci) > 1.0) ct = nan("");                       // arccos out of range
+    const double w = nratio * ci - ct;
+    sx = nratio * sx + w * nx;
+    sy = nratio * sy + w * ny;
+    sz = nratio * sz + w * nz;
+  }
+  int layer = 0;
+  int count = 0;
+  double* out = g.ds + r;
+  for (; layer < S; ++layer) {
+    const double rNow = g.radius[layer] * shape;
+    const double rNext = g.radius[layer + 1] * shape;
+    const double rdots = px * sx + py * sy + pz * sz;
+    double ds = -rdots - sqrt(rdots * rdots + rNext * rNext - rNow * rNow);
+    if (ds < 0.0) break;  // raypath.py:212-216
+    if (g.limb == RB_LIMB_SEC) ds = fabs(rNext - rNow) / mu;
+    out[(long long)layer * g.Rpad] = ds;
+    ++count;
+    // advance and re-evaluate latitude / normal at the new position (raypath.py:228-237)
+    px += ds * sx; py += ds * sy; pz += ds * sz;
+    const double nr = sqrt(px * px + py * py + pz * pz);
+    v = py / nr;
+    lat_sc(v, s_lat, c_lat);
+    shape = sqrt(q2 * s_lat * s_lat + c_lat * c_lat);
+    // incidence on the next shell with nratio = 1: s += (cos(t_inc) - |cos(t_inc)|) n   (raypath.py:176-177, 257)
+    hs = sqrt(px * px + pz * pz);
+    sl = (hs > 0.0) ? px / hs : 0.0;
+    clng = (hs > 0.0) ? pz / hs : 1.0;
+    const double inv = 1.0 / sqrt(s_lat * s_lat + q2 * c_lat * c_lat);
+    nx = g.q * c_lat * sl * inv;
+    ny = s_lat * inv;
+    nz = g.q * c_lat * clng * inv;
+    const double ci = -(sx * nx + sy * ny + sz * nz);
+    if (!(ci >= 0.0)) {  // ci < 0 (or NaN): the reference's asin/acos pair flips the normal component
+      const double w = (fabs(ci) > 1.0) ? nan("") : 2.0 * ci;
+      sx += w * nx; sy += w * ny; sz += w * nz;
+    }
+  }
+  g.nseg[r] = count;
+}
+
+// [S][Rpad] slab -> [R][S] ray-major (only for the compute_ds API that returns Ray.ds)
+__global__ void ds_transpose_kernel(const double* __restrict__ slab, long long R, long long Rpad, int S,
+                                    const int* __restrict__ nseg, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int s0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int s = s0 + j;
+    const long long r = r0 + threadIdx.x;
+    tile[j][threadIdx.x] = (s < S && r < R) ? slab[(long long)s * Rpad + r] : 0.0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long r = r0 + j;
+    const int s = s0 + threadIdx.x;
+    if (r < R && s < S) {
+      const int n = nseg[r];
+      out[r * S + s] = (s < n) ? tile[threadIdx.x][j] : 0.0;
+    }
+  }
+}
+
+__global__ void ds_to_slab_kernel(const double* __restrict__ in, long long R, long long Rpad, int S,
+                                  double* __restrict__ slab) {
+  __shared__ double tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int s0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long r = r0 + j;
+    const int s = s0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < R && s < S) ? in[r * S + s] : 0.0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int s = s0 + j;
+    const long long r = r0 + threadIdx.x;
+    if (s < S && r < Rpad) slab[(long long)s * Rpad + r] = tile[threadIdx.x][j];
+  }
+}
+
+// ---- E2(x): exponential integral of order 2 (scipy.special.expn(2, x), brightness.py:96) ----------
+// Same algorithm as the Cephes expn routine scipy wraps: power series for x <= 1, continued fraction
+// for x > 1.
+__device__ double expn2(double x) {
+  const double EUL = 0.57721566490153286060, MACHEP = 1.11022302462515654042E-16, BIG = 1.44115188075855872E+17;
+  if (x != x) return x;
+  if (x < 0.0) return nan("");
+  if (x > 7.09782712893383996843E2) return 0.0;
+  if (x == 0.0) return 1.0;  // 1/(n-1)
+  if (x > 1.0) {
+    int kk = 1;
+    double pkm2 = 1.0, qkm2 = x, pkm1 = 1.0, qkm1 = x + 2.0, ans = pkm1 / qkm1, t;
+    do {
+      kk += 1;
+      double yk, xk;
+      if (kk & 1) { yk = 1.0; xk = 2.0 + (kk - 1) / 2; }
+      else { yk = x; xk = kk / 2; }
+      const double pk = pkm1 * yk + pkm2 * xk;
+      const double qk = qkm1 * yk + qkm2 * xk;
+      if (qk != 0) { const double r = pk / qk; t = fabs((ans - r) / r); ans = r; }
+      else t = 1.0;
+      pkm2 = pkm1; pkm1 = pk; qkm2 = qkm1; qkm1 = qk;
+      if (fabs(pk) > BIG) { pkm2 /= BIG; pkm1 /= BIG; qkm2 /= BIG; qkm1 /= BIG; }
+    } while (t > MACHEP);
+    return ans * exp(-x);
+  }
+  // power series
+  double psi = -EUL - log(x) + 1.0;  // + sum_{i=1}^{n-1} 1/i with n = 2
+  const double z = -x;
+  double xk = 0.0, yk = 1.0, pk = 1.0 - 2.0, ans = 1.0 / pk, t;
+  do {
+    xk += 1.0;
+    yk *= z / xk;
+    pk += 1.0;
+    if (pk != 0.0) ans += yk / pk;
+    t = (ans != 0.0) ? fabs(yk / ans) : 1.0;
+  } while (t > MACHEP);
+  return z * psi - ans;  // pow(z, n-1) * psi / Gamma(n) - ans
+}
+
+struct RtK {
+  int L, F;
+  long long R, Rpad;
+  const double* alpha;  // [L][F]
+  const double* T;      // [L]
+  const double* ds;     // [S][Rpad]
+  const int* nseg;      // [R]
+  void* out_Tb;         // [R][F]
+  double* out_intW;     // [R][F] or null
+  int out_f32;
+  int disc;
+  double tau_cut;
+  // profile outputs for one ray (RPT = 1 launches only)
+  long long profile_ray;
+  double *out_tau, *out_W, *out_Tblyr;  // [F][S]
+};
+
+// thread = (frequency lane, RPT consecutive rays); blockDim = (32, WY); grid = (ray groups, freq groups)
+template <int RPT, bool DISC, bool PROFILE>
+__global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant__ RtK k) {
+  const int fi = blockIdx.y * 32 + threadIdx.x;
+  const long long rg = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  const long long r0 = rg * RPT;
+  if (r0 >= k.R) return;
+  const bool fvalid = fi < k.F;
+  const int f = fvalid ? fi : k.F - 1;
+  const int S = k.L - 1;
+
+  int n[RPT];
+  int nmax = 0;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    n[j] = (r0 + j < k.R) ? k.nseg[r0 + j] : -1;
+    nmax = max(nmax, n[j]);
+  }
+  double tau[RPT], Wp[RPT], iW[RPT], Tb[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) tau[j] = Wp[j] = iW[j] = Tb[j] = 0.0;
+
+  if (PROFILE && fvalid && nmax > 0) {
+    k.out_tau[(size_t)f * S] = 0.0; k.out_W[(size_t)f * S] = 0.0; k.out_Tblyr[(size_t)f * S] = 0.0;
+  }
+  double a0 = k.alpha[f];
+  double T0 = k.T[0];
+  // brightness.py:65: for i in range(len(ds) - 1)
+  for (int i = 0; i + 1 < nmax; ++i) {
+    const double a1 = k.alpha[(size_t)(i + 1) * k.F + f];
+    const double T1 = k.T[i + 1];
+    double dsv[RPT];
+    if constexpr (RPT == 4) {
+      const double4 d4 = *reinterpret_cast<const double4*>(k.ds + (size_t)i * k.Rpad + r0);
+      dsv[0] = d4.x; dsv[1] = d4.y; dsv[2] = d4.z; dsv[3] = d4.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) dsv[j] = k.ds[(size_t)i * k.Rpad + r0 + j];
+    }
+    const double asum = a0 + a1;
+    bool live = false;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      if (i + 1 < n[j] && !(tau[j] > k.tau_cut)) {
+        const double h = dsv[j] * kKmToCm * 0.5;        // ds/2 in cm
+        tau[j] = tau[j] + asum * h;                      // dtau = (a0 + a1) * ds / 2
+        const double W = DISC ? 2.0 * a1 * expn2(tau[j]) : a1 * exp(-tau[j]);
+        iW[j] += (W + Wp[j]) * h;
+        Tb[j] += (T1 * W + T0 * Wp[j]) * h;
+        Wp[j] = W;
+        live = true;
+      }
+      if (PROFILE && fvalid && i + 1 < n[j]) {
+        k.out_tau[(size_t)f * S + i + 1] = tau[j];
+        k.out_W[(size_t)f * S + i + 1] = Wp[j];
+        k.out_Tblyr[(size_t)f * S + i + 1] = Tb[j];
+      }
+    }
+    if (!PROFILE && !live) break;
+    a0 = a1;
+    T0 = T1;
+  }
+  if (!fvalid) return;
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const long long r = r0 + j;
+    if (r >= k.R) continue;
+    double v;
+    if (n[j] < 0) v = kTcmb;                               // off planet (brightness.py:46-51)
+    else v = (Tb[j] < kTcmb) ? kTcmb : Tb[j] / iW[j];      // brightness.py:109-113
+    const size_t o = (size_t)r * k.F + f;
+    if (k.out_f32) reinterpret_cast<float*>(k.out_Tb)[o] = (float)v;
+    else reinterpret_cast<double*>(k.out_Tb)[o] = v;
+    if (k.out_intW) k.out_intW[o] = (n[j] < 0) ? 0.0 : iW[j];
+  }
+}
+
+}  // namespace
+
+int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
+  GeoK k{};
+  k.L = g.L; k.radius = g.radius; k.n0 = g.n0; k.n1 = g.n1; k.q = g.q;
+  k.cz = g.rot[0]; k.sz = g.rot[1]; k.cx = g.rot[2]; k.sx = g.rot[3];
+  k.limb = g.limb; k.R = g.R; k.Rpad = g.Rpad; k.b = g.b; k.ds = g.ds; k.nseg = g.nseg;
+  const int threads = 128;
+  const long long blocks = (g.R + threads - 1) / threads;
+  if (ctx->timing) RB_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], ctx->stream));
+  ray_geometry_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(k);
+  RB_CUDA(ctx, cudaGetLastError());
+  if (ctx->timing) { RB_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], ctx->stream)); ctx->ev_valid[1] = true; }
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out) {
+  const int S = g.L - 1;
+  dim3 grid((unsigned)((g.R + 31) / 32), (S + 31) / 32), block(32, 8);
+  ds_transpose_kernel<<<grid, block, 0, ctx->stream>>>(g.ds, g.R, g.Rpad, S, g.nseg, out);
+  RB_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+int rb_launch_ds_to_slab(rb_context* ctx, const double* in, int64_t R, int64_t Rpad, int S, double* slab) {
+  dim3 grid((unsigned)((Rpad + 31) / 32), (S + 31) / 32), block(32, 8);
+  ds_to_slab_kernel<<<grid, block, 0, ctx->stream>>>(in, R, Rpad, S, slab);
+  RB_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt, void* out_Tb, double* out_intW,
+                        int64_t profile_ray, double* out_tau, double* out_W, double* out_Tblyr) {
+  RtK k{};
+  k.L = g.L; k.F = rt->n_freqs; k.R = g.R; k.Rpad = g.Rpad;
+  k.alpha = rt->alpha; k.T = rt->T; k.ds = g.ds; k.nseg = g.nseg;
+  k.out_Tb = out_Tb; k.out_intW = out_intW; k.out_f32 = rt->out_f32; k.disc = rt->disc_average;
+  k.tau_cut = (rt->tau_cut > 0.0) ? rt->tau_cut : INFINITY;
+  k.profile_ray = profile_ray; k.out_tau = out_tau; k.out_W = out_W; k.out_Tblyr = out_Tblyr;
+  const int fgroups = (k.F + 31) / 32;
+  if (ctx->timing) RB_CUDA(ctx, cudaEventRecord(ctx->ev[2][0], ctx->stream));
+  if (profile_ray >= 0) {
+    if (g.R != 1) return rb_fail(ctx, RB_ERR_INVALID, "rt: profile outputs need a single-ray launch");
+    dim3 grid(1, fgroups), block(32, 1);
+    if (k.disc) rt_integrate_kernel<1, true, true><<<grid, block, 0, ctx->stream>>>(k);
+    else rt_integrate_kernel<1, false, true><<<grid, block, 0, ctx->stream>>>(k);
+  } else if (k.disc || g.R < 4096) {
+    const int wy = 4;
+    dim3 grid((unsigned)((g.R + wy - 1) / wy), fgroups), block(32, wy);
+    if (k.disc) rt_integrate_kernel<1, true, false><<<grid, block, 0, ctx->stream>>>(k);
+    else rt_integrate_kernel<1, false, false><<<grid, block, 0, ctx->stream>>>(k);
+  } else {
+    const int wy = 4;
+    const long long groups = (g.R + 3) / 4;
+    dim3 grid((unsigned)((groups + wy - 1) / wy), fgroups), block(32, wy);
+    rt_integrate_kernel<4, false, false><<<grid, block, 0, ctx->stream>>>(k);
+  }
+  RB_CUDA(ctx, cudaGetLastError());
+  if (ctx->timing) { RB_CUDA(ctx, cudaEventRecord(ctx->ev[2][1], ctx->stream)); ctx->ev_valid[2] = true; }
+  ctx->launches += 1;
+  return RB_OK;
+}

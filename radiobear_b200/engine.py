@@ -1,0 +1,255 @@
+"""Host-side driver of the sm_100a kernels: builds the C-ABI descriptors and calls the library.
+
+This is the only module that talks to libradiobear_b200.so; the reference-shaped classes
+(alpha.Alpha, brightness.Brightness, raypath.compute_ds, constituents/<gas>/<formalism>.alpha)
+are thin layers over the three functions here.  numpy in / numpy out; `*_dev` variants take and
+return torch CUDA tensors for device-resident pipelines (Planet.run, bench.py).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import catalogs
+from ._lib import (AlphaDesc, GeometryDesc, RtDesc, FORMALISM_IDS, GAS_ORDER, CLOUD_ORDER, CLOUD_FLAG_KEYS,
+                   RB_MAX_CONSTITUENTS, f64, ptr)
+
+T_CMB = 2.725
+UNITS = {'invcm': 0, 'dBperkm': 1}
+COSHAPE = {'voigt': 0, 'vvw': 1, 'diff': 2}
+
+
+def _cloud_flags(other):
+    flags = 0
+    for bit, key in enumerate(CLOUD_FLAG_KEYS):
+        v = other.get(key, 0.0) if other else 0.0
+        try:
+            if v is not None and float(v) > 0.0:
+                flags |= (1 << bit)
+        except (TypeError, ValueError):
+            pass
+    return flags
+
+
+def build_alpha_desc(formalisms, L, F, gas_rows, gas_dict, cloud_rows, cloud_dict, other_dicts, units):
+    """formalisms: list of (constituent, formalism-name) in call order (sorted constituents)."""
+    if len(formalisms) == 0 or len(formalisms) > RB_MAX_CONSTITUENTS:
+        raise ValueError('need 1..{} constituents'.format(RB_MAX_CONSTITUENTS))
+    d = AlphaDesc()
+    d.n_layers, d.n_freqs, d.n_constituents = L, F, len(formalisms)
+    other_dicts = other_dicts or {}
+    h2state, coshape, cflags = 0, 0, 0
+    for i, (c, name) in enumerate(formalisms):
+        if name not in FORMALISM_IDS:
+            raise NotImplementedError('formalism {} is not built in radiobear_b200'.format(name))
+        d.formalism[i] = FORMALISM_IDS[name]
+        od = other_dicts.get(c, {}) or {}
+        if name in ('h2_jj_ddb',):
+            st = od.get('h2state', 'e')
+            if st not in ('e', 'n'):
+                raise ValueError('INVALID H2STATE {!r}'.format(st))      # h2_jj_ddb.py:28-30 prints and returns 0
+            h2state = 0 if st == 'e' else 1
+        if name == 'co_ddb':
+            coshape = COSHAPE.get(od.get('coshape', 'voigt'), 3)
+        if name == 'clouds_idp':
+            cflags = _cloud_flags(od)
+    d.h2state, d.coshape, d.cloud_flags = h2state, coshape, cflags
+    d.gas_rows = gas_rows
+    for i, g in enumerate(GAS_ORDER):
+        d.gas_col[i] = int(gas_dict[g]) if (gas_dict and g in gas_dict) else -1
+    d.cloud_rows = cloud_rows
+    for i, g in enumerate(CLOUD_ORDER):
+        d.cloud_col[i] = int(cloud_dict[g]) if (cloud_dict and g in cloud_dict) else -1
+    if units not in UNITS:
+        raise ValueError("units must be 'invcm' or 'dBperkm'")
+    d.units = UNITS[units]
+    return d
+
+
+def scale_matrix(scale, ordered, L):
+    """alpha.py:235-259 + 151-192: turn the user's scale (number / per-layer list / dict by constituent)
+    into a [C][L] matrix, or None for 'no scaling'."""
+    C_ = len(ordered)
+    if isinstance(scale, dict):
+        for k, v in scale.items():
+            if k not in ordered:
+                raise ValueError("{} not found as constituent for alpha".format(k))
+            if len(v) != L:
+                raise ValueError("Incorrect scale for {}:  N {} vs {}".format(k, len(v), L))
+        m = np.ones((C_, L))
+        for k, v in scale.items():
+            m[ordered.index(k)] = np.asarray(v, dtype=np.float64)
+        return m
+    if isinstance(scale, (list, np.ndarray)):
+        if len(scale) != L:
+            raise ValueError("Incorrect number of scale layers.")
+        return np.tile(np.asarray(scale, dtype=np.float64), (C_, 1))
+    if isinstance(scale, bool) or scale is None:
+        return None
+    try:
+        s = float(scale)
+    except (TypeError, ValueError):
+        return None
+    return None if s == 1.0 else np.full((C_, L), s)
+
+
+def prepare_catalogs(ctx, formalisms, truncate_strength=None, truncate_freq=None):
+    truncate_strength = truncate_strength or {}
+    truncate_freq = truncate_freq or {}
+    for c, name in formalisms:
+        catalogs.upload(ctx, name, truncate_strength.get(c), truncate_freq.get(c))
+
+
+def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formalisms=(), other_dicts=None,
+                 units='invcm', scale=None, want_cube=False, truncate_strength=None, truncate_freq=None, ctx=None):
+    """Total absorption for every (layer, freq) -> slab[L][F] (+ cube[L][F][C]).  Host arrays.
+
+    Replaces the layer loop of Alpha.get_layers (alpha.py:298-300) and the plugin calls under it.
+    """
+    ctx = ctx or _lib.get_context()
+    freqs, T, P = f64(np.atleast_1d(freqs)), f64(np.atleast_1d(T)), f64(np.atleast_1d(P))
+    gas = f64(gas)
+    if gas.ndim == 1:
+        gas = np.ascontiguousarray(gas[:, None])
+    L, F = T.shape[0], freqs.shape[0]
+    if gas.shape[1] != L or P.shape[0] != L:
+        raise ValueError('T, P and gas disagree on the number of layers')
+    if cloud is not None:
+        cloud = f64(cloud)
+        if cloud.ndim == 1:
+            cloud = np.ascontiguousarray(cloud[:, None])
+    formalisms = list(formalisms)
+    prepare_catalogs(ctx, formalisms, truncate_strength, truncate_freq)
+    d = build_alpha_desc(formalisms, L, F, gas.shape[0], gas_dict, 0 if cloud is None else cloud.shape[0], cloud_dict,
+                         other_dicts, units)
+    sm = scale_matrix(scale, [c for c, _ in formalisms], L)
+    sm = None if sm is None else f64(sm)
+    d.freqs, d.T, d.P, d.gas = ptr(freqs), ptr(T), ptr(P), ptr(gas)
+    d.cloud = ptr(cloud)
+    d.scale = ptr(sm)
+    total = np.empty((L, F))
+    cube = np.empty((L, F, len(formalisms))) if want_cube else None
+    ctx.check(ctx.lib.rb_alpha_layers(ctx.h, C.byref(d), ptr(total), ptr(cube)))
+    return (total, cube) if want_cube else total
+
+
+def alpha_layers_dev(freqs_t, T_t, P_t, gas_t, gas_dict, cloud_t=None, cloud_dict=None, formalisms=(), other_dicts=None,
+                     units='invcm', scale_t=None, want_cube=False, truncate_strength=None, truncate_freq=None, ctx=None,
+                     out=None):
+    """Device-resident variant: torch float64 CUDA tensors in, slab[L][F] CUDA tensor out (async)."""
+    import torch
+    ctx = ctx or _lib.get_context()
+    L, F = T_t.shape[0], freqs_t.shape[0]
+    formalisms = list(formalisms)
+    prepare_catalogs(ctx, formalisms, truncate_strength, truncate_freq)
+    d = build_alpha_desc(formalisms, L, F, gas_t.shape[0], gas_dict, 0 if cloud_t is None else cloud_t.shape[0],
+                         cloud_dict, other_dicts, units)
+    for t in (freqs_t, T_t, P_t, gas_t):
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+    d.freqs, d.T, d.P, d.gas = freqs_t.data_ptr(), T_t.data_ptr(), P_t.data_ptr(), gas_t.data_ptr()
+    d.cloud = cloud_t.data_ptr() if cloud_t is not None else None
+    d.scale = scale_t.data_ptr() if scale_t is not None else None
+    total = out if out is not None else torch.empty((L, F), dtype=torch.float64, device=T_t.device)
+    cube = torch.empty((L, F, len(formalisms)), dtype=torch.float64, device=T_t.device) if want_cube else None
+    ctx.set_stream(torch.cuda.current_stream(T_t.device).cuda_stream)
+    ctx.check(ctx.lib.rb_alpha_layers_dev(ctx.h, C.byref(d), total.data_ptr(), cube.data_ptr() if want_cube else None))
+    return (total, cube) if want_cube else total
+
+
+GTYPE = {'ellipse': 0, 'circle': 1, 'sphere': 1}
+LIMB = {'shape': 0, 'sec': 1}
+
+
+def build_geometry_desc(L, n0, n1, Req, Rpol, orientation, gtype, limb):
+    if gtype not in GTYPE:
+        raise NotImplementedError("gtype '{}' is not built (ellipse / circle / sphere only)".format(gtype))
+    g = GeometryDesc()
+    g.n_layers = L
+    g.n0, g.n1 = float(n0), float(n1)
+    g.Req, g.Rpol = float(Req), float(Rpol)
+    g.orientation[0], g.orientation[1] = float(orientation[0]), float(orientation[1])
+    g.gtype = GTYPE[gtype]
+    g.limb = LIMB.get(limb, 0)
+    return g
+
+
+def compute_ds(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None):
+    """raypath.compute_ds for a batch of impact points.  Returns ds[R][L-1], nseg[R], (tip, rotate, rNorm)."""
+    ctx = ctx or _lib.get_context()
+    radius = f64(radius)
+    b = f64(np.atleast_2d(b))
+    R, L = b.shape[0], radius.shape[0]
+    g = build_geometry_desc(L, refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb)
+    g.radius = ptr(radius)
+    ds = np.empty((R, L - 1))
+    nseg = np.empty(R, dtype=np.int32)
+    aspect = np.empty(3)
+    ctx.check(ctx.lib.rb_compute_ds(ctx.h, C.byref(g), R, ptr(b), ptr(ds), ptr(nseg), ptr(aspect)))
+    return ds, nseg, aspect
+
+
+def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape',
+             disc_average=False, out_f32=False, tau_cut=100.0, want_intW=False, profile_ray=-1, ctx=None, out=None):
+    """Brightness.single over a batch of rays: Tb[R][F] (+ integrated_W, + profiles of one ray)."""
+    ctx = ctx or _lib.get_context()
+    radius, T = f64(radius), f64(T)
+    alpha_slab = f64(alpha_slab)
+    b = f64(np.atleast_2d(b))
+    R, L, F = b.shape[0], radius.shape[0], alpha_slab.shape[1]
+    if alpha_slab.shape[0] != L or T.shape[0] != L:
+        raise ValueError('alpha slab must be [L][F] with L = number of layers')
+    g = build_geometry_desc(L, refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb)
+    g.radius = ptr(radius)
+    rt = RtDesc()
+    rt.n_freqs, rt.alpha, rt.T = F, ptr(alpha_slab), ptr(T)
+    rt.disc_average, rt.out_f32, rt.tau_cut = int(bool(disc_average)), int(bool(out_f32)), float(tau_cut or 0.0)
+    if out is None:
+        out = np.empty((R, F), dtype=np.float32 if out_f32 else np.float64)
+    intW = np.empty((R, F)) if want_intW else None
+    prof = None
+    if profile_ray >= 0:
+        prof = [np.zeros((F, L - 1)) for _ in range(3)]
+    ctx.check(ctx.lib.rb_rt_batch(ctx.h, C.byref(g), C.byref(rt), R, ptr(b), ptr(out), ptr(intW), int(profile_ray),
+                                  ptr(prof[0]) if prof else None, ptr(prof[1]) if prof else None,
+                                  ptr(prof[2]) if prof else None))
+    res = {'Tb': out}
+    if want_intW:
+        res['integrated_W'] = intW
+    if prof:
+        res['tau'], res['W'], res['Tb_lyr'] = prof
+    return res
+
+
+def rt_batch_dev(radius_t, n0, n1, b_t, alpha_t, T_t, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape',
+                 disc_average=False, out_f32=True, tau_cut=100.0, ctx=None, out=None):
+    """Device-resident variant (torch CUDA tensors, async on the current stream)."""
+    import torch
+    ctx = ctx or _lib.get_context()
+    R, L, F = b_t.shape[0], radius_t.shape[0], alpha_t.shape[1]
+    g = build_geometry_desc(L, n0, n1, Req, Rpol, orientation, gtype, limb)
+    g.radius = radius_t.data_ptr()
+    rt = RtDesc()
+    rt.n_freqs, rt.alpha, rt.T = F, alpha_t.data_ptr(), T_t.data_ptr()
+    rt.disc_average, rt.out_f32, rt.tau_cut = int(bool(disc_average)), int(bool(out_f32)), float(tau_cut or 0.0)
+    if out is None:
+        out = torch.empty((R, F), dtype=torch.float32 if out_f32 else torch.float64, device=b_t.device)
+    ctx.set_stream(torch.cuda.current_stream(b_t.device).cuda_stream)
+    ctx.check(ctx.lib.rb_rt_batch_dev(ctx.h, C.byref(g), C.byref(rt), R, b_t.data_ptr(), out.data_ptr(), None))
+    return out
+
+
+def rt_integrate(ds, nseg, alpha_slab, T, disc_average=False, out_f32=False, tau_cut=100.0, want_intW=False, ctx=None):
+    """Integration only, for caller-supplied segments ds[R][L-1] (km)."""
+    ctx = ctx or _lib.get_context()
+    ds = f64(np.atleast_2d(ds))
+    alpha_slab, T = f64(alpha_slab), f64(T)
+    R, S = ds.shape
+    L, F = alpha_slab.shape
+    nseg = np.ascontiguousarray(nseg, dtype=np.int32)
+    rt = RtDesc()
+    rt.n_freqs, rt.alpha, rt.T = F, ptr(alpha_slab), ptr(T)
+    rt.disc_average, rt.out_f32, rt.tau_cut = int(bool(disc_average)), int(bool(out_f32)), float(tau_cut or 0.0)
+    out = np.empty((R, F), dtype=np.float32 if out_f32 else np.float64)
+    intW = np.empty((R, F)) if want_intW else None
+    ctx.check(ctx.lib.rb_rt_integrate(ctx.h, C.byref(rt), L, R, S, ptr(ds), ptr(nseg), ptr(out), ptr(intW)))
+    return (out, intW) if want_intW else out

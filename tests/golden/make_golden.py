@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference; the GPU box does not have it).
+The reference (david-deboer/radiobear v2.0.1, pure Python) is imported read-only with a
+matplotlib stub ahead on sys.path (atm_modify.py:8 imports pyplot at module level) from a
+scratch work directory bootstrapped the way scripts/initial_planet_setup.py:12-30 does.
+
+    python tests/golden/make_golden.py [section ...]
+
+sections: atm plugins plugins_notrunc alpha rays tb neptune image   (default: all)
+
+Every array is float64 exactly as the reference produced it; nothing is post-processed.
+Reference defects driven around: log-sweep strings and float image
+requests crash in set_utils, so frequencies are passed as lists and image pixels are run
+through Brightness.single one by one.
+"""
+import os
+import sys
+import shutil
+import subprocess
+import tempfile
+import time
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get('RADIOBEAR_REFERENCE', '/root/reference')
+
+
+def bootstrap():
+    work = tempfile.mkdtemp(prefix='rbgolden_')
+    stub = os.path.join(work, 'stub', 'matplotlib')
+    os.makedirs(stub)
+    open(os.path.join(stub, '__init__.py'), 'w').close()
+    with open(os.path.join(stub, 'pyplot.py'), 'w') as fp:
+        fp.write("def __getattr__(name):\n    raise AttributeError('matplotlib stub: ' + name)\n")
+    for planet in ['Jupiter', 'Saturn', 'Uranus', 'Neptune']:
+        os.mkdir(os.path.join(work, planet))
+        src = os.path.join(REF, 'radiobear', planet)
+        for pf in os.listdir(src):
+            if pf[0] in ['.', '_']:
+                continue
+            shutil.copy(os.path.join(src, pf), os.path.join(work, planet, pf))
+    for other in ['Logs', 'Output', 'Scratch']:
+        os.mkdir(os.path.join(work, other))
+    os.chdir(work)
+    sys.path.insert(0, os.path.join(work, 'stub'))
+    sys.path.insert(0, REF)
+    return work
+
+
+def save(name, **arrays):
+    fn = os.path.join(HERE, name)
+    np.savez_compressed(fn, **arrays)
+    print('  wrote {} ({:.1f} kB)'.format(name, os.path.getsize(fn) / 1e3))
+
+
+def planet(name, **kw):
+    import radiobear as rb
+    return rb.planet.Planet(name, plot_atm=False, plot_bright=False, verbose=False, **kw)
+
+
+def cfg_arrays(p):
+    c = p.config
+    a = p.atmos[0]
+    keysC = sorted(a.config.C, key=lambda k: a.config.C[k])
+    keysCl = sorted(a.config.Cl, key=lambda k: a.config.Cl[k])
+    keysLP = sorted(a.config.LP, key=lambda k: a.config.LP[k])
+    ca = {k: ('none' if v is None else v) for k, v in c.constituent_alpha.items()}
+    return dict(gas=a.gas, cloud=a.cloud, property=a.property,
+                C_keys=np.array(keysC), Cl_keys=np.array(keysCl), LP_keys=np.array(keysLP),
+                Req=c.Req, Rpol=c.Rpol, orientation=np.array(c.orientation[:2], dtype=float),
+                gtype=c.gtype, limb=c.limb, h2state=c.h2state, coshape=c.coshape,
+                alpha_constituents=np.array(sorted(ca.keys())),
+                alpha_formalisms=np.array([ca[k] for k in sorted(ca.keys())]),
+                truncate_strength_h2s=np.nan if c.truncate_strength['h2s'] is None else c.truncate_strength['h2s'],
+                truncate_strength_ph3=np.nan if c.truncate_strength['ph3'] is None else c.truncate_strength['ph3'],
+                cloud_p=np.array([c.water_p, c.ice_p, c.nh4sh_p, c.nh3ice_p, c.h2sice_p, c.ch4_p]),
+                distance=c.distance, GM_ref=c.GM_ref, p_ref=c.p_ref)
+
+
+# ---------------------------------------------------------------------------- sections
+def sec_atm():
+    """Regridded atmospheres (gas[16,L], cloud[12,L], property[11,L]) + config scalars."""
+    save('atm_jupiter.npz', **cfg_arrays(planet('jupiter')))
+    save('atm_jupiter_benchmark.npz', **cfg_arrays(planet('jupiter', config_file='config_benchmark.par')))
+    save('atm_neptune.npz', **cfg_arrays(planet('neptune')))
+    save('atm_saturn.npz', **cfg_arrays(planet('saturn')))
+
+
+PLUGIN_FREQS = [0.6, 1.0, 5.2, 10.0, 21.9, 23.7, 25.99, 26.0, 26.5, 29.0, 30.0, 30.000001, 31.5, 33.9,
+                34.0, 35.0, 50.0, 100.0, 183.31, 250.0, 500.0, 1000.0]
+
+
+def _points():
+    """(T, P, mixing ratios) test points: the hand-picked sets of the reference's ta.py scripts
+    (h2s/ta.py:12-20, ph3/ta.py:5-14, nh3/ta.py:23-36 style) plus Jupiter layers spanning the
+    0.01 bar .. 10 kbar grid (incl. the 400..2000 bar NH3 blend region)."""
+    j = planet('jupiter')
+    a = j.atmos[0]
+    C = a.config.C
+    pts = []
+    for lyr in [0, 50, 200, 333, 400, 500, 600, 700, 760, 767, 800, 850, 883, 884, 900, 950, 999]:
+        pts.append(a.gas[:, lyr].copy())
+    # hand-picked: deep/warm, cold/low-P, PH3/CO/H2S/H2O rich
+    base = a.gas[:, 500].copy()
+    for T, P, nh3, h2s, h2o, ph3, co, ch4 in [
+            (216.4, 1.009, 1.0e-4, 0.0095, 1.0e-6, 6.0e-7, 1.0e-6, 2.0e-3),
+            (150.0, 0.5, 2.0e-4, 3.0e-5, 1.0e-7, 8.2e-4, 1.0e-3, 1.8e-3),
+            (300.0, 8.0, 4.0e-4, 9.0e-5, 3.0e-3, 1.0e-6, 0.0, 2.0e-3),
+            (80.0, 0.02, 1.0e-9, 1.0e-12, 1.0e-15, 1.0e-7, 1.0e-6, 2.0e-2),
+            (52.0, 0.05, 1.0e-8, 1.0e-10, 1.0e-12, 1.0e-9, 1.0e-7, 2.0e-2),
+            (1200.0, 900.0, 3.0e-4, 8.0e-5, 2.5e-3, 5.0e-7, 1.0e-6, 2.0e-3),
+            (1800.0, 3000.0, 3.0e-4, 8.0e-5, 2.5e-3, 5.0e-7, 1.0e-6, 2.0e-3),
+            (500.0, 0.0005, 1.0e-6, 1.0e-6, 1.0e-6, 1.0e-6, 1.0e-4, 1.0e-3),
+            (120.0, 0.0999, 1.0e-6, 1.0e-6, 1.0e-6, 1.0e-6, 1.0e-4, 1.0e-3)]:
+        g = base.copy()
+        g[C['T']], g[C['P']] = T, P
+        g[C['NH3']], g[C['H2S']], g[C['H2O']], g[C['PH3']], g[C['CO']], g[C['CH4']] = nh3, h2s, h2o, ph3, co, ch4
+        g[C['H2']], g[C['HE']] = 0.862, 0.136
+        pts.append(g)
+    return np.array(pts), dict(C), dict(a.config.Cl), a
+
+
+def _plugin_table(truncate):
+    """Call every plugin exactly like Alpha.get_alpha_from_calc does (alpha.py:202-213)."""
+    import importlib
+    pts, C, Cl, atm = _points()
+    cpath = os.path.join(REF, 'radiobear', 'constituents')
+    mods = {}
+    for gas, names in {'nh3': ['nh3_hs', 'nh3_dbs', 'nh3_sjs', 'nh3_hs_sjs', 'nh3_dbs_sjs'],
+                       'h2s': ['h2s_ddb'], 'ph3': ['ph3_jh'], 'h2o': ['h2o_bk'], 'co': ['co_ddb'],
+                       'h2': ['h2_jj_ddb', 'h2_jj'], 'clouds': ['clouds_idp']}.items():
+        sys.path.append(os.path.join(cpath, gas))
+        for n in names:
+            mods[n] = (gas, importlib.import_module(n))
+    out = {'points': pts, 'freqs': np.array(PLUGIN_FREQS), 'C_keys': np.array(sorted(C, key=lambda k: C[k])),
+           'Cl_keys': np.array(sorted(Cl, key=lambda k: Cl[k]))}
+    tstr = {'h2s': 1e-22, 'ph3': 1e-22} if truncate else {}
+    # cloud columns for the clouds plugin: use Jupiter layers that carry clouds + a synthetic column
+    cl_pts = []
+    for lyr in [300, 350, 400, 450, 500]:
+        cl_pts.append(atm.cloud[:, lyr].copy())
+    syn = atm.cloud[:, 400].copy()
+    syn[3:11] = [1e-6, 2e-6, 3e-6, 4e-6, 5e-6, 6e-6, 0.0, 0.0]
+    cl_pts.append(syn)
+    cl_pts = np.array(cl_pts)
+    out['cloud_points'] = cl_pts
+    out['cloud_T'] = np.array([260.0, 280.0, 150.0, 272.9, 273.0, 300.0])
+    for name, (gas, mod) in mods.items():
+        for units in ['invcm', 'dBperkm']:
+            res = []
+            if gas == 'clouds':
+                od = {'water_p': 1e-4, 'ice_p': 1e-4, 'nh4sh_p': 1e-4, 'nh3ice_p': 1e-4, 'h2sice_p': 1e-4,
+                      'ch4_p': 1e-4}
+                for x, T in zip(cl_pts, out['cloud_T']):
+                    res.append(np.asarray(mod.alpha(PLUGIN_FREQS, T, 1.0, x, Cl, od, units=units,
+                                                    truncate_freq=None, truncate_strength=None,
+                                                    path=os.path.join(cpath, gas), verbose=False), dtype=float))
+            else:
+                od = {'h2state': 'e', 'h2newset': True, 'coshape': 'voigt'}
+                for g in pts:
+                    T, P = g[C['T']], g[C['P']]
+                    r = mod.alpha(PLUGIN_FREQS, T, P, g, C, od, units=units, truncate_freq=None,
+                                  truncate_strength=tstr.get(gas), path=os.path.join(cpath, gas), verbose=False)
+                    res.append(np.asarray(r, dtype=float))
+            out['{}__{}'.format(name, units)] = np.array(res)
+    # extra option variants
+    res_n, res_vvw = [], []
+    for g in pts:
+        T, P = g[C['T']], g[C['P']]
+        res_n.append(np.asarray(mods['h2_jj_ddb'][1].alpha(PLUGIN_FREQS, T, P, g, C, {'h2state': 'n'}, units='invcm',
+                                                            truncate_freq=None, truncate_strength=None,
+                                                            path='', verbose=False), dtype=float))
+        res_vvw.append(np.asarray(mods['co_ddb'][1].alpha(PLUGIN_FREQS, T, P, g, C, {'coshape': 'vvw'}, units='invcm',
+                                                          truncate_freq=None, truncate_strength=None,
+                                                          path=os.path.join(cpath, 'co'), verbose=False), dtype=float))
+    out['h2_jj_ddb_n__invcm'] = np.array(res_n)
+    out['co_ddb_vvw__invcm'] = np.array(res_vvw)
+    return out
+
+
+def sec_plugins():
+    save('plugins_trunc.npz', **_plugin_table(True))
+
+
+def sec_plugins_notrunc():
+    """No-truncation variant: the reference caches catalogs per process (h2s_ddb.py:11, ph3_jh.py:14),
+    so this runs in a fresh interpreter."""
+    if os.environ.get('RB_GOLDEN_CHILD') == '1':
+        save('plugins_notrunc.npz', **{k: v for k, v in _plugin_table(False).items()
+                                       if k.startswith(('h2s', 'ph3', 'points', 'freqs', 'C_keys'))})
+        return
+    env = dict(os.environ, RB_GOLDEN_CHILD='1')
+    subprocess.check_call([sys.executable, os.path.abspath(__file__), 'plugins_notrunc'], env=env)
+
+
+ALPHA_FREQS = [1.0, 5.2, 10.0, 22.0, 29.9, 30.1, 31.5, 100.0]
+
+
+def sec_alpha():
+    """Alpha.get_layers on the Jupiter default atmosphere: total [F,L] and the per-constituent cube
+    (save_alpha='memory', alpha.py:110-131)."""
+    j = planet('jupiter')
+    al = j.alpha[0]
+    al.get_layers(ALPHA_FREQS, j.atmos[0], save_alpha='memory')
+    total = np.array(al.layers)
+    cube = np.array(al.memory.alpha_data)
+    al.get_layers(ALPHA_FREQS, j.atmos[0], scale={'nh3': list(np.linspace(0.5, 1.5, 1000)), 'h2o': [2.0] * 1000})
+    scaled_dict = np.array(al.layers)
+    al.get_layers(ALPHA_FREQS, j.atmos[0], scale=list(np.linspace(2.0, 0.1, 1000)))
+    scaled_list = np.array(al.layers)
+    save('alpha_jupiter.npz', freqs=np.array(ALPHA_FREQS), layers=total, cube=cube,
+         ordered_constituents=np.array(al.ordered_constituents), layers_scaled_dict=scaled_dict,
+         layers_scaled_list=scaled_list)
+
+
+RAY_B = [[0.0, 0.0], [0.5, 0.3], [0.0, 0.9], [0.97, 0.0], [0.2588190451025207, 0.0], [-0.4, -0.6],
+         [0.0, 0.93], [0.98, 0.0], [0.985, 0.0], [0.99, 0.0], [0.0, 0.934], [0.0, 0.936],
+         [0.7, 0.7], [0.6, 0.75], [1.0, 0.2], [0.999, 0.0], [0.0, 1.0e-3], [0.3, -0.0]]
+
+
+def _rays(p, blist):
+    from radiobear import raypath
+    out = []
+    hit = []
+    for b in blist:
+        ray = raypath.compute_ds(p.atmos[0], b, p.config.orientation, gtype=None, verbose=False)
+        if ray.ds is None:
+            out.append(np.full(len(p.atmos[0].gas[0]) - 1, -1.0))
+            hit.append(0)
+        else:
+            assert list(ray.layer4ds) == list(range(len(ray.ds))), 'layer4ds not 0..S-1'
+            d = np.full(len(p.atmos[0].gas[0]) - 1, -2.0)
+            d[:len(ray.ds)] = ray.ds
+            out.append(d)
+            hit.append(len(ray.ds))
+    return np.array(out), np.array(hit)
+
+
+def sec_rays():
+    """raypath.compute_ds: ds[ray, S] (-1 rows: off planet; -2 padding: ray ended early)."""
+    j = planet('jupiter')
+    ds, nseg = _rays(j, RAY_B)
+    n = planet('neptune')       # tilted: orientation 347.67, -29.08
+    dsn, nsegn = _rays(n, RAY_B)
+    j2 = planet('jupiter', limb='sec')
+    dss, nsegs = _rays(j2, RAY_B[:6])
+    save('rays.npz', b=np.array(RAY_B), ds_jupiter=ds, nseg_jupiter=nseg, ds_neptune=dsn, nseg_neptune=nsegn,
+         ds_jupiter_sec=dss, nseg_jupiter_sec=nsegs)
+
+
+def sec_tb():
+    """End-to-end Tb: the reference's own known-answer case (scripts/benchmark.py:10-24), the Jupiter
+    default disc spectrum '1:100:5' (config C1), point rays and a limb profile (config C3 subset)."""
+    jb = planet('jupiter', config_file='config_benchmark.par')
+    freqs = [0.6, 1.25, 2.6, 5.2, 10, 21.9]
+    b = [[0.0, 0.0], [np.sin(np.radians(15)), 0.0], [np.sin(np.radians(30)), 0.0], [np.sin(np.radians(45)), 0.0]]
+    rv = jb.run(freqs, b=b, reuse_override='False')
+    tb_bench = np.array(rv.Tb, dtype=np.float64)
+    tb_bench64 = np.array(jb.Tb, dtype=np.float64)
+    j = planet('jupiter')
+    rv = j.run('1:100:5', b='disc')
+    c1_f = np.array(j.freqs, dtype=float)
+    c1_tb = np.array(j.Tb, dtype=np.float64)
+    c1_alpha = np.array(j.alpha[0].layers)
+    prof = dict(tau=j.bright.tau, W=j.bright.W, Tb_lyr=j.bright.Tb_lyr, integrated_W=j.bright.integrated_W)
+    fpt = [1.0, 10.0, 22.0, 30.0, 31.0, 100.0]
+    bpt = [[0.0, 0.0], [0.5, 0.3], [0.0, 0.9], [0.97, 0.0], [0.985, 0.0], [1.0, 0.2]]
+    j.run(fpt, b=bpt)
+    pt_tb = np.array(j.Tb, dtype=np.float64)
+    j.run(fpt, b='disc')
+    disc_tb = np.array(j.Tb, dtype=np.float64)
+    # C3 subset: limb profile b='0.0:1.0:0.01<0' -> every 9th ray + the last four; 50 freqs 1..50
+    f3 = list(np.linspace(1, 50, 50))
+    ball = [[v, 0.0] for v in np.arange(0.0, 1.0 + 0.005, 0.01) if v < 0.995 * (j.config.Rpol / j.config.Req) /
+            np.sqrt(0.0 + (j.config.Rpol / j.config.Req)**2)]
+    sel = sorted(set(list(range(0, len(ball), 9)) + list(range(len(ball) - 4, len(ball)))))
+    b3 = [ball[i] for i in sel]
+    j.run(f3, b=b3)
+    c3_tb = np.array(j.Tb, dtype=np.float64)
+    save('tb.npz', bench_freqs=np.array(freqs, dtype=float), bench_b=np.array(b), bench_tb_f32=tb_bench,
+         bench_tb=tb_bench64, c1_freqs=c1_f, c1_tb=c1_tb, c1_alpha=c1_alpha, c1_tau=prof['tau'], c1_W=prof['W'],
+         c1_Tb_lyr=prof['Tb_lyr'], c1_integrated_W=prof['integrated_W'], pt_freqs=np.array(fpt), pt_b=np.array(bpt),
+         pt_tb=pt_tb, disc_tb=disc_tb, c3_freqs=np.array(f3), c3_b=np.array(b3), c3_nb_total=len(ball), c3_tb=c3_tb)
+
+
+def sec_neptune():
+    """Config C2: Neptune disc-averaged, 200 log-spaced freqs 1..100 GHz (passed as a list: the
+    '1;100;200' string crashes in set_utils.py:141)."""
+    n = planet('neptune')
+    freqs = list(np.logspace(0, 2, 200))
+    t0 = time.time()
+    n.run(freqs, b='disc')
+    print('  neptune run {:.1f} s'.format(time.time() - t0))
+    lay = np.array(n.alpha[0].layers)
+    save('neptune_c2.npz', freqs=np.array(freqs), tb=np.array(n.Tb, dtype=np.float64),
+         alpha_every8=lay[:, ::8], ordered_constituents=np.array(n.alpha[0].ordered_constituents))
+
+
+def sec_image():
+    """Config C4 subset: Jupiter image grid b=0.005 (601x601, set_utils.py:65-77), 64 freqs 1..100 GHz;
+    a seeded random subset of on-disc pixels + limb-ring pixels + off-disc pixels through
+    Brightness.single (float image requests crash in set_utils.py:78)."""
+    j = planet('jupiter')
+    freqs = list(np.linspace(1, 100, 64))
+    j.alpha_layers(freqs=freqs, atmos=j.atmos)
+    bstep = 0.005
+    grid = -1.0 * np.flipud(np.arange(bstep, 1.5 + bstep, bstep))
+    grid = np.concatenate((grid, np.arange(0.0, 1.5 + bstep, bstep)))
+    n = len(grid)
+    rng = np.random.default_rng(20261017)
+    q = j.config.Rpol / j.config.Req
+    xx, yy = np.meshgrid(grid, grid)          # pixel (row=y index, col=x index)
+    rr = np.sqrt(xx**2 + (yy / q)**2)
+    on = np.argwhere(rr < 0.97)
+    ring = np.argwhere((rr >= 0.97) & (rr < 1.01))
+    off = np.argwhere(rr >= 1.01)
+    pick = np.concatenate([on[rng.choice(len(on), 96, replace=False)],
+                           ring[rng.choice(len(ring), 40, replace=False)],
+                           off[rng.choice(len(off), 8, replace=False)]])
+    tbs = []
+    t0 = time.time()
+    import contextlib
+    import io
+    for (iy, ix) in pick:
+        with contextlib.redirect_stdout(io.StringIO()):
+            tb = j.bright.single([grid[ix], grid[iy]], freqs, j.atmos[0], j.alpha[0], j.config.orientation)
+        tbs.append(np.array(tb, dtype=np.float64))
+    print('  image subset {:.1f} s'.format(time.time() - t0))
+    save('image_c4.npz', freqs=np.array(freqs), grid=grid, pick_iy_ix=pick, tb=np.array(tbs), imsize=n)
+
+
+SECTIONS = {'atm': sec_atm, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
+            'rays': sec_rays, 'tb': sec_tb, 'neptune': sec_neptune, 'image': sec_image}
+
+if __name__ == '__main__':
+    import warnings
+    warnings.filterwarnings('ignore')
+    todo = sys.argv[1:] or list(SECTIONS)
+    work = bootstrap()
+    import contextlib
+    import io
+    for s in todo:
+        t0 = time.time()
+        print('[{}]'.format(s))
+        buf = io.StringIO()
+        if s == 'plugins_notrunc' and os.environ.get('RB_GOLDEN_CHILD') != '1':
+            SECTIONS[s]()
+        else:
+            with contextlib.redirect_stdout(buf):
+                try:
+                    SECTIONS[s]()
+                finally:
+                    sys.stderr.write(''.join(l + '\n' for l in buf.getvalue().splitlines() if l.startswith('  ')))
+        print('  {:.1f} s'.format(time.time() - t0))
+    shutil.rmtree(work, ignore_errors=True)
