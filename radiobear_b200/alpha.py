@@ -1,0 +1,159 @@
+"""Alpha: layer absorption for an atmosphere, computed by the sm_100a alpha_lines kernel.
+
+API mirror of the reference's Alpha (alpha.py:13-305).  Where the reference loops over layers and
+calls each constituent plugin per layer (alpha.py:298-300, 202-213), `get_layers` hands the whole
+atmosphere to one kernel launch (engine.alpha_layers).  The formalism names of `config.par`
+(`alpha nh3:nh3_hs_sjs ...`) keep their meaning; an unknown formalism is reported and dropped just
+like a failed plugin import (alpha.py:69-72).
+"""
+import os
+from argparse import Namespace
+
+import numpy as np
+
+from . import engine
+from . import logging as rblog
+from . import utils
+from ._lib import FORMALISM_IDS
+
+
+class Alpha:
+    saved_fields = ['ordered_constituents', 'alpha_data', 'freqs', 'P']
+
+    def __init__(self, idnum=0, config=None, log=None, load_formal=True, verbose=True, **kwargs):
+        self.verbose = verbose
+        self.log = rblog.setup(log)
+        if config is None or isinstance(config, str):
+            from . import config as pcfg
+            config = pcfg.planetConfig('x', configFile=config)
+            config.update_config(**kwargs)
+        self.config = config
+        self.constituentsAreAt = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'constituents')
+        self.idnum = idnum
+        self.reset_layers()
+        self.alphafile = os.path.join(getattr(config, 'scratch_directory', 'Scratch'),
+                                      'alpha{:04d}.npz'.format(idnum))
+        self.memory = Namespace()
+        self.slab = None            # [L][F] device-order copy of .layers (what the RT kernel reads)
+        if load_formal:
+            self.setup_formalisms()
+
+    # ------------------------------------------------------------------ formalisms
+    def setup_formalisms(self):
+        """Resolve config.constituent_alpha into kernel formalisms (alpha.py:49-102)."""
+        self.constituent = {}
+        self.truncate_strength = {}
+        self.truncate_freq = {}
+        cfg = self.config
+        for c, absorber in cfg.constituent_alpha.items():
+            if absorber is None:
+                continue
+            if absorber in FORMALISM_IDS:
+                self.constituent[c] = absorber
+            else:
+                msg = "WARNING:  CAN'T LOAD " + str(absorber) + '.  '
+                print(msg * 3)
+                self.log.add("Can't load " + str(absorber), True)
+            self.truncate_freq[c] = None
+            self.truncate_strength[c] = None
+            method = getattr(cfg, 'truncate_method', {}).get(c)
+            if method is not None:
+                for tm in method.split(','):
+                    getattr(self, tm)[c] = getattr(cfg, tm)[c]
+        self.ordered_constituents = sorted(self.constituent.keys())
+        self.log.add('Using modules:', self.verbose)
+        for c in self.constituent:
+            self.log.add("\t{}: {} \t".format(c, self.constituent[c]), self.verbose)
+        copy_back = {'h2': ['h2state', 'h2newset'],
+                     'clouds': ['water_p', 'ice_p', 'nh4sh_p', 'nh3ice_p', 'h2sice_p', 'ch4_p'],
+                     'co': ['coshape']}
+        self.other_dict = {}
+        for c in self.ordered_constituents:
+            self.other_dict[c] = {k: getattr(cfg, k) for k in copy_back.get(c, []) if hasattr(cfg, k)}
+
+    def formalisms(self):
+        return [(c, self.constituent[c]) for c in self.ordered_constituents]
+
+    def reset_layers(self):
+        self.P = None
+        self.freqs = None
+        self.layers = None
+        self.slab = None
+
+    # ------------------------------------------------------------------ cache (alpha.py:110-149)
+    def save_alpha_data(self, save_type):
+        if save_type == 'file':
+            np.savez(self.alphafile, ordered_constituents=self.ordered_constituents, alpha_data=self.tosave,
+                     freqs=self.freqs, P=self.P)
+        elif save_type == 'memory':
+            self.memory.ordered_constituents = self.ordered_constituents
+            self.memory.alpha_data = self.tosave
+            self.memory.freqs = self.freqs
+            self.memory.P = self.P
+
+    def read_alpha_data(self, save_type):
+        if save_type == 'file':
+            src = np.load(self.alphafile)
+            for sf in self.saved_fields:
+                setattr(self, sf, src[sf])
+        elif save_type == 'memory':
+            for sf in self.saved_fields:
+                setattr(self, sf, getattr(self.memory, sf))
+
+    def get_layer_scale(self, scale, N):
+        """Validate a scale request; returns the [C][N] matrix the kernel applies (or None)."""
+        return engine.scale_matrix(scale, self.ordered_constituents, N)
+
+    # ------------------------------------------------------------------ the hot call
+    def get_layers(self, freqs, atm, scale=False, get_alpha='calc', save_alpha='none'):
+        """Compute (or re-scale cached) absorption for all layers: sets .layers[F, L], .P, .freqs."""
+        self.reset_layers()
+        self.freqs = freqs
+        C = atm.config.C
+        self.P = atm.gas[C['P']]
+        L = atm.gas.shape[1]
+        from_cache = get_alpha in ('memory', 'file')
+        to_cache = save_alpha in ('memory', 'file')
+        self.log.add('{} layers'.format(L), self.verbose)
+        if from_cache:
+            # cached per-constituent cube [L][F][C]: only the scale-sum is redone (alpha.py:224-225)
+            self.read_alpha_data(get_alpha)
+            cube = np.asarray(self.alpha_data, dtype=np.float64)
+            sm = self.get_layer_scale(scale, L)
+            if sm is not None:
+                cube = cube * sm.T[:, None, :]
+            slab = cube.sum(axis=2)
+        else:
+            res = engine.alpha_layers(np.asarray(freqs, dtype=np.float64), atm.gas[C['T']], atm.gas[C['P']], atm.gas, C,
+                                      cloud=atm.cloud if np.size(atm.cloud) else None, cloud_dict=atm.config.Cl,
+                                      formalisms=self.formalisms(), other_dicts=self.other_dict,
+                                      units=utils.alphaUnit, scale=scale, want_cube=to_cache,
+                                      truncate_strength=self.truncate_strength, truncate_freq=self.truncate_freq)
+            slab, cube = res if to_cache else (res, None)
+        self.slab = slab
+        self.layers = slab.T            # [F][L] view, indexable as layers[j][layer] like the reference
+        if to_cache:
+            self.tosave = cube
+            self.save_alpha_data(save_alpha)
+            del self.tosave
+
+    def get_single_layer(self, freqs, layer, atm, lscale=1.0, units='invcm'):
+        """Total absorption of one layer (alpha.py:218-233)."""
+        C = atm.config.C
+        sl = slice(layer, layer + 1)
+        slab = engine.alpha_layers(np.asarray(freqs, dtype=np.float64), atm.gas[C['T']][sl], atm.gas[C['P']][sl],
+                                   np.ascontiguousarray(atm.gas[:, sl]), C,
+                                   cloud=np.ascontiguousarray(atm.cloud[:, sl]) if np.size(atm.cloud) else None,
+                                   cloud_dict=atm.config.Cl, formalisms=self.formalisms(), other_dicts=self.other_dict,
+                                   units=units, scale=None if isinstance(lscale, dict) else lscale,
+                                   truncate_strength=self.truncate_strength, truncate_freq=self.truncate_freq)
+        return slab[0]
+
+    def get_alpha_from_calc(self, freqs, T, P, gas, gas_dict, cloud, cloud_dict, units='invcm'):
+        """Per-constituent absorption of one (T, P, X) point -> [F][C] (alpha.py:194-216)."""
+        _, cube = engine.alpha_layers(np.asarray(freqs, dtype=np.float64), [T], [P], np.asarray(gas, dtype=np.float64),
+                                      gas_dict, cloud=None if cloud is None else np.asarray(cloud, dtype=np.float64),
+                                      cloud_dict=cloud_dict, formalisms=self.formalisms(), other_dicts=self.other_dict,
+                                      units=units, want_cube=True, truncate_strength=self.truncate_strength,
+                                      truncate_freq=self.truncate_freq)
+        return cube[0]

@@ -1,0 +1,78 @@
+"""Brightness: brightness temperature along rays, computed by the rt_integrate CUDA kernel.
+
+API mirror of Brightness.single (brightness.py:30-126).  `single` is the R = 1 case of `batch`,
+which runs geometry + integration for any number of impact points in two kernel launches.
+"""
+import numpy as np
+
+from . import engine
+from . import logging as rblog
+from . import raypath
+from . import utils
+
+
+class Brightness:
+    def __init__(self, config=None, log=None, verbose=True, **kwargs):
+        self.verbose = verbose
+        self.log = rblog.setup(log)
+        if config is None or isinstance(config, str):
+            from . import config as pcfg
+            config = pcfg.planetConfig('x', configFile=config)
+            config.update_config(**kwargs)
+        self.config = config
+        self.tau_cut = 100.0
+        self.travel = None
+
+    def _args(self, atm, orientation):
+        a = raypath._geometry_args(atm, orientation, None)
+        a['T'] = atm.gas[atm.config.C['T']]
+        return a
+
+    def batch(self, b, freqs, atm, alpha, orientation=None, disc_average=False, out_f32=False, want_intW=False):
+        """Tb[R][F] for impact points b[R][2]; off-planet rays give T_cmb, limb rays below the tangent
+        shell give NaN exactly like the reference."""
+        if alpha.layers is None:
+            alpha.get_layers(freqs, atm)
+        if getattr(alpha.config, 'Doppler', False):
+            raise NotImplementedError('Doppler-shifted absorption is broken in the reference (brightness.py:83-92) '
+                                      'and not built here')
+        res = engine.rt_batch(b=np.atleast_2d(np.asarray(b, dtype=np.float64)), alpha_slab=alpha.slab,
+                              disc_average=disc_average, out_f32=out_f32, tau_cut=self.tau_cut, want_intW=want_intW,
+                              **self._args(atm, orientation))
+        return res
+
+    def single(self, b, freqs, atm, alpha, orientation=None, taulimit=20.0):
+        """Brightness temperature along one ray path -> list[F]; leaves .tau .W .Tb_lyr [F][S], .P .z [S],
+        .integrated_W [F] and .travel for the ray like the reference."""
+        disc_average = utils.b_type(b).startswith('dis')
+        if disc_average:
+            b = [0.0, 0.0]
+        self.alpha = alpha
+        self.freqs = freqs
+        self.b = b
+        if alpha.layers is None:
+            alpha.get_layers(freqs, atm)
+        if getattr(alpha.config, 'Doppler', False):
+            raise NotImplementedError('Doppler-shifted absorption is not built (broken in the reference)')
+        res = engine.rt_batch(b=np.asarray([b], dtype=np.float64), alpha_slab=alpha.slab, disc_average=disc_average,
+                              tau_cut=0.0, want_intW=True, profile_ray=0, **self._args(atm, orientation))
+        self.travel = raypath.compute_ds(atm, b, orientation)
+        if self.travel.ds is None:
+            print('Off planet')
+            self.Tb = [utils.T_cmb for _ in freqs]
+            return self.Tb
+        n = len(self.travel.ds)
+        C = atm.config.C
+        P, z = atm.gas[C['P']], atm.gas[C['Z']]
+        self.tau = res['tau'][:, :n]
+        self.W = res['W'][:, :n]
+        self.Tb_lyr = res['Tb_lyr'][:, :n]
+        self.integrated_W = res['integrated_W'][0]
+        self.P = np.concatenate(([P[0]], (P[:n - 1] + P[1:n]) / 2.0))
+        self.z = np.concatenate(([z[0]], (z[:n - 1] + z[1:n]) / 2.0))
+        self.Tb = [float(x) for x in res['Tb'][0]]
+        if self.verbose:
+            for f, w in zip(freqs, self.integrated_W):
+                if w < 0.96:
+                    print("Weight correction at {:.2f} is {:.4f} (showing below 0.96)".format(f, w))
+        return self.Tb

@@ -244,13 +244,13 @@ int rb_compute_ds(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const d
   RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, L.L * 8, &p_rad));
   RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
   RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
-  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 4, &p_n));
+  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   RB_TRY(rb_ensure(ctx, RB_BUF_MISC, (size_t)R * S * 8, &p_o));
   cudaStream_t s = ctx->stream;
   RB_CUDA(ctx, cudaMemcpyAsync(p_rad, g->radius, L.L * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemsetAsync(p_ds, 0, S * L.Rpad * 8, s));
-  L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n;
+  L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
   RB_TRY(rb_launch_geometry(ctx, L));
   RB_TRY(rb_launch_ds_transpose(ctx, L, (double*)p_o));
   RB_CUDA(ctx, cudaMemcpyAsync(out_ds, p_o, (size_t)R * S * 8, cudaMemcpyDeviceToHost, s));
@@ -278,8 +278,8 @@ int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc
   const size_t S = L.L - 1;
   void *p_ds, *p_n;
   RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
-  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 4, &p_n));
-  L.radius = g->radius; L.b = b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n;
+  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
+  L.radius = g->radius; L.b = b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
   RB_TRY(rb_launch_geometry(ctx, L));
   return rb_launch_integrate(ctx, L, rt, out_Tb, out_intW, -1, nullptr, nullptr, nullptr);
 }
@@ -301,7 +301,7 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, nL * 8, &p_rad));
   RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
   RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
-  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 4, &p_n));
+  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, nL * F * 8, &p_alpha));
   RB_TRY(rb_ensure(ctx, RB_BUF_T, nL * 8, &p_T));
   RB_TRY(rb_ensure(ctx, RB_BUF_TB, (size_t)R * F * esz, &p_tb));
@@ -311,7 +311,7 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_alpha, rt->alpha, nL * F * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_T, rt->T, nL * 8, cudaMemcpyHostToDevice, s));
-  L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n;
+  L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
   rb_rt_desc rd = *rt;
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
   RB_TRY(rb_launch_geometry(ctx, L));
@@ -324,7 +324,8 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
     RB_CUDA(ctx, cudaMemsetAsync(p_prof, 0, 3 * F * S * 8 + F * 8, s));
     RtLaunch L1 = L;
     L1.R = 1; L1.Rpad = L.Rpad;
-    L1.ds = L.ds + profile_ray; L1.nseg = L.nseg + profile_ray; L1.b = L.b + 2 * profile_ray;
+    L1.ds = L.ds + profile_ray; L1.nseg = L.nseg + profile_ray; L1.nanflag = L.nanflag + profile_ray;
+    L1.b = L.b + 2 * profile_ray;
     double* pp = (double*)p_prof;
     rd.out_f32 = 0;
     RB_TRY(rb_launch_integrate(ctx, L1, &rd, pp + 3 * F * S, nullptr, 0, pp, pp + F * S, pp + 2 * F * S));
@@ -350,7 +351,7 @@ int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int
   void *p_in, *p_ds, *p_n, *p_alpha, *p_T, *p_tb, *p_iw = nullptr;
   RB_TRY(rb_ensure(ctx, RB_BUF_MISC, (size_t)R * S * 8, &p_in));
   RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
-  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 4, &p_n));
+  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, nL * F * 8, &p_alpha));
   RB_TRY(rb_ensure(ctx, RB_BUF_T, nL * 8, &p_T));
   RB_TRY(rb_ensure(ctx, RB_BUF_TB, (size_t)R * F * esz, &p_tb));
@@ -360,8 +361,8 @@ int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int
   RB_CUDA(ctx, cudaMemcpyAsync(p_n, nseg, (size_t)R * 4, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_alpha, rt->alpha, nL * F * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_T, rt->T, nL * 8, cudaMemcpyHostToDevice, s));
-  RB_TRY(rb_launch_ds_to_slab(ctx, (const double*)p_in, R, L.Rpad, (int)S, (double*)p_ds));
-  L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n;
+  L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
+  RB_TRY(rb_launch_ds_to_slab(ctx, (const double*)p_in, R, L.Rpad, (int)S, L.nseg, L.nanflag, (double*)p_ds));
   rb_rt_desc rd = *rt;
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
   RB_TRY(rb_launch_integrate(ctx, L, &rd, p_tb, (double*)p_iw, -1, nullptr, nullptr, nullptr));

@@ -75,10 +75,12 @@ struct RtLaunch {
   const double* b;  // device [R][2]
   double* ds;       // device slab [L-1][Rpad]
   int32_t* nseg;    // device [R]
+  int32_t* nanflag; // device [R]: ray carries a NaN segment the integration would use
 };
 int rb_launch_geometry(rb_context* ctx, const RtLaunch& g);
 int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out_ds_raymajor /*[R][L-1] device*/);
-int rb_launch_ds_to_slab(rb_context* ctx, const double* ds_raymajor, int64_t R, int64_t Rpad, int S, double* slab);
+int rb_launch_ds_to_slab(rb_context* ctx, const double* ds_raymajor, int64_t R, int64_t Rpad, int S, const int* nseg,
+                         int* nanflag, double* slab);
 int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt /*device pointers*/, void* out_Tb,
                         double* out_intW, int64_t profile_ray, double* out_tau, double* out_W, double* out_Tblyr);
 

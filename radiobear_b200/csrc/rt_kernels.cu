@@ -33,6 +33,7 @@ struct GeoK {
   const double* b;
   double* ds;
   int* nseg;
+  int* nanflag;  // 1 when a segment the integration uses (index <= nseg-2) is NaN -> Tb is NaN
 };
 
 __device__ __forceinline__ void rot2planet(const GeoK& g, double x, double y, double z, double& ox, double& oy,
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
   const int S = g.L - 1;
   const double bx = g.b[2 * r], by = g.b[2 * r + 1];
   const double bb = bx * bx + by * by;
+  g.nanflag[r] = 0;
   if (!(bb < 1.0)) {  // raypath.py:126-127 (NaN impact parameters also miss)
     g.nseg[r] = -1;
     return;
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
   }
   int layer = 0;
   int count = 0;
+  int first_nan = -1;
   double* out = g.ds + r;
   for (; layer < S; ++layer) {
     const double rNow = g.radius[layer] * shape;
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     if (ds < 0.0) break;  // raypath.py:212-216
     if (g.limb == RB_LIMB_SEC) ds = fabs(rNext - rNow) / mu;
     out[(long long)layer * g.Rpad] = ds;
+    if (ds != ds && first_nan < 0) first_nan = layer;
     ++count;
     // advance and re-evaluate latitude / normal at the new position (raypath.py:228-237)
     px += ds * sx; py += ds * sy; pz += ds * sz;
@@ -177,6 +181,8 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     }
   }
   g.nseg[r] = count;
+  // Brightness.single uses ds[0 .. n-2] (brightness.py:65); a NaN there makes every frequency NaN
+  g.nanflag[r] = (first_nan >= 0 && first_nan <= count - 2) ? 1 : 0;
 }
 
 // [S][Rpad] slab -> [R][S] ray-major (only for the compute_ds API that returns Ray.ds)
@@ -202,6 +208,7 @@ __global__ void ds_transpose_kernel(const double* __restrict__ slab, long long R
 }
 
 __global__ void ds_to_slab_kernel(const double* __restrict__ in, long long R, long long Rpad, int S,
+                                  const int* __restrict__ nseg, int* __restrict__ nanflag,
                                   double* __restrict__ slab) {
   __shared__ double tile[32][33];
   const long long r0 = (long long)blockIdx.x * 32;
@@ -209,7 +216,9 @@ __global__ void ds_to_slab_kernel(const double* __restrict__ in, long long R, lo
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const long long r = r0 + j;
     const int s = s0 + threadIdx.x;
-    tile[j][threadIdx.x] = (r < R && s < S) ? in[r * S + s] : 0.0;
+    const double v = (r < R && s < S) ? in[r * S + s] : 0.0;
+    tile[j][threadIdx.x] = v;
+    if (v != v && s <= nseg[r] - 2) nanflag[r] = 1;  // benign race: every writer stores 1
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -266,6 +275,7 @@ struct RtK {
   const double* T;      // [L]
   const double* ds;     // [S][Rpad]
   const int* nseg;      // [R]
+  const int* nanflag;   // [R]
   void* out_Tb;         // [R][F]
   double* out_intW;     // [R][F] or null
   int out_f32;
@@ -289,10 +299,12 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
 
   int n[RPT];
   int nmax = 0;
+  bool isnan_ray[RPT];
 #pragma unroll
   for (int j = 0; j < RPT; ++j) {
     n[j] = (r0 + j < k.R) ? k.nseg[r0 + j] : -1;
-    nmax = max(nmax, n[j]);
+    isnan_ray[j] = (r0 + j < k.R) && !PROFILE && k.nanflag[r0 + j] != 0;
+    if (!isnan_ray[j]) nmax = max(nmax, n[j]);  // rays that end NaN need no integration at all
   }
   double tau[RPT], Wp[RPT], iW[RPT], Tb[RPT];
 #pragma unroll
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
     bool live = false;
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
-      if (i + 1 < n[j] && !(tau[j] > k.tau_cut)) {
+      if (i + 1 < n[j] && !isnan_ray[j] && !(tau[j] > k.tau_cut)) {
         const double h = dsv[j] * kKmToCm * 0.5;        // ds/2 in cm
         tau[j] = tau[j] + asum * h;                      // dtau = (a0 + a1) * ds / 2
         const double W = DISC ? 2.0 * a1 * expn2(tau[j]) : a1 * exp(-tau[j]);
@@ -344,12 +356,14 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
     const long long r = r0 + j;
     if (r >= k.R) continue;
     double v;
+    double w = iW[j];
     if (n[j] < 0) v = kTcmb;                               // off planet (brightness.py:46-51)
+    else if (isnan_ray[j]) v = w = nan("");                // NaN segment below the tangent shell
     else v = (Tb[j] < kTcmb) ? kTcmb : Tb[j] / iW[j];      // brightness.py:109-113
     const size_t o = (size_t)r * k.F + f;
     if (k.out_f32) reinterpret_cast<float*>(k.out_Tb)[o] = (float)v;
     else reinterpret_cast<double*>(k.out_Tb)[o] = v;
-    if (k.out_intW) k.out_intW[o] = (n[j] < 0) ? 0.0 : iW[j];
+    if (k.out_intW) k.out_intW[o] = (n[j] < 0) ? 0.0 : w;
   }
 }
 
@@ -359,7 +373,7 @@ int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
   GeoK k{};
   k.L = g.L; k.radius = g.radius; k.n0 = g.n0; k.n1 = g.n1; k.q = g.q;
   k.cz = g.rot[0]; k.sz = g.rot[1]; k.cx = g.rot[2]; k.sx = g.rot[3];
-  k.limb = g.limb; k.R = g.R; k.Rpad = g.Rpad; k.b = g.b; k.ds = g.ds; k.nseg = g.nseg;
+  k.limb = g.limb; k.R = g.R; k.Rpad = g.Rpad; k.b = g.b; k.ds = g.ds; k.nseg = g.nseg; k.nanflag = g.nanflag;
   const int threads = 128;
   const long long blocks = (g.R + threads - 1) / threads;
   if (ctx->timing) RB_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], ctx->stream));
@@ -379,9 +393,11 @@ int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out) {
   return RB_OK;
 }
 
-int rb_launch_ds_to_slab(rb_context* ctx, const double* in, int64_t R, int64_t Rpad, int S, double* slab) {
+int rb_launch_ds_to_slab(rb_context* ctx, const double* in, int64_t R, int64_t Rpad, int S, const int* nseg,
+                         int* nanflag, double* slab) {
   dim3 grid((unsigned)((Rpad + 31) / 32), (S + 31) / 32), block(32, 8);
-  ds_to_slab_kernel<<<grid, block, 0, ctx->stream>>>(in, R, Rpad, S, slab);
+  RB_CUDA(ctx, cudaMemsetAsync(nanflag, 0, sizeof(int) * Rpad, ctx->stream));
+  ds_to_slab_kernel<<<grid, block, 0, ctx->stream>>>(in, R, Rpad, S, nseg, nanflag, slab);
   RB_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
   return RB_OK;
@@ -391,7 +407,7 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
                         int64_t profile_ray, double* out_tau, double* out_W, double* out_Tblyr) {
   RtK k{};
   k.L = g.L; k.F = rt->n_freqs; k.R = g.R; k.Rpad = g.Rpad;
-  k.alpha = rt->alpha; k.T = rt->T; k.ds = g.ds; k.nseg = g.nseg;
+  k.alpha = rt->alpha; k.T = rt->T; k.ds = g.ds; k.nseg = g.nseg; k.nanflag = g.nanflag;
   k.out_Tb = out_Tb; k.out_intW = out_intW; k.out_f32 = rt->out_f32; k.disc = rt->disc_average;
   k.tau_cut = (rt->tau_cut > 0.0) ? rt->tau_cut : INFINITY;
   k.profile_ray = profile_ray; k.out_tau = out_tau; k.out_W = out_W; k.out_Tblyr = out_Tblyr;

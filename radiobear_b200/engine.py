@@ -97,6 +97,8 @@ def prepare_catalogs(ctx, formalisms, truncate_strength=None, truncate_freq=None
     truncate_strength = truncate_strength or {}
     truncate_freq = truncate_freq or {}
     for c, name in formalisms:
+        if name not in catalogs.FORMALISM_CATALOGS:
+            raise NotImplementedError('formalism {} is not built in radiobear_b200'.format(name))
         catalogs.upload(ctx, name, truncate_strength.get(c), truncate_freq.get(c))
 
 

@@ -1,0 +1,91 @@
+"""Multi-GPU sharding: one process per GPU, torch.distributed (NCCL over NVLink; gloo in CPU tests).
+
+The hot paths shard without any data-path collective:
+* image / profile runs: contiguous blocks of image ROWS (or b-points) per rank, balanced by the number
+  of on-disc pixels (off-disc pixels cost nothing); every rank holds the full alpha slab (0.5 MB at C4,
+  recomputed locally in ~0.1 ms rather than broadcast); one final gather of Tb to rank 0.
+* frequency sweeps (alpha-dominated): contiguous FREQUENCY blocks per rank; one all_gather of the
+  [L][F/n] slabs when every rank needs the full slab.
+This replaces the reference's manual `block=[i, N]` row chunking (set_utils.py:66-76,
+scripts/image_block_pipeline.py).
+"""
+import numpy as np
+
+
+def row_weights(grid, q, floor=1.0):
+    """Work estimate per image row: on-disc pixel count (+ a small floor for the off-disc scan)."""
+    grid = np.asarray(grid, dtype=np.float64)
+    half = 1.0 - (grid / q)**2                      # x^2 < 1 - (y/q)^2
+    w = np.zeros(len(grid))
+    ok = half > 0.0
+    step = np.abs(grid[1] - grid[0]) if len(grid) > 1 else 1.0
+    w[ok] = 2.0 * np.sqrt(half[ok]) / step
+    return w + floor
+
+
+def partition_rows(grid, q, n):
+    """n contiguous [start, stop) row blocks with (nearly) equal summed weight."""
+    w = row_weights(grid, q)
+    cum = np.concatenate(([0.0], np.cumsum(w)))
+    total = cum[-1]
+    cuts = [0]
+    for i in range(1, n):
+        target = total * i / n
+        j = int(np.searchsorted(cum, target))
+        j = min(max(j, cuts[-1]), len(w))
+        cuts.append(j)
+    cuts.append(len(w))
+    return [(cuts[i], cuts[i + 1]) for i in range(n)]
+
+
+def partition_even(count, n):
+    """n contiguous [start, stop) blocks of `count` items (frequency blocks / b-lists)."""
+    base, extra = divmod(count, n)
+    out, s = [], 0
+    for i in range(n):
+        e = s + base + (1 if i < extra else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def gather_blocks(local, parts, dst=0, group=None):
+    """Gather per-rank row blocks (torch tensors [rows_i, ...]) to rank `dst` -> [sum rows, ...] or None.
+
+    Blocks are padded to the largest block so one dist.gather moves everything (NVLink: 92 MB for the
+    full C4 cube, ~0.15 ms at 700 GB/s)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    rows = [e - s for s, e in parts]
+    if world == 1:
+        return local
+    mx = max(rows)
+    pad = local
+    if local.shape[0] < mx:
+        pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+    pad = pad.contiguous()
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([bufs[i][:rows[i]] for i in range(world)], dim=0)
+
+
+def all_gather_freq_blocks(local_slab, parts, group=None):
+    """All-gather frequency-sharded alpha slabs [L][F_i] -> full [L][F] on every rank."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local_slab
+    widths = [e - s for s, e in parts]
+    mx = max(widths)
+    L = local_slab.shape[0]
+    pad = torch.zeros((L, mx), dtype=local_slab.dtype, device=local_slab.device)
+    pad[:, :local_slab.shape[1]] = local_slab
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([bufs[i][:, :widths[i]] for i in range(world)], dim=1).contiguous()

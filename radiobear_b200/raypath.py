@@ -1,0 +1,64 @@
+"""Ray geometry: path length through every layer shell for an impact point b.
+
+API mirror of raypath.compute_ds / Ray (raypath.py:20-36, 108-273).  The geometry itself runs in
+the ray_geometry CUDA kernel (csrc/rt_kernels.cu), one thread per ray; `compute_ds_batch` exposes
+the batched form the image / profile paths use.
+"""
+import numpy as np
+
+from . import engine
+
+
+class Ray:
+    """Holds the ray parameters (same fields as the reference)."""
+
+    allowed_parameters = ['ds', 'layer4ds', 'r4ds', 'P4ds', 'doppler', 'tip', 'rotate', 'rNorm']
+
+    def __init__(self):
+        for k in self.allowed_parameters:
+            setattr(self, k, None)
+
+    def update(self, **kwargs):
+        for k, v in kwargs.items():
+            if k not in self.allowed_parameters:
+                raise ValueError('{} not allowed Ray parameter'.format(k))
+            setattr(self, k, v)
+
+
+def computeAspect(Q, f=1.0):
+    """[position angle, planetographic sub-earth latitude] (deg) -> (tip, rotate) in rad (raypath.py:39-44)."""
+    tip = -Q[0] * np.pi / 180.0
+    rotate = -np.arctan(np.tan(Q[1] * np.pi / 180.0) * (1.0 - f)**2)
+    return tip, rotate
+
+
+def _geometry_args(atm, orientation, gtype):
+    cfg = atm.config
+    LP = cfg.LP
+    if gtype is None:
+        gtype = cfg.gtype
+    if orientation is None:
+        orientation = cfg.orientation
+    return dict(radius=atm.property[LP['R']], refr_index=atm.property[LP['N']], Req=cfg.Req, Rpol=cfg.Rpol,
+                orientation=[float(orientation[0]), float(orientation[1])], gtype=gtype,
+                limb=getattr(cfg, 'limb', 'shape'))
+
+
+def compute_ds_batch(atm, b, orientation=None, gtype=None):
+    """ds[R][L-1] (km), nseg[R] (-1: ray misses the planet), (tip, rotate, rNorm)."""
+    return engine.compute_ds(b=np.atleast_2d(np.asarray(b, dtype=np.float64)), **_geometry_args(atm, orientation, gtype))
+
+
+def compute_ds(atm, b, orientation=None, gtype=None, verbose=False):
+    """Path lengths for one impact point -> Ray (ds is None when the ray misses, raypath.py:126-140)."""
+    path = Ray()
+    ds, nseg, aspect = compute_ds_batch(atm, [b], orientation, gtype)
+    n = int(nseg[0])
+    if n < 0:
+        return path
+    C, LP = atm.config.C, atm.config.LP
+    layers = list(range(n))
+    radius = atm.property[LP['R']]
+    path.update(ds=list(ds[0, :n]), layer4ds=layers, r4ds=None, P4ds=list(atm.gas[C['P']][:n]), doppler=[],
+                tip=float(aspect[0]), rotate=float(aspect[1]), rNorm=float(radius[0]))
+    return path

@@ -1,0 +1,72 @@
+"""CPU, world_size 2, gloo: the N > 1 host path -- row partition, per-rank blocks, gather to rank 0, and
+the frequency-block all_gather (no kernels; the compute is stubbed by a deterministic function)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from radiobear_b200 import parallel, set_utils
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _stub_tb(rows, cols, F):
+    r = torch.arange(rows[0], rows[1], dtype=torch.float32)[:, None, None]
+    c = torch.arange(cols, dtype=torch.float32)[None, :, None]
+    f = torch.arange(F, dtype=torch.float32)[None, None, :]
+    return r * 1000.0 + c + f / 100.0
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        grid = set_utils.image_grid(0.05)
+        q = 66854.0 / 71492.0
+        parts = parallel.partition_rows(grid, q, world)
+        local = _stub_tb(parts[rank], len(grid), 3)
+        full = parallel.gather_blocks(local, parts, dst=0)
+        fparts = parallel.partition_even(7, world)
+        slab = torch.arange(5 * 7, dtype=torch.float64).reshape(5, 7)
+        got = parallel.all_gather_freq_blocks(slab[:, fparts[rank][0]:fparts[rank][1]].contiguous(), fparts)
+        ok_slab = bool(torch.equal(got, slab))
+        if rank == 0:
+            ref = _stub_tb((0, len(grid)), len(grid), 3)
+            out.put((bool(torch.equal(full, ref)), ok_slab, parts))
+        else:
+            assert full is None
+            out.put((True, ok_slab, parts))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharding_and_gather_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[0] and r[1] for r in res)
+    parts = res[0][2]
+    assert parts[0][0] == 0 and parts[0][1] == parts[1][0]
+
+
+def test_partition_even():
+    assert parallel.partition_even(7, 2) == [(0, 4), (4, 7)]
+    assert parallel.partition_even(64, 8)[-1] == (56, 64)
+    assert parallel.partition_even(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]

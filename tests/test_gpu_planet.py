@@ -1,0 +1,72 @@
+"""GPU: the executive API -- Planet.run(freqs, b) -> DataReturn, Brightness.single side attributes."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden, relerr, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def make_planet(name, snap):
+    from radiobear_b200.atmosphere import Atmosphere
+    from radiobear_b200.planet import Planet
+    atm = Atmosphere.from_npz(os.path.join(GOLDEN, snap), name)
+    return Planet(name, atmosphere=atm, verbose=False)
+
+
+def test_benchmark_script_flow():
+    """The flow of scripts/benchmark.py:10-24."""
+    tb = golden('tb.npz')
+    j = make_planet('jupiter', 'atm_jupiter_benchmark.npz')
+    freqs = [0.6, 1.25, 2.6, 5.2, 10, 21.9]
+    b = [[0.0, 0.0], [np.sin(np.radians(15)), 0.0], [np.sin(np.radians(30)), 0.0], [np.sin(np.radians(45)), 0.0]]
+    rv = j.run(freqs, b=b, reuse_override='False')
+    assert rv.Tb.dtype == np.float32 and rv.Tb.shape == (4, 6) and rv.type == 'spectrum'
+    assert np.max(np.abs(rv.Tb - tb['bench_tb_f32'])) < 1e-3
+    assert np.allclose(rv.f, freqs) and rv.header['gtype'] == '# gtype: ellipse'
+
+
+def test_disc_profile_image_requests():
+    tb = golden('tb.npz')
+    j = make_planet('jupiter', 'atm_jupiter.npz')
+    rv = j.run('1:100:5', b='disc')
+    assert rv.b == ['disc'] and rv.type == 'spectrum' and len(rv.f) == 21
+    assert np.max(np.abs(np.asarray(j.Tb) - tb['c1_tb'])) < 1e-4
+    a0 = j.alpha[0].layers
+    j.run('1:100:5', b=[0.1, 0.2])
+    assert j.alpha[0].layers is a0                                   # check_reuse skipped the absorption step
+    rv = j.run(list(np.linspace(1, 50, 50)), b='0.0:1.0:0.01<0')     # config C3
+    assert rv.type == 'profile' and rv.Tb.shape == (100, 50)
+    assert np.isnan(rv.Tb[-1]).all() and np.isfinite(rv.Tb[:90]).all()
+    rv = j.run([10.0, 22.0], b='stamp:0.1:-0.2,0.2,-0.1,0.1')
+    assert rv.type == 'image' and rv.Tb.shape == (5, 3, 2)
+    rv = j.run(22.0, b=0.05)                                          # float b: full image (crashes in the reference)
+    assert rv.type == 'image' and rv.Tb.shape == (61, 61)
+    assert rv.Tb[0, 0] == np.float32(2.725) and rv.Tb[30, 30] > 100.0
+    rv = j.run('1;100;8', b='disc', scale=2.0)                        # log sweep string + scalar scale
+    assert len(rv.f) == 8
+
+
+def test_brightness_single_attributes():
+    tb = golden('tb.npz')
+    j = make_planet('jupiter', 'atm_jupiter.npz')
+    freqs = list(tb['c1_freqs'])
+    j.alpha_layers(freqs, j.atmos)
+    Tb = j.bright.single('disc', freqs, j.atmos[0], j.alpha[0], j.config.orientation)
+    assert np.max(np.abs(np.array(Tb) - tb['c1_tb'][0])) < 1e-4
+    B = j.bright
+    assert B.tau.shape == tb['c1_tau'].shape and np.max(relerr(B.tau, tb['c1_tau'])) < 1e-8
+    assert B.Tb_lyr.shape == tb['c1_Tb_lyr'].shape and len(B.P) == B.tau.shape[1] == len(B.z)
+    assert np.max(relerr(B.integrated_W, tb['c1_integrated_W'])) < 1e-8
+    assert len(B.travel.ds) == 999
+    assert j.bright.single([1.0, 0.2], freqs, j.atmos[0], j.alpha[0]) == [2.725] * len(freqs)
+
+
+def test_neptune_c2_run():
+    n = golden('neptune_c2.npz')
+    p = make_planet('neptune', 'atm_neptune.npz')
+    rv = p.run(list(n['freqs']), b='disc')
+    assert np.max(np.abs(np.asarray(p.Tb) - n['tb'])) < 1e-4
+    assert p.alpha[0].ordered_constituents == [str(x) for x in n['ordered_constituents']]

@@ -1,0 +1,210 @@
+"""GPU: ray geometry and brightness-temperature parity (through the C ABI).
+
+Bars: ds within 1e-8 relative of the reference (the kernel is trig-free algebra, the reference goes
+through asin/atan2/sin/cos: agreement is ~1e-10), NaN limb segments at the same depth, Tb within 0.01 K
+(north_star), off-planet rays = 2.725 K."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden, keymap, relerr, formalisms_of, TRUNC, GOLDEN
+
+pytestmark = pytest.mark.gpu
+TB_TOL = 0.01
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from radiobear_b200 import engine
+    return engine
+
+
+def geom(a):
+    LP = keymap(a['LP_keys'])
+    return dict(radius=a['property'][LP['R']], refr_index=a['property'][LP['N']], Req=float(a['Req']),
+                Rpol=float(a['Rpol']), orientation=a['orientation'], gtype=str(a['gtype']), limb=str(a['limb']))
+
+
+@pytest.mark.parametrize('planet', ['jupiter', 'neptune'])
+def test_compute_ds_golden(eng, planet):
+    from oracle import ray_oracle as ro
+    g = golden('rays.npz')
+    a = golden('atm_{}.npz'.format(planet))
+    ds, nseg, aspect = eng.compute_ds(b=g['b'], **geom(a))
+    tip, rotate = ro.compute_aspect(a['orientation'], 1.0 - float(a['Rpol']) / float(a['Req']))
+    assert abs(aspect[0] - tip) < 1e-15 and abs(aspect[1] - rotate) < 1e-15 and aspect[2] == geom(a)['radius'][0]
+    for i, ns in enumerate(g['nseg_' + planet]):
+        if ns == 0:
+            assert nseg[i] == -1                                   # Ray.ds is None
+            continue
+        assert nseg[i] == ns
+        ref, d = g['ds_' + planet][i][:ns], ds[i][:ns]
+        # The recurrence is chaotic once a ray grazes a shell (the reference's asin/acos pair reflects the
+        # direction when cos(t_inc) < 0): compare strictly up to the first NaN of either, minus a margin.
+        first_nan = min(int(np.argmax(np.isnan(ref))) if np.isnan(ref).any() else ns,
+                        int(np.argmax(np.isnan(d))) if np.isnan(d).any() else ns)
+        assert np.isnan(ref).any() == np.isnan(d).any()
+        smooth = max(1, first_nan - 300) if np.isnan(ref).any() else ns
+        assert np.max(relerr(d[:smooth], ref[:smooth])) < 1e-8
+
+
+def test_compute_ds_secant_and_sphere(eng):
+    from oracle import ray_oracle as ro
+    g = golden('rays.npz')
+    a = golden('atm_jupiter.npz')
+    ga = geom(a)
+    ga['limb'] = 'sec'
+    ds, nseg, _ = eng.compute_ds(b=g['b'][:6], **ga)
+    assert np.max(relerr(ds, g['ds_jupiter_sec'][:, :999])) < 1e-8
+    ga = geom(a)
+    ga['gtype'] = 'sphere'
+    ds, nseg, _ = eng.compute_ds(b=g['b'][:6], **ga)
+    for i in range(6):
+        o = ro.compute_ds(ga['radius'], ga['refr_index'], g['b'][i], ga['Req'], ga['Rpol'], ga['orientation'], 'sphere')
+        assert nseg[i] == len(o['ds']) and np.max(relerr(ds[i], o['ds'])) < 1e-8
+    with pytest.raises(NotImplementedError):
+        eng.compute_ds(b=g['b'][:1], **dict(geom(a), gtype='gravity'))
+
+
+def test_raypath_api(eng):
+    from radiobear_b200.atmosphere import Atmosphere
+    from radiobear_b200 import raypath
+    atm = Atmosphere.from_npz(os.path.join(GOLDEN, 'atm_jupiter.npz'), 'jupiter')
+    g = golden('rays.npz')
+    ray = raypath.compute_ds(atm, [0.5, 0.3])
+    assert len(ray.ds) == 999 and ray.layer4ds == list(range(999)) and ray.rNorm == atm.property[1][0]
+    assert np.max(relerr(np.array(ray.ds), g['ds_jupiter'][1])) < 1e-8
+    assert raypath.compute_ds(atm, [1.0, 0.2]).ds is None
+    with pytest.raises(ValueError):
+        ray.update(bogus=1)
+
+
+def _slab(eng, a, freqs):
+    C = keymap(a['C_keys'])
+    return eng.alpha_layers(freqs, a['gas'][C['T']], a['gas'][C['P']], a['gas'], C, formalisms=formalisms_of(a),
+                            other_dicts={'h2': {'h2state': 'e'}, 'co': {'coshape': 'voigt'}}, truncate_strength=TRUNC)
+
+
+def test_reference_known_answer_table(eng):
+    """scripts/benchmark.py:10-24 end to end on the GPU path."""
+    a = golden('atm_jupiter_benchmark.npz')
+    tb = golden('tb.npz')
+    C = keymap(a['C_keys'])
+    slab = _slab(eng, a, tb['bench_freqs'])
+    res = eng.rt_batch(b=tb['bench_b'], alpha_slab=slab, T=a['gas'][C['T']], **geom(a))
+    assert np.max(np.abs(res['Tb'] - tb['bench_tb'])) < 1e-4
+    res32 = eng.rt_batch(b=tb['bench_b'], alpha_slab=slab, T=a['gas'][C['T']], out_f32=True, **geom(a))
+    assert res32['Tb'].dtype == np.float32 and np.max(np.abs(res32['Tb'] - tb['bench_tb_f32'])) < 1e-3
+
+
+def test_c1_disc_average_and_profiles(eng):
+    """Config C1: Jupiter disc-averaged '1:100:5' -- E2 weighting, tau / W / Tb_lyr profiles."""
+    a = golden('atm_jupiter.npz')
+    tb = golden('tb.npz')
+    C = keymap(a['C_keys'])
+    slab = _slab(eng, a, tb['c1_freqs'])
+    assert np.max(relerr(slab.T, tb['c1_alpha'])) < 1e-9
+    res = eng.rt_batch(b=[[0.0, 0.0]], alpha_slab=slab, T=a['gas'][C['T']], disc_average=True, tau_cut=0.0,
+                       want_intW=True, profile_ray=0, **geom(a))
+    assert np.max(np.abs(res['Tb'] - tb['c1_tb'])) < 1e-4
+    assert np.max(relerr(res['integrated_W'][0], tb['c1_integrated_W'])) < 1e-8
+    n = tb['c1_tau'].shape[1]
+    assert np.max(relerr(res['tau'][:, :n], tb['c1_tau'])) < 1e-8
+    big = tb['c1_W'] > 1e-300
+    assert np.max(relerr(res['W'][:, :n][big], tb['c1_W'][big])) < 1e-7
+    assert np.max(relerr(res['Tb_lyr'][:, :n], tb['c1_Tb_lyr'])) < 1e-8
+    cut = eng.rt_batch(b=[[0.0, 0.0]], alpha_slab=slab, T=a['gas'][C['T']], disc_average=True, tau_cut=100.0, **geom(a))
+    assert np.array_equal(cut['Tb'], res['Tb'])                    # the tau cut does not change a single bit
+
+
+def test_points_disc_and_limb_profile(eng):
+    a = golden('atm_jupiter.npz')
+    tb = golden('tb.npz')
+    C = keymap(a['C_keys'])
+    slab = _slab(eng, a, tb['pt_freqs'])
+    res = eng.rt_batch(b=tb['pt_b'], alpha_slab=slab, T=a['gas'][C['T']], **geom(a))
+    assert np.array_equal(np.isnan(res['Tb']), np.isnan(tb['pt_tb']))
+    assert np.nanmax(np.abs(res['Tb'] - tb['pt_tb'])) < 1e-4
+    assert np.all(res['Tb'][-1] == 2.725)                          # b = (1.0, 0.2) misses the planet
+    res = eng.rt_batch(b=[[0.0, 0.0]], alpha_slab=slab, T=a['gas'][C['T']], disc_average=True, **geom(a))
+    assert np.max(np.abs(res['Tb'] - tb['disc_tb'])) < 1e-4
+    # config C3: limb profile, 50 freqs; the last rays are NaN in the reference
+    slab = _slab(eng, a, tb['c3_freqs'])
+    res = eng.rt_batch(b=tb['c3_b'], alpha_slab=slab, T=a['gas'][C['T']], **geom(a))
+    assert np.array_equal(np.isnan(res['Tb']), np.isnan(tb['c3_tb']))
+    assert np.isnan(tb['c3_tb']).any()
+    assert np.nanmax(np.abs(res['Tb'] - tb['c3_tb'])) < TB_TOL
+    assert np.nanmax(np.abs(res['Tb'] - tb['c3_tb'])) < 1e-4
+
+
+def test_neptune_c2_disc(eng):
+    a = golden('atm_neptune.npz')
+    n = golden('neptune_c2.npz')
+    C = keymap(a['C_keys'])
+    slab = _slab(eng, a, n['freqs'])
+    res = eng.rt_batch(b=[[0.0, 0.0]], alpha_slab=slab, T=a['gas'][C['T']], disc_average=True, **geom(a))
+    assert np.max(np.abs(res['Tb'] - n['tb'])) < 1e-4
+
+
+def test_image_c4_subset_and_full_size_properties(eng):
+    """Config C4: 601 x 601 pixels x 64 freqs.  Parity on the reference-computed subset (on-disc, NaN ring,
+    off-disc) and size-independent properties on the full cube: off-disc pixels are exactly 2.725 K, the
+    image of an untilted planet is mirror-symmetric in x and y, the NaN ring hugs the limb."""
+    from radiobear_b200 import set_utils
+    a = golden('atm_jupiter.npz')
+    im = golden('image_c4.npz')
+    C = keymap(a['C_keys'])
+    slab = _slab(eng, a, im['freqs'])
+    grid = im['grid']
+    bsub = np.array([[grid[ix], grid[iy]] for iy, ix in im['pick_iy_ix']])
+    res = eng.rt_batch(b=bsub, alpha_slab=slab, T=a['gas'][C['T']], **geom(a))
+    ref = im['tb']
+    finite = ~np.isnan(ref).any(axis=1)
+    assert np.max(np.abs(res['Tb'][finite] - ref[finite])) < TB_TOL
+    # NaN <-> NaN at identical pixels
+    assert np.array_equal(np.isnan(res['Tb']).any(axis=1), np.isnan(ref).any(axis=1))
+    # full cube through the float32 image path
+    rv = set_utils.set_b(0.005)
+    ball = np.array(rv.b)
+    out = eng.rt_batch(b=ball, alpha_slab=slab, T=a['gas'][C['T']], out_f32=True, **geom(a))['Tb'].reshape(601, 601, 64)
+    q = float(a['Rpol']) / float(a['Req'])
+    xx, yy = np.meshgrid(grid, grid)
+    rr = np.sqrt(xx**2 + (yy / q)**2)
+    # (the reference's shell radius uses the geocentric latitude as the ellipse parameter, shape.py:240-244,
+    #  so its limb sits up to ~0.3 % outside the true ellipse at mid-latitudes)
+    assert np.all(out[rr >= 1.01] == np.float32(2.725))
+    assert np.all(np.isfinite(out[rr < 0.95])) and out[rr < 0.95].min() > 100.0
+    nanmask = np.isnan(out).any(axis=2)
+    assert nanmask.any() and rr[nanmask].min() > 0.95
+    assert np.array_equal(np.isnan(out), np.isnan(out[:, ::-1]))
+    ok = ~np.isnan(out) & ~np.isnan(out[:, ::-1]) & ~np.isnan(out[::-1])
+    assert np.max(np.abs(out - out[:, ::-1])[ok]) < 2e-3           # mirror in x
+    assert np.max(np.abs(out - out[::-1])[ok]) < 2e-3              # mirror in y
+    for k, (iy, ix) in enumerate(im['pick_iy_ix']):
+        if finite[k]:
+            assert np.max(np.abs(out[iy, ix] - ref[k])) < TB_TOL
+
+
+def test_rt_integrate_with_supplied_segments(eng):
+    """Integration alone on caller-supplied ds (ragged nseg, NaN segments) against the oracle."""
+    from oracle import rt_oracle as rto
+    a = golden('atm_jupiter.npz')
+    tb = golden('tb.npz')
+    g = golden('rays.npz')
+    C = keymap(a['C_keys'])
+    T = a['gas'][C['T']]
+    slab = np.ascontiguousarray(tb['c1_alpha'].T)
+    rows = [0, 1, 3, 8, 9]
+    ds = g['ds_jupiter'][rows].copy()
+    nseg = np.array([999, 700, 999, 999, 2], dtype=np.int32)
+    out, iw = eng.rt_integrate(ds, nseg, slab, T, tau_cut=0.0, want_intW=True)
+    for k in range(len(rows)):
+        n = nseg[k]
+        ref = rto.integrate_ray(ds[k][:n], np.arange(n), tb['c1_alpha'], T)
+        assert np.array_equal(np.isnan(out[k]), np.isnan(ref))
+        if not np.isnan(ref).any():
+            assert np.max(np.abs(out[k] - ref)) < 1e-6
+    d = eng.rt_integrate(ds[:1], nseg[:1], slab, T, disc_average=True)
+    ref = rto.integrate_ray(ds[0], np.arange(999), tb['c1_alpha'], T, disc_average=True)
+    assert np.max(np.abs(d[0] - ref)) < 1e-6

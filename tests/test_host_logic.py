@@ -1,0 +1,161 @@
+"""CPU: host-side request parsing, configuration, scale handling, catalog truncation, the atmosphere
+provider and the multi-GPU row partition (no kernels)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden, relerr
+from radiobear_b200 import set_utils, utils, catalogs, engine, data_handling
+from radiobear_b200.atmosphere import Atmosphere
+from radiobear_b200 import parallel
+
+
+def test_set_freq_forms():
+    assert set_utils.set_freq(5)[0] == [5.0]
+    assert set_utils.set_freq([1.0, 2.0])[0] == [1.0, 2.0]
+    f, u = set_utils.set_freq('1:100:5')
+    assert len(f) == 21 and f[-1] == 101.0                       # set_utils.py:138
+    f, _ = set_utils.set_freq('1;100;200')                       # crashes in the reference
+    assert len(f) == 200 and np.allclose(f, np.logspace(0, 2, 200))
+    assert set_utils.set_freq('1,2,3')[0] == [1.0, 2.0, 3.0]
+    assert set_utils.set_freq([1000.0], 'MHz')[0] == [1.0]
+    with pytest.raises(ValueError):
+        set_utils.set_freq({'a': 1})
+
+
+def test_set_b_forms():
+    r = set_utils.set_b('disc')
+    assert r.b == ['disc'] and r.data_type == 'spectrum'
+    r = set_utils.set_b([0.1, 0.2])
+    assert r.b == [[0.1, 0.2]] and r.data_type == 'spectrum'
+    r = set_utils.set_b([[0.0, 0.0]] * 6)
+    assert r.data_type == 'profile'
+    r = set_utils.set_b('0.0:1.0:0.01<0', Rpol=66854.0, Req=71492.0)
+    assert len(r.b) == 100 and r.data_type == 'profile' and abs(r.b[-1][0] - 0.99) < 1e-12   # config C3
+    r = set_utils.set_b('0.1,0.2<90', Rpol=66854.0, Req=71492.0)
+    assert abs(r.b[0][1] - 0.1) < 1e-15 and abs(r.b[0][0]) < 1e-16
+    r = set_utils.set_b(0.005)                                   # float image request crashes in the reference
+    assert r.data_type == 'image' and r.imSize == [601, 601] and len(r.b) == 601 * 601
+    assert r.b[0] == [-1.5, -1.5] and r.b[1][1] == -1.5          # rows of constant y, x fastest
+    r2 = set_utils.set_b(0.005, block=[2, 4])
+    assert r2.imSize[0] == 601 and len(r2.b) == 601 * r2.imSize[1]
+    r = set_utils.set_b('stamp:0.1:-0.2,0.2,-0.1,0.1')
+    assert r.data_type == 'image' and len(r.b) == 5 * 3
+
+
+def test_image_grid_on_disc_count():
+    grid = set_utils.image_grid(0.005)
+    q = 66854.0 / 71492.0
+    xx, yy = np.meshgrid(grid, grid)
+    assert len(grid) == 601
+    # 117 493 on-disc pixels of the 601 x 601 Jupiter grid (ellipse x^2 + (y/q)^2 < 1)
+    assert abs(int(np.sum(xx**2 + (yy / q)**2 < 1.0)) - 117493) < 600
+
+
+def test_units_and_helpers():
+    assert utils.proc_unit('MHz') == 'GHz' and utils.convert_unit(2.0, 'AU') == 2.0 * 149597870.691
+    assert utils.isanynum(3) and utils.isanynum('4.5') and not utils.isanynum(True) and not utils.isanynum([1])
+    assert utils.b_type('DISC') == 'disc' and utils.b_type([[0, 0]] * 25) == 'image'
+    assert utils.T_cmb == 2.725
+
+
+def test_data_return_dtypes():
+    d = data_handling.Data()
+    d.set('Tb', [[1.0, 2.0]])
+    assert d.Tb.dtype == np.float32                              # data_handling.py:46-47
+    d.set('b', ['disc'])
+    assert d.b == ['disc']
+    d.set('bogus', 1)
+    assert not hasattr(d, 'bogus')
+
+
+def test_scale_matrix_rules():
+    ordered = ['h2', 'h2o', 'nh3']
+    assert engine.scale_matrix(False, ordered, 4) is None
+    assert engine.scale_matrix(1.0, ordered, 4) is None
+    m = engine.scale_matrix(2, ordered, 4)
+    assert m.shape == (3, 4) and np.all(m == 2.0)
+    m = engine.scale_matrix([1, 2, 3, 4], ordered, 4)
+    assert np.all(m[1] == [1, 2, 3, 4])
+    m = engine.scale_matrix({'nh3': [0.5] * 4}, ordered, 4)
+    assert np.all(m[2] == 0.5) and np.all(m[:2] == 1.0)
+    with pytest.raises(ValueError):
+        engine.scale_matrix({'xx': [1] * 4}, ordered, 4)         # alpha.py:241-243
+    with pytest.raises(ValueError):
+        engine.scale_matrix({'nh3': [1] * 3}, ordered, 4)        # alpha.py:244-245
+    with pytest.raises(ValueError):
+        engine.scale_matrix([1, 2], ordered, 4)                  # alpha.py:251-252
+
+
+def test_catalog_truncation():
+    assert catalogs.table('h2s').shape == (4, 200) and catalogs.table('h2s', 1e-22).shape == (4, 121)
+    assert catalogs.table('ph3').shape == (6, 320) and catalogs.table('ph3', 1e-22).shape == (6, 33)
+    assert catalogs.table('h2o').shape == (9, 15) and catalogs.table('h2o', 0).shape == (9, 15)
+    assert catalogs.table('h2o', truncate_freq=400.0).shape == (9, 5)
+    assert catalogs.table('nh3_inv').shape == (4, 415) and catalogs.table('nh3_rot').shape == (6, 201)
+    assert catalogs.table('nh3_v2').shape == (3, 198) and catalogs.table('nh3_sjs').shape == (4, 200)
+    assert catalogs.table('co').shape == (3, 26)
+
+
+def test_config_parsing(tmp_path):
+    from radiobear_b200 import config as pcfg
+    os.makedirs(tmp_path / 'Jupiter')
+    cf = tmp_path / 'Jupiter' / 'config.par'
+    cf.write_text('# comment\n'
+                  'gasfile my.gas\nconstituents Z T P H2 HE CH4 NH3 H2O H2S SOLN OTHER PH3 CO CO13 HCN DZ\n'
+                  'alpha nh3:nh3_dbs_sjs h2s:h2s_ddb cloud:none co:co_ddb\n'
+                  'regridtype 1000\npmin 0.01\npmax 10000.0\ndistance 5.2 AU\norientation 10.0 -3.0  # deg\n'
+                  'gtype sphere\nh2state n\n')
+    c = pcfg.planetConfig('jupiter', configFile=str(cf))
+    assert c.gasFile == ['my.gas'] and c.C['NH3'] == 6 and c.C['DZ'] == 15
+    assert c.constituent_alpha['nh3'] == 'nh3_dbs_sjs' and c.constituent_alpha['cloud'] is None
+    assert c.constituent_alpha['co'] == 'co_ddb' and c.constituent_alpha['h2'] == 'h2_jj_ddb'
+    assert c.regridType == 1000 and c.pmin == 0.01 and c.gtype == 'sphere' and c.h2state == 'n'
+    assert abs(c.distance - 5.2 * 149597870.691) < 1e-3 and c.orientation == [10.0, -3.0]
+    assert c.Req == 71492.0 and c.Rpol == 66854.0 and c.truncate_strength['h2s'] == 1e-22
+    c.update_config(limb='sec', Req='70000.0')
+    assert c.limb == 'sec' and c.Req == 70000.0
+
+
+def test_atmosphere_snapshot_roundtrip(tmp_path):
+    a = Atmosphere.from_npz(os.path.join(ROOT, 'tests', 'golden', 'atm_neptune.npz'), 'neptune')
+    assert a.gas.shape == (16, 1500) and a.config.constituent_alpha['co'] == 'co_ddb'
+    assert a.config.orientation == [347.67, -29.08]
+    fn = str(tmp_path / 'snap.npz')
+    a.to_npz(fn)
+    b = Atmosphere.from_npz(fn, 'neptune')
+    assert np.array_equal(a.gas, b.gas) and b.config.constituent_alpha == a.config.constituent_alpha
+
+
+REF_PLANETS = '/root/reference/radiobear'
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_PLANETS), reason='reference planet files only exist in the build container')
+@pytest.mark.parametrize('planet,cfile,gold', [('jupiter', 'config.par', 'atm_jupiter.npz'),
+                                               ('neptune', 'config.par', 'atm_neptune.npz'),
+                                               ('saturn', 'config.par', 'atm_saturn.npz')])
+def test_atmosphere_pipeline_matches_reference(planet, cfile, gold, tmp_path, monkeypatch):
+    """readGas/readCloud/regrid/tweak/computeProp on the reference's own input files."""
+    import shutil
+    P = planet.capitalize()
+    shutil.copytree(os.path.join(REF_PLANETS, P), str(tmp_path / P))
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.syspath_prepend(str(tmp_path / P))
+    a = Atmosphere(planet, config=cfile)
+    assert a.std() == golden(gold)['gas'].shape[1]
+    g = golden(gold)
+    assert np.max(relerr(a.gas, g['gas'])) < 1e-11
+    assert np.max(relerr(a.cloud, g['cloud'])) < 1e-11
+    assert np.max(relerr(a.property, g['property'])) < 1e-11
+
+
+def test_row_partition_balances_on_disc_pixels():
+    grid = set_utils.image_grid(0.005)
+    q = 66854.0 / 71492.0
+    for n in (1, 2, 4, 8):
+        parts = parallel.partition_rows(grid, q, n)
+        assert parts[0][0] == 0 and parts[-1][1] == len(grid)
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(n - 1))
+        w = [parallel.row_weights(grid, q)[a:b].sum() for a, b in parts]
+        assert max(w) <= 1.25 * (sum(w) / n) + 700

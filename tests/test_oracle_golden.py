@@ -1,0 +1,176 @@
+"""CPU: pin the oracle (oracle/) to the reference.
+
+Golden vectors come from the unmodified reference run in the build container
+(tests/golden/make_golden.py) plus the reference's own known-answer table
+(scripts/benchmark.py:20-24).  The oracle is float64 numpy in the reference's operation order, so the
+bars here are tight: 1e-12 relative for absorption, bit-exact NaN pattern and 1e-12 for ray segments,
+1e-6 K for brightness temperatures.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, keymap, relerr, formalisms_of, TRUNC
+from oracle import alpha_oracle as ao
+from oracle import ray_oracle as ro
+from oracle import rt_oracle as rto
+
+# scripts/benchmark.py:20-24 (float32 values printed by the reference authors)
+T_RB = np.array([[805.38385, 424.58337, 298.74915, 227.0338, 179.9148, 147.3627],
+                 [790.66736, 420.24728, 296.62033, 225.69223, 179.22531, 147.24104],
+                 [745.55975, 407.28714, 290.07492, 221.56863, 177.13437, 146.8625],
+                 [668.4528, 385.59015, 278.51672, 214.30847, 173.56506, 146.17966]])
+
+GAS_PLUGINS = ['nh3_hs', 'nh3_dbs', 'nh3_sjs', 'nh3_hs_sjs', 'nh3_dbs_sjs', 'h2s_ddb', 'ph3_jh', 'h2o_bk', 'co_ddb',
+               'h2_jj_ddb', 'h2_jj']
+
+
+@pytest.mark.parametrize('name', GAS_PLUGINS)
+@pytest.mark.parametrize('units', ['invcm', 'dBperkm'])
+def test_plugin_matches_reference(name, units):
+    g = golden('plugins_trunc.npz')
+    C = keymap(g['C_keys'])
+    od = {'h2state': 'e', 'coshape': 'voigt'}
+    ref = g['{}__{}'.format(name, units)]
+    for p, r in zip(g['points'], ref):
+        kw = dict(units=units)
+        if name.startswith(('h2s', 'ph3')):
+            kw['truncate_strength'] = 1e-22
+        a = ao.FORMALISMS[name](g['freqs'], p[C['T']], p[C['P']], p, C, od, **kw)
+        assert np.array_equal(np.isnan(a), np.isnan(r))
+        assert np.nanmax(relerr(a, r)) < 1e-12
+
+
+def test_plugin_option_variants():
+    g = golden('plugins_trunc.npz')
+    C = keymap(g['C_keys'])
+    for p, rn, rv in zip(g['points'], g['h2_jj_ddb_n__invcm'], g['co_ddb_vvw__invcm']):
+        a = ao.h2_jj_ddb(g['freqs'], p[C['T']], p[C['P']], p, C, {'h2state': 'n'}, units='invcm')
+        assert np.max(relerr(a, rn)) < 1e-13
+        a = ao.co_ddb(g['freqs'], p[C['T']], p[C['P']], p, C, {'coshape': 'vvw'}, units='invcm')
+        assert np.max(relerr(a, rv)) < 1e-12
+
+
+def test_plugins_without_truncation():
+    g = golden('plugins_notrunc.npz')
+    C = keymap(g['C_keys'])
+    for name in ['h2s_ddb', 'ph3_jh']:
+        for p, r in zip(g['points'], g[name + '__invcm']):
+            a = ao.FORMALISMS[name](g['freqs'], p[C['T']], p[C['P']], p, C, {}, units='invcm')
+            assert np.max(relerr(a, r)) < 1e-12
+    cat = ao.default_catalog()
+    assert cat.get('h2s').shape[1] == 200 and cat.get('h2s', 1e-22).shape[1] == 121
+    assert cat.get('ph3').shape[1] == 320 and cat.get('ph3', 1e-22).shape[1] == 33
+
+
+def test_clouds_plugin():
+    g = golden('plugins_trunc.npz')
+    Cl = keymap(g['Cl_keys'])
+    od = {'water_p': 1e-4, 'ice_p': 1e-4, 'nh4sh_p': 1e-4, 'nh3ice_p': 1e-4, 'h2sice_p': 1e-4, 'ch4_p': 1e-4}
+    for units in ['invcm', 'dBperkm']:
+        for x, T, r in zip(g['cloud_points'], g['cloud_T'], g['clouds_idp__' + units]):
+            a = ao.clouds_idp(g['freqs'], T, 1.0, x, Cl, od, units=units)
+            assert np.max(relerr(a, r)) < 1e-13
+
+
+def test_get_layers_jupiter_cube_and_scaling():
+    a = golden('atm_jupiter.npz')
+    al = golden('alpha_jupiter.npz')
+    C, Cl = keymap(a['C_keys']), keymap(a['Cl_keys'])
+    ca = dict(formalisms_of(a))
+    lay = list(range(0, 1000, 7)) + [997, 998, 999]
+    kw = dict(other_dicts={'h2': {'h2state': str(a['h2state'])}}, truncate_strength=TRUNC, layers=lay)
+    tot, cube, ordered = ao.get_layers(al['freqs'], a['gas'], a['cloud'], C, Cl, ca, return_per_constituent=True, **kw)
+    assert ordered == [str(x) for x in al['ordered_constituents']]
+    assert np.max(relerr(tot, al['layers'][:, lay])) < 1e-12
+    assert np.nanmax(relerr(cube, al['cube'][lay])) < 1e-12
+    sc = {'nh3': list(np.linspace(0.5, 1.5, 1000)), 'h2o': [2.0] * 1000}
+    tot = ao.get_layers(al['freqs'], a['gas'], a['cloud'], C, Cl, ca, scale=sc, **kw)
+    assert np.max(relerr(tot, al['layers_scaled_dict'][:, lay])) < 1e-12
+    tot = ao.get_layers(al['freqs'], a['gas'], a['cloud'], C, Cl, ca, scale=list(np.linspace(2.0, 0.1, 1000)), **kw)
+    assert np.max(relerr(tot, al['layers_scaled_list'][:, lay])) < 1e-12
+
+
+@pytest.mark.parametrize('planet', ['jupiter', 'neptune'])
+def test_compute_ds_matches_reference(planet):
+    g = golden('rays.npz')
+    a = golden('atm_{}.npz'.format(planet))
+    LP = keymap(a['LP_keys'])
+    req, nr = a['property'][LP['R']], a['property'][LP['N']]
+    for b, dsr, ns in zip(g['b'], g['ds_' + planet], g['nseg_' + planet]):
+        out = ro.compute_ds(req, nr, b, float(a['Req']), float(a['Rpol']), a['orientation'], str(a['gtype']), 'shape')
+        if ns == 0:
+            assert out['ds'] is None
+            continue
+        ref = dsr[:ns]
+        assert len(out['ds']) == ns
+        assert np.array_equal(np.isnan(out['ds']), np.isnan(ref))          # NaN from the tangent depth on
+        assert np.nanmax(relerr(out['ds'], ref)) < 1e-12
+        assert list(out['layer4ds']) == list(range(ns))
+
+
+def test_compute_ds_secant_limb():
+    g = golden('rays.npz')
+    a = golden('atm_jupiter.npz')
+    LP = keymap(a['LP_keys'])
+    for b, dsr, ns in zip(g['b'][:6], g['ds_jupiter_sec'], g['nseg_jupiter_sec']):
+        out = ro.compute_ds(a['property'][LP['R']], a['property'][LP['N']], b, float(a['Req']), float(a['Rpol']),
+                            a['orientation'], 'ellipse', 'sec')
+        assert np.nanmax(relerr(out['ds'], dsr[:ns])) < 1e-12
+
+
+def _tb_oracle(atm, slab_FL, blist, disc=False):
+    C, LP = keymap(atm['C_keys']), keymap(atm['LP_keys'])
+    T = atm['gas'][C['T']]
+    out = []
+    for b in blist:
+        ray = ro.compute_ds(atm['property'][LP['R']], atm['property'][LP['N']], b, float(atm['Req']),
+                            float(atm['Rpol']), atm['orientation'], str(atm['gtype']), str(atm['limb']))
+        out.append(rto.integrate_ray(ray['ds'], ray['layer4ds'], slab_FL, T, disc_average=disc))
+    return np.array(out)
+
+
+def test_reference_known_answer_table():
+    """scripts/benchmark.py: Jupiter benchmark config, 6 freqs x 4 emission angles (A+B end to end)."""
+    a = golden('atm_jupiter_benchmark.npz')
+    tb = golden('tb.npz')
+    C, Cl = keymap(a['C_keys']), keymap(a['Cl_keys'])
+    lay = ao.get_layers(tb['bench_freqs'], a['gas'], a['cloud'], C, Cl, dict(formalisms_of(a)),
+                        other_dicts={'h2': {'h2state': 'e'}}, truncate_strength=TRUNC)
+    Tb = _tb_oracle(a, lay, tb['bench_b'])
+    assert np.max(np.abs(Tb - tb['bench_tb'])) < 1e-6          # vs the reference run here (float64)
+    assert np.max(np.abs(Tb - T_RB)) < 2e-4                    # vs the table printed in the reference (float32)
+    assert np.max(np.abs(tb['bench_tb_f32'] - T_RB)) < 1e-4
+
+
+def test_disc_and_point_tb_with_reference_alpha():
+    a = golden('atm_jupiter.npz')
+    tb = golden('tb.npz')
+    # C1: disc-averaged (E2 weighting) using the reference's own alpha.layers -> isolates path B
+    Tb = _tb_oracle(a, tb['c1_alpha'], [[0.0, 0.0]], disc=True)
+    assert np.max(np.abs(Tb - tb['c1_tb'])) < 1e-9
+    C, LP = keymap(a['C_keys']), keymap(a['LP_keys'])
+    ray = ro.compute_ds(a['property'][LP['R']], a['property'][LP['N']], [0.0, 0.0], float(a['Req']), float(a['Rpol']),
+                        a['orientation'], 'ellipse', 'shape')
+    _, prof = rto.integrate_ray(ray['ds'], ray['layer4ds'], tb['c1_alpha'], a['gas'][C['T']], disc_average=True,
+                                return_profiles=True)
+    for k in ['tau', 'W', 'Tb_lyr']:
+        assert np.max(relerr(prof[k], tb['c1_' + k])) < 1e-12
+    assert np.max(relerr(prof['integrated_W'], tb['c1_integrated_W'])) < 1e-12
+
+
+def test_image_subset_c4():
+    """C4 subset: on-disc pixels, the NaN limb ring and off-disc pixels (= T_cmb)."""
+    a = golden('atm_jupiter.npz')
+    im = golden('image_c4.npz')
+    C, Cl = keymap(a['C_keys']), keymap(a['Cl_keys'])
+    sel = list(range(0, 96, 8)) + list(range(96, 136, 4)) + [136, 140]
+    lay = ao.get_layers(im['freqs'][::8], a['gas'], a['cloud'], C, Cl, dict(formalisms_of(a)),
+                        other_dicts={'h2': {'h2state': 'e'}}, truncate_strength=TRUNC)
+    grid = im['grid']
+    assert len(grid) == 601 and np.allclose(grid, ro.image_grid(0.005))
+    bl = [[grid[ix], grid[iy]] for iy, ix in im['pick_iy_ix'][sel]]
+    Tb = _tb_oracle(a, lay, bl)
+    ref = im['tb'][sel][:, ::8]
+    assert np.array_equal(np.isnan(Tb), np.isnan(ref))
+    assert np.nanmax(np.abs(Tb - ref)) < 1e-6
+    assert np.all(im['tb'][136:] == 2.725)
