@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the RadioBEAR hot path on B200 (config C4 of BASELINE.json).
+
+Workload: Jupiter full image, b = 0.005 (601 x 601 pixels, ~117 k on the disc), 64 frequencies
+1..100 GHz, 1000-layer default atmosphere.  One "step" = one pass of the whole hot path:
+alpha_lines (1000 layers x 64 freqs x ~1400 catalog lines) -> ray_geometry (every pixel) ->
+rt_integrate (every on-disc pixel x 64 freqs x 999 segments).  Nothing is cached between steps.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1: launched by torchrun, one rank per GPU; image rows are sharded (balanced by on-disc pixels),
+every rank recomputes the 0.5 MB alpha slab, one NCCL gather brings Tb to rank 0 ("strong" scaling:
+the image is fixed).  Prints ONE JSON line on rank 0.
+
+metric  Tb pixel*freq / s over the on-disc pixels of the cube (off-disc pixels are computed too and
+        reported separately: they cost one findEdge scan).
+value   device-resident: inputs in HBM, CUDA events around each step on the launching stream, L2 flushed
+        between steps, max over ranks.
+e2e     the public call `Planet.run(freqs, b=0.005)` with host buffers: host->device copies of the
+        impact points / atmosphere and the device->host copy of the float32 cube are inside the timed
+        region (wall clock between device synchronisations).
+--impl reference  times the CPU restatement of the reference algorithm (oracle/, kind "port": the
+        reference itself is pure Python living in /root/reference, which does not exist on the GPU box)
+        on all host cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BSTEP = 0.005
+NFREQ = 64
+METRIC = 'Tb pixel*freq/s (Jupiter image cube b=0.005, 64 freqs 1-100 GHz, on-disc pixels)'
+UNIT = 'pixel*freq/s'
+WORKLOAD = 'C4: Jupiter full image b=0.005 (601x601 px) x 64 freqs 1-100 GHz, 1000 layers, alpha+geometry+RT per step'
+
+
+def workload():
+    from radiobear_b200.atmosphere import Atmosphere
+    from radiobear_b200 import set_utils
+    atm = Atmosphere.from_npz(os.path.join(ROOT, 'tests', 'golden', 'atm_jupiter.npz'), 'jupiter')
+    freqs = np.linspace(1.0, 100.0, NFREQ)
+    grid = set_utils.image_grid(BSTEP)
+    return atm, freqs, grid
+
+
+def on_disc_mask(grid, q):
+    xx, yy = np.meshgrid(grid, grid)
+    return xx**2 + (yy / q)**2 < 1.0
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def _cpu_pixels(args):
+    """Worker: geometry + integration of a few pixels with the oracle (one process = one core)."""
+    blist, lay, seed = args
+    from oracle import ray_oracle as ro, rt_oracle as rto
+    atm, freqs, grid = workload()
+    cfg = atm.config
+    T = atm.gas[cfg.C['T']]
+    out = []
+    for b in blist:
+        ray = ro.compute_ds(atm.property[cfg.LP['R']], atm.property[cfg.LP['N']], b, cfg.Req, cfg.Rpol, cfg.orientation,
+                            cfg.gtype, cfg.limb)
+        out.append(rto.integrate_ray(ray['ds'], ray['layer4ds'], lay, T))
+    return np.array(out)
+
+
+def _cpu_alpha(args):
+    layers, = args
+    from oracle import alpha_oracle as ao
+    atm, freqs, grid = workload()
+    cfg = atm.config
+    return ao.get_layers(freqs, atm.gas, atm.cloud, cfg.C, cfg.Cl, cfg.constituent_alpha,
+                         other_dicts={'h2': {'h2state': cfg.h2state}}, truncate_strength=cfg.truncate_strength,
+                         layers=layers)
+
+
+def cpu_sample(cores, n_pix_per_core=6, n_lay_per_core=24, pool=None):
+    """Time the oracle on a bounded sample and extrapolate linearly to the full job.
+
+    Returns (value pixel*freq/s for the whole job on `cores` cores, description, seconds spent)."""
+    atm, freqs, grid = workload()
+    q = atm.config.Rpol / atm.config.Req
+    mask = on_disc_mask(grid, q)
+    n_on = int(mask.sum())
+    L = atm.gas.shape[1]
+    rng = np.random.default_rng(0)
+    iy, ix = np.nonzero(mask)
+    pick = rng.choice(len(iy), n_pix_per_core * cores, replace=False)
+    pix = [[grid[ix[k]], grid[iy[k]]] for k in pick]
+    lay_all = sorted(rng.choice(L, min(L, n_lay_per_core * cores), replace=False).tolist())
+    t00 = time.perf_counter()
+    if pool is None:
+        t0 = time.perf_counter()
+        slab = _cpu_alpha((lay_all,))
+        t_alpha = time.perf_counter() - t0
+        # integration needs a full [F][L] slab: tile the sampled layers (timing only)
+        lay_full = np.tile(slab, (1, L // slab.shape[1] + 1))[:, :L]
+        t1 = time.perf_counter()
+        _cpu_pixels((pix, lay_full, 0))
+        t_pix = time.perf_counter() - t1
+    else:
+        chunks = [lay_all[i::cores] for i in range(cores)]
+        t0 = time.perf_counter()
+        slabs = pool.map(_cpu_alpha, [(c,) for c in chunks if c])
+        t_alpha = time.perf_counter() - t0
+        cat = np.concatenate(slabs, axis=1)
+        lay_full = np.tile(cat, (1, L // cat.shape[1] + 1))[:, :L]
+        t1 = time.perf_counter()
+        pool.map(_cpu_pixels, [(pix[i::cores], lay_full, i) for i in range(cores)])
+        t_pix = time.perf_counter() - t1
+    full = t_alpha * (L / len(lay_all)) + t_pix * (n_on / len(pix))
+    value = n_on * len(freqs) / full
+    desc = ('oracle port, {} core(s): alpha on {} of {} layers x {} freqs in {:.2f} s, geometry+RT on {} of {} on-disc '
+            'pixels x {} freqs in {:.2f} s, extrapolated linearly to the full cube ({:.0f} s)'
+            .format(cores, len(lay_all), L, len(freqs), t_alpha, len(pix), n_on, len(freqs), t_pix, full))
+    return value, desc, time.perf_counter() - t00
+
+
+def run_reference(args):
+    import multiprocessing as mp
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals, desc = [], ''
+    per = max(2, min(16, 256 // cores))
+    lay = max(2, 96 // cores)
+    with mp.get_context('spawn').Pool(cores) as pool:
+        pool.map(_cpu_alpha, [([0],)] * cores)                       # warm the workers (imports, catalogs)
+        for i in range(args.warmup + args.steps):
+            v, desc, _ = cpu_sample(cores, n_pix_per_core=per, n_lay_per_core=lay, pool=pool)
+            if i >= args.warmup:
+                vals.append(v)
+    value = float(np.mean(vals))
+    atm, freqs, grid = workload()
+    n_on = int(on_disc_mask(grid, atm.config.Rpol / atm.config.Req).sum())
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * n_on * NFREQ / value, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic image grid over the Jupiter default atmosphere fixture',
+            'config': {'workload': WORKLOAD, 'pixels': 'on-disc'},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.fn = tempfile.NamedTemporaryFile(prefix='rbclk', suffix='.csv', delete=False).name
+        self.device = device
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=open(self.fn, 'w'), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in open(self.fn):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.fn)
+        except OSError:
+            pass
+        if sm:
+            hi = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
+            out.update(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from radiobear_b200 import engine, parallel, _lib
+    from radiobear_b200.planet import Planet
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- radiobear_b200 has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    ctx = _lib.get_context(local)
+    ctx.enable_timing(True)
+
+    atm, freqs, grid = workload()
+    cfg = atm.config
+    q = cfg.Rpol / cfg.Req
+    L, F, n = atm.gas.shape[1], len(freqs), len(grid)
+    S = L - 1
+    mask = on_disc_mask(grid, q)
+    rparts = parallel.partition_rows(grid, q, world)
+    r0, r1 = rparts[rank]
+    pts_all = np.stack([np.tile(grid, n), np.repeat(grid, n)], axis=1)
+    parts = [(a * n, b * n) for a, b in rparts]
+    pts = pts_all[parts[rank][0]:parts[rank][1]]
+
+    # ---- device-resident inputs --------------------------------------------------------------
+    t64 = dict(dtype=torch.float64, device=dev)
+    freqs_t = torch.tensor(freqs, **t64)
+    T_t = torch.tensor(atm.gas[cfg.C['T']], **t64)
+    P_t = torch.tensor(atm.gas[cfg.C['P']], **t64)
+    gas_t = torch.tensor(atm.gas, **t64).contiguous()
+    radius_t = torch.tensor(atm.property[cfg.LP['R']], **t64)
+    nidx = atm.property[cfg.LP['N']]
+    b_t = torch.tensor(pts, **t64).contiguous()
+    slab_t = torch.empty((L, F), **t64)
+    tb_t = torch.empty((len(pts), F), dtype=torch.float32, device=dev)
+    forms = [(c, f) for c, f in sorted(cfg.constituent_alpha.items()) if f is not None]
+    other = {'h2': {'h2state': cfg.h2state}}
+    orient = [float(cfg.orientation[0]), float(cfg.orientation[1])]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        engine.alpha_layers_dev(freqs_t, T_t, P_t, gas_t, cfg.C, formalisms=forms, other_dicts=other,
+                                truncate_strength=cfg.truncate_strength, out=slab_t, freqs_host=freqs, ctx=ctx)
+        engine.rt_batch_dev(radius_t, nidx[0], nidx[1], b_t, slab_t, T_t, cfg.Req, cfg.Rpol, orient, cfg.gtype, cfg.limb,
+                            out_f32=True, tau_cut=100.0, out=tb_t, ctx=ctx)
+        if world > 1:
+            return parallel.gather_blocks(tb_t, parts, dst=0)
+        return tb_t
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    # pixel census from a real result (hit = anything but the cosmic background)
+    tb_host = tb_t.cpu().numpy()
+    n_on_local = int(np.sum(~(tb_host[:, 0] == np.float32(2.725))))
+    n_nan_local = int(np.sum(np.isnan(tb_host[:, 0])))
+    counts = torch.tensor([n_on_local, n_nan_local, len(pts)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(counts)
+    n_on, n_nan, n_all = [int(x) for x in counts.tolist()]
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (untimed)
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count() - launches0
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total.item()) / args.steps
+    value = n_on * F / (ms_per_step * 1e-3)
+
+    # per-kernel device times of the timed steps (library-side CUDA events on the same stream)
+    k_alpha = ctx.kernel_ms_history('alpha', args.steps)
+    k_geo = ctx.kernel_ms_history('geometry', args.steps)
+    k_rt = ctx.kernel_ms_history('rt', args.steps)
+    fp64_peak = ctx.fp64_peak_tflops(20000) if rank == 0 else 0.0
+
+    # ---- end to end through the public API (host buffers) ----------------------------------------
+    planet = Planet('jupiter', atmosphere=atm, verbose=False)
+    h2d = (pts.nbytes + atm.gas.nbytes + atm.cloud.nbytes + 3 * L * 8 + L * F * 8 + F * 8) if world == 1 else \
+        (pts.nbytes + 2 * L * 8 + L * F * 8 + atm.gas.nbytes + 3 * L * 8)
+    d2h = (n * n * F * 4 + L * F * 8) if rank == 0 else L * F * 8
+    for _ in range(2):
+        planet.run(list(freqs), b=BSTEP, reuse_override='false')
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        rv = planet.run(list(freqs), b=BSTEP, reuse_override='false')
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = n_on * F / float(e2e_t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except (OSError, ValueError):
+            pass
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+        rt_ms = float(np.mean(k_rt)) if len(k_rt) else float('nan')
+        n_on_rank = n_on_local
+        # algorithmic bytes of one rt_integrate launch: ds slab read for the on-disc rays +
+        # alpha slab + T + float32 Tb out for every pixel of the rank
+        rt_bytes = n_on_rank * S * 8 + F * L * 8 + L * 8 + len(pts) * F * 4
+        rt_flops = float(n_on_rank) * F * (S - 1) * 30.0      # 10 FP64 + exp (~20) per (ray, freq, segment), DESIGN.md
+        roofline = {'bound': 'hbm', 'kernel': 'rt_integrate_kernel', 'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9,
+                    'peak': hbm_peak, 'unit': 'GB/s', 'frac': rt_bytes / (rt_ms * 1e-3) / 1e9 / hbm_peak,
+                    'traffic': None, 'peak_source': peak_src, 'ms_per_launch': rt_ms,
+                    'note': 'at F=64 the kernel is FP64/exp-bound, not HBM-bound (SURVEY 8d): see fp64',
+                    'fp64': {'achieved_tflops': rt_flops / (rt_ms * 1e-3) / 1e12, 'peak_tflops': fp64_peak,
+                             'frac': rt_flops / (rt_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                             'flops_per_segment_step': 30, 'peak_source': 'rb_probe_fp64_peak (DFMA, same box, same run)',
+                             'note': 'algorithmic count over all (ray,freq,segment); the tau>100 early exit skips part of them'}}
+        cores = 1
+        cpu_v, cpu_desc, _ = cpu_sample(cores, n_pix_per_core=12, n_lay_per_core=48) if world == 1 else (None, None, None)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic image grid over the Jupiter default atmosphere fixture',
+            'config': {'workload': WORKLOAD, 'pixels': 'on-disc', 'on_disc_pixels': n_on, 'nan_limb_pixels': n_nan,
+                       'all_pixels': n_all, 'layers': L, 'freqs': F, 'sharding': 'image rows balanced by on-disc pixels',
+                       'l2': 'flushed between timed steps (256 MiB write, untimed); ds slab (0.94 GB) exceeds L2',
+                       'tb_dtype_out': 'f32', 'tau_cut': 100.0},
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'ms_per_step': 1e3 * float(e2e_t.item()), 'api': 'Planet.run(freqs, b=0.005)'},
+            'gpu_launches': int(launches),
+            'roofline': roofline,
+            'kernels_ms': {'alpha_lines': float(np.mean(k_alpha)), 'ray_geometry': float(np.mean(k_geo)),
+                           'rt_integrate': rt_ms},
+            'value_all_pixels': n_all * F / (ms_per_step * 1e-3),
+        }
+        if cpu_v is not None:
+            line['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': cpu_desc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -44,8 +44,11 @@ int rb_abi_version(void);
 int rb_create(int device, rb_context** ctx);
 void rb_destroy(rb_context* ctx);
 const char* rb_last_error(const rb_context* ctx);
-/* Use an existing CUDA stream (cudaStream_t as void*; NULL = the context's own stream). */
+/* Launch on an existing CUDA stream (cudaStream_t as void*).  NULL is the legacy default stream (what
+ * torch.cuda.current_stream().cuda_stream returns for torch's default stream), NOT "no stream". */
 int rb_set_stream(rb_context* ctx, void* cuda_stream);
+/* Go back to the context's own non-blocking stream (the state after rb_create). */
+int rb_use_own_stream(rb_context* ctx);
 int rb_synchronize(rb_context* ctx);
 /* Number of kernel launches issued through this context since creation (bench bookkeeping). */
 int64_t rb_launch_count(const rb_context* ctx);
@@ -54,6 +57,9 @@ int64_t rb_launch_count(const rb_context* ctx);
  * was enabled with rb_enable_timing(ctx, 1). */
 int rb_enable_timing(rb_context* ctx, int on);
 double rb_last_kernel_ms(rb_context* ctx, int which);
+/* Durations (ms) of the most recent launches of a kernel family, oldest first; returns how many were
+ * written (<= max_out, <= 64).  Synchronises on the last event. */
+int rb_kernel_ms_history(rb_context* ctx, int which, double* out_ms, int max_out);
 
 /* ---- line catalogs --------------------------------------------------------------------- *
  * Replaces the per-plugin npz readers: nh3_hs.py:62-67, nh3_sjs.py:17-23, h2s_ddb.py:14-39,
@@ -117,6 +123,7 @@ typedef struct rb_alpha_desc {
   int32_t coshape;                         /* 0 voigt, 1 vvw, 2 diff, 3 other (co_ddb.py:39-42) */
   int32_t units;                           /* RB_UNITS_* (parameters.py:4-8) */
   const double* scale;                     /* [C][L] per-constituent per-layer scale or NULL (alpha.py:151-192, 235-259) */
+  const double* freqs_host;                /* _dev calls only: optional HOST copy of freqs (saves one small D2H + sync) */
 } rb_alpha_desc;
 
 /* Alpha.get_layers (alpha.py:261-305): total absorption for every (layer, freq).
@@ -175,6 +182,13 @@ int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* geom, const rb_rt_d
  *   ds : [R][S] km host, nseg[R]; layer4ds is implicit 0..nseg-1 (raypath.py:222-225).          */
 int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int64_t n_rays, int32_t n_seg,
                     const double* ds, const int32_t* nseg, void* out_Tb, double* out_integrated_W);
+
+/* ---- measurement probes (bench.py / tests) ------------------------------------------------- */
+/* Sustained FP64 FMA rate of the device in TFLOP/s (2 flops per DFMA, 16 independent chains per thread,
+ * CUDA events): the roofline denominator of the FP64-bound kernels. */
+int rb_probe_fp64_peak(rb_context* ctx, int iters, double* out_tflops);
+/* y[i] = reciprocal of x[i] as the line loops compute it: MUFU.RCP64H seed + `newton` (0..2) Newton steps. */
+int rb_probe_rcp(rb_context* ctx, int newton, int n, const double* x, double* y);
 
 #ifdef __cplusplus
 }

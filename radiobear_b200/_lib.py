@@ -33,7 +33,7 @@ class AlphaDesc(C.Structure):
                 ('gas', C.c_void_p), ('gas_rows', C.c_int32), ('gas_col', C.c_int32 * RB_NUM_GAS),
                 ('cloud', C.c_void_p), ('cloud_rows', C.c_int32), ('cloud_col', C.c_int32 * RB_NUM_CLD),
                 ('cloud_flags', C.c_uint32), ('h2state', C.c_int32), ('coshape', C.c_int32),
-                ('units', C.c_int32), ('scale', C.c_void_p)]
+                ('units', C.c_int32), ('scale', C.c_void_p), ('freqs_host', C.c_void_p)]
 
 
 class GeometryDesc(C.Structure):
@@ -71,10 +71,12 @@ def load():
         'rb_destroy': (None, [vp]),
         'rb_last_error': (C.c_char_p, [vp]),
         'rb_set_stream': (C.c_int, [vp, vp]),
+        'rb_use_own_stream': (C.c_int, [vp]),
         'rb_synchronize': (C.c_int, [vp]),
         'rb_launch_count': (i64, [vp]),
         'rb_enable_timing': (C.c_int, [vp, C.c_int]),
         'rb_last_kernel_ms': (dbl, [vp, C.c_int]),
+        'rb_kernel_ms_history': (C.c_int, [vp, C.c_int, vp, C.c_int]),
         'rb_set_catalog': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
         'rb_alpha_layers': (C.c_int, [vp, C.POINTER(AlphaDesc), vp, vp]),
         'rb_alpha_layers_dev': (C.c_int, [vp, C.POINTER(AlphaDesc), vp, vp]),
@@ -82,6 +84,8 @@ def load():
         'rb_rt_batch': (C.c_int, [vp, C.POINTER(GeometryDesc), C.POINTER(RtDesc), i64, vp, vp, vp, i64, vp, vp, vp]),
         'rb_rt_batch_dev': (C.c_int, [vp, C.POINTER(GeometryDesc), C.POINTER(RtDesc), i64, vp, vp, vp]),
         'rb_rt_integrate': (C.c_int, [vp, C.POINTER(RtDesc), i32, i64, i32, vp, vp, vp, vp]),
+        'rb_probe_fp64_peak': (C.c_int, [vp, C.c_int, C.POINTER(dbl)]),
+        'rb_probe_rcp': (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -91,9 +95,11 @@ def load():
     return lib
 
 
-EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error', 'rb_set_stream', 'rb_synchronize',
-                    'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_set_catalog', 'rb_alpha_layers',
-                    'rb_alpha_layers_dev', 'rb_compute_ds', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate']
+EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error', 'rb_set_stream', 'rb_use_own_stream',
+                    'rb_synchronize',
+                    'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_set_catalog', 'rb_alpha_layers',
+                    'rb_alpha_layers_dev', 'rb_compute_ds', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
+                    'rb_probe_fp64_peak', 'rb_probe_rcp']
 
 _EXC = {RB_ERR_INVALID: ValueError, RB_ERR_CUDA: RadiobearB200Error, RB_ERR_NOMEM: MemoryError,
         RB_ERR_UNSUPPORTED: NotImplementedError}
@@ -143,7 +149,11 @@ class Context:
 
     # -- plumbing
     def set_stream(self, cuda_stream):
-        self.check(self.lib.rb_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """Launch on the given cudaStream_t handle (0 = the legacy default stream, e.g. torch's default)."""
+        self.check(self.lib.rb_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+
+    def use_own_stream(self):
+        self.check(self.lib.rb_use_own_stream(self.h))
 
     def synchronize(self):
         self.check(self.lib.rb_synchronize(self.h))
@@ -156,6 +166,22 @@ class Context:
 
     def last_kernel_ms(self, which):
         return float(self.lib.rb_last_kernel_ms(self.h, {'alpha': 0, 'geometry': 1, 'rt': 2}.get(which, which)))
+
+    def kernel_ms_history(self, which, n=64):
+        buf = np.zeros(n)
+        got = self.lib.rb_kernel_ms_history(self.h, {'alpha': 0, 'geometry': 1, 'rt': 2}.get(which, which), ptr(buf), n)
+        return buf[:got]
+
+    def fp64_peak_tflops(self, iters=20000):
+        out = C.c_double(0.0)
+        self.check(self.lib.rb_probe_fp64_peak(self.h, int(iters), C.byref(out)))
+        return out.value
+
+    def probe_rcp(self, x, newton):
+        x = f64(x)
+        y = np.empty_like(x)
+        self.check(self.lib.rb_probe_rcp(self.h, int(newton), x.size, ptr(x), ptr(y)))
+        return y
 
     def set_catalog(self, name, cols, key=None):
         """cols: [ncols][nlines] float64.  `key` lets callers skip re-uploads of an identical table."""

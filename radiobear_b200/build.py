@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libradiobear_b200.so')
-SOURCES = ['alpha_kernels.cu', 'rt_kernels.cu', 'capi.cu']
+SOURCES = ['alpha_kernels.cu', 'rt_kernels.cu', 'probe_kernels.cu', 'capi.cu']
 HEADERS = [os.path.join(CSRC, 'rb_common.cuh'), os.path.join(os.path.dirname(HERE), 'include', 'radiobear_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']

@@ -820,10 +820,10 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   RB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   dim3 grid(nblk_x, k.L);
   if (k.L > 65535) return rb_fail(ctx, RB_ERR_INVALID, "alpha: n_layers > 65535 not supported");
-  if (ctx->timing) RB_CUDA(ctx, cudaEventRecord(ctx->ev[0][0], ctx->stream));
+  RB_CUDA(ctx, rb_time_begin(ctx, 0));
   kern<<<grid, kThreads, smem_bytes, ctx->stream>>>(k);
   RB_CUDA(ctx, cudaGetLastError());
-  if (ctx->timing) { RB_CUDA(ctx, cudaEventRecord(ctx->ev[0][1], ctx->stream)); ctx->ev_valid[0] = true; }
+  RB_CUDA(ctx, rb_time_end(ctx, 0));
   ctx->launches += 1;
   return RB_OK;
 }

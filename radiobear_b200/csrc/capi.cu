@@ -72,7 +72,8 @@ int rb_create(int device, rb_context** out) {
   RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 2; ++j) RB_CUDA(ctx, cudaEventCreate(&ctx->ev[i][j]));
+    for (int r = 0; r < rb_context::kEvRing; ++r)
+      for (int j = 0; j < 2; ++j) RB_CUDA(ctx, cudaEventCreate(&ctx->ev[i][r][j]));
   return RB_OK;
 }
 
@@ -86,8 +87,9 @@ void rb_destroy(rb_context* ctx) {
     for (auto& c : ctx->cat)
       if (c) cudaFree(c);
     for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 2; ++j)
-        if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
+      for (int r = 0; r < rb_context::kEvRing; ++r)
+        for (int j = 0; j < 2; ++j)
+          if (ctx->ev[i][r][j]) cudaEventDestroy(ctx->ev[i][r][j]);
     cudaStreamDestroy(ctx->own_stream);
   }
   delete ctx;
@@ -97,7 +99,13 @@ const char* rb_last_error(const rb_context* ctx) { return ctx ? ctx->err.c_str()
 
 int rb_set_stream(rb_context* ctx, void* s) {
   if (!ctx) return RB_ERR_INVALID;
-  ctx->stream = s ? reinterpret_cast<cudaStream_t>(s) : ctx->own_stream;
+  ctx->stream = reinterpret_cast<cudaStream_t>(s);  // NULL = legacy default stream
+  return RB_OK;
+}
+
+int rb_use_own_stream(rb_context* ctx) {
+  if (!ctx) return RB_ERR_INVALID;
+  ctx->stream = ctx->own_stream;
   return RB_OK;
 }
 
@@ -115,12 +123,27 @@ int rb_enable_timing(rb_context* ctx, int on) {
   return RB_OK;
 }
 
-double rb_last_kernel_ms(rb_context* ctx, int which) {
-  if (!ctx || which < 0 || which > 2 || !ctx->ev_valid[which]) return -1.0;
+static double ring_ms(rb_context* ctx, int which, int64_t idx) {
+  const int r = (int)(idx % rb_context::kEvRing);
   float ms = 0.f;
-  if (cudaEventSynchronize(ctx->ev[which][1]) != cudaSuccess) return -1.0;
-  if (cudaEventElapsedTime(&ms, ctx->ev[which][0], ctx->ev[which][1]) != cudaSuccess) return -1.0;
+  if (cudaEventSynchronize(ctx->ev[which][r][1]) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, ctx->ev[which][r][0], ctx->ev[which][r][1]) != cudaSuccess) return -1.0;
   return ms;
+}
+
+double rb_last_kernel_ms(rb_context* ctx, int which) {
+  if (!ctx || which < 0 || which > 2 || ctx->ev_count[which] == 0) return -1.0;
+  return ring_ms(ctx, which, ctx->ev_count[which] - 1);
+}
+
+int rb_kernel_ms_history(rb_context* ctx, int which, double* out_ms, int max_out) {
+  if (!ctx || which < 0 || which > 2 || !out_ms || max_out <= 0) return 0;
+  int64_t n = ctx->ev_count[which];
+  if (n > rb_context::kEvRing) n = rb_context::kEvRing;
+  if (n > max_out) n = max_out;
+  const int64_t first = ctx->ev_count[which] - n;
+  for (int64_t i = 0; i < n; ++i) out_ms[i] = ring_ms(ctx, which, first + i);
+  return (int)n;
 }
 
 int rb_set_catalog(rb_context* ctx, int catalog, int nlines, int ncols, const double* cols) {
@@ -161,6 +184,7 @@ int rb_alpha_layers_dev(rb_context* ctx, const rb_alpha_desc* d, double* out_tot
   RB_TRY(check_alpha_desc(ctx, d, out_total));
   RB_CUDA(ctx, cudaSetDevice(ctx->device));
   // the frequency-class scan needs the (tiny) frequency list on the host
+  if (d->freqs_host) return rb_launch_alpha(ctx, d, d->freqs_host, out_total, out_cube);
   std::vector<double> hf(d->n_freqs);
   RB_CUDA(ctx, cudaMemcpyAsync(hf.data(), d->freqs, sizeof(double) * d->n_freqs, cudaMemcpyDeviceToHost, ctx->stream));
   RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -221,7 +245,7 @@ static int make_geometry(rb_context* ctx, const rb_geometry_desc* g, int64_t R, 
   out->rot[0] = cos(tip); out->rot[1] = sin(tip); out->rot[2] = cos(rotate); out->rot[3] = sin(rotate);
   out->limb = g->limb;
   out->R = R;
-  out->Rpad = (R + 3) & ~(int64_t)3;
+  out->Rpad = (R + 31) & ~(int64_t)31;
   return RB_OK;
 }
 
@@ -324,7 +348,7 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
     RB_CUDA(ctx, cudaMemsetAsync(p_prof, 0, 3 * F * S * 8 + F * 8, s));
     RtLaunch L1 = L;
     L1.R = 1; L1.Rpad = L.Rpad;
-    L1.ds = L.ds + profile_ray; L1.nseg = L.nseg + profile_ray; L1.nanflag = L.nanflag + profile_ray;
+    L1.ds = L.ds + ((size_t)(profile_ray >> 5) * S) * 32 + (size_t)(profile_ray & 31); L1.nseg = L.nseg + profile_ray; L1.nanflag = L.nanflag + profile_ray;
     L1.b = L.b + 2 * profile_ray;
     double* pp = (double*)p_prof;
     rd.out_f32 = 0;
@@ -345,7 +369,7 @@ int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int
   if (n_layers < 2 || n_seg != n_layers - 1) return rb_fail(ctx, RB_ERR_INVALID, "rt_integrate: n_seg must be n_layers - 1");
   RB_CUDA(ctx, cudaSetDevice(ctx->device));
   RtLaunch L{};
-  L.L = n_layers; L.R = R; L.Rpad = (R + 3) & ~(int64_t)3;
+  L.L = n_layers; L.R = R; L.Rpad = (R + 31) & ~(int64_t)31;
   const size_t nL = n_layers, S = n_seg, F = rt->n_freqs;
   const size_t esz = rt->out_f32 ? 4 : 8;
   void *p_in, *p_ds, *p_n, *p_alpha, *p_T, *p_tb, *p_iw = nullptr;

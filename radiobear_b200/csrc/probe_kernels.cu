@@ -1,0 +1,77 @@
+// radiobear_b200 -- measurement probes: the FP64 pipe peak (the roofline denominator of the two
+// compute-bound kernels; MEASURED_PEAKS.json has no FP64 entry) and the accuracy of the
+// MUFU.RCP64H + Newton reciprocal used in the line loops.
+#include "rb_common.cuh"
+
+namespace {
+
+// 16 independent DFMA chains per thread: enough ILP for the FP64 pipe at any occupancy
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fma(v[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+
+template <int NEWTON>
+__global__ void rcp_probe_kernel(const double* __restrict__ x, double* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = rb_rcp<NEWTON>(x[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rb_probe_fp64_peak(rb_context* ctx, int iters, double* out_tflops) {
+  if (!ctx || !out_tflops || iters <= 0) return rb_fail(ctx, RB_ERR_INVALID, "probe: bad arguments");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* p;
+  RB_TRY(rb_ensure(ctx, RB_BUF_MISC, 64, &p));
+  const int blocks = ctx->num_sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  RB_CUDA(ctx, cudaEventCreate(&e0));
+  RB_CUDA(ctx, cudaEventCreate(&e1));
+  fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)p, iters / 8 + 1, 0.999999, 1e-7);  // warm-up
+  RB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)p, iters, 0.999999, 1e-7);
+  RB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  RB_CUDA(ctx, cudaGetLastError());
+  RB_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  RB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ctx->launches += 2;
+  const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+  *out_tflops = flops / (ms * 1e-3) / 1e12;
+  return RB_OK;
+}
+
+int rb_probe_rcp(rb_context* ctx, int newton, int n, const double* x, double* y) {
+  if (!ctx || !x || !y || n <= 0) return rb_fail(ctx, RB_ERR_INVALID, "probe: bad arguments");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* p;
+  RB_TRY(rb_ensure(ctx, RB_BUF_MISC, (size_t)n * 16, &p));
+  double* dx = (double*)p;
+  double* dy = dx + n;
+  RB_CUDA(ctx, cudaMemcpyAsync(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = 256, blocks = (n + threads - 1) / threads;
+  if (newton == 0) rcp_probe_kernel<0><<<blocks, threads, 0, ctx->stream>>>(dx, dy, n);
+  else if (newton == 1) rcp_probe_kernel<1><<<blocks, threads, 0, ctx->stream>>>(dx, dy, n);
+  else rcp_probe_kernel<2><<<blocks, threads, 0, ctx->stream>>>(dx, dy, n);
+  RB_CUDA(ctx, cudaGetLastError());
+  RB_CUDA(ctx, cudaMemcpyAsync(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+}  // extern "C"

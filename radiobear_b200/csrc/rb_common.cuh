@@ -28,16 +28,31 @@ struct rb_context {
   int cat_n[RB_NUM_CATALOGS] = {0};
   int cat_cols[RB_NUM_CATALOGS] = {0};
   // grow-only scratch buffers
-  DevBuf buf[16];
+  DevBuf buf[20];
   // timing
   bool timing = false;
-  cudaEvent_t ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-  bool ev_valid[3] = {false, false, false};
+  static constexpr int kEvRing = 64;
+  cudaEvent_t ev[3][kEvRing][2] = {};
+  int64_t ev_count[3] = {0, 0, 0};
+  int ev_slot = 0;  // slot of the launch being timed
 };
+
+// record the start / stop event of one launch of kernel family `which` (no-ops unless timing is on)
+inline cudaError_t rb_time_begin(rb_context* ctx, int which) {
+  if (!ctx->timing) return cudaSuccess;
+  ctx->ev_slot = (int)(ctx->ev_count[which] % rb_context::kEvRing);
+  return cudaEventRecord(ctx->ev[which][ctx->ev_slot][0], ctx->stream);
+}
+inline cudaError_t rb_time_end(rb_context* ctx, int which) {
+  if (!ctx->timing) return cudaSuccess;
+  cudaError_t e = cudaEventRecord(ctx->ev[which][ctx->ev_slot][1], ctx->stream);
+  ctx->ev_count[which] += 1;
+  return e;
+}
 
 enum {
   RB_BUF_FREQS = 0, RB_BUF_T, RB_BUF_P, RB_BUF_GAS, RB_BUF_CLOUD, RB_BUF_SCALE, RB_BUF_TOTAL, RB_BUF_CUBE,
-  RB_BUF_RADIUS, RB_BUF_B, RB_BUF_DS, RB_BUF_NSEG, RB_BUF_TB, RB_BUF_INTW, RB_BUF_PROFILE, RB_BUF_MISC
+  RB_BUF_RADIUS, RB_BUF_B, RB_BUF_DS, RB_BUF_NSEG, RB_BUF_TB, RB_BUF_INTW, RB_BUF_PROFILE, RB_BUF_MISC, RB_BUF_PREP
 };
 
 int rb_fail(rb_context* ctx, int code, const char* fmt, ...);
@@ -73,7 +88,7 @@ struct RtLaunch {
   int64_t R;
   int64_t Rpad;
   const double* b;  // device [R][2]
-  double* ds;       // device slab [L-1][Rpad]
+  double* ds;       // device slab [Rpad/32][L-1][32] (tiled by 32 rays, see rt_kernels.cu)
   int32_t* nseg;    // device [R]
   int32_t* nanflag; // device [R]: ray carries a NaN segment the integration would use
 };

@@ -2,9 +2,10 @@
 // optical-depth / weighting-function / brightness-temperature integration (Brightness.single).
 //
 // Data layout in HBM
-//   ds slab   [S = L-1][Rpad]  float64, RAY index fastest: the geometry kernel (one thread per ray)
-//             writes it coalesced; the integration kernel reads 4 consecutive rays per thread with one
-//             32-byte load that the whole warp shares (lanes = frequencies).
+//   ds slab   [R/32][S = L-1][32]  float64, tiled by groups of 32 rays: the geometry kernel (one thread per
+//             ray) writes 256-byte rows coalesced, and the integration kernel (lanes = the same 32 rays)
+//             walks one contiguous 256 KB tile per block -- sequential in DRAM pages and inside one or two
+//             2 MB TLB pages (a plain [S][R] slab strides 2.9 MB per segment and thrashes the TLB).
 //   alpha slab [L][F] float64, FREQUENCY fastest (written by alpha_lines_kernel): a warp reads one
 //             256-byte row per segment, shared by all rays it carries; 0.5 MB at C4, lives in L2/L1.
 //   Tb        [R][F] float32 or float64, coalesced stores.
@@ -17,11 +18,18 @@
 // tests/test_ray_geometry.py checks it against the trigonometric oracle and the reference's vectors.
 #include "rb_common.cuh"
 #include <cmath>
+#include <climits>
 
 namespace {
 
 constexpr double kTcmb = 2.725;   // utils.py:77
 constexpr double kKmToCm = 1.0E5; // brightness.py:66
+
+// offset of (ray r, segment 0) in the tiled ds slab; consecutive segments of a ray are 32 doubles apart
+__host__ __device__ __forceinline__ size_t ds_tile_base(long long r, int S) {
+  return ((size_t)(r >> 5) * (size_t)S) * 32 + (size_t)(r & 31);
+}
+constexpr int kDsStride = 32;
 
 struct GeoK {
   int L;
@@ -149,7 +157,9 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
   int layer = 0;
   int count = 0;
   int first_nan = -1;
-  double* out = g.ds + r;
+  double* out = g.ds + ds_tile_base(r, S);
+  const double e2 = 1.0 - q2;
+  const double sin6 = 9.99999999999833333e-07, cos6 = 0.9999999999995;   // sin / cos of 1e-6 rad
   for (; layer < S; ++layer) {
     const double rNow = g.radius[layer] * shape;
     const double rNext = g.radius[layer + 1] * shape;
@@ -157,27 +167,39 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     double ds = -rdots - sqrt(rdots * rdots + rNext * rNext - rNow * rNow);
     if (ds < 0.0) break;  // raypath.py:212-216
     if (g.limb == RB_LIMB_SEC) ds = fabs(rNext - rNow) / mu;
-    out[(long long)layer * g.Rpad] = ds;
+    out[(size_t)layer * kDsStride] = ds;
     if (ds != ds && first_nan < 0) first_nan = layer;
     ++count;
-    // advance and re-evaluate latitude / normal at the new position (raypath.py:228-237)
+    // advance; shell shape factor at the new latitude: rmag/req = sqrt(q^2 sin^2 + cos^2) with
+    // sin lat = y/|r|  ->  sqrt(1 - (1 - q^2) y^2/|r|^2)                     (raypath.py:228-237)
     px += ds * sx; py += ds * sy; pz += ds * sz;
-    const double nr = sqrt(px * px + py * py + pz * pz);
-    v = py / nr;
-    lat_sc(v, s_lat, c_lat);
-    shape = sqrt(q2 * s_lat * s_lat + c_lat * c_lat);
-    // incidence on the next shell with nratio = 1: s += (cos(t_inc) - |cos(t_inc)|) n   (raypath.py:176-177, 257)
-    hs = sqrt(px * px + pz * pz);
-    sl = (hs > 0.0) ? px / hs : 0.0;
-    clng = (hs > 0.0) ? pz / hs : 1.0;
-    const double inv = 1.0 / sqrt(s_lat * s_lat + q2 * c_lat * c_lat);
-    nx = g.q * c_lat * sl * inv;
-    ny = s_lat * inv;
-    nz = g.q * c_lat * clng * inv;
-    const double ci = -(sx * nx + sy * ny + sz * nz);
-    if (!(ci >= 0.0)) {  // ci < 0 (or NaN): the reference's asin/acos pair flips the normal component
+    const double nr2 = px * px + py * py + pz * pz;
+    if (py == 0.0) shape = sqrt(q2 * sin6 * sin6 + cos6 * cos6);           // lat == 0 -> 1e-6 (shape.py:231-233)
+    else shape = sqrt(1.0 - e2 * (py * py) / nr2);
+    // incidence on the next shell with nratio = 1 (raypath.py:176-177, 246, 257): the reference's
+    // arccos / arcsin pair gives s += (cos t_inc - |cos t_inc|) n, i.e. nothing unless cos t_inc < 0.
+    // n is parallel to (q x, y, q z) (the normal of the ellipse of parameter lat at longitude lng),
+    // so only the sign of s.(q x, y, q z) has to be looked at in the common case.
+    double d;
+    if (py == 0.0) {
+      const double hxz = sqrt(px * px + pz * pz);
+      d = g.q * cos6 * (sx * px + sz * pz) / hxz + sy * sin6;
+    } else {
+      d = g.q * (sx * px + sz * pz) + sy * py;
+    }
+    if (!(d <= 0.0)) {  // cos(t_inc) < 0 (or NaN): grazing ray, rare
+      double ux, uy, uz;
+      if (py == 0.0) {
+        const double hxz = sqrt(px * px + pz * pz);
+        ux = g.q * cos6 * px / hxz; uy = sin6; uz = g.q * cos6 * pz / hxz;
+      } else {
+        ux = g.q * px; uy = py; uz = g.q * pz;
+      }
+      const double inv = 1.0 / sqrt(ux * ux + uy * uy + uz * uz);
+      ux *= inv; uy *= inv; uz *= inv;
+      const double ci = -(sx * ux + sy * uy + sz * uz);
       const double w = (fabs(ci) > 1.0) ? nan("") : 2.0 * ci;
-      sx += w * nx; sy += w * ny; sz += w * nz;
+      sx += w * ux; sy += w * uy; sz += w * uz;
     }
   }
   g.nseg[r] = count;
@@ -194,7 +216,7 @@ __global__ void ds_transpose_kernel(const double* __restrict__ slab, long long R
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int s = s0 + j;
     const long long r = r0 + threadIdx.x;
-    tile[j][threadIdx.x] = (s < S && r < R) ? slab[(long long)s * Rpad + r] : 0.0;
+    tile[j][threadIdx.x] = (s < S && r < R) ? slab[ds_tile_base(r, S) + (size_t)s * kDsStride] : 0.0;
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -224,7 +246,7 @@ __global__ void ds_to_slab_kernel(const double* __restrict__ in, long long R, lo
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int s = s0 + j;
     const long long r = r0 + threadIdx.x;
-    if (s < S && r < Rpad) slab[(long long)s * Rpad + r] = tile[threadIdx.x][j];
+    if (s < S && r < Rpad) slab[ds_tile_base(r, S) + (size_t)s * kDsStride] = tile[threadIdx.x][j];
   }
 }
 
@@ -273,6 +295,7 @@ struct RtK {
   long long R, Rpad;
   const double* alpha;  // [L][F]
   const double* T;      // [L]
+  const double4* prep;  // [F/8][L-1][8] interleaved loop operands (rays-major kernel only, see rt_prepare_kernel)
   const double* ds;     // [S][Rpad]
   const int* nseg;      // [R]
   const int* nanflag;   // [R]
@@ -320,13 +343,8 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
     const double a1 = k.alpha[(size_t)(i + 1) * k.F + f];
     const double T1 = k.T[i + 1];
     double dsv[RPT];
-    if constexpr (RPT == 4) {
-      const double4 d4 = *reinterpret_cast<const double4*>(k.ds + (size_t)i * k.Rpad + r0);
-      dsv[0] = d4.x; dsv[1] = d4.y; dsv[2] = d4.z; dsv[3] = d4.w;
-    } else {
 #pragma unroll
-      for (int j = 0; j < RPT; ++j) dsv[j] = k.ds[(size_t)i * k.Rpad + r0 + j];
-    }
+    for (int j = 0; j < RPT; ++j) dsv[j] = k.ds[ds_tile_base(r0 + j, S) + (size_t)i * kDsStride];
     const double asum = a0 + a1;
     bool live = false;
 #pragma unroll
@@ -367,6 +385,183 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
   }
 }
 
+// ---- exp(-tau) for the weighting function ------------------------------------------------------------
+// tau >= 0.  exp(-tau) = 2^k * 2^(j/1024) * exp(r) with -tau*1024*log2(e) = 1024 k + j + 1024 r/ln2,
+// |r| <= ln2/2048 = 3.4e-4, exp(r) by a degree-3 Taylor polynomial (remainder r^4/24 < 5.6e-16), the
+// 2^(j/1024) table (8 KB) in shared memory.  Branch-free, 7 FP64 instructions (libdevice exp() costs ~25
+// with its special-case paths); relative error ~1e-15, far inside the 0.01 K bar (tests hold 1e-4 K).
+// tau beyond the underflow point gives exactly 0; NaN is handled by the caller.  The constants are fetched
+// once per thread into registers (see pin()).
+constexpr int kExpTab = 1024;
+__device__ double c_expc[8] = {
+    -1477.3197218702985,      // -1024 log2(e)
+    6755399441055744.0,       // 2^52 + 2^51: adding it rounds to the nearest integer (kept in the low word)
+    -6.7690154351557157e-4,   // -ln2/1024
+    1.6666666666666666e-1,    // 1/6
+    0.5, 1.0, 0.0, 0.0};
+
+// per-(layer, freq) operands of the integration loop, hoisted out of the per-ray work and interleaved so
+// that one 32-byte shared-memory read fetches them (kHalfCm = 0.5 * 1e5 folds ds [km] -> ds/2 [cm],
+// brightness.py:66).  Grouped by blocks of 8 frequencies so that the operands one CTA needs for a chunk
+// of segments are contiguous in HBM:
+//   prep[fg][i][fl] = { (a_i + a_i+1) kHalfCm,  a_i+1 kHalfCm,  T_i+1 a_i+1 kHalfCm,  0 }
+//   f = 8 fg + fl,  i = 0 .. L-2,  zero for f >= F
+__global__ void rt_prepare_kernel(const double* __restrict__ alpha, const double* __restrict__ T, int L, int F,
+                                  int ngroups, double4* __restrict__ prep) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Lm1 = L - 1;
+  if (idx >= ngroups * Lm1 * 8) return;
+  const int fl = idx & 7;
+  const int i = (idx >> 3) % Lm1;
+  const int fg = (idx >> 3) / Lm1;
+  const int f = fg * 8 + fl;
+  double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
+  if (f < F) {
+    const double kHalfCm = 0.5 * kKmToCm;
+    const double a0 = alpha[(size_t)i * F + f], a1 = alpha[(size_t)(i + 1) * F + f];
+    v = make_double4((a0 + a1) * kHalfCm, a1 * kHalfCm, (T[i + 1] * a1) * kHalfCm, 0.0);
+  }
+  prep[idx] = v;
+}
+
+// fetch a loop-invariant FP64 constant into a register pair with a plain global load: ptxas cannot
+// re-materialise that inside the loop (it does so for immediates and constant-bank values with
+// UMOV + MOV / LDC, which costs issue slots in this issue-bound kernel)
+__device__ __forceinline__ double pin(const double* p) {
+  double x;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(x) : "l"(p));
+  return x;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// thread = (ray, frequency); lanes = 32 consecutive rays; the CTA's 8 warps are the 8 frequencies of one
+// frequency group, all working on the same 32 rays.  Both operand streams are staged through shared memory
+// in chunks of kChunk segments with cp.async (LDGSTS), three buffers deep:
+//   ds tile    (kChunk+1) x 32 doubles   -- one contiguous piece of the tiled ds slab
+//   prep tile   kChunk x 8 double4       -- one contiguous piece of the grouped operand slab
+// so the segment loop only touches shared memory (LDS latency, no scoreboard-limited global loads in flight)
+// and HBM / L2 latency is covered two chunks ahead.  One __syncthreads_or per chunk both publishes the
+// landed chunk and tells the CTA when every (ray, freq) has finished (tau > tau_cut or out of segments).
+// Frequency groups of one ray group are adjacent in launch order (blockIdx.x) so they share the ds tile
+// through L2.  The trapezoid sums are regrouped by node:
+//   sum_i (W_i+1 + W_i) h_i = sum_j W_j (h_j-1 + h_j),  W_0 = 0.
+// FP64 work per (ray, freq, segment): 1 (tau) + 9 (exp) + 1 (ds_i + ds_i+1) + 3 (weights) = 14 instructions.
+constexpr int kChunk = 32;
+constexpr int kStages = 2;
+constexpr int kTileDs = (kChunk + 1) * 32;   // doubles per ds tile
+constexpr int kTilePp = kChunk * 8;          // double4 per operand tile
+constexpr size_t kRaysSmemBytes = kStages * (kTileDs * sizeof(double) + kTilePp * sizeof(double4));
+
+__global__ void __launch_bounds__(256) rt_integrate_rays_kernel(const __grid_constant__ RtK k) {
+  __shared__ double s_tab[kExpTab];                        // 2^(j/1024)
+  __shared__ __align__(16) double s_ds[kStages * kTileDs];
+  __shared__ __align__(16) double4 s_pp[kStages * kTilePp];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int t = tid; t < kExpTab; t += 256) s_tab[t] = exp2((double)t / (double)kExpTab);
+
+  const int S = k.L - 1;
+  const long long r = (long long)blockIdx.y * 32 + threadIdx.x;
+  const int f = blockIdx.x * 8 + threadIdx.y;
+  const bool valid = (r < k.R) && (f < k.F);
+  const int n = valid ? k.nseg[r] : -1;
+  const bool nanray = valid && k.nanflag[r] != 0;
+  const int steps = (valid && !nanray) ? n - 1 : 0;        // brightness.py:65: i = 0 .. len(ds)-2
+  const double* tile_ds = k.ds + (size_t)blockIdx.y * S * 32;
+  const double4* tile_pp = k.prep + (size_t)blockIdx.x * S * 8;
+
+  auto issue = [&](int c) {
+    const int row0 = c * kChunk;
+    const int buf = c % kStages;
+    // ds rows row0 .. row0 + kChunk: 16 pieces of 16 B per row
+    for (int q = tid; q < (kChunk + 1) * 16; q += 256)
+      if (row0 + (q >> 4) < S) cp_async16(s_ds + buf * kTileDs + q * 2, tile_ds + (size_t)row0 * 32 + q * 2);
+    // operand rows row0 .. row0 + kChunk - 1: 16 pieces of 16 B per row
+    for (int q = tid; q < kChunk * 16; q += 256)
+      if (row0 + (q >> 4) < S)
+        cp_async16(reinterpret_cast<double*>(s_pp + buf * kTilePp) + q * 2,
+                   reinterpret_cast<const double*>(tile_pp + (size_t)row0 * 8) + q * 2);
+    cp_async_commit();
+  };
+  issue(0);
+
+  const double cA = pin(c_expc + 0), cM = pin(c_expc + 1), cL = pin(c_expc + 2), c3 = pin(c_expc + 3),
+               c2 = pin(c_expc + 4), c1 = pin(c_expc + 5);
+  // 32-bit shared-window address of the table, computed once (ptxas otherwise re-derives the CTA's shared
+  // window base with S2UR / UMOV / ULEA in every iteration)
+  unsigned tab_base;
+  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(tab_base) : "l"(s_tab));
+  // tau > tau_cut  <=>  round(-tau * 1024 log2 e) < ni_cut: an integer compare instead of an FP64 one
+  const double cutd = k.tau_cut * 1477.3197218702985;
+  const int ni_cut = (cutd < 2.0e9) ? -(int)cutd : INT_MIN;
+  double tau = 0.0, iW = 0.0, Tb = 0.0;
+  bool live = steps > 0;
+  int i = 0;
+  for (int c = 0;; ++c) {
+    cp_async_wait<0>();                                    // this thread's pieces of chunk c have landed
+    if (!__syncthreads_or(live)) break;                    // ... everybody's have; chunk c-1 is fully consumed
+    issue(c + 1);                                          // refill the buffer chunk c-1 used
+    if (live) {
+      double* dsb = s_ds + (c % kStages) * kTileDs + threadIdx.x;
+      const double4* ppb = s_pp + (c % kStages) * kTilePp + threadIdx.y;
+      // nothing lies below the last node: make ds_steps read as 0 in this tile (the 8 warps of the ray all
+      // store the same 0 before their own read of it)
+      const int zrow = steps - c * kChunk;
+      if (zrow <= kChunk) dsb[zrow * 32] = 0.0;
+      const int m = min(kChunk, steps - i);
+      double d0 = dsb[0];
+#pragma unroll 4
+      for (int u = 0; u < m; ++u) {
+        const double d1 = dsb[(u + 1) * 32];
+        const double4 q = ppb[u * 8];
+        tau = fma(q.x, d0, tau);                           // dtau = (a_i + a_i+1) ds / 2
+        // e = exp(-tau): 2^k 2^(j/1024) exp(rr)
+        double nd = fma(tau, cA, cM);
+        const int ni = __double2loint(nd);
+        nd -= cM;
+        const double rr = fma(nd, cL, -tau);
+        double p = fma(rr, c3, c2);
+        p = fma(p, rr, c1);
+        p = fma(p, rr, c1);
+        double tj;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_base + ((ni & (kExpTab - 1)) << 3)));
+        const double v = p * tj;
+        const double sc = __hiloint2double(__double2hiint(v) + ((ni >> 10) << 20), __double2loint(v));
+        // underflow (or tau so large that ni wrapped): nd <= -2^20 + 2^11 <=> 2^k below the normal range -> e = 0
+        const double e = ((unsigned)__double2hiint(nd) > 0xC12FF000u) ? 0.0 : sc;
+        const double w = e * (d0 + d1);                    // e^-tau (ds_i + ds_i+1)
+        iW = fma(q.y, w, iW);
+        Tb = fma(q.z, w, Tb);
+        d0 = d1;
+        if (ni < ni_cut) {                                 // tau > tau_cut
+          i = steps;
+          break;
+        }
+      }
+      i += m;
+      live = i < steps;
+    }
+  }
+  cp_async_wait<0>();
+  if (!valid) return;
+  double vout, wout = iW;
+  if (n < 0) vout = kTcmb;                                 // off planet (brightness.py:46-51)
+  else if (nanray || tau != tau) vout = wout = nan("");    // NaN segment below the tangent shell / NaN alpha
+  else vout = (Tb < kTcmb) ? kTcmb : Tb / iW;              // brightness.py:109-113
+  const size_t o = (size_t)r * k.F + f;
+  if (k.out_f32) reinterpret_cast<float*>(k.out_Tb)[o] = (float)vout;
+  else reinterpret_cast<double*>(k.out_Tb)[o] = vout;
+  if (k.out_intW) k.out_intW[o] = (n < 0) ? 0.0 : wout;
+}
+
 }  // namespace
 
 int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
@@ -376,10 +571,10 @@ int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
   k.limb = g.limb; k.R = g.R; k.Rpad = g.Rpad; k.b = g.b; k.ds = g.ds; k.nseg = g.nseg; k.nanflag = g.nanflag;
   const int threads = 128;
   const long long blocks = (g.R + threads - 1) / threads;
-  if (ctx->timing) RB_CUDA(ctx, cudaEventRecord(ctx->ev[1][0], ctx->stream));
+  RB_CUDA(ctx, rb_time_begin(ctx, 1));
   ray_geometry_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(k);
   RB_CUDA(ctx, cudaGetLastError());
-  if (ctx->timing) { RB_CUDA(ctx, cudaEventRecord(ctx->ev[1][1], ctx->stream)); ctx->ev_valid[1] = true; }
+  RB_CUDA(ctx, rb_time_end(ctx, 1));
   ctx->launches += 1;
   return RB_OK;
 }
@@ -412,25 +607,33 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
   k.tau_cut = (rt->tau_cut > 0.0) ? rt->tau_cut : INFINITY;
   k.profile_ray = profile_ray; k.out_tau = out_tau; k.out_W = out_W; k.out_Tblyr = out_Tblyr;
   const int fgroups = (k.F + 31) / 32;
-  if (ctx->timing) RB_CUDA(ctx, cudaEventRecord(ctx->ev[2][0], ctx->stream));
+  RB_CUDA(ctx, rb_time_begin(ctx, 2));
   if (profile_ray >= 0) {
     if (g.R != 1) return rb_fail(ctx, RB_ERR_INVALID, "rt: profile outputs need a single-ray launch");
     dim3 grid(1, fgroups), block(32, 1);
     if (k.disc) rt_integrate_kernel<1, true, true><<<grid, block, 0, ctx->stream>>>(k);
     else rt_integrate_kernel<1, false, true><<<grid, block, 0, ctx->stream>>>(k);
-  } else if (k.disc || g.R < 4096) {
+  } else if (k.disc || g.R < 512) {
     const int wy = 4;
     dim3 grid((unsigned)((g.R + wy - 1) / wy), fgroups), block(32, wy);
     if (k.disc) rt_integrate_kernel<1, true, false><<<grid, block, 0, ctx->stream>>>(k);
     else rt_integrate_kernel<1, false, false><<<grid, block, 0, ctx->stream>>>(k);
   } else {
-    const int wy = 4;
-    const long long groups = (g.R + 3) / 4;
-    dim3 grid((unsigned)((groups + wy - 1) / wy), fgroups), block(32, wy);
-    rt_integrate_kernel<4, false, false><<<grid, block, 0, ctx->stream>>>(k);
+    // rays-major mapping: blocks of 32 rays x 8 frequencies; per-(layer,freq) operands prepared once
+    const int ngroups = (k.F + 7) / 8;
+    void* scratch;
+    RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (k.L - 1) * 8 * sizeof(double4), &scratch));
+    const int nel = ngroups * (k.L - 1) * 8;
+    rt_prepare_kernel<<<(nel + 255) / 256, 256, 0, ctx->stream>>>(k.alpha, k.T, k.L, k.F, ngroups, (double4*)scratch);
+    k.prep = (const double4*)scratch;
+    dim3 block(32, 8), grid(ngroups, (unsigned)((g.R + 31) / 32));
+    if (grid.y > 65535) return rb_fail(ctx, RB_ERR_INVALID, "rt: more than 2M rays per call are not supported");
+    static_assert(kExpTab * sizeof(double) + kRaysSmemBytes <= 48 * 1024, "static shared memory limit");
+    rt_integrate_rays_kernel<<<grid, block, 0, ctx->stream>>>(k);
+    ctx->launches += 1;
   }
   RB_CUDA(ctx, cudaGetLastError());
-  if (ctx->timing) { RB_CUDA(ctx, cudaEventRecord(ctx->ev[2][1], ctx->stream)); ctx->ev_valid[2] = true; }
+  RB_CUDA(ctx, rb_time_end(ctx, 2));
   ctx->launches += 1;
   return RB_OK;
 }

@@ -21,12 +21,13 @@ class Data:
         if par not in self.allowed_parameters:
             print("{} not in valid data return list.".format(par))
             return
-        val = copy.copy(val)
+        if not isinstance(val, np.ndarray):      # arrays are adopted as-is (a 92 MB image cube is not copied)
+            val = copy.copy(val)
         if par == 'b' and not isinstance(val, np.ndarray) and utils.b_type(val).startswith('dis'):
             self.b = ['disc']
         elif isinstance(val, list):
             setattr(self, par, np.asarray(val, dtype=np.float32))
-        elif par == 'Tb' and isinstance(val, np.ndarray):
+        elif par in ('Tb', 'b') and isinstance(val, np.ndarray):
             setattr(self, par, val.astype(np.float32, copy=False))
         else:
             setattr(self, par, val)

@@ -15,6 +15,48 @@ from ._lib import (AlphaDesc, GeometryDesc, RtDesc, FORMALISM_IDS, GAS_ORDER, CL
                    RB_MAX_CONSTITUENTS, f64, ptr)
 
 T_CMB = 2.725
+
+
+class PinnedPool:
+    """Page-locked host result buffers (torch pinned tensors when torch + a GPU are there).
+
+    A buffer is handed out as a numpy view and re-used only after the caller dropped every view of it
+    (every view keeps a reference to the root array, so its refcount tells), so results of earlier runs
+    are never overwritten behind the user's back, while steady-state loops pay neither a 92 MB
+    allocation nor a pageable-memory D2H."""
+
+    def __init__(self, pin=True):
+        self._roots = []     # root uint8 arrays (each keeps its pinned tensor alive)
+        self._pin = pin
+
+    def _alloc(self, nbytes):
+        if self._pin:
+            try:
+                import torch
+                return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True).numpy()
+            except (ImportError, RuntimeError):
+                pass
+        return np.empty(nbytes, dtype=np.uint8)
+
+    def get(self, shape, dtype):
+        import sys
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if nbytes < (1 << 20):
+            return np.empty(shape, dtype=dtype)
+        root = None
+        for r in self._roots:
+            # refs: the list, the loop variable, getrefcount's argument -> 3 means nobody else holds a view
+            if r.size >= nbytes and sys.getrefcount(r) <= 3:
+                root = r
+                break
+        if root is None:
+            self._roots = [r for r in self._roots if sys.getrefcount(r) > 3][-3:]
+            root = self._alloc(nbytes)
+            self._roots.append(root)
+        return root[:nbytes].view(dtype).reshape(shape)
+
+
+pinned_pool = PinnedPool()
 UNITS = {'invcm': 0, 'dBperkm': 1}
 COSHAPE = {'voigt': 0, 'vvw': 1, 'diff': 2}
 
@@ -109,6 +151,7 @@ def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formal
     Replaces the layer loop of Alpha.get_layers (alpha.py:298-300) and the plugin calls under it.
     """
     ctx = ctx or _lib.get_context()
+    ctx.use_own_stream()
     freqs, T, P = f64(np.atleast_1d(freqs)), f64(np.atleast_1d(T)), f64(np.atleast_1d(P))
     gas = f64(gas)
     if gas.ndim == 1:
@@ -137,7 +180,7 @@ def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formal
 
 def alpha_layers_dev(freqs_t, T_t, P_t, gas_t, gas_dict, cloud_t=None, cloud_dict=None, formalisms=(), other_dicts=None,
                      units='invcm', scale_t=None, want_cube=False, truncate_strength=None, truncate_freq=None, ctx=None,
-                     out=None):
+                     out=None, freqs_host=None):
     """Device-resident variant: torch float64 CUDA tensors in, slab[L][F] CUDA tensor out (async)."""
     import torch
     ctx = ctx or _lib.get_context()
@@ -151,6 +194,9 @@ def alpha_layers_dev(freqs_t, T_t, P_t, gas_t, gas_dict, cloud_t=None, cloud_dic
     d.freqs, d.T, d.P, d.gas = freqs_t.data_ptr(), T_t.data_ptr(), P_t.data_ptr(), gas_t.data_ptr()
     d.cloud = cloud_t.data_ptr() if cloud_t is not None else None
     d.scale = scale_t.data_ptr() if scale_t is not None else None
+    if freqs_host is not None:
+        freqs_host = f64(freqs_host)
+        d.freqs_host = ptr(freqs_host)
     total = out if out is not None else torch.empty((L, F), dtype=torch.float64, device=T_t.device)
     cube = torch.empty((L, F, len(formalisms)), dtype=torch.float64, device=T_t.device) if want_cube else None
     ctx.set_stream(torch.cuda.current_stream(T_t.device).cuda_stream)
@@ -178,6 +224,7 @@ def build_geometry_desc(L, n0, n1, Req, Rpol, orientation, gtype, limb):
 def compute_ds(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None):
     """raypath.compute_ds for a batch of impact points.  Returns ds[R][L-1], nseg[R], (tip, rotate, rNorm)."""
     ctx = ctx or _lib.get_context()
+    ctx.use_own_stream()
     radius = f64(radius)
     b = f64(np.atleast_2d(b))
     R, L = b.shape[0], radius.shape[0]
@@ -194,6 +241,7 @@ def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 
              disc_average=False, out_f32=False, tau_cut=100.0, want_intW=False, profile_ray=-1, ctx=None, out=None):
     """Brightness.single over a batch of rays: Tb[R][F] (+ integrated_W, + profiles of one ray)."""
     ctx = ctx or _lib.get_context()
+    ctx.use_own_stream()
     radius, T = f64(radius), f64(T)
     alpha_slab = f64(alpha_slab)
     b = f64(np.atleast_2d(b))
@@ -206,7 +254,7 @@ def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 
     rt.n_freqs, rt.alpha, rt.T = F, ptr(alpha_slab), ptr(T)
     rt.disc_average, rt.out_f32, rt.tau_cut = int(bool(disc_average)), int(bool(out_f32)), float(tau_cut or 0.0)
     if out is None:
-        out = np.empty((R, F), dtype=np.float32 if out_f32 else np.float64)
+        out = pinned_pool.get((R, F), np.float32 if out_f32 else np.float64)
     intW = np.empty((R, F)) if want_intW else None
     prof = None
     if profile_ray >= 0:
@@ -243,6 +291,7 @@ def rt_batch_dev(radius_t, n0, n1, b_t, alpha_t, T_t, Req, Rpol, orientation=(0.
 def rt_integrate(ds, nseg, alpha_slab, T, disc_average=False, out_f32=False, tau_cut=100.0, want_intW=False, ctx=None):
     """Integration only, for caller-supplied segments ds[R][L-1] (km)."""
     ctx = ctx or _lib.get_context()
+    ctx.use_own_stream()
     ds = f64(np.atleast_2d(ds))
     alpha_slab, T = f64(alpha_slab), f64(T)
     R, S = ds.shape

@@ -89,3 +89,55 @@ def all_gather_freq_blocks(local_slab, parts, group=None):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([bufs[i][:, :widths[i]] for i in range(world)], dim=1).contiguous()
+
+
+def world_rank():
+    """(world_size, rank) of the default process group; (1, 0) when torch.distributed is not initialised."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), dist.get_rank()
+    except ImportError:
+        pass
+    return 1, 0
+
+
+def run_points_sharded(planet, pts, atm, alpha, out_f32=True, rows=None):
+    """Brightness temperatures of impact points pts[R][2] computed by all ranks of the process group.
+
+    Each rank takes a contiguous block (image rows balanced by on-disc pixels when `rows` = (grid, ncol)
+    is given, else an even split), runs geometry + integration on its own GPU from device-resident
+    inputs, then one gather over NCCL/NVLink brings the blocks to rank 0, which copies the result to
+    (pinned) host memory.  Returns Tb[R][F] on rank 0 and None on the other ranks."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    world, rank = world_rank()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    cfg = atm.config
+    if rows is not None:
+        grid, ncol = rows
+        rparts = partition_rows(grid, cfg.Rpol / cfg.Req if cfg.gtype == 'ellipse' else 1.0, world)
+        parts = [(a * ncol, b * ncol) for a, b in rparts]
+    else:
+        parts = partition_even(len(pts), world)
+    s, e = parts[rank]
+    radius = torch.as_tensor(np.ascontiguousarray(atm.property[cfg.LP['R']]), device=dev)
+    nidx = atm.property[cfg.LP['N']]
+    T_t = torch.as_tensor(np.ascontiguousarray(atm.gas[cfg.C['T']]), device=dev)
+    slab_t = torch.as_tensor(np.ascontiguousarray(alpha.slab), device=dev)
+    F = slab_t.shape[1]
+    if e > s:
+        b_t = torch.as_tensor(np.ascontiguousarray(pts[s:e], dtype=np.float64), device=dev)
+        local = engine.rt_batch_dev(radius, nidx[0], nidx[1], b_t, slab_t, T_t, cfg.Req, cfg.Rpol,
+                                    [float(cfg.orientation[0]), float(cfg.orientation[1])], cfg.gtype,
+                                    getattr(cfg, 'limb', 'shape'), out_f32=out_f32)
+    else:
+        local = torch.empty((0, F), dtype=torch.float32 if out_f32 else torch.float64, device=dev)
+    full = gather_blocks(local, parts, dst=0)
+    if rank != 0:
+        return None
+    out = engine.pinned_pool.get(tuple(full.shape), np.float32 if out_f32 else np.float64)
+    host = torch.from_numpy(out)
+    host.copy_(full, non_blocking=False)
+    return out

@@ -18,6 +18,7 @@ from . import brightness as rbbright
 from . import config as pcfg
 from . import data_handling
 from . import logging as rblog
+from . import parallel
 from . import set_utils
 from . import utils
 
@@ -177,14 +178,23 @@ class Planet:
             which = np.array([self.map_b_to_atm(list(p)) for p in pts]) if \
                 getattr(self.config, 'bmapmodule', 'nobmap') not in (None, 'nobmap') else np.zeros(len(pts), dtype=int)
             f32 = self.data_type == 'image'
-            Tb = np.empty((len(pts), F), dtype=np.float32 if f32 else np.float64)
-            for j in np.unique(which):
-                sel = np.nonzero(which == j)[0]
-                res = self.bright.batch(pts[sel], self.freqs, self.atmos[j], self.alpha[j], self.config.orientation,
-                                        out_f32=f32)
-                Tb[sel] = res['Tb']
+            world, rank = parallel.world_rank()
+            if world > 1 and len(pts) >= 64 * world and not which.any():
+                # one process per GPU: shard rows / points, gather to rank 0 (None on the other ranks)
+                rows = (np.unique(pts[:, 1]), self.imSize[0]) if self.data_type == 'image' else None
+                Tb = parallel.run_points_sharded(self, pts, self.atmos[0], self.alpha[0], out_f32=f32, rows=rows)
+            elif not which.any():
+                Tb = self.bright.batch(pts, self.freqs, self.atmos[0], self.alpha[0], self.config.orientation,
+                                       out_f32=f32)['Tb']
+            else:
+                Tb = np.empty((len(pts), F), dtype=np.float32 if f32 else np.float64)
+                for j in np.unique(which):
+                    sel = np.nonzero(which == j)[0]
+                    res = self.bright.batch(pts[sel], self.freqs, self.atmos[j], self.alpha[j],
+                                            self.config.orientation, out_f32=f32)
+                    Tb[sel] = res['Tb']
         runStop = datetime.datetime.now()
-        if self.data_type == 'image':
+        if self.data_type == 'image' and Tb is not None:
             ncol, nrow = self.imSize[0], len(self.b) // self.imSize[0]
             Tb = Tb.reshape(nrow, ncol, F)
             if F == 1:
@@ -195,7 +205,7 @@ class Planet:
         self.set_header(runStart, runStop)
         self.data_return.set('start', runStart)
         self.data_return.set('stop', runStop)
-        self.data_return.set('Tb', np.asarray(self.Tb))
+        self.data_return.set('Tb', None if self.Tb is None else np.asarray(self.Tb))
         self.data_return.set('type', self.data_type)
         self.data_return.set('header', self.header)
         if self.log is not None:

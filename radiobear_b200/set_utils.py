@@ -86,7 +86,8 @@ def set_b(b, block=(1, 1), **kwargs):
         last = 0 if nblk == 1 else block[0] / nblk
         first = int((block[0] - 1) * bsplit)
         rows = [first + i for i in range(int(bsplit + last)) if first + i < len(grid)]
-        rv.b = [[vcol, grid[ii]] for ii in rows for vcol in grid]
+        # [R][2] array (x fastest, rows of constant y) -- indexable like the reference's list of pairs
+        rv.b = np.stack([np.tile(grid, len(rows)), np.repeat(grid[rows], len(grid))], axis=1)
         rv.imSize = [len(grid), len(rows)]
         rv.data_type = 'image'
         return rv

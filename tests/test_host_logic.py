@@ -37,7 +37,7 @@ def test_set_b_forms():
     assert abs(r.b[0][1] - 0.1) < 1e-15 and abs(r.b[0][0]) < 1e-16
     r = set_utils.set_b(0.005)                                   # float image request crashes in the reference
     assert r.data_type == 'image' and r.imSize == [601, 601] and len(r.b) == 601 * 601
-    assert r.b[0] == [-1.5, -1.5] and r.b[1][1] == -1.5          # rows of constant y, x fastest
+    assert list(r.b[0]) == [-1.5, -1.5] and r.b[1][1] == -1.5 and abs(r.b[1][0] + 1.495) < 1e-12   # rows of constant y, x fastest
     r2 = set_utils.set_b(0.005, block=[2, 4])
     assert r2.imSize[0] == 601 and len(r2.b) == 601 * r2.imSize[1]
     r = set_utils.set_b('stamp:0.1:-0.2,0.2,-0.1,0.1')
