@@ -68,45 +68,48 @@ __device__ __forceinline__ void lat_sc(double v, double& s, double& c) {
 // one thread per ray
 __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant__ GeoK g) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= g.R) return;
+  const bool inrange = r < g.R;
   const int S = g.L - 1;
-  const double bx = g.b[2 * r], by = g.b[2 * r + 1];
+  const double bx = inrange ? g.b[2 * r] : 2.0, by = inrange ? g.b[2 * r + 1] : 2.0;
   const double bb = bx * bx + by * by;
-  g.nanflag[r] = 0;
-  if (!(bb < 1.0)) {  // raypath.py:126-127 (NaN impact parameters also miss)
-    g.nseg[r] = -1;
-    return;
-  }
   const double q2 = g.q * g.q;
   const double rNorm = g.radius[0];
-  const double mu = sqrt(1.0 - bx * bx - by * by);
+  const double mu = sqrt(fmax(0.0, 1.0 - bx * bx - by * by));
 
   // ---- findEdge (raypath.py:60-105): march zQ down by 0.005 until inside the outer shell --------
-  const double z0 = sqrt(1.0 - bb) * 1.01;
-  const int ntrial = (int)ceil(z0 / 0.005);  // len(np.arange(z0, 0, -0.005))
-  double d_prev = 0.0, z_prev = 0.0, zq = 0.0;
+  // rays with b^2 >= 1 (raypath.py:126-127; NaN impact parameters too) never hit
+  double zq = 0.0;
   bool hit = false;
-  for (int t = 0; t < ntrial; ++t) {
-    const double z = z0 + t * (-0.005);
-    double px, py, pz;
-    rot2planet(g, bx, by, z, px, py, pz);
-    const double nb = sqrt(px * px + py * py + pz * pz);
-    const double r1 = nb * rNorm;
-    double s, c;
-    lat_sc(py / nb, s, c);
-    const double r2 = rNorm * sqrt(q2 * s * s + c * c);
-    const double d = r1 - r2;
-    if (r1 < r2) {
-      hit = true;
-      // np.interp(0, [d, d_prev], [z, z_prev]); a first-trial hit returns z itself
-      zq = (t == 0) ? z : ((z_prev - z) / (d_prev - d)) * (0.0 - d) + z;
-      break;
+  if (bb < 1.0) {
+    const double z0 = sqrt(1.0 - bb) * 1.01;
+    const int ntrial = (int)ceil(z0 / 0.005);  // len(np.arange(z0, 0, -0.005))
+    double d_prev = 0.0, z_prev = 0.0;
+    for (int t = 0; t < ntrial; ++t) {
+      const double z = z0 + t * (-0.005);
+      double px, py, pz;
+      rot2planet(g, bx, by, z, px, py, pz);
+      const double nb = sqrt(px * px + py * py + pz * pz);
+      const double r1 = nb * rNorm;
+      double s, c;
+      lat_sc(py / nb, s, c);
+      const double r2 = rNorm * sqrt(q2 * s * s + c * c);
+      const double d = r1 - r2;
+      if (r1 < r2) {
+        hit = true;
+        // np.interp(0, [d, d_prev], [z, z_prev]); a first-trial hit returns z itself
+        zq = (t == 0) ? z : ((z_prev - z) / (d_prev - d)) * (0.0 - d) + z;
+        break;
+      }
+      d_prev = d;
+      z_prev = z;
     }
-    d_prev = d;
-    z_prev = z;
   }
+  // Lanes leave the trial loop at different iterations; without this the early ones run ahead into the
+  // layer loop and the warp stays split for all ~1000 segments (measured: 18.7 active lanes per issue).
+  __syncwarp();
+  if (inrange) g.nanflag[r] = 0;
   if (!hit) {
-    g.nseg[r] = -1;
+    if (inrange) g.nseg[r] = -1;
     return;
   }
   // edge position, then the shell point / normal the reference starts from (raypath.py:141-156)
@@ -160,34 +163,47 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
   double* out = g.ds + ds_tile_base(r, S);
   const double e2 = 1.0 - q2;
   const double sin6 = 9.99999999999833333e-07, cos6 = 0.9999999999995;   // sin / cos of 1e-6 rad
+  const double shape0sq = q2 * sin6 * sin6 + cos6 * cos6;               // lat == 0 -> 1e-6 rad (shape.py:231-233)
+  // Between two (rare) direction changes the ray is a straight line r(t) = r0 + t s, so the recurrence of
+  // raypath.py:176-237 only needs scalars:  r.s = rd0 + t,  |r|^2 = (r.s)^2 + perp2,  y = y0 + t sy.
+  //   shell radius factor^2 at the current latitude:   shape2 = 1 - (1 - q^2) y^2 / |r|^2
+  //   ds = -r.s - sqrt((r.s)^2 + rNext^2 - rNow^2),    rNext^2 - rNow^2 = shape2 (R_l+1^2 - R_l^2)
+  double t = 0.0;
+  double rd0 = px * sx + py * sy + pz * sz;
+  double perp2 = (px * px + py * py + pz * pz) - rd0 * rd0;
+  double y0 = py;
+  double shape2 = shape * shape;
+  double Rl = g.radius[0];
   for (; layer < S; ++layer) {
-    const double rNow = g.radius[layer] * shape;
-    const double rNext = g.radius[layer + 1] * shape;
-    const double rdots = px * sx + py * sy + pz * sz;
-    double ds = -rdots - sqrt(rdots * rdots + rNext * rNext - rNow * rNow);
-    if (ds < 0.0) break;  // raypath.py:212-216
-    if (g.limb == RB_LIMB_SEC) ds = fabs(rNext - rNow) / mu;
+    const double Rn = g.radius[layer + 1];
+    const double rd = rd0 + t;
+    double ds;
+    if (g.limb == RB_LIMB_SEC) {
+      const double sh = sqrt(shape2);
+      const double chk = -rd - sqrt(fma(rd, rd, shape2 * (Rn * Rn - Rl * Rl)));
+      if (chk < 0.0) break;
+      ds = fabs(Rn * sh - Rl * sh) / mu;                                 // raypath.py:218-219 (also replaces a NaN)
+    } else {
+      ds = -rd - sqrt(fma(rd, rd, shape2 * ((Rn - Rl) * (Rn + Rl))));
+      if (ds < 0.0) break;  // raypath.py:212-216
+    }
     out[(size_t)layer * kDsStride] = ds;
     if (ds != ds && first_nan < 0) first_nan = layer;
     ++count;
-    // advance; shell shape factor at the new latitude: rmag/req = sqrt(q^2 sin^2 + cos^2) with
-    // sin lat = y/|r|  ->  sqrt(1 - (1 - q^2) y^2/|r|^2)                     (raypath.py:228-237)
-    px += ds * sx; py += ds * sy; pz += ds * sz;
-    const double nr2 = px * px + py * py + pz * pz;
-    if (py == 0.0) shape = sqrt(q2 * sin6 * sin6 + cos6 * cos6);           // lat == 0 -> 1e-6 (shape.py:231-233)
-    else shape = sqrt(1.0 - e2 * (py * py) / nr2);
+    Rl = Rn;
+    // advance along the line and re-evaluate the latitude (raypath.py:228-237)
+    t += ds;
+    const double rdn = rd0 + t;
+    const double yn = fma(t, sy, y0);
+    const double nr2 = fma(rdn, rdn, perp2);
+    shape2 = (yn == 0.0) ? shape0sq : fma(-e2, (yn * yn) / nr2, 1.0);
     // incidence on the next shell with nratio = 1 (raypath.py:176-177, 246, 257): the reference's
     // arccos / arcsin pair gives s += (cos t_inc - |cos t_inc|) n, i.e. nothing unless cos t_inc < 0.
-    // n is parallel to (q x, y, q z) (the normal of the ellipse of parameter lat at longitude lng),
-    // so only the sign of s.(q x, y, q z) has to be looked at in the common case.
-    double d;
-    if (py == 0.0) {
-      const double hxz = sqrt(px * px + pz * pz);
-      d = g.q * cos6 * (sx * px + sz * pz) / hxz + sy * sin6;
-    } else {
-      d = g.q * (sx * px + sz * pz) + sy * py;
-    }
-    if (!(d <= 0.0)) {  // cos(t_inc) < 0 (or NaN): grazing ray, rare
+    // n is parallel to (q x, y, q z), so cos t_inc < 0  <=>  d = q (s.r - sy y) + sy y > 0.
+    const double d = fma(g.q, rdn - sy * yn, sy * yn);
+    if (!(d <= 0.0) || yn == 0.0) {
+      // grazing ray (rare) or the lat == 0 special case: go through the vector form
+      px = fma(t, sx, px); py = yn; pz = fma(t, sz, pz);
       double ux, uy, uz;
       if (py == 0.0) {
         const double hxz = sqrt(px * px + pz * pz);
@@ -198,8 +214,15 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
       const double inv = 1.0 / sqrt(ux * ux + uy * uy + uz * uz);
       ux *= inv; uy *= inv; uz *= inv;
       const double ci = -(sx * ux + sy * uy + sz * uz);
-      const double w = (fabs(ci) > 1.0) ? nan("") : 2.0 * ci;
-      sx += w * ux; sy += w * uy; sz += w * uz;
+      if (!(ci >= 0.0)) {
+        const double w = (fabs(ci) > 1.0) ? nan("") : 2.0 * ci;
+        sx += w * ux; sy += w * uy; sz += w * uz;
+      }
+      // restart the line at the current point
+      t = 0.0;
+      rd0 = px * sx + py * sy + pz * sz;
+      perp2 = (px * px + py * py + pz * pz) - rd0 * rd0;
+      y0 = py;
     }
   }
   g.nseg[r] = count;
