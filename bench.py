@@ -210,6 +210,59 @@ class ClockSampler:
         return out
 
 
+def alpha_c5(ctx, dev, reps=5):
+    """Secondary metric of BASELINE.json: alpha layer*freq*line / s on config C5 (synthetic 4096-layer
+    atmosphere x 4096 freqs x NH3 catalog, formalism nh3_dbs_sjs; SURVEY 8d: T~U(80,1800) K,
+    P log-U(1e-2,5e3) bar, X_NH3 log-U(1e-7,1e-3), X_H2 = 0.86, X_He = 0.135, seed 0)."""
+    import torch
+    from radiobear_b200 import engine
+    from oracle import alpha_oracle as ao
+    rng = np.random.default_rng(0)
+    L = F = 4096
+    C = {'Z': 0, 'T': 1, 'P': 2, 'H2': 3, 'HE': 4, 'NH3': 5}
+    gas = np.zeros((6, L))
+    gas[C['T']] = rng.uniform(80.0, 1800.0, L)
+    gas[C['P']] = 10**rng.uniform(-2.0, np.log10(5e3), L)
+    gas[C['H2']], gas[C['HE']] = 0.86, 0.135
+    gas[C['NH3']] = 10**rng.uniform(-7.0, -3.0, L)
+    freqs = np.linspace(1.0, 100.0, F)
+    P = gas[C['P']]
+    # lines actually evaluated per (layer, freq): 814 below 400 bar, 1014 in the 400..2000 bar blend, 200 above
+    nlines = np.where(P < 400.0, 814, np.where(P > 2000.0, 200, 1014))
+    n_br = np.where(P < 400.0, 415, np.where(P > 2000.0, 200, 615))          # Ben-Reuven line-evals
+    n_gr = np.where(P > 2000.0, 0, 399)                                       # Gross line-evals
+    evals = float(nlines.sum()) * F
+    flops = (10.0 * float(n_br.sum()) + 8.0 * float(n_gr.sum())) * F          # + 1 reciprocal each (not counted)
+    t64 = dict(dtype=torch.float64, device=dev)
+    g_t = torch.tensor(gas, **t64).contiguous()
+    f_t, T_t, P_t = torch.tensor(freqs, **t64), torch.tensor(gas[C['T']], **t64), torch.tensor(P, **t64)
+    out = torch.empty((L, F), **t64)
+    forms = [('nh3', 'nh3_dbs_sjs')]
+    ms = []
+    for i in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        engine.alpha_layers_dev(f_t, T_t, P_t, g_t, C, formalisms=forms, out=out, freqs_host=freqs, ctx=ctx)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ms.append(e0.elapsed_time(e1))
+    t = float(np.mean(ms)) * 1e-3
+    # parity spot check against the oracle + its speed on one host core
+    lay = [7, 1234, 4000]
+    t0 = time.perf_counter()
+    ref = ao.get_layers(freqs, gas, np.zeros((1, L)), C, {}, {'nh3': 'nh3_dbs_sjs'}, layers=lay)
+    t_cpu = time.perf_counter() - t0
+    got = out[lay].cpu().numpy().T
+    rel = float(np.nanmax(np.abs(got - ref) / np.abs(ref)))
+    cpu_rate = float(nlines[lay].sum()) * F / t_cpu
+    return {'workload': 'C5: 4096 layers x 4096 freqs x NH3 (nh3_dbs_sjs), synthetic', 'metric': 'alpha layer*freq*line/s',
+            'value': evals / t, 'ms': t * 1e3, 'line_evals': evals, 'max_rel_err_vs_oracle': rel,
+            'fp64_tflops_algorithmic': flops / t / 1e12,
+            'flops_per_line_eval': '10 (Ben-Reuven) / 8 (Gross) + 1 reciprocal (SURVEY 8d)',
+            'cpu_port_value_1core': cpu_rate}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -287,6 +340,7 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
+    kcount0 = {w: ctx.kernel_timed_count(w) for w in ('alpha', 'geometry', 'rt')}
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for i in range(args.steps):
@@ -305,9 +359,15 @@ def run_gpu(args):
     value = n_on * F / (ms_per_step * 1e-3)
 
     # per-kernel device times of the timed steps (library-side CUDA events on the same stream)
-    k_alpha = ctx.kernel_ms_history('alpha', args.steps)
-    k_geo = ctx.kernel_ms_history('geometry', args.steps)
-    k_rt = ctx.kernel_ms_history('rt', args.steps)
+    def per_step_ms(which):
+        # a step may launch a kernel family several times (ray chunks): sum per step, average over the steps
+        n = ctx.kernel_timed_count(which) - kcount0[which]
+        h = ctx.kernel_ms_history(which, min(n, 256))
+        return float(np.sum(h)) * (n / max(len(h), 1)) / args.steps, n // args.steps
+
+    k_alpha, _ = per_step_ms('alpha')
+    k_geo, _ = per_step_ms('geometry')
+    k_rt, rt_chunks = per_step_ms('rt')
     fp64_peak = ctx.fp64_peak_tflops(20000) if rank == 0 else 0.0
 
     # ---- end to end through the public API (host buffers) ----------------------------------------
@@ -337,19 +397,19 @@ def run_gpu(args):
             pass
         hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
         peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
-        rt_ms = float(np.mean(k_rt)) if len(k_rt) else float('nan')
+        rt_ms = k_rt
         n_on_rank = n_on_local
         # algorithmic bytes of one rt_integrate launch: ds slab read for the on-disc rays +
         # alpha slab + T + float32 Tb out for every pixel of the rank
         rt_bytes = n_on_rank * S * 8 + F * L * 8 + L * 8 + len(pts) * F * 4
-        rt_flops = float(n_on_rank) * F * (S - 1) * 30.0      # 10 FP64 + exp (~20) per (ray, freq, segment), DESIGN.md
-        roofline = {'bound': 'hbm', 'kernel': 'rt_integrate_kernel', 'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9,
+        rt_flops = float(n_on_rank) * F * (S - 1) * 20.0      # 12 FP64 instructions = 20 flops per (ray, freq, segment), DESIGN.md 3.3
+        roofline = {'bound': 'hbm', 'kernel': 'rt_integrate_rays_kernel', 'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9,
                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': rt_bytes / (rt_ms * 1e-3) / 1e9 / hbm_peak,
-                    'traffic': None, 'peak_source': peak_src, 'ms_per_launch': rt_ms,
+                    'traffic': None, 'peak_source': peak_src, 'ms_per_launch': rt_ms, 'launches_per_step': rt_chunks,
                     'note': 'at F=64 the kernel is FP64/exp-bound, not HBM-bound (SURVEY 8d): see fp64',
                     'fp64': {'achieved_tflops': rt_flops / (rt_ms * 1e-3) / 1e12, 'peak_tflops': fp64_peak,
                              'frac': rt_flops / (rt_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                             'flops_per_segment_step': 30, 'peak_source': 'rb_probe_fp64_peak (DFMA, same box, same run)',
+                             'flops_per_segment_step': 20, 'peak_source': 'rb_probe_fp64_peak (DFMA, same box, same run)',
                              'note': 'algorithmic count over all (ray,freq,segment); the tau>100 early exit skips part of them'}}
         cores = 1
         cpu_v, cpu_desc, _ = cpu_sample(cores, n_pix_per_core=12, n_lay_per_core=48) if world == 1 else (None, None, None)
@@ -366,12 +426,18 @@ def run_gpu(args):
                     'ms_per_step': 1e3 * float(e2e_t.item()), 'api': 'Planet.run(freqs, b=0.005)'},
             'gpu_launches': int(launches),
             'roofline': roofline,
-            'kernels_ms': {'alpha_lines': float(np.mean(k_alpha)), 'ray_geometry': float(np.mean(k_geo)),
-                           'rt_integrate': rt_ms},
+            'kernels_ms': {'alpha_lines': k_alpha, 'ray_geometry': k_geo, 'rt_integrate': rt_ms,
+                           'note': 'device time per step summed over the {} ray chunks of the pipeline; geometry(c+1) '
+                                   'overlaps integrate(c), so the sum exceeds ms_per_step'.format(rt_chunks)},
             'value_all_pixels': n_all * F / (ms_per_step * 1e-3),
         }
         if cpu_v is not None:
             line['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': cpu_desc}
+        if world == 1:
+            a5 = alpha_c5(ctx, dev)
+            a5['fp64_peak_tflops'] = fp64_peak
+            a5['fp64_frac'] = a5['fp64_tflops_algorithmic'] / fp64_peak if fp64_peak else None
+            line['alpha_c5'] = a5
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

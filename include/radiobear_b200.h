@@ -58,8 +58,13 @@ int64_t rb_launch_count(const rb_context* ctx);
 int rb_enable_timing(rb_context* ctx, int on);
 double rb_last_kernel_ms(rb_context* ctx, int which);
 /* Durations (ms) of the most recent launches of a kernel family, oldest first; returns how many were
- * written (<= max_out, <= 64).  Synchronises on the last event. */
+ * written (<= max_out, <= 256).  Synchronises on the last event. */
 int rb_kernel_ms_history(rb_context* ctx, int which, double* out_ms, int max_out);
+/* Number of timed launches of a kernel family so far (a request may be cut into several ray chunks). */
+int64_t rb_kernel_timed_count(const rb_context* ctx, int which);
+/* Ray-chunk pipeline depth for large requests: n chunks whose geometry / integration / device->host copy
+ * overlap on three streams (0 = automatic, 1 = no pipelining). */
+int rb_set_rt_chunks(rb_context* ctx, int n);
 
 /* ---- line catalogs --------------------------------------------------------------------- *
  * Replaces the per-plugin npz readers: nh3_hs.py:62-67, nh3_sjs.py:17-23, h2s_ddb.py:14-39,

@@ -77,6 +77,8 @@ def load():
         'rb_enable_timing': (C.c_int, [vp, C.c_int]),
         'rb_last_kernel_ms': (dbl, [vp, C.c_int]),
         'rb_kernel_ms_history': (C.c_int, [vp, C.c_int, vp, C.c_int]),
+        'rb_kernel_timed_count': (i64, [vp, C.c_int]),
+        'rb_set_rt_chunks': (C.c_int, [vp, C.c_int]),
         'rb_set_catalog': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
         'rb_alpha_layers': (C.c_int, [vp, C.POINTER(AlphaDesc), vp, vp]),
         'rb_alpha_layers_dev': (C.c_int, [vp, C.POINTER(AlphaDesc), vp, vp]),
@@ -97,7 +99,8 @@ def load():
 
 EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error', 'rb_set_stream', 'rb_use_own_stream',
                     'rb_synchronize',
-                    'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_set_catalog', 'rb_alpha_layers',
+                    'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_kernel_timed_count',
+                    'rb_set_rt_chunks', 'rb_set_catalog', 'rb_alpha_layers',
                     'rb_alpha_layers_dev', 'rb_compute_ds', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
                     'rb_probe_fp64_peak', 'rb_probe_rcp']
 
@@ -167,7 +170,13 @@ class Context:
     def last_kernel_ms(self, which):
         return float(self.lib.rb_last_kernel_ms(self.h, {'alpha': 0, 'geometry': 1, 'rt': 2}.get(which, which)))
 
-    def kernel_ms_history(self, which, n=64):
+    def kernel_timed_count(self, which):
+        return int(self.lib.rb_kernel_timed_count(self.h, {'alpha': 0, 'geometry': 1, 'rt': 2}.get(which, which)))
+
+    def set_rt_chunks(self, n):
+        self.check(self.lib.rb_set_rt_chunks(self.h, int(n)))
+
+    def kernel_ms_history(self, which, n=256):
         buf = np.zeros(n)
         got = self.lib.rb_kernel_ms_history(self.h, {'alpha': 0, 'geometry': 1, 'rt': 2}.get(which, which), ptr(buf), n)
         return buf[:got]

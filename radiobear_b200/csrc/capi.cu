@@ -90,6 +90,9 @@ void rb_destroy(rb_context* ctx) {
       for (int r = 0; r < rb_context::kEvRing; ++r)
         for (int j = 0; j < 2; ++j)
           if (ctx->ev[i][r][j]) cudaEventDestroy(ctx->ev[i][r][j]);
+    for (auto& a : ctx->aux)
+      if (a) cudaStreamDestroy(a);
+    for (auto& e : ctx->pipe_ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own_stream);
   }
   delete ctx;
@@ -144,6 +147,16 @@ int rb_kernel_ms_history(rb_context* ctx, int which, double* out_ms, int max_out
   const int64_t first = ctx->ev_count[which] - n;
   for (int64_t i = 0; i < n; ++i) out_ms[i] = ring_ms(ctx, which, first + i);
   return (int)n;
+}
+
+int64_t rb_kernel_timed_count(const rb_context* ctx, int which) {
+  return (ctx && which >= 0 && which <= 2) ? ctx->ev_count[which] : 0;
+}
+
+int rb_set_rt_chunks(rb_context* ctx, int n) {
+  if (!ctx || n < 0) return RB_ERR_INVALID;
+  ctx->rt_chunks = n;
+  return RB_OK;
 }
 
 int rb_set_catalog(rb_context* ctx, int catalog, int nlines, int ncols, const double* cols) {
@@ -291,6 +304,90 @@ static int check_rt(rb_context* ctx, const rb_rt_desc* rt, const void* out_Tb) {
   return RB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Result pipeline.  Geometry runs once for all rays; for HOST outputs the integration is cut into ray
+// chunks (multiples of 32 rays = whole ds tiles) on a second stream so that the device->host copy of chunk
+// c (third stream) overlaps the integration of chunk c+1.  Both streams are forked from / joined to
+// ctx->stream with events, so callers still see one in-order stream.  (Overlapping geometry(c+1) with
+// integrate(c) was measured and is slower: the latency-bound geometry kernel starves when it shares SMs.)
+// All pointers are DEVICE pointers except h_out / h_intW.
+static int pipe_setup(rb_context* ctx, int nch) {
+  for (int i = 0; i < 3; ++i)
+    if (!ctx->aux[i]) RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+  const size_t need = 4 + 2 * (size_t)nch;
+  while (ctx->pipe_ev.size() < need) {
+    cudaEvent_t e;
+    RB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_ev.push_back(e);
+  }
+  return RB_OK;
+}
+
+static int choose_chunks(const rb_context* ctx, int64_t R, bool rays_path, bool host_out) {
+  if (!rays_path || !host_out || R < 16384) return 1;
+  int n = ctx->rt_chunks;
+  if (n <= 0) {
+    const char* e = getenv("RB_RT_CHUNKS");
+    n = e ? atoi(e) : 6;
+  }
+  if (n < 1) n = 1;
+  if (n > 64) n = 64;
+  return n;
+}
+
+static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_desc* rd, void* d_out, double* d_intW,
+                           void* h_out, double* h_intW) {
+  const int64_t R = full.R;
+  const size_t S = full.L - 1, F = rd->n_freqs, esz = rd->out_f32 ? 4 : 8;
+  RtPrep prep;
+  RB_TRY(rb_rt_prepare(ctx, full.L, rd, R, false, &prep));
+  RB_TRY(rb_launch_geometry(ctx, full));
+  const int nch = choose_chunks(ctx, R, prep.use_rays, h_out != nullptr);
+  if (nch == 1) {
+    RB_TRY(rb_launch_integrate(ctx, full, rd, prep, d_out, d_intW, -1, nullptr, nullptr, nullptr));
+    if (h_out) RB_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, (size_t)R * F * esz, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_intW) RB_CUDA(ctx, cudaMemcpyAsync(h_intW, d_intW, (size_t)R * F * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return RB_OK;
+  }
+  RB_TRY(pipe_setup(ctx, nch));
+  cudaStream_t user = ctx->stream, sI = ctx->aux[1], sC = ctx->aux[2];
+  cudaEvent_t* ev = ctx->pipe_ev.data();
+  RB_CUDA(ctx, cudaEventRecord(ev[0], user));               // inputs, operands and geometry are ready
+  RB_CUDA(ctx, cudaStreamWaitEvent(sI, ev[0], 0));
+  RB_CUDA(ctx, cudaStreamWaitEvent(sC, ev[0], 0));
+  // chunk boundaries: equal numbers of planet-hitting rays would be ideal; equal tile counts in the middle
+  // rows are close enough, so cut by tiles
+  const int64_t tiles = (R + 31) / 32;
+  int status = RB_OK;
+  ctx->stream = sI;
+  for (int c = 0; c < nch && status == RB_OK; ++c) {
+    const int64_t t0 = tiles * c / nch, t1 = tiles * (c + 1) / nch;
+    const int64_t r0 = t0 * 32, r1 = (t1 * 32 < R) ? t1 * 32 : R;
+    if (r1 <= r0) continue;
+    RtLaunch Lc = full;
+    Lc.R = r1 - r0;
+    Lc.Rpad = (Lc.R + 31) & ~(int64_t)31;
+    Lc.b = full.b + 2 * r0;
+    Lc.ds = full.ds + (size_t)t0 * S * 32;
+    Lc.nseg = full.nseg + r0;
+    Lc.nanflag = full.nanflag + r0;
+    char* oc = (char*)d_out + (size_t)r0 * F * esz;
+    double* wc = d_intW ? d_intW + (size_t)r0 * F : nullptr;
+    status = rb_launch_integrate(ctx, Lc, rd, prep, oc, wc, -1, nullptr, nullptr, nullptr);
+    if (status != RB_OK) break;
+    cudaEventRecord(ev[4 + c], sI);
+    cudaStreamWaitEvent(sC, ev[4 + c], 0);
+    cudaMemcpyAsync((char*)h_out + (size_t)r0 * F * esz, oc, (size_t)(r1 - r0) * F * esz, cudaMemcpyDeviceToHost, sC);
+    if (h_intW) cudaMemcpyAsync(h_intW + (size_t)r0 * F, wc, (size_t)(r1 - r0) * F * 8, cudaMemcpyDeviceToHost, sC);
+  }
+  ctx->stream = user;
+  cudaEventRecord(ev[2], sI); cudaStreamWaitEvent(user, ev[2], 0);
+  cudaEventRecord(ev[3], sC); cudaStreamWaitEvent(user, ev[3], 0);
+  RB_TRY(status);
+  RB_CUDA(ctx, cudaGetLastError());
+  return RB_OK;
+}
+
 int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt, int64_t R, const double* b,
                     void* out_Tb, double* out_intW) {
   if (!ctx) return RB_ERR_INVALID;
@@ -304,8 +401,7 @@ int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc
   RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   L.radius = g->radius; L.b = b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
-  RB_TRY(rb_launch_geometry(ctx, L));
-  return rb_launch_integrate(ctx, L, rt, out_Tb, out_intW, -1, nullptr, nullptr, nullptr);
+  return run_rt_pipeline(ctx, L, rt, out_Tb, out_intW, nullptr, nullptr);
 }
 
 int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt, int64_t R, const double* b,
@@ -338,10 +434,7 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
   rb_rt_desc rd = *rt;
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
-  RB_TRY(rb_launch_geometry(ctx, L));
-  RB_TRY(rb_launch_integrate(ctx, L, &rd, p_tb, (double*)p_iw, -1, nullptr, nullptr, nullptr));
-  RB_CUDA(ctx, cudaMemcpyAsync(out_Tb, p_tb, (size_t)R * F * esz, cudaMemcpyDeviceToHost, s));
-  if (out_intW) RB_CUDA(ctx, cudaMemcpyAsync(out_intW, p_iw, (size_t)R * F * 8, cudaMemcpyDeviceToHost, s));
+  RB_TRY(run_rt_pipeline(ctx, L, &rd, p_tb, (double*)p_iw, out_Tb, out_intW));
   if (profile_ray >= 0) {
     // re-run the selected ray alone with the profile-writing variant (Brightness.tau/.W/.Tb_lyr)
     RB_TRY(rb_ensure(ctx, RB_BUF_PROFILE, 3 * F * S * 8 + F * 8, &p_prof));
@@ -352,7 +445,9 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
     L1.b = L.b + 2 * profile_ray;
     double* pp = (double*)p_prof;
     rd.out_f32 = 0;
-    RB_TRY(rb_launch_integrate(ctx, L1, &rd, pp + 3 * F * S, nullptr, 0, pp, pp + F * S, pp + 2 * F * S));
+    RtPrep prof_prep;
+    RB_TRY(rb_rt_prepare(ctx, L.L, &rd, 1, true, &prof_prep));
+    RB_TRY(rb_launch_integrate(ctx, L1, &rd, prof_prep, pp + 3 * F * S, nullptr, 0, pp, pp + F * S, pp + 2 * F * S));
     RB_CUDA(ctx, cudaMemcpyAsync(out_tau, pp, F * S * 8, cudaMemcpyDeviceToHost, s));
     RB_CUDA(ctx, cudaMemcpyAsync(out_W, pp + F * S, F * S * 8, cudaMemcpyDeviceToHost, s));
     RB_CUDA(ctx, cudaMemcpyAsync(out_Tblyr, pp + 2 * F * S, F * S * 8, cudaMemcpyDeviceToHost, s));
@@ -389,7 +484,9 @@ int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int
   RB_TRY(rb_launch_ds_to_slab(ctx, (const double*)p_in, R, L.Rpad, (int)S, L.nseg, L.nanflag, (double*)p_ds));
   rb_rt_desc rd = *rt;
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
-  RB_TRY(rb_launch_integrate(ctx, L, &rd, p_tb, (double*)p_iw, -1, nullptr, nullptr, nullptr));
+  RtPrep prep;
+  RB_TRY(rb_rt_prepare(ctx, L.L, &rd, R, false, &prep));
+  RB_TRY(rb_launch_integrate(ctx, L, &rd, prep, p_tb, (double*)p_iw, -1, nullptr, nullptr, nullptr));
   RB_CUDA(ctx, cudaMemcpyAsync(out_Tb, p_tb, (size_t)R * F * esz, cudaMemcpyDeviceToHost, s));
   if (out_intW) RB_CUDA(ctx, cudaMemcpyAsync(out_intW, p_iw, (size_t)R * F * 8, cudaMemcpyDeviceToHost, s));
   RB_CUDA(ctx, cudaStreamSynchronize(s));

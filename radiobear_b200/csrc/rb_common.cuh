@@ -31,10 +31,14 @@ struct rb_context {
   DevBuf buf[20];
   // timing
   bool timing = false;
-  static constexpr int kEvRing = 64;
+  static constexpr int kEvRing = 256;
   cudaEvent_t ev[3][kEvRing][2] = {};
   int64_t ev_count[3] = {0, 0, 0};
   int ev_slot = 0;  // slot of the launch being timed
+  // ray-chunk pipeline (geometry of chunk c+1 overlaps integration of chunk c and the D2H of chunk c-1)
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> pipe_ev;
+  int rt_chunks = 0;  // 0 = automatic
 };
 
 // record the start / stop event of one launch of kernel family `which` (no-ops unless timing is on)
@@ -96,8 +100,15 @@ int rb_launch_geometry(rb_context* ctx, const RtLaunch& g);
 int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out_ds_raymajor /*[R][L-1] device*/);
 int rb_launch_ds_to_slab(rb_context* ctx, const double* ds_raymajor, int64_t R, int64_t Rpad, int S, const int* nseg,
                          int* nanflag, double* slab);
-int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt /*device pointers*/, void* out_Tb,
-                        double* out_intW, int64_t profile_ray, double* out_tau, double* out_W, double* out_Tblyr);
+struct RtPrep {
+  bool use_rays = false;       // rays-major kernel (R >= 512, point rays) or the lanes = frequency kernel
+  const void* prep = nullptr;  // operand slab of the rays-major kernel
+};
+int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt /*device pointers*/, int64_t R_total, bool profile,
+                  RtPrep* out);
+int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt /*device pointers*/, const RtPrep& prep,
+                        void* out_Tb, double* out_intW, int64_t profile_ray, double* out_tau, double* out_W,
+                        double* out_Tblyr);
 
 // ---- device math helpers -----------------------------------------------------------------------
 #ifdef __CUDACC__

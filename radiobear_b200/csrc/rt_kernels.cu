@@ -484,7 +484,7 @@ constexpr int kTileDs = (kChunk + 1) * 32;   // doubles per ds tile
 constexpr int kTilePp = kChunk * 8;          // double4 per operand tile
 constexpr size_t kRaysSmemBytes = kStages * (kTileDs * sizeof(double) + kTilePp * sizeof(double4));
 
-__global__ void __launch_bounds__(256) rt_integrate_rays_kernel(const __grid_constant__ RtK k) {
+__global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_constant__ RtK k) {
   __shared__ double s_tab[kExpTab];                        // 2^(j/1024)
   __shared__ __align__(16) double s_ds[kStages * kTileDs];
   __shared__ __align__(16) double4 s_pp[kStages * kTilePp];
@@ -522,12 +522,61 @@ __global__ void __launch_bounds__(256) rt_integrate_rays_kernel(const __grid_con
   // window base with S2UR / UMOV / ULEA in every iteration)
   unsigned tab_base;
   asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(tab_base) : "l"(s_tab));
-  // tau > tau_cut  <=>  round(-tau * 1024 log2 e) < ni_cut: an integer compare instead of an FP64 one
-  const double cutd = k.tau_cut * 1477.3197218702985;
-  const int ni_cut = (cutd < 2.0e9) ? -(int)cutd : INT_MIN;
+  // One integer compare on the high word of nd = round(-tau 1024 log2 e) (a non-positive double, so its
+  // high word grows with |nd|) ends the ray when tau > tau_cut; tau_cut is capped at 707 (beyond it 2^k leaves
+  // the normal range and exp(-tau) is 0 for every purpose), so the hot loop needs neither an underflow
+  // select nor an FP64 compare.  The step that crosses the threshold is finished on a cold path.
+  const double cutd = fmin(k.tau_cut, 707.0) * 1477.3197218702985;
+  const unsigned thr_hi = (unsigned)__double2hiint(-cutd);
   double tau = 0.0, iW = 0.0, Tb = 0.0;
   bool live = steps > 0;
   int i = 0;
+  double last_dd = 0.0, last_qy = 0.0, last_qz = 0.0;    // operands of the crossing step
+
+  // one segment: consumes ds_i = dcur, ds_i+1 = dnxt and the operands q of segment i
+#define RB_RT_STEP(dcur, dnxt, q)                                                                              \
+  {                                                                                                            \
+    tau = fma((q).x, (dcur), tau);                                                                             \
+    double nd = fma(tau, cA, cM);                                                                              \
+    const int ni = __double2loint(nd);                                                                         \
+    nd -= cM;                                                                                                  \
+    if ((unsigned)__double2hiint(nd) > thr_hi) {                                                               \
+      last_dd = (dcur) + (dnxt); last_qy = (q).y; last_qz = (q).z;                                             \
+      stop = true;                                                                                             \
+      break;                                                                                                   \
+    }                                                                                                          \
+    const double rr = fma(nd, cL, -tau);                                                                       \
+    double p = fma(rr, c3, c2);                                                                                \
+    p = fma(p, rr, c1);                                                                                        \
+    p = fma(p, rr, c1);                                                                                        \
+    double tj;                                                                                                 \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_base + ((ni & (kExpTab - 1)) << 3)));                  \
+    const double v = p * tj;                                                                                   \
+    const double e = __hiloint2double(__double2hiint(v) + ((ni << 10) & 0xFFF00000), __double2loint(v));       \
+    const double w = e * ((dcur) + (dnxt));                                                                    \
+    iW = fma((q).y, w, iW);                                                                                    \
+    Tb = fma((q).z, w, Tb);                                                                                    \
+  }
+
+  // e^-tau * dd for a step known to be below the threshold (no checks): independent of the other steps of
+  // a group, so ptxas interleaves the four chains (ILP 4 instead of one ~100-cycle dependent chain per step)
+#define RB_RT_WEIGHT(tauv, dd, w)                                                                              \
+  {                                                                                                            \
+    double nd_ = fma((tauv), cA, cM);                                                                          \
+    const int ni_ = __double2loint(nd_);                                                                       \
+    nd_ -= cM;                                                                                                 \
+    const double rr_ = fma(nd_, cL, -(tauv));                                                                  \
+    double p_ = fma(rr_, c3, c2);                                                                              \
+    p_ = fma(p_, rr_, c1);                                                                                     \
+    p_ = fma(p_, rr_, c1);                                                                                     \
+    double tj_;                                                                                                \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj_) : "r"(tab_base + ((ni_ & (kExpTab - 1)) << 3)));                \
+    const double v_ = p_ * tj_;                                                                                \
+    const double e_ = __hiloint2double(__double2hiint(v_) + ((ni_ << 10) & 0xFFF00000), __double2loint(v_));   \
+    w = e_ * (dd);                                                                                             \
+  }
+
+  bool stop = false;
   for (int c = 0;; ++c) {
     cp_async_wait<0>();                                    // this thread's pieces of chunk c have landed
     if (!__syncthreads_or(live)) break;                    // ... everybody's have; chunk c-1 is fully consumed
@@ -540,38 +589,55 @@ __global__ void __launch_bounds__(256) rt_integrate_rays_kernel(const __grid_con
       const int zrow = steps - c * kChunk;
       if (zrow <= kChunk) dsb[zrow * 32] = 0.0;
       const int m = min(kChunk, steps - i);
-      double d0 = dsb[0];
-#pragma unroll 4
-      for (int u = 0; u < m; ++u) {
-        const double d1 = dsb[(u + 1) * 32];
-        const double4 q = ppb[u * 8];
-        tau = fma(q.x, d0, tau);                           // dtau = (a_i + a_i+1) ds / 2
-        // e = exp(-tau): 2^k 2^(j/1024) exp(rr)
-        double nd = fma(tau, cA, cM);
-        const int ni = __double2loint(nd);
-        nd -= cM;
-        const double rr = fma(nd, cL, -tau);
-        double p = fma(rr, c3, c2);
-        p = fma(p, rr, c1);
-        p = fma(p, rr, c1);
-        double tj;
-        asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_base + ((ni & (kExpTab - 1)) << 3)));
-        const double v = p * tj;
-        const double sc = __hiloint2double(__double2hiint(v) + ((ni >> 10) << 20), __double2loint(v));
-        // underflow (or tau so large that ni wrapped): nd <= -2^20 + 2^11 <=> 2^k below the normal range -> e = 0
-        const double e = ((unsigned)__double2hiint(nd) > 0xC12FF000u) ? 0.0 : sc;
-        const double w = e * (d0 + d1);                    // e^-tau (ds_i + ds_i+1)
-        iW = fma(q.y, w, iW);
-        Tb = fma(q.z, w, Tb);
-        d0 = d1;
-        if (ni < ni_cut) {                                 // tau > tau_cut
-          i = steps;
-          break;
-        }
+      int u = 0;
+      // groups of 4 segments: the four optical depths first (one dependent FMA each), one threshold test
+      // on the deepest, then four independent exp / accumulate chains
+      for (; u + 4 <= m; u += 4) {
+        const double d0 = dsb[u * 32], d1 = dsb[(u + 1) * 32], d2 = dsb[(u + 2) * 32], d3 = dsb[(u + 3) * 32],
+                     d4 = dsb[(u + 4) * 32];
+        const double4 q0 = ppb[u * 8], q1 = ppb[(u + 1) * 8], q2 = ppb[(u + 2) * 8], q3 = ppb[(u + 3) * 8];
+        const double t0 = fma(q0.x, d0, tau), t1 = fma(q1.x, d1, t0), t2 = fma(q2.x, d2, t1), t3 = fma(q3.x, d3, t2);
+        const double nd3 = fma(t3, cA, cM) - cM;
+        if ((unsigned)__double2hiint(nd3) > thr_hi) break;   // tau_cut is crossed inside this group: go step by step
+        double w0, w1, w2, w3;
+        RB_RT_WEIGHT(t0, d0 + d1, w0);
+        RB_RT_WEIGHT(t1, d1 + d2, w1);
+        RB_RT_WEIGHT(t2, d2 + d3, w2);
+        RB_RT_WEIGHT(t3, d3 + d4, w3);
+        iW = fma(q0.y, w0, iW); Tb = fma(q0.z, w0, Tb);
+        iW = fma(q1.y, w1, iW); Tb = fma(q1.z, w1, Tb);
+        iW = fma(q2.y, w2, iW); Tb = fma(q2.z, w2, Tb);
+        iW = fma(q3.y, w3, iW); Tb = fma(q3.z, w3, Tb);
+        tau = t3;
+      }
+      // remainder of the chunk / the group that crosses tau_cut: one segment at a time with the test
+      for (; u < m; ++u) {
+        const double da = dsb[u * 32], db = dsb[(u + 1) * 32];
+        const double4 q0 = ppb[u * 8];
+        RB_RT_STEP(da, db, q0);
       }
       i += m;
-      live = i < steps;
+      live = !stop && i < steps;
     }
+  }
+#undef RB_RT_WEIGHT
+#undef RB_RT_STEP
+  if (stop) {
+    // finish the step that crossed tau_cut: full exp(-tau) with the underflow guard
+    const double tc = fmin(tau, 800.0);
+    double nd = fma(tc, cA, cM);
+    const int ni = __double2loint(nd);
+    nd -= cM;
+    const double rr = fma(nd, cL, -tc);
+    double p = fma(rr, c3, c2);
+    p = fma(p, rr, c1);
+    p = fma(p, rr, c1);
+    const double v = p * s_tab[ni & (kExpTab - 1)];
+    double e = __hiloint2double(__double2hiint(v) + ((ni << 10) & 0xFFF00000), __double2loint(v));
+    if ((unsigned)__double2hiint(nd) > 0xC12FF000u) e = 0.0;
+    const double w = e * last_dd;
+    iW = fma(last_qy, w, iW);
+    Tb = fma(last_qz, w, Tb);
   }
   cp_async_wait<0>();
   if (!valid) return;
@@ -621,8 +687,26 @@ int rb_launch_ds_to_slab(rb_context* ctx, const double* in, int64_t R, int64_t R
   return RB_OK;
 }
 
-int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt, void* out_Tb, double* out_intW,
-                        int64_t profile_ray, double* out_tau, double* out_W, double* out_Tblyr) {
+// Decide the integration path for a request of R_total rays and, for the rays-major path, build the
+// per-(layer,freq) operand slab once (shared by all ray chunks of the request).
+int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total, bool profile, RtPrep* out) {
+  out->use_rays = !profile && !rt->disc_average && R_total >= 512;
+  out->prep = nullptr;
+  if (!out->use_rays) return RB_OK;
+  const int F = rt->n_freqs;
+  const int ngroups = (F + 7) / 8;
+  void* scratch;
+  RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (L - 1) * 8 * sizeof(double4), &scratch));
+  const int nel = ngroups * (L - 1) * 8;
+  rt_prepare_kernel<<<(nel + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ngroups, (double4*)scratch);
+  RB_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  out->prep = scratch;
+  return RB_OK;
+}
+
+int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt, const RtPrep& prep, void* out_Tb,
+                        double* out_intW, int64_t profile_ray, double* out_tau, double* out_W, double* out_Tblyr) {
   RtK k{};
   k.L = g.L; k.F = rt->n_freqs; k.R = g.R; k.Rpad = g.Rpad;
   k.alpha = rt->alpha; k.T = rt->T; k.ds = g.ds; k.nseg = g.nseg; k.nanflag = g.nanflag;
@@ -636,24 +720,18 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     dim3 grid(1, fgroups), block(32, 1);
     if (k.disc) rt_integrate_kernel<1, true, true><<<grid, block, 0, ctx->stream>>>(k);
     else rt_integrate_kernel<1, false, true><<<grid, block, 0, ctx->stream>>>(k);
-  } else if (k.disc || g.R < 512) {
+  } else if (!prep.use_rays) {
     const int wy = 4;
     dim3 grid((unsigned)((g.R + wy - 1) / wy), fgroups), block(32, wy);
     if (k.disc) rt_integrate_kernel<1, true, false><<<grid, block, 0, ctx->stream>>>(k);
     else rt_integrate_kernel<1, false, false><<<grid, block, 0, ctx->stream>>>(k);
   } else {
-    // rays-major mapping: blocks of 32 rays x 8 frequencies; per-(layer,freq) operands prepared once
-    const int ngroups = (k.F + 7) / 8;
-    void* scratch;
-    RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (k.L - 1) * 8 * sizeof(double4), &scratch));
-    const int nel = ngroups * (k.L - 1) * 8;
-    rt_prepare_kernel<<<(nel + 255) / 256, 256, 0, ctx->stream>>>(k.alpha, k.T, k.L, k.F, ngroups, (double4*)scratch);
-    k.prep = (const double4*)scratch;
-    dim3 block(32, 8), grid(ngroups, (unsigned)((g.R + 31) / 32));
-    if (grid.y > 65535) return rb_fail(ctx, RB_ERR_INVALID, "rt: more than 2M rays per call are not supported");
+    // rays-major mapping: CTAs of 32 rays x 8 frequencies; operands prepared by rb_rt_prepare
+    k.prep = (const double4*)prep.prep;
+    dim3 block(32, 8), grid((k.F + 7) / 8, (unsigned)((g.R + 31) / 32));
+    if (grid.y > 65535) return rb_fail(ctx, RB_ERR_INVALID, "rt: more than 2M rays per launch are not supported");
     static_assert(kExpTab * sizeof(double) + kRaysSmemBytes <= 48 * 1024, "static shared memory limit");
     rt_integrate_rays_kernel<<<grid, block, 0, ctx->stream>>>(k);
-    ctx->launches += 1;
   }
   RB_CUDA(ctx, cudaGetLastError());
   RB_CUDA(ctx, rb_time_end(ctx, 2));

@@ -27,8 +27,10 @@ class Data:
             self.b = ['disc']
         elif isinstance(val, list):
             setattr(self, par, np.asarray(val, dtype=np.float32))
-        elif par in ('Tb', 'b') and isinstance(val, np.ndarray):
+        elif par == 'Tb' and isinstance(val, np.ndarray):
             setattr(self, par, val.astype(np.float32, copy=False))
+        elif par == 'b' and isinstance(val, np.ndarray):
+            setattr(self, par, val)          # image grids are shared read-only arrays (no per-run conversion)
         else:
             setattr(self, par, val)
 

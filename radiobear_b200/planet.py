@@ -181,7 +181,7 @@ class Planet:
             world, rank = parallel.world_rank()
             if world > 1 and len(pts) >= 64 * world and not which.any():
                 # one process per GPU: shard rows / points, gather to rank 0 (None on the other ranks)
-                rows = (np.unique(pts[:, 1]), self.imSize[0]) if self.data_type == 'image' else None
+                rows = (pts[::self.imSize[0], 1], self.imSize[0]) if self.data_type == 'image' else None
                 Tb = parallel.run_points_sharded(self, pts, self.atmos[0], self.alpha[0], out_f32=f32, rows=rows)
             elif not which.any():
                 Tb = self.bright.batch(pts, self.freqs, self.atmos[0], self.alpha[0], self.config.orientation,

@@ -12,6 +12,9 @@ import numpy as np
 from . import utils
 
 
+_IMAGE_B_CACHE = {}
+
+
 def image_grid(bstep):
     """Pixel coordinates of a full-disc image: -1.5..1.5 in steps of bstep, symmetric about 0
     (set_utils.py:65-66)."""
@@ -86,8 +89,18 @@ def set_b(b, block=(1, 1), **kwargs):
         last = 0 if nblk == 1 else block[0] / nblk
         first = int((block[0] - 1) * bsplit)
         rows = [first + i for i in range(int(bsplit + last)) if first + i < len(grid)]
-        # [R][2] array (x fastest, rows of constant y) -- indexable like the reference's list of pairs
-        rv.b = np.stack([np.tile(grid, len(rows)), np.repeat(grid[rows], len(grid))], axis=1)
+        # [R][2] array (x fastest, rows of constant y) -- indexable like the reference's list of pairs.
+        # Pure function of (b, block): built once, kept in page-locked memory, handed out read-only.
+        key = (b, block[0], block[1])
+        pts = _IMAGE_B_CACHE.get(key)
+        if pts is None:
+            from . import hostmem
+            pts = hostmem.pinned_copy(np.stack([np.tile(grid, len(rows)), np.repeat(grid[rows], len(grid))], axis=1))
+            pts.flags.writeable = False
+            if len(_IMAGE_B_CACHE) >= 4:
+                _IMAGE_B_CACHE.pop(next(iter(_IMAGE_B_CACHE)))
+            _IMAGE_B_CACHE[key] = pts
+        rv.b = pts
         rv.imSize = [len(grid), len(rows)]
         rv.data_type = 'image'
         return rv
