@@ -811,8 +811,10 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
 
   static int newton = -1;
   if (newton < 0) {
+    // measured on B200 (tools/probe_rcp.py): seed 9.8e-7, 1 step 9.6e-13, 2 steps 1.1e-16 max relative
+    // error.  One step is 6 orders below the 1e-6 parity bar and 3 below the 1e-9 the tests hold.
     const char* e = getenv("RB_RCP_NEWTON");
-    newton = (e && e[0] == '1') ? 1 : 2;
+    newton = (e && e[0] == '2') ? 2 : 1;
   }
   void (*kern)(const AlphaK) = nullptr;
   if (k.fpt == 2) kern = (newton == 1) ? alpha_lines_kernel<2, 1> : alpha_lines_kernel<2, 2>;

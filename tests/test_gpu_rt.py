@@ -208,3 +208,54 @@ def test_rt_integrate_with_supplied_segments(eng):
     d = eng.rt_integrate(ds[:1], nseg[:1], slab, T, disc_average=True)
     ref = rto.integrate_ray(ds[0], np.arange(999), tb['c1_alpha'], T, disc_average=True)
     assert np.max(np.abs(d[0] - ref)) < 1e-6
+
+
+def test_rays_kernel_matches_small_batch_kernel_and_tau_cut_is_exact(eng):
+    """The rays-major kernel (R >= 512: cp.async tiles, table exp, regrouped sums) against the simple
+    lanes = frequency kernel (R < 512: libdevice exp, reference operation order) on the same pixels, and
+    tau_cut = 100 against no cut (capped at the exp underflow point)."""
+    a = golden('atm_jupiter.npz')
+    im = golden('image_c4.npz')
+    C = keymap(a['C_keys'])
+    slab = _slab(eng, a, im['freqs'][::3])
+    rng = np.random.default_rng(7)
+    th = rng.uniform(0, 2 * np.pi, 1200)
+    rad = np.sqrt(rng.uniform(0, 1.02, 1200))
+    q = float(a['Rpol']) / float(a['Req'])
+    b = np.stack([rad * np.cos(th), rad * np.sin(th) * q], axis=1)
+    T = a['gas'][C['T']]
+    big = eng.rt_batch(b=b, alpha_slab=slab, T=T, want_intW=True, **geom(a))
+    parts = [eng.rt_batch(b=b[i:i + 400], alpha_slab=slab, T=T, want_intW=True, **geom(a)) for i in range(0, 1200, 400)]
+    small = np.concatenate([p['Tb'] for p in parts])
+    small_w = np.concatenate([p['integrated_W'] for p in parts])
+    assert np.array_equal(np.isnan(big['Tb']), np.isnan(small))
+    assert np.isnan(small).any() and (small == 2.725).any()
+    assert np.nanmax(np.abs(big['Tb'] - small)) < 1e-7            # K
+    ok = ~np.isnan(small_w) & (small_w > 0)
+    assert np.max(np.abs(big['integrated_W'][ok] / small_w[ok] - 1.0)) < 1e-10
+    nocut = eng.rt_batch(b=b, alpha_slab=slab, T=T, tau_cut=0.0, **geom(a))
+    assert np.array_equal(nocut['Tb'][~np.isnan(small)], big['Tb'][~np.isnan(small)])
+    f32 = eng.rt_batch(b=b, alpha_slab=slab, T=T, out_f32=True, **geom(a))['Tb']
+    assert np.array_equal(f32[~np.isnan(small)], big['Tb'][~np.isnan(small)].astype(np.float32))
+
+
+def test_rt_edge_cases(eng):
+    a = golden('atm_jupiter.npz')
+    C = keymap(a['C_keys'])
+    T = a['gas'][C['T']]
+    slab = _slab(eng, a, np.array([22.0]))
+    # single frequency, ragged ray counts around the 32-ray tile and the 512-ray kernel switch
+    for R in (1, 31, 33, 511, 512, 513, 1025):
+        b = np.zeros((R, 2))
+        b[:, 0] = np.linspace(-0.9, 0.9, R)
+        out = eng.rt_batch(b=b, alpha_slab=slab, T=T, **geom(a))['Tb']
+        assert out.shape == (R, 1) and np.all(np.isfinite(out)) and np.all(out > 100.0)
+        ref = eng.rt_batch(b=b[:1], alpha_slab=slab, T=T, **geom(a))['Tb']
+        assert abs(out[0, 0] - ref[0, 0]) < 1e-7
+    with pytest.raises(ValueError):
+        eng.rt_batch(b=np.zeros((0, 2)), alpha_slab=slab, T=T, **geom(a))
+    with pytest.raises(ValueError):
+        eng.rt_batch(b=np.zeros((4, 2)), alpha_slab=slab[:10], T=T, **geom(a))
+    # NaN / infinite impact parameters miss the planet like |b| >= 1
+    out = eng.rt_batch(b=np.array([[np.nan, 0.0], [np.inf, 0.0], [0.0, 0.0]]), alpha_slab=slab, T=T, **geom(a))['Tb']
+    assert out[0, 0] == 2.725 and out[1, 0] == 2.725 and out[2, 0] > 100.0
