@@ -276,8 +276,16 @@ def run_gpu(args):
         raise SystemExit('bench.py: no CUDA device -- radiobear_b200 has no CPU fallback (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # keep stdout to the one JSON line: NCCL (and anything else below us) may print there, so fd 1 points at
+    # stderr until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = os.environ.get('RB_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
+        if 'RB_NCCL_DEBUG' in os.environ:
+            os.environ['NCCL_DEBUG'] = os.environ['RB_NCCL_DEBUG']
+        else:
+            os.environ.pop('NCCL_DEBUG', None)
         dist.init_process_group('nccl', device_id=dev)
     ctx = _lib.get_context(local)
     ctx.enable_timing(True)
@@ -438,7 +446,9 @@ def run_gpu(args):
             a5['fp64_peak_tflops'] = fp64_peak
             a5['fp64_frac'] = a5['fp64_tflops_algorithmic'] / fp64_peak if fp64_peak else None
             line['alpha_c5'] = a5
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

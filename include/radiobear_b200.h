@@ -96,7 +96,10 @@ int rb_set_catalog(rb_context* ctx, int catalog, int nlines, int ncols, const do
 #define RB_F_H2_JJ 10      /* h2/h2_jj.py:7-22          */
 #define RB_F_CLOUDS_IDP 11 /* clouds/clouds_idp.py:6-101 */
 #define RB_F_CO_DDB 12     /* co/co_ddb.py:22-99        */
-#define RB_NUM_FORMALISMS 13
+#define RB_F_NH3_KD 13     /* nh3/nh3_kd.py:115-351     */
+#define RB_F_NH3_SJSD 14   /* nh3/nh3_sjsd.py:6-24      */
+#define RB_F_NH3_BG 15     /* nh3/nh3_bg.py:26-74       */
+#define RB_NUM_FORMALISMS 16
 #define RB_MAX_CONSTITUENTS 8
 
 #define RB_UNITS_INVCM 0

@@ -108,9 +108,10 @@ _COEF_NH3 = 1.0E6 * 6.02297E23 / 8.31432E7   # nh3_hs.py:52-56
 _TO = 300.0
 
 
-def _nh3_consistent(freq, T, P, P_h2, P_he, P_nh3, cat, units, family, band):
-    """nh3_hs.py:91-312 / nh3_dbs.py:91-313 for one band ('lo': f<=30, 'hi': f>30)."""
-    c = _NH3_INV_SETS[family][band]
+def _nh3_consistent(freq, T, P, P_h2, P_he, P_nh3, cat, units, family, band, consts=None, clamp_le=False):
+    """nh3_hs.py:91-312 / nh3_dbs.py:91-313 for one band ('lo': f<=30, 'hi': f>30); nh3_kd.py:115-351 passes
+    its own pressure-dependent constants and clamps `<= 0` instead of `< 0` (nh3_kd.py:344-349)."""
+    c = consts if consts is not None else _NH3_INV_SETS[family][band]
     fo, Io, Eo, gammaNH3o = cat.get('nh3_inv')
     fo_rot, Io_rot, Eo_rot, gNH3_rot, gH2_rot, gHe_rot = cat.get('nh3_rot')
     fo_v2, Io_v2, Eo_v2 = cat.get('nh3_v2')
@@ -176,8 +177,70 @@ def _nh3_consistent(freq, T, P, P_h2, P_he, P_nh3, cat, units, family, band):
     if units == 'dBperkm':
         a = a * OPTICALDEPTH_TO_DB
     a = np.array(a)
-    a[a < 0.0] = 1.0E-8
+    if clamp_le:
+        a[a <= 0.0] = 1.0E-8
+    else:
+        a[a < 0.0] = 1.0E-8
     return a
+
+
+def nh3_kd_constants(P):
+    """Pressure switch of the inversion-line constants, linear between 12 and 20 bar (nh3_kd.py:160-195)."""
+    hi = dict(gnu_H2=1.6361, gnu_He=0.4555, gnu_NH3=0.7298, GAMMA_H2=0.8, GAMMA_He=0.5, GAMMA_NH3=1.0,
+              zeta_H2=1.1313, zeta_He=0.1, zeta_NH3=0.5152, Z_H2=0.6234, Z_He=0.5, Z_NH3=2.0 / 3.0, d=0.2, Con=1.3746)
+    lo = dict(gnu_H2=1.7465, gnu_He=0.9779, gnu_NH3=0.7298, GAMMA_H2=0.8202, GAMMA_He=1.0, GAMMA_NH3=1.0,
+              zeta_H2=1.2163, zeta_He=0.0291, zeta_NH3=0.5152, Z_H2=0.8873, Z_He=0.8994, Z_NH3=2.0 / 3.0,
+              d=-0.0627, Con=0.9862)
+    P_trans, dP_up, dP_down = 15.0, 5.0, 3.0
+    if P > P_trans + dP_up:
+        return hi
+    if P <= P_trans - dP_down:
+        return lo
+    w = (15.0 - dP_down - P) / (dP_up + dP_down)
+    out = {}
+    for k in lo:
+        out[k] = lo[k] if k in ('gnu_NH3', 'GAMMA_NH3', 'zeta_NH3', 'Z_NH3') else lo[k] + (lo[k] - hi[k]) * w
+    return out
+
+
+def nh3_kd(freq, T, P, X, P_dict, other_dict, **kwargs):
+    """nh3_kd.py:115-351: the consistent model with pressure-switched constants and no 30 GHz split."""
+    units, cat, _, _ = _par(kwargs)
+    freq = np.array(freq, dtype=np.float64)
+    P_h2 = P * X[P_dict['H2']]
+    P_he = P * X[P_dict['HE']]
+    P_nh3 = P * X[P_dict['NH3']]
+    return _nh3_consistent(freq, T, P, P_h2, P_he, P_nh3, cat, units, None, None, consts=nh3_kd_constants(P),
+                           clamp_le=True)
+
+
+def nh3_bg(freq, T, P, X, P_dict, other_dict, **kwargs):
+    """nh3_bg.py:26-74: Berge-Gulkis Ben-Reuven sum over the nh3.npz catalog (scalar loops in the reference)."""
+    units, cat, _, _ = _par(kwargs)
+    T0 = 296.0
+    P_h2 = P * X[P_dict['H2']]
+    P_he = P * X[P_dict['HE']]
+    P_nh3 = P * X[P_dict['NH3']]
+    f0, I0, E, G0 = cat.get('nh3_sjs')
+    delta = -0.45 * P_nh3
+    out = []
+    for f in np.asarray(freq, dtype=np.float64):
+        f2 = f**2
+        acc = 0.0
+        for i in range(len(f0)):
+            gamma = pow((T0 / T), 2.0 / 3.0) * (2.318 * P_h2 + 0.790 * P_he + G0[i] * 0.750 * P_nh3)
+            g2 = gamma**2
+            zeta = pow((T0 / T), 2.0 / 3.0) * (1.920 * P_h2 + 0.300 * P_he + G0[i] * 0.490 * P_nh3)
+            z2 = zeta**2
+            ITG = I0[i] * np.exp(-((1.0 / T) - (1.0 / T0)) * E[i] * _HCK)
+            num = (gamma - zeta) * f2 + (gamma + zeta) * (pow(f0[i] + delta, 2.0) + g2 - z2)
+            den = pow((f2 - pow(f0[i] + delta, 2.0) - g2 + z2), 2.0) + 4.0 * f2 * g2
+            acc += _GHZ * 2.0 * pow(f / f0[i], 2.0) * num / (np.pi * den) * ITG
+        a = _COEF_GEISA * (P_nh3 / T0) * pow((T0 / T), 3.0 / 2.0 + 2) * acc
+        if units == 'dBperkm':
+            a *= OPTICALDEPTH_TO_DB
+        out.append(a)
+    return np.array(out)
 
 
 def _nh3_split(family, freq, T, P, X, P_dict, other_dict, **kwargs):
@@ -284,6 +347,17 @@ def _nh3_pblend(lowp, freq, T, P, X, P_dict, other_dict, **kwargs):
     a2 = nh3_sjs(freq, T, P, X, P_dict, other_dict, **kwargs)
     a1 = lowp(freq, T, P, X, P_dict, other_dict, **kwargs)
     W = (P - PLower) / (PHigher - PLower)
+    return W * a2 + (1.0 - W) * a1
+
+
+def nh3_sjsd(freq, T, P, X, P_dict, other_dict, **kwargs):
+    """nh3_sjsd.py:6-24: sjs outside 10..100 bar, triangular blend with nh3_kd (peak at 35 bar) inside."""
+    PLower, PMid, PHigher = 10.0, 35.0, 100.0
+    if P < PLower or P > PHigher:
+        return nh3_sjs(freq, T, P, X, P_dict, other_dict, **kwargs)
+    a1 = np.array(nh3_sjs(freq, T, P, X, P_dict, other_dict, **kwargs))
+    a2 = np.array(nh3_kd(freq, T, P, X, P_dict, other_dict, **kwargs))
+    W = (P - PLower) / (PMid - PLower) if P < PMid else 1 - (P - PMid) / (PHigher - PMid)
     return W * a2 + (1.0 - W) * a1
 
 
@@ -599,7 +673,7 @@ def clouds_idp(freq, T, P, cloud, cloud_dict, other_dict, **kwargs):
 
 
 FORMALISMS = {
-    'nh3_hs': nh3_hs, 'nh3_dbs': nh3_dbs, 'nh3_sjs': nh3_sjs,
+    'nh3_hs': nh3_hs, 'nh3_dbs': nh3_dbs, 'nh3_sjs': nh3_sjs, 'nh3_kd': nh3_kd, 'nh3_bg': nh3_bg, 'nh3_sjsd': nh3_sjsd,
     'nh3_hs_sjs': nh3_hs_sjs, 'nh3_dbs_sjs': nh3_dbs_sjs,
     'h2s_ddb': h2s_ddb, 'ph3_jh': ph3_jh, 'co_ddb': co_ddb, 'h2o_bk': h2o_bk,
     'h2_jj_ddb': h2_jj_ddb, 'h2_jj': h2_jj, 'clouds_idp': clouds_idp,

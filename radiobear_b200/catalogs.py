@@ -66,7 +66,8 @@ def table(name, truncate_strength=None, truncate_freq=None):
 # which kernel catalogs a formalism reads, and which gas's truncation settings apply
 FORMALISM_CATALOGS = {
     'nh3_hs': ['nh3_inv', 'nh3_rot', 'nh3_v2'], 'nh3_dbs': ['nh3_inv', 'nh3_rot', 'nh3_v2'],
-    'nh3_sjs': ['nh3_sjs'],
+    'nh3_sjs': ['nh3_sjs'], 'nh3_bg': ['nh3_sjs'], 'nh3_kd': ['nh3_inv', 'nh3_rot', 'nh3_v2'],
+    'nh3_sjsd': ['nh3_inv', 'nh3_rot', 'nh3_v2', 'nh3_sjs'],
     'nh3_hs_sjs': ['nh3_inv', 'nh3_rot', 'nh3_v2', 'nh3_sjs'],
     'nh3_dbs_sjs': ['nh3_inv', 'nh3_rot', 'nh3_v2', 'nh3_sjs'],
     'h2s_ddb': ['h2s'], 'ph3_jh': ['ph3'], 'h2o_bk': ['h2o'], 'co_ddb': ['co'],

@@ -224,12 +224,35 @@ __global__ void __launch_bounds__(kThreads) alpha_lines_kernel(const __grid_cons
   const double P_co = P * ld0(k.gas[RB_GAS_CO], l);
   const double Tdiv = 300.0 / T;
 
-  // which NH3 branches this layer needs (nh3_hs_sjs.py:10-25)
-  const bool nh3_blend = (k.nh3_form == RB_F_NH3_HS_SJS || k.nh3_form == RB_F_NH3_DBS_SJS);
-  const bool use_low = (k.nh3_form == RB_F_NH3_HS || k.nh3_form == RB_F_NH3_DBS) || (nh3_blend && !(P > 2000.0));
-  const bool use_sjs = (k.nh3_form == RB_F_NH3_SJS) || (nh3_blend && !(P < 400.0));
-  const double(&cl)[14] = c_nh3inv[k.nh3_family][0];
-  const double(&ch)[14] = c_nh3inv[k.nh3_family][1];
+  // which NH3 branches this layer needs and how they blend: a = wb * a_b + (1 - wb) * a_a
+  //   nh3_hs_sjs / nh3_dbs_sjs (nh3_hs_sjs.py:10-25): (a_a, a_b) = (low, sjs), wb = (P-400)/1600 in 400..2000 bar
+  //   nh3_sjsd (nh3_sjsd.py:6-24):                    (a_a, a_b) = (sjs, kd),  triangular wb peaking at 35 bar
+  const int nform = k.nh3_form;
+  const bool nh3_blend = (nform == RB_F_NH3_HS_SJS || nform == RB_F_NH3_DBS_SJS);
+  const bool sjsd_mix = (nform == RB_F_NH3_SJSD) && !(P < 10.0 || P > 100.0);
+  const bool use_low = (nform == RB_F_NH3_HS || nform == RB_F_NH3_DBS || nform == RB_F_NH3_KD) ||
+                       (nh3_blend && !(P > 2000.0)) || sjsd_mix;
+  const bool use_sjs = (nform == RB_F_NH3_SJS || nform == RB_F_NH3_BG || nform == RB_F_NH3_SJSD) ||
+                       (nh3_blend && !(P < 400.0));
+  // inversion-line constants: tabulated per band (hs, dbs) or switched on pressure (kd, nh3_kd.py:160-195)
+  double cl[14], ch[14];
+  if (k.nh3_family < 2) {
+#pragma unroll
+    for (int i = 0; i < 14; ++i) { cl[i] = c_nh3inv[k.nh3_family][0][i]; ch[i] = c_nh3inv[k.nh3_family][1][i]; }
+  } else {
+    const double hiP[14] = {1.6361, 0.4555, 0.7298, 0.8, 0.5, 1.0, 1.1313, 0.1, 0.5152, 0.6234, 0.5, 2.0 / 3.0, 0.2, 1.3746};
+    const double loP[14] = {1.7465, 0.9779, 0.7298, 0.8202, 1.0, 1.0, 1.2163, 0.0291, 0.5152, 0.8873, 0.8994, 2.0 / 3.0,
+                            -0.0627, 0.9862};
+    const double w = (15.0 - 3.0 - P) / (5.0 + 3.0);
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+      double v;
+      if (P > 20.0) v = hiP[i];
+      else if (P <= 12.0) v = loP[i];
+      else v = (i == 2 || i == 5 || i == 8 || i == 11) ? loP[i] : loP[i] + (loP[i] - hiP[i]) * w;
+      cl[i] = ch[i] = v;
+    }
+  }
 
   // ---- phase 1: pow() jobs, one per lane of warp 0 -------------------------------------------
   if (warp == 0 && lane < PW_COUNT) {
@@ -357,11 +380,14 @@ __global__ void __launch_bounds__(kThreads) alpha_lines_kernel(const __grid_cons
     }
     const double Sg0 = th * (SG_H2 * P_h2 + SG_He * P_he), SgN = th * SG_N * P_nh3;
     const double Sz0 = th * (SZ_H2 * P_h2 + SZ_He * P_he), SzN = th * SZ_N * P_nh3;
-    const double Jg0 = th * (1.690 * P_h2 + 0.750 * P_he), JgN = th * 0.6 * P_nh3;
-    const double Jz0 = th * (1.350 * P_h2 + 0.300 * P_he), JzN = th * 0.2 * P_nh3;
+    // "Joiner" set; nh3_bg (nh3_bg.py:42-49) is the same Ben-Reuven sum with its own constants at every
+    // frequency and without the deep-atmosphere pressure scale
+    const bool bg = (nform == RB_F_NH3_BG);
+    const double Jg0 = th * ((bg ? 2.318 : 1.690) * P_h2 + (bg ? 0.790 : 0.750) * P_he), JgN = th * (bg ? 0.750 : 0.6) * P_nh3;
+    const double Jz0 = th * ((bg ? 1.920 : 1.350) * P_h2 + 0.300 * P_he), JzN = th * (bg ? 0.490 : 0.2) * P_nh3;
     const double delta = -0.45 * P_nh3;
     const double expfac = -((1.0 / T) - (1.0 / 296.0)) * kHck;
-    const double pref = kCoefGeisa * (P_nh3 / 296.0) * s_pow[PW_T296_35] * (1.0 + P / 1.0E5) * kGHz * (2.0 / kPi);
+    const double pref = kCoefGeisa * (P_nh3 / 296.0) * s_pow[PW_T296_35] * (bg ? 1.0 : (1.0 + P / 1.0E5)) * kGHz * (2.0 / kPi);
     const double* f0p = k.cat[RB_CAT_NH3_SJS];
     const int n = k.ncat[RB_CAT_NH3_SJS];
     const double *I0 = f0p + n, *E = f0p + 2 * n, *G0 = f0p + 3 * n;
@@ -501,8 +527,8 @@ __global__ void __launch_bounds__(kThreads) alpha_lines_kernel(const __grid_cons
         all_S = all_S && (f[j] <= 26.0);
         all_J = all_J && (f[j] >= 34.0);
       }
-      all_S = __all_sync(0xffffffffu, all_S);
-      all_J = __all_sync(0xffffffffu, all_J);
+      all_S = __all_sync(0xffffffffu, all_S) && nform != RB_F_NH3_BG;
+      all_J = __all_sync(0xffffffffu, all_J) || nform == RB_F_NH3_BG;
       const int n = k.ncat[RB_CAT_NH3_SJS];
       if (all_S) {
         loop_br4<FPT, NEWTON>(tS, n, slice, K, x, s_sjs);
@@ -624,13 +650,19 @@ __global__ void __launch_bounds__(kThreads) alpha_lines_kernel(const __grid_cons
       double a_low = 0.0, a_sjs = 0.0;
       if (use_low) {
         a_low = xx * s_low[j] * unit;
-        if (a_low < 0.0) a_low = 1.0E-8;  // nh3_hs.py:311-312 (in output units)
+        // nh3_hs.py:311-312: `< 0 -> 1e-8` in output units; nh3_kd.py:344-349 uses `<= 0`
+        if (a_low < 0.0 || (k.nh3_family == 2 && a_low <= 0.0)) a_low = 1.0E-8;
       }
       if (use_sjs) a_sjs = xx * s_sjs[j] * unit;
       double a;
       if (use_low && use_sjs) {
-        const double W = (P - 400.0) / (2000.0 - 400.0);
-        a = W * a_sjs + (1.0 - W) * a_low;
+        if (nform == RB_F_NH3_SJSD) {
+          const double W = (P < 35.0) ? (P - 10.0) / (35.0 - 10.0) : 1.0 - (P - 35.0) / (100.0 - 35.0);
+          a = W * a_low + (1.0 - W) * a_sjs;
+        } else {
+          const double W = (P - 400.0) / (2000.0 - 400.0);
+          a = W * a_sjs + (1.0 - W) * a_low;
+        }
       } else {
         a = use_low ? a_low : a_sjs;
       }
@@ -703,7 +735,8 @@ __global__ void __launch_bounds__(kThreads) alpha_lines_kernel(const __grid_cons
 
 int family_of(int form) {
   switch (form) {
-    case RB_F_NH3_HS: case RB_F_NH3_DBS: case RB_F_NH3_SJS: case RB_F_NH3_HS_SJS: case RB_F_NH3_DBS_SJS: return 0;
+    case RB_F_NH3_HS: case RB_F_NH3_DBS: case RB_F_NH3_SJS: case RB_F_NH3_HS_SJS: case RB_F_NH3_DBS_SJS:
+    case RB_F_NH3_KD: case RB_F_NH3_SJSD: case RB_F_NH3_BG: return 0;
     case RB_F_H2S_DDB: return 1;
     case RB_F_PH3_JH: return 2;
     case RB_F_H2O_BK: return 3;
@@ -756,10 +789,12 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
     if (*slot >= 0) return rb_fail(ctx, RB_ERR_INVALID, "alpha: two formalisms of the same gas family");
     *slot = c;
   }
-  k.nh3_family = (k.nh3_form == RB_F_NH3_DBS || k.nh3_form == RB_F_NH3_DBS_SJS) ? 1 : 0;
+  k.nh3_family = (k.nh3_form == RB_F_NH3_DBS || k.nh3_form == RB_F_NH3_DBS_SJS) ? 1
+                 : (k.nh3_form == RB_F_NH3_KD || k.nh3_form == RB_F_NH3_SJSD) ? 2 : 0;
   for (int i = 0; i < RB_NUM_CATALOGS; ++i) { k.cat[i] = ctx->cat[i]; k.ncat[i] = ctx->cat_n[i]; }
-  const bool need_low = k.slot_nh3 >= 0 && k.nh3_form != RB_F_NH3_SJS;
-  const bool need_sjs = k.slot_nh3 >= 0 && k.nh3_form != RB_F_NH3_HS && k.nh3_form != RB_F_NH3_DBS;
+  const bool need_low = k.slot_nh3 >= 0 && k.nh3_form != RB_F_NH3_SJS && k.nh3_form != RB_F_NH3_BG;
+  const bool need_sjs = k.slot_nh3 >= 0 && k.nh3_form != RB_F_NH3_HS && k.nh3_form != RB_F_NH3_DBS &&
+                        k.nh3_form != RB_F_NH3_KD;
   auto need_cat = [&](int id, const char* nm) -> int {
     if (!ctx->cat[id] || ctx->cat_n[id] <= 0) return rb_fail(ctx, RB_ERR_INVALID, "alpha: line catalog '%s' not set", nm);
     return RB_OK;
@@ -777,6 +812,7 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
     if (f <= 30.0) k.any_lo = 1; else k.any_hi = 1;
     if (f <= 26.0) k.any_S = 1; else if (f >= 34.0) k.any_J = 1; else k.any_I = 1;
   }
+  if (k.nh3_form == RB_F_NH3_BG) { k.any_S = 0; k.any_I = 0; k.any_J = 1; }   // one constant set at every frequency
   // tiling: lanes = 32*FPT frequencies per warp; K line slices per group when F is small
   k.fpt = (k.F >= 512) ? 2 : 1;
   k.ngroups = (k.F + 32 * k.fpt - 1) / (32 * k.fpt);

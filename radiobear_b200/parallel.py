@@ -128,7 +128,7 @@ def run_points_sharded(planet, pts, atm, alpha, out_f32=True, rows=None):
     slab_t = torch.as_tensor(np.ascontiguousarray(alpha.slab), device=dev)
     F = slab_t.shape[1]
     if e > s:
-        b_t = torch.as_tensor(np.ascontiguousarray(pts[s:e], dtype=np.float64), device=dev)
+        b_t = torch.as_tensor(np.array(pts[s:e], dtype=np.float64), device=dev)      # private writable copy
         local = engine.rt_batch_dev(radius, nidx[0], nidx[1], b_t, slab_t, T_t, cfg.Req, cfg.Rpol,
                                     [float(cfg.orientation[0]), float(cfg.orientation[1])], cfg.gtype,
                                     getattr(cfg, 'limb', 'shape'), out_f32=out_f32)

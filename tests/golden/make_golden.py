@@ -8,7 +8,7 @@ scratch work directory bootstrapped the way scripts/initial_planet_setup.py:12-3
 
     python tests/golden/make_golden.py [section ...]
 
-sections: atm plugins plugins_notrunc alpha rays tb neptune image   (default: all)
+sections: atm fileio plugins plugins_nh3_extra plugins_notrunc alpha rays tb neptune image   (default: all)
 
 Every array is float64 exactly as the reference produced it; nothing is post-processed.
 Reference defects driven around: log-sweep strings and float image
@@ -184,6 +184,34 @@ def sec_plugins():
     save('plugins_trunc.npz', **_plugin_table(True))
 
 
+def sec_plugins_nh3_extra():
+    """The remaining NH3 formalisms behind the same plugin API: nh3_kd (prints P on every call, nh3_kd.py:146),
+    nh3_sjsd, nh3_bg; extra points cover the 12..20 bar constant switch and the 10..100 bar blend."""
+    import importlib
+    pts, C, Cl, atm = _points()
+    extra = []
+    base = atm.gas[:, 500].copy()
+    for T, P in [(330.0, 9.99), (335.0, 10.0), (340.0, 11.9), (345.0, 12.0), (350.0, 15.0), (360.0, 19.99),
+                 (362.0, 20.0), (365.0, 20.01), (380.0, 35.0), (420.0, 60.0), (500.0, 100.0), (505.0, 100.5)]:
+        g = base.copy()
+        g[C['T']], g[C['P']] = T, P
+        extra.append(g)
+    pts = np.concatenate([pts, np.array(extra)])
+    cpath = os.path.join(REF, 'radiobear', 'constituents')
+    sys.path.append(os.path.join(cpath, 'nh3'))
+    out = {'points': pts, 'freqs': np.array(PLUGIN_FREQS), 'C_keys': np.array(sorted(C, key=lambda k: C[k]))}
+    for name in ['nh3_kd', 'nh3_sjsd', 'nh3_bg']:
+        mod = importlib.import_module(name)
+        for units in ['invcm', 'dBperkm']:
+            res = []
+            for g in pts:
+                r = mod.alpha(PLUGIN_FREQS, g[C['T']], g[C['P']], g, C, {}, units=units, truncate_freq=None,
+                              truncate_strength=None, path=os.path.join(cpath, 'nh3'), verbose=False)
+                res.append(np.asarray(r, dtype=float))
+            out['{}__{}'.format(name, units)] = np.array(res)
+    save('plugins_nh3_extra.npz', **out)
+
+
 def sec_plugins_notrunc():
     """No-truncation variant: the reference caches catalogs per process (h2s_ddb.py:11, ph3_jh.py:14),
     so this runs in a fresh interpreter."""
@@ -331,7 +359,31 @@ def sec_image():
     save('image_c4.npz', freqs=np.array(freqs), grid=grid, pick_iy_ix=pick, tb=np.array(tbs), imsize=n)
 
 
-SECTIONS = {'atm': sec_atm, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
+FILEIO_CASES = [('spectrum', [[0.0, 0.0], [0.5, 0.25]], [[100.123, 200.5, 300.25], [90.1, 80.2, 70.3]]),
+                ('spectrum', ['disc'], [[100.123, 200.5, 300.25]]),
+                ('profile', [[0.1 * i, 0.0] for i in range(6)], [[100.0 + i, 200.5 + i, 300.25 + i] for i in range(6)]),
+                ('image', [[0, 0]] * 25, [[float(i * j) + 0.123 for i in range(4)] for j in range(3)])]
+
+
+def sec_fileio():
+    """fileIO.FileIO.write (fileIO.py:19-107): the text a reference run writes for each output type."""
+    from radiobear import fileIO, data_handling
+    out = {}
+    for n, (typ, b, Tb) in enumerate(FILEIO_CASES):
+        d = data_handling.Data()
+        d.set('f', [1.0, 10.5, 22.0])
+        d.set('freqUnit', 'GHz')
+        d.set('b', b)
+        d.set('Tb', Tb)
+        d.set('type', typ)
+        d.set('header', {'z': '# z line', 'a': '# a line', 'data-type': '#* type:  ' + typ})
+        fn = fileIO.FileIO().write('fileio_case.dat', d)
+        out['case{}'.format(n)] = np.array(open(fn).read())
+        out['type{}'.format(n)] = np.array(typ)
+    save('fileio.npz', **out)
+
+
+SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
             'rays': sec_rays, 'tb': sec_tb, 'neptune': sec_neptune, 'image': sec_image}
 
 if __name__ == '__main__':

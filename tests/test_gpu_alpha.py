@@ -87,7 +87,7 @@ def test_option_variants_and_clouds(eng):
         eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('h2', 'h2_jj_ddb')],
                          other_dicts={'h2': {'h2state': 'x'}})
     with pytest.raises(NotImplementedError):
-        eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('nh3', 'nh3_kd')])
+        eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('h2', 'h2_orton')])
 
 
 def test_no_truncation(eng):
@@ -189,3 +189,21 @@ def test_alpha_object_api(tmp_path):
     assert np.max(relerr(one, al['layers'][:, 500])) < TIGHT
     with pytest.raises(ValueError):
         A.get_layers(list(al['freqs']), atm, scale={'bogus': [1.0] * 1000})
+
+
+@pytest.mark.parametrize('name', ['nh3_kd', 'nh3_sjsd', 'nh3_bg'])
+@pytest.mark.parametrize('units', ['invcm', 'dBperkm'])
+def test_remaining_nh3_formalisms(eng, name, units):
+    """nh3_kd (pressure-switched constants), nh3_sjsd (10..100 bar blend), nh3_bg."""
+    import importlib
+    g = golden('plugins_nh3_extra.npz')
+    C = keymap(g['C_keys'])
+    gas = np.ascontiguousarray(g['points'].T)
+    out = eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('nh3', name)], units=units)
+    ref = g['{}__{}'.format(name, units)]
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    assert np.nanmax(relerr(out, ref)) < TIGHT
+    mod = importlib.import_module('radiobear_b200.constituents.nh3.' + name)
+    p = g['points'][-4]
+    a = mod.alpha(list(g['freqs']), p[C['T']], p[C['P']], p, C, {}, units=units)
+    assert np.nanmax(relerr(a, ref[-4])) < TIGHT

@@ -159,3 +159,22 @@ def test_row_partition_balances_on_disc_pixels():
         assert all(parts[i][1] == parts[i + 1][0] for i in range(n - 1))
         w = [parallel.row_weights(grid, q)[a:b].sum() for a, b in parts]
         assert max(w) <= 1.25 * (sum(w) / n) + 700
+
+
+def test_fileio_text_formats_match_reference(tmp_path):
+    """fileIO.write: byte-identical files for spectrum / disc spectrum / profile / image (fileIO.py:19-107)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    from make_golden import FILEIO_CASES
+    from radiobear_b200 import fileIO
+    g = golden('fileio.npz')
+    for n, (typ, b, Tb) in enumerate(FILEIO_CASES):
+        d = data_handling.Data()
+        d.set('f', [1.0, 10.5, 22.0])
+        d.set('freqUnit', 'GHz')
+        d.set('b', b)
+        d.set('Tb', Tb)
+        d.set('type', typ)
+        d.set('header', {'z': '# z line', 'a': '# a line', 'data-type': '#* type:  ' + typ})
+        fn = fileIO.FileIO(directory=str(tmp_path)).write(str(tmp_path / 'out{}.dat'.format(n)), d)
+        assert open(fn).read() == str(g['case{}'.format(n)])

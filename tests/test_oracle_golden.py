@@ -174,3 +174,14 @@ def test_image_subset_c4():
     assert np.array_equal(np.isnan(Tb), np.isnan(ref))
     assert np.nanmax(np.abs(Tb - ref)) < 1e-6
     assert np.all(im['tb'][136:] == 2.725)
+
+
+@pytest.mark.parametrize('name', ['nh3_kd', 'nh3_sjsd', 'nh3_bg'])
+def test_remaining_nh3_formalisms(name):
+    g = golden('plugins_nh3_extra.npz')
+    C = keymap(g['C_keys'])
+    for units in ['invcm', 'dBperkm']:
+        for p, r in zip(g['points'], g['{}__{}'.format(name, units)]):
+            a = ao.FORMALISMS[name](g['freqs'], p[C['T']], p[C['P']], p, C, {}, units=units)
+            assert np.array_equal(np.isnan(a), np.isnan(r))
+            assert np.nanmax(relerr(a, r)) < 1e-12
