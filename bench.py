@@ -377,6 +377,11 @@ def run_gpu(args):
     k_geo, _ = per_step_ms('geometry')
     k_rt, rt_chunks = per_step_ms('rt')
     fp64_peak = ctx.fp64_peak_tflops(20000) if rank == 0 else 0.0
+    # executed (ray, freq, segment) steps of one step of this rank (the tau_cut exit skips the rest): untimed pass
+    ctx.count_steps(True)
+    step()
+    torch.cuda.synchronize()
+    steps_executed = ctx.count_steps(False)
 
     # ---- end to end through the public API (host buffers) ----------------------------------------
     planet = Planet('jupiter', atmosphere=atm, verbose=False)
@@ -410,7 +415,8 @@ def run_gpu(args):
         # algorithmic bytes of one rt_integrate launch: ds slab read for the on-disc rays +
         # alpha slab + T + float32 Tb out for every pixel of the rank
         rt_bytes = n_on_rank * S * 8 + F * L * 8 + L * 8 + len(pts) * F * 4
-        rt_flops = float(n_on_rank) * F * (S - 1) * 20.0      # 12 FP64 instructions = 20 flops per (ray, freq, segment), DESIGN.md 3.3
+        rt_steps_all = float(n_on_rank) * F * (S - 1)
+        rt_flops = float(steps_executed) * 20.0               # 12 FP64 instructions = 20 flops per executed segment-step, DESIGN.md 3.3
         roofline = {'bound': 'hbm', 'kernel': 'rt_integrate_rays_kernel', 'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9,
                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': rt_bytes / (rt_ms * 1e-3) / 1e9 / hbm_peak,
                     'traffic': None, 'peak_source': peak_src, 'ms_per_launch': rt_ms, 'launches_per_step': rt_chunks,
@@ -418,7 +424,9 @@ def run_gpu(args):
                     'fp64': {'achieved_tflops': rt_flops / (rt_ms * 1e-3) / 1e12, 'peak_tflops': fp64_peak,
                              'frac': rt_flops / (rt_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
                              'flops_per_segment_step': 20, 'peak_source': 'rb_probe_fp64_peak (DFMA, same box, same run)',
-                             'note': 'algorithmic count over all (ray,freq,segment); the tau>100 early exit skips part of them'}}
+                             'segment_steps_executed': int(steps_executed), 'segment_steps_all': rt_steps_all,
+                             'note': 'flops counted over the segment-steps actually executed (in-kernel counter, untimed pass); '
+                                     'the tau > tau_cut exit skips the rest of each ray'}}
         cores = 1
         cpu_v, cpu_desc, _ = cpu_sample(cores, n_pix_per_core=12, n_lay_per_core=48) if world == 1 else (None, None, None)
         line = {

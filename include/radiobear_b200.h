@@ -65,6 +65,10 @@ int64_t rb_kernel_timed_count(const rb_context* ctx, int which);
 /* Ray-chunk pipeline depth for large requests: n chunks whose geometry / integration / device->host copy
  * overlap on three streams (0 = automatic, 1 = no pipelining). */
 int rb_set_rt_chunks(rb_context* ctx, int n);
+/* Measurement aid: count the (ray, freq, segment) steps the integration kernel actually executes (the
+ * tau_cut early exit skips the rest).  enable = 1 resets and starts counting, 0 stops; the count is returned
+ * (after synchronising the context stream). */
+int64_t rb_count_steps(rb_context* ctx, int enable);
 
 /* ---- line catalogs --------------------------------------------------------------------- *
  * Replaces the per-plugin npz readers: nh3_hs.py:62-67, nh3_sjs.py:17-23, h2s_ddb.py:14-39,
@@ -140,6 +144,11 @@ typedef struct rb_alpha_desc {
  * A single plugin call (constituents/<gas>/<formalism>.alpha, alpha.py:210) is n_layers = 1.   */
 int rb_alpha_layers(rb_context* ctx, const rb_alpha_desc* desc, double* out_total, double* out_cube);
 int rb_alpha_layers_dev(rb_context* ctx, const rb_alpha_desc* desc, double* out_total, double* out_cube);
+/* Alpha.total_layer_alpha on a cached per-constituent cube (get_alpha='memory'/'file', alpha.py:151-192,
+ * 224-225): out_total[l][f] = sum_c scale[c][l] * cube[l][f][c]; when out_cube != NULL it receives the scaled
+ * cube (what a following save_alpha stores).  scale may be NULL (all ones).  Host pointers. */
+int rb_alpha_scale_sum(rb_context* ctx, int32_t n_layers, int32_t n_freqs, int32_t n_constituents,
+                       const double* cube, const double* scale, double* out_total, double* out_cube);
 
 /* ---- ray geometry + radiative transfer (hot path B) ------------------------------------- */
 #define RB_GTYPE_ELLIPSE 0 /* shape.py:223-274 */

@@ -80,9 +80,11 @@ def load():
         'rb_kernel_ms_history': (C.c_int, [vp, C.c_int, vp, C.c_int]),
         'rb_kernel_timed_count': (i64, [vp, C.c_int]),
         'rb_set_rt_chunks': (C.c_int, [vp, C.c_int]),
+        'rb_count_steps': (i64, [vp, C.c_int]),
         'rb_set_catalog': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
         'rb_alpha_layers': (C.c_int, [vp, C.POINTER(AlphaDesc), vp, vp]),
         'rb_alpha_layers_dev': (C.c_int, [vp, C.POINTER(AlphaDesc), vp, vp]),
+        'rb_alpha_scale_sum': (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp]),
         'rb_compute_ds': (C.c_int, [vp, C.POINTER(GeometryDesc), i64, vp, vp, vp, vp]),
         'rb_rt_batch': (C.c_int, [vp, C.POINTER(GeometryDesc), C.POINTER(RtDesc), i64, vp, vp, vp, i64, vp, vp, vp]),
         'rb_rt_batch_dev': (C.c_int, [vp, C.POINTER(GeometryDesc), C.POINTER(RtDesc), i64, vp, vp, vp]),
@@ -101,8 +103,8 @@ def load():
 EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error', 'rb_set_stream', 'rb_use_own_stream',
                     'rb_synchronize',
                     'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_kernel_timed_count',
-                    'rb_set_rt_chunks', 'rb_set_catalog', 'rb_alpha_layers',
-                    'rb_alpha_layers_dev', 'rb_compute_ds', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
+                    'rb_set_rt_chunks', 'rb_count_steps', 'rb_set_catalog', 'rb_alpha_layers',
+                    'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_compute_ds', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
                     'rb_probe_fp64_peak', 'rb_probe_rcp']
 
 _EXC = {RB_ERR_INVALID: ValueError, RB_ERR_CUDA: RadiobearB200Error, RB_ERR_NOMEM: MemoryError,
@@ -173,6 +175,10 @@ class Context:
 
     def kernel_timed_count(self, which):
         return int(self.lib.rb_kernel_timed_count(self.h, {'alpha': 0, 'geometry': 1, 'rt': 2}.get(which, which)))
+
+    def count_steps(self, enable):
+        """Start (True) / stop (False) counting integrated segment-steps; returns the count so far."""
+        return int(self.lib.rb_count_steps(self.h, 1 if enable else 0))
 
     def set_rt_chunks(self, n):
         self.check(self.lib.rb_set_rt_chunks(self.h, int(n)))

@@ -118,11 +118,9 @@ class Alpha:
         if from_cache:
             # cached per-constituent cube [L][F][C]: only the scale-sum is redone (alpha.py:224-225)
             self.read_alpha_data(get_alpha)
-            cube = np.asarray(self.alpha_data, dtype=np.float64)
-            sm = self.get_layer_scale(scale, L)
-            if sm is not None:
-                cube = cube * sm.T[:, None, :]
-            slab = cube.sum(axis=2)
+            res = engine.alpha_scale_sum(np.asarray(self.alpha_data, dtype=np.float64), self.get_layer_scale(scale, L),
+                                         want_cube=to_cache)
+            slab, cube = res if to_cache else (res, None)
         else:
             res = engine.alpha_layers(np.asarray(freqs, dtype=np.float64), atm.gas[C['T']], atm.gas[C['P']], atm.gas, C,
                                       cloud=atm.cloud if np.size(atm.cloud) else None, cloud_dict=atm.config.Cl,

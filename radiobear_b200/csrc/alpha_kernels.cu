@@ -865,3 +865,31 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   ctx->launches += 1;
   return RB_OK;
 }
+
+
+// ---- scale-sum of a cached per-constituent cube (alpha.py:151-192) ----------------------------------
+namespace {
+__global__ void alpha_scale_sum_kernel(const double* __restrict__ cube, const double* __restrict__ scale, int L, int F,
+                                       int C, double* __restrict__ total, double* __restrict__ out_cube) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (layer, freq)
+  if (idx >= (size_t)L * F) return;
+  const int l = (int)(idx / F);
+  double t = 0.0;
+  for (int c = 0; c < C; ++c) {                                       // left-to-right like the reference
+    double v = cube[idx * C + c];
+    if (scale) v *= scale[(size_t)c * L + l];
+    if (out_cube) out_cube[idx * C + c] = v;
+    t += v;
+  }
+  total[idx] = t;
+}
+}  // namespace
+
+int rb_launch_alpha_scale_sum(rb_context* ctx, const double* cube, const double* scale, int L, int F, int C,
+                              double* total, double* out_cube) {
+  const size_t n = (size_t)L * F;
+  alpha_scale_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(cube, scale, L, F, C, total, out_cube);
+  RB_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}

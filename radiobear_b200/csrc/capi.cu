@@ -153,6 +153,23 @@ int64_t rb_kernel_timed_count(const rb_context* ctx, int which) {
   return (ctx && which >= 0 && which <= 2) ? ctx->ev_count[which] : 0;
 }
 
+int64_t rb_count_steps(rb_context* ctx, int enable) {
+  if (!ctx) return -1;
+  cudaSetDevice(ctx->device);
+  unsigned long long h = 0;
+  static unsigned long long* dev = nullptr;
+  if (!dev && cudaMalloc(&dev, sizeof(unsigned long long)) != cudaSuccess) return -1;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->step_counter) cudaMemcpy(&h, dev, sizeof(h), cudaMemcpyDeviceToHost);
+  if (enable) {
+    cudaMemset(dev, 0, sizeof(unsigned long long));
+    ctx->step_counter = dev;
+  } else {
+    ctx->step_counter = nullptr;
+  }
+  return (int64_t)h;
+}
+
 int rb_set_rt_chunks(rb_context* ctx, int n) {
   if (!ctx || n < 0) return RB_ERR_INVALID;
   ctx->rt_chunks = n;
@@ -236,6 +253,29 @@ int rb_alpha_layers(rb_context* ctx, const rb_alpha_desc* d, double* out_total, 
   RB_TRY(rb_launch_alpha(ctx, &dd, d->freqs, (double*)p_tot, (double*)p_cube));
   RB_CUDA(ctx, cudaMemcpyAsync(out_total, p_tot, L * F * 8, cudaMemcpyDeviceToHost, s));
   if (out_cube) RB_CUDA(ctx, cudaMemcpyAsync(out_cube, p_cube, L * F * C * 8, cudaMemcpyDeviceToHost, s));
+  RB_CUDA(ctx, cudaStreamSynchronize(s));
+  return RB_OK;
+}
+
+int rb_alpha_scale_sum(rb_context* ctx, int32_t L, int32_t F, int32_t C, const double* cube, const double* scale,
+                       double* out_total, double* out_cube) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (!cube || !out_total || L <= 0 || F <= 0 || C <= 0) return rb_fail(ctx, RB_ERR_INVALID, "scale_sum: bad arguments");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)L * F;
+  void *p_cube, *p_scale = nullptr, *p_tot;
+  RB_TRY(rb_ensure(ctx, RB_BUF_CUBE, n * C * 8, &p_cube));
+  RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, n * 8, &p_tot));
+  cudaStream_t s = ctx->stream;
+  RB_CUDA(ctx, cudaMemcpyAsync(p_cube, cube, n * C * 8, cudaMemcpyHostToDevice, s));
+  if (scale) {
+    RB_TRY(rb_ensure(ctx, RB_BUF_SCALE, (size_t)C * L * 8, &p_scale));
+    RB_CUDA(ctx, cudaMemcpyAsync(p_scale, scale, (size_t)C * L * 8, cudaMemcpyHostToDevice, s));
+  }
+  RB_TRY(rb_launch_alpha_scale_sum(ctx, (const double*)p_cube, (const double*)p_scale, L, F, C, (double*)p_tot,
+                                   out_cube ? (double*)p_cube : nullptr));
+  RB_CUDA(ctx, cudaMemcpyAsync(out_total, p_tot, n * 8, cudaMemcpyDeviceToHost, s));
+  if (out_cube) RB_CUDA(ctx, cudaMemcpyAsync(out_cube, p_cube, n * C * 8, cudaMemcpyDeviceToHost, s));
   RB_CUDA(ctx, cudaStreamSynchronize(s));
   return RB_OK;
 }

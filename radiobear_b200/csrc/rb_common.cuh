@@ -39,6 +39,7 @@ struct rb_context {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> pipe_ev;
   int rt_chunks = 0;  // 0 = automatic
+  unsigned long long* step_counter = nullptr;  // device counter of integrated segment-steps (measurement aid)
 };
 
 // record the start / stop event of one launch of kernel family `which` (no-ops unless timing is on)
@@ -80,6 +81,9 @@ int rb_ensure(rb_context* ctx, int which, size_t bytes, void** out);
 // d holds DEVICE pointers; h_freqs is a host copy of d->freqs (frequency-class scan)
 int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_freqs, double* out_total,
                     double* out_cube);
+
+int rb_launch_alpha_scale_sum(rb_context* ctx, const double* cube, const double* scale, int L, int F, int C,
+                              double* total, double* out_cube);
 
 struct RtLaunch {
   // geometry

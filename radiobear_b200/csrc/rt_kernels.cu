@@ -319,6 +319,7 @@ struct RtK {
   const double* alpha;  // [L][F]
   const double* T;      // [L]
   const double4* prep;  // [F/8][L-1][8] interleaved loop operands (rays-major kernel only, see rt_prepare_kernel)
+  unsigned long long* step_counter;  // optional: number of (ray, freq, segment) steps actually integrated
   const double* ds;     // [S][Rpad]
   const int* nseg;      // [R]
   const int* nanflag;   // [R]
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
         const double4 q0 = ppb[u * 8];
         RB_RT_STEP(da, db, q0);
       }
-      i += m;
+      i += stop ? (u + 1) : m;                               // segments integrated so far (exact: feeds rb_count_steps)
       live = !stop && i < steps;
     }
   }
@@ -640,6 +641,11 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
     Tb = fma(last_qz, w, Tb);
   }
   cp_async_wait<0>();
+  if (k.step_counter) {   // measurement aid (bench.py): executed segment-steps, one atomic per warp
+    unsigned long long done = (unsigned long long)i;   // rays that crossed tau_cut count the whole last group
+    for (int o = 16; o > 0; o >>= 1) done += __shfl_down_sync(0xffffffffu, done, o);
+    if (threadIdx.x == 0) atomicAdd(k.step_counter, done);
+  }
   if (!valid) return;
   double vout, wout = iW;
   if (n < 0) vout = kTcmb;                                 // off planet (brightness.py:46-51)
@@ -728,6 +734,7 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
   } else {
     // rays-major mapping: CTAs of 32 rays x 8 frequencies; operands prepared by rb_rt_prepare
     k.prep = (const double4*)prep.prep;
+    k.step_counter = ctx->step_counter;
     dim3 block(32, 8), grid((k.F + 7) / 8, (unsigned)((g.R + 31) / 32));
     if (grid.y > 65535) return rb_fail(ctx, RB_ERR_INVALID, "rt: more than 2M rays per launch are not supported");
     static_assert(kExpTab * sizeof(double) + kRaysSmemBytes <= 48 * 1024, "static shared memory limit");

@@ -168,6 +168,19 @@ def alpha_layers_dev(freqs_t, T_t, P_t, gas_t, gas_dict, cloud_t=None, cloud_dic
     return (total, cube) if want_cube else total
 
 
+def alpha_scale_sum(cube, scale_mat=None, want_cube=False, ctx=None):
+    """Scale-sum of a cached per-constituent cube [L][F][C] -> slab[L][F] (+ the scaled cube)."""
+    ctx = ctx or _lib.get_context()
+    ctx.use_own_stream()
+    cube = f64(cube)
+    L, F, C_ = cube.shape
+    sm = None if scale_mat is None else f64(scale_mat)
+    total = np.empty((L, F))
+    scaled = np.empty((L, F, C_)) if want_cube else None
+    ctx.check(ctx.lib.rb_alpha_scale_sum(ctx.h, L, F, C_, ptr(cube), ptr(sm), ptr(total), ptr(scaled)))
+    return (total, scaled) if want_cube else total
+
+
 GTYPE = {'ellipse': 0, 'circle': 1, 'sphere': 1}
 LIMB = {'shape': 0, 'sec': 1}
 
