@@ -159,51 +159,80 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
   }
   int layer = 0;
   int count = 0;
-  int first_nan = -1;
   double* out = g.ds + ds_tile_base(r, S);
   const double e2 = 1.0 - q2;
   const double sin6 = 9.99999999999833333e-07, cos6 = 0.9999999999995;   // sin / cos of 1e-6 rad
   const double shape0sq = q2 * sin6 * sin6 + cos6 * cos6;               // lat == 0 -> 1e-6 rad (shape.py:231-233)
-  // Between two (rare) direction changes the ray is a straight line r(t) = r0 + t s, so the recurrence of
-  // raypath.py:176-237 only needs scalars:  r.s = rd0 + t,  |r|^2 = (r.s)^2 + perp2,  y = y0 + t sy.
-  //   shell radius factor^2 at the current latitude:   shape2 = 1 - (1 - q^2) y^2 / |r|^2
-  //   ds = -r.s - sqrt((r.s)^2 + rNext^2 - rNow^2),    rNext^2 - rNow^2 = shape2 (R_l+1^2 - R_l^2)
-  double t = 0.0;
-  double rd0 = px * sx + py * sy + pz * sz;
-  double perp2 = (px * px + py * py + pz * pz) - rd0 * rd0;
-  double y0 = py;
+  // Between two (rare) direction changes the ray is a straight line r(t) = r0 + t s entering the planet
+  // (r.s < 0), and the recurrence of raypath.py:176-237 collapses to ONE scalar, X = (r.s)^2:
+  //   ds_i = -r.s - sqrt((r.s)^2 + rNext^2 - rNow^2)          (raypath.py:193)
+  //   (r.s)_i+1 = (r.s)_i + ds_i = -sqrt(X_i+1),   X_i+1 = X_i + shape2_i (R_i+1^2 - R_i^2)
+  //   ds_i = sqrt(X_i) - sqrt(X_i+1)
+  //   shape2 = (shell radius / equatorial radius)^2 = 1 - (1 - q^2) y^2 / |r|^2           (shape.py:240-244)
+  //   |r|^2 = X + perp2,   y = y0 + t sy = c0 - sy sqrt(X)      (t = -sqrt(X) - r0.s)
+  // The dependent chain per segment is sqrt -> y -> shape2 -> X: ~11 FP64 instructions instead of ~26
+  // (the kernel is latency-bound: one thread per ray, ~1000 sequential segments).
+  double rd0 = px * sx + py * sy + pz * sz;                  // r0.s  (< 0: ingress)
+  double perp2 = (px * px + py * py + pz * pz) - rd0 * rd0;  // |r0|^2 - (r0.s)^2: constant along the line
+  double c0 = py - rd0 * sy;
+  double X = rd0 * rd0;
+  double sq = fabs(rd0);                                     // sqrt(X)
   double shape2 = shape * shape;
-  double Rl = g.radius[0];
+  double Rl = g.radius[0], Rn = g.radius[1];
+  bool outward = !(rd0 < 0.0);                               // only possible after a reflection (below)
   for (; layer < S; ++layer) {
-    const double Rn = g.radius[layer + 1];
-    const double rd = rd0 + t;
-    double ds;
+    const double Rnn = g.radius[min(layer + 2, g.L - 1)];    // prefetch for the next segment
+    const double Xn = fma(shape2, (Rn - Rl) * (Rn + Rl), X);
+    // sqrt(Xn): MUFU.RSQ64H seed + two coupled Newton steps (~1 ulp; NaN for Xn < 0 like np.sqrt)
+    double sqn;
+    {
+      double r0;
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(Xn));
+      double gq = Xn * r0, hq = 0.5 * r0;
+      double eq = fma(-hq, gq, 0.5);
+      gq = fma(gq, eq, gq);
+      hq = fma(hq, eq, hq);
+      eq = fma(-hq, gq, 0.5);
+      sqn = fma(gq, eq, gq);
+      if (Xn == 0.0) sqn = 0.0;
+    }
+    double ds = sq - sqn;
+    if (outward) ds = -sq - sqn;                             // r.s > 0: the reference's dsm is negative -> stop
+    if (ds < 0.0) break;                                     // raypath.py:212-216
     if (g.limb == RB_LIMB_SEC) {
       const double sh = sqrt(shape2);
-      const double chk = -rd - sqrt(fma(rd, rd, shape2 * (Rn * Rn - Rl * Rl)));
-      if (chk < 0.0) break;
-      ds = fabs(Rn * sh - Rl * sh) / mu;                                 // raypath.py:218-219 (also replaces a NaN)
-    } else {
-      ds = -rd - sqrt(fma(rd, rd, shape2 * ((Rn - Rl) * (Rn + Rl))));
-      if (ds < 0.0) break;  // raypath.py:212-216
+      ds = fabs(Rn * sh - Rl * sh) / mu;                     // raypath.py:218-219 (also replaces a NaN)
     }
     out[(size_t)layer * kDsStride] = ds;
-    if (ds != ds && first_nan < 0) first_nan = layer;
     ++count;
-    Rl = Rn;
-    // advance along the line and re-evaluate the latitude (raypath.py:228-237)
-    t += ds;
-    const double rdn = rd0 + t;
-    const double yn = fma(t, sy, y0);
-    const double nr2 = fma(rdn, rdn, perp2);
-    shape2 = (yn == 0.0) ? shape0sq : fma(-e2, (yn * yn) / nr2, 1.0);
+    if (ds != ds) {
+      // below the tangent shell: every later segment is NaN too (np.sqrt of a negative number,
+      // raypath.py:192-209 never reaches its `except`), so just fill the rest of the column
+      for (++layer; layer < S; ++layer) out[(size_t)layer * kDsStride] = ds;
+      count = S;
+      break;
+    }
+    // latitude of the new point -> shape factor of the next shell pair (raypath.py:228-237)
+    const double yn = fma(-sy, sqn, c0);
+    const double inv = rb_rcp<2>(Xn + perp2);
+    double shape2n = fma(-e2 * (yn * yn), inv, 1.0);
+    if (yn == 0.0) shape2n = shape0sq;
     // incidence on the next shell with nratio = 1 (raypath.py:176-177, 246, 257): the reference's
     // arccos / arcsin pair gives s += (cos t_inc - |cos t_inc|) n, i.e. nothing unless cos t_inc < 0.
-    // n is parallel to (q x, y, q z), so cos t_inc < 0  <=>  d = q (s.r - sy y) + sy y > 0.
-    const double d = fma(g.q, rdn - sy * yn, sy * yn);
-    if (!(d <= 0.0) || yn == 0.0) {
-      // grazing ray (rare) or the lat == 0 special case: go through the vector form
-      px = fma(t, sx, px); py = yn; pz = fma(t, sz, pz);
+    // n is parallel to (q x, y, q z), so cos t_inc < 0  <=>  d = q (r.s - sy y) + sy y > 0.
+    const double syy = sy * yn;
+    const double d = fma(g.q, -sqn - syy, syy);
+    X = Xn; sq = sqn; shape2 = shape2n; Rl = Rn; Rn = Rnn;
+    if (g.limb == RB_LIMB_SEC || !(d <= 0.0) || outward) {
+      // grazing ray (rare) or the secant mode (position advances by the secant ds, not along the chord):
+      // go through the vector form and restart the line at the current point.  (For y == 0 the reference's
+      // normal carries a 1e-6 y-component; it can only change the sign test within 1e-6 rad of tangency,
+      // where the next segment is NaN anyway, so the plain test is used.)
+      const double t = (g.limb == RB_LIMB_SEC) ? ds : ((outward ? sqn : -sqn) - rd0);
+      px = fma(t, sx, px); py = fma(t, sy, py); pz = fma(t, sz, pz);
+      if (g.limb != RB_LIMB_SEC && !outward) py = yn;
+      const double nr2 = px * px + py * py + pz * pz;
+      if (g.limb == RB_LIMB_SEC) shape2 = (py == 0.0) ? shape0sq : fma(-e2 * (py * py), 1.0 / nr2, 1.0);
       double ux, uy, uz;
       if (py == 0.0) {
         const double hxz = sqrt(px * px + pz * pz);
@@ -211,19 +240,27 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
       } else {
         ux = g.q * px; uy = py; uz = g.q * pz;
       }
-      const double inv = 1.0 / sqrt(ux * ux + uy * uy + uz * uz);
-      ux *= inv; uy *= inv; uz *= inv;
+      const double invn = 1.0 / sqrt(ux * ux + uy * uy + uz * uz);
+      ux *= invn; uy *= invn; uz *= invn;
       const double ci = -(sx * ux + sy * uy + sz * uz);
       if (!(ci >= 0.0)) {
         const double w = (fabs(ci) > 1.0) ? nan("") : 2.0 * ci;
         sx += w * ux; sy += w * uy; sz += w * uz;
       }
-      // restart the line at the current point
-      t = 0.0;
       rd0 = px * sx + py * sy + pz * sz;
-      perp2 = (px * px + py * py + pz * pz) - rd0 * rd0;
-      y0 = py;
+      perp2 = nr2 - rd0 * rd0;
+      c0 = py - rd0 * sy;
+      X = rd0 * rd0;
+      sq = fabs(rd0);
+      outward = rd0 > 0.0;
     }
+  }
+  // Brightness.single uses ds[0 .. n-2] (brightness.py:65); NaN persists once it appears, so the last
+  // used segment tells whether the ray is a NaN ray
+  int first_nan = -1;
+  if (count >= 2) {
+    const double last_used = out[(size_t)(count - 2) * kDsStride];
+    if (last_used != last_used) first_nan = 0;
   }
   g.nseg[r] = count;
   // Brightness.single uses ds[0 .. n-2] (brightness.py:65); a NaN there makes every frequency NaN
