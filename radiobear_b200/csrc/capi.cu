@@ -320,7 +320,7 @@ int rb_compute_ds(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const d
   void *p_rad, *p_b, *p_ds, *p_n, *p_o;
   RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, L.L * 8, &p_rad));
   RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
-  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   RB_TRY(rb_ensure(ctx, RB_BUF_MISC, (size_t)R * S * 8, &p_o));
   cudaStream_t s = ctx->stream;
@@ -438,7 +438,7 @@ int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc
   RB_TRY(make_geometry(ctx, g, R, &L));
   const size_t S = L.L - 1;
   void *p_ds, *p_n;
-  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   L.radius = g->radius; L.b = b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
   return run_rt_pipeline(ctx, L, rt, out_Tb, out_intW, nullptr, nullptr);
@@ -460,7 +460,7 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   void *p_rad, *p_b, *p_ds, *p_n, *p_alpha, *p_T, *p_tb, *p_iw = nullptr, *p_prof = nullptr;
   RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, nL * 8, &p_rad));
   RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
-  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, nL * F * 8, &p_alpha));
   RB_TRY(rb_ensure(ctx, RB_BUF_T, nL * 8, &p_T));
@@ -509,7 +509,7 @@ int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int
   const size_t esz = rt->out_f32 ? 4 : 8;
   void *p_in, *p_ds, *p_n, *p_alpha, *p_T, *p_tb, *p_iw = nullptr;
   RB_TRY(rb_ensure(ctx, RB_BUF_MISC, (size_t)R * S * 8, &p_in));
-  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, nL * F * 8, &p_alpha));
   RB_TRY(rb_ensure(ctx, RB_BUF_T, nL * 8, &p_T));

@@ -60,6 +60,10 @@ enum {
   RB_BUF_RADIUS, RB_BUF_B, RB_BUF_DS, RB_BUF_NSEG, RB_BUF_TB, RB_BUF_INTW, RB_BUF_PROFILE, RB_BUF_MISC, RB_BUF_PREP
 };
 
+// The rays-major integration kernel prefetches whole 32-segment chunks of the ds slab and of the operand
+// slab without bounds checks (the rows it may over-read are never consumed); both buffers carry this slack.
+constexpr size_t kRtSlackBytes = 128 * 256;
+
 int rb_fail(rb_context* ctx, int code, const char* fmt, ...);
 int rb_ensure(rb_context* ctx, int which, size_t bytes, void** out);
 

@@ -536,26 +536,37 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
   const int n = valid ? k.nseg[r] : -1;
   const bool nanray = valid && k.nanflag[r] != 0;
   const int steps = (valid && !nanray) ? n - 1 : 0;        // brightness.py:65: i = 0 .. len(ds)-2
-  const double* tile_ds = k.ds + (size_t)blockIdx.y * S * 32;
-  const double4* tile_pp = k.prep + (size_t)blockIdx.x * S * 8;
 
+  // Per-thread copy plan for one chunk, computed once: the chunk's 33 ds rows and 32 operand rows are each
+  // one contiguous piece of global memory (8448 B / 8192 B), cut into 16-byte cp.async pieces: two per
+  // thread for each stream plus a third ds piece for the first 16 threads.  No bounds checks: rows past the
+  // end of a tile are never consumed and both slabs are allocated with kRtSlackBytes of slack.
+  const char* src_ds = reinterpret_cast<const char*>(k.ds + (size_t)blockIdx.y * S * 32) + tid * 16;
+  const char* src_pp = reinterpret_cast<const char*>(k.prep + (size_t)blockIdx.x * S * 8) + tid * 16;
+  const unsigned dst_ds = (unsigned)__cvta_generic_to_shared(s_ds) + tid * 16;
+  const unsigned dst_pp = (unsigned)__cvta_generic_to_shared(s_pp) + tid * 16;
   auto issue = [&](int c) {
-    const int row0 = c * kChunk;
-    const int buf = c % kStages;
-    // ds rows row0 .. row0 + kChunk: 16 pieces of 16 B per row
-    for (int q = tid; q < (kChunk + 1) * 16; q += 256)
-      if (row0 + (q >> 4) < S) cp_async16(s_ds + buf * kTileDs + q * 2, tile_ds + (size_t)row0 * 32 + q * 2);
-    // operand rows row0 .. row0 + kChunk - 1: 16 pieces of 16 B per row
-    for (int q = tid; q < kChunk * 16; q += 256)
-      if (row0 + (q >> 4) < S)
-        cp_async16(reinterpret_cast<double*>(s_pp + buf * kTilePp) + q * 2,
-                   reinterpret_cast<const double*>(tile_pp + (size_t)row0 * 8) + q * 2);
+    const unsigned bd = (c & 1) ? (unsigned)(kTileDs * sizeof(double)) : 0u;
+    const unsigned bp = (c & 1) ? (unsigned)(kTilePp * sizeof(double4)) : 0u;
+    asm volatile(
+        "cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+        "cp.async.cg.shared.global [%0+4096], [%1+4096], 16;\n\t"
+        "cp.async.cg.shared.global [%2], [%3], 16;\n\t"
+        "cp.async.cg.shared.global [%2+4096], [%3+4096], 16;" ::"r"(dst_ds + bd), "l"(src_ds), "r"(dst_pp + bp),
+        "l"(src_pp)
+        : "memory");
+    if (tid < 16) asm volatile("cp.async.cg.shared.global [%0+8192], [%1+8192], 16;" ::"r"(dst_ds + bd), "l"(src_ds) : "memory");
     cp_async_commit();
+    src_ds += kChunk * 32 * sizeof(double);
+    src_pp += kChunk * 8 * sizeof(double4);
   };
   issue(0);
 
-  const double cA = pin(c_expc + 0), cM = pin(c_expc + 1), cL = pin(c_expc + 2), c3 = pin(c_expc + 3),
-               c2 = pin(c_expc + 4), c1 = pin(c_expc + 5);
+  // cA and c2 each meet another constant in one FMA (a DFMA takes a single uniform-register operand), so
+  // they are loaded through a thread-dependent (always zero) offset to keep them in vector registers
+  const int vz = threadIdx.x >> 5;   // blockDim.x == 32
+  const double cA = pin(c_expc + 0 + vz), cM = pin(c_expc + 1), cL = pin(c_expc + 2), c3 = pin(c_expc + 3),
+               c2 = pin(c_expc + 4 + vz), c1 = pin(c_expc + 5);
   // 32-bit shared-window address of the table, computed once (ptxas otherwise re-derives the CTA's shared
   // window base with S2UR / UMOV / ULEA in every iteration)
   unsigned tab_base;
@@ -608,9 +619,14 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
     p_ = fma(p_, rr_, c1);                                                                                     \
     p_ = fma(p_, rr_, c1);                                                                                     \
     double tj_;                                                                                                \
-    asm("ld.shared.f64 %0, [%1];" : "=d"(tj_) : "r"(tab_base + ((ni_ & (kExpTab - 1)) << 3)));                \
+    unsigned ta_, ex_;                                                                                         \
+    asm("{ .reg .b32 t; and.b32 t, %2, 1023; mad.lo.u32 %0, t, 8, %3; and.b32 %1, %2, 0xFFFFFC00; }"           \
+        : "=r"(ta_), "=r"(ex_) : "r"(ni_), "r"(tab_base));                                                     \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj_) : "r"(ta_));                                                     \
     const double v_ = p_ * tj_;                                                                                \
-    const double e_ = __hiloint2double(__double2hiint(v_) + ((ni_ << 10) & 0xFFF00000), __double2loint(v_));   \
+    int hi_;                                                                                                   \
+    asm("mad.lo.s32 %0, %1, 1024, %2;" : "=r"(hi_) : "r"(ex_), "r"(__double2hiint(v_)));                       \
+    const double e_ = __hiloint2double(hi_, __double2loint(v_));                                               \
     w = e_ * (dd);                                                                                             \
   }
 
@@ -630,10 +646,12 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
       int u = 0;
       // groups of 4 segments: the four optical depths first (one dependent FMA each), one threshold test
       // on the deepest, then four independent exp / accumulate chains
-      for (; u + 4 <= m; u += 4) {
-        const double d0 = dsb[u * 32], d1 = dsb[(u + 1) * 32], d2 = dsb[(u + 2) * 32], d3 = dsb[(u + 3) * 32],
-                     d4 = dsb[(u + 4) * 32];
-        const double4 q0 = ppb[u * 8], q1 = ppb[(u + 1) * 8], q2 = ppb[(u + 2) * 8], q3 = ppb[(u + 3) * 8];
+      const double* dp = dsb;
+      const double4* qp = ppb;
+#pragma unroll 1
+      for (; u + 4 <= m; u += 4, dp += 4 * 32, qp += 4 * 8) {
+        const double d0 = dp[0], d1 = dp[32], d2 = dp[64], d3 = dp[96], d4 = dp[128];
+        const double4 q0 = qp[0], q1 = qp[8], q2 = qp[16], q3 = qp[24];
         const double t0 = fma(q0.x, d0, tau), t1 = fma(q1.x, d1, t0), t2 = fma(q2.x, d2, t1), t3 = fma(q3.x, d3, t2);
         const double nd3 = fma(t3, cA, cM) - cM;
         if ((unsigned)__double2hiint(nd3) > thr_hi) break;   // tau_cut is crossed inside this group: go step by step
@@ -739,7 +757,7 @@ int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total,
   const int F = rt->n_freqs;
   const int ngroups = (F + 7) / 8;
   void* scratch;
-  RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (L - 1) * 8 * sizeof(double4), &scratch));
+  RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (L - 1) * 8 * sizeof(double4) + kRtSlackBytes, &scratch));
   const int nel = ngroups * (L - 1) * 8;
   rt_prepare_kernel<<<(nel + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ngroups, (double4*)scratch);
   RB_CUDA(ctx, cudaGetLastError());
