@@ -86,6 +86,7 @@ void rb_destroy(rb_context* ctx) {
       if (b.p) cudaFree(b.p);
     for (auto& c : ctx->cat)
       if (c) cudaFree(c);
+    if (ctx->exp_tab) cudaFree(ctx->exp_tab);
     for (int i = 0; i < 3; ++i)
       for (int r = 0; r < rb_context::kEvRing; ++r)
         for (int j = 0; j < 2; ++j)

@@ -40,6 +40,7 @@ struct rb_context {
   std::vector<cudaEvent_t> pipe_ev;
   int rt_chunks = 0;  // 0 = automatic
   unsigned long long* step_counter = nullptr;  // device counter of integrated segment-steps (measurement aid)
+  double* exp_tab = nullptr;  // 2^(j/1024), j = 0..1023: copied into shared memory by every integration CTA
 };
 
 // record the start / stop event of one launch of kernel family `which` (no-ops unless timing is on)

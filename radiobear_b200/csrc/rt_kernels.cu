@@ -357,6 +357,7 @@ struct RtK {
   const double* T;      // [L]
   const double4* prep;  // [F/8][L-1][8] interleaved loop operands (rays-major kernel only, see rt_prepare_kernel)
   unsigned long long* step_counter;  // optional: number of (ray, freq, segment) steps actually integrated
+  const double* exp_tab;  // 2^(j/1024) (rays-major kernel only)
   const double* ds;     // [S][Rpad]
   const int* nseg;      // [R]
   const int* nanflag;   // [R]
@@ -461,6 +462,11 @@ __device__ double c_expc[8] = {
     1.6666666666666666e-1,    // 1/6
     0.5, 1.0, 0.0, 0.0};
 
+__global__ void exp_tab_init_kernel(double* tab) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < kExpTab) tab[t] = exp2((double)t / (double)kExpTab);
+}
+
 // per-(layer, freq) operands of the integration loop, hoisted out of the per-ray work and interleaved so
 // that one 32-byte shared-memory read fetches them (kHalfCm = 0.5 * 1e5 folds ds [km] -> ds/2 [cm],
 // brightness.py:66).  Grouped by blocks of 8 frequencies so that the operands one CTA needs for a chunk
@@ -523,11 +529,10 @@ constexpr int kTilePp = kChunk * 8;          // double4 per operand tile
 constexpr size_t kRaysSmemBytes = kStages * (kTileDs * sizeof(double) + kTilePp * sizeof(double4));
 
 __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_constant__ RtK k) {
-  __shared__ double s_tab[kExpTab];                        // 2^(j/1024)
+  __shared__ __align__(16) double s_tab[kExpTab];          // 2^(j/1024), copied from k.exp_tab with chunk 0
   __shared__ __align__(16) double s_ds[kStages * kTileDs];
   __shared__ __align__(16) double4 s_pp[kStages * kTilePp];
   const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int t = tid; t < kExpTab; t += 256) s_tab[t] = exp2((double)t / (double)kExpTab);
 
   const int S = k.L - 1;
   const long long r = (long long)blockIdx.y * 32 + threadIdx.x;
@@ -560,7 +565,19 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
     src_ds += kChunk * 32 * sizeof(double);
     src_pp += kChunk * 8 * sizeof(double4);
   };
-  issue(0);
+  // a CTA with nothing to integrate (off the planet, NaN rays) skips the pipeline altogether
+  bool live = steps > 0;
+  const bool any_live = __syncthreads_or(live);
+  if (any_live) {
+    // the exponential table rides in the first copy group
+    const unsigned dst_tab = (unsigned)__cvta_generic_to_shared(s_tab) + tid * 16;
+    const char* src_tab = reinterpret_cast<const char*>(k.exp_tab) + tid * 16;
+    asm volatile(
+        "cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+        "cp.async.cg.shared.global [%0+4096], [%1+4096], 16;" ::"r"(dst_tab), "l"(src_tab)
+        : "memory");
+    issue(0);
+  }
 
   // cA and c2 each meet another constant in one FMA (a DFMA takes a single uniform-register operand), so
   // they are loaded through a thread-dependent (always zero) offset to keep them in vector registers
@@ -578,7 +595,6 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
   const double cutd = fmin(k.tau_cut, 707.0) * 1477.3197218702985;
   const unsigned thr_hi = (unsigned)__double2hiint(-cutd);
   double tau = 0.0, iW = 0.0, Tb = 0.0;
-  bool live = steps > 0;
   int i = 0;
   double last_dd = 0.0, last_qy = 0.0, last_qz = 0.0;    // operands of the crossing step
 
@@ -631,7 +647,7 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
   }
 
   bool stop = false;
-  for (int c = 0;; ++c) {
+  for (int c = 0; any_live; ++c) {
     cp_async_wait<0>();                                    // this thread's pieces of chunk c have landed
     if (!__syncthreads_or(live)) break;                    // ... everybody's have; chunk c-1 is fully consumed
     issue(c + 1);                                          // refill the buffer chunk c-1 used
@@ -759,6 +775,11 @@ int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total,
   void* scratch;
   RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (L - 1) * 8 * sizeof(double4) + kRtSlackBytes, &scratch));
   const int nel = ngroups * (L - 1) * 8;
+  if (!ctx->exp_tab) {
+    RB_CUDA(ctx, cudaMalloc(&ctx->exp_tab, kExpTab * sizeof(double)));
+    exp_tab_init_kernel<<<kExpTab / 256, 256, 0, ctx->stream>>>(ctx->exp_tab);
+    ctx->launches += 1;
+  }
   rt_prepare_kernel<<<(nel + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ngroups, (double4*)scratch);
   RB_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
@@ -790,6 +811,7 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     // rays-major mapping: CTAs of 32 rays x 8 frequencies; operands prepared by rb_rt_prepare
     k.prep = (const double4*)prep.prep;
     k.step_counter = ctx->step_counter;
+    k.exp_tab = ctx->exp_tab;
     dim3 block(32, 8), grid((k.F + 7) / 8, (unsigned)((g.R + 31) / 32));
     if (grid.y > 65535) return rb_fail(ctx, RB_ERR_INVALID, "rt: more than 2M rays per launch are not supported");
     static_assert(kExpTab * sizeof(double) + kRaysSmemBytes <= 48 * 1024, "static shared memory limit");
