@@ -460,7 +460,9 @@ __device__ double c_expc[8] = {
     6755399441055744.0,       // 2^52 + 2^51: adding it rounds to the nearest integer (kept in the low word)
     -6.7690154351557157e-4,   // -ln2/1024
     1.6666666666666666e-1,    // 1/6
-    0.5, 1.0, 0.0, 0.0};
+    0.5, 1.0,
+    1.0000000143186156,    // 1 + h^2/8, h = ln2/2048: linear coefficient of the economised quadratic (see RB_EXP_POLY)
+    0.0};
 
 __global__ void exp_tab_init_kernel(double* tab) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -500,10 +502,6 @@ __device__ __forceinline__ double pin(const double* p) {
   return x;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -583,7 +581,7 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
   // they are loaded through a thread-dependent (always zero) offset to keep them in vector registers
   const int vz = threadIdx.x >> 5;   // blockDim.x == 32
   const double cA = pin(c_expc + 0 + vz), cM = pin(c_expc + 1), cL = pin(c_expc + 2), c3 = pin(c_expc + 3),
-               c2 = pin(c_expc + 4 + vz), c1 = pin(c_expc + 5);
+               c2 = pin(c_expc + 4 + vz), c1 = pin(c_expc + 5), c1e = pin(c_expc + 6);
   // 32-bit shared-window address of the table, computed once (ptxas otherwise re-derives the CTA's shared
   // window base with S2UR / UMOV / ULEA in every iteration)
   unsigned tab_base;
@@ -625,15 +623,24 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
 
   // e^-tau * dd for a step known to be below the threshold (no checks): independent of the other steps of
   // a group, so ptxas interleaves the four chains (ILP 4 instead of one ~100-cycle dependent chain per step)
+  // exp(x) on |x| <= h = ln2/2048 for the group loop.  Default: the quadratic 1 + (1 + h^2/8) x + x^2/2 (the
+  // cubic term economised onto the linear one), |relative error| <= h^3/24 = 1.6e-12, i.e. < 1e-9 K in Tb,
+  // one FP64 instruction per segment cheaper than the cubic Taylor polynomial (-DRB_EXP_DEG=3, 5.5e-16).
+#ifndef RB_EXP_DEG
+#define RB_EXP_DEG 2
+#endif
+#if RB_EXP_DEG == 2
+#define RB_EXP_POLY(x) fma(fma((x), c2, c1e), (x), c1)
+#else
+#define RB_EXP_POLY(x) fma(fma(fma((x), c3, c2), (x), c1), (x), c1)
+#endif
 #define RB_RT_WEIGHT(tauv, dd, w)                                                                              \
   {                                                                                                            \
     double nd_ = fma((tauv), cA, cM);                                                                          \
     const int ni_ = __double2loint(nd_);                                                                       \
     nd_ -= cM;                                                                                                 \
     const double rr_ = fma(nd_, cL, -(tauv));                                                                  \
-    double p_ = fma(rr_, c3, c2);                                                                              \
-    p_ = fma(p_, rr_, c1);                                                                                     \
-    p_ = fma(p_, rr_, c1);                                                                                     \
+    double p_ = RB_EXP_POLY(rr_);                                                                              \
     double tj_;                                                                                                \
     unsigned ta_, ex_;                                                                                         \
     asm("{ .reg .b32 t; and.b32 t, %2, 1023; mad.lo.u32 %0, t, 8, %3; and.b32 %1, %2, 0xFFFFFC00; }"           \
