@@ -42,6 +42,12 @@ BSTEP = 0.005
 NFREQ = 64
 METRIC = 'Tb pixel*freq/s (Jupiter image cube b=0.005, 64 freqs 1-100 GHz, on-disc pixels)'
 UNIT = 'pixel*freq/s'
+# rt_integrate_rays_kernel, per executed (ray, freq, segment) step: 7 DFMA + 2 DMUL + 2 DADD
+RT_FLOPS_PER_STEP = 18.0
+RT_FP64_INSTR_PER_STEP = 11.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one rt_integrate_rays_kernel launch of this workload at N=1
+RT_DRAM_BYTES_N1 = 1145970000
+RT_DRAM_SOURCE = 'ncu --set full, profiles/r1_rt_integrate_rays.txt (1.070 GB read + 0.076 GB written)'
 WORKLOAD = 'C4: Jupiter full image b=0.005 (601x601 px) x 64 freqs 1-100 GHz, 1000 layers, alpha+geometry+RT per step'
 
 
@@ -416,14 +422,17 @@ def run_gpu(args):
         # alpha slab + T + float32 Tb out for every pixel of the rank
         rt_bytes = n_on_rank * S * 8 + F * L * 8 + L * 8 + len(pts) * F * 4
         rt_steps_all = float(n_on_rank) * F * (S - 1)
-        rt_flops = float(steps_executed) * 20.0               # 12 FP64 instructions = 20 flops per executed segment-step, DESIGN.md 3.3
+        rt_flops = float(steps_executed) * RT_FLOPS_PER_STEP   # 11 FP64 instructions = 18 flops per executed segment-step, DESIGN.md 3.3
         roofline = {'bound': 'hbm', 'kernel': 'rt_integrate_rays_kernel', 'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9,
                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': rt_bytes / (rt_ms * 1e-3) / 1e9 / hbm_peak,
-                    'traffic': None, 'peak_source': peak_src, 'ms_per_launch': rt_ms, 'launches_per_step': rt_chunks,
+                    'traffic': RT_DRAM_BYTES_N1 if world == 1 else None, 'traffic_source': RT_DRAM_SOURCE,
+                    'peak_source': peak_src, 'ms_per_launch': rt_ms, 'launches_per_step': rt_chunks,
                     'note': 'at F=64 the kernel is FP64/exp-bound, not HBM-bound (SURVEY 8d): see fp64',
                     'fp64': {'achieved_tflops': rt_flops / (rt_ms * 1e-3) / 1e12, 'peak_tflops': fp64_peak,
                              'frac': rt_flops / (rt_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                             'flops_per_segment_step': 20, 'peak_source': 'rb_probe_fp64_peak (DFMA, same box, same run)',
+                             'flops_per_segment_step': RT_FLOPS_PER_STEP, 'fp64_instr_per_segment_step': RT_FP64_INSTR_PER_STEP,
+                             'pipe_frac': (float(steps_executed) * RT_FP64_INSTR_PER_STEP / (rt_ms * 1e-3) / 1e12) / (fp64_peak / 2.0) if fp64_peak else None,
+                             'peak_source': 'rb_probe_fp64_peak (DFMA, same box, same run)',
                              'segment_steps_executed': int(steps_executed), 'segment_steps_all': rt_steps_all,
                              'note': 'flops counted over the segment-steps actually executed (in-kernel counter, untimed pass); '
                                      'the tau > tau_cut exit skips the rest of each ray'}}

@@ -448,21 +448,43 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
 }
 
 // ---- exp(-tau) for the weighting function ------------------------------------------------------------
-// tau >= 0.  exp(-tau) = 2^k * 2^(j/1024) * exp(r) with -tau*1024*log2(e) = 1024 k + j + 1024 r/ln2,
-// |r| <= ln2/2048 = 3.4e-4, exp(r) by a degree-3 Taylor polynomial (remainder r^4/24 < 5.6e-16), the
-// 2^(j/1024) table (8 KB) in shared memory.  Branch-free, 7 FP64 instructions (libdevice exp() costs ~25
-// with its special-case paths); relative error ~1e-15, far inside the 0.01 K bar (tests hold 1e-4 K).
-// tau beyond the underflow point gives exactly 0; NaN is handled by the caller.  The constants are fetched
-// once per thread into registers (see pin()).
-constexpr int kExpTab = 1024;
+// tau >= 0, N = kExpTab.  exp(-tau) = 2^k * 2^(j/N) * exp(r) with -tau N log2(e) = N k + j + N r/ln2,
+// |r| <= h = ln2/(2N), the 2^(j/N) table in shared memory, exp(r) by an economised polynomial (the first
+// dropped Taylor term is folded onto the lower coefficients, Chebyshev-style):
+//   RB_EXP_DEG 2:  1 + (1 + h^2/8) r + r^2/2                         |rel. error| <= h^3/24
+//   RB_EXP_DEG 3:  (1 - h^4/192) + r + (1/2 + h^2/24) r^2 + r^3/6    |rel. error| <= h^4/192
+// Branch-free; libdevice exp() costs ~25 FP64 instructions with its special-case paths.  The error bound of
+// the shipped combination is printed in DESIGN.md 3.3; it is far inside the 0.01 K bar (tests hold 1e-4 K
+// against the reference and 1e-7 K between kernels).  tau beyond the underflow point gives exactly 0; NaN
+// is handled by the caller.  The constants are fetched once per thread into registers (see pin()).
+// The table size trades shared-memory wavefronts for polynomial degree: neighbouring lanes are neighbouring
+// rays, their tau differ by a few per cent, so with a small table their entries fall into a short window
+// of consecutive entries (16 consecutive doubles never conflict), with a large one they are random.
+#ifndef RB_EXP_TABLOG
+#define RB_EXP_TABLOG 10
+#endif
+#ifndef RB_EXP_DEG
+#define RB_EXP_DEG 2
+#endif
+constexpr int kExpTabLog = RB_EXP_TABLOG;
+constexpr int kExpTab = 1 << kExpTabLog;
+constexpr double kExpH = 0.69314718055994530942 / (2.0 * kExpTab);
 __device__ double c_expc[8] = {
-    -1477.3197218702985,      // -1024 log2(e)
-    6755399441055744.0,       // 2^52 + 2^51: adding it rounds to the nearest integer (kept in the low word)
-    -6.7690154351557157e-4,   // -ln2/1024
-    1.6666666666666666e-1,    // 1/6
-    0.5, 1.0,
-    1.0000000143186156,    // 1 + h^2/8, h = ln2/2048: linear coefficient of the economised quadratic (see RB_EXP_POLY)
+    -1.4426950408889634074 * kExpTab,   // -N log2(e)
+    6755399441055744.0,                 // 2^52 + 2^51: adding it rounds to the nearest integer (kept in the low word)
+    -0.69314718055994530942 / kExpTab,  // -ln2/N
+    1.0 / 6.0,
+#if RB_EXP_DEG == 2
+    0.5, 1.0, 1.0 + kExpH * kExpH / 8.0,
+#else
+    0.5 + kExpH * kExpH / 24.0, 1.0, 1.0 - kExpH * kExpH * kExpH * kExpH / 192.0,
+#endif
     0.0};
+#if RB_EXP_DEG == 2
+#define RB_EXP_POLY(x) fma(fma((x), c2, ce), (x), c1)
+#else
+#define RB_EXP_POLY(x) fma(fma(fma((x), c3, c2), (x), c1), (x), ce)
+#endif
 
 __global__ void exp_tab_init_kernel(double* tab) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -502,6 +524,10 @@ __device__ __forceinline__ double pin(const double* p) {
   return x;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -568,12 +594,7 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
   const bool any_live = __syncthreads_or(live);
   if (any_live) {
     // the exponential table rides in the first copy group
-    const unsigned dst_tab = (unsigned)__cvta_generic_to_shared(s_tab) + tid * 16;
-    const char* src_tab = reinterpret_cast<const char*>(k.exp_tab) + tid * 16;
-    asm volatile(
-        "cp.async.cg.shared.global [%0], [%1], 16;\n\t"
-        "cp.async.cg.shared.global [%0+4096], [%1+4096], 16;" ::"r"(dst_tab), "l"(src_tab)
-        : "memory");
+    for (int q = tid; q < kExpTab / 2; q += 256) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
     issue(0);
   }
 
@@ -581,7 +602,7 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
   // they are loaded through a thread-dependent (always zero) offset to keep them in vector registers
   const int vz = threadIdx.x >> 5;   // blockDim.x == 32
   const double cA = pin(c_expc + 0 + vz), cM = pin(c_expc + 1), cL = pin(c_expc + 2), c3 = pin(c_expc + 3),
-               c2 = pin(c_expc + 4 + vz), c1 = pin(c_expc + 5), c1e = pin(c_expc + 6);
+               c2 = pin(c_expc + 4 + vz), c1 = pin(c_expc + 5), ce = pin(c_expc + 6);
   // 32-bit shared-window address of the table, computed once (ptxas otherwise re-derives the CTA's shared
   // window base with S2UR / UMOV / ULEA in every iteration)
   unsigned tab_base;
@@ -590,7 +611,7 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
   // high word grows with |nd|) ends the ray when tau > tau_cut; tau_cut is capped at 707 (beyond it 2^k leaves
   // the normal range and exp(-tau) is 0 for every purpose), so the hot loop needs neither an underflow
   // select nor an FP64 compare.  The step that crosses the threshold is finished on a cold path.
-  const double cutd = fmin(k.tau_cut, 707.0) * 1477.3197218702985;
+  const double cutd = fmin(k.tau_cut, 707.0) * (1.4426950408889634074 * kExpTab);
   const unsigned thr_hi = (unsigned)__double2hiint(-cutd);
   double tau = 0.0, iW = 0.0, Tb = 0.0;
   int i = 0;
@@ -609,13 +630,11 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
       break;                                                                                                   \
     }                                                                                                          \
     const double rr = fma(nd, cL, -tau);                                                                       \
-    double p = fma(rr, c3, c2);                                                                                \
-    p = fma(p, rr, c1);                                                                                        \
-    p = fma(p, rr, c1);                                                                                        \
+    const double p = RB_EXP_POLY(rr);                                                                          \
     double tj;                                                                                                 \
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_base + ((ni & (kExpTab - 1)) << 3)));                  \
     const double v = p * tj;                                                                                   \
-    const double e = __hiloint2double(__double2hiint(v) + ((ni << 10) & 0xFFF00000), __double2loint(v));       \
+    const double e = __hiloint2double(__double2hiint(v) + ((ni << (20 - kExpTabLog)) & 0xFFF00000), __double2loint(v)); \
     const double w = e * ((dcur) + (dnxt));                                                                    \
     iW = fma((q).y, w, iW);                                                                                    \
     Tb = fma((q).z, w, Tb);                                                                                    \
@@ -623,17 +642,6 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
 
   // e^-tau * dd for a step known to be below the threshold (no checks): independent of the other steps of
   // a group, so ptxas interleaves the four chains (ILP 4 instead of one ~100-cycle dependent chain per step)
-  // exp(x) on |x| <= h = ln2/2048 for the group loop.  Default: the quadratic 1 + (1 + h^2/8) x + x^2/2 (the
-  // cubic term economised onto the linear one), |relative error| <= h^3/24 = 1.6e-12, i.e. < 1e-9 K in Tb,
-  // one FP64 instruction per segment cheaper than the cubic Taylor polynomial (-DRB_EXP_DEG=3, 5.5e-16).
-#ifndef RB_EXP_DEG
-#define RB_EXP_DEG 2
-#endif
-#if RB_EXP_DEG == 2
-#define RB_EXP_POLY(x) fma(fma((x), c2, c1e), (x), c1)
-#else
-#define RB_EXP_POLY(x) fma(fma(fma((x), c3, c2), (x), c1), (x), c1)
-#endif
 #define RB_RT_WEIGHT(tauv, dd, w)                                                                              \
   {                                                                                                            \
     double nd_ = fma((tauv), cA, cM);                                                                          \
@@ -643,12 +651,12 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
     double p_ = RB_EXP_POLY(rr_);                                                                              \
     double tj_;                                                                                                \
     unsigned ta_, ex_;                                                                                         \
-    asm("{ .reg .b32 t; and.b32 t, %2, 1023; mad.lo.u32 %0, t, 8, %3; and.b32 %1, %2, 0xFFFFFC00; }"           \
-        : "=r"(ta_), "=r"(ex_) : "r"(ni_), "r"(tab_base));                                                     \
+    asm("{ .reg .b32 t; and.b32 t, %2, %4; mad.lo.u32 %0, t, 8, %3; and.b32 %1, %2, %5; }"                     \
+        : "=r"(ta_), "=r"(ex_) : "r"(ni_), "r"(tab_base), "n"(kExpTab - 1), "n"(~(kExpTab - 1)));              \
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj_) : "r"(ta_));                                                     \
     const double v_ = p_ * tj_;                                                                                \
     int hi_;                                                                                                   \
-    asm("mad.lo.s32 %0, %1, 1024, %2;" : "=r"(hi_) : "r"(ex_), "r"(__double2hiint(v_)));                       \
+    asm("mad.lo.s32 %0, %1, %3, %2;" : "=r"(hi_) : "r"(ex_), "r"(__double2hiint(v_)), "n"(1 << (20 - kExpTabLog))); \
     const double e_ = __hiloint2double(hi_, __double2loint(v_));                                               \
     w = e_ * (dd);                                                                                             \
   }
@@ -708,12 +716,10 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
     const int ni = __double2loint(nd);
     nd -= cM;
     const double rr = fma(nd, cL, -tc);
-    double p = fma(rr, c3, c2);
-    p = fma(p, rr, c1);
-    p = fma(p, rr, c1);
+    const double p = RB_EXP_POLY(rr);
     const double v = p * s_tab[ni & (kExpTab - 1)];
-    double e = __hiloint2double(__double2hiint(v) + ((ni << 10) & 0xFFF00000), __double2loint(v));
-    if ((unsigned)__double2hiint(nd) > 0xC12FF000u) e = 0.0;
+    double e = __hiloint2double(__double2hiint(v) + ((ni << (20 - kExpTabLog)) & 0xFFF00000), __double2loint(v));
+    if ((unsigned)__double2hiint(nd) > (unsigned)__double2hiint(-1022.0 * kExpTab)) e = 0.0;
     const double w = e * last_dd;
     iW = fma(last_qy, w, iW);
     Tb = fma(last_qz, w, Tb);
@@ -784,7 +790,7 @@ int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total,
   const int nel = ngroups * (L - 1) * 8;
   if (!ctx->exp_tab) {
     RB_CUDA(ctx, cudaMalloc(&ctx->exp_tab, kExpTab * sizeof(double)));
-    exp_tab_init_kernel<<<kExpTab / 256, 256, 0, ctx->stream>>>(ctx->exp_tab);
+    exp_tab_init_kernel<<<(kExpTab + 255) / 256, 256, 0, ctx->stream>>>(ctx->exp_tab);
     ctx->launches += 1;
   }
   rt_prepare_kernel<<<(nel + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ngroups, (double4*)scratch);
