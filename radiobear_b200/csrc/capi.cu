@@ -396,13 +396,14 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_de
   RB_CUDA(ctx, cudaEventRecord(ev[0], user));               // inputs, operands and geometry are ready
   RB_CUDA(ctx, cudaStreamWaitEvent(sI, ev[0], 0));
   RB_CUDA(ctx, cudaStreamWaitEvent(sC, ev[0], 0));
-  // chunk boundaries: equal numbers of planet-hitting rays would be ideal; equal tile counts in the middle
-  // rows are close enough, so cut by tiles
+  // chunk boundaries are cut by tiles of 32 rays
   const int64_t tiles = (R + 31) / 32;
   int status = RB_OK;
   ctx->stream = sI;
   for (int c = 0; c < nch && status == RB_OK; ++c) {
-    const int64_t t0 = tiles * c / nch, t1 = tiles * (c + 1) / nch;
+    // shrinking chunks: the copy of the last chunk is the only one nothing overlaps, so keep it small
+    auto cut = [&](int j) { return (int64_t)llround((double)tiles * (1.0 - pow(1.0 - (double)j / nch, 1.6))); };
+    const int64_t t0 = cut(c), t1 = (c + 1 == nch) ? tiles : cut(c + 1);
     const int64_t r0 = t0 * 32, r1 = (t1 * 32 < R) ? t1 * 32 : R;
     if (r1 <= r0) continue;
     RtLaunch Lc = full;

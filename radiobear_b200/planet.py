@@ -175,15 +175,18 @@ class Planet:
             Tb = res['Tb']
         else:
             pts = np.asarray(self.b, dtype=np.float64)
+            # per-point atmosphere index (planet_base.py map_b_to_atm); None = everything uses atmos[0]
             which = np.array([self.map_b_to_atm(list(p)) for p in pts]) if \
-                getattr(self.config, 'bmapmodule', 'nobmap') not in (None, 'nobmap') else np.zeros(len(pts), dtype=int)
+                getattr(self.config, 'bmapmodule', 'nobmap') not in (None, 'nobmap') else None
+            if which is not None and not which.any():
+                which = None
             f32 = self.data_type == 'image'
             world, rank = parallel.world_rank()
-            if world > 1 and len(pts) >= 64 * world and not which.any():
+            if world > 1 and len(pts) >= 64 * world and which is None:
                 # one process per GPU: shard rows / points, gather to rank 0 (None on the other ranks)
                 rows = (pts[::self.imSize[0], 1], self.imSize[0]) if self.data_type == 'image' else None
                 Tb = parallel.run_points_sharded(self, pts, self.atmos[0], self.alpha[0], out_f32=f32, rows=rows)
-            elif not which.any():
+            elif which is None:
                 Tb = self.bright.batch(pts, self.freqs, self.atmos[0], self.alpha[0], self.config.orientation,
                                        out_f32=f32)['Tb']
             else:
