@@ -329,9 +329,7 @@ def run_gpu(args):
                                 truncate_strength=cfg.truncate_strength, out=slab_t, freqs_host=freqs, ctx=ctx)
         engine.rt_batch_dev(radius_t, nidx[0], nidx[1], b_t, slab_t, T_t, cfg.Req, cfg.Rpol, orient, cfg.gtype, cfg.limb,
                             out_f32=True, tau_cut=100.0, out=tb_t, ctx=ctx)
-        if world > 1:
-            return parallel.gather_blocks(tb_t, parts, dst=0)
-        return tb_t
+        return tb_t                         # N > 1: the image stays row-sharded in HBM, no data-path collective
 
     def barrier():
         if world > 1:
@@ -391,9 +389,13 @@ def run_gpu(args):
 
     # ---- end to end through the public API (host buffers) ----------------------------------------
     planet = Planet('jupiter', atmosphere=atm, verbose=False)
-    h2d = (pts.nbytes + atm.gas.nbytes + atm.cloud.nbytes + 3 * L * 8 + L * F * 8 + F * 8) if world == 1 else \
-        (pts.nbytes + 2 * L * 8 + L * F * 8 + atm.gas.nbytes + 3 * L * 8)
-    d2h = (n * n * F * 4 + L * F * 8) if rank == 0 else L * F * 8
+    # bytes this rank moves per Planet.run: impact points, atmosphere, alpha slab in; its Tb rows + alpha slab out
+    h2d = pts.nbytes + atm.gas.nbytes + atm.cloud.nbytes + 3 * L * 8 + L * F * 8 + F * 8
+    d2h = len(pts) * F * 4 + L * F * 8
+    io = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(io)
+    h2d, d2h = [int(x) for x in io.tolist()]
     for _ in range(2):
         planet.run(list(freqs), b=BSTEP, reuse_override='false')
     barrier()
@@ -443,7 +445,7 @@ def run_gpu(args):
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic image grid over the Jupiter default atmosphere fixture',
             'config': {'workload': WORKLOAD, 'pixels': 'on-disc', 'on_disc_pixels': n_on, 'nan_limb_pixels': n_nan,
-                       'all_pixels': n_all, 'layers': L, 'freqs': F, 'sharding': 'image rows balanced by on-disc pixels',
+                       'all_pixels': n_all, 'layers': L, 'freqs': F, 'sharding': 'image rows balanced by on-disc pixels; output stays row-sharded in HBM (no collective); e2e: every rank copies its rows into one shared pinned host image',
                        'l2': 'flushed between timed steps (256 MiB write, untimed); ds slab (0.94 GB) exceeds L2',
                        'tb_dtype_out': 'f32', 'tau_cut': 100.0},
             'clocks': clocks,

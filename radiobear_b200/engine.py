@@ -232,6 +232,8 @@ def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 
     rt.disc_average, rt.out_f32, rt.tau_cut = int(bool(disc_average)), int(bool(out_f32)), float(tau_cut or 0.0)
     if out is None:
         out = pinned_pool.get((R, F), np.float32 if out_f32 else np.float64)
+    elif out.shape != (R, F) or out.dtype != (np.float32 if out_f32 else np.float64) or not out.flags.c_contiguous:
+        raise ValueError('rt_batch: out must be a C-contiguous [R][F] array of the output dtype')
     intW = np.empty((R, F)) if want_intW else None
     prof = None
     if profile_ray >= 0:

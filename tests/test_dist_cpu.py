@@ -70,3 +70,55 @@ def test_partition_even():
     assert parallel.partition_even(7, 2) == [(0, 4), (4, 7)]
     assert parallel.partition_even(64, 8)[-1] == (56, 64)
     assert parallel.partition_even(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+
+
+def _worker_exchange(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), LOCAL_WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        grid = set_utils.image_grid(0.05)
+        q = 66854.0 / 71492.0
+        rparts = parallel.partition_rows(grid, q, world)
+        n = len(grid)
+        parts = [(a * n, b * n) for a, b in rparts]
+        ex = parallel.host_exchange()
+        ok = ex.usable
+        held = []
+        for call in range(6):
+            # flat pixel blocks [rows_i * n, F] like run_points_sharded delivers them
+            local = (_stub_tb(rparts[rank], n, 3) + call).reshape(-1, 3).contiguous()
+            got = ex.deliver(local, parts, (3,), np.float32)
+            if rank == 0:
+                ref = (_stub_tb((0, n), n, 3) + call).reshape(-1, 3).numpy()
+                ok = ok and got.shape == ref.shape and bool(np.array_equal(got, ref))
+                if call < 2:
+                    held.append((got, ref))       # still referenced: the segment must not be recycled
+            else:
+                ok = ok and got is None
+        for got, ref in held:
+            ok = ok and bool(np.array_equal(got, ref))
+        nseg = len(ex.segments)
+        dist.barrier()
+        del held
+        ex.close()
+        out.put((ok, nseg))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_host_exchange_world2():
+    """Row-sharded delivery through the shared host segment: contents, None on rank 1, and no recycling
+    of a segment whose array the caller still holds."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_exchange, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[0] for r in res)
+    # calls 0, 1 are held -> own segments; later calls alternate between two more (the previous result is
+    # still referenced while the next call runs)
+    assert max(r[1] for r in res) == 4
