@@ -325,6 +325,8 @@ def run_gpu(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step():
+        # geometry first, on the library's side stream: it does not depend on the absorption and overlaps it
+        engine.geometry_prefetch_dev(radius_t, nidx[0], nidx[1], b_t, cfg.Req, cfg.Rpol, orient, cfg.gtype, cfg.limb, ctx=ctx)
         engine.alpha_layers_dev(freqs_t, T_t, P_t, gas_t, cfg.C, formalisms=forms, other_dicts=other,
                                 truncate_strength=cfg.truncate_strength, out=slab_t, freqs_host=freqs, ctx=ctx)
         engine.rt_batch_dev(radius_t, nidx[0], nidx[1], b_t, slab_t, T_t, cfg.Req, cfg.Rpol, orient, cfg.gtype, cfg.limb,
@@ -454,8 +456,8 @@ def run_gpu(args):
             'gpu_launches': int(launches),
             'roofline': roofline,
             'kernels_ms': {'alpha_lines': k_alpha, 'ray_geometry': k_geo, 'rt_integrate': rt_ms,
-                           'note': 'device time per step summed over the {} ray chunks of the pipeline; geometry(c+1) '
-                                   'overlaps integrate(c), so the sum exceeds ms_per_step'.format(rt_chunks)},
+                           'note': 'device time of each kernel family per step ({} integrate launch(es)); ray_geometry runs on a side '
+                                   'stream concurrently with alpha_lines, so the sum exceeds ms_per_step'.format(rt_chunks)},
             'value_all_pixels': n_all * F / (ms_per_step * 1e-3),
         }
         if cpu_v is not None:

@@ -195,6 +195,16 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* geom, const rb_rt_desc*
 int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* geom, const rb_rt_desc* rt, int64_t n_rays,
                     const double* b, void* out_Tb, double* out_integrated_W);
 
+/* Start the ray geometry (raypath.compute_ds of every ray, raypath.py:108-273) of the NEXT rb_rt_batch[_dev]
+ * call now, on an internal stream forked from the context stream, so that it overlaps whatever the caller
+ * enqueues in between -- typically rb_alpha_layers[_dev], which does not depend on it.  The next
+ * rb_rt_batch (after rb_geometry_prefetch: host geom->radius / b) or rb_rt_batch_dev (after
+ * rb_geometry_prefetch_dev: device pointers) with the same n_rays, b pointer and geometry descriptor waits
+ * for that stream and skips its own geometry launch; any other ray call drops the prefetched geometry.  The
+ * caller must not change b[] in between.  Purely an ordering optimisation: results are identical. */
+int rb_geometry_prefetch(rb_context* ctx, const rb_geometry_desc* geom, int64_t n_rays, const double* b);
+int rb_geometry_prefetch_dev(rb_context* ctx, const rb_geometry_desc* geom, int64_t n_rays, const double* b);
+
 /* Integration only, for caller-supplied segments (Brightness.single with a given Ray):
  *   ds : [R][S] km host, nseg[R]; layer4ds is implicit 0..nseg-1 (raypath.py:222-225).          */
 int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int64_t n_rays, int32_t n_seg,

@@ -88,6 +88,8 @@ def load():
         'rb_compute_ds': (C.c_int, [vp, C.POINTER(GeometryDesc), i64, vp, vp, vp, vp]),
         'rb_rt_batch': (C.c_int, [vp, C.POINTER(GeometryDesc), C.POINTER(RtDesc), i64, vp, vp, vp, i64, vp, vp, vp]),
         'rb_rt_batch_dev': (C.c_int, [vp, C.POINTER(GeometryDesc), C.POINTER(RtDesc), i64, vp, vp, vp]),
+        'rb_geometry_prefetch': (C.c_int, [vp, C.POINTER(GeometryDesc), i64, vp]),
+        'rb_geometry_prefetch_dev': (C.c_int, [vp, C.POINTER(GeometryDesc), i64, vp]),
         'rb_rt_integrate': (C.c_int, [vp, C.POINTER(RtDesc), i32, i64, i32, vp, vp, vp, vp]),
         'rb_probe_fp64_peak': (C.c_int, [vp, C.c_int, C.POINTER(dbl)]),
         'rb_probe_rcp': (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
@@ -104,7 +106,7 @@ EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error'
                     'rb_synchronize',
                     'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_kernel_timed_count',
                     'rb_set_rt_chunks', 'rb_count_steps', 'rb_set_catalog', 'rb_alpha_layers',
-                    'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_compute_ds', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
+                    'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_compute_ds', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
                     'rb_probe_fp64_peak', 'rb_probe_rcp']
 
 _EXC = {RB_ERR_INVALID: ValueError, RB_ERR_CUDA: RadiobearB200Error, RB_ERR_NOMEM: MemoryError,

@@ -28,6 +28,13 @@ class Brightness:
         a['T'] = atm.gas[atm.config.C['T']]
         return a
 
+    def prefetch(self, b, atm, orientation=None):
+        """Start the ray geometry of a coming batch(b, ...) now (it does not need the absorption), so that it
+        overlaps Alpha.get_layers.  `b` must be the same float64 array later handed to batch()."""
+        b = np.asarray(b, dtype=np.float64)
+        if b.ndim == 2 and b.shape[0] >= 4096 and b.flags.c_contiguous:
+            engine.geometry_prefetch(b=b, **raypath._geometry_args(atm, orientation, None))
+
     def batch(self, b, freqs, atm, alpha, orientation=None, disc_average=False, out_f32=False, want_intW=False):
         """Tb[R][F] for impact points b[R][2]; off-planet rays give T_cmb, limb rays below the tangent
         shell give NaN exactly like the reference."""

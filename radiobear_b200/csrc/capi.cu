@@ -87,6 +87,7 @@ void rb_destroy(rb_context* ctx) {
     for (auto& c : ctx->cat)
       if (c) cudaFree(c);
     if (ctx->exp_tab) cudaFree(ctx->exp_tab);
+    if (ctx->ticket.done) cudaEventDestroy(ctx->ticket.done);
     for (int i = 0; i < 3; ++i)
       for (int r = 0; r < rb_context::kEvRing; ++r)
         for (int j = 0; j < 2; ++j)
@@ -310,6 +311,72 @@ static void aspect_out(const rb_geometry_desc* g, double rNorm, double* out) {
   out[2] = rNorm;
 }
 
+// ---- prefetched geometry (rb_geometry_prefetch[_dev]) ---------------------------------------------------
+static bool same_geometry(const rb_geometry_desc& a, const rb_geometry_desc& b) {
+  return a.n_layers == b.n_layers && a.radius == b.radius && a.n0 == b.n0 && a.n1 == b.n1 && a.Req == b.Req &&
+         a.Rpol == b.Rpol && a.orientation[0] == b.orientation[0] && a.orientation[1] == b.orientation[1] &&
+         a.gtype == b.gtype && a.limb == b.limb;
+}
+
+// true (and the ticket is consumed, ctx->stream made to wait for it) when the prefetched geometry is the one
+// this call needs; any other state drops the ticket: the caller is about to overwrite the ds buffers
+static bool take_ticket(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const void* b) {
+  auto& t = ctx->ticket;
+  if (!t.valid) return false;
+  const bool hit = g && t.R == R && t.b == b && same_geometry(t.g, *g);
+  cudaStreamWaitEvent(ctx->stream, t.done, 0);   // hit: the geometry is ready; miss: it no longer writes the buffers
+  t.valid = false;
+  return hit;
+}
+static void drop_ticket(rb_context* ctx) { take_ticket(ctx, nullptr, -1, nullptr); }
+
+static int geometry_prefetch(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const double* b, bool host) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (!b || !g || !g->radius) return rb_fail(ctx, RB_ERR_INVALID, "geometry_prefetch: null pointer");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  RtLaunch L{};
+  RB_TRY(make_geometry(ctx, g, R, &L));
+  const size_t S = L.L - 1;
+  auto& t = ctx->ticket;
+  drop_ticket(ctx);
+  void *p_rad = nullptr, *p_b = nullptr, *p_ds, *p_n;
+  if (host) {
+    RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, L.L * 8, &p_rad));
+    RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
+  }
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
+  if (!ctx->aux[0]) RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking));
+  if (!t.done) RB_CUDA(ctx, cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
+  cudaStream_t user = ctx->stream, sG = ctx->aux[0];
+  // fork: everything already enqueued on the context stream (the producers of b, earlier users of the
+  // buffers) comes first
+  RB_CUDA(ctx, cudaEventRecord(t.done, user));
+  RB_CUDA(ctx, cudaStreamWaitEvent(sG, t.done, 0));
+  if (host) {
+    RB_CUDA(ctx, cudaMemcpyAsync(p_rad, g->radius, L.L * 8, cudaMemcpyHostToDevice, sG));
+    RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, sG));
+    L.radius = (const double*)p_rad; L.b = (const double*)p_b;
+  } else {
+    L.radius = g->radius; L.b = b;
+  }
+  L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
+  ctx->stream = sG;
+  const int status = rb_launch_geometry(ctx, L);
+  ctx->stream = user;
+  RB_TRY(status);
+  RB_CUDA(ctx, cudaEventRecord(t.done, sG));
+  t.valid = true; t.R = R; t.b = b; t.g = *g;
+  return RB_OK;
+}
+
+int rb_geometry_prefetch(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const double* b) {
+  return geometry_prefetch(ctx, g, R, b, true);
+}
+int rb_geometry_prefetch_dev(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const double* b) {
+  return geometry_prefetch(ctx, g, R, b, false);
+}
+
 int rb_compute_ds(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const double* b, double* out_ds,
                   int32_t* out_nseg, double* out_aspect) {
   if (!ctx) return RB_ERR_INVALID;
@@ -317,6 +384,7 @@ int rb_compute_ds(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const d
   RB_CUDA(ctx, cudaSetDevice(ctx->device));
   RtLaunch L{};
   RB_TRY(make_geometry(ctx, g, R, &L));
+  drop_ticket(ctx);                                          // a prefetched geometry shares these buffers
   const size_t S = L.L - 1;
   void *p_rad, *p_b, *p_ds, *p_n, *p_o;
   RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, L.L * 8, &p_rad));
@@ -377,12 +445,12 @@ static int choose_chunks(const rb_context* ctx, int64_t R, bool rays_path, bool 
 }
 
 static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_desc* rd, void* d_out, double* d_intW,
-                           void* h_out, double* h_intW) {
+                           void* h_out, double* h_intW, bool have_geometry) {
   const int64_t R = full.R;
   const size_t S = full.L - 1, F = rd->n_freqs, esz = rd->out_f32 ? 4 : 8;
   RtPrep prep;
   RB_TRY(rb_rt_prepare(ctx, full.L, rd, R, false, &prep));
-  RB_TRY(rb_launch_geometry(ctx, full));
+  if (!have_geometry) RB_TRY(rb_launch_geometry(ctx, full));
   const int nch = choose_chunks(ctx, R, prep.use_rays, h_out != nullptr);
   if (nch == 1) {
     RB_TRY(rb_launch_integrate(ctx, full, rd, prep, d_out, d_intW, -1, nullptr, nullptr, nullptr));
@@ -443,7 +511,8 @@ int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc
   RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   L.radius = g->radius; L.b = b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
-  return run_rt_pipeline(ctx, L, rt, out_Tb, out_intW, nullptr, nullptr);
+  const bool have_geometry = take_ticket(ctx, g, R, b);
+  return run_rt_pipeline(ctx, L, rt, out_Tb, out_intW, nullptr, nullptr, have_geometry);
 }
 
 int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt, int64_t R, const double* b,
@@ -469,14 +538,17 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   RB_TRY(rb_ensure(ctx, RB_BUF_TB, (size_t)R * F * esz, &p_tb));
   if (out_intW) RB_TRY(rb_ensure(ctx, RB_BUF_INTW, (size_t)R * F * 8, &p_iw));
   cudaStream_t s = ctx->stream;
-  RB_CUDA(ctx, cudaMemcpyAsync(p_rad, g->radius, nL * 8, cudaMemcpyHostToDevice, s));
-  RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, s));
+  const bool have_geometry = take_ticket(ctx, g, R, b);      // radius and b were staged by the prefetch
+  if (!have_geometry) {
+    RB_CUDA(ctx, cudaMemcpyAsync(p_rad, g->radius, nL * 8, cudaMemcpyHostToDevice, s));
+    RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, s));
+  }
   RB_CUDA(ctx, cudaMemcpyAsync(p_alpha, rt->alpha, nL * F * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_T, rt->T, nL * 8, cudaMemcpyHostToDevice, s));
   L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
   rb_rt_desc rd = *rt;
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
-  RB_TRY(run_rt_pipeline(ctx, L, &rd, p_tb, (double*)p_iw, out_Tb, out_intW));
+  RB_TRY(run_rt_pipeline(ctx, L, &rd, p_tb, (double*)p_iw, out_Tb, out_intW, have_geometry));
   if (profile_ray >= 0) {
     // re-run the selected ray alone with the profile-writing variant (Brightness.tau/.W/.Tb_lyr)
     RB_TRY(rb_ensure(ctx, RB_BUF_PROFILE, 3 * F * S * 8 + F * 8, &p_prof));
@@ -505,6 +577,7 @@ int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int
   if (!ds || !nseg || R <= 0) return rb_fail(ctx, RB_ERR_INVALID, "rt_integrate: null pointer / no rays");
   if (n_layers < 2 || n_seg != n_layers - 1) return rb_fail(ctx, RB_ERR_INVALID, "rt_integrate: n_seg must be n_layers - 1");
   RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  drop_ticket(ctx);
   RtLaunch L{};
   L.L = n_layers; L.R = R; L.Rpad = (R + 31) & ~(int64_t)31;
   const size_t nL = n_layers, S = n_seg, F = rt->n_freqs;

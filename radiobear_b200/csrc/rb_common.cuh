@@ -40,6 +40,14 @@ struct rb_context {
   std::vector<cudaEvent_t> pipe_ev;
   int rt_chunks = 0;  // 0 = automatic
   unsigned long long* step_counter = nullptr;  // device counter of integrated segment-steps (measurement aid)
+  // geometry computed ahead of the rt call that will use it (rb_geometry_prefetch[_dev]); single use
+  struct GeoTicket {
+    bool valid = false;
+    int64_t R = 0;
+    const void* b = nullptr;
+    rb_geometry_desc g{};
+    cudaEvent_t done = nullptr;
+  } ticket;
   double* exp_tab = nullptr;  // 2^(j/1024), j = 0..1023: copied into shared memory by every integration CTA
 };
 

@@ -214,6 +214,30 @@ def compute_ds(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='
     return ds, nseg, aspect
 
 
+def geometry_prefetch(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None):
+    """Start the ray geometry of the next rt_batch(b=<the same array>, same geometry) now so that it overlaps
+    the absorption kernel (rb_geometry_prefetch).  `radius` and `b` must be the very arrays (same memory) later
+    given to rt_batch and must stay unchanged until then; returns the (radius, b) pair to pass on."""
+    ctx = ctx or _lib.get_context()
+    ctx.use_own_stream()
+    radius = f64(radius)
+    b = f64(np.atleast_2d(b))
+    g = build_geometry_desc(radius.shape[0], refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb)
+    g.radius = ptr(radius)
+    ctx.check(ctx.lib.rb_geometry_prefetch(ctx.h, C.byref(g), b.shape[0], ptr(b)))
+    return radius, b
+
+
+def geometry_prefetch_dev(radius_t, n0, n1, b_t, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None):
+    """Device-resident variant of geometry_prefetch (torch CUDA tensors; pairs with rt_batch_dev)."""
+    import torch
+    ctx = ctx or _lib.get_context()
+    g = build_geometry_desc(radius_t.shape[0], n0, n1, Req, Rpol, orientation, gtype, limb)
+    g.radius = radius_t.data_ptr()
+    ctx.set_stream(torch.cuda.current_stream(b_t.device).cuda_stream)
+    ctx.check(ctx.lib.rb_geometry_prefetch_dev(ctx.h, C.byref(g), b_t.shape[0], b_t.data_ptr()))
+
+
 def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape',
              disc_average=False, out_f32=False, tau_cut=100.0, want_intW=False, profile_ray=-1, ctx=None, out=None):
     """Brightness.single over a batch of rays: Tb[R][F] (+ integrated_W, + profiles of one ray)."""

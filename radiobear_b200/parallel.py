@@ -311,6 +311,20 @@ def host_exchange():
     return _EXCHANGE
 
 
+def point_blocks(npts, cfg, rows, world):
+    """[start, stop) blocks of the flat point list for every rank: whole image rows balanced by on-disc
+    pixels when `rows` = (grid of row y values, pixels per row) is given, else an even split."""
+    if rows is not None:
+        grid, ncol = rows
+        rparts = partition_rows(grid, cfg.Rpol / cfg.Req if cfg.gtype == 'ellipse' else 1.0, world)
+        return [(a * ncol, b * ncol) for a, b in rparts]
+    return partition_even(npts, world)
+
+
+def local_block(npts, cfg, rows, world, rank):
+    return point_blocks(npts, cfg, rows, world)[rank]
+
+
 def run_points_sharded(planet, pts, atm, alpha, out_f32=True, rows=None):
     """Brightness temperatures of impact points pts[R][2] computed by all ranks of the process group.
 
@@ -325,12 +339,7 @@ def run_points_sharded(planet, pts, atm, alpha, out_f32=True, rows=None):
     world, rank = world_rank()
     dev = torch.device('cuda', torch.cuda.current_device())
     cfg = atm.config
-    if rows is not None:
-        grid, ncol = rows
-        rparts = partition_rows(grid, cfg.Rpol / cfg.Req if cfg.gtype == 'ellipse' else 1.0, world)
-        parts = [(a * ncol, b * ncol) for a, b in rparts]
-    else:
-        parts = partition_even(len(pts), world)
+    parts = point_blocks(len(pts), cfg, rows, world)
     s, e = parts[rank]
     F = alpha.slab.shape[1]
     ex = host_exchange()

@@ -157,6 +157,12 @@ class Planet:
         freqs, freqUnit = self.set_freqs(freqs=freqs, freqUnit=freqUnit)
         reuse = self.check_reuse(freqs, scale, get_alpha, save_alpha, reuse_override=str(reuse_override).lower())
         t0 = datetime.datetime.now()
+        self.set_b(b=b, block=block)
+        self._pts = None
+        local_pts = self._local_points()
+        if not reuse and local_pts is not None:
+            # the ray geometry does not depend on the absorption: start it first, on its own stream
+            self.bright.prefetch(local_pts, self.atmos[0], self.config.orientation)
         if not reuse:
             self.freqs = freqs
             self.freqUnit = utils.proc_unit(freqUnit)
@@ -165,7 +171,6 @@ class Planet:
                               save_alpha=save_alpha)
             if self.verbose:
                 print("Absoprtion calc took {:.3f} s".format(utils.timer(datetime.datetime.now() - t0)))
-        self.set_b(b=b, block=block)
         runStart = datetime.datetime.now()
         F = len(self.freqs)
         disc = isinstance(self.b[0], str)
@@ -174,7 +179,7 @@ class Planet:
                                     disc_average=True)
             Tb = res['Tb']
         else:
-            pts = np.asarray(self.b, dtype=np.float64)
+            pts = self._pts if self._pts is not None else np.asarray(self.b, dtype=np.float64)
             # per-point atmosphere index (planet_base.py map_b_to_atm); None = everything uses atmos[0]
             which = np.array([self.map_b_to_atm(list(p)) for p in pts]) if \
                 getattr(self.config, 'bmapmodule', 'nobmap') not in (None, 'nobmap') else None
@@ -221,6 +226,19 @@ class Planet:
             fileIO.FileIO(directory=self.config.output_directory).write(
                 os.path.join(self.config.output_directory, fn), self.data_return)
         return self.data_return
+
+    def _local_points(self):
+        """The impact points this process will integrate with atmos[0] in one batch (its row block when the
+        process group shards the image), or None for disc-averaged / b-mapped / tiny requests."""
+        if isinstance(self.b[0], str) or getattr(self.config, 'bmapmodule', 'nobmap') not in (None, 'nobmap'):
+            return None
+        pts = self._pts = np.asarray(self.b, dtype=np.float64)      # run() integrates this very array
+        world, rank = parallel.world_rank()
+        if world > 1 and len(pts) >= 64 * world:
+            rows = (pts[::self.imSize[0], 1], self.imSize[0]) if self.data_type == 'image' else None
+            s, e = parallel.local_block(len(pts), self.atmos[0].config, rows, world, rank)
+            return pts[s:e] if e > s else None
+        return pts
 
     def set_header(self, run_start, run_stop):
         from . import raypath

@@ -259,3 +259,33 @@ def test_rt_edge_cases(eng):
     # NaN / infinite impact parameters miss the planet like |b| >= 1
     out = eng.rt_batch(b=np.array([[np.nan, 0.0], [np.inf, 0.0], [0.0, 0.0]]), alpha_slab=slab, T=T, **geom(a))['Tb']
     assert out[0, 0] == 2.725 and out[1, 0] == 2.725 and out[2, 0] > 100.0
+
+
+def test_geometry_prefetch_is_only_an_ordering_optimisation(eng):
+    """rb_geometry_prefetch: identical Tb with the geometry started ahead of the absorption; a ticket for
+    other rays, or one followed by compute_ds (shared buffers), is dropped and the rays are recomputed."""
+    a = golden('atm_jupiter.npz')
+    C = keymap(a['C_keys'])
+    T = a['gas'][C['T']]
+    freqs = np.array([2.0, 22.0, 60.0])
+    rng = np.random.default_rng(11)
+    b = np.ascontiguousarray(rng.uniform(-1.02, 1.02, (6000, 2)))
+    g = geom(a)
+    radius = np.ascontiguousarray(g.pop('radius'), dtype=np.float64)
+    ref = eng.rt_batch(radius=radius, b=b, alpha_slab=_slab(eng, a, freqs), T=T, **g)['Tb'].copy()
+    # hit: prefetch, then the absorption call, then the rt call with the same arrays
+    eng.geometry_prefetch(radius, g['refr_index'], b, g['Req'], g['Rpol'], g['orientation'], g['gtype'], g['limb'])
+    slab = _slab(eng, a, freqs)
+    got = eng.rt_batch(radius=radius, b=b, alpha_slab=slab, T=T, **g)['Tb']
+    assert np.array_equal(got, ref, equal_nan=True)
+    # miss: other rays than the prefetched ones
+    eng.geometry_prefetch(radius, g['refr_index'], b, g['Req'], g['Rpol'], g['orientation'], g['gtype'], g['limb'])
+    b2 = np.ascontiguousarray(b[::-1])
+    got2 = eng.rt_batch(radius=radius, b=b2, alpha_slab=slab, T=T, **g)['Tb']
+    assert np.array_equal(got2, ref[::-1], equal_nan=True)
+    # dropped: compute_ds in between reuses the segment buffers
+    eng.geometry_prefetch(radius, g['refr_index'], b, g['Req'], g['Rpol'], g['orientation'], g['gtype'], g['limb'])
+    ds, nseg, _ = eng.compute_ds(radius=radius, b=b[:7], **g)
+    assert ds.shape[0] == 7
+    got3 = eng.rt_batch(radius=radius, b=b, alpha_slab=slab, T=T, **g)['Tb']
+    assert np.array_equal(got3, ref, equal_nan=True)
