@@ -330,7 +330,7 @@ def run_gpu(args):
         engine.alpha_layers_dev(freqs_t, T_t, P_t, gas_t, cfg.C, formalisms=forms, other_dicts=other,
                                 truncate_strength=cfg.truncate_strength, out=slab_t, freqs_host=freqs, ctx=ctx)
         engine.rt_batch_dev(radius_t, nidx[0], nidx[1], b_t, slab_t, T_t, cfg.Req, cfg.Rpol, orient, cfg.gtype, cfg.limb,
-                            out_f32=True, tau_cut=100.0, out=tb_t, ctx=ctx)
+                            out_f32=True, tau_cut=engine.TAU_CUT, out=tb_t, ctx=ctx)
         return tb_t                         # N > 1: the image stays row-sharded in HBM, no data-path collective
 
     def barrier():
@@ -449,7 +449,7 @@ def run_gpu(args):
             'config': {'workload': WORKLOAD, 'pixels': 'on-disc', 'on_disc_pixels': n_on, 'nan_limb_pixels': n_nan,
                        'all_pixels': n_all, 'layers': L, 'freqs': F, 'sharding': 'image rows balanced by on-disc pixels; output stays row-sharded in HBM (no collective); e2e: every rank copies its rows into one shared pinned host image',
                        'l2': 'flushed between timed steps (256 MiB write, untimed); ds slab (0.94 GB) exceeds L2',
-                       'tb_dtype_out': 'f32', 'tau_cut': 100.0},
+                       'tb_dtype_out': 'f32', 'tau_cut': engine.TAU_CUT},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': 1e3 * float(e2e_t.item()), 'api': 'Planet.run(freqs, b=0.005)'},

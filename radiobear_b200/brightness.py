@@ -20,7 +20,7 @@ class Brightness:
             config = pcfg.planetConfig('x', configFile=config)
             config.update_config(**kwargs)
         self.config = config
-        self.tau_cut = 100.0
+        self.tau_cut = engine.TAU_CUT
         self.travel = None
 
     def _args(self, atm, orientation):

@@ -552,7 +552,14 @@ constexpr int kTileDs = (kChunk + 1) * 32;   // doubles per ds tile
 constexpr int kTilePp = kChunk * 8;          // double4 per operand tile
 constexpr size_t kRaysSmemBytes = kStages * (kTileDs * sizeof(double) + kTilePp * sizeof(double4));
 
-__global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_constant__ RtK k) {
+#ifndef RB_RT_GROUP
+#define RB_RT_GROUP 4
+#endif
+#ifndef RB_RT_CTAS
+#define RB_RT_CTAS 4
+#endif
+constexpr int kGroup = RB_RT_GROUP;          // segments per group = independent exp chains per thread
+__global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(const __grid_constant__ RtK k) {
   __shared__ __align__(16) double s_tab[kExpTab];          // 2^(j/1024), copied from k.exp_tab with chunk 0
   __shared__ __align__(16) double s_ds[kStages * kTileDs];
   __shared__ __align__(16) double4 s_pp[kStages * kTilePp];
@@ -680,22 +687,23 @@ __global__ void __launch_bounds__(256, 4) rt_integrate_rays_kernel(const __grid_
       const double* dp = dsb;
       const double4* qp = ppb;
 #pragma unroll 1
-      for (; u + 4 <= m; u += 4, dp += 4 * 32, qp += 4 * 8) {
-        const double d0 = dp[0], d1 = dp[32], d2 = dp[64], d3 = dp[96], d4 = dp[128];
-        const double4 q0 = qp[0], q1 = qp[8], q2 = qp[16], q3 = qp[24];
-        const double t0 = fma(q0.x, d0, tau), t1 = fma(q1.x, d1, t0), t2 = fma(q2.x, d2, t1), t3 = fma(q3.x, d3, t2);
-        const double nd3 = fma(t3, cA, cM) - cM;
-        if ((unsigned)__double2hiint(nd3) > thr_hi) break;   // tau_cut is crossed inside this group: go step by step
-        double w0, w1, w2, w3;
-        RB_RT_WEIGHT(t0, d0 + d1, w0);
-        RB_RT_WEIGHT(t1, d1 + d2, w1);
-        RB_RT_WEIGHT(t2, d2 + d3, w2);
-        RB_RT_WEIGHT(t3, d3 + d4, w3);
-        iW = fma(q0.y, w0, iW); Tb = fma(q0.z, w0, Tb);
-        iW = fma(q1.y, w1, iW); Tb = fma(q1.z, w1, Tb);
-        iW = fma(q2.y, w2, iW); Tb = fma(q2.z, w2, Tb);
-        iW = fma(q3.y, w3, iW); Tb = fma(q3.z, w3, Tb);
-        tau = t3;
+      for (; u + kGroup <= m; u += kGroup, dp += kGroup * 32, qp += kGroup * 8) {
+        double d[kGroup + 1], t[kGroup], w[kGroup];
+        double4 q[kGroup];
+#pragma unroll
+        for (int j = 0; j <= kGroup; ++j) d[j] = dp[j * 32];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) q[j] = qp[j * 8];
+        t[0] = fma(q[0].x, d[0], tau);
+#pragma unroll
+        for (int j = 1; j < kGroup; ++j) t[j] = fma(q[j].x, d[j], t[j - 1]);
+        const double ndl = fma(t[kGroup - 1], cA, cM) - cM;
+        if ((unsigned)__double2hiint(ndl) > thr_hi) break;   // tau_cut is crossed inside this group: go step by step
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) RB_RT_WEIGHT(t[j], d[j] + d[j + 1], w[j]);
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) { iW = fma(q[j].y, w[j], iW); Tb = fma(q[j].z, w[j], Tb); }
+        tau = t[kGroup - 1];
       }
       // remainder of the chunk / the group that crosses tau_cut: one segment at a time with the test
       for (; u < m; ++u) {

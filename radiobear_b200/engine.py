@@ -214,6 +214,13 @@ def compute_ds(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='
     return ds, nseg, aspect
 
 
+# A ray stops once tau > TAU_CUT.  Every later term of the two sums is below e^-50 (2e-22) x T (<= 2000 K) x dtau,
+# i.e. < 1e-16: less than half an ulp of the accumulated sums (integrated_W ~ 1, Tb ~ 100 K), so adding it would not
+# change either accumulator -- the cut result is bit-identical to integrating every layer like the reference
+# (asserted in tests/test_gpu_rt.py).  tau_cut=0 disables the cut.
+TAU_CUT = 50.0
+
+
 def geometry_prefetch(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None):
     """Start the ray geometry of the next rt_batch(b=<the same array>, same geometry) now so that it overlaps
     the absorption kernel (rb_geometry_prefetch).  `radius` and `b` must be the very arrays (same memory) later
@@ -239,7 +246,7 @@ def geometry_prefetch_dev(radius_t, n0, n1, b_t, Req, Rpol, orientation=(0.0, 0.
 
 
 def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape',
-             disc_average=False, out_f32=False, tau_cut=100.0, want_intW=False, profile_ray=-1, ctx=None, out=None):
+             disc_average=False, out_f32=False, tau_cut=TAU_CUT, want_intW=False, profile_ray=-1, ctx=None, out=None):
     """Brightness.single over a batch of rays: Tb[R][F] (+ integrated_W, + profiles of one ray)."""
     ctx = ctx or _lib.get_context()
     ctx.use_own_stream()
@@ -274,7 +281,7 @@ def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 
 
 
 def rt_batch_dev(radius_t, n0, n1, b_t, alpha_t, T_t, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape',
-                 disc_average=False, out_f32=True, tau_cut=100.0, ctx=None, out=None):
+                 disc_average=False, out_f32=True, tau_cut=TAU_CUT, ctx=None, out=None):
     """Device-resident variant (torch CUDA tensors, async on the current stream)."""
     import torch
     ctx = ctx or _lib.get_context()
@@ -291,7 +298,7 @@ def rt_batch_dev(radius_t, n0, n1, b_t, alpha_t, T_t, Req, Rpol, orientation=(0.
     return out
 
 
-def rt_integrate(ds, nseg, alpha_slab, T, disc_average=False, out_f32=False, tau_cut=100.0, want_intW=False, ctx=None):
+def rt_integrate(ds, nseg, alpha_slab, T, disc_average=False, out_f32=False, tau_cut=TAU_CUT, want_intW=False, ctx=None):
     """Integration only, for caller-supplied segments ds[R][L-1] (km)."""
     ctx = ctx or _lib.get_context()
     ctx.use_own_stream()

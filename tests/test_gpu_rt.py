@@ -114,7 +114,7 @@ def test_c1_disc_average_and_profiles(eng):
     big = tb['c1_W'] > 1e-300
     assert np.max(relerr(res['W'][:, :n][big], tb['c1_W'][big])) < 1e-7
     assert np.max(relerr(res['Tb_lyr'][:, :n], tb['c1_Tb_lyr'])) < 1e-8
-    cut = eng.rt_batch(b=[[0.0, 0.0]], alpha_slab=slab, T=a['gas'][C['T']], disc_average=True, tau_cut=100.0, **geom(a))
+    cut = eng.rt_batch(b=[[0.0, 0.0]], alpha_slab=slab, T=a['gas'][C['T']], disc_average=True, tau_cut=eng.TAU_CUT, **geom(a))
     assert np.array_equal(cut['Tb'], res['Tb'])                    # the tau cut does not change a single bit
 
 
@@ -213,7 +213,7 @@ def test_rt_integrate_with_supplied_segments(eng):
 def test_rays_kernel_matches_small_batch_kernel_and_tau_cut_is_exact(eng):
     """The rays-major kernel (R >= 512: cp.async tiles, table exp, regrouped sums) against the simple
     lanes = frequency kernel (R < 512: libdevice exp, reference operation order) on the same pixels, and
-    tau_cut = 100 against no cut (capped at the exp underflow point)."""
+    the default tau_cut (engine.TAU_CUT = 50) against no cut: bit-identical."""
     a = golden('atm_jupiter.npz')
     im = golden('image_c4.npz')
     C = keymap(a['C_keys'])
