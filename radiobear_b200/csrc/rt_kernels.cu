@@ -528,6 +528,17 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
+template <int OFF>
+__device__ __forceinline__ void cp_async16_at(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%2], 16;" ::"r"(dst), "l"(src), "n"(OFF) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_rounds(unsigned dst, const void* src) {
+  if constexpr (N > 0) {
+    cp_rounds<N - 1>(dst, src);
+    cp_async16_at<(N - 1) * 4096>(dst, src);
+  }
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -546,7 +557,11 @@ __device__ __forceinline__ void cp_async_wait() {
 // through L2.  The trapezoid sums are regrouped by node:
 //   sum_i (W_i+1 + W_i) h_i = sum_j W_j (h_j-1 + h_j),  W_0 = 0.
 // FP64 work per (ray, freq, segment): 1 (tau) + 9 (exp) + 1 (ds_i + ds_i+1) + 3 (weights) = 14 instructions.
-constexpr int kChunk = 32;
+#ifndef RB_RT_CHUNK
+#define RB_RT_CHUNK 32
+#endif
+constexpr int kChunk = RB_RT_CHUNK;          // segments per staged tile (multiple of 16)
+static_assert(kChunk % 16 == 0 && kChunk >= 16, "a chunk is a whole number of 4 KB copy rounds");
 constexpr int kStages = 2;
 constexpr int kTileDs = (kChunk + 1) * 32;   // doubles per ds tile
 constexpr int kTilePp = kChunk * 8;          // double4 per operand tile
@@ -560,9 +575,11 @@ constexpr size_t kRaysSmemBytes = kStages * (kTileDs * sizeof(double) + kTilePp 
 #endif
 constexpr int kGroup = RB_RT_GROUP;          // segments per group = independent exp chains per thread
 __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(const __grid_constant__ RtK k) {
-  __shared__ __align__(16) double s_tab[kExpTab];          // 2^(j/1024), copied from k.exp_tab with chunk 0
-  __shared__ __align__(16) double s_ds[kStages * kTileDs];
-  __shared__ __align__(16) double4 s_pp[kStages * kTilePp];
+  // dynamic shared memory: [ table | ds tiles x kStages | operand tiles x kStages ]
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  double* const s_tab = reinterpret_cast<double*>(s_raw);                    // 2^(j/N), copied from k.exp_tab with chunk 0
+  double* const s_ds = s_tab + kExpTab;
+  double4* const s_pp = reinterpret_cast<double4*>(s_ds + kStages * kTileDs);
   const int tid = threadIdx.y * 32 + threadIdx.x;
 
   const int S = k.L - 1;
@@ -584,14 +601,10 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   auto issue = [&](int c) {
     const unsigned bd = (c & 1) ? (unsigned)(kTileDs * sizeof(double)) : 0u;
     const unsigned bp = (c & 1) ? (unsigned)(kTilePp * sizeof(double4)) : 0u;
-    asm volatile(
-        "cp.async.cg.shared.global [%0], [%1], 16;\n\t"
-        "cp.async.cg.shared.global [%0+4096], [%1+4096], 16;\n\t"
-        "cp.async.cg.shared.global [%2], [%3], 16;\n\t"
-        "cp.async.cg.shared.global [%2+4096], [%3+4096], 16;" ::"r"(dst_ds + bd), "l"(src_ds), "r"(dst_pp + bp),
-        "l"(src_pp)
-        : "memory");
-    if (tid < 16) asm volatile("cp.async.cg.shared.global [%0+8192], [%1+8192], 16;" ::"r"(dst_ds + bd), "l"(src_ds) : "memory");
+    // kChunk / 16 rounds of 4 KB (256 threads x 16 B) per stream, then the extra ds row
+    cp_rounds<kChunk / 16>(dst_ds + bd, src_ds);
+    cp_rounds<kChunk / 16>(dst_pp + bp, src_pp);
+    if (tid < 16) cp_async16_at<(kChunk / 16) * 4096>(dst_ds + bd, src_ds);
     cp_async_commit();
     src_ds += kChunk * 32 * sizeof(double);
     src_pp += kChunk * 8 * sizeof(double4);
@@ -835,8 +848,14 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     k.exp_tab = ctx->exp_tab;
     dim3 block(32, 8), grid((k.F + 7) / 8, (unsigned)((g.R + 31) / 32));
     if (grid.y > 65535) return rb_fail(ctx, RB_ERR_INVALID, "rt: more than 2M rays per launch are not supported");
-    static_assert(kExpTab * sizeof(double) + kRaysSmemBytes <= 48 * 1024, "static shared memory limit");
-    rt_integrate_rays_kernel<<<grid, block, 0, ctx->stream>>>(k);
+    constexpr size_t smem = kExpTab * sizeof(double) + kRaysSmemBytes;
+    static_assert(smem <= 227 * 1024, "shared memory limit");
+    static bool opted_in[64] = {false};
+    if (smem > 48 * 1024 && !opted_in[ctx->device & 63]) {
+      RB_CUDA(ctx, cudaFuncSetAttribute(rt_integrate_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      opted_in[ctx->device & 63] = true;
+    }
+    rt_integrate_rays_kernel<<<grid, block, smem, ctx->stream>>>(k);
   }
   RB_CUDA(ctx, cudaGetLastError());
   RB_CUDA(ctx, rb_time_end(ctx, 2));
