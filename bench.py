@@ -46,8 +46,8 @@ UNIT = 'pixel*freq/s'
 RT_FLOPS_PER_STEP = 18.0
 RT_FP64_INSTR_PER_STEP = 11.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one rt_integrate_rays_kernel launch of this workload at N=1
-RT_DRAM_BYTES_N1 = 1145970000
-RT_DRAM_SOURCE = 'ncu --set full, profiles/r1_rt_integrate_rays.txt (1.070 GB read + 0.076 GB written)'
+RT_DRAM_BYTES_N1 = 1088100000
+RT_DRAM_SOURCE = 'ncu --set full, profiles/r1_final_rt_integrate_rays_ncu_full.txt (1.014 GB read + 0.074 GB written)'
 WORKLOAD = 'C4: Jupiter full image b=0.005 (601x601 px) x 64 freqs 1-100 GHz, 1000 layers, alpha+geometry+RT per step'
 
 
