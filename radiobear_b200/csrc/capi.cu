@@ -346,7 +346,13 @@ static int geometry_prefetch(rb_context* ctx, const rb_geometry_desc* g, int64_t
   }
   RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
-  if (!ctx->aux[0]) RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking));
+  if (!ctx->aux[0]) {
+    // highest priority: the few, long-running geometry CTAs get their SM slots ahead of the absorption
+    // kernel they overlap with (which has thousands of short CTAs to fill in around them)
+    int lo = 0, hi = 0;
+    RB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->aux[0], cudaStreamNonBlocking, hi));
+  }
   if (!t.done) RB_CUDA(ctx, cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
   cudaStream_t user = ctx->stream, sG = ctx->aux[0];
   // fork: everything already enqueued on the context stream (the producers of b, earlier users of the
@@ -421,7 +427,7 @@ static int check_rt(rb_context* ctx, const rb_rt_desc* rt, const void* out_Tb) {
 // integrate(c) was measured and is slower: the latency-bound geometry kernel starves when it shares SMs.)
 // All pointers are DEVICE pointers except h_out / h_intW.
 static int pipe_setup(rb_context* ctx, int nch) {
-  for (int i = 0; i < 3; ++i)
+  for (int i = 1; i < 3; ++i)   // aux[0] is the (high-priority) geometry prefetch stream
     if (!ctx->aux[i]) RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
   const size_t need = 4 + 2 * (size_t)nch;
   while (ctx->pipe_ev.size() < need) {
