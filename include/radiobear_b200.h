@@ -82,7 +82,13 @@ int64_t rb_count_steps(rb_context* ctx, int enable);
 #define RB_CAT_PH3 5     /* f0, I0, E, WgtI0, WgtFGB, WgtSB                        (6 cols) */
 #define RB_CAT_CO 6      /* f0, I0, E                                              (3 cols) */
 #define RB_CAT_H2O 7     /* f_o, I_o, E_o, w_s, x_s, w_h2, w_he, x_h2, x_he  (9 cols, h2o_bk.py:23-49) */
-#define RB_NUM_CATALOGS 8
+/* Orton H2 CIA table prepared for the frequencies of the call (one "line" per frequency, in call order):
+ * cols 0..9 the tabulated temperatures; then for each of the 3 pair tables of the chosen h2 state (h2-h2,
+ * h2-he, h2-ch4; h2_orton.py:12-13) 10 values at those temperatures (after the quadratic interpolation in
+ * frequency, h2_orton.py:77-108) followed by 9 x 3 coefficients (c1, c2, c3 of every interval) of the
+ * not-a-knot cubic spline through them (scipy interp1d kind='cubic', h2_orton.py:203-211): 10 + 3 x 37 cols. */
+#define RB_CAT_H2_ORTON 8
+#define RB_NUM_CATALOGS 9
 int rb_set_catalog(rb_context* ctx, int catalog, int nlines, int ncols, const double* cols);
 
 /* ---- absorption (hot path A) ----------------------------------------------------------- *
@@ -103,7 +109,8 @@ int rb_set_catalog(rb_context* ctx, int catalog, int nlines, int ncols, const do
 #define RB_F_NH3_KD 13     /* nh3/nh3_kd.py:115-351     */
 #define RB_F_NH3_SJSD 14   /* nh3/nh3_sjsd.py:6-24      */
 #define RB_F_NH3_BG 15     /* nh3/nh3_bg.py:26-74       */
-#define RB_NUM_FORMALISMS 16
+#define RB_F_H2_ORTON 16   /* h2/h2_orton.py:126-222 (table prepared by the host: RB_CAT_H2_ORTON) */
+#define RB_NUM_FORMALISMS 17
 #define RB_MAX_CONSTITUENTS 8
 
 #define RB_UNITS_INVCM 0

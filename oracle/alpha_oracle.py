@@ -606,6 +606,109 @@ def h2_jj(freq, T, P, X, P_dict, other_dict, **kwargs):
 
 
 # --------------------------------------------------------------------------------------
+# H2 CIA from Orton's tables (h2_orton.py:17-222)
+# --------------------------------------------------------------------------------------
+_ORTON_PATH = os.path.join(os.path.dirname(_DEFAULT_LINECAT), 'orton_h2.npz')
+_ORTON = {}
+_ORTON_TABLES = {'eh2h2': 0, 'nh2h2': 1, 'eh2he': 2, 'nh2he': 3, 'eh2ch4': 4, 'nh2ch4': 5}   # h2_orton.py:12
+_ORTON_STATES = {'e': 0, 'n': 1}                                                               # h2_orton.py:13
+
+
+def orton_tables(freqs):
+    """readInputFiles (h2_orton.py:17-123): the tabulated temperatures and, per table and frequency, the
+    absorption coefficients at those temperatures after the piece-wise quadratic interpolation in frequency
+    through the three tabulated wavenumbers around f (extrapolated below the first one)."""
+    if 'raw' not in _ORTON:
+        d = np.load(_ORTON_PATH)
+        _ORTON['raw'] = (int(d['ntemp']), float(d['tmax']), float(d['tmin']), np.array(d['wavenumber']), np.array(d['logtab']))
+    nTemp, Tmax, Tmin, wn, logtab = _ORTON['raw']
+    import math
+    lTmx, lTmn = math.log(Tmax), math.log(Tmin)
+    dlT = (lTmx - lTmn) / (nTemp - 1.0)
+    ta = [lTmn]
+    for i in range(nTemp - 1):                     # h2_orton.py:35-37: accumulated, not i * dlT
+        ta.append(ta[i] + dlT)
+    Ttab = np.array([math.exp(v) for v in ta])
+    ftab = np.array([v * 29.9792458 for v in wn])  # h2_orton.py:49-54
+    h2vab = np.zeros((len(_ORTON_TABLES), len(freqs), nTemp))
+    for ii in range(len(_ORTON_TABLES)):
+        for jj, f in enumerate(freqs):
+            ifreq = int(np.where(ftab > f)[0][0])
+            if ifreq == 0:
+                ifreq = 1
+            v1, v2, v3 = logtab[ii, ifreq - 1], logtab[ii, ifreq], logtab[ii, ifreq + 1]   # h2_orton.py:87-93
+            X1 = ftab[ifreq - 1]
+            X21 = ftab[ifreq] - ftab[ifreq - 1]
+            X32 = ftab[ifreq + 1] - ftab[ifreq]
+            X212 = ftab[ifreq]**2 - ftab[ifreq - 1]**2
+            X322 = ftab[ifreq + 1]**2 - ftab[ifreq]**2
+            for ll in range(nTemp):
+                Y1 = math.exp(float(v1[ll]))
+                Y21 = (math.exp(float(v2[ll])) - Y1)
+                Y32 = (math.exp(float(v3[ll])) - math.exp(float(v2[ll])))
+                DQ = X212 * X32 - X322 * X21
+                AQ = (X32 * Y21 - X21 * Y32) / DQ
+                BQ = (X212 * Y32 - X322 * Y21) / DQ
+                CQ = Y1 - AQ * X1**2 - BQ * X1
+                h2vab[ii, jj, ll] = AQ * f**2 + BQ * f + CQ
+    return Ttab, h2vab
+
+
+def h2_orton(freq, T, P, X, P_dict, other_dict, **kwargs):
+    """h2_orton.py:126-222.  The text file of the reference prints 4-5 significant digits of log(alpha); the npz
+    repack (tools/build_orton.py) holds the same numbers."""
+    from scipy.interpolate import interp1d
+    units = kwargs.get('units', 'dBperkm')
+    T0, atm2bar = 273.0, 1.01325
+    freq = [float(f) for f in freq]
+    key = tuple(freq)
+    if _ORTON.get('key') != key:
+        _ORTON['key'] = key
+        _ORTON['tab'] = orton_tables(freq)
+    Ttab, h2vab = _ORTON['tab']
+    st = _ORTON_STATES[other_dict['h2state'].lower()]
+    xh2, xhe, xch4 = _ORTON_TABLES['eh2h2'] + st, _ORTON_TABLES['eh2he'] + st, _ORTON_TABLES['eh2ch4'] + st
+    P_h2 = P * X[P_dict['H2']]
+    P_he = P * X[P_dict['HE']]
+    P_ch4 = P * X[P_dict['CH4']]
+    out = []
+    if T < Ttab[0]:                                 # quartic extrapolation below the table (h2_orton.py:150-178)
+        nexp = 4.0
+        X1 = Ttab[0]
+        X21n = Ttab[1]**nexp - Ttab[0]**nexp
+        for ii in range(len(freq)):
+            v = []
+            for jj in (0, 1):
+                Tjj = Ttab[jj]
+                a = ((P_h2 / atm2bar) * (h2vab[xh2, ii, jj] * P_h2 / atm2bar + h2vab[xhe, ii, jj] * P_he / atm2bar +
+                                         h2vab[xch4, ii, jj] * P_ch4 / atm2bar) * (T0 / Tjj)**2)
+                v.append(a)
+            Y1 = v[0]
+            Y21 = v[1] - v[0]
+            AQ = -1.0 * Y21 / X21n
+            CQ = Y1 + AQ * (X1**nexp)
+            out.append(CQ - AQ * (T**nexp))
+    elif T > Ttab[-1]:                              # h2_jj scaled to the table at its last temperature (:179-199)
+        Tnear = Ttab[-1]
+        jjnear = h2_jj(freq, Tnear, P, X, P_dict, other_dict)
+        jj = h2_jj(freq, T, P, X, P_dict, other_dict)
+        for ii in range(len(freq)):
+            anear = ((P_h2 / atm2bar) * (h2vab[xh2, ii, -1] * P_h2 / atm2bar + h2vab[xhe, ii, -1] * P_he / atm2bar +
+                                         h2vab[xch4, ii, -1] * P_ch4 / atm2bar) * (T0 / Tnear)**2)
+            out.append(jj[ii] * (anear / jjnear[ii]))
+    else:                                           # cubic spline in T through the 10 table points (:200-214)
+        for ii in range(len(freq)):
+            ah2 = interp1d(Ttab, h2vab[xh2, ii], kind='cubic')(T)
+            ahe = interp1d(Ttab, h2vab[xhe, ii], kind='cubic')(T)
+            ach4 = interp1d(Ttab, h2vab[xch4, ii], kind='cubic')(T)
+            out.append((P_h2 / atm2bar) * (ah2 * P_h2 / atm2bar + ahe * P_he / atm2bar + ach4 * P_ch4 / atm2bar) * (T0 / T)**2)
+    out = np.array(out, dtype=np.float64)
+    if units == 'dBperkm':
+        out = out * 434294.5
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # Clouds (clouds_idp.py:6-101)
 # --------------------------------------------------------------------------------------
 _FR = [1.0E8, 3.0E8, 1.0E9, 2.0E9, 3.0E9, 5.0E9, 1.0E10, 3.0E10, 1.0E11]
@@ -676,7 +779,7 @@ FORMALISMS = {
     'nh3_hs': nh3_hs, 'nh3_dbs': nh3_dbs, 'nh3_sjs': nh3_sjs, 'nh3_kd': nh3_kd, 'nh3_bg': nh3_bg, 'nh3_sjsd': nh3_sjsd,
     'nh3_hs_sjs': nh3_hs_sjs, 'nh3_dbs_sjs': nh3_dbs_sjs,
     'h2s_ddb': h2s_ddb, 'ph3_jh': ph3_jh, 'co_ddb': co_ddb, 'h2o_bk': h2o_bk,
-    'h2_jj_ddb': h2_jj_ddb, 'h2_jj': h2_jj, 'clouds_idp': clouds_idp,
+    'h2_jj_ddb': h2_jj_ddb, 'h2_jj': h2_jj, 'h2_orton': h2_orton, 'clouds_idp': clouds_idp,
 }
 
 

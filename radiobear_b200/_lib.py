@@ -16,10 +16,11 @@ RB_MAX_CONSTITUENTS = 8
 RB_NUM_GAS = 8
 RB_NUM_CLD = 6
 
-CATALOG_IDS = {'nh3_inv': 0, 'nh3_rot': 1, 'nh3_v2': 2, 'nh3_sjs': 3, 'h2s': 4, 'ph3': 5, 'co': 6, 'h2o': 7}
+CATALOG_IDS = {'nh3_inv': 0, 'nh3_rot': 1, 'nh3_v2': 2, 'nh3_sjs': 3, 'h2s': 4, 'ph3': 5, 'co': 6, 'h2o': 7,
+               'h2_orton': 8}
 FORMALISM_IDS = {'nh3_hs': 1, 'nh3_dbs': 2, 'nh3_sjs': 3, 'nh3_hs_sjs': 4, 'nh3_dbs_sjs': 5, 'h2s_ddb': 6,
                  'ph3_jh': 7, 'h2o_bk': 8, 'h2_jj_ddb': 9, 'h2_jj': 10, 'clouds_idp': 11, 'co_ddb': 12,
-                 'nh3_kd': 13, 'nh3_sjsd': 14, 'nh3_bg': 15}
+                 'nh3_kd': 13, 'nh3_sjsd': 14, 'nh3_bg': 15, 'h2_orton': 16}
 GAS_ORDER = ['H2', 'HE', 'CH4', 'NH3', 'H2O', 'H2S', 'PH3', 'CO']           # RB_GAS_*
 CLOUD_ORDER = ['H2O', 'SOLN', 'NH4SH', 'NH3', 'H2S', 'CH4']                 # RB_CLD_*
 CLOUD_FLAG_KEYS = ['ice_p', 'water_p', 'nh4sh_p', 'nh3ice_p', 'h2sice_p', 'ch4']   # clouds_idp.py:17-45

@@ -71,12 +71,99 @@ FORMALISM_CATALOGS = {
     'nh3_hs_sjs': ['nh3_inv', 'nh3_rot', 'nh3_v2', 'nh3_sjs'],
     'nh3_dbs_sjs': ['nh3_inv', 'nh3_rot', 'nh3_v2', 'nh3_sjs'],
     'h2s_ddb': ['h2s'], 'ph3_jh': ['ph3'], 'h2o_bk': ['h2o'], 'co_ddb': ['co'],
-    'h2_jj_ddb': [], 'h2_jj': [], 'clouds_idp': [],
+    'h2_jj_ddb': [], 'h2_jj': [], 'clouds_idp': [], 'h2_orton': ['h2_orton'],
 }
 
 
-def upload(ctx, formalism, truncate_strength=None, truncate_freq=None):
+# ---- Orton H2 CIA tables (h2_orton.py:17-123) ---------------------------------------------------
+ORTON_PATH = os.path.join(os.path.dirname(LINECAT_PATH), 'orton_h2.npz')
+ORTON_TABLES = {'eh2h2': 0, 'nh2h2': 1, 'eh2he': 2, 'nh2he': 3, 'eh2ch4': 4, 'nh2ch4': 5}     # h2_orton.py:12
+_orton_raw = None
+
+
+def _orton():
+    global _orton_raw
+    if _orton_raw is None:
+        d = np.load(ORTON_PATH)
+        nT, Tmax, Tmin = int(d['ntemp']), float(d['tmax']), float(d['tmin'])
+        # h2_orton.py:28-42: log-spaced temperatures, accumulated step by step like the reference
+        import math
+        dlT = (math.log(Tmax) - math.log(Tmin)) / (nT - 1.0)
+        ta = [math.log(Tmin)]
+        for i in range(nT - 1):
+            ta.append(ta[i] + dlT)
+        _orton_raw = (np.array([math.exp(v) for v in ta]), np.array([v * 29.9792458 for v in d['wavenumber']]),
+                      np.array(d['logtab']))
+    return _orton_raw
+
+
+def notaknot_spline(x, Y):
+    """Not-a-knot cubic spline through (x[n], Y[n][m]) -- what scipy's interp1d(kind='cubic') builds.
+    Returns c1, c2, c3 [n-1][m] of s(t) = Y[i] + c1 dt + c2 dt^2 + c3 dt^3 on [x[i], x[i+1]], dt = t - x[i]."""
+    x = np.asarray(x, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    n = len(x)
+    h = np.diff(x)
+    d = np.diff(Y, axis=0) / h[:, None]
+    A = np.zeros((n, n))
+    rhs = np.zeros((n, Y.shape[1]))
+    for i in range(1, n - 1):                       # continuity of s'' (unknowns: M = s'' at the knots)
+        A[i, i - 1], A[i, i], A[i, i + 1] = h[i - 1], 2.0 * (h[i - 1] + h[i]), h[i]
+        rhs[i] = 6.0 * (d[i] - d[i - 1])
+    A[0, 0], A[0, 1], A[0, 2] = h[1], -(h[0] + h[1]), h[0]                      # s''' continuous at x[1]
+    A[-1, -3], A[-1, -2], A[-1, -1] = h[-1], -(h[-2] + h[-1]), h[-2]            # ... and at x[n-2]
+    M = np.linalg.solve(A, rhs)
+    c1 = d - h[:, None] * (2.0 * M[:-1] + M[1:]) / 6.0
+    c2 = M[:-1] / 2.0
+    c3 = (M[1:] - M[:-1]) / (6.0 * h[:, None])
+    return c1, c2, c3
+
+
+def orton_table(freqs, h2state):
+    """RB_CAT_H2_ORTON for the frequencies of a call: [121][F] (layout in include/radiobear_b200.h).
+
+    Frequency: the quadratic through the three tabulated points around f, extrapolated below the first
+    one (h2_orton.py:77-108, `ifreq = first ftab > f`, 0 -> 1).  Temperature: spline coefficients for the kernel."""
+    Ttab, ftab, logtab = _orton()
+    freqs = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
+    st = {'e': 0, 'n': 1}[str(h2state).lower()]
+    if np.any(freqs >= ftab[-2]):
+        raise ValueError('h2_orton: frequency beyond the tabulated range ({:.0f} GHz)'.format(ftab[-2]))
+    ifreq = np.maximum(np.searchsorted(ftab, freqs, side='right'), 1)          # first ftab > f
+    nT, F = len(Ttab), len(freqs)
+    out = np.empty((nT + 3 * (nT + 3 * (nT - 1)), F))
+    out[:nT] = Ttab[:, None]
+    X1, X2, X3 = ftab[ifreq - 1], ftab[ifreq], ftab[ifreq + 1]
+    X21, X32 = X2 - X1, X3 - X2
+    X212, X322 = X2**2 - X1**2, X3**2 - X2**2
+    DQ = X212 * X32 - X322 * X21
+    for t, name in enumerate(('eh2h2', 'eh2he', 'eh2ch4')):
+        tab = logtab[ORTON_TABLES[name] + st]
+        E1, E2, E3 = np.exp(tab[ifreq - 1]), np.exp(tab[ifreq]), np.exp(tab[ifreq + 1])     # [F][nT]
+        Y1, Y21, Y32 = E1, E2 - E1, E3 - E2
+        AQ = (X32[:, None] * Y21 - X21[:, None] * Y32) / DQ[:, None]
+        BQ = (X212[:, None] * Y32 - X322[:, None] * Y21) / DQ[:, None]
+        CQ = Y1 - AQ * X1[:, None]**2 - BQ * X1[:, None]
+        v = (AQ * freqs[:, None]**2 + BQ * freqs[:, None] + CQ).T               # [nT][F]
+        c1, c2, c3 = notaknot_spline(Ttab, v)
+        base = nT + t * (nT + 3 * (nT - 1))
+        out[base:base + nT] = v
+        coef = np.stack([c1, c2, c3], axis=1).reshape(3 * (nT - 1), F)          # interval-major: k*3 + m
+        out[base + nT:base + nT + 3 * (nT - 1)] = coef
+    return out
+
+
+def upload(ctx, formalism, truncate_strength=None, truncate_freq=None, freqs=None, other=None):
     """Make sure the catalogs `formalism` needs are resident on the context's GPU."""
+    if formalism == 'h2_orton':
+        st = str((other or {}).get('h2state', 'e')).lower()
+        if st not in ('e', 'n'):
+            raise ValueError('INVALID H2STATE {!r}'.format(st))
+        f = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
+        key = (st, f.tobytes())
+        if ctx.catalog_key.get('h2_orton', '__unset__') != key:
+            ctx.set_catalog('h2_orton', orton_table(f, st), key=key)
+        return
     for name in FORMALISM_CATALOGS[formalism]:
         key = (truncate_strength, truncate_freq) if name in ('h2s', 'ph3', 'h2o') else ()
         if ctx.catalog_key.get(name, '__unset__') == key:

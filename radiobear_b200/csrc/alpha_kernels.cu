@@ -77,6 +77,52 @@ struct AlphaK {
       off_h2s_ag, off_h2s_n, off_ph3, off_h2o, off_co, off_red;
 };
 
+// ---- H2 CIA from Orton's tables (h2_orton.py:126-222) --------------------------------------------
+// tab: RB_CAT_H2_ORTON, [121][F]; fi: frequency index; xx = f^2; th312.. = (273/T)^3.12 / 2.24 / 3.34.
+// Three temperature branches like the reference: below the table a T^4 extrapolation through its first two
+// temperatures (:150-178), inside the not-a-knot cubic spline (:200-214), above h2_jj scaled to the table
+// at its last temperature (:179-199; the dB/km factors of both h2_jj calls cancel).
+__device__ __forceinline__ double h2_orton_alpha(const double* __restrict__ tab, int F, int fi, double T, double xx,
+                                                 double P_h2, double P_he, double P_ch4, double th312, double th224,
+                                                 double th334) {
+  constexpr int NT = 10, TSTRIDE = 37;
+  constexpr double T0 = 273.0, atm = 1.01325;
+  auto col = [&](int c) { return tab[(size_t)c * F + fi]; };
+  auto val = [&](int t, int j) { return col(NT + t * TSTRIDE + j); };
+  auto pair = [&](double ah2, double ahe, double ach4, double Tt) {
+    const double r = T0 / Tt;
+    return ((P_h2 / atm) * (ah2 * P_h2 / atm + ahe * P_he / atm + ach4 * P_ch4 / atm) * (r * r));
+  };
+  const double Tlo = col(0), Thi = col(NT - 1);
+  if (T < Tlo) {
+    const double T1 = col(1);
+    const double v0 = pair(val(0, 0), val(1, 0), val(2, 0), Tlo), v1 = pair(val(0, 1), val(1, 1), val(2, 1), T1);
+    const double X1 = Tlo * Tlo * Tlo * Tlo;
+    const double AQ = -1.0 * (v1 - v0) / (T1 * T1 * T1 * T1 - X1);
+    const double CQ = v0 + AQ * X1;
+    return CQ - AQ * (T * T * T * T);
+  }
+  if (T > Thi) {
+    const double anear = pair(val(0, NT - 1), val(1, NT - 1), val(2, NT - 1), Thi);
+    const double thn = T0 / Thi;
+    const double cf = 3.9522E-14 * xx * P_h2;   // h2_jj.py:13-18 at T and at Thi
+    const double jj = cf * (P_h2 * th312 + 1.382 * P_he * th224 + 9.322 * P_ch4 * th334);
+    const double jjnear = cf * (P_h2 * pow(thn, 3.12) + 1.382 * P_he * pow(thn, 2.24) + 9.322 * P_ch4 * pow(thn, 3.34));
+    return jj * (anear / jjnear);
+  }
+  int kk = 0;
+#pragma unroll
+  for (int i = 1; i < NT - 1; ++i) kk += (T >= col(i)) ? 1 : 0;   // interval [Ttab[kk], Ttab[kk+1]]
+  const double dt = T - col(kk);
+  double a[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int c = NT + t * TSTRIDE + NT + kk * 3;
+    a[t] = fma(dt, fma(dt, fma(dt, col(c + 2), col(c + 1)), col(c)), val(t, kk));
+  }
+  return pair(a[0], a[1], a[2], T);
+}
+
 // ---- line loops --------------------------------------------------------------------------------
 template <int FPT, int NEWTON>
 __device__ __forceinline__ void loop_br4(const double4* __restrict__ tab, int n, int k, int K, const double (&x)[FPT],
@@ -688,7 +734,10 @@ __global__ void __launch_bounds__(kThreads) alpha_lines_kernel(const __grid_cons
       if (k.units != RB_UNITS_DBPERKM) a = a / kDb;
       a_fam[k.slot_h2o] = a;
     }
-    if (k.slot_h2 >= 0) {  // h2_jj_ddb.py:7-38 / h2_jj.py:7-22
+    if (k.slot_h2 >= 0 && k.h2_form == RB_F_H2_ORTON) {
+      a_fam[k.slot_h2] = h2_orton_alpha(k.cat[RB_CAT_H2_ORTON], k.F, fidx[j], T, xx, P_h2, P_he, P_ch4,
+                                        s_pow[PW_H2_312], s_pow[PW_H2_224], s_pow[PW_H2_334]) * unit;
+    } else if (k.slot_h2 >= 0) {  // h2_jj_ddb.py:7-38 / h2_jj.py:7-22
       double pre = 1.0;
       if (k.h2_form == RB_F_H2_JJ_DDB) {
         if (k.h2state == 0) {
@@ -740,7 +789,7 @@ int family_of(int form) {
     case RB_F_H2S_DDB: return 1;
     case RB_F_PH3_JH: return 2;
     case RB_F_H2O_BK: return 3;
-    case RB_F_H2_JJ_DDB: case RB_F_H2_JJ: return 4;
+    case RB_F_H2_JJ_DDB: case RB_F_H2_JJ: case RB_F_H2_ORTON: return 4;
     case RB_F_CLOUDS_IDP: return 5;
     case RB_F_CO_DDB: return 6;
     default: return -1;
@@ -805,6 +854,12 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   if (k.slot_ph3 >= 0) RB_TRY(need_cat(RB_CAT_PH3, "ph3"));
   if (k.slot_h2o >= 0) RB_TRY(need_cat(RB_CAT_H2O, "h2o"));
   if (k.slot_co >= 0) RB_TRY(need_cat(RB_CAT_CO, "co"));
+  if (k.slot_h2 >= 0 && k.h2_form == RB_F_H2_ORTON) {
+    RB_TRY(need_cat(RB_CAT_H2_ORTON, "h2_orton"));
+    if (ctx->cat_n[RB_CAT_H2_ORTON] != k.F)
+      return rb_fail(ctx, RB_ERR_INVALID, "alpha: the h2_orton table was prepared for %d frequencies, the call has %d",
+                     ctx->cat_n[RB_CAT_H2_ORTON], k.F);
+  }
 
   // frequency classes
   for (int i = 0; i < k.F; ++i) {

@@ -180,7 +180,7 @@ int rb_set_rt_chunks(rb_context* ctx, int n) {
 
 int rb_set_catalog(rb_context* ctx, int catalog, int nlines, int ncols, const double* cols) {
   if (!ctx) return RB_ERR_INVALID;
-  static const int want_cols[RB_NUM_CATALOGS] = {4, 6, 3, 4, 4, 6, 3, 9};
+  static const int want_cols[RB_NUM_CATALOGS] = {4, 6, 3, 4, 4, 6, 3, 9, 121};
   if (catalog < 0 || catalog >= RB_NUM_CATALOGS) return rb_fail(ctx, RB_ERR_INVALID, "catalog id %d unknown", catalog);
   if (ncols != want_cols[catalog])
     return rb_fail(ctx, RB_ERR_INVALID, "catalog %d needs %d columns, got %d", catalog, want_cols[catalog], ncols);

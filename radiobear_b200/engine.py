@@ -50,7 +50,7 @@ def build_alpha_desc(formalisms, L, F, gas_rows, gas_dict, cloud_rows, cloud_dic
             raise NotImplementedError('formalism {} is not built in radiobear_b200'.format(name))
         d.formalism[i] = FORMALISM_IDS[name]
         od = other_dicts.get(c, {}) or {}
-        if name in ('h2_jj_ddb',):
+        if name in ('h2_jj_ddb', 'h2_orton'):
             st = od.get('h2state', 'e')
             if st not in ('e', 'n'):
                 raise ValueError('INVALID H2STATE {!r}'.format(st))      # h2_jj_ddb.py:28-30 prints and returns 0
@@ -99,13 +99,14 @@ def scale_matrix(scale, ordered, L):
     return None if s == 1.0 else np.full((C_, L), s)
 
 
-def prepare_catalogs(ctx, formalisms, truncate_strength=None, truncate_freq=None):
+def prepare_catalogs(ctx, formalisms, truncate_strength=None, truncate_freq=None, freqs=None, other_dicts=None):
     truncate_strength = truncate_strength or {}
     truncate_freq = truncate_freq or {}
     for c, name in formalisms:
         if name not in catalogs.FORMALISM_CATALOGS:
             raise NotImplementedError('formalism {} is not built in radiobear_b200'.format(name))
-        catalogs.upload(ctx, name, truncate_strength.get(c), truncate_freq.get(c))
+        catalogs.upload(ctx, name, truncate_strength.get(c), truncate_freq.get(c), freqs=freqs,
+                        other=(other_dicts or {}).get(c))
 
 
 def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formalisms=(), other_dicts=None,
@@ -128,7 +129,7 @@ def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formal
         if cloud.ndim == 1:
             cloud = np.ascontiguousarray(cloud[:, None])
     formalisms = list(formalisms)
-    prepare_catalogs(ctx, formalisms, truncate_strength, truncate_freq)
+    prepare_catalogs(ctx, formalisms, truncate_strength, truncate_freq, freqs=freqs, other_dicts=other_dicts)
     d = build_alpha_desc(formalisms, L, F, gas.shape[0], gas_dict, 0 if cloud is None else cloud.shape[0], cloud_dict,
                          other_dicts, units)
     sm = scale_matrix(scale, [c for c, _ in formalisms], L)
@@ -150,7 +151,9 @@ def alpha_layers_dev(freqs_t, T_t, P_t, gas_t, gas_dict, cloud_t=None, cloud_dic
     ctx = ctx or _lib.get_context()
     L, F = T_t.shape[0], freqs_t.shape[0]
     formalisms = list(formalisms)
-    prepare_catalogs(ctx, formalisms, truncate_strength, truncate_freq)
+    if any(name == 'h2_orton' for _, name in formalisms) and freqs_host is None:
+        freqs_host = freqs_t.cpu().numpy()          # the Orton table is prepared on the host per frequency vector
+    prepare_catalogs(ctx, formalisms, truncate_strength, truncate_freq, freqs=freqs_host, other_dicts=other_dicts)
     d = build_alpha_desc(formalisms, L, F, gas_t.shape[0], gas_dict, 0 if cloud_t is None else cloud_t.shape[0],
                          cloud_dict, other_dicts, units)
     for t in (freqs_t, T_t, P_t, gas_t):

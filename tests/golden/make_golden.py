@@ -212,6 +212,38 @@ def sec_plugins_nh3_extra():
     save('plugins_nh3_extra.npz', **out)
 
 
+def sec_plugins_h2_orton():
+    """h2_orton.alpha called directly (the reference's Alpha cannot: h2_orton.py:120 rejects the truncate_* kwargs
+    alpha.py:210-213 passes).  Points cover the three temperature branches (below 40 K: quartic extrapolation,
+    40..400 K: cubic spline through the 10 tabulated temperatures, above: scaled h2_jj) for both h2 states;
+    the first frequency lies below the lowest tabulated wavenumber (extrapolated, h2_orton.py:84-85)."""
+    import importlib
+    pts, C, Cl, atm = _points()
+    extra = []
+    base = atm.gas[:, 500].copy()
+    for T, P in [(20.0, 0.01), (35.0, 0.02), (39.999, 0.03), (40.5, 0.05), (61.0, 0.1), (100.0, 0.3), (178.0, 1.0),
+                 (251.0, 3.0), (399.0, 9.0), (401.0, 9.5), (650.0, 60.0)]:
+        g = base.copy()
+        g[C['T']], g[C['P']] = T, P
+        g[C['CH4']] = 1.9e-3
+        extra.append(g)
+    pts = np.concatenate([pts, np.array(extra)])
+    cpath = os.path.join(REF, 'radiobear', 'constituents')
+    sys.path.append(os.path.join(cpath, 'h2'))
+    mod = importlib.import_module('h2_orton')
+    freqs = [0.5] + PLUGIN_FREQS
+    out = {'points': pts, 'freqs': np.array(freqs), 'C_keys': np.array(sorted(C, key=lambda k: C[k]))}
+    for state in ['e', 'n']:
+        for units in ['invcm', 'dBperkm']:
+            res = []
+            for i, g in enumerate(pts):
+                r = mod.alpha(freqs, g[C['T']], g[C['P']], g, C, {'h2state': state, 'h2newset': i == 0}, units=units,
+                              path=os.path.join(cpath, 'h2'), verbose=False)
+                res.append(np.asarray(r, dtype=float))
+            out['h2_orton_{}__{}'.format(state, units)] = np.array(res)
+    save('plugins_h2_orton.npz', **out)
+
+
 def sec_plugins_notrunc():
     """No-truncation variant: the reference caches catalogs per process (h2s_ddb.py:11, ph3_jh.py:14),
     so this runs in a fresh interpreter."""
@@ -383,7 +415,7 @@ def sec_fileio():
     save('fileio.npz', **out)
 
 
-SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
+SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins_h2_orton': sec_plugins_h2_orton, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
             'rays': sec_rays, 'tb': sec_tb, 'neptune': sec_neptune, 'image': sec_image}
 
 if __name__ == '__main__':

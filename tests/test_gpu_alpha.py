@@ -87,7 +87,7 @@ def test_option_variants_and_clouds(eng):
         eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('h2', 'h2_jj_ddb')],
                          other_dicts={'h2': {'h2state': 'x'}})
     with pytest.raises(NotImplementedError):
-        eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('h2', 'h2_orton')])
+        eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('h2o', 'h2o_ddb')])
 
 
 def test_no_truncation(eng):
@@ -207,3 +207,30 @@ def test_remaining_nh3_formalisms(eng, name, units):
     p = g['points'][-4]
     a = mod.alpha(list(g['freqs']), p[C['T']], p[C['P']], p, C, {}, units=units)
     assert np.nanmax(relerr(a, ref[-4])) < TIGHT
+
+
+@pytest.mark.parametrize('state', ['e', 'n'])
+@pytest.mark.parametrize('units', ['invcm', 'dBperkm'])
+def test_h2_orton(eng, state, units):
+    """h2_orton behind the common plugin signature (the reference module cannot be driven by
+    Alpha); T^4 extrapolation below 40 K, cubic spline inside the table, scaled h2_jj above 400 K."""
+    import importlib
+    g = golden('plugins_h2_orton.npz')
+    C = keymap(g['C_keys'])
+    gas = np.ascontiguousarray(g['points'].T)
+    out = eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('h2', 'h2_orton')], units=units,
+                           other_dicts={'h2': {'h2state': state}})
+    ref = g['h2_orton_{}__{}'.format(state, units)]
+    assert np.max(relerr(out, ref)) < TIGHT
+    mod = importlib.import_module('radiobear_b200.constituents.h2.h2_orton')
+    for i in (0, 20, 26, 30, 36):
+        p = g['points'][i]
+        a = mod.alpha(list(g['freqs']), p[C['T']], p[C['P']], p, C, {'h2state': state, 'h2newset': True}, units=units)
+        assert np.max(relerr(a, ref[i])) < TIGHT
+    # a different frequency vector re-prepares the table; a wrong state is refused
+    out2 = eng.alpha_layers(g['freqs'][3:9], gas[C['T']], gas[C['P']], gas, C, formalisms=[('h2', 'h2_orton')], units=units,
+                            other_dicts={'h2': {'h2state': state}})
+    assert np.max(relerr(out2, ref[:, 3:9])) < TIGHT
+    with pytest.raises(ValueError):
+        eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('h2', 'h2_orton')],
+                         other_dicts={'h2': {'h2state': 'x'}})

@@ -185,3 +185,38 @@ def test_remaining_nh3_formalisms(name):
             a = ao.FORMALISMS[name](g['freqs'], p[C['T']], p[C['P']], p, C, {}, units=units)
             assert np.array_equal(np.isnan(a), np.isnan(r))
             assert np.nanmax(relerr(a, r)) < 1e-12
+
+
+@pytest.mark.parametrize('state', ['e', 'n'])
+def test_h2_orton_oracle(state):
+    """Orton's H2 CIA tables; 37 points over the three temperature branches."""
+    g = golden('plugins_h2_orton.npz')
+    C = keymap(g['C_keys'])
+    for units in ['invcm', 'dBperkm']:
+        for p, r in zip(g['points'], g['h2_orton_{}__{}'.format(state, units)]):
+            a = ao.h2_orton(g['freqs'], p[C['T']], p[C['P']], p, C, {'h2state': state}, units=units)
+            assert np.max(relerr(a, r)) < 1e-13
+
+
+def test_h2_orton_host_table():
+    """The product's host-side table preparation (frequency quadratic + not-a-knot spline coefficients)
+    against the oracle's restatement of readInputFiles and scipy's interp1d(kind='cubic')."""
+    from scipy.interpolate import interp1d
+    from radiobear_b200 import catalogs
+    f = np.array([0.5, 0.6, 1.0, 22.0, 100.0, 500.0, 1000.0])
+    Ttab, h2vab = ao.orton_tables(list(f))
+    for st, tabs in (('e', (0, 2, 4)), ('n', (1, 3, 5))):
+        tab = catalogs.orton_table(f, st)
+        assert tab.shape == (121, len(f)) and np.array_equal(tab[:10, 0], Ttab)
+        for t, ii in enumerate(tabs):
+            base = 10 + 37 * t
+            assert np.max(relerr(tab[base:base + 10].T, h2vab[ii])) < 1e-14
+            for T in (40.0, 41.0, 77.7, 150.0, 250.0, 399.9):
+                k = int(np.clip(np.searchsorted(Ttab, T, side='right') - 1, 0, 8))
+                dt = T - Ttab[k]
+                c = tab[base + 10 + 3 * k:base + 13 + 3 * k]
+                got = tab[base + k] + dt * (c[0] + dt * (c[1] + dt * c[2]))
+                ref = np.array([interp1d(Ttab, h2vab[ii, j], kind='cubic')(T) for j in range(len(f))])
+                assert np.max(relerr(got, ref)) < 1e-12
+    with pytest.raises(ValueError):
+        catalogs.orton_table([80000.0], 'e')
