@@ -5,6 +5,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <cstdint>
+#include <chrono>
+#include <cstdio>
+#include <cuda.h>
 
 int rb_fail(rb_context* ctx, int code, const char* fmt, ...) {
   char buf[512];
@@ -426,6 +430,32 @@ static int check_rt(rb_context* ctx, const rb_rt_desc* rt, const void* out_Tb) {
 // ctx->stream with events, so callers still see one in-order stream.  (Overlapping geometry(c+1) with
 // integrate(c) was measured and is slower: the latency-bound geometry kernel starves when it shares SMs.)
 // All pointers are DEVICE pointers except h_out / h_intW.
+// RB_TRACE=1: host-clock trace of the stages of rb_rt_batch (stderr), for tools/e2e_breakdown.py
+static double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+static bool tracing() { static int t = -1; if (t < 0) t = getenv("RB_TRACE") ? 1 : 0; return t == 1; }
+#define RB_TRACE_AT(label) do { if (tracing()) fprintf(stderr, "[rb_trace] %-28s %.3f ms\n", label, now_ms() - trace_t0); } while (0)
+
+// cuStreamWaitValue32 through the runtime's driver entry point lookup (the library links no libcuda)
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWaitValue32Fn stream_wait_value() {
+  static StreamWaitValue32Fn fn = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (StreamWaitValue32Fn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
 static int pipe_setup(rb_context* ctx, int nch) {
   for (int i = 1; i < 3; ++i)   // aux[0] is the (high-priority) geometry prefetch stream
     if (!ctx->aux[i]) RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
@@ -459,7 +489,7 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_de
   if (!have_geometry) RB_TRY(rb_launch_geometry(ctx, full));
   const int nch = choose_chunks(ctx, R, prep.use_rays, h_out != nullptr);
   if (nch == 1) {
-    RB_TRY(rb_launch_integrate(ctx, full, rd, prep, d_out, d_intW, -1, nullptr, nullptr, nullptr));
+    RB_TRY(rb_launch_integrate(ctx, full, rd, prep, nullptr, d_out, d_intW, -1, nullptr, nullptr, nullptr));
     if (h_out) RB_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, (size_t)R * F * esz, cudaMemcpyDeviceToHost, ctx->stream));
     if (h_intW) RB_CUDA(ctx, cudaMemcpyAsync(h_intW, d_intW, (size_t)R * F * 8, cudaMemcpyDeviceToHost, ctx->stream));
     return RB_OK;
@@ -467,17 +497,67 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_de
   RB_TRY(pipe_setup(ctx, nch));
   cudaStream_t user = ctx->stream, sI = ctx->aux[1], sC = ctx->aux[2];
   cudaEvent_t* ev = ctx->pipe_ev.data();
+  const int64_t ntiles = (R + 31) / 32;
+  auto cut_at = [&](int j) {
+    // shrinking chunks: the copy of the last chunk is the only one nothing overlaps, so keep it small
+    return (j >= nch) ? ntiles : (int64_t)llround((double)ntiles * (1.0 - pow(1.0 - (double)j / nch, 1.6)));
+  };
+  if (stream_wait_value() && nch <= kMaxProgressChunks && !getenv("RB_RT_SPLIT_LAUNCHES")) {
+    // One integration launch; its CTAs count themselves into per-chunk counters when their results are in
+    // global memory, and the copy stream waits on each counter (stream memory operation) before moving
+    // that chunk to the host: the copies overlap the same launch, no launch tails between chunks.
+    void* p_flags;
+    RB_TRY(rb_ensure(ctx, RB_BUF_FLAGS, kMaxProgressChunks * sizeof(unsigned), &p_flags));
+    RtProgress pg;
+    pg.nchunks = nch;
+    pg.done = (unsigned*)p_flags;
+    // CTAs run in launch order; a disc image ends with rows that miss the planet (no work), which would all
+    // complete -- and queue for copy-out -- at the very end of the launch.  Start in the middle of the ray
+    // list instead (the centre row of an image) and wrap around: the cheap tiles are done early and the
+    // chunks complete evenly in time.
+    pg.shift = (int)(ntiles / 2);
+    for (int c = 0; c <= nch; ++c) pg.cut[c] = (int)cut_at(c);
+    RB_CUDA(ctx, cudaMemsetAsync(p_flags, 0, kMaxProgressChunks * sizeof(unsigned), user));
+    RB_CUDA(ctx, cudaEventRecord(ev[0], user));             // counters are zero; the copy stream may start waiting
+    RB_CUDA(ctx, cudaStreamWaitEvent(sC, ev[0], 0));
+    RB_TRY(rb_launch_integrate(ctx, full, rd, prep, &pg, d_out, d_intW, -1, nullptr, nullptr, nullptr));
+    const unsigned fgroups = (unsigned)((F + 7) / 8);
+    auto copy_tiles = [&](int64_t t0, int64_t t1) -> int {   // memory-order tiles [t0, t1)
+      const int64_t r0 = t0 * 32, r1 = (t1 * 32 < R) ? t1 * 32 : R;
+      if (r1 <= r0) return RB_OK;
+      RB_CUDA(ctx, cudaMemcpyAsync((char*)h_out + (size_t)r0 * F * esz, (char*)d_out + (size_t)r0 * F * esz,
+                                   (size_t)(r1 - r0) * F * esz, cudaMemcpyDeviceToHost, sC));
+      if (h_intW)
+        RB_CUDA(ctx, cudaMemcpyAsync(h_intW + (size_t)r0 * F, d_intW + (size_t)r0 * F, (size_t)(r1 - r0) * F * 8,
+                                     cudaMemcpyDeviceToHost, sC));
+      return RB_OK;
+    };
+    for (int c = 0; c < nch; ++c) {
+      const int64_t p0 = pg.cut[c], p1 = pg.cut[c + 1];      // processing-order tiles of the chunk
+      if (p1 <= p0) continue;
+      if (stream_wait_value()((CUstream)sC, (CUdeviceptr)(uintptr_t)(pg.done + c), (unsigned)(p1 - p0) * fgroups,
+                              CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+        return rb_fail(ctx, RB_ERR_CUDA, "rt: cuStreamWaitValue32 failed");
+      const int64_t m0 = (p0 + pg.shift) % ntiles, len = p1 - p0;
+      if (m0 + len <= ntiles) {
+        RB_TRY(copy_tiles(m0, m0 + len));
+      } else {
+        RB_TRY(copy_tiles(m0, ntiles));
+        RB_TRY(copy_tiles(0, m0 + len - ntiles));
+      }
+    }
+    RB_CUDA(ctx, cudaEventRecord(ev[3], sC));
+    RB_CUDA(ctx, cudaStreamWaitEvent(user, ev[3], 0));
+    return RB_OK;
+  }
   RB_CUDA(ctx, cudaEventRecord(ev[0], user));               // inputs, operands and geometry are ready
   RB_CUDA(ctx, cudaStreamWaitEvent(sI, ev[0], 0));
   RB_CUDA(ctx, cudaStreamWaitEvent(sC, ev[0], 0));
-  // chunk boundaries are cut by tiles of 32 rays
-  const int64_t tiles = (R + 31) / 32;
+  // fallback: one integration launch per chunk (chunk boundaries are cut by tiles of 32 rays)
   int status = RB_OK;
   ctx->stream = sI;
   for (int c = 0; c < nch && status == RB_OK; ++c) {
-    // shrinking chunks: the copy of the last chunk is the only one nothing overlaps, so keep it small
-    auto cut = [&](int j) { return (int64_t)llround((double)tiles * (1.0 - pow(1.0 - (double)j / nch, 1.6))); };
-    const int64_t t0 = cut(c), t1 = (c + 1 == nch) ? tiles : cut(c + 1);
+    const int64_t t0 = cut_at(c), t1 = cut_at(c + 1);
     const int64_t r0 = t0 * 32, r1 = (t1 * 32 < R) ? t1 * 32 : R;
     if (r1 <= r0) continue;
     RtLaunch Lc = full;
@@ -489,7 +569,7 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_de
     Lc.nanflag = full.nanflag + r0;
     char* oc = (char*)d_out + (size_t)r0 * F * esz;
     double* wc = d_intW ? d_intW + (size_t)r0 * F : nullptr;
-    status = rb_launch_integrate(ctx, Lc, rd, prep, oc, wc, -1, nullptr, nullptr, nullptr);
+    status = rb_launch_integrate(ctx, Lc, rd, prep, nullptr, oc, wc, -1, nullptr, nullptr, nullptr);
     if (status != RB_OK) break;
     cudaEventRecord(ev[4 + c], sI);
     cudaStreamWaitEvent(sC, ev[4 + c], 0);
@@ -544,6 +624,7 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   RB_TRY(rb_ensure(ctx, RB_BUF_TB, (size_t)R * F * esz, &p_tb));
   if (out_intW) RB_TRY(rb_ensure(ctx, RB_BUF_INTW, (size_t)R * F * 8, &p_iw));
   cudaStream_t s = ctx->stream;
+  const double trace_t0 = now_ms();
   const bool have_geometry = take_ticket(ctx, g, R, b);      // radius and b were staged by the prefetch
   if (!have_geometry) {
     RB_CUDA(ctx, cudaMemcpyAsync(p_rad, g->radius, nL * 8, cudaMemcpyHostToDevice, s));
@@ -551,10 +632,12 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   }
   RB_CUDA(ctx, cudaMemcpyAsync(p_alpha, rt->alpha, nL * F * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_T, rt->T, nL * 8, cudaMemcpyHostToDevice, s));
+  RB_TRACE_AT("inputs enqueued");
   L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
   rb_rt_desc rd = *rt;
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
   RB_TRY(run_rt_pipeline(ctx, L, &rd, p_tb, (double*)p_iw, out_Tb, out_intW, have_geometry));
+  RB_TRACE_AT("pipeline enqueued");
   if (profile_ray >= 0) {
     // re-run the selected ray alone with the profile-writing variant (Brightness.tau/.W/.Tb_lyr)
     RB_TRY(rb_ensure(ctx, RB_BUF_PROFILE, 3 * F * S * 8 + F * 8, &p_prof));
@@ -567,12 +650,13 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
     rd.out_f32 = 0;
     RtPrep prof_prep;
     RB_TRY(rb_rt_prepare(ctx, L.L, &rd, 1, true, &prof_prep));
-    RB_TRY(rb_launch_integrate(ctx, L1, &rd, prof_prep, pp + 3 * F * S, nullptr, 0, pp, pp + F * S, pp + 2 * F * S));
+    RB_TRY(rb_launch_integrate(ctx, L1, &rd, prof_prep, nullptr, pp + 3 * F * S, nullptr, 0, pp, pp + F * S, pp + 2 * F * S));
     RB_CUDA(ctx, cudaMemcpyAsync(out_tau, pp, F * S * 8, cudaMemcpyDeviceToHost, s));
     RB_CUDA(ctx, cudaMemcpyAsync(out_W, pp + F * S, F * S * 8, cudaMemcpyDeviceToHost, s));
     RB_CUDA(ctx, cudaMemcpyAsync(out_Tblyr, pp + 2 * F * S, F * S * 8, cudaMemcpyDeviceToHost, s));
   }
   RB_CUDA(ctx, cudaStreamSynchronize(s));
+  RB_TRACE_AT("synchronised");
   return RB_OK;
 }
 
@@ -607,7 +691,7 @@ int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
   RtPrep prep;
   RB_TRY(rb_rt_prepare(ctx, L.L, &rd, R, false, &prep));
-  RB_TRY(rb_launch_integrate(ctx, L, &rd, prep, p_tb, (double*)p_iw, -1, nullptr, nullptr, nullptr));
+  RB_TRY(rb_launch_integrate(ctx, L, &rd, prep, nullptr, p_tb, (double*)p_iw, -1, nullptr, nullptr, nullptr));
   RB_CUDA(ctx, cudaMemcpyAsync(out_Tb, p_tb, (size_t)R * F * esz, cudaMemcpyDeviceToHost, s));
   if (out_intW) RB_CUDA(ctx, cudaMemcpyAsync(out_intW, p_iw, (size_t)R * F * 8, cudaMemcpyDeviceToHost, s));
   RB_CUDA(ctx, cudaStreamSynchronize(s));

@@ -66,7 +66,8 @@ inline cudaError_t rb_time_end(rb_context* ctx, int which) {
 
 enum {
   RB_BUF_FREQS = 0, RB_BUF_T, RB_BUF_P, RB_BUF_GAS, RB_BUF_CLOUD, RB_BUF_SCALE, RB_BUF_TOTAL, RB_BUF_CUBE,
-  RB_BUF_RADIUS, RB_BUF_B, RB_BUF_DS, RB_BUF_NSEG, RB_BUF_TB, RB_BUF_INTW, RB_BUF_PROFILE, RB_BUF_MISC, RB_BUF_PREP
+  RB_BUF_RADIUS, RB_BUF_B, RB_BUF_DS, RB_BUF_NSEG, RB_BUF_TB, RB_BUF_INTW, RB_BUF_PROFILE, RB_BUF_MISC, RB_BUF_PREP,
+  RB_BUF_FLAGS
 };
 
 // The rays-major integration kernel prefetches whole 32-segment chunks of the ds slab and of the operand
@@ -117,6 +118,17 @@ int rb_launch_geometry(rb_context* ctx, const RtLaunch& g);
 int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out_ds_raymajor /*[R][L-1] device*/);
 int rb_launch_ds_to_slab(rb_context* ctx, const double* ds_raymajor, int64_t R, int64_t Rpad, int S, const int* nseg,
                          int* nanflag, double* slab);
+// Progress reporting of one integration launch: ray tiles [cut[c], cut[c+1]) form chunk c; every CTA adds 1 to
+// done[c] of its chunk when its results are in global memory, so that a copy stream can wait (stream memory
+// operation) until a chunk is complete and move it to the host while the same launch keeps integrating.
+constexpr int kMaxProgressChunks = 16;
+struct RtProgress {
+  int nchunks = 0;
+  int shift = 0;              // CTA y processes ray tile (y + shift) mod #tiles (see run_rt_pipeline)
+  int cut[kMaxProgressChunks + 1] = {0};   // in processing order
+  unsigned* done = nullptr;   // device, nchunks counters, zeroed before the launch
+};
+
 struct RtPrep {
   bool use_rays = false;       // rays-major kernel (R >= 512, point rays) or the lanes = frequency kernel
   const void* prep = nullptr;  // operand slab of the rays-major kernel
@@ -124,6 +136,7 @@ struct RtPrep {
 int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt /*device pointers*/, int64_t R_total, bool profile,
                   RtPrep* out);
 int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt /*device pointers*/, const RtPrep& prep,
+                        const RtProgress* progress,
                         void* out_Tb, double* out_intW, int64_t profile_ray, double* out_tau, double* out_W,
                         double* out_Tblyr);
 

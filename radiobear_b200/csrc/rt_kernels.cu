@@ -358,6 +358,7 @@ struct RtK {
   const double4* prep;  // [F/8][L-1][8] interleaved loop operands (rays-major kernel only, see rt_prepare_kernel)
   unsigned long long* step_counter;  // optional: number of (ray, freq, segment) steps actually integrated
   const double* exp_tab;  // 2^(j/1024) (rays-major kernel only)
+  RtProgress progress;    // optional per-chunk completion counters (rays-major kernel only)
   const double* ds;     // [S][Rpad]
   const int* nseg;      // [R]
   const int* nanflag;   // [R]
@@ -583,7 +584,10 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   const int tid = threadIdx.y * 32 + threadIdx.x;
 
   const int S = k.L - 1;
-  const long long r = (long long)blockIdx.y * 32 + threadIdx.x;
+  // ray tile of this CTA: launch order rotated by progress.shift (0 unless the host pipelines the copy-out)
+  unsigned tile = blockIdx.y + (unsigned)k.progress.shift;
+  if (tile >= gridDim.y) tile -= gridDim.y;
+  const long long r = (long long)tile * 32 + threadIdx.x;
   const int f = blockIdx.x * 8 + threadIdx.y;
   const bool valid = (r < k.R) && (f < k.F);
   const int n = valid ? k.nseg[r] : -1;
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   // one contiguous piece of global memory (8448 B / 8192 B), cut into 16-byte cp.async pieces: two per
   // thread for each stream plus a third ds piece for the first 16 threads.  No bounds checks: rows past the
   // end of a tile are never consumed and both slabs are allocated with kRtSlackBytes of slack.
-  const char* src_ds = reinterpret_cast<const char*>(k.ds + (size_t)blockIdx.y * S * 32) + tid * 16;
+  const char* src_ds = reinterpret_cast<const char*>(k.ds + (size_t)tile * S * 32) + tid * 16;
   const char* src_pp = reinterpret_cast<const char*>(k.prep + (size_t)blockIdx.x * S * 8) + tid * 16;
   const unsigned dst_ds = (unsigned)__cvta_generic_to_shared(s_ds) + tid * 16;
   const unsigned dst_pp = (unsigned)__cvta_generic_to_shared(s_pp) + tid * 16;
@@ -751,15 +755,27 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
     for (int o = 16; o > 0; o >>= 1) done += __shfl_down_sync(0xffffffffu, done, o);
     if (threadIdx.x == 0) atomicAdd(k.step_counter, done);
   }
-  if (!valid) return;
-  double vout, wout = iW;
-  if (n < 0) vout = kTcmb;                                 // off planet (brightness.py:46-51)
-  else if (nanray || tau != tau) vout = wout = nan("");    // NaN segment below the tangent shell / NaN alpha
-  else vout = (Tb < kTcmb) ? kTcmb : Tb / iW;              // brightness.py:109-113
-  const size_t o = (size_t)r * k.F + f;
-  if (k.out_f32) reinterpret_cast<float*>(k.out_Tb)[o] = (float)vout;
-  else reinterpret_cast<double*>(k.out_Tb)[o] = vout;
-  if (k.out_intW) k.out_intW[o] = (n < 0) ? 0.0 : wout;
+  if (valid) {
+    double vout, wout = iW;
+    if (n < 0) vout = kTcmb;                                 // off planet (brightness.py:46-51)
+    else if (nanray || tau != tau) vout = wout = nan("");    // NaN segment below the tangent shell / NaN alpha
+    else vout = (Tb < kTcmb) ? kTcmb : Tb / iW;              // brightness.py:109-113
+    const size_t o = (size_t)r * k.F + f;
+    if (k.out_f32) reinterpret_cast<float*>(k.out_Tb)[o] = (float)vout;
+    else reinterpret_cast<double*>(k.out_Tb)[o] = vout;
+    if (k.out_intW) k.out_intW[o] = (n < 0) ? 0.0 : wout;
+  }
+  if (k.progress.done) {
+    // this CTA's results are in global memory: count it in its chunk (the host's copy stream waits on the
+    // counter with a stream memory operation and then copies the chunk device -> host)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      int c = 0;
+      while (c + 1 < k.progress.nchunks && (int)blockIdx.y >= k.progress.cut[c + 1]) ++c;
+      atomicAdd(k.progress.done + c, 1u);
+    }
+  }
 }
 
 }  // namespace
@@ -821,7 +837,8 @@ int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total,
   return RB_OK;
 }
 
-int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt, const RtPrep& prep, void* out_Tb,
+int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt, const RtPrep& prep,
+                        const RtProgress* progress, void* out_Tb,
                         double* out_intW, int64_t profile_ray, double* out_tau, double* out_W, double* out_Tblyr) {
   RtK k{};
   k.L = g.L; k.F = rt->n_freqs; k.R = g.R; k.Rpad = g.Rpad;
@@ -846,6 +863,7 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     k.prep = (const double4*)prep.prep;
     k.step_counter = ctx->step_counter;
     k.exp_tab = ctx->exp_tab;
+    if (progress) k.progress = *progress;
     dim3 block(32, 8), grid((k.F + 7) / 8, (unsigned)((g.R + 31) / 32));
     if (grid.y > 65535) return rb_fail(ctx, RB_ERR_INVALID, "rt: more than 2M rays per launch are not supported");
     constexpr size_t smem = kExpTab * sizeof(double) + kRaysSmemBytes;
