@@ -481,6 +481,29 @@ __device__ double c_expc[8] = {
     0.5 + kExpH * kExpH / 24.0, 1.0, 1.0 - kExpH * kExpH * kExpH * kExpH / 192.0,
 #endif
     0.0};
+// Small optical depths (about half of all executed segment-steps: tau grows exponentially with depth) need no
+// range reduction: on 0 <= tau <= H = 2^-11 the economised quadratic
+//   exp(-tau) ~ E [1 - (1 + m^2/8)(tau - m) + (tau - m)^2 / 2],  m = H/2, E = exp(-m)
+// is within m^3/24 = 6e-13 (relative; the table path holds 1.6e-12) -- two FMAs instead of the table path's
+// six FP64 instructions, one shared-memory read and four integer instructions.  Measured on C4: H = 2^-15
+// 4.22 ms, 2^-13 4.11 ms, 2^-11 3.95 ms against 4.50 ms without the path (RB_EXP_SMALL_LOG = 0).
+#ifndef RB_EXP_SMALL_LOG
+#define RB_EXP_SMALL_LOG 11
+#endif
+constexpr double kSmallH = (RB_EXP_SMALL_LOG > 0) ? 1.0 / (double)(1 << (RB_EXP_SMALL_LOG > 0 ? RB_EXP_SMALL_LOG : 1)) : 0.0;
+constexpr double kSmallM = 0.5 * kSmallH;
+constexpr double exp_neg_small(double m) {   // exp(-m) for m << 1 (compile time)
+  double term = 1.0, sum = 1.0;
+  for (int i = 1; i < 12; ++i) { term *= -m / i; sum += term; }
+  return sum;
+}
+constexpr double kSmallE = exp_neg_small(kSmallM);
+constexpr double kSmallK1 = 1.0 + kSmallM * kSmallM / 8.0;
+__device__ double c_small[4] = {
+    kSmallE * (1.0 + kSmallK1 * kSmallM + 0.5 * kSmallM * kSmallM),   // a0
+    -kSmallE * (kSmallK1 + kSmallM),                                  // a1
+    0.5 * kSmallE,                                                    // a2
+    0.0};
 #if RB_EXP_DEG == 2
 #define RB_EXP_POLY(x) fma(fma((x), c2, ce), (x), c1)
 #else
@@ -686,6 +709,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   }
 
   bool stop = false;
+  bool small = true;                                       // this ray is still in the small-tau phase A
   for (int c = 0; any_live; ++c) {
     cp_async_wait<0>();                                    // this thread's pieces of chunk c have landed
     if (!__syncthreads_or(live)) break;                    // ... everybody's have; chunk c-1 is fully consumed
@@ -699,28 +723,57 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
       if (zrow <= kChunk) dsb[zrow * 32] = 0.0;
       const int m = min(kChunk, steps - i);
       int u = 0;
-      // groups of 4 segments: the four optical depths first (one dependent FMA each), one threshold test
-      // on the deepest, then four independent exp / accumulate chains
       const double* dp = dsb;
       const double4* qp = ppb;
+      // Phase A (per ray, while tau < 2^-13; tau only grows): groups of kGroup segments with the short
+      // polynomial -- no range reduction, no table, no tau_cut test.  The group that crosses the bound is
+      // left to phase B.  The three coefficients are re-read per chunk so that they are not live in phase B.
+      if (RB_EXP_SMALL_LOG > 0 && small) {
+        const double sa0 = pin(c_small + 0), sa1 = pin(c_small + 1 + vz), sa2 = pin(c_small + 2);
+        constexpr int small_hi = (int)(((0x3FFull - RB_EXP_SMALL_LOG) << 20));   // high word of 2^-RB_EXP_SMALL_LOG
 #pragma unroll 1
-      for (; u + kGroup <= m; u += kGroup, dp += kGroup * 32, qp += kGroup * 8) {
-        double d[kGroup + 1], t[kGroup], w[kGroup];
-        double4 q[kGroup];
+        for (; u + kGroup <= m; u += kGroup, dp += kGroup * 32, qp += kGroup * 8) {
+          double d[kGroup + 1], t[kGroup];
+          double4 q[kGroup];
 #pragma unroll
-        for (int j = 0; j <= kGroup; ++j) d[j] = dp[j * 32];
+          for (int j = 0; j <= kGroup; ++j) d[j] = dp[j * 32];
 #pragma unroll
-        for (int j = 0; j < kGroup; ++j) q[j] = qp[j * 8];
-        t[0] = fma(q[0].x, d[0], tau);
+          for (int j = 0; j < kGroup; ++j) q[j] = qp[j * 8];
+          t[0] = fma(q[0].x, d[0], tau);
 #pragma unroll
-        for (int j = 1; j < kGroup; ++j) t[j] = fma(q[j].x, d[j], t[j - 1]);
-        const double ndl = fma(t[kGroup - 1], cA, cM) - cM;
-        if ((unsigned)__double2hiint(ndl) > thr_hi) break;   // tau_cut is crossed inside this group: go step by step
+          for (int j = 1; j < kGroup; ++j) t[j] = fma(q[j].x, d[j], t[j - 1]);
+          if (__double2hiint(t[kGroup - 1]) >= small_hi) { small = false; break; }
 #pragma unroll
-        for (int j = 0; j < kGroup; ++j) RB_RT_WEIGHT(t[j], d[j] + d[j + 1], w[j]);
+          for (int j = 0; j < kGroup; ++j) {
+            const double w = fma(fma(t[j], sa2, sa1), t[j], sa0) * (d[j] + d[j + 1]);
+            iW = fma(q[j].y, w, iW);
+            Tb = fma(q[j].z, w, Tb);
+          }
+          tau = t[kGroup - 1];
+        }
+      }
+      // Phase B: groups of kGroup segments: the optical depths first (one dependent FMA each), one threshold
+      // test on the deepest, then kGroup independent exp / accumulate chains through the table
+      if (!(RB_EXP_SMALL_LOG > 0) || !small) {
+#pragma unroll 1
+        for (; u + kGroup <= m; u += kGroup, dp += kGroup * 32, qp += kGroup * 8) {
+          double d[kGroup + 1], t[kGroup], w[kGroup];
+          double4 q[kGroup];
 #pragma unroll
-        for (int j = 0; j < kGroup; ++j) { iW = fma(q[j].y, w[j], iW); Tb = fma(q[j].z, w[j], Tb); }
-        tau = t[kGroup - 1];
+          for (int j = 0; j <= kGroup; ++j) d[j] = dp[j * 32];
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) q[j] = qp[j * 8];
+          t[0] = fma(q[0].x, d[0], tau);
+#pragma unroll
+          for (int j = 1; j < kGroup; ++j) t[j] = fma(q[j].x, d[j], t[j - 1]);
+          const double ndl = fma(t[kGroup - 1], cA, cM) - cM;
+          if ((unsigned)__double2hiint(ndl) > thr_hi) break;   // tau_cut is crossed inside this group: go step by step
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) RB_RT_WEIGHT(t[j], d[j] + d[j + 1], w[j]);
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) { iW = fma(q[j].y, w[j], iW); Tb = fma(q[j].z, w[j], Tb); }
+          tau = t[kGroup - 1];
+        }
       }
       // remainder of the chunk / the group that crosses tau_cut: one segment at a time with the test
       for (; u < m; ++u) {
