@@ -42,9 +42,13 @@ BSTEP = 0.005
 NFREQ = 64
 METRIC = 'Tb pixel*freq/s (Jupiter image cube b=0.005, 64 freqs 1-100 GHz, on-disc pixels)'
 UNIT = 'pixel*freq/s'
-# rt_integrate_rays_kernel, per executed (ray, freq, segment) step: 7 DFMA + 2 DMUL + 2 DADD
+# rt_integrate_rays_kernel, per executed (ray, freq, segment) step:
+#   table phase  7 DFMA + 2 DMUL + 2 DADD = 11 FP64 instructions, 18 flops
+#   small-tau phase (tau < 2^-11)  5 DFMA + 1 DMUL + 1 DADD = 7 FP64 instructions, 12 flops
 RT_FLOPS_PER_STEP = 18.0
 RT_FP64_INSTR_PER_STEP = 11.0
+RT_FLOPS_PER_SMALL_STEP = 12.0
+RT_FP64_INSTR_PER_SMALL_STEP = 7.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one rt_integrate_rays_kernel launch of this workload at N=1
 RT_DRAM_BYTES_N1 = 1088100000
 RT_DRAM_SOURCE = 'ncu --set full, profiles/r1_final_rt_integrate_rays_ncu_full.txt (1.014 GB read + 0.074 GB written)'
@@ -388,6 +392,7 @@ def run_gpu(args):
     step()
     torch.cuda.synchronize()
     steps_executed = ctx.count_steps(False)
+    steps_small = ctx.count_small_steps()
 
     # ---- end to end through the public API (host buffers) ----------------------------------------
     planet = Planet('jupiter', atmosphere=atm, verbose=False)
@@ -426,7 +431,8 @@ def run_gpu(args):
         # alpha slab + T + float32 Tb out for every pixel of the rank
         rt_bytes = n_on_rank * S * 8 + F * L * 8 + L * 8 + len(pts) * F * 4
         rt_steps_all = float(n_on_rank) * F * (S - 1)
-        rt_flops = float(steps_executed) * RT_FLOPS_PER_STEP   # 11 FP64 instructions = 18 flops per executed segment-step, DESIGN.md 3.3
+        rt_flops = float(steps_executed - steps_small) * RT_FLOPS_PER_STEP + float(steps_small) * RT_FLOPS_PER_SMALL_STEP
+        rt_instr = float(steps_executed - steps_small) * RT_FP64_INSTR_PER_STEP + float(steps_small) * RT_FP64_INSTR_PER_SMALL_STEP
         roofline = {'bound': 'hbm', 'kernel': 'rt_integrate_rays_kernel', 'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9,
                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': rt_bytes / (rt_ms * 1e-3) / 1e9 / hbm_peak,
                     'traffic': RT_DRAM_BYTES_N1 if world == 1 else None, 'traffic_source': RT_DRAM_SOURCE,
@@ -435,7 +441,9 @@ def run_gpu(args):
                     'fp64': {'achieved_tflops': rt_flops / (rt_ms * 1e-3) / 1e12, 'peak_tflops': fp64_peak,
                              'frac': rt_flops / (rt_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
                              'flops_per_segment_step': RT_FLOPS_PER_STEP, 'fp64_instr_per_segment_step': RT_FP64_INSTR_PER_STEP,
-                             'pipe_frac': (float(steps_executed) * RT_FP64_INSTR_PER_STEP / (rt_ms * 1e-3) / 1e12) / (fp64_peak / 2.0) if fp64_peak else None,
+                             'pipe_frac': (rt_instr / (rt_ms * 1e-3) / 1e12) / (fp64_peak / 2.0) if fp64_peak else None,
+                             'flops_per_small_tau_step': RT_FLOPS_PER_SMALL_STEP, 'fp64_instr_per_small_tau_step': RT_FP64_INSTR_PER_SMALL_STEP,
+                             'segment_steps_small_tau': int(steps_small),
                              'peak_source': 'rb_probe_fp64_peak (DFMA, same box, same run)',
                              'segment_steps_executed': int(steps_executed), 'segment_steps_all': rt_steps_all,
                              'note': 'flops counted over the segment-steps actually executed (in-kernel counter, untimed pass); '

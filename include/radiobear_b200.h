@@ -69,6 +69,9 @@ int rb_set_rt_chunks(rb_context* ctx, int n);
  * tau_cut early exit skips the rest).  enable = 1 resets and starts counting, 0 stops; the count is returned
  * (after synchronising the context stream). */
 int64_t rb_count_steps(rb_context* ctx, int enable);
+/* Of the count returned by the last rb_count_steps call: the steps taken in the kernel's small-optical-depth
+ * phase (tau < 2^-11: short polynomial instead of the table exponential). */
+int64_t rb_count_small_steps(const rb_context* ctx);
 
 /* ---- line catalogs --------------------------------------------------------------------- *
  * Replaces the per-plugin npz readers: nh3_hs.py:62-67, nh3_sjs.py:17-23, h2s_ddb.py:14-39,

@@ -82,6 +82,7 @@ def load():
         'rb_kernel_timed_count': (i64, [vp, C.c_int]),
         'rb_set_rt_chunks': (C.c_int, [vp, C.c_int]),
         'rb_count_steps': (i64, [vp, C.c_int]),
+        'rb_count_small_steps': (i64, [vp]),
         'rb_set_catalog': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
         'rb_alpha_layers': (C.c_int, [vp, C.POINTER(AlphaDesc), vp, vp]),
         'rb_alpha_layers_dev': (C.c_int, [vp, C.POINTER(AlphaDesc), vp, vp]),
@@ -106,7 +107,7 @@ def load():
 EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error', 'rb_set_stream', 'rb_use_own_stream',
                     'rb_synchronize',
                     'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_kernel_timed_count',
-                    'rb_set_rt_chunks', 'rb_count_steps', 'rb_set_catalog', 'rb_alpha_layers',
+                    'rb_set_rt_chunks', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
                     'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_compute_ds', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
                     'rb_probe_fp64_peak', 'rb_probe_rcp']
 
@@ -182,6 +183,10 @@ class Context:
     def count_steps(self, enable):
         """Start (True) / stop (False) counting integrated segment-steps; returns the count so far."""
         return int(self.lib.rb_count_steps(self.h, 1 if enable else 0))
+
+    def count_small_steps(self):
+        """Of the last count_steps() result: the steps of the small-tau phase."""
+        return int(self.lib.rb_count_small_steps(self.h))
 
     def set_rt_chunks(self, n):
         self.check(self.lib.rb_set_rt_chunks(self.h, int(n)))

@@ -162,19 +162,22 @@ int64_t rb_kernel_timed_count(const rb_context* ctx, int which) {
 int64_t rb_count_steps(rb_context* ctx, int enable) {
   if (!ctx) return -1;
   cudaSetDevice(ctx->device);
-  unsigned long long h = 0;
+  unsigned long long h[2] = {0, 0};
   static unsigned long long* dev = nullptr;
-  if (!dev && cudaMalloc(&dev, sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (!dev && cudaMalloc(&dev, sizeof(h)) != cudaSuccess) return -1;
   cudaStreamSynchronize(ctx->stream);
-  if (ctx->step_counter) cudaMemcpy(&h, dev, sizeof(h), cudaMemcpyDeviceToHost);
+  if (ctx->step_counter) cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost);
   if (enable) {
-    cudaMemset(dev, 0, sizeof(unsigned long long));
+    cudaMemset(dev, 0, sizeof(h));
     ctx->step_counter = dev;
   } else {
     ctx->step_counter = nullptr;
   }
-  return (int64_t)h;
+  ctx->last_small_steps = (int64_t)h[1];
+  return (int64_t)h[0];
 }
+
+int64_t rb_count_small_steps(const rb_context* ctx) { return ctx ? ctx->last_small_steps : -1; }
 
 int rb_set_rt_chunks(rb_context* ctx, int n) {
   if (!ctx || n < 0) return RB_ERR_INVALID;

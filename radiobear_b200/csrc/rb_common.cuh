@@ -39,7 +39,8 @@ struct rb_context {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> pipe_ev;
   int rt_chunks = 0;  // 0 = automatic
-  unsigned long long* step_counter = nullptr;  // device counter of integrated segment-steps (measurement aid)
+  unsigned long long* step_counter = nullptr;  // device counters of integrated segment-steps (measurement aid)
+  int64_t last_small_steps = 0;                // of the count last read: steps taken in the small-tau phase
   // geometry computed ahead of the rt call that will use it (rb_geometry_prefetch[_dev]); single use
   struct GeoTicket {
     bool valid = false;

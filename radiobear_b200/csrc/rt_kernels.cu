@@ -356,7 +356,7 @@ struct RtK {
   const double* alpha;  // [L][F]
   const double* T;      // [L]
   const double4* prep;  // [F/8][L-1][8] interleaved loop operands (rays-major kernel only, see rt_prepare_kernel)
-  unsigned long long* step_counter;  // optional: number of (ray, freq, segment) steps actually integrated
+  unsigned long long* step_counter;  // optional: [0] (ray, freq, segment) steps actually integrated, [1] of which in phase A
   const double* exp_tab;  // 2^(j/1024) (rays-major kernel only)
   RtProgress progress;    // optional per-chunk completion counters (rays-major kernel only)
   const double* ds;     // [S][Rpad]
@@ -710,6 +710,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
 
   bool stop = false;
   bool small = true;                                       // this ray is still in the small-tau phase A
+  int ia = 0;                                              // segments integrated in phase A
   for (int c = 0; any_live; ++c) {
     cp_async_wait<0>();                                    // this thread's pieces of chunk c have landed
     if (!__syncthreads_or(live)) break;                    // ... everybody's have; chunk c-1 is fully consumed
@@ -751,6 +752,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
           }
           tau = t[kGroup - 1];
         }
+        ia += u;                                             // phase-A steps of this chunk (feeds rb_count_steps)
       }
       // Phase B: groups of kGroup segments: the optical depths first (one dependent FMA each), one threshold
       // test on the deepest, then kGroup independent exp / accumulate chains through the table
@@ -805,8 +807,12 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   cp_async_wait<0>();
   if (k.step_counter) {   // measurement aid (bench.py): executed segment-steps, one atomic per warp
     unsigned long long done = (unsigned long long)i;   // rays that crossed tau_cut count the whole last group
-    for (int o = 16; o > 0; o >>= 1) done += __shfl_down_sync(0xffffffffu, done, o);
-    if (threadIdx.x == 0) atomicAdd(k.step_counter, done);
+    unsigned long long done_a = (unsigned long long)ia;
+    for (int o = 16; o > 0; o >>= 1) {
+      done += __shfl_down_sync(0xffffffffu, done, o);
+      done_a += __shfl_down_sync(0xffffffffu, done_a, o);
+    }
+    if (threadIdx.x == 0) { atomicAdd(k.step_counter, done); atomicAdd(k.step_counter + 1, done_a); }
   }
   if (valid) {
     double vout, wout = iW;
