@@ -289,3 +289,33 @@ def test_geometry_prefetch_is_only_an_ordering_optimisation(eng):
     assert ds.shape[0] == 7
     got3 = eng.rt_batch(radius=radius, b=b, alpha_slab=slab, T=T, **g)['Tb']
     assert np.array_equal(got3, ref, equal_nan=True)
+
+
+def test_chunked_copy_out_equals_single_copy(eng):
+    """Host-output pipeline: one launch whose CTAs report per-chunk progress while a copy stream moves finished
+    chunks out (rotated launch order, wrapped chunk, ragged last tile) == the plain launch + one copy, bit for
+    bit, for Tb (f32 and f64) and integrated_W."""
+    from radiobear_b200 import _lib
+    a = golden('atm_jupiter.npz')
+    C = keymap(a['C_keys'])
+    T = a['gas'][C['T']]
+    slab = _slab(eng, a, np.array([1.5, 9.0, 22.0, 44.0, 95.0]))
+    rng = np.random.default_rng(5)
+    R = 16384 + 4321                                  # not a multiple of 32; above the pipelining threshold
+    b = np.ascontiguousarray(rng.uniform(-1.05, 1.05, (R, 2)))
+    ctx = _lib.get_context()
+    try:
+        ctx.set_rt_chunks(1)
+        ref = eng.rt_batch(b=b, alpha_slab=slab, T=T, want_intW=True, **geom(a))
+        ref = {k: v.copy() for k, v in ref.items()}
+        ref32 = eng.rt_batch(b=b, alpha_slab=slab, T=T, out_f32=True, **geom(a))['Tb'].copy()
+        for nch in (0, 3, 7, 16):
+            ctx.set_rt_chunks(nch)
+            got = eng.rt_batch(b=b, alpha_slab=slab, T=T, want_intW=True, **geom(a))
+            assert np.array_equal(got['Tb'], ref['Tb'], equal_nan=True)
+            assert np.array_equal(got['integrated_W'], ref['integrated_W'], equal_nan=True)
+            got32 = eng.rt_batch(b=b, alpha_slab=slab, T=T, out_f32=True, **geom(a))['Tb']
+            assert np.array_equal(got32, ref32, equal_nan=True)
+    finally:
+        ctx.set_rt_chunks(0)
+    assert np.isnan(ref['Tb']).any() and (ref['Tb'] == 2.725).any() and (ref['Tb'] > 100.0).any()
