@@ -52,6 +52,11 @@ RT_FP64_INSTR_PER_SMALL_STEP = 7.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one rt_integrate_rays_kernel launch of this workload at N=1
 RT_DRAM_BYTES_N1 = 1088100000
 RT_DRAM_SOURCE = 'ncu --set full, profiles/r1_final_rt_integrate_rays_ncu_full.txt (1.014 GB read + 0.074 GB written)'
+# SASS instructions (cuobjdump) and shared-memory wavefronts (128 B/clk/SM crossbar) per executed segment-step of the
+# two integration kernels, {precision: (phase A, phase B)}: the resources the kernels are actually short of
+RT_SASS_PER_STEP = {'f64': (12.75, 21.5), 'mixed': (10.0, 14.5)}
+RT_SMEM_WAVEFRONTS_PER_STEP = {'f64': (4.5, 8.5), 'mixed': (2.0, 4.25)}
+RT_KERNEL = {'f64': 'rt_integrate_rays_kernel', 'mixed': 'rt_integrate_rays_mixed_kernel'}
 WORKLOAD = 'C4: Jupiter full image b=0.005 (601x601 px) x 64 freqs 1-100 GHz, 1000 layers, alpha+geometry+RT per step'
 
 
@@ -299,6 +304,7 @@ def run_gpu(args):
         dist.init_process_group('nccl', device_id=dev)
     ctx = _lib.get_context(local)
     ctx.enable_timing(True)
+    precision = ctx.rt_precision()          # 'f64' unless RB_RT_PRECISION=mixed (include/radiobear_b200.h)
 
     atm, freqs, grid = workload()
     cfg = atm.config
@@ -433,12 +439,30 @@ def run_gpu(args):
         rt_steps_all = float(n_on_rank) * F * (S - 1)
         rt_flops = float(steps_executed - steps_small) * RT_FLOPS_PER_STEP + float(steps_small) * RT_FLOPS_PER_SMALL_STEP
         rt_instr = float(steps_executed - steps_small) * RT_FP64_INSTR_PER_STEP + float(steps_small) * RT_FP64_INSTR_PER_SMALL_STEP
-        roofline = {'bound': 'hbm', 'kernel': 'rt_integrate_rays_kernel', 'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9,
+        steps_b = float(steps_executed - steps_small)
+        sm_hz = 1e6 * float((clocks or {}).get('sm_mhz') or 1965.0)
+        n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        sass_a, sass_b = RT_SASS_PER_STEP[precision]
+        wf_a, wf_b = RT_SMEM_WAVEFRONTS_PER_STEP[precision]
+        warp_cycles = n_sms * sm_hz * (rt_ms * 1e-3)          # SM-cycles of the launch
+        roofline = {'bound': 'hbm', 'kernel': RT_KERNEL[precision], 'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9,
                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': rt_bytes / (rt_ms * 1e-3) / 1e9 / hbm_peak,
-                    'traffic': RT_DRAM_BYTES_N1 if world == 1 else None, 'traffic_source': RT_DRAM_SOURCE,
+                    'traffic': RT_DRAM_BYTES_N1 if (world == 1 and precision == 'f64') else None,
+                    'traffic_source': RT_DRAM_SOURCE if precision == 'f64' else None,
                     'peak_source': peak_src, 'ms_per_launch': rt_ms, 'launches_per_step': rt_chunks,
-                    'note': 'at F=64 the kernel is FP64/exp-bound, not HBM-bound (SURVEY 8d): see fp64',
-                    'fp64': {'achieved_tflops': rt_flops / (rt_ms * 1e-3) / 1e12, 'peak_tflops': fp64_peak,
+                    'note': 'at F=64 the kernel is issue / shared-memory / FP64 bound, not HBM-bound (SURVEY 8d): see issue, smem, fp64',
+                    # what actually binds: warp-instruction issue slots (4 schedulers per SM, 1 instruction per clock
+                    # each) and the shared-memory crossbar (1 wavefront = 128 B per clock per SM)
+                    'issue': {'sass_per_step_phase_a': sass_a, 'sass_per_step_phase_b': sass_b,
+                              'frac': (float(steps_small) * sass_a + steps_b * sass_b) / 32.0 / (4.0 * warp_cycles)},
+                    'smem': {'wavefronts_per_step_phase_a': wf_a, 'wavefronts_per_step_phase_b': wf_b,
+                             'frac': (float(steps_small) * wf_a + steps_b * wf_b) / 32.0 / warp_cycles,
+                             'peak': '128 B/clk/SM (B300_MICROARCH.md, LDS/STS)'},
+                    'sm_mhz_used': sm_hz / 1e6,
+                    'segment_steps_executed': int(steps_executed), 'segment_steps_small_tau': int(steps_small),
+                    'segment_steps_all': rt_steps_all}
+        if precision == 'f64':
+            roofline['fp64'] = {'achieved_tflops': rt_flops / (rt_ms * 1e-3) / 1e12, 'peak_tflops': fp64_peak,
                              'frac': rt_flops / (rt_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
                              'flops_per_segment_step': RT_FLOPS_PER_STEP, 'fp64_instr_per_segment_step': RT_FP64_INSTR_PER_STEP,
                              'pipe_frac': (rt_instr / (rt_ms * 1e-3) / 1e12) / (fp64_peak / 2.0) if fp64_peak else None,
@@ -447,9 +471,13 @@ def run_gpu(args):
                              'peak_source': 'rb_probe_fp64_peak (DFMA, same box, same run)',
                              'segment_steps_executed': int(steps_executed), 'segment_steps_all': rt_steps_all,
                              'note': 'flops counted over the segment-steps actually executed (in-kernel counter, untimed pass); '
-                                     'the tau > tau_cut exit skips the rest of each ray'}}
+                                     'the tau > tau_cut exit skips the rest of each ray'}
+        else:
+            roofline['mixed'] = {'fp64_instr_per_step_phase_b': 2, 'mufu_per_step_phase_b': 1,
+                                 'note': 'optical depth in FP64 (2 DFMA per step in phase B, none in phase A), exp on the SFU, '
+                                         'weights and chunk sums in FP32 (FFMA2 / FMUL2), chunk sums accumulated in FP64'}
         cores = 1
-        cpu_v, cpu_desc, _ = cpu_sample(cores, n_pix_per_core=12, n_lay_per_core=48) if world == 1 else (None, None, None)
+        cpu_v, cpu_desc, _ = cpu_sample(cores, n_pix_per_core=int(os.environ.get('RB_BENCH_CPU_PIXELS', '160')), n_lay_per_core=128) if world == 1 else (None, None, None)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
@@ -457,7 +485,7 @@ def run_gpu(args):
             'config': {'workload': WORKLOAD, 'pixels': 'on-disc', 'on_disc_pixels': n_on, 'nan_limb_pixels': n_nan,
                        'all_pixels': n_all, 'layers': L, 'freqs': F, 'sharding': 'image rows balanced by on-disc pixels; output stays row-sharded in HBM (no collective); e2e: every rank copies its rows into one shared pinned host image',
                        'l2': 'flushed between timed steps (256 MiB write, untimed); ds slab (0.94 GB) exceeds L2',
-                       'tb_dtype_out': 'f32', 'tau_cut': engine.TAU_CUT},
+                       'tb_dtype_out': 'f32', 'tau_cut': engine.TAU_CUT, 'rt_precision': precision},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': 1e3 * float(e2e_t.item()), 'api': 'Planet.run(freqs, b=0.005)'},

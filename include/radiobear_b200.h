@@ -65,6 +65,19 @@ int64_t rb_kernel_timed_count(const rb_context* ctx, int which);
 /* Ray-chunk pipeline depth for large requests: n chunks whose geometry / integration / device->host copy
  * overlap on three streams (0 = automatic, 1 = no pipelining). */
 int rb_set_rt_chunks(rb_context* ctx, int n);
+/* Arithmetic of the batched ray integration (Brightness.single over >= 512 point rays, brightness.py:60-113).
+ *   RB_RT_F64   : every operation in FP64 (|Tb - reference| ~ 1e-9 K).
+ *   RB_RT_MIXED : the optical depth tau stays FP64; exp(-tau) on the SFU (ex2.approx), weights and per-chunk
+ *                 partial sums in FP32, chunk sums accumulated in FP64.  Error against RB_RT_F64 is at the level of
+ *                 one float32 ulp of Tb (Data.Tb is float32 in the reference, data_handling.py:46-47), two orders
+ *                 inside the 0.01 K parity bar; see DESIGN.md 3.3 for the measured figure.
+ * Disc-averaged runs, profile outputs, small batches and rb_rt_integrate always run in FP64.  The initial value is
+ * RB_RT_DEFAULT_PRECISION unless the environment variable RB_RT_PRECISION is "f64" or "mixed". */
+#define RB_RT_F64 0
+#define RB_RT_MIXED 1
+#define RB_RT_DEFAULT_PRECISION RB_RT_F64
+int rb_set_rt_precision(rb_context* ctx, int precision);
+int rb_get_rt_precision(const rb_context* ctx);
 /* Measurement aid: count the (ray, freq, segment) steps the integration kernel actually executes (the
  * tau_cut early exit skips the rest).  enable = 1 resets and starts counting, 0 stops; the count is returned
  * (after synchronising the context stream). */

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libradiobear_b200.so')
+# RB_LIB_PATH: another build of the same library (tools/ab_quick.py compares build variants on the GPU box)
+LIB_PATH = os.environ.get('RB_LIB_PATH') or os.path.join(_HERE, 'lib', 'libradiobear_b200.so')
 
 RB_OK, RB_ERR_INVALID, RB_ERR_CUDA, RB_ERR_NOMEM, RB_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 RB_MAX_CONSTITUENTS = 8
@@ -24,6 +25,8 @@ FORMALISM_IDS = {'nh3_hs': 1, 'nh3_dbs': 2, 'nh3_sjs': 3, 'nh3_hs_sjs': 4, 'nh3_
 GAS_ORDER = ['H2', 'HE', 'CH4', 'NH3', 'H2O', 'H2S', 'PH3', 'CO']           # RB_GAS_*
 CLOUD_ORDER = ['H2O', 'SOLN', 'NH4SH', 'NH3', 'H2S', 'CH4']                 # RB_CLD_*
 CLOUD_FLAG_KEYS = ['ice_p', 'water_p', 'nh4sh_p', 'nh3ice_p', 'h2sice_p', 'ch4']   # clouds_idp.py:17-45
+
+RT_PRECISIONS = {'f64': 0, 'mixed': 1}                                      # RB_RT_*
 
 _dp = C.POINTER(C.c_double)
 
@@ -81,6 +84,8 @@ def load():
         'rb_kernel_ms_history': (C.c_int, [vp, C.c_int, vp, C.c_int]),
         'rb_kernel_timed_count': (i64, [vp, C.c_int]),
         'rb_set_rt_chunks': (C.c_int, [vp, C.c_int]),
+        'rb_set_rt_precision': (C.c_int, [vp, C.c_int]),
+        'rb_get_rt_precision': (C.c_int, [vp]),
         'rb_count_steps': (i64, [vp, C.c_int]),
         'rb_count_small_steps': (i64, [vp]),
         'rb_set_catalog': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -107,7 +112,7 @@ def load():
 EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error', 'rb_set_stream', 'rb_use_own_stream',
                     'rb_synchronize',
                     'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_kernel_timed_count',
-                    'rb_set_rt_chunks', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
+                    'rb_set_rt_chunks', 'rb_set_rt_precision', 'rb_get_rt_precision', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
                     'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_compute_ds', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
                     'rb_probe_fp64_peak', 'rb_probe_rcp']
 
@@ -190,6 +195,16 @@ class Context:
 
     def set_rt_chunks(self, n):
         self.check(self.lib.rb_set_rt_chunks(self.h, int(n)))
+
+    def set_rt_precision(self, precision):
+        """'f64' or 'mixed' (include/radiobear_b200.h: RB_RT_F64 / RB_RT_MIXED) for the batched ray integration."""
+        if precision not in RT_PRECISIONS:
+            raise ValueError("rt precision must be one of {}".format(sorted(RT_PRECISIONS)))
+        self.check(self.lib.rb_set_rt_precision(self.h, RT_PRECISIONS[precision]))
+
+    def rt_precision(self):
+        code = int(self.lib.rb_get_rt_precision(self.h))
+        return {v: k for k, v in RT_PRECISIONS.items()}[code]
 
     def kernel_ms_history(self, which, n=256):
         buf = np.zeros(n)

@@ -75,6 +75,12 @@ int rb_create(int device, rb_context** out) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
+  ctx->rt_precision = RB_RT_DEFAULT_PRECISION;
+  if (const char* pe = getenv("RB_RT_PRECISION")) {
+    if (!strcmp(pe, "mixed")) ctx->rt_precision = RB_RT_MIXED;
+    else if (!strcmp(pe, "f64")) ctx->rt_precision = RB_RT_F64;
+    else return rb_fail(ctx, RB_ERR_INVALID, "RB_RT_PRECISION must be f64 or mixed, got '%s'", pe);
+  }
   for (int i = 0; i < 3; ++i)
     for (int r = 0; r < rb_context::kEvRing; ++r)
       for (int j = 0; j < 2; ++j) RB_CUDA(ctx, cudaEventCreate(&ctx->ev[i][r][j]));
@@ -184,6 +190,19 @@ int rb_set_rt_chunks(rb_context* ctx, int n) {
   ctx->rt_chunks = n;
   return RB_OK;
 }
+
+static void drop_ticket(rb_context* ctx);
+
+int rb_set_rt_precision(rb_context* ctx, int precision) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (precision != RB_RT_F64 && precision != RB_RT_MIXED)
+    return rb_fail(ctx, RB_ERR_INVALID, "rt precision %d unknown (RB_RT_F64 / RB_RT_MIXED)", precision);
+  if (precision != ctx->rt_precision) drop_ticket(ctx);   // a prefetched geometry has the other slab layout
+  ctx->rt_precision = precision;
+  return RB_OK;
+}
+
+int rb_get_rt_precision(const rb_context* ctx) { return ctx ? ctx->rt_precision : -1; }
 
 int rb_set_catalog(rb_context* ctx, int catalog, int nlines, int ncols, const double* cols) {
   if (!ctx) return RB_ERR_INVALID;
@@ -337,6 +356,20 @@ static bool take_ticket(rb_context* ctx, const rb_geometry_desc* g, int64_t R, c
 }
 static void drop_ticket(rb_context* ctx) { take_ticket(ctx, nullptr, -1, nullptr); }
 
+// The ds buffer of a ray request: the tiled FP64 slab, followed -- when the context integrates in mixed
+// precision -- by the float slab of the same tiling (each with its over-read slack).
+static size_t ds_bytes(const rb_context* ctx, size_t S, int64_t Rpad) {
+  const size_t one = S * (size_t)Rpad * 8 + kRtSlackBytes;
+  return ctx->rt_precision == RB_RT_MIXED ? one + S * (size_t)Rpad * 4 + kRtSlackBytes : one;
+}
+static void bind_ds(const rb_context* ctx, RtLaunch& L, void* p_ds, void* p_n) {
+  const size_t S = L.L - 1;
+  L.ds = (double*)p_ds;
+  L.dsf = ctx->rt_precision == RB_RT_MIXED ? (float*)((char*)p_ds + S * (size_t)L.Rpad * 8 + kRtSlackBytes) : nullptr;
+  L.nseg = (int32_t*)p_n;
+  L.nanflag = (int32_t*)p_n + L.Rpad;
+}
+
 static int geometry_prefetch(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const double* b, bool host) {
   if (!ctx) return RB_ERR_INVALID;
   if (!b || !g || !g->radius) return rb_fail(ctx, RB_ERR_INVALID, "geometry_prefetch: null pointer");
@@ -351,7 +384,7 @@ static int geometry_prefetch(rb_context* ctx, const rb_geometry_desc* g, int64_t
     RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, L.L * 8, &p_rad));
     RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
   }
-  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, ds_bytes(ctx, S, L.Rpad), &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   if (!ctx->aux[0]) {
     // highest priority: the few, long-running geometry CTAs get their SM slots ahead of the absorption
@@ -373,7 +406,7 @@ static int geometry_prefetch(rb_context* ctx, const rb_geometry_desc* g, int64_t
   } else {
     L.radius = g->radius; L.b = b;
   }
-  L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
+  bind_ds(ctx, L, p_ds, p_n);
   ctx->stream = sG;
   const int status = rb_launch_geometry(ctx, L);
   ctx->stream = user;
@@ -488,7 +521,7 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_de
   const int64_t R = full.R;
   const size_t S = full.L - 1, F = rd->n_freqs, esz = rd->out_f32 ? 4 : 8;
   RtPrep prep;
-  RB_TRY(rb_rt_prepare(ctx, full.L, rd, R, false, &prep));
+  RB_TRY(rb_rt_prepare(ctx, full.L, rd, R, false, full.dsf != nullptr, &prep));
   if (!have_geometry) RB_TRY(rb_launch_geometry(ctx, full));
   const int nch = choose_chunks(ctx, R, prep.use_rays, h_out != nullptr);
   if (nch == 1) {
@@ -568,6 +601,7 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_de
     Lc.Rpad = (Lc.R + 31) & ~(int64_t)31;
     Lc.b = full.b + 2 * r0;
     Lc.ds = full.ds + (size_t)t0 * S * 32;
+    if (full.dsf) Lc.dsf = full.dsf + (size_t)t0 * S * 32;
     Lc.nseg = full.nseg + r0;
     Lc.nanflag = full.nanflag + r0;
     char* oc = (char*)d_out + (size_t)r0 * F * esz;
@@ -597,9 +631,10 @@ int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc
   RB_TRY(make_geometry(ctx, g, R, &L));
   const size_t S = L.L - 1;
   void *p_ds, *p_n;
-  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, ds_bytes(ctx, S, L.Rpad), &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
-  L.radius = g->radius; L.b = b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
+  L.radius = g->radius; L.b = b;
+  bind_ds(ctx, L, p_ds, p_n);
   const bool have_geometry = take_ticket(ctx, g, R, b);
   return run_rt_pipeline(ctx, L, rt, out_Tb, out_intW, nullptr, nullptr, have_geometry);
 }
@@ -620,7 +655,7 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   void *p_rad, *p_b, *p_ds, *p_n, *p_alpha, *p_T, *p_tb, *p_iw = nullptr, *p_prof = nullptr;
   RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, nL * 8, &p_rad));
   RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
-  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, ds_bytes(ctx, S, L.Rpad), &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, nL * F * 8, &p_alpha));
   RB_TRY(rb_ensure(ctx, RB_BUF_T, nL * 8, &p_T));
@@ -636,7 +671,8 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   RB_CUDA(ctx, cudaMemcpyAsync(p_alpha, rt->alpha, nL * F * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_T, rt->T, nL * 8, cudaMemcpyHostToDevice, s));
   RB_TRACE_AT("inputs enqueued");
-  L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
+  L.radius = (const double*)p_rad; L.b = (const double*)p_b;
+  bind_ds(ctx, L, p_ds, p_n);
   rb_rt_desc rd = *rt;
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
   RB_TRY(run_rt_pipeline(ctx, L, &rd, p_tb, (double*)p_iw, out_Tb, out_intW, have_geometry));
@@ -652,7 +688,7 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
     double* pp = (double*)p_prof;
     rd.out_f32 = 0;
     RtPrep prof_prep;
-    RB_TRY(rb_rt_prepare(ctx, L.L, &rd, 1, true, &prof_prep));
+    RB_TRY(rb_rt_prepare(ctx, L.L, &rd, 1, true, false, &prof_prep));
     RB_TRY(rb_launch_integrate(ctx, L1, &rd, prof_prep, nullptr, pp + 3 * F * S, nullptr, 0, pp, pp + F * S, pp + 2 * F * S));
     RB_CUDA(ctx, cudaMemcpyAsync(out_tau, pp, F * S * 8, cudaMemcpyDeviceToHost, s));
     RB_CUDA(ctx, cudaMemcpyAsync(out_W, pp + F * S, F * S * 8, cudaMemcpyDeviceToHost, s));
@@ -693,7 +729,7 @@ int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int
   rb_rt_desc rd = *rt;
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
   RtPrep prep;
-  RB_TRY(rb_rt_prepare(ctx, L.L, &rd, R, false, &prep));
+  RB_TRY(rb_rt_prepare(ctx, L.L, &rd, R, false, false, &prep));
   RB_TRY(rb_launch_integrate(ctx, L, &rd, prep, nullptr, p_tb, (double*)p_iw, -1, nullptr, nullptr, nullptr));
   RB_CUDA(ctx, cudaMemcpyAsync(out_Tb, p_tb, (size_t)R * F * esz, cudaMemcpyDeviceToHost, s));
   if (out_intW) RB_CUDA(ctx, cudaMemcpyAsync(out_intW, p_iw, (size_t)R * F * 8, cudaMemcpyDeviceToHost, s));

@@ -39,6 +39,7 @@ struct rb_context {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> pipe_ev;
   int rt_chunks = 0;  // 0 = automatic
+  int rt_precision = 0;  // RB_RT_F64 / RB_RT_MIXED: arithmetic of the rays-major integration (rb_set_rt_precision)
   unsigned long long* step_counter = nullptr;  // device counters of integrated segment-steps (measurement aid)
   int64_t last_small_steps = 0;                // of the count last read: steps taken in the small-tau phase
   // geometry computed ahead of the rt call that will use it (rb_geometry_prefetch[_dev]); single use
@@ -112,6 +113,7 @@ struct RtLaunch {
   int64_t Rpad;
   const double* b;  // device [R][2]
   double* ds;       // device slab [Rpad/32][L-1][32] (tiled by 32 rays, see rt_kernels.cu)
+  float* dsf;       // device slab of float segments, same tiling (mixed-precision integration only, else null)
   int32_t* nseg;    // device [R]
   int32_t* nanflag; // device [R]: ray carries a NaN segment the integration would use
 };
@@ -132,10 +134,11 @@ struct RtProgress {
 
 struct RtPrep {
   bool use_rays = false;       // rays-major kernel (R >= 512, point rays) or the lanes = frequency kernel
+  bool mixed = false;          // rays-major kernel in mixed precision (operand rows of rt_prepare_mixed_kernel)
   const void* prep = nullptr;  // operand slab of the rays-major kernel
 };
 int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt /*device pointers*/, int64_t R_total, bool profile,
-                  RtPrep* out);
+                  bool have_pairs /*RtLaunch::dsf was written*/, RtPrep* out);
 int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt /*device pointers*/, const RtPrep& prep,
                         const RtProgress* progress,
                         void* out_Tb, double* out_intW, int64_t profile_ray, double* out_tau, double* out_W,

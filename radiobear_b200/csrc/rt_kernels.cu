@@ -40,6 +40,7 @@ struct GeoK {
   long long R, Rpad;
   const double* b;
   double* ds;
+  float* dsf;    // optional (mixed-precision integration): [R/32][S][32] (float)ds_i, 0 below the last used one
   int* nseg;
   int* nanflag;  // 1 when a segment the integration uses (index <= nseg-2) is NaN -> Tb is NaN
 };
@@ -160,6 +161,10 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
   int layer = 0;
   int count = 0;
   double* out = g.ds + ds_tile_base(r, S);
+  // mixed-precision integration (rt_integrate_rays_mixed_kernel) also wants every segment as a float; the
+  // one below the last used segment (i = n-1, brightness.py:65 stops at n-2) is stored as 0 so that the
+  // trapezoid weight ds_i + ds_i+1 of the last node needs no special case
+  float* const outf = g.dsf ? g.dsf + ds_tile_base(r, S) : nullptr;
   const double e2 = 1.0 - q2;
   const double sin6 = 9.99999999999833333e-07, cos6 = 0.9999999999995;   // sin / cos of 1e-6 rad
   const double shape0sq = q2 * sin6 * sin6 + cos6 * cos6;               // lat == 0 -> 1e-6 rad (shape.py:231-233)
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     }
     out[(size_t)layer * kDsStride] = ds;
     ++count;
+    if (outf) outf[(size_t)layer * kDsStride] = (float)ds;
     if (ds != ds) {
       // below the tangent shell: every later segment is NaN too (np.sqrt of a negative number,
       // raypath.py:192-209 never reaches its `except`), so just fill the rest of the column
@@ -263,6 +269,7 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     if (last_used != last_used) first_nan = 0;
   }
   g.nseg[r] = count;
+  if (outf && count >= 1) outf[(size_t)(count - 1) * kDsStride] = 0.0f;
   // Brightness.single uses ds[0 .. n-2] (brightness.py:65); a NaN there makes every frequency NaN
   g.nanflag[r] = (first_nan >= 0 && first_nan <= count - 2) ? 1 : 0;
 }
@@ -358,6 +365,8 @@ struct RtK {
   const double4* prep;  // [F/8][L-1][8] interleaved loop operands (rays-major kernel only, see rt_prepare_kernel)
   unsigned long long* step_counter;  // optional: [0] (ray, freq, segment) steps actually integrated, [1] of which in phase A
   const double* exp_tab;  // 2^(j/1024) (rays-major kernel only)
+  const float* dsf;               // mixed-precision rays-major kernel: float segments (see GeoK::dsf)
+  const void* prepm;              // mixed-precision rays-major kernel: operand rows (see rt_prepare_mixed_kernel)
   RtProgress progress;    // optional per-chunk completion counters (rays-major kernel only)
   const double* ds;     // [S][Rpad]
   const int* nseg;      // [R]
@@ -504,6 +513,8 @@ __device__ double c_small[4] = {
     -kSmallE * (kSmallK1 + kSmallM),                                  // a1
     0.5 * kSmallE,                                                    // a2
     0.0};
+// mixed-precision kernel: -2^23 log2 e and the rounding constant 2^52 + 2^51 with 0x3F000000 folded into its low word
+__device__ double c_mxc[2] = {-1.4426950408889634074 * 8388608.0, 6755399441055744.0 + 1056964608.0};
 #if RB_EXP_DEG == 2
 #define RB_EXP_POLY(x) fma(fma((x), c2, ce), (x), c1)
 #else
@@ -837,13 +848,292 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   }
 }
 
+// ====================================================================================================
+// Mixed-precision variant of the rays-major integration (rb_set_rt_precision(ctx, RB_RT_MIXED)).
+//
+// Data.Tb is float32 in the reference (data_handling.py:46-47: 3e-5 K per ulp at 300 K) and the parity bar is
+// 0.01 K, but the optical depth must be carried in FP64: exp(-tau) turns an absolute error of tau into a relative
+// error of every later term, and a float32 running sum over ~500 segments loses 1e-5.  So tau stays in FP64 and
+// the rest moves to the FP32 and SFU pipes, which idle in the FP64 kernel -- and the 8 KB exponential table with
+// its bank-conflicting lookups (about half of the FP64 kernel's shared-memory wavefronts) disappears:
+//   phase B (tau >= 2^-RB_RTM_SMALL_LOG), per (ray, freq, segment)
+//     t   = fma(asum, ds, t)                              FP64
+//     nd  = fma(t, -2^23 log2 e, 2^52 + 2^51 + 0x3F000000)  FP64: low word ni = k 2^23 + x + 0x3F000000, x in [0, 2^23)
+//     y   = (ni & 0x7FFFFF) | 0x3F800000                  LOP3: the float 1 + x 2^-23, built from the bits of x (no
+//                                                         FP64 -> FP32 conversion: those run at a quarter of the DFMA rate)
+//     e   = ex2.approx(y) as bits + ni - y                MUFU.EX2 + IADD3: 2^(1 + x 2^-23) scaled by 2^(k-1)
+//     w   = e (ds_i + ds_i+1);  iW += a' w;  Tb += T a' w        FP32 (FADD, FMUL, 2 FFMA) on float copies of ds
+//                                                         (geometry kernel) and of the operands (prepare kernel)
+//   phase A (tau < 2^-RB_RTM_SMALL_LOG, half of the executed steps): everything in FP32, tau included (its absolute
+//     error stays below 1e-8 there), exp(-t) = 1 - t + t^2/2 (truncation t^3/6 < 2^-26 for t < 2^-8).
+// The FP32 partial sums of one chunk (<= 32 segments) are added to FP64 accumulators at the end of the chunk.
+// Shared-memory wavefronts per (warp, segment): 2.25 in phase A, 4.25 in phase B (FP64 kernel: 4.5 / ~8.5).
+//
+// Operand rows (rt_prepare_mixed_kernel): 32 bytes per frequency, 256 bytes per (frequency group, segment):
+//   { double asum | float a' | float T a' || float a' | float T a' | float asum | 0 }     (all x 0.5e5)
+// phase B reads the first 16 bytes, phase A the second.
+// Shared-memory stage (x 2): ds tile 32 x 32 doubles | 32 operand rows | float ds tile 33 x 32 floats = 20.1 KB.
+#ifndef RB_RTM_CTAS
+#define RB_RTM_CTAS 4
+#endif
+#ifndef RB_RTM_SMALL_LOG
+#define RB_RTM_SMALL_LOG 8
+#endif
+constexpr int kMxChunk = 32;
+constexpr int kMxRow = 256;                               // bytes per operand row
+constexpr int kMxTileD = kMxChunk * 32 * 8;               // FP64 segment lengths
+constexpr int kMxTileP = kMxChunk * kMxRow;               // operand rows
+constexpr int kMxTileF = (kMxChunk + 1) * 32 * 4;         // float segment lengths, one extra row (ds_i+1 of the last)
+constexpr int kMxStage = kMxTileD + kMxTileP + kMxTileF;
+constexpr size_t kMixedSmemBytes = 2 * (size_t)kMxStage;
+static_assert(kMxTileD == 2 * 4096 && kMxTileP == 2 * 4096 && kMxTileF == 4096 + 128 && kMxStage % 16 == 0,
+              "the copy plan below is written for these sizes");
+constexpr double kMxTauMax = 85.0;   // 2^(k-1) stays a normal float while tau log2 e <= 126
+
+struct alignas(16) MxOperand {
+  double asum;                  // (a_i + a_i+1) 0.5e5
+  float ay, az;                 // a_i+1 0.5e5,  T_i+1 a_i+1 0.5e5   (an aligned pair: one FFMA2 operand)
+  float ay_f, az_f;             // the same pair again, for phase A's 16-byte read
+  float asum_f, pad;
+};
+static_assert(sizeof(MxOperand) == 32, "operand layout");
+
+__global__ void rt_prepare_mixed_kernel(const double* __restrict__ alpha, const double* __restrict__ T, int L, int F,
+                                        int ngroups, MxOperand* __restrict__ prepm) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Lm1 = L - 1;
+  if (idx >= ngroups * Lm1 * 8) return;
+  const int fl = idx & 7;
+  const int i = (idx >> 3) % Lm1;
+  const int fg = (idx >> 3) / Lm1;
+  const int f = fg * 8 + fl;
+  double vx = 0.0, vy = 0.0, vz = 0.0;
+  if (f < F) {
+    const double kHalfCm = 0.5 * kKmToCm;
+    const double a0 = alpha[(size_t)i * F + f], a1 = alpha[(size_t)(i + 1) * F + f];
+    vx = (a0 + a1) * kHalfCm; vy = a1 * kHalfCm; vz = (T[i + 1] * a1) * kHalfCm;
+  }
+  MxOperand o;
+  o.asum = vx; o.ay = (float)vy; o.az = (float)vz;
+  o.ay_f = (float)vy; o.az_f = (float)vz; o.asum_f = (float)vx; o.pad = 0.0f;
+  prepm[idx] = o;                                            // idx = (fg (L-1) + i) 8 + fl
+}
+
+// packed FP32 pairs (sm_100 FFMA2 / FMUL2): one issue slot for two operations
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// one 16-byte shared-memory read that ptxas cannot split into narrower ones (a split costs wavefronts: the
+// kernel's scarcest resource after issue slots is the 128 B/clk shared-memory crossbar)
+__device__ __forceinline__ ulonglong2 lds128(const void* p) {
+  ulonglong2 v;
+  asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
+
+// exp(-tau) as a float for 0 <= tau <= kMxTauMax (see the header comment);
+// cA = -2^23 log2 e, cM = 2^52 + 2^51 + 0x3F000000, fmask = 0x7FFFFF in a register (one LOP3 does the and-or)
+__device__ __forceinline__ float exp_neg_mixed(double tau, double cA, double cM, unsigned fmask) {
+  const unsigned ni = (unsigned)__double2loint(fma(tau, cA, cM));
+  unsigned y;
+  asm("lop3.b32 %0, %1, %2, 0x3F800000, 0xEA;" : "=r"(y) : "r"(ni), "r"(fmask));   // (ni & fmask) | 0x3F800000
+  float ev;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ev) : "f"(__uint_as_float(y)));
+  return __uint_as_float(__float_as_uint(ev) + ni - y);
+}
+
+__global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kernel(const __grid_constant__ RtK k) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int S = k.L - 1;
+  unsigned tile = blockIdx.y + (unsigned)k.progress.shift;
+  if (tile >= gridDim.y) tile -= gridDim.y;
+  const long long r = (long long)tile * 32 + threadIdx.x;
+  const int f = blockIdx.x * 8 + threadIdx.y;
+  const bool valid = (r < k.R) && (f < k.F);
+  const int n = valid ? k.nseg[r] : -1;
+  const bool nanray = valid && k.nanflag[r] != 0;
+  const int steps = (valid && !nanray) ? n - 1 : 0;        // brightness.py:65: i = 0 .. len(ds)-2
+
+  // copy plan of one chunk: 2 + 2 + 1 rounds of 256 x 16 bytes and 8 extra pieces, each stream one contiguous
+  // piece of global memory; unchecked like the FP64 kernel's (rows past the end of a tile are never consumed,
+  // the slabs carry kRtSlackBytes of slack)
+  const char* src_d = reinterpret_cast<const char*>(k.ds + (size_t)tile * S * 32) + tid * 16;
+  const char* src_p = reinterpret_cast<const char*>(k.prepm) + (size_t)blockIdx.x * S * kMxRow + tid * 16;
+  const char* src_f = reinterpret_cast<const char*>(k.dsf + (size_t)tile * S * 32) + tid * 16;
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(s_raw) + tid * 16;
+  auto issue = [&](int c) {
+    const unsigned o = dst + ((c & 1) ? (unsigned)kMxStage : 0u);
+    cp_rounds<2>(o, src_d);
+    cp_rounds<2>(o + kMxTileD, src_p);
+    cp_async16_at<0>(o + kMxTileD + kMxTileP, src_f);
+    if (tid < 8) cp_async16_at<4096>(o + kMxTileD + kMxTileP, src_f);
+    cp_async_commit();
+    src_d += kMxTileD;
+    src_p += kMxTileP;
+    src_f += kMxChunk * 32 * 4;
+  };
+  bool live = steps > 0;
+  const bool any_live = __syncthreads_or(live);
+  if (any_live) issue(0);
+
+  // loop-invariant constants fetched into registers (see pin()): c_mxc = {cA, cM}
+  const double cA = pin(c_mxc + 0), cM = pin(c_mxc + 1);
+  unsigned fmask;
+  asm volatile("mov.b32 %0, 0x007FFFFF;" : "=r"(fmask));
+  constexpr float kSmallF = 1.0f / (float)(1 << RB_RTM_SMALL_LOG);
+  const double cutd = fmin(k.tau_cut, kMxTauMax);
+  const int cut_hi = __double2hiint(cutd);                 // positive doubles order like their high words
+  double tau = 0.0, iW = 0.0, Tb = 0.0;
+  float tauf = 0.0f;
+  unsigned long long acc = 0ull;                            // packed FP32 {sum a' w, sum T a' w} of the current chunk
+  int i = 0, ia = 0;
+  bool stop = false;
+  bool small = cutd > (double)kSmallF;                     // phase A ignores tau_cut: only run it below the cut
+
+  for (int c = 0; any_live; ++c) {
+    cp_async_wait<0>();                                    // this thread's pieces of chunk c have landed
+    if (!__syncthreads_or(live)) break;                    // ... everybody's have; chunk c-1 is fully consumed
+    issue(c + 1);                                          // refill the buffer chunk c-1 used
+    if (live) {
+      const unsigned char* st = s_raw + (c & 1) * kMxStage;
+      const double* dp = reinterpret_cast<const double*>(st) + threadIdx.x;
+      const MxOperand* qp = reinterpret_cast<const MxOperand*>(st + kMxTileD) + threadIdx.y;
+      const float* fp = reinterpret_cast<const float*>(st + kMxTileD + kMxTileP) + threadIdx.x;
+      const int m = min(kMxChunk, steps - i);
+      int u = 0;
+      if (small) {
+        // phase A: all FP32, groups of 4 segments; the group that reaches 2^-RB_RTM_SMALL_LOG is left to phase B
+#pragma unroll 1
+        for (; u + 4 <= m; u += 4, fp += 4 * 32, qp += 4 * 8) {
+          float d[5], t[4];
+          ulonglong2 q[4];                                   // .x = {a', T a'} (FFMA2 operand), .y = {asum, 0}
+#pragma unroll
+          for (int j = 0; j < 5; ++j) d[j] = fp[j * 32];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[j] = lds128(&qp[j * 8].ay_f);
+          t[0] = fmaf(__uint_as_float((unsigned)q[0].y), d[0], tauf);
+#pragma unroll
+          for (int j = 1; j < 4; ++j) t[j] = fmaf(__uint_as_float((unsigned)q[j].y), d[j], t[j - 1]);
+          if (!(t[3] < kSmallF)) { small = false; break; }   // also leaves on NaN
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            // two segments per packed instruction: w = (1 - t + t^2/2) (ds_j + ds_j+1)
+            const unsigned long long tt = pack2(t[j], t[j + 1]);
+            const unsigned long long pp = ffma2(ffma2(tt, pack2(0.5f, 0.5f), pack2(-1.0f, -1.0f)), tt, pack2(1.0f, 1.0f));
+            float w0, w1;
+            unpack2(fmul2(pp, pack2(d[j] + d[j + 1], d[j + 1] + d[j + 2])), w0, w1);
+            acc = ffma2(q[j].x, pack2(w0, w0), acc);
+            acc = ffma2(q[j + 1].x, pack2(w1, w1), acc);
+          }
+          tauf = t[3];
+        }
+        ia += u;
+        if (u < m) small = false;                            // chunk remainder (end of the ray): one by one below
+        if (!small) tau = (double)tauf;
+      }
+      if (!small) {
+        // phase B: FP64 optical depth, SFU exponential, FP32 weights
+        dp += u * 32;
+#pragma unroll 1
+        for (; u + 4 <= m; u += 4, dp += 4 * 32, fp += 4 * 32, qp += 4 * 8) {
+          double t[4];
+          float d[5];
+          unsigned long long qa[4];                           // {a', T a'}
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // one 16-byte read: {double asum, float a', float T a'}
+            const ulonglong2 q = lds128(&qp[j * 8].asum);
+            qa[j] = q.y;
+            t[j] = fma(__longlong_as_double((long long)q.x), dp[j * 32], j ? t[j > 0 ? j - 1 : 0] : tau);
+          }
+          if (__double2hiint(t[3]) >= cut_hi) break;          // tau_cut (or a NaN) inside this group: one by one below
+#pragma unroll
+          for (int j = 0; j < 5; ++j) d[j] = fp[j * 32];
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            float w0, w1;
+            unpack2(fmul2(pack2(exp_neg_mixed(t[j], cA, cM, fmask), exp_neg_mixed(t[j + 1], cA, cM, fmask)),
+                          pack2(d[j] + d[j + 1], d[j + 1] + d[j + 2])), w0, w1);
+            acc = ffma2(qa[j], pack2(w0, w0), acc);
+            acc = ffma2(qa[j + 1], pack2(w1, w1), acc);
+          }
+          tau = t[3];
+        }
+        // chunk remainder / the group that crosses tau_cut: one segment at a time; the crossing step is included
+        for (; u < m; dp += 32, fp += 32, qp += 8) {
+          tau = fma(qp->asum, dp[0], tau);
+          const bool cross = __double2hiint(tau) >= cut_hi;   // true for NaN as well (tau stays NaN -> NaN output)
+          const double tc = cross ? fmin(tau, kMxTauMax) : tau;
+          const float w = exp_neg_mixed(tc, cA, cM, fmask) * (fp[0] + fp[32]);
+          acc = ffma2(pack2(qp->ay, qp->az), pack2(w, w), acc);
+          ++u;
+          if (cross) { stop = true; break; }
+        }
+      }
+      i += u;                                                // segments integrated so far (feeds rb_count_steps)
+      live = !stop && i < steps;
+      float iWf, Tbf;                                        // FP32 partial sums of this chunk -> FP64 accumulators
+      unpack2(acc, iWf, Tbf);
+      iW += (double)iWf;
+      Tb += (double)Tbf;
+      acc = 0ull;
+    }
+  }
+  cp_async_wait<0>();
+  if (small) tau = (double)tauf;                             // a NaN optical depth that never left phase A
+  if (k.step_counter) {
+    unsigned long long done = (unsigned long long)i;
+    unsigned long long done_a = (unsigned long long)ia;
+    for (int o = 16; o > 0; o >>= 1) {
+      done += __shfl_down_sync(0xffffffffu, done, o);
+      done_a += __shfl_down_sync(0xffffffffu, done_a, o);
+    }
+    if (threadIdx.x == 0) { atomicAdd(k.step_counter, done); atomicAdd(k.step_counter + 1, done_a); }
+  }
+  if (valid) {
+    double vout, wout = iW;
+    if (n < 0) vout = kTcmb;                                 // off planet (brightness.py:46-51)
+    else if (nanray || tau != tau) vout = wout = nan("");    // NaN segment below the tangent shell / NaN alpha
+    else vout = (Tb < kTcmb) ? kTcmb : Tb / iW;              // brightness.py:109-113
+    const size_t o = (size_t)r * k.F + f;
+    if (k.out_f32) reinterpret_cast<float*>(k.out_Tb)[o] = (float)vout;
+    else reinterpret_cast<double*>(k.out_Tb)[o] = vout;
+    if (k.out_intW) k.out_intW[o] = (n < 0) ? 0.0 : wout;
+  }
+  if (k.progress.done) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      int c = 0;
+      while (c + 1 < k.progress.nchunks && (int)blockIdx.y >= k.progress.cut[c + 1]) ++c;
+      atomicAdd(k.progress.done + c, 1u);
+    }
+  }
+}
 }  // namespace
 
 int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
   GeoK k{};
   k.L = g.L; k.radius = g.radius; k.n0 = g.n0; k.n1 = g.n1; k.q = g.q;
   k.cz = g.rot[0]; k.sz = g.rot[1]; k.cx = g.rot[2]; k.sx = g.rot[3];
-  k.limb = g.limb; k.R = g.R; k.Rpad = g.Rpad; k.b = g.b; k.ds = g.ds; k.nseg = g.nseg; k.nanflag = g.nanflag;
+  k.limb = g.limb; k.R = g.R; k.Rpad = g.Rpad; k.b = g.b; k.ds = g.ds; k.dsf = g.dsf; k.nseg = g.nseg; k.nanflag = g.nanflag;
   const int threads = 128;
   const long long blocks = (g.R + threads - 1) / threads;
   RB_CUDA(ctx, rb_time_begin(ctx, 1));
@@ -875,15 +1165,26 @@ int rb_launch_ds_to_slab(rb_context* ctx, const double* in, int64_t R, int64_t R
 
 // Decide the integration path for a request of R_total rays and, for the rays-major path, build the
 // per-(layer,freq) operand slab once (shared by all ray chunks of the request).
-int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total, bool profile, RtPrep* out) {
+int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total, bool profile, bool have_pairs,
+                  RtPrep* out) {
   out->use_rays = !profile && !rt->disc_average && R_total >= 512;
+  out->mixed = out->use_rays && have_pairs && ctx->rt_precision == RB_RT_MIXED;
   out->prep = nullptr;
   if (!out->use_rays) return RB_OK;
   const int F = rt->n_freqs;
   const int ngroups = (F + 7) / 8;
-  void* scratch;
-  RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (L - 1) * 8 * sizeof(double4) + kRtSlackBytes, &scratch));
   const int nel = ngroups * (L - 1) * 8;
+  void* scratch;
+  if (out->mixed) {
+    RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (L - 1) * kMxRow + kRtSlackBytes, &scratch));
+    rt_prepare_mixed_kernel<<<(nel + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ngroups,
+                                                                         (MxOperand*)scratch);
+    RB_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    out->prep = scratch;
+    return RB_OK;
+  }
+  RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (L - 1) * 8 * sizeof(double4) + kRtSlackBytes, &scratch));
   if (!ctx->exp_tab) {
     RB_CUDA(ctx, cudaMalloc(&ctx->exp_tab, kExpTab * sizeof(double)));
     exp_tab_init_kernel<<<(kExpTab + 255) / 256, 256, 0, ctx->stream>>>(ctx->exp_tab);
@@ -919,12 +1220,28 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     else rt_integrate_kernel<1, false, false><<<grid, block, 0, ctx->stream>>>(k);
   } else {
     // rays-major mapping: CTAs of 32 rays x 8 frequencies; operands prepared by rb_rt_prepare
-    k.prep = (const double4*)prep.prep;
     k.step_counter = ctx->step_counter;
-    k.exp_tab = ctx->exp_tab;
     if (progress) k.progress = *progress;
     dim3 block(32, 8), grid((k.F + 7) / 8, (unsigned)((g.R + 31) / 32));
     if (grid.y > 65535) return rb_fail(ctx, RB_ERR_INVALID, "rt: more than 2M rays per launch are not supported");
+    if (prep.mixed) {
+      if (!g.dsf) return rb_fail(ctx, RB_ERR_INVALID, "rt: mixed-precision integration without the float ds slab");
+      k.dsf = g.dsf;
+      k.prepm = prep.prep;
+      static bool opted_in_m[64] = {false};
+      if (kMixedSmemBytes > 48 * 1024 && !opted_in_m[ctx->device & 63]) {
+        RB_CUDA(ctx, cudaFuncSetAttribute(rt_integrate_rays_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kMixedSmemBytes));
+        opted_in_m[ctx->device & 63] = true;
+      }
+      rt_integrate_rays_mixed_kernel<<<grid, block, kMixedSmemBytes, ctx->stream>>>(k);
+      RB_CUDA(ctx, cudaGetLastError());
+      RB_CUDA(ctx, rb_time_end(ctx, 2));
+      ctx->launches += 1;
+      return RB_OK;
+    }
+    k.prep = (const double4*)prep.prep;
+    k.exp_tab = ctx->exp_tab;
     constexpr size_t smem = kExpTab * sizeof(double) + kRaysSmemBytes;
     static_assert(smem <= 227 * 1024, "shared memory limit");
     static bool opted_in[64] = {false};

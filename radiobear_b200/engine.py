@@ -21,6 +21,17 @@ from .hostmem import PinnedPool, pinned_pool  # noqa: E402,F401
 
 
 
+def set_rt_precision(precision, ctx=None):
+    """Arithmetic of the batched ray integration: 'f64' (every operation in FP64) or 'mixed' (FP64 optical
+    depth, SFU exponential, FP32 weights; |dTb| ~ one float32 ulp of Tb -- include/radiobear_b200.h).  The
+    library starts in the mode RB_RT_PRECISION names (default 'f64')."""
+    (ctx or _lib.get_context()).set_rt_precision(precision)
+
+
+def rt_precision(ctx=None):
+    return (ctx or _lib.get_context()).rt_precision()
+
+
 UNITS = {'invcm': 0, 'dBperkm': 1}
 COSHAPE = {'voigt': 0, 'vvw': 1, 'diff': 2}
 

@@ -14,10 +14,25 @@ pytestmark = pytest.mark.gpu
 TB_TOL = 0.01
 
 
+MIXED_TOL = 1e-3      # K; measured ~3e-5 K (one float32 ulp of Tb), asserted well inside the 0.01 K bar
+
+
 @pytest.fixture(scope='module')
 def eng():
+    """The engine with the batched integration in FP64 (the exactness assertions below: 1e-7 K, bit identity);
+    the mixed-precision integration has its own tests at the end of the file."""
     from radiobear_b200 import engine
-    return engine
+    before = engine.rt_precision()
+    engine.set_rt_precision('f64')
+    yield engine
+    engine.set_rt_precision(before)
+
+
+@pytest.fixture()
+def mixed(eng):
+    eng.set_rt_precision('mixed')
+    yield eng
+    eng.set_rt_precision('f64')
 
 
 def geom(a):
@@ -319,3 +334,108 @@ def test_chunked_copy_out_equals_single_copy(eng):
     finally:
         ctx.set_rt_chunks(0)
     assert np.isnan(ref['Tb']).any() and (ref['Tb'] == 2.725).any() and (ref['Tb'] > 100.0).any()
+
+
+# ---- mixed-precision integration (rb_set_rt_precision(ctx, RB_RT_MIXED)) -----------------------------------------
+def _random_disc_points(a, n, seed, rmax=1.02):
+    rng = np.random.default_rng(seed)
+    th = rng.uniform(0, 2 * np.pi, n)
+    rad = np.sqrt(rng.uniform(0, rmax, n))
+    q = float(a['Rpol']) / float(a['Req'])
+    return np.ascontiguousarray(np.stack([rad * np.cos(th), rad * np.sin(th) * q], axis=1))
+
+
+def test_mixed_precision_matches_f64_kernel(eng):
+    """FP64 optical depth + SFU exponential + FP32 weights against the all-FP64 kernel on the same rays: Tb within
+    MIXED_TOL (0.01 K is the bar), integrated_W within 1e-5, NaN rays and off-planet rays at identical pixels,
+    tau_cut variants, ragged ray / frequency counts, float32 output."""
+    a = golden('atm_jupiter.npz')
+    im = golden('image_c4.npz')
+    C = keymap(a['C_keys'])
+    T = a['gas'][C['T']]
+    b = _random_disc_points(a, 3000, 17)
+    assert eng.rt_precision() == 'f64'
+    worst = 0.0
+    for freqs in (im['freqs'], im['freqs'][::3], np.array([22.0])):        # 64 / 22 / 1 frequencies (ragged groups of 8)
+        slab = _slab(eng, a, freqs)
+        ref = eng.rt_batch(b=b, alpha_slab=slab, T=T, want_intW=True, **geom(a))
+        ref = {k: v.copy() for k, v in ref.items()}
+        ref_cut5 = eng.rt_batch(b=b, alpha_slab=slab, T=T, tau_cut=5.0, **geom(a))['Tb'].copy()
+        eng.set_rt_precision('mixed')
+        try:
+            assert eng.rt_precision() == 'mixed'
+            got = eng.rt_batch(b=b, alpha_slab=slab, T=T, want_intW=True, **geom(a))
+            got = {k: v.copy() for k, v in got.items()}
+            nocut = eng.rt_batch(b=b, alpha_slab=slab, T=T, tau_cut=0.0, **geom(a))['Tb'].copy()
+            cut5 = eng.rt_batch(b=b, alpha_slab=slab, T=T, tau_cut=5.0, **geom(a))['Tb'].copy()
+            f32 = eng.rt_batch(b=b, alpha_slab=slab, T=T, out_f32=True, **geom(a))['Tb'].copy()
+            ragged = eng.rt_batch(b=b[:1025], alpha_slab=slab, T=T, **geom(a))['Tb'].copy()
+        finally:
+            eng.set_rt_precision('f64')
+        nan = np.isnan(ref['Tb'])
+        assert np.array_equal(np.isnan(got['Tb']), nan) and nan.any()
+        assert np.array_equal(got['Tb'] == 2.725, ref['Tb'] == 2.725) and (ref['Tb'] == 2.725).any()
+        err = np.abs(got['Tb'] - ref['Tb'])[~nan]
+        worst = max(worst, float(err.max()))
+        assert err.max() < MIXED_TOL
+        ok = ~np.isnan(ref['integrated_W']) & (ref['integrated_W'] > 0)
+        assert np.max(np.abs(got['integrated_W'][ok] / ref['integrated_W'][ok] - 1.0)) < 1e-5
+        assert np.max(np.abs(nocut - got['Tb'])[~nan]) < 1e-6            # e^-50 terms are invisible here as well
+        assert np.max(np.abs(cut5 - ref_cut5)[~nan]) < MIXED_TOL          # same tau_cut semantics as the FP64 kernel
+        assert np.array_equal(f32[~nan], got['Tb'][~nan].astype(np.float32))
+        assert np.array_equal(ragged, got['Tb'][:1025], equal_nan=True)   # results do not depend on the batch
+    assert worst < MIXED_TOL
+
+
+def test_mixed_precision_c4_subset_against_reference(mixed):
+    """Config C4 pixels the reference computed (on-disc, NaN ring, off-disc), padded above the 512-ray switch so that
+    they run through the mixed-precision rays-major kernel: the north-star bar (0.01 K) against the reference."""
+    eng = mixed
+    a = golden('atm_jupiter.npz')
+    im = golden('image_c4.npz')
+    C = keymap(a['C_keys'])
+    slab = _slab(eng, a, im['freqs'])
+    grid = im['grid']
+    bsub = np.array([[grid[ix], grid[iy]] for iy, ix in im['pick_iy_ix']])
+    pad = _random_disc_points(a, 700, 3)
+    res = eng.rt_batch(b=np.concatenate([bsub, pad]), alpha_slab=slab, T=a['gas'][C['T']], **geom(a))['Tb'][:len(bsub)]
+    ref = im['tb']
+    finite = ~np.isnan(ref).any(axis=1)
+    assert np.array_equal(np.isnan(res).any(axis=1), ~finite)
+    assert np.max(np.abs(res[finite] - ref[finite])) < MIXED_TOL < TB_TOL
+
+
+def test_mixed_precision_pipelines_are_bit_identical(mixed):
+    """Prefetched geometry, the chunked copy-out pipeline and the plain launch give the same bits in mixed mode."""
+    from radiobear_b200 import _lib
+    eng = mixed
+    a = golden('atm_jupiter.npz')
+    C = keymap(a['C_keys'])
+    T = a['gas'][C['T']]
+    slab = _slab(eng, a, np.array([1.5, 9.0, 22.0, 44.0, 95.0]))
+    R = 16384 + 4321
+    b = np.ascontiguousarray(np.random.default_rng(5).uniform(-1.05, 1.05, (R, 2)))
+    g = geom(a)
+    radius = np.ascontiguousarray(g.pop('radius'), dtype=np.float64)
+    ctx = _lib.get_context()
+    try:
+        ctx.set_rt_chunks(1)
+        ref = eng.rt_batch(radius=radius, b=b, alpha_slab=slab, T=T, out_f32=True, **g)['Tb'].copy()
+        for nch in (0, 7):
+            ctx.set_rt_chunks(nch)
+            got = eng.rt_batch(radius=radius, b=b, alpha_slab=slab, T=T, out_f32=True, **g)['Tb']
+            assert np.array_equal(got, ref, equal_nan=True)
+        eng.geometry_prefetch(radius, g['refr_index'], b, g['Req'], g['Rpol'], g['orientation'], g['gtype'], g['limb'])
+        got = eng.rt_batch(radius=radius, b=b, alpha_slab=slab, T=T, out_f32=True, **g)['Tb']
+        assert np.array_equal(got, ref, equal_nan=True)
+        # a geometry prefetched in the other precision has the other slab layout: the switch drops it
+        eng.set_rt_precision('f64')
+        eng.geometry_prefetch(radius, g['refr_index'], b, g['Req'], g['Rpol'], g['orientation'], g['gtype'], g['limb'])
+        eng.set_rt_precision('mixed')
+        got = eng.rt_batch(radius=radius, b=b, alpha_slab=slab, T=T, out_f32=True, **g)['Tb']
+        assert np.array_equal(got, ref, equal_nan=True)
+    finally:
+        ctx.set_rt_chunks(0)
+    assert np.isnan(ref).any() and (ref == np.float32(2.725)).any() and (ref > 100.0).any()
+    with pytest.raises(ValueError):
+        eng.set_rt_precision('f16')
