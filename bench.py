@@ -400,6 +400,40 @@ def run_gpu(args):
     steps_executed = ctx.count_steps(False)
     steps_small = ctx.count_small_steps()
 
+    # ---- the same step with the integration in mixed precision (rb_set_rt_precision; not the headline) ----------
+    rt_mixed = None
+    if precision == 'f64' and os.environ.get('RB_BENCH_SKIP_MIXED') is None:
+        tb_ref = tb_t.clone()
+        ctx.set_rt_precision('mixed')
+        for _ in range(3):
+            step()
+        barrier()
+        km0 = ctx.kernel_timed_count('rt')
+        evm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush.zero_()
+            evm[i][0].record()
+            step()
+            evm[i][1].record()
+        barrier()
+        tm = torch.tensor([sum(a.elapsed_time(b) for a, b in evm)], dtype=torch.float64, device=dev)
+        ok = ~torch.isnan(tb_ref)
+        same_nan = bool(torch.equal(torch.isnan(tb_t), torch.isnan(tb_ref)))
+        dmax = torch.tensor([float((tb_t[ok].double() - tb_ref[ok].double()).abs().max()) if bool(ok.any()) else 0.0],
+                            dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+        hm = ctx.kernel_ms_history('rt', min(ctx.kernel_timed_count('rt') - km0, 256))
+        ctx.set_rt_precision('f64')
+        ms_mixed = float(tm.item()) / args.steps
+        rt_mixed = {'precision': 'mixed: FP64 optical depth, SFU ex2, FP32 (FFMA2) weights and chunk sums, FP64 totals',
+                    'ms_per_step': ms_mixed, 'value': n_on * F / (ms_mixed * 1e-3), 'unit': UNIT,
+                    'rt_integrate_ms': float(np.mean(hm)) if len(hm) else None,
+                    'max_abs_dTb_K_vs_f64': float(dmax.item()), 'nan_pattern_equal': same_nan,
+                    'note': 'same step, same inputs, same run; float32 Tb outputs compared (1 ulp of Tb = 3e-5 K at 300-500 K); '
+                            'parity bar 0.01 K; opt-in (RB_RT_PRECISION=mixed / rb_set_rt_precision), not the headline'}
+
     # ---- end to end through the public API (host buffers) ----------------------------------------
     planet = Planet('jupiter', atmosphere=atm, verbose=False)
     # bytes this rank moves per Planet.run: impact points, atmosphere, alpha slab in; its Tb rows + alpha slab out
@@ -481,7 +515,7 @@ def run_gpu(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic image grid over the Jupiter default atmosphere fixture',
+            'dtype': 'f64' if precision == 'f64' else 'f64 optical depth + f32 weights (mixed)', 'data': 'synthetic image grid over the Jupiter default atmosphere fixture',
             'config': {'workload': WORKLOAD, 'pixels': 'on-disc', 'on_disc_pixels': n_on, 'nan_limb_pixels': n_nan,
                        'all_pixels': n_all, 'layers': L, 'freqs': F, 'sharding': 'image rows balanced by on-disc pixels; output stays row-sharded in HBM (no collective); e2e: every rank copies its rows into one shared pinned host image',
                        'l2': 'flushed between timed steps (256 MiB write, untimed); ds slab (0.94 GB) exceeds L2',
@@ -498,6 +532,8 @@ def run_gpu(args):
         }
         if cpu_v is not None:
             line['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': cpu_desc}
+        if rt_mixed is not None:
+            line['rt_mixed'] = rt_mixed
         if world == 1:
             a5 = alpha_c5(ctx, dev)
             a5['fp64_peak_tflops'] = fp64_peak
