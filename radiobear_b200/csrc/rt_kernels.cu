@@ -889,6 +889,11 @@ constexpr size_t kMixedSmemBytes = 2 * (size_t)kMxStage;
 static_assert(kMxTileD == 2 * 4096 && kMxTileP == 2 * 4096 && kMxTileF == 4096 + 128 && kMxStage % 16 == 0,
               "the copy plan below is written for these sizes");
 constexpr double kMxTauMax = 85.0;   // 2^(k-1) stays a normal float while tau log2 e <= 126
+// Every term beyond tau = 25 is below e^-25 (1.4e-11) x T (<= 2000 K) x dtau, i.e. < 3e-8 K in Tb: three orders below
+// the resolution of this mode's FP32 partial sums (1e-5 K), so the mixed kernel never integrates deeper than that
+// whatever tau_cut asks for (the FP64 kernel's default, 50, is the same argument at FP64 resolution).  7 % of the
+// segment-steps of C4 lie between tau = 25 and tau = 50.
+constexpr double kMxTauCut = 25.0;
 
 struct alignas(16) MxOperand {
   double asum;                  // (a_i + a_i+1) 0.5e5
@@ -998,7 +1003,7 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
   unsigned fmask;
   asm volatile("mov.b32 %0, 0x007FFFFF;" : "=r"(fmask));
   constexpr float kSmallF = 1.0f / (float)(1 << RB_RTM_SMALL_LOG);
-  const double cutd = fmin(k.tau_cut, kMxTauMax);
+  const double cutd = fmin(k.tau_cut, kMxTauCut);
   const int cut_hi = __double2hiint(cutd);                 // positive doubles order like their high words
   double tau = 0.0, iW = 0.0, Tb = 0.0;
   float tauf = 0.0f;
