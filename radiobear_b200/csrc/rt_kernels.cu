@@ -857,7 +857,8 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
 // the rest moves to the FP32 and SFU pipes, which idle in the FP64 kernel -- and the 8 KB exponential table with
 // its bank-conflicting lookups (about half of the FP64 kernel's shared-memory wavefronts) disappears:
 //   phase B (tau >= 2^-RB_RTM_SMALL_LOG), per (ray, freq, segment)
-//     t   = fma(asum, ds, t)                              FP64
+//     t   = fma(asum, ds, t)                              FP64; ds is the float copy widened with two integer
+//                                                         instructions (its 2^-24 rounding moves tau by < 1e-8)
 //     nd  = fma(t, -2^23 log2 e, 2^52 + 2^51 + 0x3F000000)  FP64: low word ni = k 2^23 + x + 0x3F000000, x in [0, 2^23)
 //     y   = (ni & 0x7FFFFF) | 0x3F800000                  LOP3: the float 1 + x 2^-23, built from the bits of x (no
 //                                                         FP64 -> FP32 conversion: those run at a quarter of the DFMA rate)
@@ -867,27 +868,31 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
 //   phase A (tau < 2^-RB_RTM_SMALL_LOG, half of the executed steps): everything in FP32, tau included (its absolute
 //     error stays below 1e-8 there), exp(-t) = 1 - t + t^2/2 (truncation t^3/6 < 2^-26 for t < 2^-8).
 // The FP32 partial sums of one chunk (<= 32 segments) are added to FP64 accumulators at the end of the chunk.
-// Shared-memory wavefronts per (warp, segment): 2.25 in phase A, 4.25 in phase B (FP64 kernel: 4.5 / ~8.5).
+// Shared-memory wavefronts per (warp, segment): 2 in phase A, 2.25 in phase B (FP64 kernel: 4.5 / ~8.5) -- the
+// 128 B/clk shared-memory pipe is what both kernels run out of first (ncu: l1tex data pipe 74-81 % busy).
 //
 // Operand rows (rt_prepare_mixed_kernel): 32 bytes per frequency, 256 bytes per (frequency group, segment):
 //   { double asum | float a' | float T a' || float a' | float T a' | float asum | 0 }     (all x 0.5e5)
 // phase B reads the first 16 bytes, phase A the second.
-// Shared-memory stage (x 2): ds tile 32 x 32 doubles | 32 operand rows | float ds tile 33 x 32 floats = 20.1 KB.
+// Shared-memory stage (x 2): kMxChunk operand rows | float ds tile (kMxChunk + 1) x 32 floats = 12.1 KB at 32
+// segments per chunk; the FP64 ds slab is not read at all.
 #ifndef RB_RTM_CTAS
 #define RB_RTM_CTAS 4
 #endif
 #ifndef RB_RTM_SMALL_LOG
 #define RB_RTM_SMALL_LOG 8
 #endif
-constexpr int kMxChunk = 32;
+#ifndef RB_RTM_CHUNK
+#define RB_RTM_CHUNK 32
+#endif
+constexpr int kMxChunk = RB_RTM_CHUNK;                    // segments per staged tile: 32 or 64
+static_assert(kMxChunk == 32 || kMxChunk == 64, "copy plan below");
 constexpr int kMxRow = 256;                               // bytes per operand row
-constexpr int kMxTileD = kMxChunk * 32 * 8;               // FP64 segment lengths
 constexpr int kMxTileP = kMxChunk * kMxRow;               // operand rows
 constexpr int kMxTileF = (kMxChunk + 1) * 32 * 4;         // float segment lengths, one extra row (ds_i+1 of the last)
-constexpr int kMxStage = kMxTileD + kMxTileP + kMxTileF;
+constexpr int kMxStage = kMxTileP + kMxTileF;
 constexpr size_t kMixedSmemBytes = 2 * (size_t)kMxStage;
-static_assert(kMxTileD == 2 * 4096 && kMxTileP == 2 * 4096 && kMxTileF == 4096 + 128 && kMxStage % 16 == 0,
-              "the copy plan below is written for these sizes");
+static_assert(kMxTileP % 4096 == 0 && (kMxTileF - 128) % 4096 == 0 && kMxStage % 16 == 0, "the copy plan below is written for these sizes");
 constexpr double kMxTauMax = 85.0;   // 2^(k-1) stays a normal float while tau log2 e <= 126
 // Every term beyond tau = 25 is below e^-25 (1.4e-11) x T (<= 2000 K) x dtau, i.e. < 3e-8 K in Tb: three orders below
 // the resolution of this mode's FP32 partial sums (1e-5 K), so the mixed kernel never integrates deeper than that
@@ -952,6 +957,13 @@ __device__ __forceinline__ ulonglong2 lds128(const void* p) {
   return v;
 }
 
+// float -> double of a non-negative normal float with two integer instructions (F2F.F64.F32 runs at a quarter of the
+// DFMA rate): exponent rebias 127 -> 1023 and mantissa shift.  0 maps to 2^-127 (used only as a segment length: harmless).
+__device__ __forceinline__ double f2d_bits(float f) {
+  const unsigned b = __float_as_uint(f);
+  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+
 // exp(-tau) as a float for 0 <= tau <= kMxTauMax (see the header comment);
 // cA = -2^23 log2 e, cM = 2^52 + 2^51 + 0x3F000000, fmask = 0x7FFFFF in a register (one LOP3 does the and-or)
 __device__ __forceinline__ float exp_neg_mixed(double tau, double cA, double cM, unsigned fmask) {
@@ -976,21 +988,18 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
   const bool nanray = valid && k.nanflag[r] != 0;
   const int steps = (valid && !nanray) ? n - 1 : 0;        // brightness.py:65: i = 0 .. len(ds)-2
 
-  // copy plan of one chunk: 2 + 2 + 1 rounds of 256 x 16 bytes and 8 extra pieces, each stream one contiguous
-  // piece of global memory; unchecked like the FP64 kernel's (rows past the end of a tile are never consumed,
-  // the slabs carry kRtSlackBytes of slack)
-  const char* src_d = reinterpret_cast<const char*>(k.ds + (size_t)tile * S * 32) + tid * 16;
+  // copy plan of one chunk: kMxChunk / 16 rounds of 256 x 16 bytes for the operand rows, kMxChunk / 32 rounds and 8
+  // extra pieces for the float segments, each stream one contiguous piece of global memory; unchecked like the
+  // FP64 kernel's (rows past the end of a tile are never consumed, the slabs carry kRtSlackBytes of slack)
   const char* src_p = reinterpret_cast<const char*>(k.prepm) + (size_t)blockIdx.x * S * kMxRow + tid * 16;
   const char* src_f = reinterpret_cast<const char*>(k.dsf + (size_t)tile * S * 32) + tid * 16;
   const unsigned dst = (unsigned)__cvta_generic_to_shared(s_raw) + tid * 16;
   auto issue = [&](int c) {
     const unsigned o = dst + ((c & 1) ? (unsigned)kMxStage : 0u);
-    cp_rounds<2>(o, src_d);
-    cp_rounds<2>(o + kMxTileD, src_p);
-    cp_async16_at<0>(o + kMxTileD + kMxTileP, src_f);
-    if (tid < 8) cp_async16_at<4096>(o + kMxTileD + kMxTileP, src_f);
+    cp_rounds<kMxChunk / 16>(o, src_p);
+    cp_rounds<kMxChunk / 32>(o + kMxTileP, src_f);
+    if (tid < 8) cp_async16_at<kMxChunk * 128>(o + kMxTileP, src_f);
     cp_async_commit();
-    src_d += kMxTileD;
     src_p += kMxTileP;
     src_f += kMxChunk * 32 * 4;
   };
@@ -1018,9 +1027,8 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
     issue(c + 1);                                          // refill the buffer chunk c-1 used
     if (live) {
       const unsigned char* st = s_raw + (c & 1) * kMxStage;
-      const double* dp = reinterpret_cast<const double*>(st) + threadIdx.x;
-      const MxOperand* qp = reinterpret_cast<const MxOperand*>(st + kMxTileD) + threadIdx.y;
-      const float* fp = reinterpret_cast<const float*>(st + kMxTileD + kMxTileP) + threadIdx.x;
+      const MxOperand* qp = reinterpret_cast<const MxOperand*>(st) + threadIdx.y;
+      const float* fp = reinterpret_cast<const float*>(st + kMxTileP) + threadIdx.x;
       const int m = min(kMxChunk, steps - i);
       int u = 0;
       if (small) {
@@ -1055,22 +1063,21 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
       }
       if (!small) {
         // phase B: FP64 optical depth, SFU exponential, FP32 weights
-        dp += u * 32;
 #pragma unroll 1
-        for (; u + 4 <= m; u += 4, dp += 4 * 32, fp += 4 * 32, qp += 4 * 8) {
+        for (; u + 4 <= m; u += 4, fp += 4 * 32, qp += 4 * 8) {
           double t[4];
           float d[5];
           unsigned long long qa[4];                           // {a', T a'}
+#pragma unroll
+          for (int j = 0; j < 5; ++j) d[j] = fp[j * 32];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             // one 16-byte read: {double asum, float a', float T a'}
             const ulonglong2 q = lds128(&qp[j * 8].asum);
             qa[j] = q.y;
-            t[j] = fma(__longlong_as_double((long long)q.x), dp[j * 32], j ? t[j > 0 ? j - 1 : 0] : tau);
+            t[j] = fma(__longlong_as_double((long long)q.x), f2d_bits(d[j]), j ? t[j > 0 ? j - 1 : 0] : tau);
           }
           if (__double2hiint(t[3]) >= cut_hi) break;          // tau_cut (or a NaN) inside this group: one by one below
-#pragma unroll
-          for (int j = 0; j < 5; ++j) d[j] = fp[j * 32];
 #pragma unroll
           for (int j = 0; j < 4; j += 2) {
             float w0, w1;
@@ -1082,11 +1089,12 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
           tau = t[3];
         }
         // chunk remainder / the group that crosses tau_cut: one segment at a time; the crossing step is included
-        for (; u < m; dp += 32, fp += 32, qp += 8) {
-          tau = fma(qp->asum, dp[0], tau);
+        for (; u < m; fp += 32, qp += 8) {
+          const float d0 = fp[0];
+          tau = fma(qp->asum, f2d_bits(d0), tau);
           const bool cross = __double2hiint(tau) >= cut_hi;   // true for NaN as well (tau stays NaN -> NaN output)
           const double tc = cross ? fmin(tau, kMxTauMax) : tau;
-          const float w = exp_neg_mixed(tc, cA, cM, fmask) * (fp[0] + fp[32]);
+          const float w = exp_neg_mixed(tc, cA, cM, fmask) * (d0 + fp[32]);
           acc = ffma2(pack2(qp->ay, qp->az), pack2(w, w), acc);
           ++u;
           if (cross) { stop = true; break; }
