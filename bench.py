@@ -52,10 +52,12 @@ RT_FP64_INSTR_PER_SMALL_STEP = 7.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one rt_integrate_rays_kernel launch of this workload at N=1
 RT_DRAM_BYTES_N1 = 1088100000
 RT_DRAM_SOURCE = 'ncu --set full, profiles/r1_final_rt_integrate_rays_ncu_full.txt (1.014 GB read + 0.074 GB written)'
+RT_DRAM_BYTES_N1_MIXED = 645195776
+RT_DRAM_SOURCE_MIXED = 'ncu --set full, profiles/r1_mixed_rt_integrate_rays_mixed_ncu_full.txt (0.505 GB read + 0.140 GB written)'
 # SASS instructions (cuobjdump) and shared-memory wavefronts (128 B/clk/SM crossbar) per executed segment-step of the
 # two integration kernels, {precision: (phase A, phase B)}: the resources the kernels are actually short of
-RT_SASS_PER_STEP = {'f64': (12.75, 21.5), 'mixed': (10.0, 14.5)}
-RT_SMEM_WAVEFRONTS_PER_STEP = {'f64': (4.5, 8.5), 'mixed': (2.0, 4.25)}
+RT_SASS_PER_STEP = {'f64': (12.75, 21.5), 'mixed': (10.0, 15.25)}
+RT_SMEM_WAVEFRONTS_PER_STEP = {'f64': (4.5, 8.5), 'mixed': (2.0, 2.0)}
 RT_KERNEL = {'f64': 'rt_integrate_rays_kernel', 'mixed': 'rt_integrate_rays_mixed_kernel'}
 WORKLOAD = 'C4: Jupiter full image b=0.005 (601x601 px) x 64 freqs 1-100 GHz, 1000 layers, alpha+geometry+RT per step'
 
@@ -469,7 +471,8 @@ def run_gpu(args):
         n_on_rank = n_on_local
         # algorithmic bytes of one rt_integrate launch: ds slab read for the on-disc rays +
         # alpha slab + T + float32 Tb out for every pixel of the rank
-        rt_bytes = n_on_rank * S * 8 + F * L * 8 + L * 8 + len(pts) * F * 4
+        # (the mixed kernel reads the float copy of ds: 4 bytes per segment, and 32-byte operand rows per (layer, freq))
+        rt_bytes = n_on_rank * S * (8 if precision == 'f64' else 4) + F * L * (8 if precision == 'f64' else 32) + L * 8 + len(pts) * F * 4
         rt_steps_all = float(n_on_rank) * F * (S - 1)
         rt_flops = float(steps_executed - steps_small) * RT_FLOPS_PER_STEP + float(steps_small) * RT_FLOPS_PER_SMALL_STEP
         rt_instr = float(steps_executed - steps_small) * RT_FP64_INSTR_PER_STEP + float(steps_small) * RT_FP64_INSTR_PER_SMALL_STEP
@@ -481,8 +484,8 @@ def run_gpu(args):
         warp_cycles = n_sms * sm_hz * (rt_ms * 1e-3)          # SM-cycles of the launch
         roofline = {'bound': 'hbm', 'kernel': RT_KERNEL[precision], 'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9,
                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': rt_bytes / (rt_ms * 1e-3) / 1e9 / hbm_peak,
-                    'traffic': RT_DRAM_BYTES_N1 if (world == 1 and precision == 'f64') else None,
-                    'traffic_source': RT_DRAM_SOURCE if precision == 'f64' else None,
+                    'traffic': (RT_DRAM_BYTES_N1 if precision == 'f64' else RT_DRAM_BYTES_N1_MIXED) if world == 1 else None,
+                    'traffic_source': RT_DRAM_SOURCE if precision == 'f64' else RT_DRAM_SOURCE_MIXED,
                     'peak_source': peak_src, 'ms_per_launch': rt_ms, 'launches_per_step': rt_chunks,
                     'note': 'at F=64 the kernel is issue / shared-memory / FP64 bound, not HBM-bound (SURVEY 8d): see issue, smem, fp64',
                     # what actually binds: warp-instruction issue slots (4 schedulers per SM, 1 instruction per clock
