@@ -8,7 +8,7 @@ scratch work directory bootstrapped the way scripts/initial_planet_setup.py:12-3
 
     python tests/golden/make_golden.py [section ...]
 
-sections: atm fileio plugins plugins_nh3_extra plugins_notrunc alpha rays tb neptune image   (default: all)
+sections: atm fileio plugins plugins_nh3_extra plugins_notrunc alpha rays tb neptune uranus image   (default: all)
 
 Every array is float64 exactly as the reference produced it; nothing is post-processed.
 Reference defects driven around: log-sweep strings and float image
@@ -86,6 +86,7 @@ def sec_atm():
     save('atm_jupiter_benchmark.npz', **cfg_arrays(planet('jupiter', config_file='config_benchmark.par')))
     save('atm_neptune.npz', **cfg_arrays(planet('neptune')))
     save('atm_saturn.npz', **cfg_arrays(planet('saturn')))
+    save('atm_uranus.npz', **cfg_arrays(planet('uranus')))
 
 
 PLUGIN_FREQS = [0.6, 1.0, 5.2, 10.0, 21.9, 23.7, 25.99, 26.0, 26.5, 29.0, 30.0, 30.000001, 31.5, 33.9,
@@ -358,6 +359,22 @@ def sec_neptune():
          alpha_every8=lay[:, ::8], ordered_constituents=np.array(n.alpha[0].ordered_constituents))
 
 
+def sec_uranus():
+    """Uranus (10x solar wet atmosphere, its own cloud file, no tilt): disc-averaged Tb and two points at 8 frequencies
+    through the unmodified reference -- a planet none of the BASELINE configs names."""
+    u = planet('uranus')
+    freqs = [1.0, 3.0, 10.0, 22.0, 30.5, 45.0, 100.0, 200.0]
+    t0 = time.time()
+    u.run(freqs, b='disc')
+    disc = np.array(u.Tb, dtype=np.float64)
+    lay = np.array(u.alpha[0].layers)
+    pts = [[0.0, 0.0], [0.6, 0.3]]
+    u.run(freqs, b=pts)
+    print('  uranus runs {:.1f} s'.format(time.time() - t0))
+    save('uranus.npz', freqs=np.array(freqs), disc_tb=disc, pts=np.array(pts), pt_tb=np.array(u.Tb, dtype=np.float64),
+         alpha=lay, ordered_constituents=np.array(u.alpha[0].ordered_constituents))
+
+
 def sec_image():
     """Config C4 subset: Jupiter image grid b=0.005 (601x601, set_utils.py:65-77), 64 freqs 1..100 GHz;
     a seeded random subset of on-disc pixels + limb-ring pixels + off-disc pixels through
@@ -416,7 +433,7 @@ def sec_fileio():
 
 
 SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins_h2_orton': sec_plugins_h2_orton, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
-            'rays': sec_rays, 'tb': sec_tb, 'neptune': sec_neptune, 'image': sec_image}
+            'rays': sec_rays, 'tb': sec_tb, 'neptune': sec_neptune, 'uranus': sec_uranus, 'image': sec_image}
 
 if __name__ == '__main__':
     import warnings

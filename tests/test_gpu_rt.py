@@ -162,6 +162,20 @@ def test_neptune_c2_disc(eng):
     assert np.max(np.abs(res['Tb'] - n['tb'])) < 1e-4
 
 
+def test_uranus_disc_and_points(eng):
+    """Uranus (not one of the BASELINE configs): alpha, disc-averaged Tb and two points against the reference."""
+    a = golden('atm_uranus.npz')
+    u = golden('uranus.npz')
+    C = keymap(a['C_keys'])
+    slab = _slab(eng, a, u['freqs'])
+    assert np.max(relerr(slab.T, u['alpha'])) < 1e-9
+    T = a['gas'][C['T']]
+    res = eng.rt_batch(b=[[0.0, 0.0]], alpha_slab=slab, T=T, disc_average=True, **geom(a))
+    assert np.max(np.abs(res['Tb'] - u['disc_tb'])) < 1e-4
+    res = eng.rt_batch(b=u['pts'], alpha_slab=slab, T=T, **geom(a))
+    assert np.max(np.abs(res['Tb'] - u['pt_tb'])) < 1e-4
+
+
 def test_image_c4_subset_and_full_size_properties(eng):
     """Config C4: 601 x 601 pixels x 64 freqs.  Parity on the reference-computed subset (on-disc, NaN ring,
     off-disc) and size-independent properties on the full cube: off-disc pixels are exactly 2.725 K, the

@@ -134,7 +134,8 @@ REF_PLANETS = '/root/reference/radiobear'
 @pytest.mark.skipif(not os.path.isdir(REF_PLANETS), reason='reference planet files only exist in the build container')
 @pytest.mark.parametrize('planet,cfile,gold', [('jupiter', 'config.par', 'atm_jupiter.npz'),
                                                ('neptune', 'config.par', 'atm_neptune.npz'),
-                                               ('saturn', 'config.par', 'atm_saturn.npz')])
+                                               ('saturn', 'config.par', 'atm_saturn.npz'),
+                                               ('uranus', 'config.par', 'atm_uranus.npz')])
 def test_atmosphere_pipeline_matches_reference(planet, cfile, gold, tmp_path, monkeypatch):
     """readGas/readCloud/regrid/tweak/computeProp on the reference's own input files."""
     import shutil

@@ -158,6 +158,21 @@ def test_disc_and_point_tb_with_reference_alpha():
     assert np.max(relerr(prof['integrated_W'], tb['c1_integrated_W'])) < 1e-12
 
 
+def test_uranus_end_to_end():
+    """A planet outside the BASELINE configs (Uranus, 10x solar wet, own cloud file): oracle alpha on a layer subset,
+    then disc-averaged and point Tb with the reference's alpha, against the unmodified reference."""
+    a = golden('atm_uranus.npz')
+    u = golden('uranus.npz')
+    C, Cl = keymap(a['C_keys']), keymap(a['Cl_keys'])
+    lay = list(range(0, 1000, 9)) + [998, 999]
+    tot, _, ordered = ao.get_layers(u['freqs'], a['gas'], a['cloud'], C, Cl, dict(formalisms_of(a)), return_per_constituent=True,
+                                    other_dicts={'h2': {'h2state': str(a['h2state'])}}, truncate_strength=TRUNC, layers=lay)
+    assert ordered == [str(x) for x in u['ordered_constituents']]
+    assert np.max(relerr(tot, u['alpha'][:, lay])) < 1e-12
+    assert np.max(np.abs(_tb_oracle(a, u['alpha'], [[0.0, 0.0]], disc=True) - u['disc_tb'])) < 1e-9
+    assert np.max(np.abs(_tb_oracle(a, u['alpha'], u['pts']) - u['pt_tb'])) < 1e-9
+
+
 def test_image_subset_c4():
     """C4 subset: on-disc pixels, the NaN limb ring and off-disc pixels (= T_cmb)."""
     a = golden('atm_jupiter.npz')
