@@ -885,6 +885,11 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
 #ifndef RB_RTM_CHUNK
 #define RB_RTM_CHUNK 32
 #endif
+#ifndef RB_RTM_GROUP
+#define RB_RTM_GROUP 4
+#endif
+constexpr int kMxG = RB_RTM_GROUP;                        // segments per group (2 or 4): independent weight chains per thread
+static_assert(kMxG == 2 || kMxG == 4 || kMxG == 8, "groups are processed in pairs");
 constexpr int kMxChunk = RB_RTM_CHUNK;                    // segments per staged tile: 32 or 64
 static_assert(kMxChunk == 32 || kMxChunk == 64, "copy plan below");
 constexpr int kMxRow = 256;                               // bytes per operand row
@@ -1025,28 +1030,30 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
     cp_async_wait<0>();                                    // this thread's pieces of chunk c have landed
     if (!__syncthreads_or(live)) break;                    // ... everybody's have; chunk c-1 is fully consumed
     issue(c + 1);                                          // refill the buffer chunk c-1 used
-    if (live) {
+    // a staged tile is consumed in pieces of 32 segments: the FP32 partial sums are flushed after each
+#pragma unroll 1
+    for (int h = 0; h < kMxChunk / 32 && live; ++h) {
       const unsigned char* st = s_raw + (c & 1) * kMxStage;
-      const MxOperand* qp = reinterpret_cast<const MxOperand*>(st) + threadIdx.y;
-      const float* fp = reinterpret_cast<const float*>(st + kMxTileP) + threadIdx.x;
-      const int m = min(kMxChunk, steps - i);
+      const MxOperand* qp = reinterpret_cast<const MxOperand*>(st) + h * 32 * 8 + threadIdx.y;
+      const float* fp = reinterpret_cast<const float*>(st + kMxTileP) + h * 32 * 32 + threadIdx.x;
+      const int m = min(32, steps - i);
       int u = 0;
       if (small) {
-        // phase A: all FP32, groups of 4 segments; the group that reaches 2^-RB_RTM_SMALL_LOG is left to phase B
+        // phase A: all FP32, groups of kMxG segments; the group that reaches 2^-RB_RTM_SMALL_LOG is left to phase B
 #pragma unroll 1
-        for (; u + 4 <= m; u += 4, fp += 4 * 32, qp += 4 * 8) {
-          float d[5], t[4];
-          ulonglong2 q[4];                                   // .x = {a', T a'} (FFMA2 operand), .y = {asum, 0}
+        for (; u + kMxG <= m; u += kMxG, fp += kMxG * 32, qp += kMxG * 8) {
+          float d[kMxG + 1], t[kMxG];
+          ulonglong2 q[kMxG];                                   // .x = {a', T a'} (FFMA2 operand), .y = {asum, 0}
 #pragma unroll
-          for (int j = 0; j < 5; ++j) d[j] = fp[j * 32];
+          for (int j = 0; j <= kMxG; ++j) d[j] = fp[j * 32];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) q[j] = lds128(&qp[j * 8].ay_f);
+          for (int j = 0; j < kMxG; ++j) q[j] = lds128(&qp[j * 8].ay_f);
           t[0] = fmaf(__uint_as_float((unsigned)q[0].y), d[0], tauf);
 #pragma unroll
-          for (int j = 1; j < 4; ++j) t[j] = fmaf(__uint_as_float((unsigned)q[j].y), d[j], t[j - 1]);
-          if (!(t[3] < kSmallF)) { small = false; break; }   // also leaves on NaN
+          for (int j = 1; j < kMxG; ++j) t[j] = fmaf(__uint_as_float((unsigned)q[j].y), d[j], t[j - 1]);
+          if (!(t[kMxG - 1] < kSmallF)) { small = false; break; }   // also leaves on NaN
 #pragma unroll
-          for (int j = 0; j < 4; j += 2) {
+          for (int j = 0; j < kMxG; j += 2) {
             // two segments per packed instruction: w = (1 - t + t^2/2) (ds_j + ds_j+1)
             const unsigned long long tt = pack2(t[j], t[j + 1]);
             const unsigned long long pp = ffma2(ffma2(tt, pack2(0.5f, 0.5f), pack2(-1.0f, -1.0f)), tt, pack2(1.0f, 1.0f));
@@ -1055,7 +1062,7 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
             acc = ffma2(q[j].x, pack2(w0, w0), acc);
             acc = ffma2(q[j + 1].x, pack2(w1, w1), acc);
           }
-          tauf = t[3];
+          tauf = t[kMxG - 1];
         }
         ia += u;
         if (u < m) small = false;                            // chunk remainder (end of the ray): one by one below
@@ -1064,29 +1071,29 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
       if (!small) {
         // phase B: FP64 optical depth, SFU exponential, FP32 weights
 #pragma unroll 1
-        for (; u + 4 <= m; u += 4, fp += 4 * 32, qp += 4 * 8) {
-          double t[4];
-          float d[5];
-          unsigned long long qa[4];                           // {a', T a'}
+        for (; u + kMxG <= m; u += kMxG, fp += kMxG * 32, qp += kMxG * 8) {
+          double t[kMxG];
+          float d[kMxG + 1];
+          unsigned long long qa[kMxG];                           // {a', T a'}
 #pragma unroll
-          for (int j = 0; j < 5; ++j) d[j] = fp[j * 32];
+          for (int j = 0; j <= kMxG; ++j) d[j] = fp[j * 32];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kMxG; ++j) {
             // one 16-byte read: {double asum, float a', float T a'}
             const ulonglong2 q = lds128(&qp[j * 8].asum);
             qa[j] = q.y;
             t[j] = fma(__longlong_as_double((long long)q.x), f2d_bits(d[j]), j ? t[j > 0 ? j - 1 : 0] : tau);
           }
-          if (__double2hiint(t[3]) >= cut_hi) break;          // tau_cut (or a NaN) inside this group: one by one below
+          if (__double2hiint(t[kMxG - 1]) >= cut_hi) break;          // tau_cut (or a NaN) inside this group: one by one below
 #pragma unroll
-          for (int j = 0; j < 4; j += 2) {
+          for (int j = 0; j < kMxG; j += 2) {
             float w0, w1;
             unpack2(fmul2(pack2(exp_neg_mixed(t[j], cA, cM, fmask), exp_neg_mixed(t[j + 1], cA, cM, fmask)),
                           pack2(d[j] + d[j + 1], d[j + 1] + d[j + 2])), w0, w1);
             acc = ffma2(qa[j], pack2(w0, w0), acc);
             acc = ffma2(qa[j + 1], pack2(w1, w1), acc);
           }
-          tau = t[3];
+          tau = t[kMxG - 1];
         }
         // chunk remainder / the group that crosses tau_cut: one segment at a time; the crossing step is included
         for (; u < m; fp += 32, qp += 8) {
@@ -1102,7 +1109,7 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
       }
       i += u;                                                // segments integrated so far (feeds rb_count_steps)
       live = !stop && i < steps;
-      float iWf, Tbf;                                        // FP32 partial sums of this chunk -> FP64 accumulators
+      float iWf, Tbf;                                        // FP32 partial sums of these 32 segments -> FP64 accumulators
       unpack2(acc, iWf, Tbf);
       iW += (double)iWf;
       Tb += (double)Tbf;
