@@ -314,7 +314,9 @@ def run_gpu(args):
     L, F, n = atm.gas.shape[1], len(freqs), len(grid)
     S = L - 1
     mask = on_disc_mask(grid, q)
-    rparts = parallel.partition_rows(grid, q, world)
+    # RB_BENCH_EMULATE_WORLD=N: time rank 0's share of an N-rank run on one GPU (development aid; the line says so)
+    emulate = int(os.environ.get('RB_BENCH_EMULATE_WORLD', '0')) if world == 1 else 0
+    rparts = parallel.partition_rows(grid, q, emulate or world)
     r0, r1 = rparts[rank]
     pts_all = np.stack([np.tile(grid, n), np.repeat(grid, n)], axis=1)
     parts = [(a * n, b * n) for a, b in rparts]
@@ -522,7 +524,8 @@ def run_gpu(args):
             'config': {'workload': WORKLOAD, 'pixels': 'on-disc', 'on_disc_pixels': n_on, 'nan_limb_pixels': n_nan,
                        'all_pixels': n_all, 'layers': L, 'freqs': F, 'sharding': 'image rows balanced by on-disc pixels; output stays row-sharded in HBM (no collective); e2e: every rank copies its rows into one shared pinned host image',
                        'l2': 'flushed between timed steps (256 MiB write, untimed); ds slab (0.94 GB) exceeds L2',
-                       'tb_dtype_out': 'f32', 'tau_cut': engine.TAU_CUT, 'rt_precision': precision},
+                       'tb_dtype_out': 'f32', 'tau_cut': engine.TAU_CUT, 'rt_precision': precision,
+                       **({'emulated_rank0_share_of_world': emulate} if emulate else {})},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': 1e3 * float(e2e_t.item()), 'api': 'Planet.run(freqs, b=0.005)'},
