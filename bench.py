@@ -181,12 +181,51 @@ class ClockSampler:
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, device):
+    def __init__(self, device, period_s=0.004):
         self.fn = tempfile.NamedTemporaryFile(prefix='rbclk', suffix='.csv', delete=False).name
         self.device = device
         self.p = None
+        self.period_s = period_s
+        self.thread = None
+        self.samples = []          # (sm MHz, max sm MHz, reasons bitmask) from the NVML thread
+        self._stop = False
+
+    def _nvml_loop(self, nv, h):
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            time.sleep(self.period_s)
 
     def start(self):
+        # the timed region is tens of milliseconds: nvidia-smi's fastest loop (100 ms) would sample it once at best,
+        # so the same counters are polled through NVML from a thread; nvidia-smi stays as the fallback
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            try:                               # CUDA_VISIBLE_DEVICES may renumber the devices: go by UUID when torch has it
+                import torch
+                uuid = 'GPU-' + str(torch.cuda.get_device_properties(int(self.device)).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, 'encode') else uuid)
+            except Exception:
+                h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(int(self.device))
+            self._stop = False
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
                                        '--format=csv,noheader,nounits', '-lms', '100'],
@@ -196,6 +235,19 @@ class ClockSampler:
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            bits = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'sw_power_cap': 0x4}
+            if self.samples:
+                sm = [x[0] for x in self.samples]
+                hi = sorted(sm)[len(sm) // 2:]      # upper half = samples under load
+                seen = 0
+                for x in self.samples:
+                    seen |= x[2]
+                out.update(sm_mhz=statistics.median(hi), sm_max_mhz=max(x[1] for x in self.samples),
+                           reasons=sorted(k for k, v in bits.items() if seen & v), samples=len(sm), source='nvml')
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -223,7 +275,8 @@ class ClockSampler:
             pass
         if sm:
             hi = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
-            out.update(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       source='nvidia-smi')
         return out
 
 
