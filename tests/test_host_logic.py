@@ -179,3 +179,32 @@ def test_fileio_text_formats_match_reference(tmp_path):
         d.set('header', {'z': '# z line', 'a': '# a line', 'data-type': '#* type:  ' + typ})
         fn = fileIO.FileIO(directory=str(tmp_path)).write(str(tmp_path / 'out{}.dat'.format(n)), d)
         assert open(fn).read() == str(g['case{}'.format(n)])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's
+    keys, the oracle port timed on every host core, zero host<->device bytes."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['unit'] == 'pixel*freq/s' and d['higher_is_better'] is True
+    assert d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'C4' in d['config']['workload']
+
+
+def test_bench_clock_sampler_without_gpu():
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    got = s.stop()
+    assert set(got) >= {'sm_mhz', 'sm_max_mhz', 'reasons', 'samples'}
