@@ -280,15 +280,18 @@ class ClockSampler:
         return out
 
 
-def alpha_c5(ctx, dev, reps=5):
-    """Secondary metric of BASELINE.json: alpha layer*freq*line / s on config C5 (synthetic 4096-layer
+def alpha_c5(ctx, dev, reps=5, full=False):
+    """full=True: the untrimmed NH3 line lists (415 + 1301 + 4198 = 5914 lines, SURVEY 8d "full catalog").
+    Secondary metric of BASELINE.json: alpha layer*freq*line / s on config C5 (synthetic 4096-layer
     atmosphere x 4096 freqs x NH3 catalog, formalism nh3_dbs_sjs; SURVEY 8d: T~U(80,1800) K,
     P log-U(1e-2,5e3) bar, X_NH3 log-U(1e-7,1e-3), X_H2 = 0.86, X_He = 0.135, seed 0)."""
     import torch
-    from radiobear_b200 import engine
+    from radiobear_b200 import engine, catalogs
     from oracle import alpha_oracle as ao
     rng = np.random.default_rng(0)
     L = F = 4096
+    n_gross = (1301 + 4198) if full else 399
+    reps = max(2, reps // 2) if full else reps
     C = {'Z': 0, 'T': 1, 'P': 2, 'H2': 3, 'HE': 4, 'NH3': 5}
     gas = np.zeros((6, L))
     gas[C['T']] = rng.uniform(80.0, 1800.0, L)
@@ -298,9 +301,10 @@ def alpha_c5(ctx, dev, reps=5):
     freqs = np.linspace(1.0, 100.0, F)
     P = gas[C['P']]
     # lines actually evaluated per (layer, freq): 814 below 400 bar, 1014 in the 400..2000 bar blend, 200 above
-    nlines = np.where(P < 400.0, 814, np.where(P > 2000.0, 200, 1014))
+    # (full catalog: 5914 / 6114 / 200)
+    nlines = np.where(P < 400.0, 415 + n_gross, np.where(P > 2000.0, 200, 615 + n_gross))
     n_br = np.where(P < 400.0, 415, np.where(P > 2000.0, 200, 615))          # Ben-Reuven line-evals
-    n_gr = np.where(P > 2000.0, 0, 399)                                       # Gross line-evals
+    n_gr = np.where(P > 2000.0, 0, n_gross)                                   # Gross line-evals
     evals = float(nlines.sum()) * F
     flops = (10.0 * float(n_br.sum()) + 8.0 * float(n_gr.sum())) * F          # + 1 reciprocal each (not counted)
     t64 = dict(dtype=torch.float64, device=dev)
@@ -309,24 +313,31 @@ def alpha_c5(ctx, dev, reps=5):
     out = torch.empty((L, F), **t64)
     forms = [('nh3', 'nh3_dbs_sjs')]
     ms = []
-    for i in range(reps + 2):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        engine.alpha_layers_dev(f_t, T_t, P_t, g_t, C, formalisms=forms, out=out, freqs_host=freqs, ctx=ctx)
-        e1.record()
-        torch.cuda.synchronize()
-        if i >= 2:
-            ms.append(e0.elapsed_time(e1))
+    catalogs.use_full_nh3_catalog(full)
+    try:
+        for i in range(reps + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            engine.alpha_layers_dev(f_t, T_t, P_t, g_t, C, formalisms=forms, out=out, freqs_host=freqs, ctx=ctx)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ms.append(e0.elapsed_time(e1))
+    finally:
+        catalogs.use_full_nh3_catalog(False)
     t = float(np.mean(ms)) * 1e-3
     # parity spot check against the oracle + its speed on one host core
     lay = [7, 1234, 4000]
     t0 = time.perf_counter()
-    ref = ao.get_layers(freqs, gas, np.zeros((1, L)), C, {}, {'nh3': 'nh3_dbs_sjs'}, layers=lay)
+    ref = ao.get_layers(freqs, gas, np.zeros((1, L)), C, {}, {'nh3': 'nh3_dbs_sjs'}, layers=lay,
+                        cat=ao.LineCatalog(full_nh3=True) if full else None)
     t_cpu = time.perf_counter() - t0
     got = out[lay].cpu().numpy().T
     rel = float(np.nanmax(np.abs(got - ref) / np.abs(ref)))
     cpu_rate = float(nlines[lay].sum()) * F / t_cpu
-    return {'workload': 'C5: 4096 layers x 4096 freqs x NH3 (nh3_dbs_sjs), synthetic', 'metric': 'alpha layer*freq*line/s',
+    return {'workload': 'C5: 4096 layers x 4096 freqs x NH3 (nh3_dbs_sjs{}), synthetic'.format(
+                ', full catalog: 415 + 1301 + 4198 lines' if full else ', shipped catalog: 415 + 201 + 198 lines'),
+            'metric': 'alpha layer*freq*line/s',
             'value': evals / t, 'ms': t * 1e3, 'line_evals': evals, 'max_rel_err_vs_oracle': rel,
             'fp64_tflops_algorithmic': flops / t / 1e12,
             'flops_per_line_eval': '10 (Ben-Reuven) / 8 (Gross) + 1 reciprocal (SURVEY 8d)',
@@ -598,6 +609,10 @@ def run_gpu(args):
             a5['fp64_peak_tflops'] = fp64_peak
             a5['fp64_frac'] = a5['fp64_tflops_algorithmic'] / fp64_peak if fp64_peak else None
             line['alpha_c5'] = a5
+            a5f = alpha_c5(ctx, dev, full=True)
+            a5f['fp64_peak_tflops'] = fp64_peak
+            a5f['fp64_frac'] = a5f['fp64_tflops_algorithmic'] / fp64_peak if fp64_peak else None
+            line['alpha_c5_full'] = a5f
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -28,9 +28,13 @@ class LineCatalog:
     f0 < truncate_freq.  The reference applies this once at first load (module cache).
     """
 
-    def __init__(self, path=_DEFAULT_LINECAT):
+    def __init__(self, path=_DEFAULT_LINECAT, full_nh3=False):
+        """full_nh3: the untrimmed rotational / roto-vibrational NH3 line lists (1301 / 4198 lines) instead of the
+        201 / 198 the reference ships in ammonia.npz (constituents/txt2npz.py:21-56) -- SURVEY 8d "full catalog"."""
         d = np.load(path)
         self.raw = {k: np.array(d[k]) for k in d.files if not k.endswith('_cols')}
+        if full_nh3:
+            self.raw['nh3_rot'], self.raw['nh3_v2'] = self.raw['nh3_rot_full'], self.raw['nh3_v2_full']
         self._cache = {}
 
     def get(self, name, truncate_strength=None, truncate_freq=None):

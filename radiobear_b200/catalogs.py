@@ -29,6 +29,15 @@ _H2O = np.array([
 _H2O[3] = _H2O[3] / 0.001
 
 _raw = None
+# BASELINE config C5 / SURVEY 8d "full NH3 catalog": the untrimmed rotational (1301) and roto-vibrational (4198) line
+# lists instead of the 201 / 198 lines the reference ships in ammonia.npz (constituents/txt2npz.py:21-56)
+_full_nh3 = False
+
+
+def use_full_nh3_catalog(flag=True):
+    """Switch nh3_hs / nh3_dbs / nh3_kd (and the *_sjs blends) to the 5914-line NH3 catalog (off by default)."""
+    global _full_nh3
+    _full_nh3 = bool(flag)
 
 
 def raw():
@@ -43,6 +52,8 @@ def raw():
 def table(name, truncate_strength=None, truncate_freq=None):
     """[ncols][nlines] float64 table for kernel catalog `name` after truncation."""
     r = raw()
+    if name in ('nh3_rot', 'nh3_v2') and _full_nh3:
+        return r[name + '_full']
     if name in ('nh3_inv', 'nh3_rot', 'nh3_v2', 'nh3_sjs', 'co'):
         return r[name]
     if name == 'h2s':
@@ -165,7 +176,8 @@ def upload(ctx, formalism, truncate_strength=None, truncate_freq=None, freqs=Non
             ctx.set_catalog('h2_orton', orton_table(f, st), key=key)
         return
     for name in FORMALISM_CATALOGS[formalism]:
-        key = (truncate_strength, truncate_freq) if name in ('h2s', 'ph3', 'h2o') else ()
+        key = (truncate_strength, truncate_freq) if name in ('h2s', 'ph3', 'h2o') else \
+            (('full',) if (_full_nh3 and name in ('nh3_rot', 'nh3_v2')) else ())
         if ctx.catalog_key.get(name, '__unset__') == key:
             continue
         ctx.set_catalog(name, table(name, truncate_strength, truncate_freq), key=key)

@@ -8,7 +8,7 @@ scratch work directory bootstrapped the way scripts/initial_planet_setup.py:12-3
 
     python tests/golden/make_golden.py [section ...]
 
-sections: atm fileio plugins plugins_nh3_extra plugins_notrunc alpha rays tb neptune uranus image   (default: all)
+sections: atm fileio plugins plugins_nh3_extra plugins_nh3_full plugins_notrunc alpha rays tb neptune uranus image   (default: all)
 
 Every array is float64 exactly as the reference produced it; nothing is post-processed.
 Reference defects driven around: log-sweep strings and float image
@@ -211,6 +211,44 @@ def sec_plugins_nh3_extra():
                 res.append(np.asarray(r, dtype=float))
             out['{}__{}'.format(name, units)] = np.array(res)
     save('plugins_nh3_extra.npz', **out)
+
+
+def sec_plugins_nh3_full():
+    """SURVEY 8d "full catalog" variant of config C5: the reference's own NH3 plugins reading an ammonia.npz rebuilt from
+    the untrimmed line lists (constituents/txt2npz.py:7-57 with rm = vm = 0: 415 + 1301 + 4198 = 5914 lines) through
+    their `path` keyword.  The plugins cache the file in module globals, so this runs in a fresh interpreter."""
+    if os.environ.get('RB_GOLDEN_CHILD') != '1':
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), 'plugins_nh3_full'],
+                              env=dict(os.environ, RB_GOLDEN_CHILD='1'))
+        return
+    import importlib
+    import shutil
+    import tempfile
+    assert 'nh3_dbs' not in sys.modules and 'nh3_hs' not in sys.modules
+    pts, C, Cl, atm = _points()
+    cpath = os.path.join(REF, 'radiobear', 'constituents', 'nh3')
+    tmp = tempfile.mkdtemp(prefix='rb_fullcat_')
+    inv = np.loadtxt(os.path.join(cpath, 'ammonia_inversion.dat'), skiprows=1, unpack=True)
+    rot = np.loadtxt(os.path.join(cpath, 'ammonia_rotational.dat'), skiprows=1, unpack=True)
+    v2 = np.loadtxt(os.path.join(cpath, 'ammonia_rotovibrational.dat'), skiprows=1, unpack=True)
+    np.savez(os.path.join(tmp, 'ammonia.npz'), fo=inv[0], Io=inv[1], Eo=inv[2], gammaNH3o=inv[3], H2HeBroad=inv[4],
+             fo_rot=rot[0], Io_rot=rot[1], Eo_rot=rot[2], gNH3_rot=rot[3], gH2_rot=rot[4], gHe_rot=rot[5],
+             fo_v2=v2[0], Io_v2=v2[1], Eo_v2=v2[2])
+    shutil.copy(os.path.join(cpath, 'nh3.npz'), tmp)
+    sys.path.append(cpath)
+    out = {'points': pts, 'freqs': np.array(PLUGIN_FREQS), 'C_keys': np.array(sorted(C, key=lambda k: C[k])),
+           'nlines': np.array([inv.shape[1], rot.shape[1], v2.shape[1]])}
+    for name in ['nh3_hs', 'nh3_dbs', 'nh3_kd', 'nh3_dbs_sjs']:
+        mod = importlib.import_module(name)
+        for units in ['invcm', 'dBperkm']:
+            res = []
+            for g in pts:
+                r = mod.alpha(PLUGIN_FREQS, g[C['T']], g[C['P']], g, C, {}, units=units, truncate_freq=None,
+                              truncate_strength=None, path=tmp, verbose=False)
+                res.append(np.asarray(r, dtype=float))
+            out['{}__{}'.format(name, units)] = np.array(res)
+    shutil.rmtree(tmp)
+    save('plugins_nh3_full.npz', **out)
 
 
 def sec_plugins_h2_orton():
@@ -432,7 +470,7 @@ def sec_fileio():
     save('fileio.npz', **out)
 
 
-SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins_h2_orton': sec_plugins_h2_orton, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
+SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins_nh3_full': sec_plugins_nh3_full, 'plugins_h2_orton': sec_plugins_h2_orton, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
             'rays': sec_rays, 'tb': sec_tb, 'neptune': sec_neptune, 'uranus': sec_uranus, 'image': sec_image}
 
 if __name__ == '__main__':
@@ -446,7 +484,7 @@ if __name__ == '__main__':
         t0 = time.time()
         print('[{}]'.format(s))
         buf = io.StringIO()
-        if s == 'plugins_notrunc' and os.environ.get('RB_GOLDEN_CHILD') != '1':
+        if s in ('plugins_notrunc', 'plugins_nh3_full') and os.environ.get('RB_GOLDEN_CHILD') != '1':
             SECTIONS[s]()
         else:
             with contextlib.redirect_stdout(buf):

@@ -209,6 +209,30 @@ def test_remaining_nh3_formalisms(eng, name, units):
     assert np.nanmax(relerr(a, ref[-4])) < TIGHT
 
 
+@pytest.mark.parametrize('name', ['nh3_hs', 'nh3_dbs', 'nh3_kd', 'nh3_dbs_sjs'])
+def test_nh3_full_catalog(eng, name):
+    """SURVEY 8d / BASELINE config C5 "full NH3 catalog" (415 + 1301 + 4198 = 5914 lines, 181 KB of line tables in
+    shared memory with the sjs blend): the kernel against the reference's plugins run on the untrimmed line lists;
+    switching back restores the shipped catalog."""
+    from radiobear_b200 import catalogs
+    g = golden('plugins_nh3_full.npz')
+    t = golden('plugins_trunc.npz')
+    C = keymap(g['C_keys'])
+    gas = np.ascontiguousarray(g['points'].T)
+    catalogs.use_full_nh3_catalog(True)
+    try:
+        for units in ('invcm', 'dBperkm'):
+            out = eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('nh3', name)], units=units)
+            ref = g['{}__{}'.format(name, units)]
+            assert np.array_equal(np.isnan(out), np.isnan(ref))
+            assert np.nanmax(relerr(out, ref)) < TIGHT
+    finally:
+        catalogs.use_full_nh3_catalog(False)
+    if name in t.files or (name + '__invcm') in t.files:
+        out = eng.alpha_layers(t['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('nh3', name)], units='invcm')
+        assert np.nanmax(relerr(out, t[name + '__invcm'])) < TIGHT
+
+
 @pytest.mark.parametrize('state', ['e', 'n'])
 @pytest.mark.parametrize('units', ['invcm', 'dBperkm'])
 def test_h2_orton(eng, state, units):

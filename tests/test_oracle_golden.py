@@ -202,6 +202,25 @@ def test_remaining_nh3_formalisms(name):
             assert np.nanmax(relerr(a, r)) < 1e-12
 
 
+@pytest.mark.parametrize('name', ['nh3_hs', 'nh3_dbs', 'nh3_kd', 'nh3_dbs_sjs'])
+def test_nh3_full_catalog(name):
+    """SURVEY 8d / BASELINE config C5 "full NH3 catalog": the reference's plugins on an ammonia.npz rebuilt from the
+    untrimmed line lists (415 + 1301 + 4198 = 5914 lines) against the oracle with LineCatalog(full_nh3=True)."""
+    g = golden('plugins_nh3_full.npz')
+    assert list(g['nlines']) == [415, 1301, 4198]
+    cat = ao.LineCatalog(full_nh3=True)
+    assert cat.get('nh3_rot').shape == (6, 1301) and cat.get('nh3_v2').shape == (3, 4198)
+    C = keymap(g['C_keys'])
+    trimmed = golden('plugins_trunc.npz')
+    for units in ['invcm', 'dBperkm']:
+        for p, r in zip(g['points'], g['{}__{}'.format(name, units)]):
+            a = ao.FORMALISMS[name](g['freqs'], p[C['T']], p[C['P']], p, C, {}, units=units, cat=cat)
+            assert np.array_equal(np.isnan(a), np.isnan(r))
+            assert np.nanmax(relerr(a, r)) < 1e-12
+    if name in ('nh3_hs', 'nh3_dbs'):          # the extra lines matter: not the trimmed-catalog answer
+        assert np.nanmax(relerr(g[name + '__invcm'], trimmed[name + '__invcm'])) > 1e-6
+
+
 @pytest.mark.parametrize('state', ['e', 'n'])
 def test_h2_orton_oracle(state):
     """Orton's H2 CIA tables; 37 points over the three temperature branches."""

@@ -35,8 +35,22 @@ PACK = {
 }
 
 
+# The untrimmed NH3 line lists (ammonia_rotational.dat: 1301 lines, ammonia_rotovibrational.dat: 4198 lines; the
+# shipped ammonia.npz keeps the first 201 / 198 of them, constituents/txt2npz.py:21-56 with rm = 1100, vm = 4000):
+# BASELINE config C5 / SURVEY 8d "full catalog" variant, 415 + 1301 + 4198 = 5914 lines.
+FULL = {
+    'nh3_rot_full': ('nh3/ammonia_rotational.dat', 6),
+    'nh3_v2_full': ('nh3/ammonia_rotovibrational.dat', 3),
+}
+
+
 def main():
     out = {}
+    for name, (fn, ncols) in FULL.items():
+        arr = np.loadtxt(os.path.join(SRC, fn), skiprows=1, unpack=True)
+        assert arr.shape[0] == ncols, (fn, arr.shape)
+        out[name] = np.ascontiguousarray(arr, dtype=np.float64)
+        print('{:13s} {:34s} -> [{} x {}]'.format(name, fn, arr.shape[0], arr.shape[1]))
     for name, (fn, cols) in PACK.items():
         d = np.load(os.path.join(SRC, fn))
         arr = np.stack([np.asarray(d[c], dtype=np.float64) for c in cols])
