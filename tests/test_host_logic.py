@@ -208,3 +208,33 @@ def test_bench_clock_sampler_without_gpu():
     s.start()
     got = s.stop()
     assert set(got) >= {'sm_mhz', 'sm_max_mhz', 'reasons', 'samples'}
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_PLANETS), reason='imports the reference: build container only')
+def test_saturn_regrid_4096_against_live_reference(tmp_path, monkeypatch):
+    """SURVEY 8d, config C5's concrete input: Planet('saturn', regridType=4096) -- the reference regrids
+    saturn.paulSolar onto 4096 log-spaced pressures (0.01 .. 5000 bar); our Atmosphere pipeline on the same files."""
+    import shutil
+    import sys
+    import types
+    shutil.copytree(os.path.join(REF_PLANETS, 'Saturn'), str(tmp_path / 'Saturn'))
+    for d in ('Logs', 'Output', 'Scratch'):
+        os.makedirs(tmp_path / d)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.syspath_prepend(str(tmp_path / 'Saturn'))
+    monkeypatch.syspath_prepend(os.path.dirname(REF_PLANETS))
+    if 'matplotlib' not in sys.modules:            # atm_modify.py:8 imports it at module level; never used here
+        stub = types.ModuleType('matplotlib')
+        stub.pyplot = types.ModuleType('matplotlib.pyplot')
+        monkeypatch.setitem(sys.modules, 'matplotlib', stub)
+        monkeypatch.setitem(sys.modules, 'matplotlib.pyplot', stub.pyplot)
+    import radiobear as rb
+    ref = rb.planet.Planet('saturn', plot_atm=False, plot_bright=False, verbose=False, regridType=4096).atmos[0]
+    from radiobear_b200 import config as pcfg
+    c = pcfg.planetConfig('Saturn', configFile='Saturn/config.par')
+    c.update_config(regridType=4096)
+    a = Atmosphere('saturn', config=c)
+    assert a.std() == 4096 and a.gas.shape == ref.gas.shape == (16, 4096)
+    assert np.max(relerr(a.gas, ref.gas)) < 1e-10
+    assert np.max(relerr(a.cloud, ref.cloud)) < 1e-10
+    assert np.max(relerr(a.property, ref.property)) < 1e-10
