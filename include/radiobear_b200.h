@@ -78,6 +78,14 @@ int rb_set_rt_chunks(rb_context* ctx, int n);
 #define RB_RT_DEFAULT_PRECISION RB_RT_F64
 int rb_set_rt_precision(rb_context* ctx, int precision);
 int rb_get_rt_precision(const rb_context* ctx);
+/* Work decomposition of the batched FP64 ray integration (results do not depend on it: bit-identical Tb).
+ *   pairs   : 1 = two frequencies per thread (CTAs of 32 rays x 16 frequencies), 0 = one (32 x 8), -1 = automatic
+ *             (whichever wastes fewer frequency slots for the request's F).  Environment: RB_RT_PAIRS.
+ *   compact : 1 = trace and integrate only the rays that hit the planet, as full tiles of a compacted list, and
+ *             scatter the results (requests of >= 512 point rays), 0 = walk the rays in the order given.
+ *             Environment: RB_RT_COMPACT.
+ * Kept as a call for A/B measurements and for the tests that compare the decompositions. */
+int rb_set_rt_tuning(rb_context* ctx, int pairs, int compact);
 /* Measurement aid: count the (ray, freq, segment) steps the integration kernel actually executes (the
  * tau_cut early exit skips the rest).  enable = 1 resets and starts counting, 0 stops; the count is returned
  * (after synchronising the context stream). */

@@ -86,6 +86,7 @@ def load():
         'rb_set_rt_chunks': (C.c_int, [vp, C.c_int]),
         'rb_set_rt_precision': (C.c_int, [vp, C.c_int]),
         'rb_get_rt_precision': (C.c_int, [vp]),
+        'rb_set_rt_tuning': (C.c_int, [vp, C.c_int, C.c_int]),
         'rb_count_steps': (i64, [vp, C.c_int]),
         'rb_count_small_steps': (i64, [vp]),
         'rb_set_catalog': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -112,7 +113,7 @@ def load():
 EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error', 'rb_set_stream', 'rb_use_own_stream',
                     'rb_synchronize',
                     'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_kernel_timed_count',
-                    'rb_set_rt_chunks', 'rb_set_rt_precision', 'rb_get_rt_precision', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
+                    'rb_set_rt_chunks', 'rb_set_rt_precision', 'rb_get_rt_precision', 'rb_set_rt_tuning', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
                     'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_compute_ds', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
                     'rb_probe_fp64_peak', 'rb_probe_rcp']
 
@@ -201,6 +202,11 @@ class Context:
         if precision not in RT_PRECISIONS:
             raise ValueError("rt precision must be one of {}".format(sorted(RT_PRECISIONS)))
         self.check(self.lib.rb_set_rt_precision(self.h, RT_PRECISIONS[precision]))
+
+    def set_rt_tuning(self, pairs=-1, compact=True):
+        """Work decomposition of the FP64 ray integration (results are bit-identical): pairs -1 auto / 0 / 1,
+        compact: integrate only the rays that hit the planet (include/radiobear_b200.h: rb_set_rt_tuning)."""
+        self.check(self.lib.rb_set_rt_tuning(self.h, int(pairs), 1 if compact else 0))
 
     def rt_precision(self):
         code = int(self.lib.rb_get_rt_precision(self.h))

@@ -900,13 +900,13 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
     return rb_fail(ctx, RB_ERR_INVALID, "alpha: line tables need %zu B of shared memory (limit %zu B)", smem_bytes,
                    ctx->smem_optin);
 
-  static int newton = -1;
-  if (newton < 0) {
+  if (ctx->alpha_newton < 0) {
     // measured on B200 (tools/probe_rcp.py): seed 9.8e-7, 1 step 9.6e-13, 2 steps 1.1e-16 max relative
     // error.  One step is 6 orders below the 1e-6 parity bar and 3 below the 1e-9 the tests hold.
     const char* e = getenv("RB_RCP_NEWTON");
-    newton = (e && e[0] == '2') ? 2 : 1;
+    ctx->alpha_newton = (e && e[0] == '2') ? 2 : 1;
   }
+  const int newton = ctx->alpha_newton;
   void (*kern)(const AlphaK) = nullptr;
   if (k.fpt == 2) kern = (newton == 1) ? alpha_lines_kernel<2, 1> : alpha_lines_kernel<2, 2>;
   else kern = (newton == 1) ? alpha_lines_kernel<1, 1> : alpha_lines_kernel<1, 2>;

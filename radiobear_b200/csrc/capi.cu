@@ -81,6 +81,8 @@ int rb_create(int device, rb_context** out) {
     else if (!strcmp(pe, "f64")) ctx->rt_precision = RB_RT_F64;
     else return rb_fail(ctx, RB_ERR_INVALID, "RB_RT_PRECISION must be f64 or mixed, got '%s'", pe);
   }
+  if (const char* e = getenv("RB_RT_PAIRS")) ctx->rt_pairs = atoi(e) < 0 ? -1 : (atoi(e) ? 1 : 0);
+  if (const char* e = getenv("RB_RT_COMPACT")) ctx->rt_compact = atoi(e) ? 1 : 0;
   for (int i = 0; i < 3; ++i)
     for (int r = 0; r < rb_context::kEvRing; ++r)
       for (int j = 0; j < 2; ++j) RB_CUDA(ctx, cudaEventCreate(&ctx->ev[i][r][j]));
@@ -97,6 +99,7 @@ void rb_destroy(rb_context* ctx) {
     for (auto& c : ctx->cat)
       if (c) cudaFree(c);
     if (ctx->exp_tab) cudaFree(ctx->exp_tab);
+    if (ctx->step_counter_buf) cudaFree(ctx->step_counter_buf);
     if (ctx->ticket.done) cudaEventDestroy(ctx->ticket.done);
     for (int i = 0; i < 3; ++i)
       for (int r = 0; r < rb_context::kEvRing; ++r)
@@ -169,8 +172,8 @@ int64_t rb_count_steps(rb_context* ctx, int enable) {
   if (!ctx) return -1;
   cudaSetDevice(ctx->device);
   unsigned long long h[2] = {0, 0};
-  static unsigned long long* dev = nullptr;
-  if (!dev && cudaMalloc(&dev, sizeof(h)) != cudaSuccess) return -1;
+  if (!ctx->step_counter_buf && cudaMalloc(&ctx->step_counter_buf, sizeof(h)) != cudaSuccess) return -1;
+  unsigned long long* const dev = ctx->step_counter_buf;
   cudaStreamSynchronize(ctx->stream);
   if (ctx->step_counter) cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost);
   if (enable) {
@@ -203,6 +206,16 @@ int rb_set_rt_precision(rb_context* ctx, int precision) {
 }
 
 int rb_get_rt_precision(const rb_context* ctx) { return ctx ? ctx->rt_precision : -1; }
+
+int rb_set_rt_tuning(rb_context* ctx, int pairs, int compact) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (pairs < -1 || pairs > 1 || compact < 0 || compact > 1)
+    return rb_fail(ctx, RB_ERR_INVALID, "rt tuning: pairs must be -1 / 0 / 1 and compact 0 / 1");
+  if (compact != ctx->rt_compact) drop_ticket(ctx);        // a prefetched geometry has the other indexing
+  ctx->rt_pairs = pairs;
+  ctx->rt_compact = compact;
+  return RB_OK;
+}
 
 int rb_set_catalog(rb_context* ctx, int catalog, int nlines, int ncols, const double* cols) {
   if (!ctx) return RB_ERR_INVALID;
@@ -370,6 +383,27 @@ static void bind_ds(const rb_context* ctx, RtLaunch& L, void* p_ds, void* p_n) {
   L.nanflag = (int32_t*)p_n + L.Rpad;
 }
 
+// Requests that go to the FP64 rays-major integration (>= 512 point rays; rb_rt_prepare) trace and integrate
+// only the rays that hit the planet, as full tiles of a compacted list (rt_kernels.cu: ray_edge_kernel).
+// rb_set_rt_tuning / RB_RT_COMPACT=0 switch it off (A/B measurements, tests of the plain path).
+static bool want_compact(const rb_context* ctx, int64_t R) {
+  return ctx->rt_compact == 1 && R >= 512 && R < 2000000000LL && ctx->rt_precision == RB_RT_F64;
+}
+static int bind_compact(rb_context* ctx, RtLaunch& L) {
+  L.compact = want_compact(ctx, L.R);
+  L.cidx = nullptr; L.ncomp = nullptr; L.zq = nullptr; L.blkcnt = nullptr;
+  if (!L.compact) return RB_OK;
+  void *p_c, *p_z, *p_k;
+  RB_TRY(rb_ensure(ctx, RB_BUF_CIDX, ((size_t)L.Rpad + 32) * 4, &p_c));
+  RB_TRY(rb_ensure(ctx, RB_BUF_ZQ, (size_t)L.Rpad * 8, &p_z));
+  RB_TRY(rb_ensure(ctx, RB_BUF_BLKCNT, ((size_t)L.Rpad / 256 + 2) * 4, &p_k));
+  L.cidx = (int32_t*)p_c;
+  L.ncomp = (int32_t*)p_c + L.Rpad;
+  L.zq = (double*)p_z;
+  L.blkcnt = (int32_t*)p_k;
+  return RB_OK;
+}
+
 static int geometry_prefetch(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const double* b, bool host) {
   if (!ctx) return RB_ERR_INVALID;
   if (!b || !g || !g->radius) return rb_fail(ctx, RB_ERR_INVALID, "geometry_prefetch: null pointer");
@@ -407,6 +441,7 @@ static int geometry_prefetch(rb_context* ctx, const rb_geometry_desc* g, int64_t
     L.radius = g->radius; L.b = b;
   }
   bind_ds(ctx, L, p_ds, p_n);
+  RB_TRY(bind_compact(ctx, L));
   ctx->stream = sG;
   const int status = rb_launch_geometry(ctx, L);
   ctx->stream = user;
@@ -516,14 +551,22 @@ static int choose_chunks(const rb_context* ctx, int64_t R, bool rays_path, bool 
   return n;
 }
 
-static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_desc* rd, void* d_out, double* d_intW,
+static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full_in, const rb_rt_desc* rd, void* d_out, double* d_intW,
                            void* h_out, double* h_intW, bool have_geometry) {
+  RtLaunch full = full_in;
   const int64_t R = full.R;
   const size_t S = full.L - 1, F = rd->n_freqs, esz = rd->out_f32 ? 4 : 8;
   RtPrep prep;
   RB_TRY(rb_rt_prepare(ctx, full.L, rd, R, false, full.dsf != nullptr, &prep));
+  if (full.compact && !prep.use_rays) {
+    // a disc-averaged request over >= 512 rays: the lanes = frequency kernel walks the plain ray order
+    full.compact = false;
+    have_geometry = false;
+  }
   if (!have_geometry) RB_TRY(rb_launch_geometry(ctx, full));
-  const int nch = choose_chunks(ctx, R, prep.use_rays, h_out != nullptr);
+  int nch = choose_chunks(ctx, R, prep.use_rays, h_out != nullptr);
+  const bool one_launch = stream_wait_value() && nch <= kMaxProgressChunks && !getenv("RB_RT_SPLIT_LAUNCHES");
+  if (full.compact && !one_launch) nch = 1;   // the per-chunk launches below cut the plain ray order
   if (nch == 1) {
     RB_TRY(rb_launch_integrate(ctx, full, rd, prep, nullptr, d_out, d_intW, -1, nullptr, nullptr, nullptr));
     if (h_out) RB_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, (size_t)R * F * esz, cudaMemcpyDeviceToHost, ctx->stream));
@@ -538,7 +581,7 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_de
     // shrinking chunks: the copy of the last chunk is the only one nothing overlaps, so keep it small
     return (j >= nch) ? ntiles : (int64_t)llround((double)ntiles * (1.0 - pow(1.0 - (double)j / nch, 1.6)));
   };
-  if (stream_wait_value() && nch <= kMaxProgressChunks && !getenv("RB_RT_SPLIT_LAUNCHES")) {
+  if (one_launch) {
     // One integration launch; its CTAs count themselves into per-chunk counters when their results are in
     // global memory, and the copy stream waits on each counter (stream memory operation) before moving
     // that chunk to the host: the copies overlap the same launch, no launch tails between chunks.
@@ -553,11 +596,17 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_de
     // chunks complete evenly in time.
     pg.shift = (int)(ntiles / 2);
     for (int c = 0; c <= nch; ++c) pg.cut[c] = (int)cut_at(c);
+    const unsigned fgroups = (unsigned)(prep.pairs ? (F + 15) / 16 : (F + 7) / 8);
+    // value the counter of a chunk of `len` ray tiles ends at: one count per CTA; compacted launches start the
+    // counters at their deficit so that they end at (len + 4) * fgroups (rt_progress_init_kernel)
+    const unsigned extra = full.compact ? 4u : 0u;
     RB_CUDA(ctx, cudaMemsetAsync(p_flags, 0, kMaxProgressChunks * sizeof(unsigned), user));
-    RB_CUDA(ctx, cudaEventRecord(ev[0], user));             // counters are zero; the copy stream may start waiting
+    // compacted launch: the counters start at their deficits (how many CTAs will report into each chunk is only
+    // known on the device)
+    if (full.compact) RB_TRY(rb_launch_progress_init(ctx, full, pg, fgroups));
+    RB_CUDA(ctx, cudaEventRecord(ev[0], user));             // counters are set; the copy stream may start waiting
     RB_CUDA(ctx, cudaStreamWaitEvent(sC, ev[0], 0));
     RB_TRY(rb_launch_integrate(ctx, full, rd, prep, &pg, d_out, d_intW, -1, nullptr, nullptr, nullptr));
-    const unsigned fgroups = (unsigned)((F + 7) / 8);
     auto copy_tiles = [&](int64_t t0, int64_t t1) -> int {   // memory-order tiles [t0, t1)
       const int64_t r0 = t0 * 32, r1 = (t1 * 32 < R) ? t1 * 32 : R;
       if (r1 <= r0) return RB_OK;
@@ -571,7 +620,7 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full, const rb_rt_de
     for (int c = 0; c < nch; ++c) {
       const int64_t p0 = pg.cut[c], p1 = pg.cut[c + 1];      // processing-order tiles of the chunk
       if (p1 <= p0) continue;
-      if (stream_wait_value()((CUstream)sC, (CUdeviceptr)(uintptr_t)(pg.done + c), (unsigned)(p1 - p0) * fgroups,
+      if (stream_wait_value()((CUstream)sC, (CUdeviceptr)(uintptr_t)(pg.done + c), ((unsigned)(p1 - p0) + extra) * fgroups,
                               CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
         return rb_fail(ctx, RB_ERR_CUDA, "rt: cuStreamWaitValue32 failed");
       const int64_t m0 = (p0 + pg.shift) % ntiles, len = p1 - p0;
@@ -635,6 +684,7 @@ int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   L.radius = g->radius; L.b = b;
   bind_ds(ctx, L, p_ds, p_n);
+  RB_TRY(bind_compact(ctx, L));
   const bool have_geometry = take_ticket(ctx, g, R, b);
   return run_rt_pipeline(ctx, L, rt, out_Tb, out_intW, nullptr, nullptr, have_geometry);
 }
@@ -673,6 +723,7 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   RB_TRACE_AT("inputs enqueued");
   L.radius = (const double*)p_rad; L.b = (const double*)p_b;
   bind_ds(ctx, L, p_ds, p_n);
+  RB_TRY(bind_compact(ctx, L));
   rb_rt_desc rd = *rt;
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
   RB_TRY(run_rt_pipeline(ctx, L, &rd, p_tb, (double*)p_iw, out_Tb, out_intW, have_geometry));
@@ -681,10 +732,14 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
     // re-run the selected ray alone with the profile-writing variant (Brightness.tau/.W/.Tb_lyr)
     RB_TRY(rb_ensure(ctx, RB_BUF_PROFILE, 3 * F * S * 8 + F * 8, &p_prof));
     RB_CUDA(ctx, cudaMemsetAsync(p_prof, 0, 3 * F * S * 8 + F * 8, s));
+    // (its geometry is traced again on its own: the batch above may have run over the compacted ray list)
     RtLaunch L1 = L;
-    L1.R = 1; L1.Rpad = L.Rpad;
-    L1.ds = L.ds + ((size_t)(profile_ray >> 5) * S) * 32 + (size_t)(profile_ray & 31); L1.nseg = L.nseg + profile_ray; L1.nanflag = L.nanflag + profile_ray;
+    L1.R = 1; L1.Rpad = 32;
+    L1.compact = false;
+    L1.dsf = nullptr;
+    L1.nanflag = L.nseg + 32;
     L1.b = L.b + 2 * profile_ray;
+    RB_TRY(rb_launch_geometry(ctx, L1));
     double* pp = (double*)p_prof;
     rd.out_f32 = 0;
     RtPrep prof_prep;

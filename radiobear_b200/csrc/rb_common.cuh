@@ -28,7 +28,7 @@ struct rb_context {
   int cat_n[RB_NUM_CATALOGS] = {0};
   int cat_cols[RB_NUM_CATALOGS] = {0};
   // grow-only scratch buffers
-  DevBuf buf[20];
+  DevBuf buf[24];
   // timing
   bool timing = false;
   static constexpr int kEvRing = 256;
@@ -40,7 +40,12 @@ struct rb_context {
   std::vector<cudaEvent_t> pipe_ev;
   int rt_chunks = 0;  // 0 = automatic
   int rt_precision = 0;  // RB_RT_F64 / RB_RT_MIXED: arithmetic of the rays-major integration (rb_set_rt_precision)
+  int rt_pairs = -1;     // rb_set_rt_tuning: two frequencies per thread (-1 automatic)
+  int rt_compact = 1;    // rb_set_rt_tuning: integrate the compacted list of rays that hit the planet
+  bool smem_opted[4] = {false, false, false, false};  // kernels opted into > 48 KB of dynamic shared memory
+  int alpha_newton = -1; // Newton steps of the line reciprocal (RB_RCP_NEWTON), read once per context
   unsigned long long* step_counter = nullptr;  // device counters of integrated segment-steps (measurement aid)
+  unsigned long long* step_counter_buf = nullptr;  // their allocation (rb_count_steps)
   int64_t last_small_steps = 0;                // of the count last read: steps taken in the small-tau phase
   // geometry computed ahead of the rt call that will use it (rb_geometry_prefetch[_dev]); single use
   struct GeoTicket {
@@ -69,7 +74,7 @@ inline cudaError_t rb_time_end(rb_context* ctx, int which) {
 enum {
   RB_BUF_FREQS = 0, RB_BUF_T, RB_BUF_P, RB_BUF_GAS, RB_BUF_CLOUD, RB_BUF_SCALE, RB_BUF_TOTAL, RB_BUF_CUBE,
   RB_BUF_RADIUS, RB_BUF_B, RB_BUF_DS, RB_BUF_NSEG, RB_BUF_TB, RB_BUF_INTW, RB_BUF_PROFILE, RB_BUF_MISC, RB_BUF_PREP,
-  RB_BUF_FLAGS
+  RB_BUF_FLAGS, RB_BUF_CIDX, RB_BUF_ZQ, RB_BUF_BLKCNT
 };
 
 // The rays-major integration kernel prefetches whole 32-segment chunks of the ds slab and of the operand
@@ -116,6 +121,13 @@ struct RtLaunch {
   float* dsf;       // device slab of float segments, same tiling (mixed-precision integration only, else null)
   int32_t* nseg;    // device [R]
   int32_t* nanflag; // device [R]: ray carries a NaN segment the integration would use
+  // compacted geometry (FP64 rays-major integration of >= 512 point rays): the layer march and the integration
+  // run over the list of rays that hit the planet; ds tiles / nseg / nanflag are indexed by list position
+  bool compact;
+  int32_t* cidx;    // device [R]: list position -> ray index
+  int32_t* ncomp;   // device scalar: length of the list
+  double* zq;       // device [R]: findEdge depth per ray, NaN = misses the planet
+  int32_t* blkcnt;  // device [ceil(R / 256)]
 };
 int rb_launch_geometry(rb_context* ctx, const RtLaunch& g);
 int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out_ds_raymajor /*[R][L-1] device*/);
@@ -132,9 +144,13 @@ struct RtProgress {
   unsigned* done = nullptr;   // device, nchunks counters, zeroed before the launch
 };
 
+// compacted launches: start the chunk counters at (len + 4) * fgroups minus the CTAs that will report into them
+int rb_launch_progress_init(rb_context* ctx, const RtLaunch& g, const RtProgress& pg, unsigned fgroups);
+
 struct RtPrep {
   bool use_rays = false;       // rays-major kernel (R >= 512, point rays) or the lanes = frequency kernel
   bool mixed = false;          // rays-major kernel in mixed precision (operand rows of rt_prepare_mixed_kernel)
+  bool pairs = false;          // FP64 rays-major kernel with two frequencies per thread (pair operand rows)
   const void* prep = nullptr;  // operand slab of the rays-major kernel
 };
 int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt /*device pointers*/, int64_t R_total, bool profile,

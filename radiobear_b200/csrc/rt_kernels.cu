@@ -43,6 +43,12 @@ struct GeoK {
   float* dsf;    // optional (mixed-precision integration): [R/32][S][32] (float)ds_i, 0 below the last used one
   int* nseg;
   int* nanflag;  // 1 when a segment the integration uses (index <= nseg-2) is NaN -> Tb is NaN
+  // compacted mode (see ray_edge_kernel): ds tiles, nseg and nanflag are indexed by the position in the list
+  // of hitting rays instead of the ray index
+  int* cidx;     // [<= R] list position -> ray index
+  int* ncomp;    // length of the list (device scalar)
+  double* zq;    // [R] edge depth found by findEdge, NaN for a ray that misses
+  int* blkcnt;   // [ceil(R / kEdgeThreads)] hits per block of rays
 };
 
 __device__ __forceinline__ void rot2planet(const GeoK& g, double x, double y, double z, double& ox, double& oy,
@@ -66,53 +72,142 @@ __device__ __forceinline__ void lat_sc(double v, double& s, double& c) {
   }
 }
 
-// one thread per ray
-__global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant__ GeoK g) {
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool inrange = r < g.R;
-  const int S = g.L - 1;
-  const double bx = inrange ? g.b[2 * r] : 2.0, by = inrange ? g.b[2 * r + 1] : 2.0;
+// ---- findEdge (raypath.py:60-105): march zQ down by 0.005 until inside the outer shell ----------------
+// rays with b^2 >= 1 (raypath.py:126-127; NaN impact parameters too) never hit
+__device__ __forceinline__ bool find_edge(const GeoK& g, double bx, double by, double& zq) {
   const double bb = bx * bx + by * by;
   const double q2 = g.q * g.q;
   const double rNorm = g.radius[0];
-  const double mu = sqrt(fmax(0.0, 1.0 - bx * bx - by * by));
+  zq = 0.0;
+  if (!(bb < 1.0)) return false;
+  const double z0 = sqrt(1.0 - bb) * 1.01;
+  const int ntrial = (int)ceil(z0 / 0.005);  // len(np.arange(z0, 0, -0.005))
+  double d_prev = 0.0, z_prev = 0.0;
+  for (int t = 0; t < ntrial; ++t) {
+    const double z = z0 + t * (-0.005);
+    double px, py, pz;
+    rot2planet(g, bx, by, z, px, py, pz);
+    const double nb = sqrt(px * px + py * py + pz * pz);
+    const double r1 = nb * rNorm;
+    double s, c;
+    lat_sc(py / nb, s, c);
+    const double r2 = rNorm * sqrt(q2 * s * s + c * c);
+    const double d = r1 - r2;
+    if (r1 < r2) {
+      // np.interp(0, [d, d_prev], [z, z_prev]); a first-trial hit returns z itself
+      zq = (t == 0) ? z : ((z_prev - z) / (d_prev - d)) * (0.0 - d) + z;
+      return true;
+    }
+    d_prev = d;
+    z_prev = z;
+  }
+  return false;
+}
 
-  // ---- findEdge (raypath.py:60-105): march zQ down by 0.005 until inside the outer shell --------
-  // rays with b^2 >= 1 (raypath.py:126-127; NaN impact parameters too) never hit
-  double zq = 0.0;
+// sqrt / scaled reciprocal of the layer march: SFU seed (MUFU.RSQ64H / MUFU.RCP64H read the high word of the
+// operand only: relative error eps <= 2^-20) and ONE third-order correction, so that each sits on the dependent
+// chain of a segment with four / three FP64 latencies instead of six (two coupled Newton steps):
+//   sqrt(x) = g (1 - 2e)^-1/2 = g (1 + e + 3/2 e^2) + O(5/2 e^3),  g = x r0,  e = 1/2 - (r0/2) g   (|e| ~ eps)
+//   c / x   = c r0 (1 + e + e^2) + O(e^3),                         e = 1 - x r0
+// 2.5 eps^3 < 3e-18: below half an ulp.  x = 0 gives NaN (0 * inf) and x < 0 gives NaN like np.sqrt.
+__device__ __forceinline__ double sqrt_seeded(double x) {
+  double r0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+  const double gq = x * r0, hq = 0.5 * r0;
+  const double eq = fma(-hq, gq, 0.5);
+  return fma(gq * eq, fma(1.5, eq, 1.0), gq);
+}
+__device__ __forceinline__ double rcp_seeded_scaled(double x, double c) {
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+  const double eq = fma(-x, r0, 1.0);
+  const double rc = r0 * c;
+  return fma(rc, fma(eq, eq, eq), rc);
+}
+
+// ---- compaction of the rays that hit the planet (rays-major FP64 integration) --------------------------
+// An image grid is 2/3 sky, and a tile of 32 consecutive pixels that straddles the limb carries idle lanes
+// through every instruction of the layer march and of the integration (measured: 28.9 of 32 lanes active).
+// ray_edge_kernel classifies every ray (findEdge) and counts the hits per block; ray_compact_kernel turns the
+// counts into offsets and writes the list of hitting rays in their original order; the layer march and the
+// integration then run over full tiles of that list and scatter their results to the original ray index.
+constexpr int kEdgeThreads = 256;
+__global__ void __launch_bounds__(kEdgeThreads) ray_edge_kernel(const __grid_constant__ GeoK g) {
+  const long long r = (long long)blockIdx.x * kEdgeThreads + threadIdx.x;
   bool hit = false;
-  if (bb < 1.0) {
-    const double z0 = sqrt(1.0 - bb) * 1.01;
-    const int ntrial = (int)ceil(z0 / 0.005);  // len(np.arange(z0, 0, -0.005))
-    double d_prev = 0.0, z_prev = 0.0;
-    for (int t = 0; t < ntrial; ++t) {
-      const double z = z0 + t * (-0.005);
-      double px, py, pz;
-      rot2planet(g, bx, by, z, px, py, pz);
-      const double nb = sqrt(px * px + py * py + pz * pz);
-      const double r1 = nb * rNorm;
-      double s, c;
-      lat_sc(py / nb, s, c);
-      const double r2 = rNorm * sqrt(q2 * s * s + c * c);
-      const double d = r1 - r2;
-      if (r1 < r2) {
-        hit = true;
-        // np.interp(0, [d, d_prev], [z, z_prev]); a first-trial hit returns z itself
-        zq = (t == 0) ? z : ((z_prev - z) / (d_prev - d)) * (0.0 - d) + z;
-        break;
-      }
-      d_prev = d;
-      z_prev = z;
+  double zq = 0.0;
+  if (r < g.R) {
+    hit = find_edge(g, g.b[2 * r], g.b[2 * r + 1], zq);
+    g.zq[r] = hit ? zq : nan("");
+  }
+  const int n = __syncthreads_count(hit);
+  if (threadIdx.x == 0) g.blkcnt[blockIdx.x] = n;
+}
+
+__global__ void __launch_bounds__(kEdgeThreads) ray_compact_kernel(const __grid_constant__ GeoK g) {
+  __shared__ int s_part[kEdgeThreads / 32];
+  __shared__ int s_base;
+  // hits in the blocks before this one
+  int acc = 0;
+  for (int j = threadIdx.x; j < (int)blockIdx.x; j += kEdgeThreads) acc += g.blkcnt[j];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int b = 0;
+    for (int w = 0; w < kEdgeThreads / 32; ++w) b += s_part[w];
+    s_base = b;
+  }
+  __syncthreads();
+  const int base = s_base;
+  __syncthreads();
+  const long long r = (long long)blockIdx.x * kEdgeThreads + threadIdx.x;
+  const double z = (r < g.R) ? g.zq[r] : nan("");
+  const bool hit = (z == z);
+  const unsigned m = __ballot_sync(0xffffffffu, hit);
+  if (lane == 0) s_part[warp] = __popc(m);
+  __syncthreads();
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += s_part[w];
+  if (hit) g.cidx[base + before + __popc(m & ((1u << lane) - 1u))] = (int)r;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    int tot = base;
+    for (int w = 0; w < kEdgeThreads / 32; ++w) tot += s_part[w];
+    *g.ncomp = tot;
+  }
+}
+
+// one thread per ray (COMPACT: per entry of the list of hitting rays)
+template <bool COMPACT>
+__global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant__ GeoK g) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int S = g.L - 1;
+  long long r = t;
+  bool inrange, hit;
+  double bx = 2.0, by = 2.0, zq = 0.0;
+  if (COMPACT) {
+    inrange = hit = t < (long long)*g.ncomp;
+    if (!inrange) return;
+    r = g.cidx[t];
+    bx = g.b[2 * r]; by = g.b[2 * r + 1];
+    zq = g.zq[r];
+  } else {
+    inrange = r < g.R;
+    if (inrange) { bx = g.b[2 * r]; by = g.b[2 * r + 1]; }
+    hit = find_edge(g, bx, by, zq);
+    // Lanes leave the trial loop at different iterations; without this the early ones run ahead into the
+    // layer loop and the warp stays split for all ~1000 segments (measured: 18.7 active lanes per issue).
+    __syncwarp();
+    if (inrange) g.nanflag[r] = 0;
+    if (!hit) {
+      if (inrange) g.nseg[r] = -1;
+      return;
     }
   }
-  // Lanes leave the trial loop at different iterations; without this the early ones run ahead into the
-  // layer loop and the warp stays split for all ~1000 segments (measured: 18.7 active lanes per issue).
-  __syncwarp();
-  if (inrange) g.nanflag[r] = 0;
-  if (!hit) {
-    if (inrange) g.nseg[r] = -1;
-    return;
-  }
+  const double q2 = g.q * g.q;
+  const double rNorm = g.radius[0];
+  const double mu = sqrt(fmax(0.0, 1.0 - bx * bx - by * by));
   // edge position, then the shell point / normal the reference starts from (raypath.py:141-156)
   double ex, ey, ez;
   rot2planet(g, bx, by, zq, ex, ey, ez);
@@ -160,11 +255,12 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
   }
   int layer = 0;
   int count = 0;
-  double* out = g.ds + ds_tile_base(r, S);
+  const long long o = COMPACT ? t : r;                       // where this ray's results live
+  double* out = g.ds + ds_tile_base(o, S);
   // mixed-precision integration (rt_integrate_rays_mixed_kernel) also wants every segment as a float; the
   // one below the last used segment (i = n-1, brightness.py:65 stops at n-2) is stored as 0 so that the
   // trapezoid weight ds_i + ds_i+1 of the last node needs no special case
-  float* const outf = g.dsf ? g.dsf + ds_tile_base(r, S) : nullptr;
+  float* const outf = g.dsf ? g.dsf + ds_tile_base(o, S) : nullptr;
   const double e2 = 1.0 - q2;
   const double sin6 = 9.99999999999833333e-07, cos6 = 0.9999999999995;   // sin / cos of 1e-6 rad
   const double shape0sq = q2 * sin6 * sin6 + cos6 * cos6;               // lat == 0 -> 1e-6 rad (shape.py:231-233)
@@ -175,8 +271,9 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
   //   ds_i = sqrt(X_i) - sqrt(X_i+1)
   //   shape2 = (shell radius / equatorial radius)^2 = 1 - (1 - q^2) y^2 / |r|^2           (shape.py:240-244)
   //   |r|^2 = X + perp2,   y = y0 + t sy = c0 - sy sqrt(X)      (t = -sqrt(X) - r0.s)
-  // The dependent chain per segment is sqrt -> y -> shape2 -> X: ~11 FP64 instructions instead of ~26
-  // (the kernel is latency-bound: one thread per ray, ~1000 sequential segments).
+  // The kernel is bound by the latency of this chain (one thread per ray, ~1000 sequential segments):
+  //   X' = fma -> sqrt (seed + 4) -> y' (1) -> y'^2 (1) -> shape2' (1)      = SFU seed + 8 FP64 latencies,
+  // the reciprocal of |r|^2 (seed + 4) running beside the square root.
   double rd0 = px * sx + py * sy + pz * sz;                  // r0.s  (< 0: ingress)
   double perp2 = (px * px + py * py + pz * pz) - rd0 * rd0;  // |r0|^2 - (r0.s)^2: constant along the line
   double c0 = py - rd0 * sy;
@@ -185,22 +282,52 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
   double shape2 = shape * shape;
   double Rl = g.radius[0], Rn = g.radius[1];
   bool outward = !(rd0 < 0.0);                               // only possible after a reflection (below)
-  for (; layer < S; ++layer) {
-    const double Rnn = g.radius[min(layer + 2, g.L - 1)];    // prefetch for the next segment
-    const double Xn = fma(shape2, (Rn - Rl) * (Rn + Rl), X);
-    // sqrt(Xn): MUFU.RSQ64H seed + two coupled Newton steps (~1 ulp; NaN for Xn < 0 like np.sqrt)
-    double sqn;
-    {
-      double r0;
-      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(Xn));
-      double gq = Xn * r0, hq = 0.5 * r0;
-      double eq = fma(-hq, gq, 0.5);
-      gq = fma(gq, eq, gq);
-      hq = fma(hq, eq, hq);
-      eq = fma(-hq, gq, 0.5);
-      sqn = fma(gq, eq, gq);
-      if (Xn == 0.0) sqn = 0.0;
+  int cool = 0;                                              // careful steps to take before speculating again
+  while (layer < S) {
+    // Speculative block of kSpec segments: the plain recurrence with every exceptional condition (ray leaves,
+    // NaN below the tangent shell, y == 0, grazing incidence) folded into one flag that nothing waits for until
+    // the end of the block -- no branch sits between two segments of the chain.  A flagged block is discarded
+    // and its segments are redone one at a time by the careful step below (same arithmetic, same values).
+    constexpr int kSpec = 4;
+    if (cool == 0 && !outward && g.limb != RB_LIMB_SEC && layer + kSpec <= S) {
+      const double X0 = X, sq0 = sq, sh0 = shape2;
+      double dsv[kSpec];
+      double Ra = Rl, Rb = Rn;
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < kSpec; ++j) {
+        const double Rc = g.radius[min(layer + j + 2, g.L - 1)];
+        const double Xn = fma(shape2, (Rb - Ra) * (Rb + Ra), X);
+        const double sqn = sqrt_seeded(Xn);
+        const double inve = rcp_seeded_scaled(Xn + perp2, -e2);
+        const double ds = sq - sqn;
+        const double yn = fma(-sy, sqn, c0);
+        const double syy = sy * yn;
+        const double d = fma(g.q, -sqn - syy, syy);
+        bad |= !(ds >= 0.0) | (yn == 0.0) | !(d <= 0.0);
+        dsv[j] = ds;
+        shape2 = fma(yn * yn, inve, 1.0);
+        X = Xn; sq = sqn; Ra = Rb; Rb = Rc;
+      }
+      if (!bad) {
+#pragma unroll
+        for (int j = 0; j < kSpec; ++j) {
+          out[(size_t)(layer + j) * kDsStride] = dsv[j];
+          if (outf) outf[(size_t)(layer + j) * kDsStride] = (float)dsv[j];
+        }
+        layer += kSpec; count += kSpec;
+        Rl = Ra; Rn = Rb;
+        continue;
+      }
+      X = X0; sq = sq0; shape2 = sh0;
+      cool = kSpec;
     }
+    if (cool > 0) --cool;
+    // ---- careful step: one segment with every test of the reference in place ----
+    const double Rnn = g.radius[min(layer + 2, g.L - 1)];
+    const double Xn = fma(shape2, (Rn - Rl) * (Rn + Rl), X);
+    double sqn = sqrt_seeded(Xn);                            // NaN for Xn < 0 like np.sqrt
+    if (Xn == 0.0) sqn = 0.0;
     double ds = sq - sqn;
     if (outward) ds = -sq - sqn;                             // r.s > 0: the reference's dsm is negative -> stop
     if (ds < 0.0) break;                                     // raypath.py:212-216
@@ -220,8 +347,8 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     }
     // latitude of the new point -> shape factor of the next shell pair (raypath.py:228-237)
     const double yn = fma(-sy, sqn, c0);
-    const double inv = rb_rcp<2>(Xn + perp2);
-    double shape2n = fma(-e2 * (yn * yn), inv, 1.0);
+    const double inve = rcp_seeded_scaled(Xn + perp2, -e2);
+    double shape2n = fma(yn * yn, inve, 1.0);
     if (yn == 0.0) shape2n = shape0sq;
     // incidence on the next shell with nratio = 1 (raypath.py:176-177, 246, 257): the reference's
     // arccos / arcsin pair gives s += (cos t_inc - |cos t_inc|) n, i.e. nothing unless cos t_inc < 0.
@@ -229,13 +356,14 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     const double syy = sy * yn;
     const double d = fma(g.q, -sqn - syy, syy);
     X = Xn; sq = sqn; shape2 = shape2n; Rl = Rn; Rn = Rnn;
+    ++layer;
     if (g.limb == RB_LIMB_SEC || !(d <= 0.0) || outward) {
       // grazing ray (rare) or the secant mode (position advances by the secant ds, not along the chord):
       // go through the vector form and restart the line at the current point.  (For y == 0 the reference's
       // normal carries a 1e-6 y-component; it can only change the sign test within 1e-6 rad of tangency,
       // where the next segment is NaN anyway, so the plain test is used.)
-      const double t = (g.limb == RB_LIMB_SEC) ? ds : ((outward ? sqn : -sqn) - rd0);
-      px = fma(t, sx, px); py = fma(t, sy, py); pz = fma(t, sz, pz);
+      const double tt = (g.limb == RB_LIMB_SEC) ? ds : ((outward ? sqn : -sqn) - rd0);
+      px = fma(tt, sx, px); py = fma(tt, sy, py); pz = fma(tt, sz, pz);
       if (g.limb != RB_LIMB_SEC && !outward) py = yn;
       const double nr2 = px * px + py * py + pz * pz;
       if (g.limb == RB_LIMB_SEC) shape2 = (py == 0.0) ? shape0sq : fma(-e2 * (py * py), 1.0 / nr2, 1.0);
@@ -268,10 +396,10 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     const double last_used = out[(size_t)(count - 2) * kDsStride];
     if (last_used != last_used) first_nan = 0;
   }
-  g.nseg[r] = count;
+  g.nseg[o] = count;
   if (outf && count >= 1) outf[(size_t)(count - 1) * kDsStride] = 0.0f;
   // Brightness.single uses ds[0 .. n-2] (brightness.py:65); a NaN there makes every frequency NaN
-  g.nanflag[r] = (first_nan >= 0 && first_nan <= count - 2) ? 1 : 0;
+  g.nanflag[o] = (first_nan >= 0 && first_nan <= count - 2) ? 1 : 0;
 }
 
 // [S][Rpad] slab -> [R][S] ray-major (only for the compute_ds API that returns Ray.ds)
@@ -368,6 +496,10 @@ struct RtK {
   const float* dsf;               // mixed-precision rays-major kernel: float segments (see GeoK::dsf)
   const void* prepm;              // mixed-precision rays-major kernel: operand rows (see rt_prepare_mixed_kernel)
   RtProgress progress;    // optional per-chunk completion counters (rays-major kernel only)
+  const double2* prep2;   // [F/16][L-1][8][3] pair operands (rt_integrate_pairs_kernel, see rt_prepare_pairs_kernel)
+  unsigned fgroups, ntiles;  // rays-major launches are 1-D: block = tile * fgroups + frequency group
+  const int* cidx;        // compacted launch: list position -> ray index (null: ds / nseg / nanflag are per ray index)
+  const int* ncomp;       // compacted launch: length of the list
   const double* ds;     // [S][Rpad]
   const int* nseg;      // [R]
   const int* nanflag;   // [R]
@@ -410,6 +542,8 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
   }
   double a0 = k.alpha[f];
   double T0 = k.T[0];
+  // a ray stops once tau >= tau_cut, by the high words (the rule of the rays-major kernels; INFINITY disables it)
+  const int cut_hi = __double2hiint(k.tau_cut);
   // brightness.py:65: for i in range(len(ds) - 1)
   for (int i = 0; i + 1 < nmax; ++i) {
     const double a1 = k.alpha[(size_t)(i + 1) * k.F + f];
@@ -421,7 +555,7 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
     bool live = false;
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
-      if (i + 1 < n[j] && !isnan_ray[j] && !(tau[j] > k.tau_cut)) {
+      if (i + 1 < n[j] && !isnan_ray[j] && __double2hiint(tau[j]) < cut_hi) {
         const double h = dsv[j] * kKmToCm * 0.5;        // ds/2 in cm
         tau[j] = tau[j] + asum * h;                      // dtau = (a0 + a1) * ds / 2
         const double W = DISC ? 2.0 * a1 * expn2(tau[j]) : a1 * exp(-tau[j]);
@@ -580,6 +714,125 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- ray tile of a CTA of the rays-major kernels ----------------------------------------------------------
+// Plain launch: CTA y owns rays 32 y .. 32 y + 31.  Compacted launch (k.cidx): CTA y owns 32 consecutive entries
+// of the list of rays that hit the planet; ds / nseg / nanflag are indexed by list position, results are scattered
+// to the ray index.  When the host pipelines the copy-out (k.progress.done) the launch order is rotated to the
+// middle of the ray list: an image starts and ends with rows of sky, so the centre rows -- the long ones -- start
+// first and the chunks complete evenly in time.
+struct RayTile {
+  unsigned fg, by;     // frequency group / position in launch order (frequency groups of a tile are adjacent: they
+                       // share the ds tile through L2)
+  unsigned tile;       // tile of the ds slab
+  long long t;         // this lane: index into ds tiles / nseg / nanflag
+  long long r;         // this lane: ray index (row of out_Tb)
+  bool in;             // this lane carries a ray
+  bool dead;           // whole CTA beyond the end of the compacted list
+  int first_r, last_r; // compacted launch: ray index of the first / last ray of the tile
+};
+__device__ __forceinline__ RayTile map_ray_tile(const RtK& k) {
+  RayTile m;
+  m.dead = false;
+  m.first_r = m.last_r = 0;
+  m.by = blockIdx.x / k.fgroups;
+  m.fg = blockIdx.x - m.by * k.fgroups;
+  if (k.cidx) {
+    const int nc = *k.ncomp;
+    const unsigned ntile = (unsigned)((nc + 31) >> 5);
+    m.dead = m.by >= ntile;
+    unsigned tile = m.by + (k.progress.done ? (ntile >> 1) : 0u);
+    if (tile >= ntile) tile -= ntile;
+    m.tile = tile;
+    m.t = (long long)tile * 32 + threadIdx.x;
+    m.in = !m.dead && m.t < nc;
+    m.r = m.in ? k.cidx[m.t] : 0;
+    if (!m.dead && k.progress.done) {
+      m.first_r = k.cidx[(long long)tile * 32];
+      const long long last = (long long)tile * 32 + 31;
+      m.last_r = k.cidx[last < nc ? last : nc - 1];
+    }
+  } else {
+    unsigned tile = m.by + (unsigned)k.progress.shift;
+    if (tile >= k.ntiles) tile -= k.ntiles;
+    m.tile = tile;
+    m.t = m.r = (long long)tile * 32 + threadIdx.x;
+    m.in = m.r < k.R;
+  }
+  return m;
+}
+
+// chunks (bit c) of the copy-out pipeline whose rows intersect the ray-index tiles [m0, m1] (compacted launches:
+// a tile of the list spans rays of several image rows).  Chunk c is the tiles (p + shift) mod ntiles,
+// p in [cut[c], cut[c+1]), of the plain ray order.
+__device__ __forceinline__ unsigned progress_touched(const RtProgress& pg, int ntiles, int m0, int m1) {
+  unsigned mask = 0;
+  for (int c = 0; c < pg.nchunks; ++c) {
+    const int len = pg.cut[c + 1] - pg.cut[c];
+    if (len <= 0) continue;
+    int a = pg.cut[c] + pg.shift;
+    if (a >= ntiles) a -= ntiles;
+    const int e = a + len;                               // [a, e) possibly wrapping past ntiles
+    const bool hit = (e <= ntiles) ? (m0 < e && m1 >= a) : ((m1 >= a) || (m0 < e - ntiles));
+    if (hit) mask |= 1u << c;
+  }
+  return mask;
+}
+
+// this CTA's results are in global memory: count it in its chunk(s) (the host's copy stream waits on the counters
+// with a stream memory operation and then copies the chunk device -> host)
+__device__ __forceinline__ void progress_report(const RtK& k, const RayTile& m, int tid) {
+  if (!k.progress.done) return;
+  __threadfence();
+  __syncthreads();
+  if (tid != 0) return;
+  if (k.cidx) {
+    unsigned mask = progress_touched(k.progress, (int)k.ntiles, m.first_r >> 5, m.last_r >> 5);
+    for (; mask; mask &= mask - 1) atomicAdd(k.progress.done + (__ffs(mask) - 1), 1u);
+  } else {
+    int c = 0;
+    while (c + 1 < k.progress.nchunks && (int)m.by >= k.progress.cut[c + 1]) ++c;
+    atomicAdd(k.progress.done + c, 1u);
+  }
+}
+
+// Compacted launch, before the integration: done[c] = nominal(c) - (CTAs that will report into chunk c), so that
+// every counter ends at its nominal value (len + 4) * fgroups -- the value the host waits for, known without
+// reading the list back (at most len + 4 tiles of the list touch a chunk of len ray tiles: each spans >= 32 rays).
+__global__ void __launch_bounds__(256) rt_progress_init_kernel(RtProgress pg, const int* __restrict__ cidx,
+                                                               const int* __restrict__ ncomp, int ntiles,
+                                                               unsigned fgroups) {
+  __shared__ unsigned s_cnt[kMaxProgressChunks];
+  if (threadIdx.x < kMaxProgressChunks) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int nc = *ncomp;
+  const int nct = (nc + 31) >> 5;
+  for (int tl = threadIdx.x; tl < nct; tl += blockDim.x) {
+    const int first = cidx[(long long)tl * 32];
+    const long long last = (long long)tl * 32 + 31;
+    const int lastr = cidx[last < nc ? last : nc - 1];
+    unsigned mask = progress_touched(pg, ntiles, first >> 5, lastr >> 5);
+    for (; mask; mask &= mask - 1) atomicAdd(&s_cnt[__ffs(mask) - 1], 1u);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < pg.nchunks) {
+    const unsigned len = (unsigned)(pg.cut[threadIdx.x + 1] - pg.cut[threadIdx.x]);
+    pg.done[threadIdx.x] = (len + 4u) * fgroups - s_cnt[threadIdx.x] * fgroups;
+  }
+}
+
+// rays that miss the planet see the sky (brightness.py:46-51); compacted launches never visit them
+__global__ void rt_fill_miss_kernel(const double* __restrict__ zq, long long R, int F, void* out_Tb, double* out_intW,
+                                    int out_f32) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * F) return;
+  const long long r = idx / F;
+  const double z = zq[r];
+  if (z == z) return;
+  if (out_f32) reinterpret_cast<float*>(out_Tb)[idx] = (float)kTcmb;
+  else reinterpret_cast<double*>(out_Tb)[idx] = kTcmb;
+  if (out_intW) out_intW[idx] = 0.0;
+}
+
 // thread = (ray, frequency); lanes = 32 consecutive rays; the CTA's 8 warps are the 8 frequencies of one
 // frequency group, all working on the same 32 rays.  Both operand streams are staged through shared memory
 // in chunks of kChunk segments with cp.async (LDGSTS), three buffers deep:
@@ -618,14 +871,16 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   const int tid = threadIdx.y * 32 + threadIdx.x;
 
   const int S = k.L - 1;
-  // ray tile of this CTA: launch order rotated by progress.shift (0 unless the host pipelines the copy-out)
-  unsigned tile = blockIdx.y + (unsigned)k.progress.shift;
-  if (tile >= gridDim.y) tile -= gridDim.y;
-  const long long r = (long long)tile * 32 + threadIdx.x;
-  const int f = blockIdx.x * 8 + threadIdx.y;
-  const bool valid = (r < k.R) && (f < k.F);
-  const int n = valid ? k.nseg[r] : -1;
-  const bool nanray = valid && k.nanflag[r] != 0;
+  // ray tile of this CTA (see RayTile)
+  const RayTile rt_ = map_ray_tile(k);
+  if (rt_.dead) return;
+  const unsigned tile = rt_.tile;
+  const long long tpos = rt_.t;       // where this ray's ds / nseg / nanflag live
+  const long long r = rt_.r;          // ray index (output row)
+  const int f = rt_.fg * 8 + threadIdx.y;
+  const bool valid = rt_.in && (f < k.F);
+  const int n = valid ? k.nseg[tpos] : -1;
+  const bool nanray = valid && k.nanflag[tpos] != 0;
   const int steps = (valid && !nanray) ? n - 1 : 0;        // brightness.py:65: i = 0 .. len(ds)-2
 
   // Per-thread copy plan for one chunk, computed once: the chunk's 33 ds rows and 32 operand rows are each
@@ -633,7 +888,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   // thread for each stream plus a third ds piece for the first 16 threads.  No bounds checks: rows past the
   // end of a tile are never consumed and both slabs are allocated with kRtSlackBytes of slack.
   const char* src_ds = reinterpret_cast<const char*>(k.ds + (size_t)tile * S * 32) + tid * 16;
-  const char* src_pp = reinterpret_cast<const char*>(k.prep + (size_t)blockIdx.x * S * 8) + tid * 16;
+  const char* src_pp = reinterpret_cast<const char*>(k.prep + (size_t)rt_.fg * S * 8) + tid * 16;
   const unsigned dst_ds = (unsigned)__cvta_generic_to_shared(s_ds) + tid * 16;
   const unsigned dst_pp = (unsigned)__cvta_generic_to_shared(s_pp) + tid * 16;
   auto issue = [&](int c) {
@@ -665,12 +920,12 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   // window base with S2UR / UMOV / ULEA in every iteration)
   unsigned tab_base;
   asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(tab_base) : "l"(s_tab));
-  // One integer compare on the high word of nd = round(-tau 1024 log2 e) (a non-positive double, so its
-  // high word grows with |nd|) ends the ray when tau > tau_cut; tau_cut is capped at 707 (beyond it 2^k leaves
-  // the normal range and exp(-tau) is 0 for every purpose), so the hot loop needs neither an underflow
-  // select nor an FP64 compare.  The step that crosses the threshold is finished on a cold path.
-  const double cutd = fmin(k.tau_cut, 707.0) * (1.4426950408889634074 * kExpTab);
-  const unsigned thr_hi = (unsigned)__double2hiint(-cutd);
+  // One integer compare on the high word of tau (a non-negative double: it orders like its high word; a NaN
+  // compares as "beyond") ends the ray once tau >= tau_cut -- the same rule in every integration kernel of this
+  // file (tau_cut to the 20 mantissa bits of its high word: exact for 5, 50, ...).  tau_cut is capped at 707
+  // (beyond it 2^k leaves the normal range and exp(-tau) is 0 for every purpose), so the hot loop needs neither
+  // an underflow select nor an FP64 compare.  The step that crosses the threshold is finished on a cold path.
+  const int cut_hi = __double2hiint(fmin(k.tau_cut, 707.0));
   double tau = 0.0, iW = 0.0, Tb = 0.0;
   int i = 0;
   double last_dd = 0.0, last_qy = 0.0, last_qz = 0.0;    // operands of the crossing step
@@ -682,7 +937,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
     double nd = fma(tau, cA, cM);                                                                              \
     const int ni = __double2loint(nd);                                                                         \
     nd -= cM;                                                                                                  \
-    if ((unsigned)__double2hiint(nd) > thr_hi) {                                                               \
+    if (__double2hiint(tau) >= cut_hi) {                                                                       \
       last_dd = (dcur) + (dnxt); last_qy = (q).y; last_qz = (q).z;                                             \
       stop = true;                                                                                             \
       break;                                                                                                   \
@@ -779,8 +1034,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
           t[0] = fma(q[0].x, d[0], tau);
 #pragma unroll
           for (int j = 1; j < kGroup; ++j) t[j] = fma(q[j].x, d[j], t[j - 1]);
-          const double ndl = fma(t[kGroup - 1], cA, cM) - cM;
-          if ((unsigned)__double2hiint(ndl) > thr_hi) break;   // tau_cut is crossed inside this group: go step by step
+          if (__double2hiint(t[kGroup - 1]) >= cut_hi) break;   // tau_cut is crossed inside this group: go step by step
 #pragma unroll
           for (int j = 0; j < kGroup; ++j) RB_RT_WEIGHT(t[j], d[j] + d[j + 1], w[j]);
 #pragma unroll
@@ -835,17 +1089,347 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
     else reinterpret_cast<double*>(k.out_Tb)[o] = vout;
     if (k.out_intW) k.out_intW[o] = (n < 0) ? 0.0 : wout;
   }
-  if (k.progress.done) {
-    // this CTA's results are in global memory: count it in its chunk (the host's copy stream waits on the
-    // counter with a stream memory operation and then copies the chunk device -> host)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      int c = 0;
-      while (c + 1 < k.progress.nchunks && (int)blockIdx.y >= k.progress.cut[c + 1]) ++c;
-      atomicAdd(k.progress.done + c, 1u);
+  progress_report(k, rt_, tid);
+}
+
+// ====================================================================================================
+// Two frequencies per thread (F >= 16): rt_integrate_pairs_kernel.
+//
+// Same arithmetic, operation for operation, as rt_integrate_rays_kernel (results are bit-identical), other
+// decomposition: a thread owns one ray and TWO adjacent frequencies, a CTA 32 rays x 16 frequencies.  What that
+// buys (the one-frequency kernel ends at 59 % of its issue slots with the shared-memory data pipe as its
+// busiest unit, 0.81 wavefronts per clock -- profiles/r1_final_rt_integrate_rays_ncu_full.txt):
+//   * every ds value read from shared memory (LDS.64, two wavefronts per warp) feeds two chains, the carried
+//     ds_i+1 of a group is kept in a register, and ds_i + ds_i+1 is added once for both frequencies;
+//   * the operands of a pair are one 48-byte row {asum_a, asum_b | a'_a, T a'_a | a'_b, T a'_b}: three LDS.128
+//     per segment for two steps instead of four reads;
+//   * half as many CTAs per ray tile: half the per-chunk work (copy plan, wait, barrier vote) per step and half
+//     the L2 -> shared-memory traffic of the ds tiles.
+// A thread runs its two frequencies together while both are live: phase A while both optical depths are below
+// 2^-RB_EXP_SMALL_LOG, phase B until one of them crosses tau_cut inside a group; the crossing is resolved one
+// segment at a time, and the frequency that is left alone finishes on the single-segment path (adjacent
+// frequencies stop a few layers apart).  A frequency beyond F (odd F) is a ghost: zero operands, ends with its
+// partner.
+constexpr int kPairRow = 3;                          // double2 per (segment, pair)
+constexpr int kPairTileQ = kChunk * 8 * kPairRow;    // double2 per operand tile
+constexpr size_t kPairsSmemBytes = kStages * (kTileDs * sizeof(double) + kPairTileQ * sizeof(double2));
+static_assert((kChunk * 8 * kPairRow * sizeof(double2)) % 4096 == 0, "pair operand tile: whole 4 KB copy rounds");
+static_assert(kRtSlackBytes >= (kChunk + 1) * 32 * sizeof(double) + 256, "ds slab slack covers one over-read chunk");
+static_assert(kRtSlackBytes >= kChunk * 8 * kPairRow * sizeof(double2), "pair operand slack covers one over-read chunk");
+static_assert(kRtSlackBytes >= kChunk * 8 * sizeof(double4), "operand slack covers one over-read chunk");
+
+// pair operands:  prep2[fg][i][p] = { asum_a, asum_b }, { a'_a, T_i+1 a'_a }, { a'_b, T_i+1 a'_b },
+//   a = 16 fg + 2 p, b = a + 1; asum = (a_i + a_i+1) kHalfCm, a' = a_i+1 kHalfCm; zero for f >= F
+__global__ void rt_prepare_pairs_kernel(const double* __restrict__ alpha, const double* __restrict__ T, int L, int F,
+                                        int ngroups, double2* __restrict__ prep2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Lm1 = L - 1;
+  if (idx >= ngroups * Lm1 * 8) return;
+  const int p = idx & 7;
+  const int i = (idx >> 3) % Lm1;
+  const int fg = (idx >> 3) / Lm1;
+  const double kHalfCm = 0.5 * kKmToCm;
+  double v[2][3];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int f = fg * 16 + 2 * p + h;
+    v[h][0] = v[h][1] = v[h][2] = 0.0;
+    if (f < F) {
+      const double a0 = alpha[(size_t)i * F + f], a1 = alpha[(size_t)(i + 1) * F + f];
+      v[h][0] = (a0 + a1) * kHalfCm; v[h][1] = a1 * kHalfCm; v[h][2] = (T[i + 1] * a1) * kHalfCm;
     }
   }
+  double2* o = prep2 + (size_t)idx * kPairRow;
+  o[0] = make_double2(v[0][0], v[1][0]);
+  o[1] = make_double2(v[0][1], v[0][2]);
+  o[2] = make_double2(v[1][1], v[1][2]);
+}
+
+// shared-memory reads at a 32-bit shared-window address plus a compile-time offset (one LDS each, no address
+// arithmetic in the loops)
+template <unsigned OFF>
+__device__ __forceinline__ double lds_f64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+template <unsigned OFF>
+__device__ __forceinline__ double2 lds_v2(unsigned a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF));
+  return v;
+}
+
+__global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_pairs_kernel(const __grid_constant__ RtK k) {
+  // dynamic shared memory: [ table | ds tiles x kStages | pair operand tiles x kStages ]
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  double* const s_tab = reinterpret_cast<double*>(s_raw);
+  double* const s_ds = s_tab + kExpTab;
+  double2* const s_q = reinterpret_cast<double2*>(s_ds + kStages * kTileDs);
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+
+  const int S = k.L - 1;
+  const RayTile rt_ = map_ray_tile(k);
+  if (rt_.dead) return;
+  const unsigned tile = rt_.tile;
+  const long long tpos = rt_.t;
+  const long long r = rt_.r;
+  const int fA = rt_.fg * 16 + 2 * threadIdx.y;
+  const bool validA = rt_.in && (fA < k.F), validB = rt_.in && (fA + 1 < k.F);
+  const int n = validA ? k.nseg[tpos] : -1;
+  const bool nanray = validA && k.nanflag[tpos] != 0;
+  const int steps = (validA && !nanray) ? n - 1 : 0;        // brightness.py:65: i = 0 .. len(ds)-2
+
+  // copy plan (see rt_integrate_rays_kernel): ds chunk 33 x 256 B, operand chunk kChunk x 384 B, 16-byte pieces
+  const char* src_ds = reinterpret_cast<const char*>(k.ds + (size_t)tile * S * 32) + tid * 16;
+  const char* src_q = reinterpret_cast<const char*>(k.prep2 + (size_t)rt_.fg * S * 8 * kPairRow) + tid * 16;
+  const unsigned dst_ds = (unsigned)__cvta_generic_to_shared(s_ds) + tid * 16;
+  const unsigned dst_q = (unsigned)__cvta_generic_to_shared(s_q) + tid * 16;
+  auto issue = [&](int c) {
+    const unsigned bd = (c & 1) ? (unsigned)(kTileDs * sizeof(double)) : 0u;
+    const unsigned bq = (c & 1) ? (unsigned)(kPairTileQ * sizeof(double2)) : 0u;
+    cp_rounds<kChunk / 16>(dst_ds + bd, src_ds);
+    cp_rounds<(kChunk * 8 * kPairRow * (int)sizeof(double2)) / 4096>(dst_q + bq, src_q);
+    if (tid < 16) cp_async16_at<(kChunk / 16) * 4096>(dst_ds + bd, src_ds);
+    cp_async_commit();
+    src_ds += kChunk * 32 * sizeof(double);
+    src_q += kChunk * 8 * kPairRow * sizeof(double2);
+  };
+  // bit 0: frequency a is live, bit 1: frequency b (a ghost b beyond F rides along with zero operands)
+  int mode = (steps > 0) ? 3 : 0;
+  const bool any_live = __syncthreads_or(mode != 0);
+  if (any_live) {
+    for (int q = tid; q < kExpTab / 2; q += 256) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
+    issue(0);
+  }
+
+  const int vz = threadIdx.x >> 5;   // blockDim.x == 32: always zero, unknown to ptxas (see pin())
+  // cM = 2^52 + 2^51, 1 and 1/2 have an all-zero low word: they are encoded in the instruction (a DFMA / DADD takes
+  // a 32-bit immediate for the high word) and cost no register; the full-mantissa constants are pinned (see pin())
+  const double cA = pin(c_expc + 0 + vz), cL = pin(c_expc + 2), ce = pin(c_expc + 6);
+  constexpr double cM = 6755399441055744.0;
+#if RB_EXP_DEG == 2
+  constexpr double c2 = 0.5, c1 = 1.0;
+#else
+  const double c3 = pin(c_expc + 3), c2 = pin(c_expc + 4 + vz);
+  constexpr double c1 = 1.0;
+#endif
+  unsigned tab_base;
+  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(tab_base) : "l"(s_tab));
+  const int cut_hi = __double2hiint(fmin(k.tau_cut, 707.0));   // tau >= tau_cut <=> hi(tau) >= cut_hi (see above)
+  double tauA = 0.0, iWA = 0.0, TbA = 0.0, tauB = 0.0, iWB = 0.0, TbB = 0.0;
+  int i = 0;                 // segments consumed so far (both frequencies walk together)
+  int nf = 0, ns = 0;        // rb_count_steps: segments taken by the pair loops (two steps each) / single steps
+  int ia = 0;                // steps in phase A (both frequencies counted)
+  bool small = true;
+
+  // e^-tau * dd for a step known to be below the threshold (the table path of rt_integrate_rays_kernel);
+  // ndraw = fma(tau, cA, cM) (the caller may have it from the tau_cut test)
+  auto weight_nd = [&](double tauv, double ndraw, double dd) -> double {
+    const int ni_ = __double2loint(ndraw);
+    const double nd_ = ndraw - cM;
+    const double rr_ = fma(nd_, cL, -tauv);
+    const double p_ = RB_EXP_POLY(rr_);
+    double tj_;
+    unsigned ta_, ex_;
+    asm("{ .reg .b32 t; and.b32 t, %2, %4; mad.lo.u32 %0, t, 8, %3; and.b32 %1, %2, %5; }"
+        : "=r"(ta_), "=r"(ex_) : "r"(ni_), "r"(tab_base), "n"(kExpTab - 1), "n"(~(kExpTab - 1)));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj_) : "r"(ta_));
+    const double v_ = p_ * tj_;
+    int hi_;
+    asm("mad.lo.s32 %0, %1, %3, %2;" : "=r"(hi_) : "r"(ex_), "r"(__double2hiint(v_)), "n"(1 << (20 - kExpTabLog)));
+    return __hiloint2double(hi_, __double2loint(v_)) * dd;
+  };
+  auto weight = [&](double tauv, double dd) -> double { return weight_nd(tauv, fma(tauv, cA, cM), dd); };
+  // one step of frequency h (0: a, 1: b) whose optical depth tk is known: the table exponential with the tau_cut
+  // test of rt_integrate_rays_kernel's single-step path.  The step that crosses tau_cut is still accumulated (full
+  // exp(-tau) with the underflow guard), then the frequency stops.
+  auto step_known = [&](int h, double tk, double dd, double2 op) {
+    double nd = fma(tk, cA, cM);
+    int ni = __double2loint(nd);
+    nd -= cM;
+    const bool crossed = __double2hiint(tk) >= cut_hi;
+    double tc = tk;
+    if (crossed) {
+      tc = fmin(tk, 800.0);
+      nd = fma(tc, cA, cM);
+      ni = __double2loint(nd);
+      nd -= cM;
+    }
+    const double rr = fma(nd, cL, -tc);
+    const double p = RB_EXP_POLY(rr);
+    const double v = p * s_tab[ni & (kExpTab - 1)];
+    double e = __hiloint2double(__double2hiint(v) + ((ni << (20 - kExpTabLog)) & 0xFFF00000), __double2loint(v));
+    if (crossed && (unsigned)__double2hiint(nd) > (unsigned)__double2hiint(-1022.0 * kExpTab)) e = 0.0;
+    const double w = e * dd;
+    if (h) { iWB = fma(op.x, w, iWB); TbB = fma(op.y, w, TbB); }
+    else { iWA = fma(op.x, w, iWA); TbA = fma(op.y, w, TbA); }
+    ++ns;
+    if (crossed) mode &= ~(1 << h);
+  };
+
+  // shared-window addresses of this thread's ds column / operand rows in stage 0
+  const unsigned ds_a0 = (unsigned)__cvta_generic_to_shared(s_ds + threadIdx.x);
+  const unsigned q_a0 = (unsigned)__cvta_generic_to_shared(s_q + threadIdx.y * kPairRow);
+  constexpr unsigned kRowB = 8 * kPairRow * sizeof(double2);   // bytes between the operand rows of two segments
+  constexpr int small_hi = (int)(((0x3FFull - (RB_EXP_SMALL_LOG > 0 ? RB_EXP_SMALL_LOG : 1)) << 20));
+
+  for (int c = 0; any_live; ++c) {
+    cp_async_wait<0>();
+    if (!__syncthreads_or(mode != 0)) break;
+    issue(c + 1);
+    if (mode != 0) {
+      double* dsb = s_ds + (c % kStages) * kTileDs + threadIdx.x;
+      const double2* qb = s_q + (c % kStages) * kPairTileQ + threadIdx.y * kPairRow;
+      const int zrow = steps - c * kChunk;
+      if (zrow <= kChunk) dsb[zrow * 32] = 0.0;              // nothing lies below the last node
+      const int m = min(kChunk, steps - i);
+      int u = 0;
+      if (mode == 3 && m >= 4) {
+        // Trips of 2 x (two segments x two frequencies).  The optical depths are updated in place; a group the
+        // fast loops cannot finish (it leaves the small-tau range / a frequency crosses tau_cut inside it) is
+        // handed, with its four optical depths, to finish_group, which takes it one step at a time.
+        const unsigned dbase = ds_a0 + (unsigned)((c % kStages) * kTileDs * sizeof(double));
+        unsigned dpa = dbase;
+        unsigned qpa = q_a0 + (unsigned)((c % kStages) * kPairTileQ * sizeof(double2));
+        const unsigned dlast = dbase + 256u * (unsigned)(m - 4);   // last trip start with four segments left
+        double d0 = lds_f64<0>(dpa), d1, d2, d3, tA0, tB0;
+        double2 s0, s1;
+        // the group of segments (u, u+1) = rows QO, QO + kRowB of the operand tile, segment lengths D0, D1, D2
+#define RB_PAIR_TAUS(D0, D1, QO)                                                        \
+        s0 = lds_v2<(QO)>(qpa); s1 = lds_v2<(QO) + kRowB>(qpa);                         \
+        tA0 = fma(s0.x, (D0), tauA); tB0 = fma(s0.y, (D0), tauB);                       \
+        tauA = fma(s1.x, (D1), tA0); tauB = fma(s1.y, (D1), tB0);
+#define RB_PAIR_ACC(QO, WA0, WB0, WA1, WB1)                                             \
+        {                                                                               \
+          const double2 a0 = lds_v2<(QO) + 16>(qpa), b0 = lds_v2<(QO) + 32>(qpa);       \
+          const double2 a1 = lds_v2<(QO) + kRowB + 16>(qpa), b1 = lds_v2<(QO) + kRowB + 32>(qpa); \
+          iWA = fma(a0.x, (WA0), iWA); TbA = fma(a0.y, (WA0), TbA);                     \
+          iWB = fma(b0.x, (WB0), iWB); TbB = fma(b0.y, (WB0), TbB);                     \
+          iWA = fma(a1.x, (WA1), iWA); TbA = fma(a1.y, (WA1), TbA);                     \
+          iWB = fma(b1.x, (WB1), iWB); TbB = fma(b1.y, (WB1), TbB);                     \
+        }
+        auto finish_group = [&](double e0, double e1, double e2, unsigned qa) {
+          const double dd0 = e0 + e1, dd1 = e1 + e2;
+          const double tA1 = tauA, tB1 = tauB;
+          if (mode & 1) { tauA = tA0; step_known(0, tA0, dd0, lds_v2<16>(qa)); }
+          if (mode & 2) { tauB = tB0; step_known(1, tB0, dd0, lds_v2<32>(qa)); }
+          if (mode & 1) { tauA = tA1; step_known(0, tA1, dd1, lds_v2<kRowB + 16>(qa)); }
+          if (mode & 2) { tauB = tB1; step_known(1, tB1, dd1, lds_v2<kRowB + 32>(qa)); }
+          nf -= 2;                                           // counted step by step in ns
+        };
+        if (RB_EXP_SMALL_LOG > 0 && small) {
+          const double sa0 = pin(c_small + 0), sa1 = pin(c_small + 1 + vz), sa2 = pin(c_small + 2);
+#define RB_PAIR_WA(T, DD) (fma(fma((T), sa2, sa1), (T), sa0) * (DD))
+#pragma unroll 1
+          while (dpa <= dlast) {
+            d1 = lds_f64<256>(dpa); d2 = lds_f64<512>(dpa);
+            RB_PAIR_TAUS(d0, d1, 0)
+            if (max(__double2hiint(tauA), __double2hiint(tauB)) >= small_hi) goto small_exit_0;
+            {
+              const double dd0 = d0 + d1, dd1 = d1 + d2;
+              RB_PAIR_ACC(0, RB_PAIR_WA(tA0, dd0), RB_PAIR_WA(tB0, dd0), RB_PAIR_WA(tauA, dd1), RB_PAIR_WA(tauB, dd1))
+            }
+            d3 = lds_f64<768>(dpa); d0 = lds_f64<1024>(dpa);
+            RB_PAIR_TAUS(d2, d3, 2 * kRowB)
+            if (max(__double2hiint(tauA), __double2hiint(tauB)) >= small_hi) goto small_exit_1;
+            {
+              const double dd0 = d2 + d3, dd1 = d3 + d0;
+              RB_PAIR_ACC(2 * kRowB, RB_PAIR_WA(tA0, dd0), RB_PAIR_WA(tB0, dd0), RB_PAIR_WA(tauA, dd1), RB_PAIR_WA(tauB, dd1))
+            }
+            dpa += 1024; qpa += 4 * kRowB;
+          }
+          ia += 2 * (int)((dpa - dbase) >> 8);
+          goto small_done;
+        small_exit_1:
+          { const double t0 = d0; d0 = d2; d1 = d3; d2 = t0; }
+          dpa += 512; qpa += 2 * kRowB;
+        small_exit_0:
+          ia += 2 * (int)((dpa - dbase) >> 8);
+          small = false;
+          finish_group(d0, d1, d2, qpa);
+          d0 = d2; dpa += 512; qpa += 2 * kRowB;
+        small_done:;
+#undef RB_PAIR_WA
+        }
+        if ((!(RB_EXP_SMALL_LOG > 0) || !small) && mode == 3) {
+#pragma unroll 1
+          while (dpa <= dlast) {
+            d1 = lds_f64<256>(dpa); d2 = lds_f64<512>(dpa);
+            RB_PAIR_TAUS(d0, d1, 0)
+            // a frequency crosses tau_cut inside this group?
+            if (max(__double2hiint(tauA), __double2hiint(tauB)) >= cut_hi) goto cut_exit_0;
+            {
+              const double dd0 = d0 + d1, dd1 = d1 + d2;
+              const double wA0 = weight(tA0, dd0), wB0 = weight(tB0, dd0);
+              const double wA1 = weight(tauA, dd1), wB1 = weight(tauB, dd1);
+              RB_PAIR_ACC(0, wA0, wB0, wA1, wB1)
+            }
+            d3 = lds_f64<768>(dpa); d0 = lds_f64<1024>(dpa);
+            RB_PAIR_TAUS(d2, d3, 2 * kRowB)
+            if (max(__double2hiint(tauA), __double2hiint(tauB)) >= cut_hi) goto cut_exit_1;
+            {
+              const double dd0 = d2 + d3, dd1 = d3 + d0;
+              const double wA0 = weight(tA0, dd0), wB0 = weight(tB0, dd0);
+              const double wA1 = weight(tauA, dd1), wB1 = weight(tauB, dd1);
+              RB_PAIR_ACC(2 * kRowB, wA0, wB0, wA1, wB1)
+            }
+            dpa += 1024; qpa += 4 * kRowB;
+          }
+          goto cut_done;
+        cut_exit_1:
+          { const double t0 = d0; d0 = d2; d1 = d3; d2 = t0; }
+          dpa += 512; qpa += 2 * kRowB;
+        cut_exit_0:
+          finish_group(d0, d1, d2, qpa);
+          d0 = d2; dpa += 512; qpa += 2 * kRowB;
+        cut_done:;
+        }
+#undef RB_PAIR_TAUS
+#undef RB_PAIR_ACC
+        u = (int)((dpa - dbase) >> 8);
+        nf += u;
+      }
+      // one segment at a time: the chunk remainder, and the frequency that is left alone after its partner stopped
+#pragma unroll 1
+      for (; u < m && mode != 0; ++u) {
+        const double dcur = dsb[u * 32];
+        const double dd = dcur + dsb[(u + 1) * 32];
+        const double2* qr = qb + (size_t)u * 8 * kPairRow;
+        const double2 s0 = qr[0];
+        if (mode & 1) { tauA = fma(s0.x, dcur, tauA); step_known(0, tauA, dd, qr[1]); }
+        if (mode & 2) { tauB = fma(s0.y, dcur, tauB); step_known(1, tauB, dd, qr[2]); }
+        // a ghost frequency (beyond F: zero operands) never crosses: it ends with its partner
+        if (mode == 2 && !validB) mode = 0;
+      }
+      i += u;
+      if (i >= steps || (mode == 2 && !validB)) mode = 0;
+    }
+  }
+  cp_async_wait<0>();
+  if (k.step_counter) {   // measurement aid (bench.py): executed (ray, freq, segment) steps, one atomic per warp
+    unsigned long long done = 2ull * (unsigned long long)nf + (unsigned long long)ns;
+    unsigned long long done_a = (unsigned long long)ia;
+    for (int o = 16; o > 0; o >>= 1) {
+      done += __shfl_down_sync(0xffffffffu, done, o);
+      done_a += __shfl_down_sync(0xffffffffu, done_a, o);
+    }
+    if (threadIdx.x == 0) { atomicAdd(k.step_counter, done); atomicAdd(k.step_counter + 1, done_a); }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (!(h ? validB : validA)) continue;
+    const double tau = h ? tauB : tauA, iW = h ? iWB : iWA, Tb = h ? TbB : TbA;
+    double vout, wout = iW;
+    if (n < 0) vout = kTcmb;                                 // off planet (brightness.py:46-51)
+    else if (nanray || tau != tau) vout = wout = nan("");    // NaN segment below the tangent shell / NaN alpha
+    else vout = (Tb < kTcmb) ? kTcmb : Tb / iW;              // brightness.py:109-113
+    const size_t o = (size_t)r * k.F + fA + h;
+    if (k.out_f32) reinterpret_cast<float*>(k.out_Tb)[o] = (float)vout;
+    else reinterpret_cast<double*>(k.out_Tb)[o] = vout;
+    if (k.out_intW) k.out_intW[o] = (n < 0) ? 0.0 : wout;
+  }
+  progress_report(k, rt_, tid);
 }
 
 // ====================================================================================================
@@ -999,11 +1583,11 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int S = k.L - 1;
-  unsigned tile = blockIdx.y + (unsigned)k.progress.shift;
-  if (tile >= gridDim.y) tile -= gridDim.y;
-  const long long r = (long long)tile * 32 + threadIdx.x;
-  const int f = blockIdx.x * 8 + threadIdx.y;
-  const bool valid = (r < k.R) && (f < k.F);
+  const RayTile rt_ = map_ray_tile(k);                      // never a compacted launch (k.cidx == null)
+  const unsigned tile = rt_.tile;
+  const long long r = rt_.r;
+  const int f = rt_.fg * 8 + threadIdx.y;
+  const bool valid = rt_.in && (f < k.F);
   const int n = valid ? k.nseg[r] : -1;
   const bool nanray = valid && k.nanflag[r] != 0;
   const int steps = (valid && !nanray) ? n - 1 : 0;        // brightness.py:65: i = 0 .. len(ds)-2
@@ -1011,7 +1595,7 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
   // copy plan of one chunk: kMxChunk / 16 rounds of 256 x 16 bytes for the operand rows, kMxChunk / 32 rounds and 8
   // extra pieces for the float segments, each stream one contiguous piece of global memory; unchecked like the
   // FP64 kernel's (rows past the end of a tile are never consumed, the slabs carry kRtSlackBytes of slack)
-  const char* src_p = reinterpret_cast<const char*>(k.prepm) + (size_t)blockIdx.x * S * kMxRow + tid * 16;
+  const char* src_p = reinterpret_cast<const char*>(k.prepm) + (size_t)rt_.fg * S * kMxRow + tid * 16;
   const char* src_f = reinterpret_cast<const char*>(k.dsf + (size_t)tile * S * 32) + tid * 16;
   const unsigned dst = (unsigned)__cvta_generic_to_shared(s_raw) + tid * 16;
   auto issue = [&](int c) {
@@ -1152,15 +1736,7 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
     else reinterpret_cast<double*>(k.out_Tb)[o] = vout;
     if (k.out_intW) k.out_intW[o] = (n < 0) ? 0.0 : wout;
   }
-  if (k.progress.done) {
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      int c = 0;
-      while (c + 1 < k.progress.nchunks && (int)blockIdx.y >= k.progress.cut[c + 1]) ++c;
-      atomicAdd(k.progress.done + c, 1u);
-    }
-  }
+  progress_report(k, rt_, tid);
 }
 }  // namespace
 
@@ -1172,7 +1748,18 @@ int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
   const int threads = 128;
   const long long blocks = (g.R + threads - 1) / threads;
   RB_CUDA(ctx, rb_time_begin(ctx, 1));
-  ray_geometry_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(k);
+  if (g.compact) {
+    // classify (findEdge), list the rays that hit, march only those (full warps, full tiles for the integration)
+    if (!g.cidx || !g.ncomp || !g.zq || !g.blkcnt) return rb_fail(ctx, RB_ERR_INVALID, "geometry: compaction buffers missing");
+    k.cidx = g.cidx; k.ncomp = g.ncomp; k.zq = g.zq; k.blkcnt = g.blkcnt;
+    const unsigned eblocks = (unsigned)((g.R + kEdgeThreads - 1) / kEdgeThreads);
+    ray_edge_kernel<<<eblocks, kEdgeThreads, 0, ctx->stream>>>(k);
+    ray_compact_kernel<<<eblocks, kEdgeThreads, 0, ctx->stream>>>(k);
+    ray_geometry_kernel<true><<<(unsigned)blocks, threads, 0, ctx->stream>>>(k);
+    ctx->launches += 2;
+  } else {
+    ray_geometry_kernel<false><<<(unsigned)blocks, threads, 0, ctx->stream>>>(k);
+  }
   RB_CUDA(ctx, cudaGetLastError());
   RB_CUDA(ctx, rb_time_end(ctx, 1));
   ctx->launches += 1;
@@ -1200,10 +1787,20 @@ int rb_launch_ds_to_slab(rb_context* ctx, const double* in, int64_t R, int64_t R
 
 // Decide the integration path for a request of R_total rays and, for the rays-major path, build the
 // per-(layer,freq) operand slab once (shared by all ray chunks of the request).
+// rb_set_rt_tuning / RB_RT_PAIRS force the one- / two-frequency kernel (default: whichever wastes fewer frequency slots).
+static bool choose_pairs(const rb_context* ctx, int F) {
+  if (ctx->rt_pairs == 0 || F < 2) return false;
+  if (ctx->rt_pairs == 1) return true;
+  // slots executed per useful frequency; the pair kernel does ~1.2x the work per issue slot
+  const double fill1 = (double)F / (8.0 * ((F + 7) / 8)), fill2 = (double)F / (16.0 * ((F + 15) / 16));
+  return fill2 * 1.2 >= fill1;
+}
+
 int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total, bool profile, bool have_pairs,
                   RtPrep* out) {
   out->use_rays = !profile && !rt->disc_average && R_total >= 512;
   out->mixed = out->use_rays && have_pairs && ctx->rt_precision == RB_RT_MIXED;
+  out->pairs = false;
   out->prep = nullptr;
   if (!out->use_rays) return RB_OK;
   const int F = rt->n_freqs;
@@ -1219,16 +1816,42 @@ int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total,
     out->prep = scratch;
     return RB_OK;
   }
-  RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (L - 1) * 8 * sizeof(double4) + kRtSlackBytes, &scratch));
   if (!ctx->exp_tab) {
     RB_CUDA(ctx, cudaMalloc(&ctx->exp_tab, kExpTab * sizeof(double)));
     exp_tab_init_kernel<<<(kExpTab + 255) / 256, 256, 0, ctx->stream>>>(ctx->exp_tab);
     ctx->launches += 1;
   }
-  rt_prepare_kernel<<<(nel + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ngroups, (double4*)scratch);
+  out->pairs = choose_pairs(ctx, F);
+  if (out->pairs) {
+    const int ng2 = (F + 15) / 16;
+    const int nel2 = ng2 * (L - 1) * 8;
+    RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)nel2 * kPairRow * sizeof(double2) + kRtSlackBytes, &scratch));
+    rt_prepare_pairs_kernel<<<(nel2 + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ng2, (double2*)scratch);
+  } else {
+    RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (L - 1) * 8 * sizeof(double4) + kRtSlackBytes, &scratch));
+    rt_prepare_kernel<<<(nel + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ngroups, (double4*)scratch);
+  }
   RB_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
   out->prep = scratch;
+  return RB_OK;
+}
+
+int rb_launch_progress_init(rb_context* ctx, const RtLaunch& g, const RtProgress& pg, unsigned fgroups) {
+  if (!g.compact || !pg.done) return rb_fail(ctx, RB_ERR_INVALID, "rt: progress init needs a compacted launch");
+  rt_progress_init_kernel<<<1, 256, 0, ctx->stream>>>(pg, g.cidx, g.ncomp, (int)((g.R + 31) / 32), fgroups);
+  RB_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+// opt a kernel into more than 48 KB of dynamic shared memory, once per context (= per device of the process)
+template <typename K>
+static int opt_in_smem(rb_context* ctx, K kernel, size_t bytes, int slot) {
+  if (bytes > 48 * 1024 && !ctx->smem_opted[slot]) {
+    RB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    ctx->smem_opted[slot] = true;
+  }
   return RB_OK;
 }
 
@@ -1242,6 +1865,8 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
   k.tau_cut = (rt->tau_cut > 0.0) ? rt->tau_cut : INFINITY;
   k.profile_ray = profile_ray; k.out_tau = out_tau; k.out_W = out_W; k.out_Tblyr = out_Tblyr;
   const int fgroups = (k.F + 31) / 32;
+  if (g.compact && (profile_ray >= 0 || !prep.use_rays || prep.mixed))
+    return rb_fail(ctx, RB_ERR_INVALID, "rt: compacted geometry needs the FP64 rays-major integration");
   RB_CUDA(ctx, rb_time_begin(ctx, 2));
   if (profile_ray >= 0) {
     if (g.R != 1) return rb_fail(ctx, RB_ERR_INVALID, "rt: profile outputs need a single-ray launch");
@@ -1250,41 +1875,53 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     else rt_integrate_kernel<1, false, true><<<grid, block, 0, ctx->stream>>>(k);
   } else if (!prep.use_rays) {
     const int wy = 4;
-    dim3 grid((unsigned)((g.R + wy - 1) / wy), fgroups), block(32, wy);
+    const long long gx = (g.R + wy - 1) / wy;
+    if (gx > 2147483647LL) return rb_fail(ctx, RB_ERR_INVALID, "rt: too many rays for one launch");
+    dim3 grid((unsigned)gx, fgroups), block(32, wy);
     if (k.disc) rt_integrate_kernel<1, true, false><<<grid, block, 0, ctx->stream>>>(k);
     else rt_integrate_kernel<1, false, false><<<grid, block, 0, ctx->stream>>>(k);
   } else {
-    // rays-major mapping: CTAs of 32 rays x 8 frequencies; operands prepared by rb_rt_prepare
+    // rays-major mapping: CTAs of 32 rays x 8 (16: pair kernel) frequencies in a 1-D grid, the frequency groups
+    // of a ray tile adjacent in launch order; operands prepared by rb_rt_prepare
     k.step_counter = ctx->step_counter;
     if (progress) k.progress = *progress;
-    dim3 block(32, 8), grid((k.F + 7) / 8, (unsigned)((g.R + 31) / 32));
-    if (grid.y > 65535) return rb_fail(ctx, RB_ERR_INVALID, "rt: more than 2M rays per launch are not supported");
+    k.fgroups = (unsigned)(prep.pairs ? (k.F + 15) / 16 : (k.F + 7) / 8);
+    k.ntiles = (unsigned)((g.R + 31) / 32);
+    const unsigned long long nblocks = (unsigned long long)k.fgroups * k.ntiles;
+    if (nblocks > 2147483647ULL) return rb_fail(ctx, RB_ERR_INVALID, "rt: too many (ray tile, frequency group) blocks for one launch");
+    dim3 block(32, 8), grid((unsigned)nblocks);
     if (prep.mixed) {
       if (!g.dsf) return rb_fail(ctx, RB_ERR_INVALID, "rt: mixed-precision integration without the float ds slab");
       k.dsf = g.dsf;
       k.prepm = prep.prep;
-      static bool opted_in_m[64] = {false};
-      if (kMixedSmemBytes > 48 * 1024 && !opted_in_m[ctx->device & 63]) {
-        RB_CUDA(ctx, cudaFuncSetAttribute(rt_integrate_rays_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kMixedSmemBytes));
-        opted_in_m[ctx->device & 63] = true;
-      }
+      RB_TRY(opt_in_smem(ctx, rt_integrate_rays_mixed_kernel, kMixedSmemBytes, 0));
       rt_integrate_rays_mixed_kernel<<<grid, block, kMixedSmemBytes, ctx->stream>>>(k);
       RB_CUDA(ctx, cudaGetLastError());
       RB_CUDA(ctx, rb_time_end(ctx, 2));
       ctx->launches += 1;
       return RB_OK;
     }
-    k.prep = (const double4*)prep.prep;
-    k.exp_tab = ctx->exp_tab;
-    constexpr size_t smem = kExpTab * sizeof(double) + kRaysSmemBytes;
-    static_assert(smem <= 227 * 1024, "shared memory limit");
-    static bool opted_in[64] = {false};
-    if (smem > 48 * 1024 && !opted_in[ctx->device & 63]) {
-      RB_CUDA(ctx, cudaFuncSetAttribute(rt_integrate_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      opted_in[ctx->device & 63] = true;
+    if (g.compact) {
+      // sky pixels first: the compacted launch never visits them
+      k.cidx = g.cidx; k.ncomp = g.ncomp;
+      const long long nout = (long long)g.R * k.F;
+      rt_fill_miss_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, ctx->stream>>>(g.zq, g.R, k.F, out_Tb, out_intW, k.out_f32);
+      ctx->launches += 1;
     }
-    rt_integrate_rays_kernel<<<grid, block, smem, ctx->stream>>>(k);
+    k.exp_tab = ctx->exp_tab;
+    if (prep.pairs) {
+      k.prep2 = (const double2*)prep.prep;
+      constexpr size_t smem = kExpTab * sizeof(double) + kPairsSmemBytes;
+      static_assert(smem <= 227 * 1024, "shared memory limit");
+      RB_TRY(opt_in_smem(ctx, rt_integrate_pairs_kernel, smem, 1));
+      rt_integrate_pairs_kernel<<<grid, block, smem, ctx->stream>>>(k);
+    } else {
+      k.prep = (const double4*)prep.prep;
+      constexpr size_t smem = kExpTab * sizeof(double) + kRaysSmemBytes;
+      static_assert(smem <= 227 * 1024, "shared memory limit");
+      RB_TRY(opt_in_smem(ctx, rt_integrate_rays_kernel, smem, 2));
+      rt_integrate_rays_kernel<<<grid, block, smem, ctx->stream>>>(k);
+    }
   }
   RB_CUDA(ctx, cudaGetLastError());
   RB_CUDA(ctx, rb_time_end(ctx, 2));

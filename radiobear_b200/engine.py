@@ -32,6 +32,12 @@ def rt_precision(ctx=None):
     return (ctx or _lib.get_context()).rt_precision()
 
 
+def set_rt_tuning(pairs=-1, compact=True, ctx=None):
+    """Work decomposition of the batched FP64 ray integration (rb_set_rt_tuning): two frequencies per thread
+    (-1 automatic, 0, 1) and ray compaction.  Results do not depend on it."""
+    (ctx or _lib.get_context()).set_rt_tuning(pairs, compact)
+
+
 UNITS = {'invcm': 0, 'dBperkm': 1}
 COSHAPE = {'voigt': 0, 'vvw': 1, 'diff': 2}
 

@@ -8,7 +8,8 @@ scratch work directory bootstrapped the way scripts/initial_planet_setup.py:12-3
 
     python tests/golden/make_golden.py [section ...]
 
-sections: atm fileio plugins plugins_nh3_extra plugins_nh3_full plugins_notrunc alpha rays tb neptune uranus image   (default: all)
+sections: atm fileio plugins plugins_nh3_extra plugins_nh3_full plugins_notrunc alpha rays tb neptune uranus image
+          image_full ring c3_full c5_saturn   (default: all; the last four take ~10 min each on 8 cores)
 
 Every array is float64 exactly as the reference produced it; nothing is post-processed.
 Reference defects driven around: log-sweep strings and float image
@@ -446,6 +447,160 @@ def sec_image():
     save('image_c4.npz', freqs=np.array(freqs), grid=grid, pick_iy_ix=pick, tb=np.array(tbs), imsize=n)
 
 
+
+# ---------------------------------------------------------------------------- round-2 sections (SURVEY 8d sizes)
+# These run the reference over thousands of rays; they are spread over a fork pool (one Planet per worker, the
+# reference is single-threaded).  RB_GOLDEN_PROCS sets the pool size (default: all cores).
+_W = {}
+
+
+def _pool(n_items, init, *initargs):
+    import multiprocessing as mp
+    procs = int(os.environ.get('RB_GOLDEN_PROCS', os.cpu_count() or 1))
+    return mp.get_context('fork').Pool(max(1, min(procs, n_items)), initializer=init, initargs=initargs)
+
+
+def _quiet(fn, *a, **kw):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **kw)
+
+
+def _image_grid(bstep=0.005):
+    grid = -1.0 * np.flipud(np.arange(bstep, 1.5 + bstep, bstep))      # set_utils.py:65-77
+    return np.concatenate((grid, np.arange(0.0, 1.5 + bstep, bstep)))
+
+
+def _w_tb_init(freqs):
+    j = planet('jupiter')
+    _quiet(j.alpha_layers, freqs=freqs, atmos=j.atmos)
+    _W['j'], _W['freqs'] = j, freqs
+
+
+def _w_tb(b):
+    j = _W['j']
+    tb = _quiet(j.bright.single, list(b), _W['freqs'], j.atmos[0], j.alpha[0], j.config.orientation)
+    return np.array(tb, dtype=np.float64)
+
+
+def sec_image_full():
+    """Config C4 at the size SURVEY 8d states: 288 seeded on-disc pixels (r < 0.97), 64 limb-ring pixels
+    (0.97 <= r < 1.01: finite / NaN mix) and 16 off-disc pixels of the 601 x 601 grid, 64 freqs 1..100 GHz, each
+    through the unmodified Brightness.single (brightness.py:30-126)."""
+    freqs = list(np.linspace(1, 100, 64))
+    grid = _image_grid()
+    rng = np.random.default_rng(2026101702)
+    jq = planet('jupiter')
+    q = jq.config.Rpol / jq.config.Req
+    xx, yy = np.meshgrid(grid, grid)
+    rr = np.sqrt(xx**2 + (yy / q)**2)
+    on = np.argwhere(rr < 0.97)
+    ring = np.argwhere((rr >= 0.97) & (rr < 1.01))
+    off = np.argwhere(rr >= 1.01)
+    pick = np.concatenate([on[rng.choice(len(on), 288, replace=False)],
+                           ring[rng.choice(len(ring), 64, replace=False)],
+                           off[rng.choice(len(off), 16, replace=False)]])
+    blist = [(grid[ix], grid[iy]) for (iy, ix) in pick]
+    t0 = time.time()
+    with _pool(len(blist), _w_tb_init, freqs) as pool:
+        tbs = pool.map(_w_tb, blist, chunksize=4)
+    print('  image_full {} pixels {:.1f} s'.format(len(blist), time.time() - t0))
+    save('image_c4_full.npz', freqs=np.array(freqs), grid=grid, pick_iy_ix=pick, tb=np.array(tbs), imsize=len(grid))
+
+
+def _w_geo_init(_):
+    _W['j'] = planet('jupiter')
+
+
+def _w_geo(b):
+    from radiobear import raypath
+    j = _W['j']
+    ray = _quiet(raypath.compute_ds, j.atmos[0], list(b), j.config.orientation, gtype=None, verbose=False)
+    if ray.ds is None:
+        return (-1, 0, -1, 0.0)
+    ds = np.asarray(ray.ds, dtype=np.float64)
+    n = len(ds)
+    bad = np.nonzero(np.isnan(ds))[0]
+    first_nan = int(bad[0]) if len(bad) else -1
+    used_nan = int(first_nan >= 0 and first_nan <= n - 2)          # Brightness.single uses ds[0 .. n-2]
+    return (n, used_nan, first_nan, float(np.nansum(ds)))
+
+
+def sec_ring():
+    """Geometry-only classification of EVERY pixel of the limb ring of the C4 grid in one quadrant (x >= 0, y >= 0;
+    the orientation is (0, 0), so the other three are mirror images): 0.93 < r < 1.02 with r = sqrt(x^2 + (y/q)^2).
+    Per pixel: number of segments raypath.compute_ds returns (-1: ray misses), whether a segment Brightness.single
+    uses is NaN (=> Tb is NaN), index of the first NaN segment, nansum(ds).  raypath.py:108-273."""
+    grid = _image_grid()
+    jq = planet('jupiter')
+    q = jq.config.Rpol / jq.config.Req
+    xx, yy = np.meshgrid(grid, grid)
+    rr = np.sqrt(xx**2 + (yy / q)**2)
+    sel = np.argwhere((rr > 0.93) & (rr < 1.02) & (xx >= 0.0) & (yy >= 0.0))
+    blist = [(grid[ix], grid[iy]) for (iy, ix) in sel]
+    t0 = time.time()
+    with _pool(len(blist), _w_geo_init, 0) as pool:
+        res = pool.map(_w_geo, blist, chunksize=16)
+    print('  ring {} pixels {:.1f} s'.format(len(blist), time.time() - t0))
+    res = np.array(res)
+    save('ring_quadrant.npz', grid=grid, iy_ix=sel, nseg=res[:, 0].astype(np.int32), used_nan=res[:, 1].astype(np.int8),
+         first_nan=res[:, 2].astype(np.int32), nansum_ds=res[:, 3], q=q)
+
+
+def sec_c3_full():
+    """Config C3 in full: Planet.run(freqs 1..50 GHz (50), b='0.0:1.0:0.01<0') -- all 100 limb-profile rays the
+    reference derives from the string (set_utils.py:52-63), each through Brightness.single."""
+    freqs = list(np.linspace(1, 50, 50))
+    jq = planet('jupiter')
+    from radiobear import set_utils
+    bq = set_utils.set_b('0.0:1.0:0.01<0', [1, 1], Rpol=jq.config.Rpol, Req=jq.config.Req)
+    blist = [tuple(b) for b in bq.b]
+    t0 = time.time()
+    with _pool(len(blist), _w_tb_init, freqs) as pool:
+        tbs = pool.map(_w_tb, blist, chunksize=2)
+    print('  c3_full {} rays {:.1f} s'.format(len(blist), time.time() - t0))
+    save('c3_full.npz', freqs=np.array(freqs), b=np.array(blist), tb=np.array(tbs), data_type=np.array(bq.data_type))
+
+
+def _w_c5_init(_):
+    import importlib
+    s = planet('saturn', regridType=4096)
+    cpath = os.path.join(REF, 'radiobear', 'constituents', 'nh3')
+    sys.path.append(cpath)
+    _W['s'], _W['mod'], _W['path'] = s, importlib.import_module('nh3_dbs_sjs'), cpath
+
+
+def _w_c5(args):
+    lyr, freqs = args
+    a = _W['s'].atmos[0]
+    C = a.config.C
+    g = a.gas[:, lyr]
+    r = _quiet(_W['mod'].alpha, freqs, g[C['T']], g[C['P']], g, C, {}, units='invcm', truncate_freq=None,
+               truncate_strength=None, path=_W['path'], verbose=False)
+    return np.asarray(r, dtype=np.float64)
+
+
+def sec_c5_saturn():
+    """Config C5 on its concrete input: Planet('saturn', regridType=4096) x np.linspace(1, 100, 4096) x NH3 only
+    (nh3_dbs_sjs, nh3_dbs_sjs.py:6-26 called like alpha.py:210-213): 96 layers -- every 64th of the 4096 plus 16 around
+    each of the 400 bar and 2000 bar switches of the pressure blend."""
+    s = planet('saturn', regridType=4096)
+    a = s.atmos[0]
+    P = a.gas[a.config.C['P']]
+    L = len(P)
+    freqs = list(np.linspace(1, 100, 4096))
+    i400, i2000 = int(np.argmin(np.abs(P - 400.0))), int(np.argmin(np.abs(P - 2000.0)))
+    lyrs = sorted(set(list(range(0, L, 64)) + list(range(max(0, i400 - 8), min(L, i400 + 8))) +
+                      list(range(max(0, i2000 - 8), min(L, i2000 + 8)))))
+    t0 = time.time()
+    with _pool(len(lyrs), _w_c5_init, 0) as pool:
+        res = pool.map(_w_c5, [(l, freqs) for l in lyrs], chunksize=1)
+    print('  c5_saturn {} layers x {} freqs {:.1f} s'.format(len(lyrs), len(freqs), time.time() - t0))
+    save('c5_saturn.npz', layers=np.array(lyrs, dtype=np.int32), freqs=np.array(freqs), alpha=np.array(res),
+         gas=a.gas, C_keys=np.array(sorted(a.config.C, key=lambda k: a.config.C[k])))
+
+
 FILEIO_CASES = [('spectrum', [[0.0, 0.0], [0.5, 0.25]], [[100.123, 200.5, 300.25], [90.1, 80.2, 70.3]]),
                 ('spectrum', ['disc'], [[100.123, 200.5, 300.25]]),
                 ('profile', [[0.1 * i, 0.0] for i in range(6)], [[100.0 + i, 200.5 + i, 300.25 + i] for i in range(6)]),
@@ -471,7 +626,8 @@ def sec_fileio():
 
 
 SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins_nh3_full': sec_plugins_nh3_full, 'plugins_h2_orton': sec_plugins_h2_orton, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
-            'rays': sec_rays, 'tb': sec_tb, 'neptune': sec_neptune, 'uranus': sec_uranus, 'image': sec_image}
+            'rays': sec_rays, 'tb': sec_tb, 'neptune': sec_neptune, 'uranus': sec_uranus, 'image': sec_image,
+            'image_full': sec_image_full, 'ring': sec_ring, 'c3_full': sec_c3_full, 'c5_saturn': sec_c5_saturn}
 
 if __name__ == '__main__':
     import warnings

@@ -254,3 +254,85 @@ def test_h2_orton_host_table():
                 assert np.max(relerr(got, ref)) < 1e-12
     with pytest.raises(ValueError):
         catalogs.orton_table([80000.0], 'e')
+
+
+# ---- round 2: the SURVEY 8d sized fixtures (make_golden.py sections ring, c3_full, image_full, c5_saturn) ----------
+def _geom_args(a):
+    LP = keymap(a['LP_keys'])
+    return (a['property'][LP['R']], a['property'][LP['N']]), (float(a['Req']), float(a['Rpol']), a['orientation'],
+                                                             str(a['gtype']), str(a['limb']))
+
+
+def test_ring_quadrant_classification_subset():
+    """Every 19th pixel of the limb-ring quadrant (hit / miss, segment count, NaN in the segments Brightness.single
+    uses, first NaN layer): the oracle reproduces the reference's classification exactly.  (The GPU test covers all
+    5177 pixels.)"""
+    ring = golden('ring_quadrant.npz')
+    a = golden('atm_jupiter.npz')
+    (req, nr), rest = _geom_args(a)
+    grid = ring['grid']
+    sel = np.arange(0, len(ring['nseg']), 19)
+    assert (ring['nseg'][sel] < 0).any() and ring['used_nan'][sel].any() and (ring['used_nan'][sel] == 0).any()
+    for k in sel:
+        iy, ix = ring['iy_ix'][k]
+        out = ro.compute_ds(req, nr, [grid[ix], grid[iy]], *rest)
+        if ring['nseg'][k] < 0:
+            assert out['ds'] is None
+            continue
+        ds = np.asarray(out['ds'])
+        assert len(ds) == ring['nseg'][k]
+        bad = np.nonzero(np.isnan(ds))[0]
+        assert (int(bad[0]) if len(bad) else -1) == ring['first_nan'][k]
+        assert abs(np.nansum(ds) / ring['nansum_ds'][k] - 1.0) < 1e-12
+
+
+def test_c3_full_profile_rays():
+    """Config C3 in full: the 100 rays of b = '0.0:1.0:0.01<0'.  NaN rays at the same b; Tb of every 7th ray at
+    every 7th frequency within 1e-6 K."""
+    from radiobear_b200 import set_utils
+    a = golden('atm_jupiter.npz')
+    c3 = golden('c3_full.npz')
+    C, Cl = keymap(a['C_keys']), keymap(a['Cl_keys'])
+    rv = set_utils.set_b('0.0:1.0:0.01<0', [1, 1], Rpol=float(a['Rpol']), Req=float(a['Req']))
+    assert np.array_equal(np.array(rv.b), c3['b'])
+    sel = sorted(set(list(range(0, 100, 7)) + [96, 97, 98, 99]))
+    lay = ao.get_layers(c3['freqs'][::7], a['gas'], a['cloud'], C, Cl, dict(formalisms_of(a)),
+                        other_dicts={'h2': {'h2state': 'e'}}, truncate_strength=TRUNC)
+    Tb = _tb_oracle(a, lay, [c3['b'][i] for i in sel])
+    ref = c3['tb'][sel][:, ::7]
+    assert np.isnan(ref).any()
+    assert np.array_equal(np.isnan(Tb), np.isnan(ref))
+    assert np.nanmax(np.abs(Tb - ref)) < 1e-6
+
+
+def test_image_full_golden_is_what_8d_asks_for():
+    """The C4 fixture holds >= 256 finite on-disc pixels, NaN-ring pixels and off-disc pixels; a slice of it through
+    the oracle."""
+    a = golden('atm_jupiter.npz')
+    im = golden('image_c4_full.npz')
+    ref = im['tb']
+    nan = np.isnan(ref).any(axis=1)
+    sky = (ref == 2.725).all(axis=1)
+    assert (~nan & ~sky).sum() >= 256 and nan.sum() >= 8 and sky.sum() >= 16 and ref.shape[1] == 64
+    C, Cl = keymap(a['C_keys']), keymap(a['Cl_keys'])
+    sel = list(range(0, 288, 24)) + list(range(288, 352, 8)) + [352, 360]
+    lay = ao.get_layers(im['freqs'][::16], a['gas'], a['cloud'], C, Cl, dict(formalisms_of(a)),
+                        other_dicts={'h2': {'h2state': 'e'}}, truncate_strength=TRUNC)
+    grid = im['grid']
+    Tb = _tb_oracle(a, lay, [[grid[ix], grid[iy]] for iy, ix in im['pick_iy_ix'][sel]])
+    assert np.array_equal(np.isnan(Tb), np.isnan(ref[sel][:, ::16]))
+    assert np.nanmax(np.abs(Tb - ref[sel][:, ::16])) < 1e-6
+
+
+def test_c5_saturn_oracle_rows():
+    """Config C5's concrete input (Saturn regridType=4096 x 4096 freqs x nh3_dbs_sjs): oracle against the reference's
+    plugin on layers from all three branches of the pressure blend."""
+    g = golden('c5_saturn.npz')
+    C = keymap(g['C_keys'])
+    P = g['gas'][C['P']][g['layers']]
+    pick = [0, 20, 40, int(np.argmax(P >= 400)) - 1, int(np.argmax(P >= 400)), int(np.argmax(P >= 400)) + 5,
+            int(np.argmax(P > 2000)) - 1, int(np.argmax(P > 2000)), len(P) - 1]
+    for k in pick:
+        col = g['gas'][:, g['layers'][k]]
+        out = ao.FORMALISMS['nh3_dbs_sjs'](g['freqs'], col[C['T']], col[C['P']], col, C, {}, units='invcm')
+        assert np.max(relerr(out, g['alpha'][k])) < 1e-12
