@@ -49,6 +49,7 @@ struct GeoK {
   int* ncomp;    // length of the list (device scalar)
   double* zq;    // [R] edge depth found by findEdge, NaN for a ray that misses
   int* blkcnt;   // [ceil(R / kEdgeThreads)] hits per block of rays
+  const double* dr2;  // [L-1] R_l+1^2 - R_l^2 (layer_dr2_kernel)
 };
 
 __device__ __forceinline__ void rot2planet(const GeoK& g, double x, double y, double z, double& ox, double& oy,
@@ -74,7 +75,9 @@ __device__ __forceinline__ void lat_sc(double v, double& s, double& c) {
 
 // ---- findEdge (raypath.py:60-105): march zQ down by 0.005 until inside the outer shell ----------------
 // rays with b^2 >= 1 (raypath.py:126-127; NaN impact parameters too) never hit
-__device__ __forceinline__ bool find_edge(const GeoK& g, double bx, double by, double& zq) {
+// (not inlined: the classification kernel and the plain geometry kernel must run the very same instructions, so that
+//  compacted and plain launches give the same bits)
+__device__ __noinline__ bool find_edge(const GeoK& g, double bx, double by, double& zq) {
   const double bb = bx * bx + by * by;
   const double q2 = g.q * g.q;
   const double rNorm = g.radius[0];
@@ -123,6 +126,12 @@ __device__ __forceinline__ double rcp_seeded_scaled(double x, double c) {
   const double eq = fma(-x, r0, 1.0);
   const double rc = r0 * c;
   return fma(rc, fma(eq, eq, eq), rc);
+}
+
+// R_l+1^2 - R_l^2 for every shell pair, once per launch instead of three FP64 instructions per (ray, segment)
+__global__ void layer_dr2_kernel(const double* __restrict__ radius, int L, double* __restrict__ dr2) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < L - 1) dr2[l] = (radius[l + 1] - radius[l]) * (radius[l + 1] + radius[l]);
 }
 
 // ---- compaction of the rays that hit the planet (rays-major FP64 integration) --------------------------
@@ -179,8 +188,14 @@ __global__ void __launch_bounds__(kEdgeThreads) ray_compact_kernel(const __grid_
 }
 
 // one thread per ray (COMPACT: per entry of the list of hitting rays)
+#ifndef RB_GEO_CTAS
+#define RB_GEO_CTAS 8
+#endif
+// 64 registers: 8 CTAs of 128 rays per SM = 151 k rays in flight, so that the ~117 k rays of the C4 image are ONE
+// wave (every ray is the same ~1000-step chain: a second, nearly empty wave doubles the kernel time -- measured with
+// 80 registers, 6 CTAs per SM: 918 CTAs on 888 slots, 0.50 ms)
 template <bool COMPACT>
-__global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant__ GeoK g) {
+__global__ void __launch_bounds__(128, RB_GEO_CTAS) ray_geometry_kernel(const __grid_constant__ GeoK g) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int S = g.L - 1;
   long long r = t;
@@ -280,7 +295,6 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
   double X = rd0 * rd0;
   double sq = fabs(rd0);                                     // sqrt(X)
   double shape2 = shape * shape;
-  double Rl = g.radius[0], Rn = g.radius[1];
   bool outward = !(rd0 < 0.0);                               // only possible after a reflection (below)
   int cool = 0;                                              // careful steps to take before speculating again
   while (layer < S) {
@@ -292,12 +306,10 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     if (cool == 0 && !outward && g.limb != RB_LIMB_SEC && layer + kSpec <= S) {
       const double X0 = X, sq0 = sq, sh0 = shape2;
       double dsv[kSpec];
-      double Ra = Rl, Rb = Rn;
       bool bad = false;
 #pragma unroll
       for (int j = 0; j < kSpec; ++j) {
-        const double Rc = g.radius[min(layer + j + 2, g.L - 1)];
-        const double Xn = fma(shape2, (Rb - Ra) * (Rb + Ra), X);
+        const double Xn = fma(shape2, g.dr2[layer + j], X);
         const double sqn = sqrt_seeded(Xn);
         const double inve = rcp_seeded_scaled(Xn + perp2, -e2);
         const double ds = sq - sqn;
@@ -307,7 +319,7 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
         bad |= !(ds >= 0.0) | (yn == 0.0) | !(d <= 0.0);
         dsv[j] = ds;
         shape2 = fma(yn * yn, inve, 1.0);
-        X = Xn; sq = sqn; Ra = Rb; Rb = Rc;
+        X = Xn; sq = sqn;
       }
       if (!bad) {
 #pragma unroll
@@ -316,7 +328,6 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
           if (outf) outf[(size_t)(layer + j) * kDsStride] = (float)dsv[j];
         }
         layer += kSpec; count += kSpec;
-        Rl = Ra; Rn = Rb;
         continue;
       }
       X = X0; sq = sq0; shape2 = sh0;
@@ -324,8 +335,7 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     }
     if (cool > 0) --cool;
     // ---- careful step: one segment with every test of the reference in place ----
-    const double Rnn = g.radius[min(layer + 2, g.L - 1)];
-    const double Xn = fma(shape2, (Rn - Rl) * (Rn + Rl), X);
+    const double Xn = fma(shape2, g.dr2[layer], X);
     double sqn = sqrt_seeded(Xn);                            // NaN for Xn < 0 like np.sqrt
     if (Xn == 0.0) sqn = 0.0;
     double ds = sq - sqn;
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     if (ds < 0.0) break;                                     // raypath.py:212-216
     if (g.limb == RB_LIMB_SEC) {
       const double sh = sqrt(shape2);
-      ds = fabs(Rn * sh - Rl * sh) / mu;                     // raypath.py:218-219 (also replaces a NaN)
+      ds = fabs(g.radius[layer + 1] * sh - g.radius[layer] * sh) / mu;   // raypath.py:218-219 (also replaces a NaN)
     }
     out[(size_t)layer * kDsStride] = ds;
     ++count;
@@ -355,7 +365,7 @@ __global__ void __launch_bounds__(128) ray_geometry_kernel(const __grid_constant
     // n is parallel to (q x, y, q z), so cos t_inc < 0  <=>  d = q (r.s - sy y) + sy y > 0.
     const double syy = sy * yn;
     const double d = fma(g.q, -sqn - syy, syy);
-    X = Xn; sq = sqn; shape2 = shape2n; Rl = Rn; Rn = Rnn;
+    X = Xn; sq = sqn; shape2 = shape2n;
     ++layer;
     if (g.limb == RB_LIMB_SEC || !(d <= 0.0) || outward) {
       // grazing ray (rare) or the secant mode (position advances by the secant ds, not along the chord):
@@ -1747,7 +1757,12 @@ int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
   k.limb = g.limb; k.R = g.R; k.Rpad = g.Rpad; k.b = g.b; k.ds = g.ds; k.dsf = g.dsf; k.nseg = g.nseg; k.nanflag = g.nanflag;
   const int threads = 128;
   const long long blocks = (g.R + threads - 1) / threads;
+  void* p_dr2;
+  RB_TRY(rb_ensure(ctx, RB_BUF_DR2, (size_t)g.L * 8, &p_dr2));
   RB_CUDA(ctx, rb_time_begin(ctx, 1));
+  layer_dr2_kernel<<<(g.L + 255) / 256, 256, 0, ctx->stream>>>(g.radius, g.L, (double*)p_dr2);
+  ctx->launches += 1;
+  k.dr2 = (const double*)p_dr2;
   if (g.compact) {
     // classify (findEdge), list the rays that hit, march only those (full warps, full tiles for the integration)
     if (!g.cidx || !g.ncomp || !g.zq || !g.blkcnt) return rb_fail(ctx, RB_ERR_INVALID, "geometry: compaction buffers missing");

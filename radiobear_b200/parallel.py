@@ -145,7 +145,10 @@ class SharedHostExchange:
     gather-to-rank-0 + one D2H copy this removes the NVLink gather and spreads the 92 MB (C4) copy over
     N PCIe links.  Control words live in a small shared segment: rank 0 publishes (seq, segment id) for
     call number seq, every rank stores seq into its own `done` slot when its copy has landed, rank 0 waits
-    for all slots.  Segments are recycled once the array handed out earlier is no longer referenced.
+    for all slots.  Segments are recycled once nothing references the memory handed out earlier: every result is
+    a view of a fresh "owner" array over the segment (numpy points the .base of every derived view -- reshape,
+    slices, astype(copy=False) -- at that owner), and rank 0 keeps only a weak reference to the owner, so the
+    segment is free exactly when the owner has been collected.
     """
     _CTRL_WORDS = 8 + 256
 
@@ -157,8 +160,8 @@ class SharedHostExchange:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.seq = 0
-        self.segments = {}          # seg_id -> (SharedMemory, uint8 ndarray, pinned?)
-        self.handed_out = {}        # rank 0: seg_id -> root array given to the caller
+        self.segments = {}          # seg_id -> [shared file, uint8 ndarray over it, pinned?]
+        self.handed_out = {}        # rank 0: seg_id -> (weakref to the owner array of the result handed out, nbytes)
         self._cur = None
         self.base = None
         self.ctrl_shm = None
@@ -218,7 +221,6 @@ class SharedHostExchange:
     def begin(self, total_rows, tail_shape, dtype, pin):
         """Collective: agree on the result segment of this call; returns it as [total_rows, *tail_shape]
         (every rank sees the same memory; write only your own rows), page-locked for CUDA when `pin`."""
-        import sys
         self.seq += 1
         seq = self.seq
         dtype = np.dtype(dtype)
@@ -226,13 +228,10 @@ class SharedHostExchange:
         ctrl = self.ctrl
         if self.rank == 0:
             seg_id = None
-            for sid in list(self.handed_out):
-                root = self.handed_out[sid]
-                # references: the dict, `root`, getrefcount's argument -> nobody else holds the array
-                if root.nbytes == nbytes and sys.getrefcount(root) <= 3:
+            for sid, (ref, size) in self.handed_out.items():
+                if size == nbytes and ref() is None:    # the owner array (hence every view of it) is gone
                     seg_id = sid
                     break
-            root = None
             if seg_id is None:
                 seg_id = len(self.handed_out)
             seg = self._segment(seg_id, nbytes, create=seg_id not in self.segments, pin=pin)
@@ -243,7 +242,10 @@ class SharedHostExchange:
             self._spin(lambda: ctrl[0] >= seq, 'rank 0 to publish the result segment')
             seg_id = int(ctrl[1])
             seg = self._segment(seg_id, nbytes, create=False, pin=pin)
-        self._cur = (seg_id, seg.view(dtype).reshape((int(total_rows),) + tuple(tail_shape)))
+        # a fresh owner per call: an ndarray straight over the shared file's buffer is the array numpy collapses
+        # the .base of every derived view to
+        owner = np.ndarray((max(nbytes, 0),), dtype=np.uint8, buffer=self.segments[seg_id][0].buf)
+        self._cur = (seg_id, owner[:nbytes].view(dtype).reshape((int(total_rows),) + tuple(tail_shape)), owner)
         return self._cur[1]
 
     def finish(self):
@@ -251,13 +253,14 @@ class SharedHostExchange:
         assembled array; the other ranks return None at once."""
         seq = self.seq
         ctrl = self.ctrl
-        seg_id, root = self._cur
+        import weakref
+        seg_id, root, owner = self._cur
         self._cur = None
         ctrl[8 + self.rank] = seq
         if self.rank != 0:
             return None
         self._spin(lambda: all(ctrl[8 + r] >= seq for r in range(self.world)), 'the other ranks to copy their blocks')
-        self.handed_out[seg_id] = root
+        self.handed_out[seg_id] = (weakref.ref(owner), owner.nbytes)
         return root
 
     def deliver(self, local, parts, tail_shape, dtype):

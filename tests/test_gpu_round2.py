@@ -146,34 +146,43 @@ def test_c5_saturn_4096_layers_against_reference(eng):
     assert np.all(np.isfinite(slab)) and slab.min() >= 0.0
 
 
-def test_decompositions_are_bit_identical(eng, c4):
-    """One / two frequencies per thread x plain / compacted ray order on the full C4 cube: the same bits, NaN ring
-    and sky included (rb_set_rt_tuning); float32 output and integrated_W through the compacted pair path."""
+def test_decompositions_agree(eng, c4):
+    """One / two frequencies per thread x plain / compacted ray order on the full C4 cube.  Compaction changes no
+    bit (same kernel, same arithmetic per ray; NaN ring and sky included).  The two kernels run the same operations
+    per step but hand a ray from the small-tau polynomial to the table exponential at different segments (groups of
+    4 vs 2 segments, and a pair leaves the polynomial together): they agree to 1e-9 K, five orders inside the bar."""
     a, b, slab, T = c4['a'], c4['b'], c4['slab'], c4['T']
     ref = c4['cube'].reshape(-1, 64)
+    res = {}
     try:
         for pairs, compact in ((0, False), (1, False), (0, True), (1, True)):
             eng.set_rt_tuning(pairs, compact)
-            got = eng.rt_batch(b=b, alpha_slab=slab, T=T, want_intW=(pairs == 1), **geom(a))
-            assert np.array_equal(got['Tb'], ref, equal_nan=True), (pairs, compact)
-            if pairs == 1:
-                if compact:
-                    assert np.array_equal(got['integrated_W'], iw, equal_nan=True)
-                iw = got['integrated_W'].copy()
+            got = eng.rt_batch(b=b, alpha_slab=slab, T=T, want_intW=True, **geom(a))
+            res[(pairs, compact)] = (got['Tb'].copy(), got['integrated_W'].copy())
+        for pairs in (0, 1):
+            assert np.array_equal(res[(pairs, False)][0], res[(pairs, True)][0], equal_nan=True), pairs
+            assert np.array_equal(res[(pairs, False)][1], res[(pairs, True)][1], equal_nan=True), pairs
+        one, two = res[(0, True)], res[(1, True)]
+        assert np.array_equal(np.isnan(one[0]), np.isnan(two[0])) and np.array_equal(one[0] == 2.725, two[0] == 2.725)
+        assert np.nanmax(np.abs(one[0] - two[0])) < 1e-9
+        ok = ~np.isnan(one[1]) & (one[1] > 0)
+        assert np.max(np.abs(two[1][ok] / one[1][ok] - 1.0)) < 1e-12
+        assert np.array_equal(res[(1, True)][0], ref, equal_nan=True)          # the default path is the pair kernel here
         # ragged frequency counts through the pair kernel (ghost partner, partial groups)
         for nf in (2, 3, 17, 33):
             eng.set_rt_tuning(0, True)
-            one = eng.rt_batch(b=b[180000:184000], alpha_slab=np.ascontiguousarray(slab[:, :nf]), T=T, **geom(a))['Tb'].copy()
+            o1 = eng.rt_batch(b=b[180000:184000], alpha_slab=np.ascontiguousarray(slab[:, :nf]), T=T, **geom(a))['Tb'].copy()
             eng.set_rt_tuning(1, True)
-            two = eng.rt_batch(b=b[180000:184000], alpha_slab=np.ascontiguousarray(slab[:, :nf]), T=T, **geom(a))['Tb']
-            assert np.array_equal(one, two, equal_nan=True), nf
-        # small tau_cut: both kernels stop at the same step
+            o2 = eng.rt_batch(b=b[180000:184000], alpha_slab=np.ascontiguousarray(slab[:, :nf]), T=T, **geom(a))['Tb']
+            assert o2.shape == (4000, nf) and np.array_equal(np.isnan(o1), np.isnan(o2))
+            assert np.nanmax(np.abs(o1 - o2)) < 1e-9, nf
+        # small tau_cut: both kernels stop at the same step (one rule: tau >= tau_cut by the high words)
         for cut in (5.0, 0.3):
             eng.set_rt_tuning(0, False)
-            one = eng.rt_batch(b=b[180000:200000], alpha_slab=slab, T=T, tau_cut=cut, **geom(a))['Tb'].copy()
+            o1 = eng.rt_batch(b=b[180000:200000], alpha_slab=slab, T=T, tau_cut=cut, **geom(a))['Tb'].copy()
             eng.set_rt_tuning(1, True)
-            two = eng.rt_batch(b=b[180000:200000], alpha_slab=slab, T=T, tau_cut=cut, **geom(a))['Tb']
-            assert np.array_equal(one, two, equal_nan=True), cut
+            o2 = eng.rt_batch(b=b[180000:200000], alpha_slab=slab, T=T, tau_cut=cut, **geom(a))['Tb']
+            assert np.nanmax(np.abs(o1 - o2)) < 1e-9, cut
     finally:
         eng.set_rt_tuning(-1, True)
     f32 = eng.rt_batch(b=b, alpha_slab=slab, T=T, out_f32=True, **geom(a))['Tb']
@@ -182,7 +191,7 @@ def test_decompositions_are_bit_identical(eng, c4):
 
 def test_widely_separated_frequency_pair(eng, c4):
     """A pair whose members stop hundreds of layers apart (1 GHz next to 100 GHz): the frequency left alone finishes
-    on the single-segment path with the same bits as the one-frequency kernel."""
+    on the single-segment path; same values as the one-frequency kernel (1e-9 K)."""
     a, b, T = c4['a'], c4['b'], c4['T']
     slab = _slab(eng, a, np.array([1.0, 100.0, 3.0, 60.0]))
     try:
@@ -192,4 +201,5 @@ def test_widely_separated_frequency_pair(eng, c4):
         two = eng.rt_batch(b=b[170000:190000], alpha_slab=slab, T=T, **geom(a))['Tb']
     finally:
         eng.set_rt_tuning(-1, True)
-    assert np.array_equal(one, two, equal_nan=True) and np.isfinite(one).any()
+    assert np.array_equal(np.isnan(one), np.isnan(two)) and np.isfinite(one).any()
+    assert np.nanmax(np.abs(one - two)) < 1e-9
