@@ -96,6 +96,9 @@ class Alpha:
             src = np.load(self.alphafile)
             for sf in self.saved_fields:
                 setattr(self, sf, src[sf])
+            # the npz holds a numpy string array; the reference looks constituents up by key (alpha.py:151-192), a
+            # dict `scale` therefore works on a file cache too
+            self.ordered_constituents = [str(c) for c in src['ordered_constituents']]
         elif save_type == 'memory':
             for sf in self.saved_fields:
                 setattr(self, sf, getattr(self.memory, sf))

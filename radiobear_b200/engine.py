@@ -92,6 +92,7 @@ def build_alpha_desc(formalisms, L, F, gas_rows, gas_dict, cloud_rows, cloud_dic
 def scale_matrix(scale, ordered, L):
     """alpha.py:235-259 + 151-192: turn the user's scale (number / per-layer list / dict by constituent)
     into a [C][L] matrix, or None for 'no scaling'."""
+    ordered = [str(c) for c in ordered]
     C_ = len(ordered)
     if isinstance(scale, dict):
         for k, v in scale.items():
@@ -132,8 +133,6 @@ def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formal
 
     Replaces the layer loop of Alpha.get_layers (alpha.py:298-300) and the plugin calls under it.
     """
-    ctx = ctx or _lib.get_context()
-    ctx.use_own_stream()
     freqs, T, P = f64(np.atleast_1d(freqs)), f64(np.atleast_1d(T)), f64(np.atleast_1d(P))
     gas = f64(gas)
     if gas.ndim == 1:
@@ -145,6 +144,12 @@ def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formal
         cloud = f64(cloud)
         if cloud.ndim == 1:
             cloud = np.ascontiguousarray(cloud[:, None])
+        if cloud.shape[1] != L:
+            # regridType none: the cloud file may hold fewer layers than the gas file (the reference fails with an
+            # IndexError in the clouds plugin); the kernel indexes cloud[c][layer] for every layer
+            raise ValueError('cloud has {} layers, the gas profile {}'.format(cloud.shape[1], L))
+    ctx = ctx or _lib.get_context()
+    ctx.use_own_stream()
     formalisms = list(formalisms)
     prepare_catalogs(ctx, formalisms, truncate_strength, truncate_freq, freqs=freqs, other_dicts=other_dicts)
     d = build_alpha_desc(formalisms, L, F, gas.shape[0], gas_dict, 0 if cloud is None else cloud.shape[0], cloud_dict,
@@ -171,6 +176,8 @@ def alpha_layers_dev(freqs_t, T_t, P_t, gas_t, gas_dict, cloud_t=None, cloud_dic
     if any(name == 'h2_orton' for _, name in formalisms) and freqs_host is None:
         freqs_host = freqs_t.cpu().numpy()          # the Orton table is prepared on the host per frequency vector
     prepare_catalogs(ctx, formalisms, truncate_strength, truncate_freq, freqs=freqs_host, other_dicts=other_dicts)
+    if gas_t.shape[1] != L or P_t.shape[0] != L or (cloud_t is not None and cloud_t.shape[1] != L):
+        raise ValueError('T, P, gas and cloud disagree on the number of layers')
     d = build_alpha_desc(formalisms, L, F, gas_t.shape[0], gas_dict, 0 if cloud_t is None else cloud_t.shape[0],
                          cloud_dict, other_dicts, units)
     for t in (freqs_t, T_t, P_t, gas_t):

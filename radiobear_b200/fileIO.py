@@ -84,3 +84,101 @@ class FileIO(object):
                 fp.write('# f = {}\n'.format(data.f[k]))
             for row in plane:
                 fp.write('\t'.join('{:7.2f}'.format(v) for v in row).strip() + '\n')
+
+    # ------------------------------------------------------------------ reading back (fileIO.py:109-330)
+    def flist(self, files=None, tag=None):
+        """File names to read: an index / list of indices into the sorted directory listing (filtered by `tag`),
+        a name, a comma-separated string or a list of names (fileIO.py:109-155).  `None` takes every match
+        (the reference prompts on stdin)."""
+        names = sorted(os.path.join(self.directory, fn) for fn in os.listdir(self.directory)
+                       if fn[0] != '.' and (tag is None or tag in fn)) if os.path.isdir(self.directory) else []
+        if isinstance(files, str):
+            return files.split(',')
+        if isinstance(files, (list, tuple)) and files and isinstance(files[0], str):
+            return list(files)
+        if not names:
+            print("No files found in {}".format(self.directory))
+            return []
+        if files is None:
+            return names
+        idx = [files] if isinstance(files, int) else list(files)
+        return [names[i] for i in idx]
+
+    def read_header(self, header_text):
+        """'# key: value' lines -> dict; '#*' marks the keys copied onto the Data object (fileIO.py:305-330)."""
+        header = {}
+        self.starred_header_keys = []
+        for line in header_text:
+            body = line.strip('#').strip()
+            if 'K@' in line:
+                header['label-line'] = body
+                continue
+            key, value = (body.split(':', 1) + [''])[:2] if ':' in line else (body.split()[0] if body.split() else '', body)
+            key, value = key.strip(), value.strip()
+            if key in header:
+                key = 'other_{}'.format(key)
+            if key.startswith('*'):
+                key = key.strip('*').strip()
+                self.starred_header_keys.append(key)
+            header[key] = value
+        if 'res' in header:
+            self.resolution = header['res'].split()[0]
+        return header
+
+    def read(self, fn=None, tag='dat', file_type='spectrum'):
+        """Read spectrum / profile / image files written by `write` (or by the reference): fills self.files and
+        self.data[filename] (Data with header, f, b, Tb -- Tb[b][f] like DataReturn; an image is Tb[row][col],
+        or Tb[row][col][f] for the multi-frequency blocks this writer produces)."""
+        from . import data_handling
+        self.files, self.data = [], {}
+        for filename in self.flist(fn, tag):
+            if file_type.lower() != 'all' and file_type.lower() not in os.path.basename(filename).lower():
+                continue
+            try:
+                lines = open(filename).read().splitlines()
+            except IOError:
+                print(filename + " not found - removing from list")
+                continue
+            d = data_handling.Data()
+            d.header = self.read_header([ln for ln in lines if ln.startswith('#')])
+            for key in self.starred_header_keys:
+                if key in d.allowed_parameters:
+                    setattr(d, key, d.header[key])
+            kind = d.header.get('type', file_type).lower()
+            rows = [[float(x) for x in ln.split()] for ln in lines if ln.strip() and not ln.startswith('#')
+                    and not ln.startswith('disc')]
+            if 'image' in kind:
+                planes, cur = [], []
+                for ln in lines:
+                    if ln.startswith('# f ='):
+                        if cur:
+                            planes.append(cur)
+                        cur = []
+                    elif ln.strip() and not ln.startswith('#'):
+                        cur.append([float(x) for x in ln.split()])
+                planes.append(cur)
+                d.Tb = np.array(planes[0]) if len(planes) == 1 else np.stack([np.array(p) for p in planes], axis=2)
+                d.f = np.array([float(ln.split('=')[1]) for ln in lines if ln.startswith('# f =')])
+                d.b = getattr(self, 'resolution', None)
+            else:
+                labels = d.header.get('label-line', '').split()[2:]
+                tab = np.array(rows)
+                if 'spectrum' in kind:
+                    d.f = tab[:, 0]
+                    d.Tb = tab[:, 1:].T
+                    d.b = ['disc'] if labels == ['disc'] else \
+                        np.array([[float(x) for x in lb.strip('()').split(',')] for lb in labels])
+                else:                                   # profile: 'bx by  Tb(f0) Tb(f1) ...'
+                    d.f = np.array([float(x) for x in labels])
+                    d.b = tab[:, :2]
+                    d.Tb = tab[:, 2:]
+            d.type = kind
+            self.files.append(filename)
+            self.data[filename] = d
+        return self.data
+
+    def show(self, property='all'):
+        for filename, d in getattr(self, 'data', {}).items():
+            print(filename)
+            d.show(include=d.allowed_parameters if property == 'all' else
+                   ([property] if isinstance(property, str) else property))

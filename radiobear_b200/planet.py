@@ -84,6 +84,8 @@ class Planet:
         self.alpha = [rbalpha.Alpha(idnum=i, config=self.config, log=self.log, load_formal=load_formal,
                                     verbose=verbose) for i in range(len(self.atmos))]
         self.bright = rbbright.Brightness(config=self.config, log=self.log, verbose=verbose)
+        from . import fileIO
+        self.fIO = fileIO.FileIO(directory=getattr(self.config, 'output_directory', 'Output'))   # planet_base.py:115-118
         self.Tb = []
         self.rNorm = self.tip = self.rotate = None
 
@@ -220,11 +222,14 @@ class Planet:
             self.data_return.set('logfile', self.log.logfile)
         if self.verbose:
             print("RT calc took {:.3f} s".format(utils.timer(runStop - runStart)))
-        if getattr(self.config, 'write_output_files', False):
-            from . import fileIO
-            fn = '{}_{}_{}.dat'.format(self.planet, self.data_type, runStart.strftime("%Y%m%d_%H%M%S"))
-            fileIO.FileIO(directory=self.config.output_directory).write(
-                os.path.join(self.config.output_directory, fn), self.data_return)
+        # output files are written by the process that holds the result (rank 0 of a sharded run); the name carries
+        # the image block like the reference's (planet.py:142-146, planet_base.py:197-207)
+        if getattr(self.config, 'write_output_files', False) and self.Tb is not None:
+            block_postfix = '_'
+            if self.data_type == 'image' and abs(self.block[1]) > 1:
+                block_postfix = '_{:02d}of{:02d}_'.format(self.block[0], abs(self.block[1]))
+            fn = '{}_{}{}{}.dat'.format(self.planet, self.data_type, block_postfix, runStart.strftime("%Y%m%d_%H%M%S"))
+            self.fIO.write(os.path.join(self.config.output_directory, fn), self.data_return)
         return self.data_return
 
     def _local_points(self):
@@ -257,5 +262,7 @@ class Planet:
         h['gtype'] = '# gtype: {}'.format(self.config.gtype)
         h['radii'] = '# radii:  {:.1f}  {:.1f}  km'.format(self.config.Req, self.config.Rpol)
         h['distance'] = '# distance:  {} km'.format(self.config.distance)
+        if getattr(self.config, 'write_log_file', False) and self.log is not None:
+            h['log-file:'] = '#* logfile: {}'.format(self.log.logfile)
         h['start'] = "#* start: {:%Y-%m-%d %H:%M:%S}".format(run_start)
         h['stop'] = "#* stop: {:%Y-%m-%d %H:%M:%S}".format(run_stop)

@@ -238,3 +238,56 @@ def test_saturn_regrid_4096_against_live_reference(tmp_path, monkeypatch):
     assert np.max(relerr(a.gas, ref.gas)) < 1e-10
     assert np.max(relerr(a.cloud, ref.cloud)) < 1e-10
     assert np.max(relerr(a.property, ref.property)) < 1e-10
+
+
+# ---- round 2: advisor findings ------------------------------------------------------------------------------------
+def test_scale_matrix_accepts_constituents_read_back_from_a_file_cache():
+    """get_alpha='file' hands Alpha.ordered_constituents back as a numpy string array (np.load); a dict scale must
+    still resolve its keys (the reference looks constituents up by key, alpha.py:151-192)."""
+    import numpy as np
+    from radiobear_b200 import engine
+    ordered = np.array(['h2', 'h2o', 'nh3'])
+    m = engine.scale_matrix({'nh3': [2.0, 3.0], 'h2': [0.5, 0.25]}, ordered, 2)
+    assert m.shape == (3, 2) and np.array_equal(m, [[0.5, 0.25], [1.0, 1.0], [2.0, 3.0]])
+    with pytest.raises(ValueError):
+        engine.scale_matrix({'co': [1.0, 1.0]}, ordered, 2)
+
+
+def test_cloud_layer_count_is_validated_before_any_device_work():
+    import numpy as np
+    from radiobear_b200 import engine
+    gas = np.ones((16, 5))
+    C = {'Z': 0, 'T': 1, 'P': 2, 'H2': 3, 'HE': 4, 'NH3': 6}
+    with pytest.raises(ValueError, match='cloud has 3 layers'):
+        engine.alpha_layers([1.0, 2.0], gas[1], gas[2], gas, C, cloud=np.zeros((12, 3)), cloud_dict={'NH3': 6},
+                            formalisms=[('nh3', 'nh3_hs')])
+
+
+def test_fileio_read_back_round_trip(tmp_path):
+    """FileIO.read / flist (fileIO.py:109-330): spectrum, disc spectrum, profile and image files written by
+    FileIO.write come back as Data with the same f, b and Tb (to the precision of the text format)."""
+    import numpy as np
+    from radiobear_b200 import fileIO, data_handling
+    io = fileIO.FileIO(directory=str(tmp_path))
+    cases = [('spectrum', [[0.0, 0.0], [0.5, 0.25]], [[100.123, 200.5, 300.25], [90.1, 80.2, 70.3]]),
+             ('spectrum', ['disc'], [[100.123, 200.5, 300.25]]),
+             ('profile', [[0.1 * i, 0.0] for i in range(6)], [[100.0 + i, 200.5 + i, 300.25 + i] for i in range(6)]),
+             ('image', [[0, 0]] * 12, np.arange(12.0).reshape(3, 4) + 0.5)]
+    for n, (typ, b, Tb) in enumerate(cases):
+        d = data_handling.Data()
+        d.set('f', [1.0, 10.5, 22.0] if typ != 'image' else [22.0])
+        d.set('freqUnit', 'GHz')
+        d.set('b', b)
+        d.set('Tb', Tb)
+        d.set('type', typ)
+        d.set('header', {'z': '# z line', 'data-type': '#* type:  ' + typ, 'start': '#* start: 2026-01-01 00:00:00'})
+        fn = io.write(str(tmp_path / 'jupiter_{}_{}.dat'.format(typ, n)), d)
+        out = io.read(fn, file_type=typ)[fn]
+        assert out.type == typ and out.start == '2026-01-01 00:00:00'
+        assert np.allclose(np.asarray(out.Tb), np.asarray(d.Tb), atol=6e-3)
+        if typ != 'image':
+            assert np.allclose(out.f, d.f)
+        if typ == 'profile':
+            assert np.allclose(out.b, np.asarray(b), atol=1e-3)
+    assert len(io.flist(None, 'dat')) == 4 and io.flist(1, 'dat') == [sorted(io.flist(None, 'dat'))[1]]
+    assert len(io.read(None, tag='dat', file_type='spectrum')) == 2
