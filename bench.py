@@ -42,23 +42,24 @@ BSTEP = 0.005
 NFREQ = 64
 METRIC = 'Tb pixel*freq/s (Jupiter image cube b=0.005, 64 freqs 1-100 GHz, on-disc pixels)'
 UNIT = 'pixel*freq/s'
-# rt_integrate_rays_kernel, per executed (ray, freq, segment) step:
-#   table phase  7 DFMA + 2 DMUL + 2 DADD = 11 FP64 instructions, 18 flops
-#   small-tau phase (tau < 2^-11)  5 DFMA + 1 DMUL + 1 DADD = 7 FP64 instructions, 12 flops
-RT_FLOPS_PER_STEP = 18.0
-RT_FP64_INSTR_PER_STEP = 11.0
-RT_FLOPS_PER_SMALL_STEP = 12.0
-RT_FP64_INSTR_PER_SMALL_STEP = 7.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one rt_integrate_rays_kernel launch of this workload at N=1
-RT_DRAM_BYTES_N1 = 1088100000
-RT_DRAM_SOURCE = 'ncu --set full, profiles/r1_final_rt_integrate_rays_ncu_full.txt (1.014 GB read + 0.074 GB written)'
+# rt_integrate_pairs_kernel (two frequencies per thread), per executed (ray, freq, segment) step (DESIGN.md 3.3;
+# counted in the SASS of the two hot loops, profiles/r2_sass_rt_integrate_pairs.txt: 8 steps per trip):
+#   table phase      6.5 DFMA + 2 DMUL + 2 DADD = 10.5 FP64 instructions, 17 flops   (ds_i + ds_i+1 is shared by the pair)
+#   small-tau phase (tau < 2^-11)  4.5 DFMA + 1 DMUL + 1 DADD = 6.5 FP64 instructions, 11 flops
+RT_FLOPS_PER_STEP = 17.0
+RT_FP64_INSTR_PER_STEP = 10.5
+RT_FLOPS_PER_SMALL_STEP = 11.0
+RT_FP64_INSTR_PER_SMALL_STEP = 6.5
+# dram__bytes_read.sum + dram__bytes_write.sum of one rt_integrate_pairs_kernel launch of this workload at N=1
+RT_DRAM_BYTES_N1 = 1008942848
+RT_DRAM_SOURCE = 'ncu --set full, profiles/r2_rt_integrate_pairs_ncu_full.txt (0.946 GB read + 0.063 GB written)'
 RT_DRAM_BYTES_N1_MIXED = 645195776
 RT_DRAM_SOURCE_MIXED = 'ncu --set full, profiles/r1_mixed_rt_integrate_rays_mixed_ncu_full.txt (0.505 GB read + 0.140 GB written)'
-# SASS instructions (cuobjdump) and shared-memory wavefronts (128 B/clk/SM crossbar) per executed segment-step of the
-# two integration kernels, {precision: (phase A, phase B)}: the resources the kernels are actually short of
-RT_SASS_PER_STEP = {'f64': (12.75, 21.5), 'mixed': (10.0, 15.25)}
-RT_SMEM_WAVEFRONTS_PER_STEP = {'f64': (4.5, 8.5), 'mixed': (2.0, 2.0)}
-RT_KERNEL = {'f64': 'rt_integrate_rays_kernel', 'mixed': 'rt_integrate_rays_mixed_kernel'}
+# SASS instructions (cuobjdump, hot loops) and shared-memory wavefronts (128 B/clk/SM data pipe) per executed segment-step
+# of the integration kernels, {precision: (phase A, phase B)}
+RT_SASS_PER_STEP = {'f64': (10.0, 19.25), 'mixed': (10.0, 15.25)}
+RT_SMEM_WAVEFRONTS_PER_STEP = {'f64': (2.5, 8.0), 'mixed': (2.0, 2.0)}
+RT_KERNEL = {'f64': 'rt_integrate_pairs_kernel', 'mixed': 'rt_integrate_rays_mixed_kernel'}
 WORKLOAD = 'C4: Jupiter full image b=0.005 (601x601 px) x 64 freqs 1-100 GHz, 1000 layers, alpha+geometry+RT per step'
 
 
@@ -146,6 +147,19 @@ def cpu_sample(cores, n_pix_per_core=6, n_lay_per_core=24, pool=None):
     return value, desc, time.perf_counter() - t00
 
 
+def stock_reference_record():
+    """The UNMODIFIED reference timed next to the port on the same sample -- in the build container, where
+    /root/reference exists (tools/time_stock_reference.py); the GPU box has no reference to run."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, 'profiles', 'r2_stock_reference_timing.json')))
+    except (OSError, ValueError):
+        return None
+    return {'kind': 'reference', 'value': rec['reference']['value'], 'unit': rec['reference']['unit'], 'cores': 1,
+            'port_value_same_host': rec['port']['value'], 'port_over_reference': rec['port_over_reference'],
+            'sample': rec['sample'], 'where': rec['host']['where'],
+            'source': 'profiles/r2_stock_reference_timing.json (tools/time_stock_reference.py)'}
+
+
 def run_reference(args):
     import multiprocessing as mp
     rank = int(os.environ.get('RANK', '0'))
@@ -168,7 +182,8 @@ def run_reference(args):
             'warmup': args.warmup, 'ms_per_step': 1e3 * n_on * NFREQ / value, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic image grid over the Jupiter default atmosphere fixture',
             'config': {'workload': WORKLOAD, 'pixels': 'on-disc'},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc,
+                             'stock_reference': stock_reference_record()},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
@@ -280,13 +295,19 @@ class ClockSampler:
         return out
 
 
-def alpha_c5(ctx, dev, reps=5, full=False):
+def alpha_c5(ctx, dev, reps=5, full=False, world=1, rank=0):
     """full=True: the untrimmed NH3 line lists (415 + 1301 + 4198 = 5914 lines, SURVEY 8d "full catalog").
     Secondary metric of BASELINE.json: alpha layer*freq*line / s on config C5 (synthetic 4096-layer
     atmosphere x 4096 freqs x NH3 catalog, formalism nh3_dbs_sjs; SURVEY 8d: T~U(80,1800) K,
-    P log-U(1e-2,5e3) bar, X_NH3 log-U(1e-7,1e-3), X_H2 = 0.86, X_He = 0.135, seed 0)."""
+    P log-U(1e-2,5e3) bar, X_NH3 log-U(1e-7,1e-3), X_H2 = 0.86, X_He = 0.135, seed 0).
+
+    world > 1: the frequencies are split into contiguous blocks, one per rank; every rank computes
+    its [L][F/world] block and one NCCL all_gather + a transposing copy leave the full [L][F] slab on every GPU
+    (what the ray integration of every rank needs).  Timed with CUDA events around compute + collective, max over
+    ranks; `value` is the whole job."""
     import torch
-    from radiobear_b200 import engine, catalogs
+    import torch.distributed as dist
+    from radiobear_b200 import engine, catalogs, parallel
     from oracle import alpha_oracle as ao
     rng = np.random.default_rng(0)
     L = F = 4096
@@ -308,37 +329,66 @@ def alpha_c5(ctx, dev, reps=5, full=False):
     evals = float(nlines.sum()) * F
     flops = (10.0 * float(n_br.sum()) + 8.0 * float(n_gr.sum())) * F          # + 1 reciprocal each (not counted)
     t64 = dict(dtype=torch.float64, device=dev)
+    parts = parallel.partition_even(F, world)
+    lo, hi = parts[rank]
+    wmax = max(e - s_ for s_, e in parts)
     g_t = torch.tensor(gas, **t64).contiguous()
-    f_t, T_t, P_t = torch.tensor(freqs, **t64), torch.tensor(gas[C['T']], **t64), torch.tensor(P, **t64)
-    out = torch.empty((L, F), **t64)
+    f_t, T_t, P_t = torch.tensor(freqs[lo:hi], **t64), torch.tensor(gas[C['T']], **t64), torch.tensor(P, **t64)
+    block = torch.zeros((L, wmax), **t64)            # this rank's frequencies (padded to the widest block)
+    local = block if wmax == hi - lo else torch.empty((L, hi - lo), **t64)
+    out = block if world == 1 else torch.empty((L, F), **t64)
+    gathered = torch.empty((world, L, wmax), **t64) if world > 1 else None
     forms = [('nh3', 'nh3_dbs_sjs')]
-    ms = []
+    ms, ms_k = [], []
     catalogs.use_full_nh3_catalog(full)
     try:
         for i in range(reps + 2):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-            engine.alpha_layers_dev(f_t, T_t, P_t, g_t, C, formalisms=forms, out=out, freqs_host=freqs, ctx=ctx)
+            engine.alpha_layers_dev(f_t, T_t, P_t, g_t, C, formalisms=forms, out=local, freqs_host=freqs[lo:hi], ctx=ctx)
             e1.record()
+            if world > 1:
+                if local is not block:
+                    block[:, :hi - lo].copy_(local)
+                dist.all_gather_into_tensor(gathered, block)
+                if wmax * world == F:
+                    out.view(L, world, wmax).copy_(gathered.permute(1, 0, 2))
+                else:
+                    for r_, (s_, e_) in enumerate(parts):
+                        out[:, s_:e_].copy_(gathered[r_, :, :e_ - s_])
+            e2.record()
             torch.cuda.synchronize()
             if i >= 2:
-                ms.append(e0.elapsed_time(e1))
+                ms.append(e0.elapsed_time(e2))
+                ms_k.append(e0.elapsed_time(e1))
     finally:
         catalogs.use_full_nh3_catalog(False)
-    t = float(np.mean(ms)) * 1e-3
-    # parity spot check against the oracle + its speed on one host core
+    tt = torch.tensor([float(np.mean(ms)), float(np.mean(ms_k))], **t64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t, t_kernel = float(tt[0].item()) * 1e-3, float(tt[1].item()) * 1e-3
+    if rank != 0:
+        return None
+    # parity spot check against the oracle + its speed on one host core (layers spread over the three pressure
+    # branches, frequencies over every rank's block)
     lay = [7, 1234, 4000]
     t0 = time.perf_counter()
     ref = ao.get_layers(freqs, gas, np.zeros((1, L)), C, {}, {'nh3': 'nh3_dbs_sjs'}, layers=lay,
                         cat=ao.LineCatalog(full_nh3=True) if full else None)
     t_cpu = time.perf_counter() - t0
-    got = out[lay].cpu().numpy().T
+    got = out[lay][:, :F].cpu().numpy().T
     rel = float(np.nanmax(np.abs(got - ref) / np.abs(ref)))
     cpu_rate = float(nlines[lay].sum()) * F / t_cpu
     return {'workload': 'C5: 4096 layers x 4096 freqs x NH3 (nh3_dbs_sjs{}), synthetic'.format(
                 ', full catalog: 415 + 1301 + 4198 lines' if full else ', shipped catalog: 415 + 201 + 198 lines'),
             'metric': 'alpha layer*freq*line/s',
-            'value': evals / t, 'ms': t * 1e3, 'line_evals': evals, 'max_rel_err_vs_oracle': rel,
+            'value': evals / t, 'ms': t * 1e3, 'kernel_ms': t_kernel * 1e3, 'n_gpus': world,
+            'sharding': 'none' if world == 1 else 'contiguous frequency blocks per rank + all_gather (NCCL) of the [L][F/N] slabs: '
+                        'every rank ends with the full [L][F] slab',
+            'line_evals': evals, 'max_rel_err_vs_oracle': rel,
             'fp64_tflops_algorithmic': flops / t / 1e12,
             'flops_per_line_eval': '10 (Ben-Reuven) / 8 (Gross) + 1 reciprocal (SURVEY 8d)',
             'cpu_port_value_1core': cpu_rate}
@@ -363,10 +413,7 @@ def run_gpu(args):
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     if world > 1:
-        if 'RB_NCCL_DEBUG' in os.environ:
-            os.environ['NCCL_DEBUG'] = os.environ['RB_NCCL_DEBUG']
-        else:
-            os.environ.pop('NCCL_DEBUG', None)
+        # NCCL_DEBUG is left as the launcher set it: its lines go to stderr (fd 1 points there until the JSON line)
         dist.init_process_group('nccl', device_id=dev)
     ctx = _lib.get_context(local)
     ctx.enable_timing(True)
@@ -525,6 +572,10 @@ def run_gpu(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = n_on * F / float(e2e_t.item())
 
+    # secondary metric: config C5 absorption, frequency-sharded over the ranks (every rank takes part)
+    a5_short = alpha_c5(ctx, dev, world=world, rank=rank)
+    a5_full = alpha_c5(ctx, dev, full=True, world=world, rank=rank) if os.environ.get('RB_BENCH_SKIP_C5_FULL') is None else None
+
     if rank == 0:
         peaks = {}
         try:
@@ -548,37 +599,48 @@ def run_gpu(args):
         sass_a, sass_b = RT_SASS_PER_STEP[precision]
         wf_a, wf_b = RT_SMEM_WAVEFRONTS_PER_STEP[precision]
         warp_cycles = n_sms * sm_hz * (rt_ms * 1e-3)          # SM-cycles of the launch
-        roofline = {'bound': 'hbm', 'kernel': RT_KERNEL[precision], 'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9,
-                    'peak': hbm_peak, 'unit': 'GB/s', 'frac': rt_bytes / (rt_ms * 1e-3) / 1e9 / hbm_peak,
-                    'traffic': (RT_DRAM_BYTES_N1 if precision == 'f64' else RT_DRAM_BYTES_N1_MIXED) if world == 1 else None,
-                    'traffic_source': RT_DRAM_SOURCE if precision == 'f64' else RT_DRAM_SOURCE_MIXED,
-                    'peak_source': peak_src, 'ms_per_launch': rt_ms, 'launches_per_step': rt_chunks,
-                    'note': 'at F=64 the kernel is issue / shared-memory / FP64 bound, not HBM-bound (SURVEY 8d): see issue, smem, fp64',
-                    # what actually binds: warp-instruction issue slots (4 schedulers per SM, 1 instruction per clock
-                    # each) and the shared-memory crossbar (1 wavefront = 128 B per clock per SM)
-                    'issue': {'sass_per_step_phase_a': sass_a, 'sass_per_step_phase_b': sass_b,
-                              'frac': (float(steps_small) * sass_a + steps_b * sass_b) / 32.0 / (4.0 * warp_cycles)},
-                    'smem': {'wavefronts_per_step_phase_a': wf_a, 'wavefronts_per_step_phase_b': wf_b,
-                             'frac': (float(steps_small) * wf_a + steps_b * wf_b) / 32.0 / warp_cycles,
-                             'peak': '128 B/clk/SM (B300_MICROARCH.md, LDS/STS)'},
-                    'sm_mhz_used': sm_hz / 1e6,
-                    'segment_steps_executed': int(steps_executed), 'segment_steps_small_tau': int(steps_small),
-                    'segment_steps_all': rt_steps_all}
+        hbm = {'achieved': rt_bytes / (rt_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+               'frac': rt_bytes / (rt_ms * 1e-3) / 1e9 / hbm_peak, 'algorithmic_bytes': int(rt_bytes), 'peak_source': peak_src,
+               'note': 'SURVEY 8d bytes: ds of the on-disc rays + alpha slab + T + Tb out; at F = 64 every ds byte feeds 64 '
+                       'frequencies, so HBM is 4 % busy and does not bind'}
+        common = {'kernel': RT_KERNEL[precision],
+                  'traffic': (RT_DRAM_BYTES_N1 if precision == 'f64' else RT_DRAM_BYTES_N1_MIXED) if world == 1 else None,
+                  'traffic_source': RT_DRAM_SOURCE if precision == 'f64' else RT_DRAM_SOURCE_MIXED,
+                  'ms_per_launch': rt_ms, 'launches_per_step': rt_chunks, 'hbm': hbm,
+                  # the other two resources the kernel runs close to: warp-instruction issue slots (4 schedulers per SM,
+                  # 1 instruction per clock each) and the shared-memory data pipe (1 wavefront = 128 B per clock per SM)
+                  'issue': {'sass_per_step_phase_a': sass_a, 'sass_per_step_phase_b': sass_b,
+                            'frac': (float(steps_small) * sass_a + steps_b * sass_b) / 32.0 / (4.0 * warp_cycles),
+                            'note': 'hot-loop instructions only (static SASS count x executed steps)'},
+                  'smem': {'wavefronts_per_step_phase_a': wf_a, 'wavefronts_per_step_phase_b': wf_b,
+                           'frac': (float(steps_small) * wf_a + steps_b * wf_b) / 32.0 / warp_cycles,
+                           'peak': '128 B/clk/SM (B300_MICROARCH.md, LDS/STS)'},
+                  'sm_mhz_used': sm_hz / 1e6,
+                  'segment_steps_executed': int(steps_executed), 'segment_steps_small_tau': int(steps_small),
+                  'segment_steps_all': rt_steps_all}
         if precision == 'f64':
-            roofline['fp64'] = {'achieved_tflops': rt_flops / (rt_ms * 1e-3) / 1e12, 'peak_tflops': fp64_peak,
-                             'frac': rt_flops / (rt_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                             'flops_per_segment_step': RT_FLOPS_PER_STEP, 'fp64_instr_per_segment_step': RT_FP64_INSTR_PER_STEP,
-                             'pipe_frac': (rt_instr / (rt_ms * 1e-3) / 1e12) / (fp64_peak / 2.0) if fp64_peak else None,
-                             'flops_per_small_tau_step': RT_FLOPS_PER_SMALL_STEP, 'fp64_instr_per_small_tau_step': RT_FP64_INSTR_PER_SMALL_STEP,
-                             'segment_steps_small_tau': int(steps_small),
-                             'peak_source': 'rb_probe_fp64_peak (DFMA, same box, same run)',
-                             'segment_steps_executed': int(steps_executed), 'segment_steps_all': rt_steps_all,
-                             'note': 'flops counted over the segment-steps actually executed (in-kernel counter, untimed pass); '
-                                     'the tau > tau_cut exit skips the rest of each ray'}
+            # the binding resource of the dominant kernel at F = 64: the FP64 pipe (compute-bound for F >~ 4)
+            tf = rt_flops / (rt_ms * 1e-3) / 1e12
+            roofline = {'bound': 'fp64', 'achieved': tf, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                        'frac': tf / fp64_peak if fp64_peak else None,
+                        'peak_source': 'rb_probe_fp64_peak: independent DFMA chains on every SM, same box, same run '
+                                       '(MEASURED_PEAKS.json has no FP64 entry)',
+                        'flops_per_segment_step': RT_FLOPS_PER_STEP, 'fp64_instr_per_segment_step': RT_FP64_INSTR_PER_STEP,
+                        'flops_per_small_tau_step': RT_FLOPS_PER_SMALL_STEP,
+                        'fp64_instr_per_small_tau_step': RT_FP64_INSTR_PER_SMALL_STEP,
+                        'pipe_frac': (rt_instr / (rt_ms * 1e-3) / 1e12) / (fp64_peak / 2.0) if fp64_peak else None,
+                        'note': 'flops counted over the segment-steps actually executed (in-kernel counter, untimed pass); the '
+                                'tau >= tau_cut exit skips the rest of each ray; pipe_frac counts FP64 instructions (a DADD / '
+                                'DMUL occupies the pipe like a DFMA)'}
+            roofline.update(common)
         else:
-            roofline['mixed'] = {'fp64_instr_per_step_phase_b': 2, 'mufu_per_step_phase_b': 1,
-                                 'note': 'optical depth in FP64 (2 DFMA per step in phase B, none in phase A), exp on the SFU, '
-                                         'weights and chunk sums in FP32 (FFMA2 / FMUL2), chunk sums accumulated in FP64'}
+            roofline = {'bound': 'hbm', 'achieved': hbm['achieved'], 'peak': hbm_peak, 'unit': 'GB/s', 'frac': hbm['frac'],
+                        'peak_source': peak_src,
+                        'mixed': {'fp64_instr_per_step_phase_b': 2, 'mufu_per_step_phase_b': 1,
+                                  'note': 'optical depth in FP64 (2 DFMA per step in phase B, none in phase A), exp on the SFU, '
+                                          'weights and chunk sums in FP32 (FFMA2 / FMUL2), chunk sums accumulated in FP64; '
+                                          'issue-bound, see issue / smem'}}
+            roofline.update(common)
         cores = 1
         cpu_v, cpu_desc, _ = cpu_sample(cores, n_pix_per_core=int(os.environ.get('RB_BENCH_CPU_PIXELS', '160')), n_lay_per_core=128) if world == 1 else (None, None, None)
         line = {
@@ -601,18 +663,15 @@ def run_gpu(args):
             'value_all_pixels': n_all * F / (ms_per_step * 1e-3),
         }
         if cpu_v is not None:
-            line['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': cpu_desc}
+            line['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': cpu_desc,
+                                    'stock_reference': stock_reference_record()}
         if rt_mixed is not None:
             line['rt_mixed'] = rt_mixed
-        if world == 1:
-            a5 = alpha_c5(ctx, dev)
-            a5['fp64_peak_tflops'] = fp64_peak
-            a5['fp64_frac'] = a5['fp64_tflops_algorithmic'] / fp64_peak if fp64_peak else None
-            line['alpha_c5'] = a5
-            a5f = alpha_c5(ctx, dev, full=True)
-            a5f['fp64_peak_tflops'] = fp64_peak
-            a5f['fp64_frac'] = a5f['fp64_tflops_algorithmic'] / fp64_peak if fp64_peak else None
-            line['alpha_c5_full'] = a5f
+        for key, a5 in (('alpha_c5', a5_short), ('alpha_c5_full', a5_full)):
+            if a5 is not None:
+                a5['fp64_peak_tflops_per_gpu'] = fp64_peak
+                a5['fp64_frac'] = a5['fp64_tflops_algorithmic'] / (fp64_peak * world) if fp64_peak else None
+                line[key] = a5
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

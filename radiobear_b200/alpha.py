@@ -35,6 +35,8 @@ class Alpha:
                                       'alpha{:04d}.npz'.format(idnum))
         self.memory = Namespace()
         self.slab = None            # [L][F] device-order copy of .layers (what the RT kernel reads)
+        # frequency sharding of get_layers over the ranks of torch.distributed: 'auto' (large requests), True, False
+        self.shard_freqs = kwargs.get('shard_freqs', 'auto')
         if load_formal:
             self.setup_formalisms()
 
@@ -125,12 +127,23 @@ class Alpha:
                                          want_cube=to_cache)
             slab, cube = res if to_cache else (res, None)
         else:
-            res = engine.alpha_layers(np.asarray(freqs, dtype=np.float64), atm.gas[C['T']], atm.gas[C['P']], atm.gas, C,
-                                      cloud=atm.cloud if np.size(atm.cloud) else None, cloud_dict=atm.config.Cl,
-                                      formalisms=self.formalisms(), other_dicts=self.other_dict,
-                                      units=utils.alphaUnit, scale=scale, want_cube=to_cache,
-                                      truncate_strength=self.truncate_strength, truncate_freq=self.truncate_freq)
-            slab, cube = res if to_cache else (res, None)
+            fr = np.asarray(freqs, dtype=np.float64)
+
+            def calc(lo=0, hi=len(fr), want_cube=to_cache):
+                return engine.alpha_layers(fr[lo:hi], atm.gas[C['T']], atm.gas[C['P']], atm.gas, C,
+                                           cloud=atm.cloud if np.size(atm.cloud) else None, cloud_dict=atm.config.Cl,
+                                           formalisms=self.formalisms(), other_dicts=self.other_dict,
+                                           units=utils.alphaUnit, scale=scale, want_cube=want_cube,
+                                           truncate_strength=self.truncate_strength, truncate_freq=self.truncate_freq)
+            from . import parallel
+            world, _ = parallel.world_rank()
+            if not to_cache and parallel.shard_alpha(L, len(fr), world, self.shard_freqs):
+                # one process per GPU: this rank's frequency block, then one all_gather (every rank traces rays
+                # with the full slab afterwards)
+                slab, cube = parallel.alpha_layers_sharded(lambda lo, hi: calc(lo, hi, False), L, len(fr)), None
+            else:
+                res = calc()
+                slab, cube = res if to_cache else (res, None)
         self.slab = slab
         self.layers = slab.T            # [F][L] view, indexable as layers[j][layer] like the reference
         if to_cache:

@@ -596,7 +596,7 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full_in, const rb_rt
     // chunks complete evenly in time.
     pg.shift = (int)(ntiles / 2);
     for (int c = 0; c <= nch; ++c) pg.cut[c] = (int)cut_at(c);
-    const unsigned fgroups = (unsigned)(prep.pairs ? (F + 15) / 16 : (F + 7) / 8);
+    const unsigned fgroups = (unsigned)(prep.pairs ? (F + kPairFreqs - 1) / kPairFreqs : (F + 7) / 8);
     // value the counter of a chunk of `len` ray tiles ends at: one count per CTA; compacted launches start the
     // counters at their deficit so that they end at (len + 4) * fgroups (rt_progress_init_kernel)
     const unsigned extra = full.compact ? 4u : 0u;

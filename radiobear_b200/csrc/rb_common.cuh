@@ -80,6 +80,15 @@ enum {
 // The rays-major integration kernel prefetches whole 32-segment chunks of the ds slab and of the operand
 // slab without bounds checks (the rows it may over-read are never consumed); both buffers carry this slack.
 constexpr size_t kRtSlackBytes = 128 * 256;
+// warps (= frequency pairs) per CTA of rt_integrate_pairs_kernel: a CTA is 32 rays x 2 kPairWarps frequencies.
+// The warps of a CTA advance chunk by chunk together (one barrier per 32 segments) although their frequencies reach
+// the table phase and tau_cut at different layers; 4 warps (8 adjacent frequencies, 6 CTAs per SM) wait less for each
+// other than 8 (16 frequencies, 3 CTAs per SM): 3.48 against 3.74 ms on C4, same bits (profiles/r2_ab_variants.jsonl).
+#ifndef RB_RT_WARPS
+#define RB_RT_WARPS 4
+#endif
+constexpr int kPairWarps = RB_RT_WARPS;
+constexpr int kPairFreqs = 2 * kPairWarps;
 
 int rb_fail(rb_context* ctx, int code, const char* fmt, ...);
 int rb_ensure(rb_context* ctx, int which, size_t bytes, void** out);

@@ -194,10 +194,13 @@ __global__ void __launch_bounds__(kEdgeThreads) ray_compact_kernel(const __grid_
 // 64 registers: 8 CTAs of 128 rays per SM = 151 k rays in flight, so that the ~117 k rays of the C4 image are ONE
 // wave (every ray is the same ~1000-step chain: a second, nearly empty wave doubles the kernel time -- measured with
 // 80 registers, 6 CTAs per SM: 918 CTAs on 888 slots, 0.50 ms)
-template <bool COMPACT>
+// (one kernel for the plain and the compacted launch -- g.cidx selects -- so that both run the very same instructions
+//  per ray: two template instantiations were contracted into FMAs differently by the compiler in the start-up and
+//  restart arithmetic, and 743 rays of the C4 image differed in the last bits of ds)
 __global__ void __launch_bounds__(128, RB_GEO_CTAS) ray_geometry_kernel(const __grid_constant__ GeoK g) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int S = g.L - 1;
+  const bool COMPACT = g.cidx != nullptr;
   long long r = t;
   bool inrange, hit;
   double bx = 2.0, by = 2.0, zq = 0.0;
@@ -622,6 +625,15 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
 #endif
 constexpr int kExpTabLog = RB_EXP_TABLOG;
 constexpr int kExpTab = 1 << kExpTabLog;
+// RB_EXP_REP copies of every entry, interleaved ([entry][copy]): lane l reads copy l % RB_EXP_REP.  With 16 copies
+// each lane of a half-warp owns its own pair of banks, so a lookup costs exactly two shared-memory wavefronts
+// whatever the 32 indices are (a single copy: ~5.5 wavefronts for 32 random entries of a 1024-entry table).
+#ifndef RB_EXP_REP
+#define RB_EXP_REP 1
+#endif
+constexpr int kExpRep = RB_EXP_REP;
+static_assert(kExpRep == 1 || kExpRep == 2 || kExpRep == 4 || kExpRep == 8 || kExpRep == 16, "copies per table entry");
+constexpr int kExpTabDoubles = kExpTab * kExpRep;
 constexpr double kExpH = 0.69314718055994530942 / (2.0 * kExpTab);
 __device__ double c_expc[8] = {
     -1.4426950408889634074 * kExpTab,   // -N log2(e)
@@ -667,7 +679,7 @@ __device__ double c_mxc[2] = {-1.4426950408889634074 * 8388608.0, 67553994410557
 
 __global__ void exp_tab_init_kernel(double* tab) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < kExpTab) tab[t] = exp2((double)t / (double)kExpTab);
+  if (t < kExpTabDoubles) tab[t] = exp2((double)(t / kExpRep) / (double)kExpTab);
 }
 
 // per-(layer, freq) operands of the integration loop, hoisted out of the per-ray work and interleaved so
@@ -711,11 +723,11 @@ template <int OFF>
 __device__ __forceinline__ void cp_async16_at(unsigned dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%2], 16;" ::"r"(dst), "l"(src), "n"(OFF) : "memory");
 }
-template <int N>
+template <int N, int ROUND = 4096>
 __device__ __forceinline__ void cp_rounds(unsigned dst, const void* src) {
   if constexpr (N > 0) {
-    cp_rounds<N - 1>(dst, src);
-    cp_async16_at<(N - 1) * 4096>(dst, src);
+    cp_rounds<N - 1, ROUND>(dst, src);
+    cp_async16_at<(N - 1) * ROUND>(dst, src);
   }
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -876,7 +888,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   // dynamic shared memory: [ table | ds tiles x kStages | operand tiles x kStages ]
   extern __shared__ __align__(16) unsigned char s_raw[];
   double* const s_tab = reinterpret_cast<double*>(s_raw);                    // 2^(j/N), copied from k.exp_tab with chunk 0
-  double* const s_ds = s_tab + kExpTab;
+  double* const s_ds = s_tab + kExpTabDoubles;
   double4* const s_pp = reinterpret_cast<double4*>(s_ds + kStages * kTileDs);
   const int tid = threadIdx.y * 32 + threadIdx.x;
 
@@ -917,7 +929,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   const bool any_live = __syncthreads_or(live);
   if (any_live) {
     // the exponential table rides in the first copy group
-    for (int q = tid; q < kExpTab / 2; q += 256) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
+    for (int q = tid; q < kExpTabDoubles / 2; q += 256) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
     issue(0);
   }
 
@@ -930,6 +942,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
   // window base with S2UR / UMOV / ULEA in every iteration)
   unsigned tab_base;
   asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(tab_base) : "l"(s_tab));
+  tab_base += (threadIdx.x & (kExpRep - 1)) * 8u;            // this lane's copy of the table (see kExpRep)
   // One integer compare on the high word of tau (a non-negative double: it orders like its high word; a NaN
   // compares as "beyond") ends the ray once tau >= tau_cut -- the same rule in every integration kernel of this
   // file (tau_cut to the 20 mantissa bits of its high word: exact for 5, 50, ...).  tau_cut is capped at 707
@@ -955,7 +968,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
     const double rr = fma(nd, cL, -tau);                                                                       \
     const double p = RB_EXP_POLY(rr);                                                                          \
     double tj;                                                                                                 \
-    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_base + ((ni & (kExpTab - 1)) << 3)));                  \
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(tab_base + (ni & (kExpTab - 1)) * (8 * kExpRep)));                  \
     const double v = p * tj;                                                                                   \
     const double e = __hiloint2double(__double2hiint(v) + ((ni << (20 - kExpTabLog)) & 0xFFF00000), __double2loint(v)); \
     const double w = e * ((dcur) + (dnxt));                                                                    \
@@ -974,8 +987,8 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
     double p_ = RB_EXP_POLY(rr_);                                                                              \
     double tj_;                                                                                                \
     unsigned ta_, ex_;                                                                                         \
-    asm("{ .reg .b32 t; and.b32 t, %2, %4; mad.lo.u32 %0, t, 8, %3; and.b32 %1, %2, %5; }"                     \
-        : "=r"(ta_), "=r"(ex_) : "r"(ni_), "r"(tab_base), "n"(kExpTab - 1), "n"(~(kExpTab - 1)));              \
+    asm("{ .reg .b32 t; and.b32 t, %2, %4; mad.lo.u32 %0, t, %6, %3; and.b32 %1, %2, %5; }"                     \
+        : "=r"(ta_), "=r"(ex_) : "r"(ni_), "r"(tab_base), "n"(kExpTab - 1), "n"(~(kExpTab - 1)), "n"(8 * kExpRep)); \
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj_) : "r"(ta_));                                                     \
     const double v_ = p_ * tj_;                                                                                \
     int hi_;                                                                                                   \
@@ -1072,7 +1085,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
     nd -= cM;
     const double rr = fma(nd, cL, -tc);
     const double p = RB_EXP_POLY(rr);
-    const double v = p * s_tab[ni & (kExpTab - 1)];
+    const double v = p * s_tab[(ni & (kExpTab - 1)) * kExpRep];
     double e = __hiloint2double(__double2hiint(v) + ((ni << (20 - kExpTabLog)) & 0xFFF00000), __double2loint(v));
     if ((unsigned)__double2hiint(nd) > (unsigned)__double2hiint(-1022.0 * kExpTab)) e = 0.0;
     const double w = e * last_dd;
@@ -1120,29 +1133,37 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
 // segment at a time, and the frequency that is left alone finishes on the single-segment path (adjacent
 // frequencies stop a few layers apart).  A frequency beyond F (odd F) is a ghost: zero operands, ends with its
 // partner.
+// CTAs per SM the pair kernel is compiled for: 3 x 256 threads leave 80 registers per thread (4 x 256: 64 registers
+// and spills in the loops -- measured 4.07 against 3.74 ms on C4)
+#ifndef RB_RTP_CTAS
+#define RB_RTP_CTAS (3 * 8 / RB_RT_WARPS)
+#endif
 constexpr int kPairRow = 3;                          // double2 per (segment, pair)
-constexpr int kPairTileQ = kChunk * 8 * kPairRow;    // double2 per operand tile
+constexpr int kPairThreads = 32 * kPairWarps;
+constexpr int kPairTileQ = kChunk * kPairWarps * kPairRow;    // double2 per operand tile
+constexpr int kPairRound = kPairThreads * 16;        // bytes one round of 16-byte copies of the whole CTA moves
 constexpr size_t kPairsSmemBytes = kStages * (kTileDs * sizeof(double) + kPairTileQ * sizeof(double2));
-static_assert((kChunk * 8 * kPairRow * sizeof(double2)) % 4096 == 0, "pair operand tile: whole 4 KB copy rounds");
+static_assert((kChunk * 32 * sizeof(double)) % kPairRound == 0, "ds tile: whole copy rounds");
+static_assert((kPairTileQ * sizeof(double2)) % kPairRound == 0, "pair operand tile: whole copy rounds");
 static_assert(kRtSlackBytes >= (kChunk + 1) * 32 * sizeof(double) + 256, "ds slab slack covers one over-read chunk");
 static_assert(kRtSlackBytes >= kChunk * 8 * kPairRow * sizeof(double2), "pair operand slack covers one over-read chunk");
 static_assert(kRtSlackBytes >= kChunk * 8 * sizeof(double4), "operand slack covers one over-read chunk");
 
 // pair operands:  prep2[fg][i][p] = { asum_a, asum_b }, { a'_a, T_i+1 a'_a }, { a'_b, T_i+1 a'_b },
-//   a = 16 fg + 2 p, b = a + 1; asum = (a_i + a_i+1) kHalfCm, a' = a_i+1 kHalfCm; zero for f >= F
+//   a = kPairFreqs fg + 2 p, b = a + 1; asum = (a_i + a_i+1) kHalfCm, a' = a_i+1 kHalfCm; zero for f >= F
 __global__ void rt_prepare_pairs_kernel(const double* __restrict__ alpha, const double* __restrict__ T, int L, int F,
                                         int ngroups, double2* __restrict__ prep2) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int Lm1 = L - 1;
-  if (idx >= ngroups * Lm1 * 8) return;
-  const int p = idx & 7;
-  const int i = (idx >> 3) % Lm1;
-  const int fg = (idx >> 3) / Lm1;
+  if (idx >= ngroups * Lm1 * kPairWarps) return;
+  const int p = idx % kPairWarps;
+  const int i = (idx / kPairWarps) % Lm1;
+  const int fg = (idx / kPairWarps) / Lm1;
   const double kHalfCm = 0.5 * kKmToCm;
   double v[2][3];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int f = fg * 16 + 2 * p + h;
+    const int f = fg * kPairFreqs + 2 * p + h;
     v[h][0] = v[h][1] = v[h][2] = 0.0;
     if (f < F) {
       const double a0 = alpha[(size_t)i * F + f], a1 = alpha[(size_t)(i + 1) * F + f];
@@ -1170,11 +1191,11 @@ __device__ __forceinline__ double2 lds_v2(unsigned a) {
   return v;
 }
 
-__global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_pairs_kernel(const __grid_constant__ RtK k) {
+__global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_kernel(const __grid_constant__ RtK k) {
   // dynamic shared memory: [ table | ds tiles x kStages | pair operand tiles x kStages ]
   extern __shared__ __align__(16) unsigned char s_raw[];
   double* const s_tab = reinterpret_cast<double*>(s_raw);
-  double* const s_ds = s_tab + kExpTab;
+  double* const s_ds = s_tab + kExpTabDoubles;
   double2* const s_q = reinterpret_cast<double2*>(s_ds + kStages * kTileDs);
   const int tid = threadIdx.y * 32 + threadIdx.x;
 
@@ -1184,7 +1205,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_pairs_kernel(con
   const unsigned tile = rt_.tile;
   const long long tpos = rt_.t;
   const long long r = rt_.r;
-  const int fA = rt_.fg * 16 + 2 * threadIdx.y;
+  const int fA = rt_.fg * kPairFreqs + 2 * threadIdx.y;
   const bool validA = rt_.in && (fA < k.F), validB = rt_.in && (fA + 1 < k.F);
   const int n = validA ? k.nseg[tpos] : -1;
   const bool nanray = validA && k.nanflag[tpos] != 0;
@@ -1192,24 +1213,25 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_pairs_kernel(con
 
   // copy plan (see rt_integrate_rays_kernel): ds chunk 33 x 256 B, operand chunk kChunk x 384 B, 16-byte pieces
   const char* src_ds = reinterpret_cast<const char*>(k.ds + (size_t)tile * S * 32) + tid * 16;
-  const char* src_q = reinterpret_cast<const char*>(k.prep2 + (size_t)rt_.fg * S * 8 * kPairRow) + tid * 16;
+  const char* src_q = reinterpret_cast<const char*>(k.prep2 + (size_t)rt_.fg * S * kPairWarps * kPairRow) + tid * 16;
   const unsigned dst_ds = (unsigned)__cvta_generic_to_shared(s_ds) + tid * 16;
   const unsigned dst_q = (unsigned)__cvta_generic_to_shared(s_q) + tid * 16;
   auto issue = [&](int c) {
     const unsigned bd = (c & 1) ? (unsigned)(kTileDs * sizeof(double)) : 0u;
     const unsigned bq = (c & 1) ? (unsigned)(kPairTileQ * sizeof(double2)) : 0u;
-    cp_rounds<kChunk / 16>(dst_ds + bd, src_ds);
-    cp_rounds<(kChunk * 8 * kPairRow * (int)sizeof(double2)) / 4096>(dst_q + bq, src_q);
-    if (tid < 16) cp_async16_at<(kChunk / 16) * 4096>(dst_ds + bd, src_ds);
+    constexpr int kDsRounds = (kChunk * 32 * (int)sizeof(double)) / kPairRound;
+    cp_rounds<kDsRounds, kPairRound>(dst_ds + bd, src_ds);
+    cp_rounds<(kPairTileQ * (int)sizeof(double2)) / kPairRound, kPairRound>(dst_q + bq, src_q);
+    if (tid < 16) cp_async16_at<kDsRounds * kPairRound>(dst_ds + bd, src_ds);
     cp_async_commit();
     src_ds += kChunk * 32 * sizeof(double);
-    src_q += kChunk * 8 * kPairRow * sizeof(double2);
+    src_q += kPairTileQ * sizeof(double2);
   };
   // bit 0: frequency a is live, bit 1: frequency b (a ghost b beyond F rides along with zero operands)
   int mode = (steps > 0) ? 3 : 0;
   const bool any_live = __syncthreads_or(mode != 0);
   if (any_live) {
-    for (int q = tid; q < kExpTab / 2; q += 256) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
+    for (int q = tid; q < kExpTabDoubles / 2; q += kPairThreads) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
     issue(0);
   }
 
@@ -1226,6 +1248,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_pairs_kernel(con
 #endif
   unsigned tab_base;
   asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(tab_base) : "l"(s_tab));
+  tab_base += (threadIdx.x & (kExpRep - 1)) * 8u;            // this lane's copy of the table (see kExpRep)
   const int cut_hi = __double2hiint(fmin(k.tau_cut, 707.0));   // tau >= tau_cut <=> hi(tau) >= cut_hi (see above)
   double tauA = 0.0, iWA = 0.0, TbA = 0.0, tauB = 0.0, iWB = 0.0, TbB = 0.0;
   int i = 0;                 // segments consumed so far (both frequencies walk together)
@@ -1242,8 +1265,8 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_pairs_kernel(con
     const double p_ = RB_EXP_POLY(rr_);
     double tj_;
     unsigned ta_, ex_;
-    asm("{ .reg .b32 t; and.b32 t, %2, %4; mad.lo.u32 %0, t, 8, %3; and.b32 %1, %2, %5; }"
-        : "=r"(ta_), "=r"(ex_) : "r"(ni_), "r"(tab_base), "n"(kExpTab - 1), "n"(~(kExpTab - 1)));
+    asm("{ .reg .b32 t; and.b32 t, %2, %4; mad.lo.u32 %0, t, %6, %3; and.b32 %1, %2, %5; }"
+        : "=r"(ta_), "=r"(ex_) : "r"(ni_), "r"(tab_base), "n"(kExpTab - 1), "n"(~(kExpTab - 1)), "n"(8 * kExpRep));
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj_) : "r"(ta_));
     const double v_ = p_ * tj_;
     int hi_;
@@ -1268,7 +1291,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_pairs_kernel(con
     }
     const double rr = fma(nd, cL, -tc);
     const double p = RB_EXP_POLY(rr);
-    const double v = p * s_tab[ni & (kExpTab - 1)];
+    const double v = p * s_tab[(ni & (kExpTab - 1)) * kExpRep];
     double e = __hiloint2double(__double2hiint(v) + ((ni << (20 - kExpTabLog)) & 0xFFF00000), __double2loint(v));
     if (crossed && (unsigned)__double2hiint(nd) > (unsigned)__double2hiint(-1022.0 * kExpTab)) e = 0.0;
     const double w = e * dd;
@@ -1281,7 +1304,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_pairs_kernel(con
   // shared-window addresses of this thread's ds column / operand rows in stage 0
   const unsigned ds_a0 = (unsigned)__cvta_generic_to_shared(s_ds + threadIdx.x);
   const unsigned q_a0 = (unsigned)__cvta_generic_to_shared(s_q + threadIdx.y * kPairRow);
-  constexpr unsigned kRowB = 8 * kPairRow * sizeof(double2);   // bytes between the operand rows of two segments
+  constexpr unsigned kRowB = kPairWarps * kPairRow * sizeof(double2);   // bytes between the operand rows of two segments
   constexpr int small_hi = (int)(((0x3FFull - (RB_EXP_SMALL_LOG > 0 ? RB_EXP_SMALL_LOG : 1)) << 20));
 
   for (int c = 0; any_live; ++c) {
@@ -1405,7 +1428,7 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_pairs_kernel(con
       for (; u < m && mode != 0; ++u) {
         const double dcur = dsb[u * 32];
         const double dd = dcur + dsb[(u + 1) * 32];
-        const double2* qr = qb + (size_t)u * 8 * kPairRow;
+        const double2* qr = qb + (size_t)u * kPairWarps * kPairRow;
         const double2 s0 = qr[0];
         if (mode & 1) { tauA = fma(s0.x, dcur, tauA); step_known(0, tauA, dd, qr[1]); }
         if (mode & 2) { tauB = fma(s0.y, dcur, tauB); step_known(1, tauB, dd, qr[2]); }
@@ -1770,11 +1793,9 @@ int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
     const unsigned eblocks = (unsigned)((g.R + kEdgeThreads - 1) / kEdgeThreads);
     ray_edge_kernel<<<eblocks, kEdgeThreads, 0, ctx->stream>>>(k);
     ray_compact_kernel<<<eblocks, kEdgeThreads, 0, ctx->stream>>>(k);
-    ray_geometry_kernel<true><<<(unsigned)blocks, threads, 0, ctx->stream>>>(k);
     ctx->launches += 2;
-  } else {
-    ray_geometry_kernel<false><<<(unsigned)blocks, threads, 0, ctx->stream>>>(k);
   }
+  ray_geometry_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(k);
   RB_CUDA(ctx, cudaGetLastError());
   RB_CUDA(ctx, rb_time_end(ctx, 1));
   ctx->launches += 1;
@@ -1807,7 +1828,7 @@ static bool choose_pairs(const rb_context* ctx, int F) {
   if (ctx->rt_pairs == 0 || F < 2) return false;
   if (ctx->rt_pairs == 1) return true;
   // slots executed per useful frequency; the pair kernel does ~1.2x the work per issue slot
-  const double fill1 = (double)F / (8.0 * ((F + 7) / 8)), fill2 = (double)F / (16.0 * ((F + 15) / 16));
+  const double fill1 = (double)F / (8.0 * ((F + 7) / 8)), fill2 = (double)F / ((double)kPairFreqs * ((F + kPairFreqs - 1) / kPairFreqs));
   return fill2 * 1.2 >= fill1;
 }
 
@@ -1832,14 +1853,14 @@ int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total,
     return RB_OK;
   }
   if (!ctx->exp_tab) {
-    RB_CUDA(ctx, cudaMalloc(&ctx->exp_tab, kExpTab * sizeof(double)));
-    exp_tab_init_kernel<<<(kExpTab + 255) / 256, 256, 0, ctx->stream>>>(ctx->exp_tab);
+    RB_CUDA(ctx, cudaMalloc(&ctx->exp_tab, kExpTabDoubles * sizeof(double)));
+    exp_tab_init_kernel<<<(kExpTabDoubles + 255) / 256, 256, 0, ctx->stream>>>(ctx->exp_tab);
     ctx->launches += 1;
   }
   out->pairs = choose_pairs(ctx, F);
   if (out->pairs) {
-    const int ng2 = (F + 15) / 16;
-    const int nel2 = ng2 * (L - 1) * 8;
+    const int ng2 = (F + kPairFreqs - 1) / kPairFreqs;
+    const int nel2 = ng2 * (L - 1) * kPairWarps;
     RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)nel2 * kPairRow * sizeof(double2) + kRtSlackBytes, &scratch));
     rt_prepare_pairs_kernel<<<(nel2 + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ng2, (double2*)scratch);
   } else {
@@ -1900,11 +1921,11 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     // of a ray tile adjacent in launch order; operands prepared by rb_rt_prepare
     k.step_counter = ctx->step_counter;
     if (progress) k.progress = *progress;
-    k.fgroups = (unsigned)(prep.pairs ? (k.F + 15) / 16 : (k.F + 7) / 8);
+    k.fgroups = (unsigned)(prep.pairs ? (k.F + kPairFreqs - 1) / kPairFreqs : (k.F + 7) / 8);
     k.ntiles = (unsigned)((g.R + 31) / 32);
     const unsigned long long nblocks = (unsigned long long)k.fgroups * k.ntiles;
     if (nblocks > 2147483647ULL) return rb_fail(ctx, RB_ERR_INVALID, "rt: too many (ray tile, frequency group) blocks for one launch");
-    dim3 block(32, 8), grid((unsigned)nblocks);
+    dim3 block(32, prep.pairs ? kPairWarps : 8), grid((unsigned)nblocks);
     if (prep.mixed) {
       if (!g.dsf) return rb_fail(ctx, RB_ERR_INVALID, "rt: mixed-precision integration without the float ds slab");
       k.dsf = g.dsf;
@@ -1926,13 +1947,13 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     k.exp_tab = ctx->exp_tab;
     if (prep.pairs) {
       k.prep2 = (const double2*)prep.prep;
-      constexpr size_t smem = kExpTab * sizeof(double) + kPairsSmemBytes;
+      constexpr size_t smem = kExpTabDoubles * sizeof(double) + kPairsSmemBytes;
       static_assert(smem <= 227 * 1024, "shared memory limit");
       RB_TRY(opt_in_smem(ctx, rt_integrate_pairs_kernel, smem, 1));
       rt_integrate_pairs_kernel<<<grid, block, smem, ctx->stream>>>(k);
     } else {
       k.prep = (const double4*)prep.prep;
-      constexpr size_t smem = kExpTab * sizeof(double) + kRaysSmemBytes;
+      constexpr size_t smem = kExpTabDoubles * sizeof(double) + kRaysSmemBytes;
       static_assert(smem <= 227 * 1024, "shared memory limit");
       RB_TRY(opt_in_smem(ctx, rt_integrate_rays_kernel, smem, 2));
       rt_integrate_rays_kernel<<<grid, block, smem, ctx->stream>>>(k);

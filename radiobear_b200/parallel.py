@@ -91,6 +91,46 @@ def all_gather_freq_blocks(local_slab, parts, group=None):
     return torch.cat([bufs[i][:, :widths[i]] for i in range(world)], dim=1).contiguous()
 
 
+# Below this many (layer, frequency) pairs the absorption of a request is recomputed on every rank: at C4
+# (1000 x 64) the kernel takes 0.1 ms, less than one collective; at C5 (4096 x 4096) it takes 7.5 ms on one GPU.
+ALPHA_SHARD_MIN_PAIRS = 1 << 20
+
+
+def shard_alpha(L, F, world, policy='auto'):
+    """Should `Alpha.get_layers` split the frequencies of this request over the ranks?  policy: 'auto' (by size),
+    True / False (RB_ALPHA_SHARD=1 / 0 overrides 'auto')."""
+    import os
+    if world <= 1 or F < world:
+        return False
+    env = os.environ.get('RB_ALPHA_SHARD')
+    if policy == 'auto' and env is not None:
+        policy = env not in ('0', 'false', 'False', '')
+    if policy == 'auto':
+        return L * F >= ALPHA_SHARD_MIN_PAIRS
+    return bool(policy)
+
+
+def alpha_layers_sharded(compute_block, L, F, group=None):
+    """Absorption slab [L][F] with the frequencies split over the ranks: rank r computes the contiguous block
+    `partition_even(F, world)[r]` with `compute_block(f_lo, f_hi)` (-> [L][f_hi - f_lo], numpy array or torch
+    tensor) and one all_gather gives every rank the full slab -- every rank traces rays afterwards
+    (the reference's only counterpart is running blocks of the request by hand,
+    set_utils.py:66-76).  Returns a numpy [L][F] array on every rank."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = partition_even(F, world)
+    lo, hi = parts[rank]
+    local = compute_block(lo, hi)
+    t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local))
+    if t.shape != (L, hi - lo):
+        raise ValueError('compute_block({}, {}) returned {}, expected {}'.format(lo, hi, tuple(t.shape), (L, hi - lo)))
+    if dist.get_backend(group) == 'nccl' and not t.is_cuda:
+        t = t.cuda()
+    full = all_gather_freq_blocks(t.contiguous(), parts, group=group)
+    return full.cpu().numpy() if full.is_cuda else full.numpy()
+
+
 def world_rank():
     """(world_size, rank) of the default process group; (1, 0) when torch.distributed is not initialised."""
     try:

@@ -128,3 +128,62 @@ def test_shared_host_exchange_world2():
     # calls 0, 1 are held (call 1 only through derived views) -> own segments; the later calls drop their result
     # before the next one and share a third
     assert max(r[1] for r in res) == 3
+
+
+def _worker_alpha(rank, world, port, out):
+    """Alpha.get_layers with the frequencies split over two ranks.  The kernel call (engine.alpha_layers) is stood in
+    for by the oracle so that the host path -- block bounds, all_gather, slab / layers layout -- runs on CPU."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import sys
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        from oracle import alpha_oracle as ao
+        from radiobear_b200 import alpha as rbalpha, engine
+        from radiobear_b200.atmosphere import Atmosphere
+        atm = Atmosphere.from_npz(os.path.join(root, 'tests', 'golden', 'atm_jupiter_benchmark.npz'), 'jupiter')
+        cfg = atm.config
+        keep = slice(0, atm.gas.shape[1], 40)                  # a thin atmosphere: the oracle is the slow part here
+        atm.gas = np.ascontiguousarray(atm.gas[:, keep])
+        atm.cloud = np.ascontiguousarray(atm.cloud[:, keep])
+        calls = []
+
+        def stub(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formalisms=(), other_dicts=None, **kw):
+            calls.append(np.array(freqs))
+            lay = ao.get_layers(freqs, gas, cloud, gas_dict, cloud_dict, dict(formalisms), other_dicts=other_dicts,
+                                truncate_strength=kw.get('truncate_strength'))
+            return np.ascontiguousarray(lay.T)                 # [L][F] like the kernel
+        engine.alpha_layers = stub
+        freqs = np.linspace(2.0, 40.0, 7)
+        a = rbalpha.Alpha(config=cfg, verbose=False, shard_freqs=True)
+        a.get_layers(freqs, atm)
+        sharded_calls = [c.copy() for c in calls]
+        full = a.layers.copy()
+        b = rbalpha.Alpha(config=cfg, verbose=False, shard_freqs=False)
+        b.get_layers(freqs, atm)
+        lo, hi = parallel.partition_even(7, world)[rank]
+        checks = [len(sharded_calls) == 1, np.array_equal(sharded_calls[0], freqs[lo:hi]),
+                  full.shape == (7, atm.gas.shape[1]), bool(np.allclose(full, b.layers, rtol=1e-12, atol=0.0)),   # numpy SIMD tails: last-bit differences per batch shape
+                  a.slab.shape == (atm.gas.shape[1], 7)]
+        ok = all(checks)
+        # 'auto' leaves a request of this size replicated; the size rule and the environment override
+        ok = ok and not parallel.shard_alpha(1000, 64, 2) and parallel.shard_alpha(4096, 4096, 8)
+        ok = ok and not parallel.shard_alpha(4096, 4096, 1) and parallel.shard_alpha(10, 10, 2, True)
+        out.put(bool(ok) or checks)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_alpha_frequency_sharding_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_alpha, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r is True for r in res), res

@@ -29,6 +29,8 @@ def main():
     ctx.enable_timing(True)
     ctx.set_rt_precision(precision)
     atm, freqs, grid = bench.workload()
+    if os.environ.get("RB_AB_SAMEFREQ", ""):       # every frequency the same: no pace differences between the warps of a CTA
+        freqs = np.full(len(freqs), float(os.environ["RB_AB_SAMEFREQ"]))
     cfg = atm.config
     n = len(grid)
     pts = np.stack([np.tile(grid, n), np.repeat(grid, n)], axis=1)
@@ -72,6 +74,11 @@ def main():
     for w in ('alpha', 'geometry', 'rt'):
         h = ctx.kernel_ms_history(w, ctx.kernel_timed_count(w) - k0[w])
         out[w + '_ms'] = float(np.mean(h)) if len(h) else None
+    ctx.count_steps(True)
+    step()
+    torch.cuda.synchronize()
+    out['steps_executed'] = ctx.count_steps(False)
+    out['steps_small'] = ctx.count_small_steps()
     tb = tb_t.cpu().numpy()
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     ref_fn = '/tmp/ab_ref_tb.npy'                      # 185 MB: stays on the GPU box
