@@ -394,6 +394,51 @@ def alpha_c5(ctx, dev, reps=5, full=False, world=1, rank=0):
             'cpu_port_value_1core': cpu_rate}
 
 
+def retrieval_loop(atm, iters=20):
+    """the retrieval inner loop of scripts/demo_batch.py -- `run('1:10:1', save_alpha='memory')` once, then
+    `run('1:10:1', scale=<dict>, get_alpha='memory')` per iteration (disc-averaged, 10 frequencies): only the scale-sum
+    over the cached per-constituent cube and the radiative transfer are redone.  The cube stays on the device
+    (rb_alpha_rescale_resident); the same loop with the cube re-uploaded from the host cache every iteration
+    (rb_alpha_scale_sum, round 1's path) and a full recomputation (get_alpha='calc') are timed beside it.
+    Wall clock per Planet.run call, host buffers in and out."""
+    from radiobear_b200.planet import Planet
+    p = Planet('jupiter', atmosphere=atm, verbose=False)
+    L = atm.gas.shape[1]
+    P = atm.gas[atm.config.C['P']]
+    rng = np.random.default_rng(3)
+
+    def scale_of(i):
+        return {'nh3': list(0.5 + rng.random() + 0.3 * np.sin(np.log10(P) + i)), 'h2o': [float(1.0 + 0.05 * i)] * L}
+    p.run('1:10:1', save_alpha='memory')
+    scales = [scale_of(i) for i in range(iters + 3)]
+    out = {}
+    ref = None
+    for mode in ('resident', 'host_cube', 'recompute'):
+        tbs = []
+        for i, sc in enumerate(scales):
+            if i == 3:
+                t0 = time.perf_counter()
+            if mode == 'host_cube':
+                p.alpha[0]._dev_cube = None               # forget the device copy: the cube is uploaded again
+            if mode == 'recompute':
+                tbs.append(np.array(p.run('1:10:1', scale=sc, reuse_override='false').Tb))
+            else:
+                tbs.append(np.array(p.run('1:10:1', scale=sc, get_alpha='memory', reuse_override='false').Tb))
+        out[mode + '_ms_per_iteration'] = 1e3 * (time.perf_counter() - t0) / iters
+        if mode == 'resident':
+            ref = tbs
+            resident_used = p.alpha[0]._res is not None
+        else:
+            out['max_abs_dTb_K_resident_vs_' + mode] = float(max(np.max(np.abs(a - b)) for a, b in zip(ref, tbs)))
+        if mode == 'host_cube':
+            p.run('1:10:1', save_alpha='memory')          # put the cube back on the device for whoever comes next
+    out.update(workload="Planet.run('1:10:1', b='disc', scale=dict(nh3, h2o), get_alpha='memory') after one save_alpha='memory' "
+                        "(scripts/demo_batch.py), {} layers x 10 freqs x {} constituents".format(L, len(p.alpha[0].ordered_constituents)),
+               iterations=iters, resident_path_used=bool(resident_used),
+               iterations_per_s=1e3 / out['resident_ms_per_iteration'])
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -667,6 +712,7 @@ def run_gpu(args):
                                     'stock_reference': stock_reference_record()}
         if rt_mixed is not None:
             line['rt_mixed'] = rt_mixed
+        line['retrieval_loop'] = retrieval_loop(atm)
         for key, a5 in (('alpha_c5', a5_short), ('alpha_c5_full', a5_full)):
             if a5 is not None:
                 a5['fp64_peak_tflops_per_gpu'] = fp64_peak

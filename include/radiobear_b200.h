@@ -181,6 +181,24 @@ int rb_alpha_layers_dev(rb_context* ctx, const rb_alpha_desc* desc, double* out_
 int rb_alpha_scale_sum(rb_context* ctx, int32_t n_layers, int32_t n_freqs, int32_t n_constituents,
                        const double* cube, const double* scale, double* out_total, double* out_cube);
 
+/* ---- device-resident absorption ------------------------------------------------------------
+ * The reference's absorption cache keeps the per-constituent cube in host memory between runs (save_alpha /
+ * get_alpha = 'memory', alpha.py:110-149) so that a retrieval loop only re-does the scale-sum and the radiative
+ * transfer (scripts/demo_batch.py).  Here the slab [L][F] and the cube [L][F][C] stay in buffers owned by the context:
+ * no copy back, no synchronisation; rb_rt_batch_resident integrates straight from the resident slab.  Every overwrite
+ * of the slab / cube gets a new generation number (> 0), so a caller can tell whether "its" data is still there. */
+/* rb_alpha_layers (host pointers in desc) into the resident slab and, when keep_cube, the resident cube. */
+int rb_alpha_layers_resident(rb_context* ctx, const rb_alpha_desc* desc, int32_t keep_cube, uint64_t* out_slab_generation,
+                             uint64_t* out_cube_generation);
+/* Alpha.total_layer_alpha on the resident cube (alpha.py:151-192): resident slab[l][f] = sum_c scale[c][l] cube[l][f][c].
+ * scale: host [C][L] or NULL (all ones).  The cube is not modified. */
+int rb_alpha_rescale_resident(rb_context* ctx, const double* scale, uint64_t* out_slab_generation);
+/* slab_shape[2] = {L, F}, cube_shape[3] = {L, F, C}; a generation of 0 means nothing is resident.  Any may be NULL. */
+int rb_alpha_resident_info(rb_context* ctx, int32_t* slab_shape, uint64_t* slab_generation, int32_t* cube_shape,
+                           uint64_t* cube_generation);
+/* Copy the resident slab [L][F] / cube [L][F][C] to host memory (either may be NULL); synchronises. */
+int rb_alpha_fetch(rb_context* ctx, double* out_total, double* out_cube);
+
 /* ---- ray geometry + radiative transfer (hot path B) ------------------------------------- */
 #define RB_GTYPE_ELLIPSE 0 /* shape.py:223-274 */
 #define RB_GTYPE_SPHERE 1  /* 'circle' / 'sphere' */
@@ -222,6 +240,11 @@ typedef struct rb_rt_desc {
 int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* geom, const rb_rt_desc* rt, int64_t n_rays,
                 const double* b, void* out_Tb, double* out_integrated_W, int64_t profile_ray, double* out_tau,
                 double* out_W, double* out_Tb_lyr);
+/* rb_rt_batch reading the resident absorption slab (rb_alpha_layers_resident / rb_alpha_rescale_resident) instead of
+ * rt->alpha, which is ignored; geom->n_layers and rt->n_freqs must match the resident shape. */
+int rb_rt_batch_resident(rb_context* ctx, const rb_geometry_desc* geom, const rb_rt_desc* rt, int64_t n_rays,
+                         const double* b, void* out_Tb, double* out_integrated_W, int64_t profile_ray, double* out_tau,
+                         double* out_W, double* out_Tb_lyr);
 /* Device-pointer variant: geom->radius, rt->alpha, rt->T, b, out_* are device pointers. */
 int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* geom, const rb_rt_desc* rt, int64_t n_rays,
                     const double* b, void* out_Tb, double* out_integrated_W);

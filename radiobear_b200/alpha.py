@@ -34,7 +34,10 @@ class Alpha:
         self.alphafile = os.path.join(getattr(config, 'scratch_directory', 'Scratch'),
                                       'alpha{:04d}.npz'.format(idnum))
         self.memory = Namespace()
-        self.slab = None            # [L][F] device-order copy of .layers (what the RT kernel reads)
+        self._slab = None           # [L][F] host copy of the slab (what .layers is the transpose view of)
+        self._layers_view = None
+        self._res = None            # engine.ResidentSlab: the slab (and, after save_alpha='memory', the cube) on the device
+        self._dev_cube = None       # (ResidentSlab holding the cube, the host array it mirrors)
         # frequency sharding of get_layers over the ranks of torch.distributed: 'auto' (large requests), True, False
         self.shard_freqs = kwargs.get('shard_freqs', 'auto')
         if load_formal:
@@ -79,8 +82,52 @@ class Alpha:
     def reset_layers(self):
         self.P = None
         self.freqs = None
-        self.layers = None
-        self.slab = None
+        self._slab = None
+        self._res = None
+
+    # ------------------------------------------------------------------ the slab: on the device until somebody reads it
+    # Planet.run -> Alpha.get_layers -> Brightness.batch never needs the absorption on the host: the kernel leaves it in
+    # the context's resident buffer and the integration reads it there.  `.layers` / `.slab` copy it back on first use.
+    def has_layers(self):
+        return self._slab is not None or (self._res is not None and self._res.valid())
+
+    def materialize(self):
+        """Bring the device-resident slab to the host (called before another computation overwrites the buffer)."""
+        if self._slab is None and self._res is not None and self._res.valid():
+            self._slab = self._res.fetch()
+
+    @property
+    def slab(self):
+        self.materialize()
+        return self._slab
+
+    @slab.setter
+    def slab(self, value):
+        self._slab, self._res = value, None
+
+    @property
+    def layers(self):
+        """[F][L] view, indexable as layers[j][layer] like the reference (alpha.py:301)."""
+        s = self.slab
+        if s is None:
+            return None
+        if self._layers_view is None or self._layers_view.base is not s:
+            self._layers_view = s.T
+        return self._layers_view
+
+    @layers.setter
+    def layers(self, value):
+        self.slab = None if value is None else np.ascontiguousarray(np.asarray(value, dtype=np.float64).T)
+
+    def rt_slab(self):
+        """What the integration should read: the resident handle while it is valid, else the host slab."""
+        if self._res is not None and self._res.valid():
+            return self._res
+        return self.slab
+
+    @property
+    def n_freqs(self):
+        return (self._slab if self._slab is not None else self._res).shape[1]
 
     # ------------------------------------------------------------------ cache (alpha.py:110-149)
     def save_alpha_data(self, save_type):
@@ -120,35 +167,47 @@ class Alpha:
         from_cache = get_alpha in ('memory', 'file')
         to_cache = save_alpha in ('memory', 'file')
         self.log.add('{} layers'.format(L), self.verbose)
+        slab = cube = res = None
         if from_cache:
             # cached per-constituent cube [L][F][C]: only the scale-sum is redone (alpha.py:224-225)
             self.read_alpha_data(get_alpha)
-            res = engine.alpha_scale_sum(np.asarray(self.alpha_data, dtype=np.float64), self.get_layer_scale(scale, L),
-                                         want_cube=to_cache)
-            slab, cube = res if to_cache else (res, None)
+            dev = self._dev_cube
+            if (get_alpha == 'memory' and not to_cache and dev is not None and dev[1] is self.alpha_data
+                    and dev[0].cube_valid() and dev[0].cube_shape[0] == L):
+                # the cube this cache holds is still on the device (left there by save_alpha='memory'): the retrieval
+                # loop of scripts/demo_batch.py re-runs only the scale-sum and the radiative transfer, with no copy
+                res = engine.alpha_rescale_resident(dev[0], self.get_layer_scale(scale, L), owner=self)
+            else:
+                out = engine.alpha_scale_sum(np.asarray(self.alpha_data, dtype=np.float64), self.get_layer_scale(scale, L),
+                                             want_cube=to_cache)
+                slab, cube = out if to_cache else (out, None)
         else:
             fr = np.asarray(freqs, dtype=np.float64)
-
-            def calc(lo=0, hi=len(fr), want_cube=to_cache):
-                return engine.alpha_layers(fr[lo:hi], atm.gas[C['T']], atm.gas[C['P']], atm.gas, C,
-                                           cloud=atm.cloud if np.size(atm.cloud) else None, cloud_dict=atm.config.Cl,
-                                           formalisms=self.formalisms(), other_dicts=self.other_dict,
-                                           units=utils.alphaUnit, scale=scale, want_cube=want_cube,
-                                           truncate_strength=self.truncate_strength, truncate_freq=self.truncate_freq)
+            common = dict(cloud=atm.cloud if np.size(atm.cloud) else None, cloud_dict=atm.config.Cl,
+                          formalisms=self.formalisms(), other_dicts=self.other_dict, units=utils.alphaUnit, scale=scale,
+                          truncate_strength=self.truncate_strength, truncate_freq=self.truncate_freq)
             from . import parallel
             world, _ = parallel.world_rank()
             if not to_cache and parallel.shard_alpha(L, len(fr), world, self.shard_freqs):
                 # one process per GPU: this rank's frequency block, then one all_gather (every rank traces rays
                 # with the full slab afterwards)
-                slab, cube = parallel.alpha_layers_sharded(lambda lo, hi: calc(lo, hi, False), L, len(fr)), None
+                slab = parallel.alpha_layers_sharded(
+                    lambda lo, hi: engine.alpha_layers(fr[lo:hi], atm.gas[C['T']], atm.gas[C['P']], atm.gas, C, **common),
+                    L, len(fr))
+            elif os.environ.get('RB_ALPHA_RESIDENT', '1') == '0':     # A/B switch: results through host memory
+                out = engine.alpha_layers(fr, atm.gas[C['T']], atm.gas[C['P']], atm.gas, C, want_cube=to_cache, **common)
+                slab, cube = out if to_cache else (out, None)
             else:
-                res = calc()
-                slab, cube = res if to_cache else (res, None)
-        self.slab = slab
-        self.layers = slab.T            # [F][L] view, indexable as layers[j][layer] like the reference
+                res = engine.alpha_layers_resident(fr, atm.gas[C['T']], atm.gas[C['P']], atm.gas, C, keep_cube=to_cache,
+                                                   owner=self, **common)
+                if to_cache:
+                    cube = res.fetch_cube()
+        self._slab, self._res = slab, res
         if to_cache:
             self.tosave = cube
             self.save_alpha_data(save_alpha)
+            # the device copy of what the memory cache now holds (None when the cube went through the host path)
+            self._dev_cube = (res, self.memory.alpha_data) if (save_alpha == 'memory' and res is not None) else None
             del self.tosave
 
     def get_single_layer(self, freqs, layer, atm, lscale=1.0, units='invcm'):

@@ -38,12 +38,12 @@ class Brightness:
     def batch(self, b, freqs, atm, alpha, orientation=None, disc_average=False, out_f32=False, want_intW=False):
         """Tb[R][F] for impact points b[R][2]; off-planet rays give T_cmb, limb rays below the tangent
         shell give NaN exactly like the reference."""
-        if alpha.layers is None:
+        if not alpha.has_layers():
             alpha.get_layers(freqs, atm)
         if getattr(alpha.config, 'Doppler', False):
             raise NotImplementedError('Doppler-shifted absorption is broken in the reference (brightness.py:83-92) '
                                       'and not built here')
-        res = engine.rt_batch(b=np.atleast_2d(np.asarray(b, dtype=np.float64)), alpha_slab=alpha.slab,
+        res = engine.rt_batch(b=np.atleast_2d(np.asarray(b, dtype=np.float64)), alpha_slab=alpha.rt_slab(),
                               disc_average=disc_average, out_f32=out_f32, tau_cut=self.tau_cut, want_intW=want_intW,
                               **self._args(atm, orientation))
         return res
@@ -57,11 +57,11 @@ class Brightness:
         self.alpha = alpha
         self.freqs = freqs
         self.b = b
-        if alpha.layers is None:
+        if not alpha.has_layers():
             alpha.get_layers(freqs, atm)
         if getattr(alpha.config, 'Doppler', False):
             raise NotImplementedError('Doppler-shifted absorption is not built (broken in the reference)')
-        res = engine.rt_batch(b=np.asarray([b], dtype=np.float64), alpha_slab=alpha.slab, disc_average=disc_average,
+        res = engine.rt_batch(b=np.asarray([b], dtype=np.float64), alpha_slab=alpha.rt_slab(), disc_average=disc_average,
                               tau_cut=0.0, want_intW=True, profile_ray=0, **self._args(atm, orientation))
         self.travel = raypath.compute_ds(atm, b, orientation)
         if self.travel.ds is None:

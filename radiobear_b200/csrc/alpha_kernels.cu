@@ -518,10 +518,15 @@ __global__ void __launch_bounds__(kThreads) alpha_lines_kernel(const __grid_cons
   __syncthreads();
 
   // ---- phase 3: line sums ---------------------------------------------------------------------
-  const int gpb = kWarps / k.K;  // frequency groups per block
-  const int g = blockIdx.x * gpb + warp / k.K;
+  // A CTA keeps its layer's line tables for several frequency groups per warp (grid.x is sized for a few waves of
+  // CTAs, not for one group per warp): at C5 the tables of a layer are built once instead of eight times, and the
+  // barriers of phases 1-2, where the FP64 pipe idles, are paid once per layer.
+  const int gpb = kWarps / k.K;  // frequency groups per block and trip
   const int slice = warp % k.K;
   const int K = k.K;
+  const int trips = (k.ngroups + gpb * (int)gridDim.x - 1) / (gpb * (int)gridDim.x);   // the same for every warp
+  for (int trip = 0; trip < trips; ++trip) {
+  const int g = (trip * (int)gridDim.x + (int)blockIdx.x) * gpb + warp / k.K;
   double f[FPT], x[FPT];
   int fidx[FPT];
   bool valid[FPT];
@@ -681,7 +686,8 @@ __global__ void __launch_bounds__(kThreads) alpha_lines_kernel(const __grid_cons
       }
     }
   }
-  if (slice != 0 || g >= k.ngroups) return;
+  if (K > 1 && trip + 1 < trips) __syncthreads();   // the reduction buffer is reused by the next trip
+  if (slice != 0 || g >= k.ngroups) continue;
 
   // ---- phase 4: epilogue -------------------------------------------------------------------------
   const double unit = (k.units == RB_UNITS_DBPERKM) ? kDb : 1.0;
@@ -780,6 +786,7 @@ __global__ void __launch_bounds__(kThreads) alpha_lines_kernel(const __grid_cons
     }
     k.out_total[o] = total;
   }
+  }  // trips
 }
 
 int family_of(int form) {
@@ -874,7 +881,16 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   k.K = 1;
   while (k.K < kWarps && k.ngroups * k.K * 2 <= kWarps) k.K *= 2;
   const int gpb = kWarps / k.K;
-  const int nblk_x = (k.ngroups + gpb - 1) / gpb;
+  // CTAs per layer: one group per warp when that is what fills the GPU, else as few as leave ~4 CTAs per slot
+  // (2 resident CTAs per SM), each looping over the remaining groups with the layer's tables in place
+  int nblk_x = (k.ngroups + gpb - 1) / gpb;
+  {
+    const long long want = 8LL * ctx->num_sms;
+    const int per_layer = (int)((want + k.L - 1) / k.L);
+    if (per_layer < nblk_x) nblk_x = per_layer < 1 ? 1 : per_layer;
+    const char* e = getenv("RB_ALPHA_BLOCKS_PER_LAYER");
+    if (e && atoi(e) > 0 && atoi(e) < nblk_x) nblk_x = atoi(e);
+  }
 
   // smem layout
   int off = 0;

@@ -262,16 +262,19 @@ int rb_alpha_layers_dev(rb_context* ctx, const rb_alpha_desc* d, double* out_tot
   return rb_launch_alpha(ctx, d, hf.data(), out_total, out_cube);
 }
 
-int rb_alpha_layers(rb_context* ctx, const rb_alpha_desc* d, double* out_total, double* out_cube) {
-  RB_TRY(check_alpha_desc(ctx, d, out_total));
+// Host-pointer absorption call.  resident: the results stay in the context's RB_BUF_RES_* buffers, nothing is
+// copied back and the stream is not synchronised (rb_alpha_layers_resident); else they land in out_total / out_cube.
+static int alpha_layers_host(rb_context* ctx, const rb_alpha_desc* d, double* out_total, double* out_cube, bool resident,
+                             bool keep_cube) {
   RB_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t L = d->n_layers, F = d->n_freqs, C = d->n_constituents;
   rb_alpha_desc dd = *d;
   void *p_f, *p_T, *p_P, *p_gas = nullptr, *p_cloud = nullptr, *p_scale = nullptr, *p_tot, *p_cube = nullptr;
+  const bool want_cube = resident ? keep_cube : (out_cube != nullptr);
   RB_TRY(rb_ensure(ctx, RB_BUF_FREQS, F * 8, &p_f));
   RB_TRY(rb_ensure(ctx, RB_BUF_T, L * 8, &p_T));
   RB_TRY(rb_ensure(ctx, RB_BUF_P, L * 8, &p_P));
-  RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, L * F * 8, &p_tot));
+  RB_TRY(rb_ensure(ctx, resident ? RB_BUF_RES_TOTAL : RB_BUF_TOTAL, L * F * 8, &p_tot));
   cudaStream_t s = ctx->stream;
   RB_CUDA(ctx, cudaMemcpyAsync(p_f, d->freqs, F * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_T, d->T, L * 8, cudaMemcpyHostToDevice, s));
@@ -288,13 +291,88 @@ int rb_alpha_layers(rb_context* ctx, const rb_alpha_desc* d, double* out_total, 
     RB_TRY(rb_ensure(ctx, RB_BUF_SCALE, C * L * 8, &p_scale));
     RB_CUDA(ctx, cudaMemcpyAsync(p_scale, d->scale, C * L * 8, cudaMemcpyHostToDevice, s));
   }
-  if (out_cube) RB_TRY(rb_ensure(ctx, RB_BUF_CUBE, L * F * C * 8, &p_cube));
+  if (want_cube) RB_TRY(rb_ensure(ctx, resident ? RB_BUF_RES_CUBE : RB_BUF_CUBE, L * F * C * 8, &p_cube));
   dd.freqs = (const double*)p_f; dd.T = (const double*)p_T; dd.P = (const double*)p_P;
   dd.gas = (const double*)p_gas; dd.cloud = (const double*)p_cloud; dd.scale = (const double*)p_scale;
+  if (resident) {                       // whatever happens below, the old contents are gone
+    ctx->res.slab_gen = 0;
+    if (want_cube) ctx->res.cube_gen = 0;
+  }
   RB_TRY(rb_launch_alpha(ctx, &dd, d->freqs, (double*)p_tot, (double*)p_cube));
+  if (resident) {
+    ctx->res.L = (int)L; ctx->res.F = (int)F;
+    ctx->res.slab_gen = ++ctx->res.counter;
+    if (want_cube) {
+      ctx->res.cL = (int)L; ctx->res.cF = (int)F; ctx->res.cC = (int)C;
+      ctx->res.cube_gen = ++ctx->res.counter;
+    }
+    return RB_OK;
+  }
   RB_CUDA(ctx, cudaMemcpyAsync(out_total, p_tot, L * F * 8, cudaMemcpyDeviceToHost, s));
   if (out_cube) RB_CUDA(ctx, cudaMemcpyAsync(out_cube, p_cube, L * F * C * 8, cudaMemcpyDeviceToHost, s));
   RB_CUDA(ctx, cudaStreamSynchronize(s));
+  return RB_OK;
+}
+
+int rb_alpha_layers(rb_context* ctx, const rb_alpha_desc* d, double* out_total, double* out_cube) {
+  RB_TRY(check_alpha_desc(ctx, d, out_total));
+  return alpha_layers_host(ctx, d, out_total, out_cube, false, false);
+}
+
+int rb_alpha_layers_resident(rb_context* ctx, const rb_alpha_desc* d, int32_t keep_cube, uint64_t* out_slab_generation,
+                             uint64_t* out_cube_generation) {
+  static const double dummy = 0.0;
+  RB_TRY(check_alpha_desc(ctx, d, &dummy));
+  RB_TRY(alpha_layers_host(ctx, d, nullptr, nullptr, true, keep_cube != 0));
+  if (out_slab_generation) *out_slab_generation = ctx->res.slab_gen;
+  if (out_cube_generation) *out_cube_generation = keep_cube ? ctx->res.cube_gen : 0;
+  return RB_OK;
+}
+
+int rb_alpha_rescale_resident(rb_context* ctx, const double* scale, uint64_t* out_slab_generation) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (!ctx->res.cube_gen) return rb_fail(ctx, RB_ERR_INVALID, "rescale_resident: no per-constituent cube is resident");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = ctx->res.cL, F = ctx->res.cF, C = ctx->res.cC;
+  void *p_tot, *p_scale = nullptr;
+  RB_TRY(rb_ensure(ctx, RB_BUF_RES_TOTAL, (size_t)L * F * 8, &p_tot));
+  ctx->res.slab_gen = 0;
+  if (scale) {
+    RB_TRY(rb_ensure(ctx, RB_BUF_SCALE, (size_t)C * L * 8, &p_scale));
+    RB_CUDA(ctx, cudaMemcpyAsync(p_scale, scale, (size_t)C * L * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  RB_TRY(rb_launch_alpha_scale_sum(ctx, (const double*)ctx->buf[RB_BUF_RES_CUBE].p, (const double*)p_scale, L, F, C,
+                                   (double*)p_tot, nullptr));
+  ctx->res.L = L; ctx->res.F = F;
+  ctx->res.slab_gen = ++ctx->res.counter;
+  if (out_slab_generation) *out_slab_generation = ctx->res.slab_gen;
+  return RB_OK;
+}
+
+int rb_alpha_resident_info(rb_context* ctx, int32_t* slab_shape, uint64_t* slab_generation, int32_t* cube_shape,
+                           uint64_t* cube_generation) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (slab_shape) { slab_shape[0] = ctx->res.L; slab_shape[1] = ctx->res.F; }
+  if (slab_generation) *slab_generation = ctx->res.slab_gen;
+  if (cube_shape) { cube_shape[0] = ctx->res.cL; cube_shape[1] = ctx->res.cF; cube_shape[2] = ctx->res.cC; }
+  if (cube_generation) *cube_generation = ctx->res.cube_gen;
+  return RB_OK;
+}
+
+int rb_alpha_fetch(rb_context* ctx, double* out_total, double* out_cube) {
+  if (!ctx) return RB_ERR_INVALID;
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (out_total) {
+    if (!ctx->res.slab_gen) return rb_fail(ctx, RB_ERR_INVALID, "alpha_fetch: no slab is resident");
+    RB_CUDA(ctx, cudaMemcpyAsync(out_total, ctx->buf[RB_BUF_RES_TOTAL].p, (size_t)ctx->res.L * ctx->res.F * 8,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (out_cube) {
+    if (!ctx->res.cube_gen) return rb_fail(ctx, RB_ERR_INVALID, "alpha_fetch: no cube is resident");
+    RB_CUDA(ctx, cudaMemcpyAsync(out_cube, ctx->buf[RB_BUF_RES_CUBE].p,
+                                 (size_t)ctx->res.cL * ctx->res.cF * ctx->res.cC * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return RB_OK;
 }
 
@@ -689,11 +767,19 @@ int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc
   return run_rt_pipeline(ctx, L, rt, out_Tb, out_intW, nullptr, nullptr, have_geometry);
 }
 
-int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt, int64_t R, const double* b,
-                void* out_Tb, double* out_intW, int64_t profile_ray, double* out_tau, double* out_W,
-                double* out_Tblyr) {
+static int rt_batch_host(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt, int64_t R, const double* b,
+                         void* out_Tb, double* out_intW, int64_t profile_ray, double* out_tau, double* out_W,
+                         double* out_Tblyr, bool resident_alpha) {
   if (!ctx) return RB_ERR_INVALID;
-  RB_TRY(check_rt(ctx, rt, out_Tb));
+  if (resident_alpha) {
+    if (!rt || !out_Tb || rt->n_freqs <= 0 || !rt->T) return rb_fail(ctx, RB_ERR_INVALID, "rt: null descriptor / output");
+    if (!ctx->res.slab_gen) return rb_fail(ctx, RB_ERR_INVALID, "rt: no absorption slab is resident");
+    if (ctx->res.F != rt->n_freqs || !g || ctx->res.L != g->n_layers)
+      return rb_fail(ctx, RB_ERR_INVALID, "rt: the resident slab is [%d][%d], the request needs [%d][%d]", ctx->res.L,
+                     ctx->res.F, g ? g->n_layers : -1, rt->n_freqs);
+  } else {
+    RB_TRY(check_rt(ctx, rt, out_Tb));
+  }
   if (!b || !g || !g->radius) return rb_fail(ctx, RB_ERR_INVALID, "rt: null pointer");
   if (profile_ray >= 0 && (!out_tau || !out_W || !out_Tblyr)) return rb_fail(ctx, RB_ERR_INVALID, "rt: profile outputs null");
   if (profile_ray >= R) return rb_fail(ctx, RB_ERR_INVALID, "rt: profile_ray out of range");
@@ -707,7 +793,8 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
   RB_TRY(rb_ensure(ctx, RB_BUF_DS, ds_bytes(ctx, S, L.Rpad), &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
-  RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, nL * F * 8, &p_alpha));
+  if (resident_alpha) p_alpha = ctx->buf[RB_BUF_RES_TOTAL].p;
+  else RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, nL * F * 8, &p_alpha));
   RB_TRY(rb_ensure(ctx, RB_BUF_T, nL * 8, &p_T));
   RB_TRY(rb_ensure(ctx, RB_BUF_TB, (size_t)R * F * esz, &p_tb));
   if (out_intW) RB_TRY(rb_ensure(ctx, RB_BUF_INTW, (size_t)R * F * 8, &p_iw));
@@ -718,7 +805,7 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
     RB_CUDA(ctx, cudaMemcpyAsync(p_rad, g->radius, nL * 8, cudaMemcpyHostToDevice, s));
     RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, s));
   }
-  RB_CUDA(ctx, cudaMemcpyAsync(p_alpha, rt->alpha, nL * F * 8, cudaMemcpyHostToDevice, s));
+  if (!resident_alpha) RB_CUDA(ctx, cudaMemcpyAsync(p_alpha, rt->alpha, nL * F * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_T, rt->T, nL * 8, cudaMemcpyHostToDevice, s));
   RB_TRACE_AT("inputs enqueued");
   L.radius = (const double*)p_rad; L.b = (const double*)p_b;
@@ -752,6 +839,18 @@ int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt
   RB_CUDA(ctx, cudaStreamSynchronize(s));
   RB_TRACE_AT("synchronised");
   return RB_OK;
+}
+
+int rb_rt_batch(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt, int64_t R, const double* b,
+                void* out_Tb, double* out_intW, int64_t profile_ray, double* out_tau, double* out_W,
+                double* out_Tblyr) {
+  return rt_batch_host(ctx, g, rt, R, b, out_Tb, out_intW, profile_ray, out_tau, out_W, out_Tblyr, false);
+}
+
+int rb_rt_batch_resident(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt, int64_t R, const double* b,
+                         void* out_Tb, double* out_intW, int64_t profile_ray, double* out_tau, double* out_W,
+                         double* out_Tblyr) {
+  return rt_batch_host(ctx, g, rt, R, b, out_Tb, out_intW, profile_ray, out_tau, out_W, out_Tblyr, true);
 }
 
 int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int64_t R, int32_t n_seg, const double* ds,

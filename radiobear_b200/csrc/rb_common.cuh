@@ -55,6 +55,14 @@ struct rb_context {
     rb_geometry_desc g{};
     cudaEvent_t done = nullptr;
   } ticket;
+  // device-resident absorption (rb_alpha_layers_resident / rb_alpha_rescale_resident): the slab and the
+  // per-constituent cube stay in RB_BUF_RES_TOTAL / RB_BUF_RES_CUBE between calls; generations count overwrites
+  struct Resident {
+    int L = 0, F = 0;            // slab [L][F]
+    int cL = 0, cF = 0, cC = 0;  // cube [cL][cF][cC]
+    uint64_t slab_gen = 0, cube_gen = 0;   // 0 = nothing resident
+    uint64_t counter = 0;
+  } res;
   double* exp_tab = nullptr;  // 2^(j/1024), j = 0..1023: copied into shared memory by every integration CTA
 };
 
@@ -74,7 +82,7 @@ inline cudaError_t rb_time_end(rb_context* ctx, int which) {
 enum {
   RB_BUF_FREQS = 0, RB_BUF_T, RB_BUF_P, RB_BUF_GAS, RB_BUF_CLOUD, RB_BUF_SCALE, RB_BUF_TOTAL, RB_BUF_CUBE,
   RB_BUF_RADIUS, RB_BUF_B, RB_BUF_DS, RB_BUF_NSEG, RB_BUF_TB, RB_BUF_INTW, RB_BUF_PROFILE, RB_BUF_MISC, RB_BUF_PREP,
-  RB_BUF_FLAGS, RB_BUF_CIDX, RB_BUF_ZQ, RB_BUF_BLKCNT, RB_BUF_DR2
+  RB_BUF_FLAGS, RB_BUF_CIDX, RB_BUF_ZQ, RB_BUF_BLKCNT, RB_BUF_DR2, RB_BUF_RES_TOTAL, RB_BUF_RES_CUBE
 };
 
 // The rays-major integration kernel prefetches whole 32-segment chunks of the ds slab and of the operand

@@ -127,8 +127,81 @@ def prepare_catalogs(ctx, formalisms, truncate_strength=None, truncate_freq=None
                         other=(other_dicts or {}).get(c))
 
 
+class ResidentSlab:
+    """Handle of an absorption slab [L][F] (and possibly the per-constituent cube [L][F][C]) living in the context's
+    device buffers (rb_alpha_layers_resident / rb_alpha_rescale_resident).  `rt_batch(alpha_slab=handle)` integrates
+    from it without any copy; `fetch()` brings it to the host on demand.  A later resident computation overwrites the
+    buffers: the generation numbers tell whether this handle's data is still there."""
+
+    def __init__(self, ctx, L, F, slab_gen, cube_shape=None, cube_gen=0):
+        self.ctx, self.shape, self.slab_gen = ctx, (int(L), int(F)), int(slab_gen)
+        self.cube_shape, self.cube_gen = cube_shape, int(cube_gen)
+
+    def _gens(self):
+        sg, cg = C.c_uint64(0), C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.rb_alpha_resident_info(self.ctx.h, None, C.byref(sg), None, C.byref(cg)))
+        return int(sg.value), int(cg.value)
+
+    def valid(self):
+        return self.slab_gen != 0 and self._gens()[0] == self.slab_gen
+
+    def cube_valid(self):
+        return self.cube_gen != 0 and self._gens()[1] == self.cube_gen
+
+    def fetch(self):
+        if not self.valid():
+            raise RuntimeError('the resident absorption slab has been overwritten')
+        out = np.empty(self.shape)
+        self.ctx.check(self.ctx.lib.rb_alpha_fetch(self.ctx.h, ptr(out), None))
+        return out
+
+    def fetch_cube(self):
+        if not self.cube_valid():
+            raise RuntimeError('the resident absorption cube has been overwritten')
+        out = np.empty(self.cube_shape)
+        self.ctx.check(self.ctx.lib.rb_alpha_fetch(self.ctx.h, None, ptr(out)))
+        return out
+
+
+_resident_owner = None      # weak reference to the object whose (not yet fetched) slab sits in the resident buffer
+
+
+def _claim_resident(owner):
+    """Before the resident slab is overwritten: let its current owner copy it to the host if it still needs it."""
+    import weakref
+    global _resident_owner
+    prev = _resident_owner() if _resident_owner is not None else None
+    if prev is not None and prev is not owner and hasattr(prev, 'materialize'):
+        prev.materialize()
+    _resident_owner = weakref.ref(owner) if owner is not None else None
+
+
+def alpha_layers_resident(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formalisms=(), other_dicts=None,
+                          units='invcm', scale=None, keep_cube=False, truncate_strength=None, truncate_freq=None,
+                          owner=None, ctx=None):
+    """alpha_layers whose results stay on the device: returns a ResidentSlab handle, does not synchronise."""
+    return alpha_layers(freqs, T, P, gas, gas_dict, cloud, cloud_dict, formalisms, other_dicts, units, scale, keep_cube,
+                        truncate_strength, truncate_freq, ctx, _resident=(owner,))
+
+
+def alpha_rescale_resident(handle, scale_mat=None, owner=None):
+    """Scale-sum of the resident cube of `handle` into the resident slab (the retrieval inner loop: get_alpha='memory'
+    with a new `scale`, alpha.py:151-192) -> new ResidentSlab handle sharing the cube."""
+    if not handle.cube_valid():
+        raise RuntimeError('the resident absorption cube has been overwritten')
+    ctx = handle.ctx
+    _claim_resident(owner)
+    sm = None if scale_mat is None else f64(scale_mat)
+    if sm is not None and sm.shape != (handle.cube_shape[2], handle.cube_shape[0]):
+        raise ValueError('scale matrix must be [C][L]')
+    gen = C.c_uint64(0)
+    ctx.check(ctx.lib.rb_alpha_rescale_resident(ctx.h, ptr(sm), C.byref(gen)))
+    return ResidentSlab(ctx, handle.cube_shape[0], handle.cube_shape[1], gen.value, handle.cube_shape, handle.cube_gen)
+
+
 def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formalisms=(), other_dicts=None,
-                 units='invcm', scale=None, want_cube=False, truncate_strength=None, truncate_freq=None, ctx=None):
+                 units='invcm', scale=None, want_cube=False, truncate_strength=None, truncate_freq=None, ctx=None,
+                 _resident=None):
     """Total absorption for every (layer, freq) -> slab[L][F] (+ cube[L][F][C]).  Host arrays.
 
     Replaces the layer loop of Alpha.get_layers (alpha.py:298-300) and the plugin calls under it.
@@ -159,6 +232,11 @@ def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formal
     d.freqs, d.T, d.P, d.gas = ptr(freqs), ptr(T), ptr(P), ptr(gas)
     d.cloud = ptr(cloud)
     d.scale = ptr(sm)
+    if _resident is not None:
+        _claim_resident(_resident[0])
+        sg, cg = C.c_uint64(0), C.c_uint64(0)
+        ctx.check(ctx.lib.rb_alpha_layers_resident(ctx.h, C.byref(d), 1 if want_cube else 0, C.byref(sg), C.byref(cg)))
+        return ResidentSlab(ctx, L, F, sg.value, (L, F, len(formalisms)) if want_cube else None, cg.value)
     total = np.empty((L, F))
     cube = np.empty((L, F, len(formalisms))) if want_cube else None
     ctx.check(ctx.lib.rb_alpha_layers(ctx.h, C.byref(d), ptr(total), ptr(cube)))
@@ -275,10 +353,15 @@ def geometry_prefetch_dev(radius_t, n0, n1, b_t, Req, Rpol, orientation=(0.0, 0.
 def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape',
              disc_average=False, out_f32=False, tau_cut=TAU_CUT, want_intW=False, profile_ray=-1, ctx=None, out=None):
     """Brightness.single over a batch of rays: Tb[R][F] (+ integrated_W, + profiles of one ray)."""
-    ctx = ctx or _lib.get_context()
+    resident = isinstance(alpha_slab, ResidentSlab)
+    ctx = ctx or (alpha_slab.ctx if resident else _lib.get_context())
     ctx.use_own_stream()
     radius, T = f64(radius), f64(T)
-    alpha_slab = f64(alpha_slab)
+    if resident:
+        if not alpha_slab.valid():
+            raise RuntimeError('the resident absorption slab has been overwritten')
+    else:
+        alpha_slab = f64(alpha_slab)
     b = f64(np.atleast_2d(b))
     R, L, F = b.shape[0], radius.shape[0], alpha_slab.shape[1]
     if alpha_slab.shape[0] != L or T.shape[0] != L:
@@ -286,7 +369,7 @@ def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 
     g = build_geometry_desc(L, refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb)
     g.radius = ptr(radius)
     rt = RtDesc()
-    rt.n_freqs, rt.alpha, rt.T = F, ptr(alpha_slab), ptr(T)
+    rt.n_freqs, rt.alpha, rt.T = F, (None if resident else ptr(alpha_slab)), ptr(T)
     rt.disc_average, rt.out_f32, rt.tau_cut = int(bool(disc_average)), int(bool(out_f32)), float(tau_cut or 0.0)
     if out is None:
         out = pinned_pool.get((R, F), np.float32 if out_f32 else np.float64)
@@ -296,9 +379,9 @@ def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 
     prof = None
     if profile_ray >= 0:
         prof = [np.zeros((F, L - 1)) for _ in range(3)]
-    ctx.check(ctx.lib.rb_rt_batch(ctx.h, C.byref(g), C.byref(rt), R, ptr(b), ptr(out), ptr(intW), int(profile_ray),
-                                  ptr(prof[0]) if prof else None, ptr(prof[1]) if prof else None,
-                                  ptr(prof[2]) if prof else None))
+    call = ctx.lib.rb_rt_batch_resident if resident else ctx.lib.rb_rt_batch
+    ctx.check(call(ctx.h, C.byref(g), C.byref(rt), R, ptr(b), ptr(out), ptr(intW), int(profile_ray),
+                   ptr(prof[0]) if prof else None, ptr(prof[1]) if prof else None, ptr(prof[2]) if prof else None))
     res = {'Tb': out}
     if want_intW:
         res['integrated_W'] = intW

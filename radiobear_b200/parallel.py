@@ -384,7 +384,7 @@ def run_points_sharded(planet, pts, atm, alpha, out_f32=True, rows=None):
     cfg = atm.config
     parts = point_blocks(len(pts), cfg, rows, world)
     s, e = parts[rank]
-    F = alpha.slab.shape[1]
+    F = alpha.n_freqs
     ex = host_exchange()
     if ex.usable:
         # one node: every rank integrates its rows with the chunked host-output pipeline (D2H of ray chunk c
@@ -393,7 +393,7 @@ def run_points_sharded(planet, pts, atm, alpha, out_f32=True, rows=None):
         full = ex.begin(parts[-1][1], (F,), np.float32 if out_f32 else np.float64, pin=True)
         if e > s:
             engine.rt_batch(radius=atm.property[cfg.LP['R']], refr_index=nidx_of(atm), b=np.asarray(pts[s:e], dtype=np.float64),
-                            alpha_slab=alpha.slab, T=atm.gas[cfg.C['T']], Req=cfg.Req, Rpol=cfg.Rpol,
+                            alpha_slab=alpha.rt_slab(), T=atm.gas[cfg.C['T']], Req=cfg.Req, Rpol=cfg.Rpol,
                             orientation=[float(cfg.orientation[0]), float(cfg.orientation[1])], gtype=cfg.gtype,
                             limb=getattr(cfg, 'limb', 'shape'), out_f32=out_f32, out=full[s:e])
         return ex.finish()

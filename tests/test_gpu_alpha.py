@@ -258,3 +258,64 @@ def test_h2_orton(eng, state, units):
     with pytest.raises(ValueError):
         eng.alpha_layers(g['freqs'], gas[C['T']], gas[C['P']], gas, C, formalisms=[('h2', 'h2_orton')],
                          other_dicts={'h2': {'h2state': 'x'}})
+
+
+def test_resident_slab_and_retrieval_loop(tmp_path):
+    """The absorption stays on the device between Alpha.get_layers and the integration (no copy to the host unless
+    `.layers` is read), and the retrieval loop of scripts/demo_batch.py -- save_alpha='memory' once, then
+    get_alpha='memory' with a new `scale` per iteration -- re-runs only the scale-sum on the resident cube.
+    Values against the reference's own scaled layers (alpha.py:151-192) and against the host path."""
+    import os
+    from conftest import GOLDEN
+    from radiobear_b200 import engine
+    from radiobear_b200.atmosphere import Atmosphere
+    from radiobear_b200.alpha import Alpha
+    from radiobear_b200.brightness import Brightness
+    atm = Atmosphere.from_npz(os.path.join(GOLDEN, 'atm_jupiter.npz'), 'jupiter')
+    al = golden('alpha_jupiter.npz')
+    freqs = list(al['freqs'])
+    atm.config.scratch_directory = str(tmp_path)
+    A = Alpha(config=atm.config, verbose=False)
+    A.get_layers(freqs, atm)
+    assert A._slab is None and A._res is not None and A._res.valid() and A.has_layers()      # nothing copied back yet
+    h = A.rt_slab()
+    assert isinstance(h, engine.ResidentSlab) and h.shape == (1000, 8)
+    bright = Brightness(config=atm.config, verbose=False)
+    pts = np.array([[0.0, 0.0], [0.3, 0.2], [0.6, -0.4], [0.9, 0.1]])
+    tb_res = bright.batch(pts, freqs, atm, A, atm.config.orientation)['Tb'].copy()
+    assert A._slab is None                                            # the integration read the device copy
+    assert np.max(relerr(A.layers, al['layers'])) < TIGHT             # first host access copies it back
+    tb_host = bright.batch(pts, freqs, atm, A, atm.config.orientation)['Tb']
+    assert np.array_equal(tb_res, tb_host)
+    # a second Alpha takes the resident buffer: the first one is handed its slab before it is overwritten
+    A.get_layers(freqs, atm)
+    B = Alpha(config=atm.config, verbose=False)
+    B.get_layers(freqs[:3], atm)
+    assert A._slab is not None and not (A._res is not None and A._res.valid())
+    assert np.max(relerr(A.layers, al['layers'])) < TIGHT and B.layers.shape == (3, 1000)
+    # retrieval loop: the cube stays on the device
+    A.get_layers(freqs, atm, save_alpha='memory')
+    assert np.nanmax(relerr(A.memory.alpha_data, al['cube'])) < TIGHT
+    assert A._dev_cube is not None and A._dev_cube[0].cube_valid()
+    sc = {'nh3': list(np.linspace(0.5, 1.5, 1000)), 'h2o': [2.0] * 1000}
+    A.get_layers(freqs, atm, scale=sc, get_alpha='memory')
+    assert A._slab is None and A._res.valid() and A._res.cube_gen == A._dev_cube[0].cube_gen   # device scale-sum, no copy
+    tb_scaled = bright.batch(pts, freqs, atm, A, atm.config.orientation)['Tb'].copy()
+    assert np.max(relerr(A.layers, al['layers_scaled_dict'])) < TIGHT
+    A.get_layers(freqs, atm, scale=list(np.linspace(2.0, 0.1, 1000)), get_alpha='memory')
+    assert np.max(relerr(A.layers, al['layers_scaled_list'])) < TIGHT
+    # the same iteration through the host path (another Alpha whose memory cache is a host array only)
+    H = Alpha(config=atm.config, verbose=False)
+    H.memory = A.memory
+    H.get_layers(freqs, atm, scale=sc, get_alpha='memory')
+    assert H._res is None and np.max(relerr(H.layers, al["layers_scaled_dict"])) < TIGHT
+    tb_scaled_host = bright.batch(pts, freqs, atm, H, atm.config.orientation)['Tb']
+    assert np.allclose(tb_scaled, tb_scaled_host, rtol=0, atol=1e-9) and np.abs(tb_scaled - tb_res).max() > 0.1
+    # a replaced cache array is not mistaken for the device copy
+    A.memory.alpha_data = np.array(A.memory.alpha_data) * 2.0
+    A.get_layers(freqs, atm, get_alpha='memory')
+    assert A._res is None and np.max(relerr(A.layers, 2.0 * al['layers'])) < TIGHT
+    # error handling of the C ABI: no resident slab of the right shape
+    with pytest.raises((ValueError, RuntimeError)):
+        engine.rt_batch(b=pts, alpha_slab=h, T=atm.gas[atm.config.C['T']], radius=atm.property[atm.config.LP['R']],
+                        refr_index=atm.property[atm.config.LP['N']], Req=atm.config.Req, Rpol=atm.config.Rpol)
