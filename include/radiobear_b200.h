@@ -268,6 +268,11 @@ int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int
 /* Sustained FP64 FMA rate of the device in TFLOP/s (2 flops per DFMA, 16 independent chains per thread,
  * CUDA events): the roofline denominator of the FP64-bound kernels. */
 int rb_probe_fp64_peak(rb_context* ctx, int iters, double* out_tflops);
+/* Measurement aid: time in ms of `iters` trips of 16 DFMA + n_mufu (0, 2, 4, 8) MUFU.RCP64H per thread, 8 x 256 threads
+ * per SM; rrr: 0 one register operand, 1 three distinct register pairs per DFMA, 2 two + an immediate, 3 three with two
+ * shared by all chains (n_mufu = 0 only for 2 and 3).  Shows what the reciprocal seed and the register
+ * file cost the FP64 pipe. */
+int rb_probe_fp64_mix(rb_context* ctx, int iters, int n_mufu, int rrr, double* out_ms);
 /* y[i] = reciprocal of x[i] as the line loops compute it: MUFU.RCP64H seed + `newton` (0..2) Newton steps. */
 int rb_probe_rcp(rb_context* ctx, int newton, int n, const double* x, double* y);
 

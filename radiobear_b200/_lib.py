@@ -106,6 +106,7 @@ def load():
         'rb_rt_integrate': (C.c_int, [vp, C.POINTER(RtDesc), i32, i64, i32, vp, vp, vp, vp]),
         'rb_probe_fp64_peak': (C.c_int, [vp, C.c_int, C.POINTER(dbl)]),
         'rb_probe_rcp': (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+        'rb_probe_fp64_mix': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(dbl)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -121,7 +122,7 @@ EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error'
                     'rb_set_rt_chunks', 'rb_set_rt_precision', 'rb_get_rt_precision', 'rb_set_rt_tuning', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
                     'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_alpha_layers_resident', 'rb_alpha_rescale_resident',
                     'rb_alpha_resident_info', 'rb_alpha_fetch', 'rb_rt_batch_resident', 'rb_compute_ds', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
-                    'rb_probe_fp64_peak', 'rb_probe_rcp']
+                    'rb_probe_fp64_peak', 'rb_probe_rcp', 'rb_probe_fp64_mix']
 
 _EXC = {RB_ERR_INVALID: ValueError, RB_ERR_CUDA: RadiobearB200Error, RB_ERR_NOMEM: MemoryError,
         RB_ERR_UNSUPPORTED: NotImplementedError}

@@ -248,8 +248,11 @@ __device__ __forceinline__ double acloud(double k, double fraction, cplx e) {
 __device__ __forceinline__ double ld0(const double* p, int l) { return p ? p[l] : 0.0; }
 
 // ================================================================================================
+#ifndef RB_ALPHA_FPT4_CTAS
+#define RB_ALPHA_FPT4_CTAS 1
+#endif
 template <int FPT, int NEWTON>
-__global__ void __launch_bounds__(kThreads) alpha_lines_kernel(const __grid_constant__ AlphaK k) {
+__global__ void __launch_bounds__(kThreads, FPT >= 4 ? RB_ALPHA_FPT4_CTAS : 2) alpha_lines_kernel(const __grid_constant__ AlphaK k) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double s_pow[PW_COUNT];
 
@@ -877,6 +880,13 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   if (k.nh3_form == RB_F_NH3_BG) { k.any_S = 0; k.any_I = 0; k.any_J = 1; }   // one constant set at every frequency
   // tiling: lanes = 32*FPT frequencies per warp; K line slices per group when F is small
   k.fpt = (k.F >= 512) ? 2 : 1;
+  {
+    // RB_ALPHA_FPT=4: four frequencies per lane (128 per warp) for wide sweeps -- half the table reads per line
+    // evaluation of FPT = 2, at one CTA per SM (measured at C5: see DESIGN.md 3.1)
+    const char* e = getenv("RB_ALPHA_FPT");
+    if (e && atoi(e) == 4 && k.F >= 1024) k.fpt = 4;
+    if (e && atoi(e) == 1) k.fpt = 1;
+  }
   k.ngroups = (k.F + 32 * k.fpt - 1) / (32 * k.fpt);
   k.K = 1;
   while (k.K < kWarps && k.ngroups * k.K * 2 <= kWarps) k.K *= 2;
@@ -887,9 +897,9 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   {
     const long long want = 8LL * ctx->num_sms;
     const int per_layer = (int)((want + k.L - 1) / k.L);
-    if (per_layer < nblk_x) nblk_x = per_layer < 1 ? 1 : per_layer;
-    const char* e = getenv("RB_ALPHA_BLOCKS_PER_LAYER");
-    if (e && atoi(e) > 0 && atoi(e) < nblk_x) nblk_x = atoi(e);
+    const char* e = getenv("RB_ALPHA_BLOCKS_PER_LAYER");     // measurement aid: 0 = one group per warp (no trips)
+    if (e && atoi(e) > 0) { if (atoi(e) < nblk_x) nblk_x = atoi(e); }
+    else if (!e && per_layer < nblk_x) nblk_x = per_layer < 1 ? 1 : per_layer;
   }
 
   // smem layout
@@ -924,7 +934,8 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   }
   const int newton = ctx->alpha_newton;
   void (*kern)(const AlphaK) = nullptr;
-  if (k.fpt == 2) kern = (newton == 1) ? alpha_lines_kernel<2, 1> : alpha_lines_kernel<2, 2>;
+  if (k.fpt == 4) kern = (newton == 1) ? alpha_lines_kernel<4, 1> : alpha_lines_kernel<4, 2>;
+  else if (k.fpt == 2) kern = (newton == 1) ? alpha_lines_kernel<2, 1> : alpha_lines_kernel<2, 2>;
   else kern = (newton == 1) ? alpha_lines_kernel<1, 1> : alpha_lines_kernel<1, 2>;
   RB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   dim3 grid(nblk_x, k.L);

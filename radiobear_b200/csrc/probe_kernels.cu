@@ -5,19 +5,53 @@
 
 namespace {
 
-// 16 independent DFMA chains per thread: enough ILP for the FP64 pipe at any occupancy
+// 16 independent DFMA chains per thread: enough ILP for the FP64 pipe at any occupancy.  Each DFMA reads two
+// distinct register pairs and an immediate -- the operand pattern that reaches the pipe's issue rate of one warp
+// instruction per two clocks per scheduler (three fresh register reads per DFMA: one per three clocks; two operands from
+// the reuse cache: one per 2.2 -- rb_probe_fp64_mix, tools/probe_pipes.py)
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
-  double v[16];
+  double v[16], w[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  for (int i = 0; i < 16; ++i) { v[i] = 1.0 + 1e-9 * (threadIdx.x + i); w[i] = a + b * (threadIdx.x + i); }
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fma(v[i], a, b);
+    for (int i = 0; i < 16; ++i) v[i] = fma(v[i], w[i], 1.5);
   }
   double s = 0.0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += v[i];
   if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+
+// Pipe-sharing probe: 16 DFMA per trip and thread next to NM MUFU.RCP64H (the reciprocal seed of the line loops);
+// RRR: every DFMA reads three distinct register pairs (the probe above has one register operand, two from the
+// constant bank).  Tells whether the SFU instruction and the register file cost the FP64 pipe issue cycles.
+// RRR modes: 0 one register operand (v) + two from the constant bank; 1 three distinct register pairs per DFMA;
+// 2 two distinct register pairs + an immediate; 3 three register pairs, two of them shared by all 16 chains (reuse cache)
+template <int NM, int RRR>
+__global__ void __launch_bounds__(256) fp64_mix_kernel(double* out, int iters, double a, double b) {
+  double v[16], w[16], u[16], m[8];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    w[i] = a + 1e-12 * (threadIdx.x + i);
+    u[i] = b + 1e-12 * (threadIdx.x + 2 * i);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = 1.5 + 1e-3 * (threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      v[i] = RRR == 1 ? fma(v[i], w[i], u[i]) : RRR == 2 ? fma(v[i], w[i], 1.5) : RRR == 3 ? fma(v[i], w[0], u[0]) : fma(v[i], a, b);
+#pragma unroll
+    for (int i = 0; i < NM; ++i) asm volatile("rcp.approx.ftz.f64 %0, %0;" : "+d"(m[i]));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += m[i];
+  if (s == 123.456) out[0] = s;
 }
 
 template <int NEWTON>
@@ -52,6 +86,45 @@ int rb_probe_fp64_peak(rb_context* ctx, int iters, double* out_tflops) {
   ctx->launches += 2;
   const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
   *out_tflops = flops / (ms * 1e-3) / 1e12;
+  return RB_OK;
+}
+
+// time (ms) of `iters` trips of 16 DFMA + n_mufu MUFU.RCP64H per thread on 8 CTAs x 256 threads per SM
+int rb_probe_fp64_mix(rb_context* ctx, int iters, int n_mufu, int rrr, double* out_ms) {
+  if (!ctx || !out_ms || iters <= 0) return rb_fail(ctx, RB_ERR_INVALID, "probe: bad arguments");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* p;
+  RB_TRY(rb_ensure(ctx, RB_BUF_MISC, 64, &p));
+  const int blocks = ctx->num_sms * 8, threads = 256;
+  void (*kern)(double*, int, double, double) = nullptr;
+  switch (n_mufu * 4 + (rrr & 3)) {
+    case 0: kern = fp64_mix_kernel<0, 0>; break;
+    case 1: kern = fp64_mix_kernel<0, 1>; break;
+    case 2: kern = fp64_mix_kernel<0, 2>; break;
+    case 3: kern = fp64_mix_kernel<0, 3>; break;
+    case 8: kern = fp64_mix_kernel<2, 0>; break;
+    case 9: kern = fp64_mix_kernel<2, 1>; break;
+    case 16: kern = fp64_mix_kernel<4, 0>; break;
+    case 17: kern = fp64_mix_kernel<4, 1>; break;
+    case 32: kern = fp64_mix_kernel<8, 0>; break;
+    case 33: kern = fp64_mix_kernel<8, 1>; break;
+    default: return rb_fail(ctx, RB_ERR_INVALID, "probe: unsupported (n_mufu, rrr) combination");
+  }
+  cudaEvent_t e0, e1;
+  RB_CUDA(ctx, cudaEventCreate(&e0));
+  RB_CUDA(ctx, cudaEventCreate(&e1));
+  kern<<<blocks, threads, 0, ctx->stream>>>((double*)p, iters / 8 + 1, 0.999999, 1e-7);
+  RB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  kern<<<blocks, threads, 0, ctx->stream>>>((double*)p, iters, 0.999999, 1e-7);
+  RB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  RB_CUDA(ctx, cudaGetLastError());
+  RB_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  RB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ctx->launches += 2;
+  *out_ms = ms;
   return RB_OK;
 }
 

@@ -1138,15 +1138,41 @@ __global__ void __launch_bounds__(256, RB_RT_CTAS) rt_integrate_rays_kernel(cons
 #ifndef RB_RTP_CTAS
 #define RB_RTP_CTAS (3 * 8 / RB_RT_WARPS)
 #endif
+// RB_RT_RING = 1: the operand streams of the pair kernel are staged by bulk copies (cp.async.bulk, the TMA engine)
+// into a ring of kPStages buffers guarded by mbarriers instead of cp.async + one CTA barrier per chunk: whichever warp
+// finds the next buffer free issues the copy of the next chunk (one thread, two instructions), and a warp that is ahead
+// of the others -- its frequencies are still in the cheap small-tau phase, or already finished -- keeps going for up to
+// kPStages - 2 chunks instead of waiting at the barrier (see the ring protocol in the kernel).
+// Measured on B200 (C4, profiles/r2_ab_ring.jsonl), same bits as the barrier version: 3 x 16 segments 3.96 ms,
+// 4 x 16 (5 CTAs/SM) 3.97, 4 x 8 4.78, 3 x 32 (5 CTAs/SM) 3.80 against 3.49 ms with cp.async + one barrier per 32
+// segments -- a warp parked at a CTA barrier costs nothing, a warp polling an mbarrier takes issue slots from the warps
+// that have work, and the kernel is short of exactly those.  Kept as a build option, off by default.
+#ifndef RB_RT_RING
+#define RB_RT_RING 0
+#endif
+#ifndef RB_RTP_CHUNK
+#define RB_RTP_CHUNK (RB_RT_RING ? 16 : RB_RT_CHUNK)
+#endif
+#ifndef RB_RTP_STAGES
+#define RB_RTP_STAGES (RB_RT_RING ? 4 : 2)
+#endif
+constexpr int kPChunk = RB_RTP_CHUNK;                // segments per staged tile of the pair kernel
+constexpr int kPStages = RB_RTP_STAGES;
+constexpr int kPTileDs = (kPChunk + 1) * 32;         // doubles per ds tile (one extra row: ds_i+1 of the last segment)
+static_assert(kPChunk % 4 == 0 && kPChunk >= 8, "pair kernel: trips of four segments");
+static_assert(RB_RT_RING ? kPStages >= 3 : kPStages == 2, "ring: at least three buffers; barrier version: two");
 constexpr int kPairRow = 3;                          // double2 per (segment, pair)
 constexpr int kPairThreads = 32 * kPairWarps;
-constexpr int kPairTileQ = kChunk * kPairWarps * kPairRow;    // double2 per operand tile
+constexpr int kPairTileQ = kPChunk * kPairWarps * kPairRow;    // double2 per operand tile
 constexpr int kPairRound = kPairThreads * 16;        // bytes one round of 16-byte copies of the whole CTA moves
-constexpr size_t kPairsSmemBytes = kStages * (kTileDs * sizeof(double) + kPairTileQ * sizeof(double2));
-static_assert((kChunk * 32 * sizeof(double)) % kPairRound == 0, "ds tile: whole copy rounds");
-static_assert((kPairTileQ * sizeof(double2)) % kPairRound == 0, "pair operand tile: whole copy rounds");
-static_assert(kRtSlackBytes >= (kChunk + 1) * 32 * sizeof(double) + 256, "ds slab slack covers one over-read chunk");
-static_assert(kRtSlackBytes >= kChunk * 8 * kPairRow * sizeof(double2), "pair operand slack covers one over-read chunk");
+constexpr size_t kPairStageBytes = kPTileDs * sizeof(double) + kPairTileQ * sizeof(double2);
+constexpr size_t kPairsSmemBytes = kPStages * kPairStageBytes + (RB_RT_RING ? 2 * kPStages * 8 + 16 : 0);
+static_assert(RB_RT_RING || (kPChunk * 32 * sizeof(double)) % kPairRound == 0, "ds tile: whole copy rounds");
+static_assert(RB_RT_RING || (kPairTileQ * sizeof(double2)) % kPairRound == 0, "pair operand tile: whole copy rounds");
+static_assert((kPTileDs * sizeof(double)) % 16 == 0 && (kPairTileQ * sizeof(double2)) % 16 == 0, "bulk copies: 16-byte sizes");
+// (the ring issues no chunk beyond the one that holds row S - 1: at most one chunk of over-read in both versions)
+static_assert(kRtSlackBytes >= (size_t)(kPChunk + 1) * 32 * sizeof(double) + 256, "ds slab slack covers one over-read chunk");
+static_assert(kRtSlackBytes >= (size_t)kPChunk * 8 * kPairRow * sizeof(double2), "pair operand slack covers one over-read chunk");
 static_assert(kRtSlackBytes >= kChunk * 8 * sizeof(double4), "operand slack covers one over-read chunk");
 
 // pair operands:  prep2[fg][i][p] = { asum_a, asum_b }, { a'_a, T_i+1 a'_a }, { a'_b, T_i+1 a'_b },
@@ -1191,12 +1217,39 @@ __device__ __forceinline__ double2 lds_v2(unsigned a) {
   return v;
 }
 
+// ---- mbarrier / bulk-copy primitives of the ring (PTX; shared-window addresses) ---------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {     // may block for a bounded time
+  unsigned ok;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {         // never blocks
+  unsigned ok;
+  asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_kernel(const __grid_constant__ RtK k) {
   // dynamic shared memory: [ table | ds tiles x kStages | pair operand tiles x kStages ]
   extern __shared__ __align__(16) unsigned char s_raw[];
   double* const s_tab = reinterpret_cast<double*>(s_raw);
   double* const s_ds = s_tab + kExpTabDoubles;
-  double2* const s_q = reinterpret_cast<double2*>(s_ds + kStages * kTileDs);
+  double2* const s_q = reinterpret_cast<double2*>(s_ds + kPStages * kPTileDs);
   const int tid = threadIdx.y * 32 + threadIdx.x;
 
   const int S = k.L - 1;
@@ -1211,29 +1264,77 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
   const bool nanray = validA && k.nanflag[tpos] != 0;
   const int steps = (validA && !nanray) ? n - 1 : 0;        // brightness.py:65: i = 0 .. len(ds)-2
 
+  // bit 0: frequency a is live, bit 1: frequency b (a ghost b beyond F rides along with zero operands)
+  int mode = (steps > 0) ? 3 : 0;
+#if RB_RT_RING
+  // ---- ring protocol ------------------------------------------------------------------------------------------
+  // Chunk n of the tile (kPChunk segments: one contiguous piece of the ds tile and one of the operand slab) lives in
+  // buffer n % kPStages.  full[b] completes when the two bulk copies of the chunk have landed (transaction bytes);
+  // empty[b] when all warps of the CTA have released the chunk (one arrival per warp).  After releasing a chunk, lane 0
+  // of a warp issues every following chunk whose buffer is free (s_issued counts them; an atomic claims a chunk), so
+  // the copies run up to kPStages - 1 chunks ahead of the slowest warp and the fastest warp at most kPStages - 2
+  // chunks ahead of it.  A warp whose rays are all finished keeps releasing chunks without work until s_live -- the
+  // number of warps with unfinished rays -- reaches 0.
+  unsigned long long* const s_bar = reinterpret_cast<unsigned long long*>(s_q + kPStages * kPairTileQ);
+  int* const s_ctl = reinterpret_cast<int*>(s_bar + 2 * kPStages);     // [0] live warps, [1] chunks issued so far
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(s_bar);
+  auto bar_full = [&](int b) { return bar0 + 8u * (unsigned)b; };
+  auto bar_empty = [&](int b) { return bar0 + 8u * (unsigned)(kPStages + b); };
+  const char* const g_ds = reinterpret_cast<const char*>(k.ds + (size_t)tile * S * 32);
+  const char* const g_q = reinterpret_cast<const char*>(k.prep2 + (size_t)rt_.fg * S * kPairWarps * kPairRow);
+  const unsigned sh_ds = (unsigned)__cvta_generic_to_shared(s_ds), sh_q = (unsigned)__cvta_generic_to_shared(s_q);
+  constexpr unsigned kDsBytes = kPTileDs * sizeof(double), kQBytes = kPairTileQ * sizeof(double2);
+  const int last_chunk = (S - 1) / kPChunk;                  // no ray uses rows beyond S - 1
+  auto issue = [&](int n) {                                  // one thread
+    const int b = n % kPStages;
+    mbar_expect_tx(bar_full(b), kDsBytes + kQBytes);
+    bulk_g2s(sh_ds + (unsigned)b * kDsBytes, g_ds + (size_t)n * (kPChunk * 32 * sizeof(double)), kDsBytes, bar_full(b));
+    bulk_g2s(sh_q + (unsigned)b * kQBytes, g_q + (size_t)n * kQBytes, kQBytes, bar_full(b));
+  };
+  if (tid == 0) {
+    for (int b = 0; b < kPStages; ++b) { mbar_init(bar_full(b), 1); mbar_init(bar_empty(b), kPairWarps); }
+    s_ctl[0] = 0; s_ctl[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  bool warp_live = __any_sync(0xffffffffu, mode != 0);
+  if (threadIdx.x == 0 && warp_live) atomicAdd(&s_ctl[0], 1);
+  __syncthreads();
+  const bool any_live = s_ctl[0] > 0;
+  if (any_live) {
+    for (int q = tid; q < kExpTabDoubles / 2; q += kPairThreads) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
+    cp_async_commit();
+    if (tid == 0) {
+      const int n0 = min(kPStages - 1, last_chunk + 1);      // the first chunks: every buffer but one
+      for (int n = 0; n < n0; ++n) issue(n);
+      s_ctl[1] = n0;
+    }
+    cp_async_wait<0>();
+  }
+  __syncthreads();                                           // table landed, s_ctl[1] published
+#else
   // copy plan (see rt_integrate_rays_kernel): ds chunk 33 x 256 B, operand chunk kChunk x 384 B, 16-byte pieces
   const char* src_ds = reinterpret_cast<const char*>(k.ds + (size_t)tile * S * 32) + tid * 16;
   const char* src_q = reinterpret_cast<const char*>(k.prep2 + (size_t)rt_.fg * S * kPairWarps * kPairRow) + tid * 16;
   const unsigned dst_ds = (unsigned)__cvta_generic_to_shared(s_ds) + tid * 16;
   const unsigned dst_q = (unsigned)__cvta_generic_to_shared(s_q) + tid * 16;
   auto issue = [&](int c) {
-    const unsigned bd = (c & 1) ? (unsigned)(kTileDs * sizeof(double)) : 0u;
+    const unsigned bd = (c & 1) ? (unsigned)(kPTileDs * sizeof(double)) : 0u;
     const unsigned bq = (c & 1) ? (unsigned)(kPairTileQ * sizeof(double2)) : 0u;
-    constexpr int kDsRounds = (kChunk * 32 * (int)sizeof(double)) / kPairRound;
+    constexpr int kDsRounds = (kPChunk * 32 * (int)sizeof(double)) / kPairRound;
     cp_rounds<kDsRounds, kPairRound>(dst_ds + bd, src_ds);
     cp_rounds<(kPairTileQ * (int)sizeof(double2)) / kPairRound, kPairRound>(dst_q + bq, src_q);
     if (tid < 16) cp_async16_at<kDsRounds * kPairRound>(dst_ds + bd, src_ds);
     cp_async_commit();
-    src_ds += kChunk * 32 * sizeof(double);
+    src_ds += kPChunk * 32 * sizeof(double);
     src_q += kPairTileQ * sizeof(double2);
   };
-  // bit 0: frequency a is live, bit 1: frequency b (a ghost b beyond F rides along with zero operands)
-  int mode = (steps > 0) ? 3 : 0;
   const bool any_live = __syncthreads_or(mode != 0);
   if (any_live) {
     for (int q = tid; q < kExpTabDoubles / 2; q += kPairThreads) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
     issue(0);
   }
+#endif
 
   const int vz = threadIdx.x >> 5;   // blockDim.x == 32: always zero, unknown to ptxas (see pin())
   // cM = 2^52 + 2^51, 1 and 1/2 have an all-zero low word: they are encoded in the instruction (a DFMA / DADD takes
@@ -1308,23 +1409,40 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
   constexpr int small_hi = (int)(((0x3FFull - (RB_EXP_SMALL_LOG > 0 ? RB_EXP_SMALL_LOG : 1)) << 20));
 
   for (int c = 0; any_live; ++c) {
+#if RB_RT_RING
+    {
+      // wait for chunk c; give up when no warp of the CTA has work left (nobody will issue it any more)
+      const unsigned fb = bar_full(c % kPStages), par = (unsigned)(c / kPStages) & 1u;
+      bool got = __all_sync(0xffffffffu, mbar_try_wait(fb, par));
+      while (!got) {
+        if (__any_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&s_ctl[0]) <= 0)) break;
+        got = __all_sync(0xffffffffu, mbar_try_wait(fb, par));
+      }
+      if (!got) break;
+    }
+    bool wrote_zero = false;
+#else
     cp_async_wait<0>();
     if (!__syncthreads_or(mode != 0)) break;
     issue(c + 1);
+#endif
     if (mode != 0) {
-      double* dsb = s_ds + (c % kStages) * kTileDs + threadIdx.x;
-      const double2* qb = s_q + (c % kStages) * kPairTileQ + threadIdx.y * kPairRow;
-      const int zrow = steps - c * kChunk;
-      if (zrow <= kChunk) dsb[zrow * 32] = 0.0;              // nothing lies below the last node
-      const int m = min(kChunk, steps - i);
+      double* dsb = s_ds + (c % kPStages) * kPTileDs + threadIdx.x;
+      const double2* qb = s_q + (c % kPStages) * kPairTileQ + threadIdx.y * kPairRow;
+      const int zrow = steps - c * kPChunk;
+#if RB_RT_RING
+      wrote_zero = zrow <= kPChunk;
+#endif
+      if (zrow <= kPChunk) dsb[zrow * 32] = 0.0;             // nothing lies below the last node
+      const int m = min(kPChunk, steps - i);
       int u = 0;
       if (mode == 3 && m >= 4) {
         // Trips of 2 x (two segments x two frequencies).  The optical depths are updated in place; a group the
         // fast loops cannot finish (it leaves the small-tau range / a frequency crosses tau_cut inside it) is
         // handed, with its four optical depths, to finish_group, which takes it one step at a time.
-        const unsigned dbase = ds_a0 + (unsigned)((c % kStages) * kTileDs * sizeof(double));
+        const unsigned dbase = ds_a0 + (unsigned)((c % kPStages) * kPTileDs * sizeof(double));
         unsigned dpa = dbase;
-        unsigned qpa = q_a0 + (unsigned)((c % kStages) * kPairTileQ * sizeof(double2));
+        unsigned qpa = q_a0 + (unsigned)((c % kPStages) * kPairTileQ * sizeof(double2));
         const unsigned dlast = dbase + 256u * (unsigned)(m - 4);   // last trip start with four segments left
         double d0 = lds_f64<0>(dpa), d1, d2, d3, tA0, tB0;
         double2 s0, s1;
@@ -1438,8 +1556,39 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
       i += u;
       if (i >= steps || (mode == 2 && !validB)) mode = 0;
     }
+#if RB_RT_RING
+    {
+      // release chunk c; the zero written over ds_steps (generic proxy) must be ordered before the bulk copy (async
+      // proxy) that refills the buffer
+      if (__any_sync(0xffffffffu, wrote_zero)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const bool still = __any_sync(0xffffffffu, mode != 0);
+      if (threadIdx.x == 0) {
+        if (warp_live && !still) atomicSub(&s_ctl[0], 1);
+        mbar_arrive(bar_empty(c % kPStages));
+        // issue every following chunk whose buffer has been released by all warps (chunk n reuses the buffer of chunk
+        // n - kPStages); whoever releases a buffer last finds it free here, so no chunk is left unissued
+        while (*reinterpret_cast<volatile int*>(&s_ctl[0]) > 0) {
+          const int nx = *reinterpret_cast<volatile int*>(&s_ctl[1]);
+          if (nx > last_chunk) break;
+          if (nx >= kPStages && !mbar_test(bar_empty(nx % kPStages), (unsigned)(nx / kPStages - 1) & 1u)) break;
+          if (atomicCAS(&s_ctl[1], nx, nx + 1) == nx) issue(nx);
+        }
+      }
+      warp_live = still;
+    }
+#endif
   }
+#if RB_RT_RING
+  __syncthreads();
+  if (any_live && tid == 0) {
+    // bulk copies still in flight must land before the CTA gives up its shared memory: the last chunk of every buffer
+    const int issued = s_ctl[1];
+    for (int n = max(0, issued - kPStages); n < issued; ++n)
+      while (!mbar_try_wait(bar_full(n % kPStages), (unsigned)(n / kPStages) & 1u)) {}
+  }
+#else
   cp_async_wait<0>();
+#endif
   if (k.step_counter) {   // measurement aid (bench.py): executed (ray, freq, segment) steps, one atomic per warp
     unsigned long long done = 2ull * (unsigned long long)nf + (unsigned long long)ns;
     unsigned long long done_a = (unsigned long long)ia;
