@@ -301,8 +301,9 @@ def alpha_c5(ctx, dev, reps=5, full=False, world=1, rank=0):
     atmosphere x 4096 freqs x NH3 catalog, formalism nh3_dbs_sjs; SURVEY 8d: T~U(80,1800) K,
     P log-U(1e-2,5e3) bar, X_NH3 log-U(1e-7,1e-3), X_H2 = 0.86, X_He = 0.135, seed 0).
 
-    world > 1: the frequencies are split into contiguous blocks, one per rank; every rank computes
-    its [L][F/world] block and one NCCL all_gather + a transposing copy leave the full [L][F] slab on every GPU
+    world > 1: the layers are split into contiguous blocks, one per rank (layers rather than
+    frequencies because a CTA builds its layer's line tables once -- parallel.alpha_layers_sharded); every rank computes
+    its [L/world][F] block and one NCCL all_gather writes the blocks straight into the full [L][F] slab on every GPU
     (what the ray integration of every rank needs).  Timed with CUDA events around compute + collective, max over
     ranks; `value` is the whole job."""
     import torch
@@ -329,15 +330,13 @@ def alpha_c5(ctx, dev, reps=5, full=False, world=1, rank=0):
     evals = float(nlines.sum()) * F
     flops = (10.0 * float(n_br.sum()) + 8.0 * float(n_gr.sum())) * F          # + 1 reciprocal each (not counted)
     t64 = dict(dtype=torch.float64, device=dev)
-    parts = parallel.partition_even(F, world)
+    parts = parallel.partition_even(L, world)
     lo, hi = parts[rank]
-    wmax = max(e - s_ for s_, e in parts)
-    g_t = torch.tensor(gas, **t64).contiguous()
-    f_t, T_t, P_t = torch.tensor(freqs[lo:hi], **t64), torch.tensor(gas[C['T']], **t64), torch.tensor(P, **t64)
-    block = torch.zeros((L, wmax), **t64)            # this rank's frequencies (padded to the widest block)
-    local = block if wmax == hi - lo else torch.empty((L, hi - lo), **t64)
-    out = block if world == 1 else torch.empty((L, F), **t64)
-    gathered = torch.empty((world, L, wmax), **t64) if world > 1 else None
+    assert L % world == 0
+    g_t = torch.tensor(gas[:, lo:hi], **t64).contiguous()
+    f_t, T_t, P_t = torch.tensor(freqs, **t64), torch.tensor(gas[C['T']][lo:hi], **t64), torch.tensor(P[lo:hi], **t64)
+    out = torch.empty((L, F), **t64)                 # the full slab; this rank's block of layers is out[lo:hi]
+    local = out[lo:hi]
     forms = [('nh3', 'nh3_dbs_sjs')]
     ms, ms_k = [], []
     catalogs.use_full_nh3_catalog(full)
@@ -348,17 +347,10 @@ def alpha_c5(ctx, dev, reps=5, full=False, world=1, rank=0):
             torch.cuda.synchronize()
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-            engine.alpha_layers_dev(f_t, T_t, P_t, g_t, C, formalisms=forms, out=local, freqs_host=freqs[lo:hi], ctx=ctx)
+            engine.alpha_layers_dev(f_t, T_t, P_t, g_t, C, formalisms=forms, out=local, freqs_host=freqs, ctx=ctx)
             e1.record()
             if world > 1:
-                if local is not block:
-                    block[:, :hi - lo].copy_(local)
-                dist.all_gather_into_tensor(gathered, block)
-                if wmax * world == F:
-                    out.view(L, world, wmax).copy_(gathered.permute(1, 0, 2))
-                else:
-                    for r_, (s_, e_) in enumerate(parts):
-                        out[:, s_:e_].copy_(gathered[r_, :, :e_ - s_])
+                dist.all_gather_into_tensor(out, local)      # in place: block r of the output is rank r's input
             e2.record()
             torch.cuda.synchronize()
             if i >= 2:
@@ -379,15 +371,15 @@ def alpha_c5(ctx, dev, reps=5, full=False, world=1, rank=0):
     ref = ao.get_layers(freqs, gas, np.zeros((1, L)), C, {}, {'nh3': 'nh3_dbs_sjs'}, layers=lay,
                         cat=ao.LineCatalog(full_nh3=True) if full else None)
     t_cpu = time.perf_counter() - t0
-    got = out[lay][:, :F].cpu().numpy().T
+    got = out[lay].cpu().numpy().T
     rel = float(np.nanmax(np.abs(got - ref) / np.abs(ref)))
     cpu_rate = float(nlines[lay].sum()) * F / t_cpu
     return {'workload': 'C5: 4096 layers x 4096 freqs x NH3 (nh3_dbs_sjs{}), synthetic'.format(
                 ', full catalog: 415 + 1301 + 4198 lines' if full else ', shipped catalog: 415 + 201 + 198 lines'),
             'metric': 'alpha layer*freq*line/s',
             'value': evals / t, 'ms': t * 1e3, 'kernel_ms': t_kernel * 1e3, 'n_gpus': world,
-            'sharding': 'none' if world == 1 else 'contiguous frequency blocks per rank + all_gather (NCCL) of the [L][F/N] slabs: '
-                        'every rank ends with the full [L][F] slab',
+            'sharding': 'none' if world == 1 else 'contiguous blocks of layers per rank + one all_gather (NCCL) in place into the '
+                        '[L][F] slab: every rank ends with the full slab',
             'line_evals': evals, 'max_rel_err_vs_oracle': rel,
             'fp64_tflops_algorithmic': flops / t / 1e12,
             'flops_per_line_eval': '10 (Ben-Reuven) / 8 (Gross) + 1 reciprocal (SURVEY 8d)',
@@ -413,7 +405,7 @@ def retrieval_loop(atm, iters=20):
     scales = [scale_of(i) for i in range(iters + 3)]
     out = {}
     ref = None
-    for mode in ('resident', 'host_cube', 'recompute'):
+    for mode in ('resident', 'host_cube', 'recompute') * 2:      # two passes: the second is reported (everything warm)
         tbs = []
         for i, sc in enumerate(scales):
             if i == 3:
@@ -718,12 +710,14 @@ def run_gpu(args):
                 a5['fp64_peak_tflops_per_gpu'] = fp64_peak
                 a5['fp64_frac'] = a5['fp64_tflops_algorithmic'] / (fp64_peak * world) if fp64_peak else None
                 line[key] = a5
-        sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        dist.destroy_process_group()      # before stdout is handed back: NCCL_DEBUG=INFO reports the teardown on fd 1
+    if rank == 0:
+        # the one JSON line goes to the real stdout; fd 1 stays pointed at stderr until the process ends (NCCL and its
+        # plugins still report their shutdown there with NCCL_DEBUG=INFO)
+        sys.stdout.flush()
+        os.write(saved_stdout, (json.dumps(line) + '\n').encode())
 
 
 def main():

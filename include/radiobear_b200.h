@@ -222,6 +222,13 @@ typedef struct rb_geometry_desc {
 int rb_compute_ds(rb_context* ctx, const rb_geometry_desc* geom, int64_t n_rays, const double* b,
                   double* out_ds, int32_t* out_nseg, double* out_aspect);
 
+/* The descriptive per-step fields of raypath.compute_ds beside ds (raypath.py:186-187, 224): for every ray
+ *   out_fields[r][0][i] = Ray.r4ds[i], the shell radius at the latitude of the point where step i starts, km
+ *   out_fields[r][1][i], out_fields[r][2][i] = planetocentric latitude / longitude of that point, degrees (what
+ *   Ray.doppler is computed from, raypath.py:186); [R][3][L-1], zero beyond the ray's last step.  Host pointers. */
+int rb_compute_ray_fields(rb_context* ctx, const rb_geometry_desc* geom, int64_t n_rays, const double* b,
+                          double* out_fields);
+
 typedef struct rb_rt_desc {
   int32_t n_freqs;          /* F */
   const double* alpha;      /* [L][F] alpha slab in cm^-1 (rb_alpha_layers out_total) */

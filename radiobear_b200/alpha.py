@@ -38,8 +38,9 @@ class Alpha:
         self._layers_view = None
         self._res = None            # engine.ResidentSlab: the slab (and, after save_alpha='memory', the cube) on the device
         self._dev_cube = None       # (ResidentSlab holding the cube, the host array it mirrors)
-        # frequency sharding of get_layers over the ranks of torch.distributed: 'auto' (large requests), True, False
-        self.shard_freqs = kwargs.get('shard_freqs', 'auto')
+        # sharding of get_layers over the ranks of torch.distributed: 'auto' (large requests), True, False
+        self.shard = kwargs.get('shard', kwargs.get('shard_freqs', 'auto'))
+        self.shard_axis = kwargs.get('shard_axis', 'layers')    # 'layers' (default) or 'freqs'  (parallel.alpha_layers_sharded)
         if load_formal:
             self.setup_formalisms()
 
@@ -188,12 +189,22 @@ class Alpha:
                           truncate_strength=self.truncate_strength, truncate_freq=self.truncate_freq)
             from . import parallel
             world, _ = parallel.world_rank()
-            if not to_cache and parallel.shard_alpha(L, len(fr), world, self.shard_freqs):
-                # one process per GPU: this rank's frequency block, then one all_gather (every rank traces rays
-                # with the full slab afterwards)
-                slab = parallel.alpha_layers_sharded(
-                    lambda lo, hi: engine.alpha_layers(fr[lo:hi], atm.gas[C['T']], atm.gas[C['P']], atm.gas, C, **common),
-                    L, len(fr))
+            if not to_cache and parallel.shard_alpha(L, len(fr), world, self.shard):
+                # one process per GPU: this rank's block of layers (or of frequencies), then one all_gather (every
+                # rank traces rays with the full slab afterwards)
+                cl = common['cloud']
+                if self.shard_axis == 'freqs':
+                    def block(lo, hi):
+                        return engine.alpha_layers(fr[lo:hi], atm.gas[C['T']], atm.gas[C['P']], atm.gas, C, **common)
+                else:
+                    def block(lo, hi):
+                        kw = dict(common, cloud=None if cl is None else np.ascontiguousarray(cl[:, lo:hi]),
+                                  scale=parallel.slice_scale(scale, lo, hi))
+                        if isinstance(scale, dict):                # validated against all layers before it is cut
+                            self.get_layer_scale(scale, L)
+                        return engine.alpha_layers(fr, atm.gas[C['T']][lo:hi], atm.gas[C['P']][lo:hi],
+                                                   np.ascontiguousarray(atm.gas[:, lo:hi]), C, **kw)
+                slab = parallel.alpha_layers_sharded(block, L, len(fr), axis=self.shard_axis)
             elif os.environ.get('RB_ALPHA_RESIDENT', '1') == '0':     # A/B switch: results through host memory
                 out = engine.alpha_layers(fr, atm.gas[C['T']], atm.gas[C['P']], atm.gas, C, want_cube=to_cache, **common)
                 slab, cube = out if to_cache else (out, None)

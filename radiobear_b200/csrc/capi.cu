@@ -565,6 +565,32 @@ int rb_compute_ds(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const d
   return RB_OK;
 }
 
+int rb_compute_ray_fields(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const double* b, double* out_fields) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (!b || !out_fields || !g || !g->radius) return rb_fail(ctx, RB_ERR_INVALID, "ray_fields: null pointer");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  RtLaunch L{};
+  RB_TRY(make_geometry(ctx, g, R, &L));
+  drop_ticket(ctx);
+  const size_t S = L.L - 1;
+  void *p_rad, *p_b, *p_ds, *p_n, *p_o;
+  RB_TRY(rb_ensure(ctx, RB_BUF_RADIUS, L.L * 8, &p_rad));
+  RB_TRY(rb_ensure(ctx, RB_BUF_B, (size_t)R * 16, &p_b));
+  RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
+  RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
+  RB_TRY(rb_ensure(ctx, RB_BUF_MISC, (size_t)R * 3 * S * 8, &p_o));
+  cudaStream_t s = ctx->stream;
+  RB_CUDA(ctx, cudaMemcpyAsync(p_rad, g->radius, L.L * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemsetAsync(p_o, 0, (size_t)R * 3 * S * 8, s));
+  L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
+  RB_TRY(rb_launch_geometry(ctx, L));
+  RB_TRY(rb_launch_ray_fields(ctx, L, (double*)p_o));
+  RB_CUDA(ctx, cudaMemcpyAsync(out_fields, p_o, (size_t)R * 3 * S * 8, cudaMemcpyDeviceToHost, s));
+  RB_CUDA(ctx, cudaStreamSynchronize(s));
+  return RB_OK;
+}
+
 static int check_rt(rb_context* ctx, const rb_rt_desc* rt, const void* out_Tb) {
   if (!rt || !out_Tb) return rb_fail(ctx, RB_ERR_INVALID, "rt: null descriptor / output");
   if (rt->n_freqs <= 0) return rb_fail(ctx, RB_ERR_INVALID, "rt: n_freqs must be positive");

@@ -147,6 +147,7 @@ struct RtLaunch {
   int32_t* blkcnt;  // device [ceil(R / 256)]
 };
 int rb_launch_geometry(rb_context* ctx, const RtLaunch& g);
+int rb_launch_ray_fields(rb_context* ctx, const RtLaunch& g, double* out);
 int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out_ds_raymajor /*[R][L-1] device*/);
 int rb_launch_ds_to_slab(rb_context* ctx, const double* ds_raymajor, int64_t R, int64_t Rpad, int S, const int* nseg,
                          int* nanflag, double* slab);

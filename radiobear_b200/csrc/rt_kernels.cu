@@ -415,6 +415,58 @@ __global__ void __launch_bounds__(128, RB_GEO_CTAS) ray_geometry_kernel(const __
   g.nanflag[o] = (first_nan >= 0 && first_nan <= count - 2) ? 1 : 0;
 }
 
+// ---- descriptive ray fields of the compute_ds API (Ray.r4ds, and the latitude / longitude Ray.doppler is made of) ---
+// raypath.py:186-187, 224: per step the reference records rNowMag (the shell radius at the latitude of the current
+// point) and a Doppler factor of that point's latitude / longitude.  They describe the ray and feed nothing on the
+// hot path, so they are not carried through ray_geometry_kernel: this kernel walks the positions r_i+1 = r_i + ds_i s
+// (raypath.py:227) along the segments the geometry kernel produced, in the reference's own vector form.
+__global__ void ray_fields_kernel(const __grid_constant__ GeoK g, double* __restrict__ out) {   // out [R][3][S]
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= g.R) return;
+  const int S = g.L - 1;
+  double* o_r = out + (size_t)r * 3 * S;
+  double* o_lat = o_r + S;
+  double* o_lng = o_lat + S;
+  const int n = g.nseg[r];
+  const double q2 = g.q * g.q, rNorm = g.radius[0];
+  double zq;
+  if (n <= 0 || !find_edge(g, g.b[2 * r], g.b[2 * r + 1], zq)) return;
+  double ex, ey, ez;
+  rot2planet(g, g.b[2 * r], g.b[2 * r + 1], zq, ex, ey, ez);
+  const double kDeg = 57.295779513082320877;
+  // the shell point / normal the reference starts from (raypath.py:141-156), then Snell at the first interface
+  double v = ey / sqrt(ex * ex + ey * ey + ez * ez), sl, cl;
+  lat_sc(v, sl, cl);
+  const double hs = sqrt(ex * ex + ez * ez);
+  const double sln = (hs > 0.0) ? ex / hs : 0.0, cln = (hs > 0.0) ? ez / hs : 1.0;
+  double px = rNorm * cl * sln, py = g.q * rNorm * sl, pz = rNorm * cl * cln;
+  const double inv = 1.0 / sqrt(sl * sl + q2 * cl * cl);
+  const double nx = g.q * cl * sln * inv, ny = sl * inv, nz = g.q * cl * cln * inv;
+  double sx, sy, sz;
+  rot2planet(g, 0.0, 0.0, -1.0, sx, sy, sz);
+  {
+    const double nratio = g.n0 / g.n1;
+    const double ci = -(sx * nx + sy * ny + sz * nz);
+    const double st = nratio * sqrt(fmax(0.0, 1.0 - ci * ci));
+    const double w = nratio * ci - sqrt(1.0 - st * st);
+    sx = nratio * sx + w * nx; sy = nratio * sy + w * ny; sz = nratio * sz + w * nz;
+  }
+  const double* ds = g.ds + ds_tile_base(r, S);
+  // step 0 is described by the edge point (raypath.py:141-146), step i + 1 by r_i+1 = r_i + ds_i s (raypath.py:227-231)
+  o_r[0] = rNorm * sqrt(q2 * sl * sl + cl * cl);
+  o_lat[0] = asin(v) * kDeg;
+  o_lng[0] = atan2(ex, ez) * kDeg;
+  for (int i = 0; i + 1 < n; ++i) {
+    const double d = ds[(size_t)i * kDsStride];
+    px = fma(d, sx, px); py = fma(d, sy, py); pz = fma(d, sz, pz);
+    const double nr = sqrt(px * px + py * py + pz * pz);
+    lat_sc(py / nr, sl, cl);
+    o_r[i + 1] = g.radius[i + 1] * sqrt(q2 * sl * sl + cl * cl);   // Shape.rmag of the new point (shape.py:240-244)
+    o_lat[i + 1] = asin(py / nr) * kDeg;
+    o_lng[i + 1] = atan2(px, pz) * kDeg;
+  }
+}
+
 // [S][Rpad] slab -> [R][S] ray-major (only for the compute_ds API that returns Ray.ds)
 __global__ void ds_transpose_kernel(const double* __restrict__ slab, long long R, long long Rpad, int S,
                                     const int* __restrict__ nseg, double* __restrict__ out) {
@@ -602,6 +654,76 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
     else reinterpret_cast<double*>(k.out_Tb)[o] = v;
     if (k.out_intW) k.out_intW[o] = (n[j] < 0) ? 0.0 : w;
   }
+}
+
+// ---- disc-averaged integration (brightness.py:95-96: W = 2 a E2(tau)) -----------------------------------------
+// One CTA per (ray, frequency).  The exponential integral costs hundreds of instructions per layer (Cephes series /
+// continued fraction), and a thread that walks the ~1000 layers of a ray one after the other spends 16 ms on it
+// (rt_integrate_kernel<1, true, *>, round 1).  Only the optical depth is a recurrence: thread 0 accumulates it (one
+// FMA-class step per layer, the operations and the order of the sequential kernel), all threads evaluate E2 of the
+// layers in parallel, and thread 0 adds the weighting-function and brightness sums in layer order again -- the same
+// operations in the same order as the sequential kernel, so the same bits.  Optional profile outputs
+// (Brightness.tau / .W / .Tb_lyr, brightness.py:118-120) as in rt_integrate_kernel<1, true, true>.
+constexpr int kDiscThreads = 256;
+__global__ void __launch_bounds__(kDiscThreads) rt_disc_kernel(const __grid_constant__ RtK k, int profile) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  double* const s_tau = reinterpret_cast<double*>(s_raw);     // [S + 1] tau after step i at index i + 1
+  double* const s_W = s_tau + k.L;                            // [S + 1] W after step i at index i + 1
+  __shared__ int s_last;                                      // number of steps taken
+  const int f = blockIdx.y;
+  const long long r = blockIdx.x;
+  const int S = k.L - 1;
+  const int n = k.nseg[r];
+  const bool nanray = !profile && k.nanflag[r] != 0;
+  const int nsteps = (n > 0 && !nanray) ? n - 1 : 0;          // brightness.py:65: i = 0 .. len(ds) - 2
+  const int cut_hi = __double2hiint(k.tau_cut);
+  const double* ds = k.ds + ds_tile_base(r, S);
+  if (threadIdx.x == 0) {
+    double tau = 0.0, a0 = k.alpha[f];
+    int i = 0;
+    s_tau[0] = 0.0;
+    for (; i < nsteps; ++i) {
+      if (!(__double2hiint(tau) < cut_hi)) break;             // the rule of every integration kernel of this file
+      const double a1 = k.alpha[(size_t)(i + 1) * k.F + f];
+      const double h = ds[(size_t)i * kDsStride] * kKmToCm * 0.5;
+      tau = tau + (a0 + a1) * h;
+      s_tau[i + 1] = tau;
+      a0 = a1;
+    }
+    s_last = i;
+  }
+  __syncthreads();
+  const int last = s_last;
+  for (int i = threadIdx.x; i < last; i += kDiscThreads)
+    s_W[i + 1] = 2.0 * k.alpha[(size_t)(i + 1) * k.F + f] * expn2(s_tau[i + 1]);
+  if (threadIdx.x == 0) s_W[0] = 0.0;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double iW = 0.0, Tb = 0.0, Wp = 0.0, T0 = k.T[0];
+  if (profile && n > 0) { k.out_tau[(size_t)f * S] = 0.0; k.out_W[(size_t)f * S] = 0.0; k.out_Tblyr[(size_t)f * S] = 0.0; }
+  for (int i = 0; i < (profile ? nsteps : last); ++i) {
+    if (i < last) {
+      const double h = ds[(size_t)i * kDsStride] * kKmToCm * 0.5;
+      const double W = s_W[i + 1], T1 = k.T[i + 1];
+      iW += (W + Wp) * h;
+      Tb += (T1 * W + T0 * Wp) * h;
+      Wp = W;
+      T0 = T1;
+    }
+    if (profile) {                                            // beyond tau_cut the profiles repeat their last values
+      k.out_tau[(size_t)f * S + i + 1] = s_tau[min(i, last - 1) + 1];
+      k.out_W[(size_t)f * S + i + 1] = Wp;
+      k.out_Tblyr[(size_t)f * S + i + 1] = Tb;
+    }
+  }
+  double v, w = iW;
+  if (n < 0) v = kTcmb;
+  else if (nanray) v = w = nan("");
+  else v = (Tb < kTcmb) ? kTcmb : Tb / iW;
+  const size_t o = (size_t)r * k.F + f;
+  if (k.out_f32) reinterpret_cast<float*>(k.out_Tb)[o] = (float)v;
+  else reinterpret_cast<double*>(k.out_Tb)[o] = v;
+  if (k.out_intW) k.out_intW[o] = (n < 0) ? 0.0 : w;
 }
 
 // ---- exp(-tau) for the weighting function ------------------------------------------------------------
@@ -1217,6 +1339,7 @@ __device__ __forceinline__ double2 lds_v2(unsigned a) {
   return v;
 }
 
+#if RB_RT_RING
 // ---- mbarrier / bulk-copy primitives of the ring (PTX; shared-window addresses) ---------------------------------
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -1243,6 +1366,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+#endif
 
 __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_kernel(const __grid_constant__ RtK k) {
   // dynamic shared memory: [ table | ds tiles x kStages | pair operand tiles x kStages ]
@@ -1951,6 +2075,17 @@ int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
   return RB_OK;
 }
 
+int rb_launch_ray_fields(rb_context* ctx, const RtLaunch& g, double* out) {
+  GeoK k{};
+  k.L = g.L; k.radius = g.radius; k.n0 = g.n0; k.n1 = g.n1; k.q = g.q;
+  k.cz = g.rot[0]; k.sz = g.rot[1]; k.cx = g.rot[2]; k.sx = g.rot[3];
+  k.limb = g.limb; k.R = g.R; k.Rpad = g.Rpad; k.b = g.b; k.ds = g.ds; k.nseg = g.nseg; k.nanflag = g.nanflag;
+  ray_fields_kernel<<<(unsigned)((g.R + 127) / 128), 128, 0, ctx->stream>>>(k, out);
+  RB_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
 int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out) {
   const int S = g.L - 1;
   dim3 grid((unsigned)((g.R + 31) / 32), (S + 31) / 32), block(32, 8);
@@ -2056,14 +2191,18 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
   if (profile_ray >= 0) {
     if (g.R != 1) return rb_fail(ctx, RB_ERR_INVALID, "rt: profile outputs need a single-ray launch");
     dim3 grid(1, fgroups), block(32, 1);
-    if (k.disc) rt_integrate_kernel<1, true, true><<<grid, block, 0, ctx->stream>>>(k);
+    if (k.disc && 2 * (size_t)k.L * sizeof(double) <= 48 * 1024)
+      rt_disc_kernel<<<dim3(1, k.F), kDiscThreads, 2 * (size_t)k.L * sizeof(double), ctx->stream>>>(k, 1);
+    else if (k.disc) rt_integrate_kernel<1, true, true><<<grid, block, 0, ctx->stream>>>(k);
     else rt_integrate_kernel<1, false, true><<<grid, block, 0, ctx->stream>>>(k);
   } else if (!prep.use_rays) {
     const int wy = 4;
     const long long gx = (g.R + wy - 1) / wy;
     if (gx > 2147483647LL) return rb_fail(ctx, RB_ERR_INVALID, "rt: too many rays for one launch");
     dim3 grid((unsigned)gx, fgroups), block(32, wy);
-    if (k.disc) rt_integrate_kernel<1, true, false><<<grid, block, 0, ctx->stream>>>(k);
+    if (k.disc && g.R <= 65535 && 2 * (size_t)k.L * sizeof(double) <= 48 * 1024)
+      rt_disc_kernel<<<dim3((unsigned)g.R, k.F), kDiscThreads, 2 * (size_t)k.L * sizeof(double), ctx->stream>>>(k, 0);
+    else if (k.disc) rt_integrate_kernel<1, true, false><<<grid, block, 0, ctx->stream>>>(k);
     else rt_integrate_kernel<1, false, false><<<grid, block, 0, ctx->stream>>>(k);
   } else {
     // rays-major mapping: CTAs of 32 rays x 8 (16: pair kernel) frequencies in a 1-D grid, the frequency groups

@@ -319,6 +319,21 @@ def compute_ds(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='
     return ds, nseg, aspect
 
 
+def compute_ray_fields(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None):
+    """Per step of every ray: Ray.r4ds (km) and the planetocentric latitude / longitude (deg) of the point the step starts
+    at (raypath.py:186-187, 224).  Returns fields[R][3][L-1]."""
+    ctx = ctx or _lib.get_context()
+    ctx.use_own_stream()
+    radius = f64(radius)
+    b = f64(np.atleast_2d(b))
+    R, L = b.shape[0], radius.shape[0]
+    g = build_geometry_desc(L, refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb)
+    g.radius = ptr(radius)
+    out = np.empty((R, 3, L - 1))
+    ctx.check(ctx.lib.rb_compute_ray_fields(ctx.h, C.byref(g), R, ptr(b), ptr(out)))
+    return out
+
+
 # A ray stops once tau > TAU_CUT.  Every later term of the two sums is below e^-50 (2e-22) x T (<= 2000 K) x dtau,
 # i.e. < 1e-16: less than half an ulp of the accumulated sums (integrated_W ~ 1, Tb ~ 100 K), so adding it would not
 # change either accumulator -- the cut result is bit-identical to integrating every layer like the reference

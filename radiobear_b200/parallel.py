@@ -4,8 +4,8 @@ The hot paths shard without any data-path collective:
 * image / profile runs: contiguous blocks of image ROWS (or b-points) per rank, balanced by the number
   of on-disc pixels (off-disc pixels cost nothing); every rank holds the full alpha slab (0.5 MB at C4,
   recomputed locally in ~0.1 ms rather than broadcast); one final gather of Tb to rank 0.
-* frequency sweeps (alpha-dominated): contiguous FREQUENCY blocks per rank; one all_gather of the
-  [L][F/n] slabs when every rank needs the full slab.
+* large absorption requests (alpha-dominated sweeps): contiguous blocks of LAYERS per rank (or of frequencies,
+  `Alpha.shard_axis = 'freqs'`); one all_gather of the blocks when every rank needs the full slab.
 This replaces the reference's manual `block=[i, N]` row chunking (set_utils.py:66-76,
 scripts/image_block_pipeline.py).
 """
@@ -97,10 +97,10 @@ ALPHA_SHARD_MIN_PAIRS = 1 << 20
 
 
 def shard_alpha(L, F, world, policy='auto'):
-    """Should `Alpha.get_layers` split the frequencies of this request over the ranks?  policy: 'auto' (by size),
-    True / False (RB_ALPHA_SHARD=1 / 0 overrides 'auto')."""
+    """Should `Alpha.get_layers` split this request over the ranks?  policy: 'auto' (by size), True / False
+    (RB_ALPHA_SHARD=1 / 0 overrides 'auto')."""
     import os
-    if world <= 1 or F < world:
+    if world <= 1 or min(L, F) < world:
         return False
     env = os.environ.get('RB_ALPHA_SHARD')
     if policy == 'auto' and env is not None:
@@ -110,25 +110,62 @@ def shard_alpha(L, F, world, policy='auto'):
     return bool(policy)
 
 
-def alpha_layers_sharded(compute_block, L, F, group=None):
-    """Absorption slab [L][F] with the frequencies split over the ranks: rank r computes the contiguous block
-    `partition_even(F, world)[r]` with `compute_block(f_lo, f_hi)` (-> [L][f_hi - f_lo], numpy array or torch
-    tensor) and one all_gather gives every rank the full slab -- every rank traces rays afterwards
-    (the reference's only counterpart is running blocks of the request by hand,
-    set_utils.py:66-76).  Returns a numpy [L][F] array on every rank."""
+def all_gather_layer_blocks(local_slab, parts, group=None):
+    """All-gather layer-sharded alpha slabs [L_i][F] -> full [L][F] on every rank.  The blocks are contiguous pieces of
+    the [L][F] slab: with equal block sizes the collective writes straight into it (no padding, no transposing copy)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local_slab
+    heights = [e - s for s, e in parts]
+    F = local_slab.shape[1]
+    if len(set(heights)) == 1:
+        full = torch.empty((sum(heights), F), dtype=local_slab.dtype, device=local_slab.device)
+        dist.all_gather_into_tensor(full, local_slab.contiguous(), group=group)
+        return full
+    mx = max(heights)
+    pad = torch.zeros((mx, F), dtype=local_slab.dtype, device=local_slab.device)
+    pad[:local_slab.shape[0]] = local_slab
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([bufs[i][:heights[i]] for i in range(world)], dim=0).contiguous()
+
+
+def alpha_layers_sharded(compute_block, L, F, axis='layers', group=None):
+    """Absorption slab [L][F] computed by all ranks: rank r computes the contiguous block `partition_even(n, world)[r]`
+    of the layers (axis='layers', n = L) or of the frequencies (axis='freqs', n = F) with `compute_block(lo, hi)`
+    (-> [hi - lo][F] / [L][hi - lo], numpy array or torch tensor) and one all_gather gives every rank the full slab --
+    every rank traces rays afterwards (the reference's only counterpart is running blocks of the
+    request by hand, set_utils.py:66-76).  Layers are the default: the kernel builds a layer's line tables once per
+    CTA, so frequency blocks repeat that work on every rank (measured at C5, N = 2: 3.99 ms per rank against 3.65 for
+    half of the one-GPU time) while layer blocks do not, and a block of layers is a contiguous piece of the slab.
+    Returns a numpy [L][F] array on every rank."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    parts = partition_even(F, world)
+    by_layers = axis == 'layers'
+    parts = partition_even(L if by_layers else F, world)
     lo, hi = parts[rank]
     local = compute_block(lo, hi)
     t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local))
-    if t.shape != (L, hi - lo):
-        raise ValueError('compute_block({}, {}) returned {}, expected {}'.format(lo, hi, tuple(t.shape), (L, hi - lo)))
+    want = (hi - lo, F) if by_layers else (L, hi - lo)
+    if tuple(t.shape) != want:
+        raise ValueError('compute_block({}, {}) returned {}, expected {}'.format(lo, hi, tuple(t.shape), want))
     if dist.get_backend(group) == 'nccl' and not t.is_cuda:
         t = t.cuda()
-    full = all_gather_freq_blocks(t.contiguous(), parts, group=group)
+    full = (all_gather_layer_blocks if by_layers else all_gather_freq_blocks)(t.contiguous(), parts, group=group)
     return full.cpu().numpy() if full.is_cuda else full.numpy()
+
+
+def slice_scale(scale, lo, hi):
+    """The part of a `scale` request (number / per-layer list / dict of per-layer lists, alpha.py:235-259) that belongs
+    to layers [lo, hi)."""
+    if isinstance(scale, dict):
+        return {k: list(v)[lo:hi] for k, v in scale.items()}
+    if isinstance(scale, (list, tuple, np.ndarray)):
+        return list(scale)[lo:hi]
+    return scale
 
 
 def world_rank():

@@ -59,6 +59,14 @@ def compute_ds(atm, b, orientation=None, gtype=None, verbose=False):
     C, LP = atm.config.C, atm.config.LP
     layers = list(range(n))
     radius = atm.property[LP['R']]
-    path.update(ds=list(ds[0, :n]), layer4ds=layers, r4ds=None, P4ds=list(atm.gas[C['P']][:n]), doppler=[],
+    # the descriptive fields of the ray (raypath.py:186-187, 224): shell radius at each step and the Doppler factor
+    # 1 - (omega r cos(lat) + vw(lat)) sin(lng) / c of the point it starts at
+    fields = engine.compute_ray_fields(b=np.atleast_2d(np.asarray(b, dtype=np.float64)),
+                                       **_geometry_args(atm, orientation, gtype))[0]
+    r4, lat, lng = fields[0, :n], fields[1, :n], fields[2, :n]
+    cfg = atm.config
+    vw = np.interp(lat, getattr(cfg, 'vwlat', [0.0, 90.0]), getattr(cfg, 'vwdat', [0.0, 0.0])) / 1000.0
+    doppler = 1.0 - (getattr(cfg, 'omega_m', 0.0) * r4 * np.cos(np.radians(lat)) + vw) * np.sin(np.radians(lng)) / 3.0E5
+    path.update(ds=list(ds[0, :n]), layer4ds=layers, r4ds=list(r4), P4ds=list(atm.gas[C['P']][:n]), doppler=list(doppler),
                 tip=float(aspect[0]), rotate=float(aspect[1]), rNorm=float(radius[0]))
     return path

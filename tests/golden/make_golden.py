@@ -8,7 +8,7 @@ scratch work directory bootstrapped the way scripts/initial_planet_setup.py:12-3
 
     python tests/golden/make_golden.py [section ...]
 
-sections: atm fileio plugins plugins_nh3_extra plugins_nh3_full plugins_notrunc alpha rays tb neptune uranus image
+sections: atm fileio plugins plugins_nh3_extra plugins_nh3_full plugins_notrunc alpha rays ray_fields tb neptune uranus image
           image_full ring c3_full c5_saturn   (default: all; the last four take ~10 min each on 8 cores)
 
 Every array is float64 exactly as the reference produced it; nothing is post-processed.
@@ -350,6 +350,35 @@ def sec_rays():
          ds_jupiter_sec=dss, nseg_jupiter_sec=nsegs)
 
 
+def sec_ray_fields():
+    """raypath.compute_ds: the descriptive fields of a ray beside ds -- r4ds and doppler (raypath.py:186-187, 224) --
+    for four Jupiter rays and four rays of tilted Neptune (doppler is one entry longer than ds when the loop ends in a
+    break; the first len(ds) entries are kept)."""
+    import radiobear as rb
+    out = {}
+    blist = [[0.0, 0.0], [0.3, 0.2], [0.6, -0.4], [-0.85, 0.3]]
+    for name in ('jupiter', 'neptune'):
+        p = planet(name)
+        r4, dop, nn = [], [], []
+        for b in blist:
+            ray = rb.raypath.compute_ds(p.atmos[0], b, p.config.orientation)
+            n = len(ray.ds)
+            S = len(p.atmos[0].gas[0]) - 1
+            a, d = np.zeros(S), np.zeros(S)
+            a[:n] = ray.r4ds
+            d[:n] = ray.doppler[:n]
+            r4.append(a)
+            dop.append(d)
+            nn.append(n)
+        out['r4ds_' + name] = np.array(r4)
+        out['doppler_' + name] = np.array(dop)
+        out['nseg_' + name] = np.array(nn)
+        out['omega_m_' + name] = p.config.omega_m
+        out['vwlat_' + name] = np.array(p.config.vwlat, dtype=float)     # the zonal wind table (config.zonal), an input
+        out['vwdat_' + name] = np.array(p.config.vwdat, dtype=float)
+    save('ray_fields.npz', b=np.array(blist), **out)
+
+
 def sec_tb():
     """End-to-end Tb: the reference's own known-answer case (scripts/benchmark.py:10-24), the Jupiter
     default disc spectrum '1:100:5' (config C1), point rays and a limb profile (config C3 subset)."""
@@ -626,7 +655,7 @@ def sec_fileio():
 
 
 SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins_nh3_full': sec_plugins_nh3_full, 'plugins_h2_orton': sec_plugins_h2_orton, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
-            'rays': sec_rays, 'tb': sec_tb, 'neptune': sec_neptune, 'uranus': sec_uranus, 'image': sec_image,
+            'rays': sec_rays, 'ray_fields': sec_ray_fields, 'tb': sec_tb, 'neptune': sec_neptune, 'uranus': sec_uranus, 'image': sec_image,
             'image_full': sec_image_full, 'ring': sec_ring, 'c3_full': sec_c3_full, 'c5_saturn': sec_c5_saturn}
 
 if __name__ == '__main__':

@@ -156,14 +156,37 @@ def _worker_alpha(rank, world, port, out):
             return np.ascontiguousarray(lay.T)                 # [L][F] like the kernel
         engine.alpha_layers = stub
         freqs = np.linspace(2.0, 40.0, 7)
-        a = rbalpha.Alpha(config=cfg, verbose=False, shard_freqs=True)
+        a = rbalpha.Alpha(config=cfg, verbose=False, shard=True, shard_axis='freqs')
         a.get_layers(freqs, atm)
         sharded_calls = [c.copy() for c in calls]
         full = a.layers.copy()
+        # the default axis: blocks of layers, here with a per-constituent scale that has to be cut the same way
+        L = atm.gas.shape[1]
+        sc = {'nh3': list(np.linspace(0.5, 1.5, L))}
+        seen = []
+
+        def stub_l(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formalisms=(), other_dicts=None, **kw):
+            seen.append((gas.shape[1], None if cloud is None else cloud.shape[1], len(kw['scale']['nh3'])))
+            lay = ao.get_layers(freqs, gas, cloud, gas_dict, cloud_dict, dict(formalisms), other_dicts=other_dicts,
+                                truncate_strength=kw.get('truncate_strength'))
+            j = [c for c, _ in formalisms].index('nh3')
+            cube = ao.get_layers(freqs, gas, cloud, gas_dict, cloud_dict, {'nh3': dict(formalisms)['nh3']},
+                                 other_dicts=other_dicts, truncate_strength=kw.get('truncate_strength'))
+            return np.ascontiguousarray((lay + cube * (np.array(kw['scale']['nh3'])[None, :] - 1.0)).T)
+        engine.alpha_layers = stub_l
+        al = rbalpha.Alpha(config=cfg, verbose=False, shard=True)
+        al.get_layers(freqs, atm, scale=sc)
+        llo, lhi = parallel.partition_even(L, world)[rank]
+        by_layers = al.layers.copy()
+        engine.alpha_layers = stub
         whole = stub(freqs, None, None, atm.gas, cfg.C, cloud=atm.cloud, cloud_dict=cfg.Cl, formalisms=a.formalisms(),
                      other_dicts=a.other_dict, truncate_strength=a.truncate_strength).T      # all frequencies in one call
         lo, hi = parallel.partition_even(7, world)[rank]
-        checks = [len(sharded_calls) == 1, np.array_equal(sharded_calls[0], freqs[lo:hi]),
+        whole_l = stub_l(freqs, None, None, atm.gas, cfg.C, cloud=atm.cloud, cloud_dict=cfg.Cl, formalisms=a.formalisms(),
+                         other_dicts=a.other_dict, truncate_strength=a.truncate_strength, scale=sc).T
+        checks = [seen[0] == (lhi - llo, lhi - llo, lhi - llo), by_layers.shape == (7, L),
+                  bool(np.allclose(by_layers, whole_l, rtol=1e-12, atol=0.0)),
+                  len(sharded_calls) == 1, np.array_equal(sharded_calls[0], freqs[lo:hi]),
                   full.shape == (7, atm.gas.shape[1]), bool(np.allclose(full, whole, rtol=1e-12, atol=0.0)),   # numpy SIMD tails: last-bit differences per batch shape
                   a.slab.shape == (atm.gas.shape[1], 7)]
         ok = all(checks)

@@ -458,3 +458,23 @@ def test_mixed_precision_pipelines_are_bit_identical(mixed):
     assert np.isnan(ref).any() and (ref == np.float32(2.725)).any() and (ref > 100.0).any()
     with pytest.raises(ValueError):
         eng.set_rt_precision('f16')
+
+
+def test_ray_fields_r4ds_and_doppler():
+    """raypath.compute_ds returns the descriptive fields of the ray like the reference (raypath.py:186-187, 224):
+    r4ds (shell radius per step) and doppler, for Jupiter and for tilted Neptune."""
+    import os
+    from conftest import GOLDEN
+    from radiobear_b200 import raypath
+    from radiobear_b200.atmosphere import Atmosphere
+    g = golden('ray_fields.npz')
+    for name, fn in (('jupiter', 'atm_jupiter.npz'), ('neptune', 'atm_neptune.npz')):
+        atm = Atmosphere.from_npz(os.path.join(GOLDEN, fn), name)
+        assert abs(atm.config.omega_m - float(g['omega_m_' + name])) < 1e-18
+        atm.config.vwlat, atm.config.vwdat = list(g['vwlat_' + name]), list(g['vwdat_' + name])   # config.zonal table
+        for k, b in enumerate(g['b']):
+            ray = raypath.compute_ds(atm, list(b), atm.config.orientation)
+            n = int(g['nseg_' + name][k])
+            assert len(ray.ds) == n == len(ray.r4ds) == len(ray.doppler) == len(ray.layer4ds)
+            assert np.max(np.abs(np.array(ray.r4ds) / g['r4ds_' + name][k, :n] - 1.0)) < 1e-10
+            assert np.max(np.abs(np.array(ray.doppler) - g['doppler_' + name][k, :n])) < 1e-12
