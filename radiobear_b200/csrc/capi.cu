@@ -698,16 +698,20 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full_in, const rb_rt
     // complete -- and queue for copy-out -- at the very end of the launch.  Start in the middle of the ray
     // list instead (the centre row of an image) and wrap around: the cheap tiles are done early and the
     // chunks complete evenly in time.
-    pg.shift = (int)(ntiles / 2);
+    pg.shift = rb_progress_shift(R);
     for (int c = 0; c <= nch; ++c) pg.cut[c] = (int)cut_at(c);
     const unsigned fgroups = (unsigned)(prep.pairs ? (F + kPairFreqs - 1) / kPairFreqs : (F + 7) / 8);
-    // value the counter of a chunk of `len` ray tiles ends at: one count per CTA; compacted launches start the
-    // counters at their deficit so that they end at (len + 4) * fgroups (rt_progress_init_kernel)
-    const unsigned extra = full.compact ? 4u : 0u;
+    // value the counter of a chunk of `len` ray tiles ends at: one count per CTA (len * fgroups); compacted launches
+    // start the counters at their deficit so that they end at kProgressTarget (rt_progress_init_kernel)
     RB_CUDA(ctx, cudaMemsetAsync(p_flags, 0, kMaxProgressChunks * sizeof(unsigned), user));
     // compacted launch: the counters start at their deficits (how many CTAs will report into each chunk is only
     // known on the device)
-    if (full.compact) RB_TRY(rb_launch_progress_init(ctx, full, pg, fgroups));
+    // (and the sky pixels are written before the copy stream may move anything: a chunk without a single hit is
+    // complete from the start)
+    if (full.compact) {
+      RB_TRY(rb_launch_progress_init(ctx, full, pg, fgroups));
+      RB_TRY(rb_launch_fill_miss(ctx, full, (int)F, d_out, d_intW, rd->out_f32));
+    }
     RB_CUDA(ctx, cudaEventRecord(ev[0], user));             // counters are set; the copy stream may start waiting
     RB_CUDA(ctx, cudaStreamWaitEvent(sC, ev[0], 0));
     RB_TRY(rb_launch_integrate(ctx, full, rd, prep, &pg, d_out, d_intW, -1, nullptr, nullptr, nullptr));
@@ -724,7 +728,8 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full_in, const rb_rt
     for (int c = 0; c < nch; ++c) {
       const int64_t p0 = pg.cut[c], p1 = pg.cut[c + 1];      // processing-order tiles of the chunk
       if (p1 <= p0) continue;
-      if (stream_wait_value()((CUstream)sC, (CUdeviceptr)(uintptr_t)(pg.done + c), ((unsigned)(p1 - p0) + extra) * fgroups,
+      const unsigned target = full.compact ? kProgressTarget : (unsigned)(p1 - p0) * fgroups;
+      if (stream_wait_value()((CUstream)sC, (CUdeviceptr)(uintptr_t)(pg.done + c), target,
                               CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
         return rb_fail(ctx, RB_ERR_CUDA, "rt: cuStreamWaitValue32 failed");
       const int64_t m0 = (p0 + pg.shift) % ntiles, len = p1 - p0;

@@ -88,6 +88,21 @@ enum {
 // The rays-major integration kernel prefetches whole 32-segment chunks of the ds slab and of the operand
 // slab without bounds checks (the rows it may over-read are never consumed); both buffers carry this slack.
 constexpr size_t kRtSlackBytes = 128 * 256;
+// Compaction of the rays that hit the planet (ray_compact_kernel): within super-blocks of kSortBlock consecutive rays
+// the list is ordered by projected radius, so that the 32 rays of a tile (= the lanes of a warp of the layer march and
+// of the integration) have nearly the same path: they change phase and finish together.  A tile of the list may then
+// hold rays from anywhere in its super-block(s), and how many tiles of the list touch a copy-out chunk is only known on
+// the device: the chunk counters of a compacted launch start at kProgressTarget minus that number
+// (rt_progress_init_kernel) and the copy stream waits for kProgressTarget.
+constexpr int kSortBlock = 8192;
+constexpr unsigned kProgressTarget = 0x40000000u;
+// The copy-out pipeline starts the integration in the middle of the ray list (see run_rt_pipeline) -- at the first ray
+// tile of a super-block, so that the list of hitting rays can be entered at the same place: the first hit of that
+// super-block (ray_compact_kernel leaves its list position in ncomp[1]).  Plain ray tiles (32 rays) to skip:
+__host__ __device__ inline int rb_progress_shift(long long R) {
+  const long long ntiles = (R + 31) / 32, per = kSortBlock / 32;
+  return (int)(((ntiles / 2) / per) * per);
+}
 // warps (= frequency pairs) per CTA of rt_integrate_pairs_kernel: a CTA is 32 rays x 2 kPairWarps frequencies.
 // The warps of a CTA advance chunk by chunk together (one barrier per 32 segments) although their frequencies reach
 // the table phase and tau_cut at different layers; 4 warps (8 adjacent frequencies, 6 CTAs per SM) wait less for each
@@ -147,6 +162,7 @@ struct RtLaunch {
   int32_t* blkcnt;  // device [ceil(R / 256)]
 };
 int rb_launch_geometry(rb_context* ctx, const RtLaunch& g);
+int rb_launch_fill_miss(rb_context* ctx, const RtLaunch& g, int F, void* out_Tb, double* out_intW, int out_f32);
 int rb_launch_ray_fields(rb_context* ctx, const RtLaunch& g, double* out);
 int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out_ds_raymajor /*[R][L-1] device*/);
 int rb_launch_ds_to_slab(rb_context* ctx, const double* ds_raymajor, int64_t R, int64_t Rpad, int S, const int* nseg,

@@ -153,37 +153,73 @@ __global__ void __launch_bounds__(kEdgeThreads) ray_edge_kernel(const __grid_con
   if (threadIdx.x == 0) g.blkcnt[blockIdx.x] = n;
 }
 
-__global__ void __launch_bounds__(kEdgeThreads) ray_compact_kernel(const __grid_constant__ GeoK g) {
-  __shared__ int s_part[kEdgeThreads / 32];
+// One CTA per super-block of kSortBlock rays: counting sort of its hits by projected radius (256 bins), written at the
+// super-block's offset in the list (the hits of all earlier blocks).  The order of the rays inside one bin is whatever
+// the shared-memory atomics make it; nothing depends on it (every ray is computed on its own, only its lane changes).
+constexpr int kSortThreads = 1024;
+constexpr int kSortBins = 256;
+__global__ void __launch_bounds__(kSortThreads) ray_compact_kernel(const __grid_constant__ GeoK g) {
+  __shared__ int s_part[kSortThreads / 32];
+  __shared__ int s_hist[kSortBins], s_cur[kSortBins];
   __shared__ int s_base;
-  // hits in the blocks before this one
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // hits in the edge blocks (kEdgeThreads rays each) before this super-block
+  const int first_blk = (int)blockIdx.x * (kSortBlock / kEdgeThreads);
   int acc = 0;
-  for (int j = threadIdx.x; j < (int)blockIdx.x; j += kEdgeThreads) acc += g.blkcnt[j];
+  for (int j = tid; j < first_blk; j += kSortThreads) acc += g.blkcnt[j];
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) s_part[warp] = acc;
+  if (tid < kSortBins) { s_hist[tid] = 0; s_cur[tid] = 0; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     int b = 0;
-    for (int w = 0; w < kEdgeThreads / 32; ++w) b += s_part[w];
+    for (int w = 0; w < kSortThreads / 32; ++w) b += s_part[w];
     s_base = b;
+  }
+  const double iq2 = 1.0 / (g.q * g.q);
+  constexpr int kPer = kSortBlock / kSortThreads;
+  int bin[kPer];
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const long long r = (long long)blockIdx.x * kSortBlock + i * kSortThreads + tid;
+    bin[i] = -1;
+    if (r < g.R) {
+      const double z = g.zq[r];
+      if (z == z) {
+        const double bx = g.b[2 * r], by = g.b[2 * r + 1];
+        const double rho2 = fmin(bx * bx + by * by * iq2, 1.0);    // 0 at the disc centre, ~1 at the limb
+        // bins of equal width in mu = sqrt(1 - rho^2): the path geometry changes fastest near the limb
+        bin[i] = min(kSortBins - 1, (int)((1.0 - sqrt(1.0 - rho2)) * kSortBins));
+        atomicAdd(&s_hist[bin[i]], 1);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {                                           // exclusive scan of the 256 bin counts by one warp
+    int carry = 0;
+    for (int c = 0; c < kSortBins; c += 32) {
+      const int v = s_hist[c + lane];
+      int x = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      s_hist[c + lane] = carry + x - v;
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0 && blockIdx.x == gridDim.x - 1) g.ncomp[0] = s_base + carry;
+    // where the copy-out pipeline enters the list: the tile that holds the first hit of the super-block its plain
+    // ray order starts with (rb_progress_shift)
+    if (lane == 0 && (long long)blockIdx.x * kSortBlock == 32LL * rb_progress_shift(g.R)) g.ncomp[1] = s_base >> 5;
   }
   __syncthreads();
   const int base = s_base;
-  __syncthreads();
-  const long long r = (long long)blockIdx.x * kEdgeThreads + threadIdx.x;
-  const double z = (r < g.R) ? g.zq[r] : nan("");
-  const bool hit = (z == z);
-  const unsigned m = __ballot_sync(0xffffffffu, hit);
-  if (lane == 0) s_part[warp] = __popc(m);
-  __syncthreads();
-  int before = 0;
-  for (int w = 0; w < warp; ++w) before += s_part[w];
-  if (hit) g.cidx[base + before + __popc(m & ((1u << lane) - 1u))] = (int)r;
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-    int tot = base;
-    for (int w = 0; w < kEdgeThreads / 32; ++w) tot += s_part[w];
-    *g.ncomp = tot;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    if (bin[i] >= 0) {
+      const long long r = (long long)blockIdx.x * kSortBlock + i * kSortThreads + tid;
+      g.cidx[base + s_hist[bin[i]] + atomicAdd(&s_cur[bin[i]], 1)] = (int)r;
+    }
   }
 }
 
@@ -884,16 +920,17 @@ __device__ __forceinline__ RayTile map_ray_tile(const RtK& k) {
     const int nc = *k.ncomp;
     const unsigned ntile = (unsigned)((nc + 31) >> 5);
     m.dead = m.by >= ntile;
-    unsigned tile = m.by + (k.progress.done ? (ntile >> 1) : 0u);
+    unsigned tile = m.by + (k.progress.done ? (unsigned)k.ncomp[1] : 0u);
     if (tile >= ntile) tile -= ntile;
     m.tile = tile;
     m.t = (long long)tile * 32 + threadIdx.x;
     m.in = !m.dead && m.t < nc;
     m.r = m.in ? k.cidx[m.t] : 0;
     if (!m.dead && k.progress.done) {
-      m.first_r = k.cidx[(long long)tile * 32];
-      const long long last = (long long)tile * 32 + 31;
-      m.last_r = k.cidx[last < nc ? last : nc - 1];
+      // the tile's rays come from anywhere in its super-block(s) of the sorted list: smallest / largest ray index
+      // (all 32 lanes of every warp get here together: blockDim.x == 32)
+      m.first_r = (int)__reduce_min_sync(0xffffffffu, m.in ? (unsigned)m.r : 0x7fffffffu);
+      m.last_r = (int)__reduce_max_sync(0xffffffffu, m.in ? (unsigned)m.r : 0u);
     }
   } else {
     unsigned tile = m.by + (unsigned)k.progress.shift;
@@ -939,9 +976,8 @@ __device__ __forceinline__ void progress_report(const RtK& k, const RayTile& m, 
   }
 }
 
-// Compacted launch, before the integration: done[c] = nominal(c) - (CTAs that will report into chunk c), so that
-// every counter ends at its nominal value (len + 4) * fgroups -- the value the host waits for, known without
-// reading the list back (at most len + 4 tiles of the list touch a chunk of len ray tiles: each spans >= 32 rays).
+// Compacted launch, before the integration: done[c] = kProgressTarget - (CTAs that will report into chunk c), so that
+// every counter ends at kProgressTarget -- the value the host waits for, known without reading the list back.
 __global__ void __launch_bounds__(256) rt_progress_init_kernel(RtProgress pg, const int* __restrict__ cidx,
                                                                const int* __restrict__ ncomp, int ntiles,
                                                                unsigned fgroups) {
@@ -951,17 +987,17 @@ __global__ void __launch_bounds__(256) rt_progress_init_kernel(RtProgress pg, co
   const int nc = *ncomp;
   const int nct = (nc + 31) >> 5;
   for (int tl = threadIdx.x; tl < nct; tl += blockDim.x) {
-    const int first = cidx[(long long)tl * 32];
-    const long long last = (long long)tl * 32 + 31;
-    const int lastr = cidx[last < nc ? last : nc - 1];
+    int first = 0x7fffffff, lastr = 0;
+    for (int e = tl * 32; e < min(nc, tl * 32 + 32); ++e) {
+      const int rr = cidx[e];
+      first = min(first, rr);
+      lastr = max(lastr, rr);
+    }
     unsigned mask = progress_touched(pg, ntiles, first >> 5, lastr >> 5);
     for (; mask; mask &= mask - 1) atomicAdd(&s_cnt[__ffs(mask) - 1], 1u);
   }
   __syncthreads();
-  if ((int)threadIdx.x < pg.nchunks) {
-    const unsigned len = (unsigned)(pg.cut[threadIdx.x + 1] - pg.cut[threadIdx.x]);
-    pg.done[threadIdx.x] = (len + 4u) * fgroups - s_cnt[threadIdx.x] * fgroups;
-  }
+  if ((int)threadIdx.x < pg.nchunks) pg.done[threadIdx.x] = kProgressTarget - s_cnt[threadIdx.x] * fgroups;
 }
 
 // rays that miss the planet see the sky (brightness.py:46-51); compacted launches never visit them
@@ -2065,7 +2101,7 @@ int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
     k.cidx = g.cidx; k.ncomp = g.ncomp; k.zq = g.zq; k.blkcnt = g.blkcnt;
     const unsigned eblocks = (unsigned)((g.R + kEdgeThreads - 1) / kEdgeThreads);
     ray_edge_kernel<<<eblocks, kEdgeThreads, 0, ctx->stream>>>(k);
-    ray_compact_kernel<<<eblocks, kEdgeThreads, 0, ctx->stream>>>(k);
+    ray_compact_kernel<<<(unsigned)((g.R + kSortBlock - 1) / kSortBlock), kSortThreads, 0, ctx->stream>>>(k);
     ctx->launches += 2;
   }
   ray_geometry_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(k);
@@ -2157,6 +2193,14 @@ int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total,
   return RB_OK;
 }
 
+int rb_launch_fill_miss(rb_context* ctx, const RtLaunch& g, int F, void* out_Tb, double* out_intW, int out_f32) {
+  const long long nout = (long long)g.R * F;
+  rt_fill_miss_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, ctx->stream>>>(g.zq, g.R, F, out_Tb, out_intW, out_f32);
+  RB_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
 int rb_launch_progress_init(rb_context* ctx, const RtLaunch& g, const RtProgress& pg, unsigned fgroups) {
   if (!g.compact || !pg.done) return rb_fail(ctx, RB_ERR_INVALID, "rt: progress init needs a compacted launch");
   rt_progress_init_kernel<<<1, 256, 0, ctx->stream>>>(pg, g.cidx, g.ncomp, (int)((g.R + 31) / 32), fgroups);
@@ -2226,11 +2270,10 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
       return RB_OK;
     }
     if (g.compact) {
-      // sky pixels first: the compacted launch never visits them
+      // sky pixels first: the compacted launch never visits them (the copy-out pipeline has filled them already,
+      // before its copy stream was released: rb_launch_fill_miss)
       k.cidx = g.cidx; k.ncomp = g.ncomp;
-      const long long nout = (long long)g.R * k.F;
-      rt_fill_miss_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, ctx->stream>>>(g.zq, g.R, k.F, out_Tb, out_intW, k.out_f32);
-      ctx->launches += 1;
+      if (!progress) RB_TRY(rb_launch_fill_miss(ctx, g, k.F, out_Tb, out_intW, k.out_f32));
     }
     k.exp_tab = ctx->exp_tab;
     if (prep.pairs) {

@@ -34,6 +34,14 @@ def main():
     cfg = atm.config
     n = len(grid)
     pts = np.stack([np.tile(grid, n), np.repeat(grid, n)], axis=1)
+    if os.environ.get('RB_AB_SORT', ''):            # upper bound of what ordering the rays by work would give
+        blk = int(os.environ['RB_AB_SORT'])
+        key = np.hypot(pts[:, 0], pts[:, 1] * (71492.0 / 66854.0))
+        if blk > 1:                                   # sort within blocks of `blk` consecutive rays only
+            order = np.concatenate([s0 + np.argsort(key[s0:s0 + blk], kind='stable') for s0 in range(0, len(pts), blk)])
+        else:
+            order = np.argsort(key, kind='stable')
+        pts = np.ascontiguousarray(pts[order])
     t64 = dict(dtype=torch.float64, device=dev)
     freqs_t = torch.tensor(freqs, **t64)
     T_t = torch.tensor(atm.gas[cfg.C['T']], **t64)
