@@ -701,10 +701,14 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
 // operations in the same order as the sequential kernel, so the same bits.  Optional profile outputs
 // (Brightness.tau / .W / .Tb_lyr, brightness.py:118-120) as in rt_integrate_kernel<1, true, true>.
 constexpr int kDiscThreads = 256;
+constexpr size_t disc_smem_bytes(int L) { return 5 * (size_t)L * sizeof(double); }
 __global__ void __launch_bounds__(kDiscThreads) rt_disc_kernel(const __grid_constant__ RtK k, int profile) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  double* const s_tau = reinterpret_cast<double*>(s_raw);     // [S + 1] tau after step i at index i + 1
-  double* const s_W = s_tau + k.L;                            // [S + 1] W after step i at index i + 1
+  double* const s_tau = reinterpret_cast<double*>(s_raw);     // [L] tau after step i at index i + 1
+  double* const s_W = s_tau + k.L;                            // [L] W after step i at index i + 1
+  double* const s_a = s_W + k.L;                              // [L] this frequency's column of the alpha slab
+  double* const s_h = s_a + k.L;                              // [L] ds_i / 2 in cm
+  double* const s_T = s_h + k.L;                              // [L]
   __shared__ int s_last;                                      // number of steps taken
   const int f = blockIdx.y;
   const long long r = blockIdx.x;
@@ -714,15 +718,22 @@ __global__ void __launch_bounds__(kDiscThreads) rt_disc_kernel(const __grid_cons
   const int nsteps = (n > 0 && !nanray) ? n - 1 : 0;          // brightness.py:65: i = 0 .. len(ds) - 2
   const int cut_hi = __double2hiint(k.tau_cut);
   const double* ds = k.ds + ds_tile_base(r, S);
+  // the operands of the two sequential passes, fetched by all threads (the passes themselves then only touch
+  // shared memory: a thread that walks global memory alone waits an L2 round trip per layer)
+  for (int i = threadIdx.x; i <= nsteps && i < k.L; i += kDiscThreads) {
+    s_a[i] = k.alpha[(size_t)i * k.F + f];
+    s_T[i] = k.T[i];
+    if (i < nsteps) s_h[i] = ds[(size_t)i * kDsStride] * kKmToCm * 0.5;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    double tau = 0.0, a0 = k.alpha[f];
+    double tau = 0.0, a0 = s_a[0];
     int i = 0;
     s_tau[0] = 0.0;
     for (; i < nsteps; ++i) {
       if (!(__double2hiint(tau) < cut_hi)) break;             // the rule of every integration kernel of this file
-      const double a1 = k.alpha[(size_t)(i + 1) * k.F + f];
-      const double h = ds[(size_t)i * kDsStride] * kKmToCm * 0.5;
-      tau = tau + (a0 + a1) * h;
+      const double a1 = s_a[i + 1];
+      tau = tau + (a0 + a1) * s_h[i];
       s_tau[i + 1] = tau;
       a0 = a1;
     }
@@ -730,17 +741,16 @@ __global__ void __launch_bounds__(kDiscThreads) rt_disc_kernel(const __grid_cons
   }
   __syncthreads();
   const int last = s_last;
-  for (int i = threadIdx.x; i < last; i += kDiscThreads)
-    s_W[i + 1] = 2.0 * k.alpha[(size_t)(i + 1) * k.F + f] * expn2(s_tau[i + 1]);
+  for (int i = threadIdx.x; i < last; i += kDiscThreads) s_W[i + 1] = 2.0 * s_a[i + 1] * expn2(s_tau[i + 1]);
   if (threadIdx.x == 0) s_W[0] = 0.0;
   __syncthreads();
   if (threadIdx.x != 0) return;
-  double iW = 0.0, Tb = 0.0, Wp = 0.0, T0 = k.T[0];
+  double iW = 0.0, Tb = 0.0, Wp = 0.0, T0 = s_T[0];
   if (profile && n > 0) { k.out_tau[(size_t)f * S] = 0.0; k.out_W[(size_t)f * S] = 0.0; k.out_Tblyr[(size_t)f * S] = 0.0; }
   for (int i = 0; i < (profile ? nsteps : last); ++i) {
     if (i < last) {
-      const double h = ds[(size_t)i * kDsStride] * kKmToCm * 0.5;
-      const double W = s_W[i + 1], T1 = k.T[i + 1];
+      const double h = s_h[i];
+      const double W = s_W[i + 1], T1 = s_T[i + 1];
       iW += (W + Wp) * h;
       Tb += (T1 * W + T0 * Wp) * h;
       Wp = W;
@@ -2235,18 +2245,20 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
   if (profile_ray >= 0) {
     if (g.R != 1) return rb_fail(ctx, RB_ERR_INVALID, "rt: profile outputs need a single-ray launch");
     dim3 grid(1, fgroups), block(32, 1);
-    if (k.disc && 2 * (size_t)k.L * sizeof(double) <= 48 * 1024)
-      rt_disc_kernel<<<dim3(1, k.F), kDiscThreads, 2 * (size_t)k.L * sizeof(double), ctx->stream>>>(k, 1);
-    else if (k.disc) rt_integrate_kernel<1, true, true><<<grid, block, 0, ctx->stream>>>(k);
+    if (k.disc && disc_smem_bytes(k.L) <= 200 * 1024) {
+      RB_TRY(opt_in_smem(ctx, rt_disc_kernel, 200 * 1024, 3));
+      rt_disc_kernel<<<dim3(1, k.F), kDiscThreads, disc_smem_bytes(k.L), ctx->stream>>>(k, 1);
+    } else if (k.disc) rt_integrate_kernel<1, true, true><<<grid, block, 0, ctx->stream>>>(k);
     else rt_integrate_kernel<1, false, true><<<grid, block, 0, ctx->stream>>>(k);
   } else if (!prep.use_rays) {
     const int wy = 4;
     const long long gx = (g.R + wy - 1) / wy;
     if (gx > 2147483647LL) return rb_fail(ctx, RB_ERR_INVALID, "rt: too many rays for one launch");
     dim3 grid((unsigned)gx, fgroups), block(32, wy);
-    if (k.disc && g.R <= 65535 && 2 * (size_t)k.L * sizeof(double) <= 48 * 1024)
-      rt_disc_kernel<<<dim3((unsigned)g.R, k.F), kDiscThreads, 2 * (size_t)k.L * sizeof(double), ctx->stream>>>(k, 0);
-    else if (k.disc) rt_integrate_kernel<1, true, false><<<grid, block, 0, ctx->stream>>>(k);
+    if (k.disc && g.R <= 65535 && disc_smem_bytes(k.L) <= 200 * 1024) {
+      RB_TRY(opt_in_smem(ctx, rt_disc_kernel, 200 * 1024, 3));
+      rt_disc_kernel<<<dim3((unsigned)g.R, k.F), kDiscThreads, disc_smem_bytes(k.L), ctx->stream>>>(k, 0);
+    } else if (k.disc) rt_integrate_kernel<1, true, false><<<grid, block, 0, ctx->stream>>>(k);
     else rt_integrate_kernel<1, false, false><<<grid, block, 0, ctx->stream>>>(k);
   } else {
     // rays-major mapping: CTAs of 32 rays x 8 (16: pair kernel) frequencies in a 1-D grid, the frequency groups
