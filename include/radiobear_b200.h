@@ -202,6 +202,7 @@ int rb_alpha_fetch(rb_context* ctx, double* out_total, double* out_cube);
 /* ---- ray geometry + radiative transfer (hot path B) ------------------------------------- */
 #define RB_GTYPE_ELLIPSE 0 /* shape.py:223-274 */
 #define RB_GTYPE_SPHERE 1  /* 'circle' / 'sphere' */
+#define RB_GTYPE_GRAVITY 2 /* shape.py:141-221; needs rb_set_gravity_model */
 #define RB_LIMB_SHAPE 0
 #define RB_LIMB_SEC 1      /* raypath.py:218-219 */
 
@@ -214,6 +215,31 @@ typedef struct rb_geometry_desc {
   int32_t gtype;            /* RB_GTYPE_* */
   int32_t limb;             /* RB_LIMB_* */
 } rb_geometry_desc;
+
+/* The 'gravity' shape (Shape._calcGeoid / _gravity, shape.py:141-221): the geoid is marched from the equator in steps of
+ * latstep degrees with the gravity vector of the zonal harmonics Jn, the rotation omega_m and the zonal winds vw(lat);
+ * the shape the ray loop gets is that of the last grid latitude of the march.  The call builds, on the device, the table
+ * of every (layer, grid latitude, hemisphere) the march can return; geometry requests with gtype = RB_GTYPE_GRAVITY
+ * then look it up.  Host pointers, copied.
+ *   radius   [L] equatorial radius of each layer (the profile later passed in rb_geometry_desc.radius)
+ *   GM_layer [L] GM used for the march that starts at radius[l]: np.interp(radius[l], R profile, GM profile) as
+ *                shape.py:156-157 calls it
+ *   vwlat, vwdat [n_vw] zonal wind table (config.vwlat / vwdat, m/s), latitudes ascending */
+typedef struct rb_gravity_model {
+  int32_t n_layers;
+  const double* radius;
+  const double* GM_layer;
+  int32_t n_J;
+  const double* Jn;
+  double RJ;
+  double omega_m;
+  int32_t n_vw;
+  const double* vwlat;
+  const double* vwdat;
+  double latstep;           /* degrees; the reference's default_gravcalc_latstep is 0.01 */
+  double max_lat;           /* degrees covered by the table (<= 90) */
+} rb_gravity_model;
+int rb_set_gravity_model(rb_context* ctx, const rb_gravity_model* model);
 
 /* raypath.compute_ds (raypath.py:108-273) for n_rays impact points b[R][2].
  *   out_ds   : [R][L-1] path length per layer, km (NaN from the tangent depth on, as in the reference)

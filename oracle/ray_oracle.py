@@ -81,6 +81,145 @@ class Ellipse:
         return self.rmag
 
 
+class Geoid:
+    """State of Shape after _calcGeoid (shape.py:141-171) with _gravity (shape.py:173-221): the 'gravity' shape.
+
+    Starts at the equatorial radius r and marches north (or south) in steps of 0.01 deg to the first grid latitude at
+    or beyond pclat; every step evaluates the gravity vector (zonal harmonics Jn, rotation with the zonal winds) and
+    moves along the local tangent.  r, n and rmag are those of the LAST grid latitude (the march is quantised: the
+    latitude the shape is evaluated at is k * latstep, not pclat).  GM is np.interp(r, R profile, GM profile) exactly as
+    the reference calls it (the R profile decreases with index; np.interp is used as is).
+    """
+    latstep0 = 0.01
+
+    def __init__(self, R_profile, GM_profile, Jn, RJ, omega_m, vwlat, vwdat):
+        from scipy.special import eval_legendre      # what scipy.special.legendre(i)(x) evaluates
+        self._P = eval_legendre
+        self.Rp, self.GMp = np.asarray(R_profile, dtype=float), np.asarray(GM_profile, dtype=float)
+        self.Jn, self.RJ, self.omega_m = [float(x) for x in Jn], float(RJ), float(omega_m)
+        self.vwlat, self.vwdat = np.asarray(vwlat, dtype=float), np.asarray(vwdat, dtype=float)
+        self.r = np.zeros(3)
+        self.n = np.zeros(3)
+        self.t = np.zeros(3)
+        self.rmag = 0.0
+        self.gamma = 0.0
+
+    def _gravity(self, pclat, delta_lng, r, GM, omega):
+        P = self._P
+        g_static = GM / r**2
+        lat = _d2r(pclat)
+        lng = _d2r(delta_lng)
+        nsl = 1.0 if lat == 0.0 else np.sign(lat)
+        dphi = nsl * 0.00001
+        Sr = 0.0
+        Sp = 0.0
+        sp = np.sin(lat)
+        sp1 = np.sin(lat + dphi)
+        sp0 = np.sin(lat - dphi)
+        for i in range(len(self.Jn)):
+            Sr += (i + 1.0) * self.Jn[i] * pow(self.RJ / r, i) * P(i, sp)
+            dP = (P(i, sp1) - P(i, sp)) / dphi
+            dP += (P(i, sp) - P(i, sp0)) / dphi
+            dP *= 0.5
+            Sp += self.Jn[i] * pow(self.RJ / r, i) * dP
+        gr = (g_static * (1.0 - Sr) - (2.0 / 3.0) * (omega**2.0) * r * (1.0 - P(2, sp)))
+        dP = (3.0 * sp * np.sqrt(1.0 - sp**2))
+        gp = (1.0 / 3.0) * (omega**2.0) * r * dP + g_static * Sp
+        gamma = np.arctan2(gp, gr)
+        self.n = rotY(lng, np.array([0.0, np.sin(lat + gamma), np.cos(lat + gamma)]))
+        self.t = rotY(lng, np.array([0.0, np.cos(lat + gamma), -np.sin(lat + gamma)]))
+        self.r = rotY(lng, np.array([0.0, r * np.sin(lat), r * np.cos(lat)]))
+        self.rmag = np.linalg.norm(self.r)
+        self.gamma = gamma
+
+    def calc(self, r, pclat, delta_lng):
+        nsp = 1.0 if pclat == 0.0 else np.sign(pclat)
+        latstep = nsp * self.latstep0
+        steps = np.arange(0.0, pclat + latstep, latstep)
+        GM = np.interp(r, self.Rp, self.GMp)
+        for latv in steps:
+            vw = np.interp(latv, self.vwlat, self.vwdat) / 1000.0
+            omega = self.omega_m + vw / (r * np.cos(_d2r(latv)))
+            self._gravity(latv, delta_lng, r, GM, omega)
+            r = np.linalg.norm(self.r + r * _d2r(latstep) * self.t)
+        return self.rmag
+
+
+class GeoidTable(Geoid):
+    """The same 'gravity' shape for every layer at once.  A march of Shape._calcGeoid visits the grid latitudes
+    k * 0.01 deg one after the other and returns the state of the last one, so every shape raypath.compute_ds asks for is
+    an entry (layer, k, hemisphere) of one table; here the march of all layers advances together (numpy over layers,
+    the operations of Geoid._gravity in the same order), which makes a gravity ray affordable for the tests.
+    `calc(r, ...)` takes r = req[layer] (the only radii the ray loop passes)."""
+
+    def __init__(self, R_profile, GM_profile, Jn, RJ, omega_m, vwlat, vwdat, max_abs_lat=90.0):
+        Geoid.__init__(self, R_profile, GM_profile, Jn, RJ, omega_m, vwlat, vwdat)
+        self.layer_of = {float(r): i for i, r in enumerate(self.Rp)}
+        self.K = int(np.ceil((max_abs_lat + self.latstep0) / self.latstep0))
+        self.tab = {}
+        for nsp in (1.0, -1.0):
+            latstep = nsp * self.latstep0
+            r = self.Rp.copy()
+            GM = np.array([np.interp(x, self.Rp, self.GMp) for x in self.Rp])
+            rm = np.empty((self.K, len(r)))
+            gm = np.empty((self.K, len(r)))
+            for k in range(self.K):
+                latv = 0.0 + k * latstep
+                vw = np.interp(latv, self.vwlat, self.vwdat) / 1000.0
+                omega = self.omega_m + vw / (r * np.cos(_d2r(latv)))
+                rm[k] = r
+                gm[k], tvec, rvec = self._gravity_vec(latv, r, GM, omega)
+                r = np.sqrt((rvec[0] + r * _d2r(latstep) * tvec[0])**2 + (rvec[1] + r * _d2r(latstep) * tvec[1])**2)
+            self.tab[nsp] = (rm, gm)
+
+    def _gravity_vec(self, pclat, r, GM, omega):
+        """Geoid._gravity for an array of radii at delta_lng = 0 -> gamma, (t_y, t_z), (r_y, r_z)."""
+        P = self._P
+        g_static = GM / r**2
+        lat = _d2r(pclat)
+        nsl = 1.0 if lat == 0.0 else np.sign(lat)
+        dphi = nsl * 0.00001
+        Sr = 0.0
+        Sp = 0.0
+        sp, sp1, sp0 = np.sin(lat), np.sin(lat + dphi), np.sin(lat - dphi)
+        for i in range(len(self.Jn)):
+            Sr = Sr + (i + 1.0) * self.Jn[i] * (self.RJ / r)**i * P(i, sp)
+            dP = (P(i, sp1) - P(i, sp)) / dphi
+            dP += (P(i, sp) - P(i, sp0)) / dphi
+            dP *= 0.5
+            Sp = Sp + self.Jn[i] * (self.RJ / r)**i * dP
+        gr = (g_static * (1.0 - Sr) - (2.0 / 3.0) * (omega**2.0) * r * (1.0 - P(2, sp)))
+        dP = (3.0 * sp * np.sqrt(1.0 - sp**2))
+        gp = (1.0 / 3.0) * (omega**2.0) * r * dP + g_static * Sp
+        gamma = np.arctan2(gp, gr)
+        return gamma, (np.cos(lat + gamma), -np.sin(lat + gamma)), (r * np.sin(lat), r * np.cos(lat))
+
+    def kindex(self, pclat):
+        """Index of the last grid latitude of the march to pclat: len(np.arange(0, pclat + latstep, latstep)) - 1."""
+        nsp = 1.0 if pclat == 0.0 else float(np.sign(pclat))
+        latstep = nsp * self.latstep0
+        return nsp, int(np.ceil((pclat + latstep) / latstep)) - 1
+
+    def calc(self, r, pclat, delta_lng):
+        if pclat != pclat:
+            # a ray below its tangent shell carries NaN positions; the reference's march raises on np.arange(0, nan, nan)
+            # here, the ellipse path (and the CUDA kernel for both shapes) carries the NaN on
+            self.r = self.n = np.full(3, np.nan)
+            self.rmag = np.nan
+            return self.rmag
+        l = self.layer_of[float(r)]
+        nsp, k = self.kindex(pclat)
+        rm, gm = self.tab[nsp]
+        rk, gamma = rm[k, l], gm[k, l]
+        lat = _d2r(0.0 + k * (nsp * self.latstep0))
+        lng = _d2r(delta_lng)
+        self.n = rotY(lng, np.array([0.0, np.sin(lat + gamma), np.cos(lat + gamma)]))
+        self.r = rotY(lng, np.array([0.0, rk * np.sin(lat), rk * np.cos(lat)]))
+        self.rmag = np.linalg.norm(self.r)
+        self.gamma = gamma
+        return self.rmag
+
+
 def find_edge(b, rNorm, tip, rotate, geoid):
     """raypath.py:60-105."""
     tmp = (b[0]**2 + b[1]**2)
@@ -107,8 +246,9 @@ def find_edge(b, rNorm, tip, rotate, geoid):
     return rNorm * rotate2planet(rotate, tip, bq), bq
 
 
-def compute_ds(req, nr, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape'):
+def compute_ds(req, nr, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', gravity=None):
     """raypath.py:108-273.  req/nr: equatorial radius and refractive index per layer.
+    gtype='gravity': `gravity` = dict(GM=GM profile per layer, Jn, RJ, omega_m, vwlat, vwdat).
 
     Returns dict(ds, layer4ds, r4ds, tip, rotate, rNorm) with ds=None when the ray misses.
     """
@@ -119,7 +259,11 @@ def compute_ds(req, nr, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', l
     mu = np.sqrt(1.0 - b[0]**2 - b[1]**2)
     f = 1.0 - Rpol / Req
     tip, rotate = compute_aspect(orientation, f)
-    geoid = Ellipse(gtype, Req, Rpol)
+    if gtype == 'gravity':
+        geoid = gravity.get('table') or Geoid(req, gravity['GM'], gravity['Jn'], gravity['RJ'], gravity['omega_m'],
+                                              gravity['vwlat'], gravity['vwdat'])
+    else:
+        geoid = Ellipse(gtype, Req, Rpol)
     edge, bq = find_edge(b, rNorm, tip, rotate, geoid)
     if edge is None:
         return out

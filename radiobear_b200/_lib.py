@@ -47,6 +47,12 @@ class GeometryDesc(C.Structure):
                 ('gtype', C.c_int32), ('limb', C.c_int32)]
 
 
+class GravityModel(C.Structure):
+    _fields_ = [('n_layers', C.c_int32), ('radius', C.c_void_p), ('GM_layer', C.c_void_p), ('n_J', C.c_int32),
+                ('Jn', C.c_void_p), ('RJ', C.c_double), ('omega_m', C.c_double), ('n_vw', C.c_int32),
+                ('vwlat', C.c_void_p), ('vwdat', C.c_void_p), ('latstep', C.c_double), ('max_lat', C.c_double)]
+
+
 class RtDesc(C.Structure):
     _fields_ = [('n_freqs', C.c_int32), ('alpha', C.c_void_p), ('T', C.c_void_p),
                 ('disc_average', C.c_int32), ('out_f32', C.c_int32), ('tau_cut', C.c_double)]
@@ -99,6 +105,7 @@ def load():
         'rb_alpha_fetch': (C.c_int, [vp, vp, vp]),
         'rb_rt_batch_resident': (C.c_int, [vp, C.POINTER(GeometryDesc), C.POINTER(RtDesc), i64, vp, vp, vp, i64, vp, vp, vp]),
         'rb_compute_ds': (C.c_int, [vp, C.POINTER(GeometryDesc), i64, vp, vp, vp, vp]),
+        'rb_set_gravity_model': (C.c_int, [vp, C.POINTER(GravityModel)]),
         'rb_compute_ray_fields': (C.c_int, [vp, C.POINTER(GeometryDesc), i64, vp, vp]),
         'rb_rt_batch': (C.c_int, [vp, C.POINTER(GeometryDesc), C.POINTER(RtDesc), i64, vp, vp, vp, i64, vp, vp, vp]),
         'rb_rt_batch_dev': (C.c_int, [vp, C.POINTER(GeometryDesc), C.POINTER(RtDesc), i64, vp, vp, vp]),
@@ -122,7 +129,7 @@ EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error'
                     'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_kernel_timed_count',
                     'rb_set_rt_chunks', 'rb_set_rt_precision', 'rb_get_rt_precision', 'rb_set_rt_tuning', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
                     'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_alpha_layers_resident', 'rb_alpha_rescale_resident',
-                    'rb_alpha_resident_info', 'rb_alpha_fetch', 'rb_rt_batch_resident', 'rb_compute_ds', 'rb_compute_ray_fields', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
+                    'rb_alpha_resident_info', 'rb_alpha_fetch', 'rb_rt_batch_resident', 'rb_compute_ds', 'rb_compute_ray_fields', 'rb_set_gravity_model', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
                     'rb_probe_fp64_peak', 'rb_probe_rcp', 'rb_probe_fp64_mix']
 
 _EXC = {RB_ERR_INVALID: ValueError, RB_ERR_CUDA: RadiobearB200Error, RB_ERR_NOMEM: MemoryError,

@@ -99,6 +99,8 @@ void rb_destroy(rb_context* ctx) {
     for (auto& c : ctx->cat)
       if (c) cudaFree(c);
     if (ctx->exp_tab) cudaFree(ctx->exp_tab);
+    if (ctx->grav.rmag) cudaFree(ctx->grav.rmag);
+    if (ctx->grav.gamma) cudaFree(ctx->grav.gamma);
     if (ctx->step_counter_buf) cudaFree(ctx->step_counter_buf);
     if (ctx->ticket.done) cudaEventDestroy(ctx->ticket.done);
     for (int i = 0; i < 3; ++i)
@@ -405,8 +407,12 @@ static int make_geometry(rb_context* ctx, const rb_geometry_desc* g, int64_t R, 
   if (g->n_layers < 2) return rb_fail(ctx, RB_ERR_INVALID, "geometry: need at least 2 layers");
   if (R <= 0) return rb_fail(ctx, RB_ERR_INVALID, "geometry: n_rays must be positive");
   if (!(g->Req > 0.0) || !(g->Rpol > 0.0)) return rb_fail(ctx, RB_ERR_INVALID, "geometry: Req / Rpol must be positive");
-  if (g->gtype != RB_GTYPE_ELLIPSE && g->gtype != RB_GTYPE_SPHERE)
-    return rb_fail(ctx, RB_ERR_UNSUPPORTED, "geometry: gtype %d not built (ellipse / sphere only)", g->gtype);
+  if (g->gtype != RB_GTYPE_ELLIPSE && g->gtype != RB_GTYPE_SPHERE && g->gtype != RB_GTYPE_GRAVITY)
+    return rb_fail(ctx, RB_ERR_UNSUPPORTED, "geometry: gtype %d not built (ellipse / sphere / gravity only)", g->gtype);
+  if (g->gtype == RB_GTYPE_GRAVITY && (!ctx->grav.rmag || ctx->grav.L != g->n_layers))
+    return rb_fail(ctx, RB_ERR_INVALID, "geometry: gtype 'gravity' needs rb_set_gravity_model for this %d-layer profile",
+                   g->n_layers);
+  out->gtype = g->gtype;
   out->L = g->n_layers;
   out->n0 = g->n0; out->n1 = g->n1;
   out->q = (g->gtype == RB_GTYPE_ELLIPSE) ? g->Rpol / g->Req : 1.0;
@@ -468,7 +474,8 @@ static bool want_compact(const rb_context* ctx, int64_t R) {
   return ctx->rt_compact == 1 && R >= 512 && R < 2000000000LL && ctx->rt_precision == RB_RT_F64;
 }
 static int bind_compact(rb_context* ctx, RtLaunch& L) {
-  L.compact = want_compact(ctx, L.R);
+  L.compact = want_compact(ctx, L.R) && L.gtype != RB_GTYPE_GRAVITY;   // the gravity march walks the plain ray order
+  if (L.gtype == RB_GTYPE_GRAVITY) L.dsf = nullptr;                    // ... and feeds the FP64 integration only
   L.cidx = nullptr; L.ncomp = nullptr; L.zq = nullptr; L.blkcnt = nullptr;
   if (!L.compact) return RB_OK;
   void *p_c, *p_z, *p_k;
@@ -565,6 +572,43 @@ int rb_compute_ds(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const d
   return RB_OK;
 }
 
+int rb_set_gravity_model(rb_context* ctx, const rb_gravity_model* m) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (!m || m->n_layers < 2 || !m->radius || !m->GM_layer || m->n_J < 3 || !m->Jn || m->n_vw < 2 || !m->vwlat || !m->vwdat)
+    return rb_fail(ctx, RB_ERR_INVALID, "gravity model: null pointer / too few entries");
+  if (!(m->latstep > 0.0) || !(m->max_lat > 0.0) || m->max_lat > 90.0 || !(m->RJ > 0.0))
+    return rb_fail(ctx, RB_ERR_INVALID, "gravity model: latstep, max_lat (<= 90) and RJ must be positive");
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int L = m->n_layers;
+  const int K = (int)ceil((m->max_lat + m->latstep) / m->latstep);
+  RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->grav.rmag) { cudaFree(ctx->grav.rmag); ctx->grav.rmag = nullptr; }
+  if (ctx->grav.gamma) { cudaFree(ctx->grav.gamma); ctx->grav.gamma = nullptr; }
+  ctx->grav.L = 0;
+  const size_t nent = 2 * (size_t)K * L;
+  if (cudaMalloc(&ctx->grav.rmag, nent * 8) != cudaSuccess || cudaMalloc(&ctx->grav.gamma, nent * 8) != cudaSuccess) {
+    cudaGetLastError();
+    return rb_fail(ctx, RB_ERR_NOMEM, "gravity model: %zu MB for the shape table", 2 * nent * 8 >> 20);
+  }
+  // inputs: radius | GM | Jn | vwlat | vwdat in one scratch buffer
+  const size_t nin = 2 * (size_t)L + m->n_J + 2 * (size_t)m->n_vw;
+  void* p;
+  RB_TRY(rb_ensure(ctx, RB_BUF_MISC, nin * 8, &p));
+  double* d = (double*)p;
+  double *d_rad = d, *d_GM = d + L, *d_J = d + 2 * L, *d_vl = d_J + m->n_J, *d_vd = d_vl + m->n_vw;
+  cudaStream_t s = ctx->stream;
+  RB_CUDA(ctx, cudaMemcpyAsync(d_rad, m->radius, (size_t)L * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(d_GM, m->GM_layer, (size_t)L * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(d_J, m->Jn, (size_t)m->n_J * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(d_vl, m->vwlat, (size_t)m->n_vw * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(d_vd, m->vwdat, (size_t)m->n_vw * 8, cudaMemcpyHostToDevice, s));
+  ctx->grav.L = L; ctx->grav.K = K; ctx->grav.latstep = m->latstep;
+  ctx->grav.r0 = m->radius[0]; ctx->grav.rlast = m->radius[L - 1];
+  RB_TRY(rb_build_geoid_table(ctx, L, K, m->n_J, m->n_vw, d_rad, d_GM, d_J, d_vl, d_vd, m->RJ, m->omega_m, m->latstep));
+  RB_CUDA(ctx, cudaStreamSynchronize(s));      // the scratch inputs may be reused by the next call
+  return RB_OK;
+}
+
 int rb_compute_ray_fields(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const double* b, double* out_fields) {
   if (!ctx) return RB_ERR_INVALID;
   if (!b || !out_fields || !g || !g->radius) return rb_fail(ctx, RB_ERR_INVALID, "ray_fields: null pointer");
@@ -584,8 +628,12 @@ int rb_compute_ray_fields(rb_context* ctx, const rb_geometry_desc* g, int64_t R,
   RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemsetAsync(p_o, 0, (size_t)R * 3 * S * 8, s));
   L.radius = (const double*)p_rad; L.b = (const double*)p_b; L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
-  RB_TRY(rb_launch_geometry(ctx, L));
-  RB_TRY(rb_launch_ray_fields(ctx, L, (double*)p_o));
+  if (L.gtype == RB_GTYPE_GRAVITY) {
+    RB_TRY(rb_launch_gravity_geometry(ctx, L, (double*)p_o));   // the gravity march knows these fields itself
+  } else {
+    RB_TRY(rb_launch_geometry(ctx, L));
+    RB_TRY(rb_launch_ray_fields(ctx, L, (double*)p_o));
+  }
   RB_CUDA(ctx, cudaMemcpyAsync(out_fields, p_o, (size_t)R * 3 * S * 8, cudaMemcpyDeviceToHost, s));
   RB_CUDA(ctx, cudaStreamSynchronize(s));
   return RB_OK;

@@ -63,6 +63,15 @@ struct rb_context {
     uint64_t slab_gen = 0, cube_gen = 0;   // 0 = nothing resident
     uint64_t counter = 0;
   } res;
+  // 'gravity' geoid (rb_set_gravity_model): the shape table [2 hemispheres][K grid latitudes][L layers] of
+  // (shell radius, gamma) that Shape._calcGeoid's march visits (shape.py:141-221), built once per model
+  struct Gravity {
+    int L = 0, K = 0;
+    double latstep = 0.0;
+    double* rmag = nullptr;   // device [2][K][L]
+    double* gamma = nullptr;  // device [2][K][L]
+    double r0 = 0.0, rlast = 0.0;   // first / last radius the table was built for (checked at launch)
+  } grav;
   double* exp_tab = nullptr;  // 2^(j/1024), j = 0..1023: copied into shared memory by every integration CTA
 };
 
@@ -145,6 +154,7 @@ struct RtLaunch {
   double n0, n1, q;      // q = Rpol/Req (1 for sphere)
   double rot[4];         // cos(tip), sin(tip), cos(rotate), sin(rotate)
   int limb;
+  int gtype;             // RB_GTYPE_*
   // rays
   int64_t R;
   int64_t Rpad;
@@ -162,6 +172,10 @@ struct RtLaunch {
   int32_t* blkcnt;  // device [ceil(R / 256)]
 };
 int rb_launch_geometry(rb_context* ctx, const RtLaunch& g);
+int rb_launch_gravity_geometry(rb_context* ctx, const RtLaunch& g, double* out_fields);
+int rb_build_geoid_table(rb_context* ctx, int L, int K, int nJ, int nvw, const double* d_radius, const double* d_GM,
+                         const double* d_Jn, const double* d_vwlat, const double* d_vwdat, double RJ, double omega_m,
+                         double latstep);
 int rb_launch_fill_miss(rb_context* ctx, const RtLaunch& g, int F, void* out_Tb, double* out_intW, int out_f32);
 int rb_launch_ray_fields(rb_context* ctx, const RtLaunch& g, double* out);
 int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out_ds_raymajor /*[R][L-1] device*/);

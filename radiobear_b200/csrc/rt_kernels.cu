@@ -503,6 +503,213 @@ __global__ void ray_fields_kernel(const __grid_constant__ GeoK g, double* __rest
   }
 }
 
+// ==== 'gravity' shape (Shape._calcGeoid / _gravity, shape.py:141-221) =======================================
+// The reference finds the shell radius at latitude pclat by marching from the equator in steps of 0.01 deg: at
+// every grid latitude it evaluates the gravity vector (zonal harmonics, rotation + zonal wind), takes the local
+// tangent and steps along it; what it returns is the state at the LAST grid latitude (k = len(np.arange(0, pclat +
+// step, step)) - 1), not at pclat.  So every shape the ray loop can ask for is an entry of a table indexed by
+// (hemisphere, k, layer): geoid_table_kernel fills it with one march per (layer, hemisphere) -- the operations of
+// _gravity in their order -- and ray_geometry_gravity_kernel is raypath.compute_ds in the reference's own vector /
+// trigonometric form with table look-ups for Shape.calcShape (the scalar recurrence of ray_geometry_kernel is
+// specific to the ellipse).  Descriptive kernel, not tuned: the reference spends minutes per ray here.
+struct GravK {
+  int L, K, nJ, nvw;
+  const double* radius;   // [L]
+  const double* GM;       // [L]
+  const double* Jn;       // [nJ]
+  const double* vwlat;    // [nvw]
+  const double* vwdat;
+  double RJ, omega_m, latstep;
+  double* rmag;           // [2][K][L]
+  double* gamma;          // [2][K][L]
+};
+
+// np.interp(x, xp, fp) for ascending xp
+__device__ double np_interp(const double* __restrict__ xp, const double* __restrict__ fp, int n, double x) {
+  if (x <= xp[0]) return fp[0];
+  if (x >= xp[n - 1]) return fp[n - 1];
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (xp[mid] <= x) lo = mid; else hi = mid;
+  }
+  const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+  return slope * (x - xp[lo]) + fp[lo];
+}
+
+// Legendre polynomial P_n(x) (scipy.special.legendre(n)(x)) by the three-term recurrence
+__device__ double legendre_p(int n, double x) {
+  if (n == 0) return 1.0;
+  double pm = 1.0, p = x;
+  for (int m = 1; m < n; ++m) {
+    const double pn = ((2.0 * m + 1.0) * x * p - m * pm) / (m + 1.0);
+    pm = p; p = pn;
+  }
+  return p;
+}
+
+__global__ void geoid_table_kernel(const __grid_constant__ GravK g) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hemi = blockIdx.y;                                // 0: north (and the equator), 1: south
+  if (l >= g.L) return;
+  const double kD2R = 3.14159265358979323846 / 180.0;
+  const double latstep = hemi ? -g.latstep : g.latstep;
+  const double dlat = latstep * kD2R;
+  const double GM = g.GM[l];
+  double r = g.radius[l];
+  for (int k = 0; k < g.K; ++k) {
+    const double latv = 0.0 + k * latstep;
+    const double vw = np_interp(g.vwlat, g.vwdat, g.nvw, latv) / 1000.0;
+    const double omega = g.omega_m + vw / (r * cos(latv * kD2R));
+    // ---- _gravity(latv, lng, r, GM, omega) (shape.py:173-221)
+    const double g_static = GM / (r * r);
+    const double lat = latv * kD2R;
+    const double nsl = (lat == 0.0) ? 1.0 : (lat > 0.0 ? 1.0 : -1.0);
+    const double dphi = nsl * 0.00001;
+    const double sp = sin(lat), sp1 = sin(lat + dphi), sp0 = sin(lat - dphi);
+    double Sr = 0.0, Sp = 0.0;
+    for (int i = 0; i < g.nJ; ++i) {
+      const double pw = pow(g.RJ / r, (double)i);
+      const double P = legendre_p(i, sp);
+      Sr += (i + 1.0) * g.Jn[i] * pw * P;
+      double dP = (legendre_p(i, sp1) - P) / dphi;
+      dP += (P - legendre_p(i, sp0)) / dphi;
+      dP *= 0.5;
+      Sp += g.Jn[i] * pw * dP;
+    }
+    const double gr = g_static * (1.0 - Sr) - (2.0 / 3.0) * (omega * omega) * r * (1.0 - legendre_p(2, sp));
+    const double dP2 = 3.0 * sp * sqrt(1.0 - sp * sp);
+    const double gp = (1.0 / 3.0) * (omega * omega) * r * dP2 + g_static * Sp;
+    const double gamma = atan2(gp, gr);
+    const double ry = r * sin(lat), rz = r * cos(lat);
+    const size_t o = ((size_t)hemi * g.K + k) * g.L + l;
+    g.rmag[o] = sqrt(ry * ry + rz * rz);                      // Shape.rmag = |r_vec|
+    g.gamma[o] = gamma;
+    // ---- step along the tangent (shape.py:163-166)
+    const double ty = cos(lat + gamma), tz = -sin(lat + gamma);
+    const double ny = ry + r * dlat * ty, nz = rz + r * dlat * tz;
+    r = sqrt(ny * ny + nz * nz);
+  }
+}
+
+// Shape.calcShape(atm, radius[layer], pclat, dlng) for gtype 'gravity': shell radius, position and normal
+struct GeoidState { double rmag, rx, ry, rz, nx, ny, nz; };
+__device__ GeoidState geoid_lookup(const GravK& g, int layer, double pclat, double dlng) {
+  const double kD2R = 3.14159265358979323846 / 180.0;
+  const double nsp = (pclat == 0.0) ? 1.0 : (pclat > 0.0 ? 1.0 : -1.0);
+  const double latstep = nsp * g.latstep;
+  int k = (int)ceil((pclat + latstep) / latstep) - 1;         // len(np.arange(0, pclat + latstep, latstep)) - 1
+  GeoidState st;
+  if (!(pclat == pclat) || k >= g.K) {                        // NaN latitude (the ray is gone) / beyond the table
+    st.rmag = st.rx = st.ry = st.rz = st.nx = st.ny = st.nz = nan("");
+    return st;
+  }
+  if (k < 0) k = 0;
+  const size_t o = ((size_t)(nsp < 0.0 ? 1 : 0) * g.K + k) * g.L + layer;
+  const double rk = g.rmag[o], gamma = g.gamma[o];
+  const double lat = (0.0 + k * latstep) * kD2R, lng = dlng * kD2R;
+  const double vy = rk * sin(lat), vz = rk * cos(lat);
+  // rotY(lng, [0, vy, vz]) = [sin(lng) vz, vy, cos(lng) vz]   (shape.py:285-290)
+  st.rx = sin(lng) * vz; st.ry = vy; st.rz = cos(lng) * vz;
+  st.rmag = sqrt(st.rx * st.rx + st.ry * st.ry + st.rz * st.rz);
+  const double my = sin(lat + gamma), mz = cos(lat + gamma);
+  st.nx = sin(lng) * mz; st.ny = my; st.nz = cos(lng) * mz;
+  return st;
+}
+
+// raypath.compute_ds (raypath.py:108-273) for the 'gravity' shape, one thread per ray, plain ray order
+__global__ void __launch_bounds__(128) ray_geometry_gravity_kernel(const __grid_constant__ GeoK g, const __grid_constant__ GravK gv,
+                                                                   double* __restrict__ fields) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= g.R) return;
+  const int S = g.L - 1;
+  const double kDeg = 180.0 / 3.14159265358979323846;
+  const double bx = g.b[2 * r], by = g.b[2 * r + 1];
+  const double rNorm = g.radius[0];
+  double* out = g.ds + ds_tile_base(r, S);
+  g.nanflag[r] = 0;
+  g.nseg[r] = -1;
+  const double bb = bx * bx + by * by;
+  if (!(bb < 1.0)) return;
+  const double mu = sqrt(1.0 - bx * bx - by * by);
+  // ---- findEdge (raypath.py:60-105) with the geoid of the outer shell
+  double zq = 0.0;
+  {
+    const double z0 = sqrt(1.0 - bb) * 1.01;
+    const int ntrial = (int)ceil(z0 / 0.005);
+    double d_prev = 0.0, z_prev = 0.0;
+    bool hit = false;
+    for (int t = 0; t < ntrial; ++t) {
+      const double z = z0 + t * (-0.005);
+      double px, py, pz;
+      rot2planet(g, bx, by, z, px, py, pz);
+      const double nb = sqrt(px * px + py * py + pz * pz);
+      const double r1 = nb * rNorm;
+      const GeoidState st = geoid_lookup(gv, 0, asin(py / nb) * kDeg, atan2(px, pz) * kDeg);
+      const double d = r1 - st.rmag;
+      if (r1 < st.rmag) {
+        zq = (t == 0) ? z : ((z_prev - z) / (d_prev - d)) * (0.0 - d) + z;
+        hit = true;
+        break;
+      }
+      d_prev = d; z_prev = z;
+    }
+    if (!hit) return;
+  }
+  double ex, ey, ez;
+  rot2planet(g, bx, by, zq, ex, ey, ez);
+  ex *= rNorm; ey *= rNorm; ez *= rNorm;
+  double pclat = asin(ey / sqrt(ex * ex + ey * ey + ez * ez)) * kDeg;
+  double dlng = atan2(ex, ez) * kDeg;
+  GeoidState st = geoid_lookup(gv, 0, pclat, dlng);
+  double px = st.rx, py = st.ry, pz = st.rz;                  // r[0] = geoid.r
+  double sx, sy, sz;
+  rot2planet(g, 0.0, 0.0, -1.0, sx, sy, sz);
+  double t_inc = acos(-(sx * st.nx + sy * st.ny + sz * st.nz));
+  double nratio = g.n0 / g.n1;
+  double t_tran = asin(nratio * sin(t_inc));
+  int layer = 0, count = 0;
+  while (true) {
+    const double w = nratio * cos(t_inc) - cos(t_tran);       // s += ... n  (raypath.py:179-180)
+    sx = nratio * sx + w * st.nx; sy = nratio * sy + w * st.ny; sz = nratio * sz + w * st.nz;
+    const double rNow = st.rmag;
+    const GeoidState nx_ = geoid_lookup(gv, layer + 1, pclat, dlng);
+    const double rNext = nx_.rmag;
+    const double rdots = px * sx + py * sy + pz * sz;
+    double ds = -rdots - sqrt(rdots * rdots + rNext * rNext - rNow * rNow);
+    if (ds < 0.0) break;                                      // raypath.py:212-216
+    if (g.limb == RB_LIMB_SEC) ds = fabs(rNext - rNow) / mu;  // raypath.py:218-219
+    out[(size_t)layer * kDsStride] = ds;
+    if (fields) {
+      double* f = fields + (size_t)r * 3 * S;
+      f[layer] = rNow; f[S + layer] = pclat; f[2 * S + layer] = dlng;
+    }
+    ++count;
+    if (ds != ds) {
+      // below the tangent shell every later segment is NaN (the reference's march raises on the NaN latitude here;
+      // the ellipse path carries the NaN on, and so does this one)
+      for (++layer; layer < S; ++layer) out[(size_t)layer * kDsStride] = ds;
+      count = S;
+      break;
+    }
+    px = fma(ds, sx, px); py = fma(ds, sy, py); pz = fma(ds, sz, pz);
+    const double nr = sqrt(px * px + py * py + pz * pz);
+    pclat = asin(py / nr) * kDeg;
+    dlng = atan2(px, pz) * kDeg;
+    st = geoid_lookup(gv, layer + 1, pclat, dlng);
+    ++layer;
+    t_inc = acos(-(sx * st.nx + sy * st.ny + sz * st.nz));
+    if (layer + 1 >= g.L) break;                              // raypath.py:255-264 (IndexError exit)
+    nratio = 1.0;                                             // raypath.py:257
+    t_tran = asin(nratio * sin(t_inc));
+  }
+  g.nseg[r] = count;
+  if (count >= 2) {
+    const double last_used = out[(size_t)(count - 2) * kDsStride];
+    if (last_used != last_used) g.nanflag[r] = 1;
+  }
+}
+
 // [S][Rpad] slab -> [R][S] ray-major (only for the compute_ds API that returns Ray.ds)
 __global__ void ds_transpose_kernel(const double* __restrict__ slab, long long R, long long Rpad, int S,
                                     const int* __restrict__ nseg, double* __restrict__ out) {
@@ -2093,6 +2300,7 @@ __global__ void __launch_bounds__(256, RB_RTM_CTAS) rt_integrate_rays_mixed_kern
 }  // namespace
 
 int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
+  if (g.gtype == RB_GTYPE_GRAVITY) return rb_launch_gravity_geometry(ctx, g, nullptr);
   GeoK k{};
   k.L = g.L; k.radius = g.radius; k.n0 = g.n0; k.n1 = g.n1; k.q = g.q;
   k.cz = g.rot[0]; k.sz = g.rot[1]; k.cx = g.rot[2]; k.sx = g.rot[3];
@@ -2200,6 +2408,40 @@ int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total,
   RB_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
   out->prep = scratch;
+  return RB_OK;
+}
+
+static GravK grav_of(const rb_context* ctx) {
+  GravK v{};
+  v.L = ctx->grav.L; v.K = ctx->grav.K; v.latstep = ctx->grav.latstep;
+  v.rmag = ctx->grav.rmag; v.gamma = ctx->grav.gamma;
+  return v;
+}
+
+int rb_build_geoid_table(rb_context* ctx, int L, int K, int nJ, int nvw, const double* d_radius, const double* d_GM,
+                         const double* d_Jn, const double* d_vwlat, const double* d_vwdat, double RJ, double omega_m,
+                         double latstep) {
+  GravK v = grav_of(ctx);
+  v.L = L; v.K = K; v.nJ = nJ; v.nvw = nvw; v.radius = d_radius; v.GM = d_GM; v.Jn = d_Jn; v.vwlat = d_vwlat; v.vwdat = d_vwdat;
+  v.RJ = RJ; v.omega_m = omega_m; v.latstep = latstep;
+  geoid_table_kernel<<<dim3((L + 63) / 64, 2), 64, 0, ctx->stream>>>(v);
+  RB_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+int rb_launch_gravity_geometry(rb_context* ctx, const RtLaunch& g, double* out_fields) {
+  if (!ctx->grav.rmag || ctx->grav.L != g.L)
+    return rb_fail(ctx, RB_ERR_INVALID, "geometry: gtype 'gravity' needs rb_set_gravity_model for this %d-layer profile", g.L);
+  GeoK k{};
+  k.L = g.L; k.radius = g.radius; k.n0 = g.n0; k.n1 = g.n1; k.q = g.q;
+  k.cz = g.rot[0]; k.sz = g.rot[1]; k.cx = g.rot[2]; k.sx = g.rot[3];
+  k.limb = g.limb; k.R = g.R; k.Rpad = g.Rpad; k.b = g.b; k.ds = g.ds; k.nseg = g.nseg; k.nanflag = g.nanflag;
+  RB_CUDA(ctx, rb_time_begin(ctx, 1));
+  ray_geometry_gravity_kernel<<<(unsigned)((g.R + 127) / 128), 128, 0, ctx->stream>>>(k, grav_of(ctx), out_fields);
+  RB_CUDA(ctx, cudaGetLastError());
+  RB_CUDA(ctx, rb_time_end(ctx, 1));
+  ctx->launches += 1;
   return RB_OK;
 }
 

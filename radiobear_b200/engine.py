@@ -286,11 +286,41 @@ def alpha_scale_sum(cube, scale_mat=None, want_cube=False, ctx=None):
     return (total, scaled) if want_cube else total
 
 
-GTYPE = {'ellipse': 0, 'circle': 1, 'sphere': 1}
+GTYPE = {'ellipse': 0, 'circle': 1, 'sphere': 1, 'gravity': 2}
+_gravity_key = {}      # context handle -> digest of the gravity model whose shape table is on the device
+
+
+def set_gravity_model(radius, GM_profile, Jn, RJ, omega_m, vwlat, vwdat, latstep=0.01, max_lat=90.0, ctx=None):
+    """The 'gravity' shape (Shape._calcGeoid, shape.py:141-221) for a radius / GM profile: builds the table of every
+    shape the geoid march can return on the device (once per model: a digest of the inputs is remembered)."""
+    import hashlib
+    ctx = ctx or _lib.get_context()
+    radius, GMp = f64(radius), f64(GM_profile)
+    Jn, vwlat, vwdat = f64(np.atleast_1d(Jn)), f64(np.atleast_1d(vwlat)), f64(np.atleast_1d(vwdat))
+    h = hashlib.sha1()
+    for a in (radius, GMp, Jn, vwlat, vwdat, np.array([RJ, omega_m, latstep, max_lat], dtype=np.float64)):
+        h.update(a.tobytes())
+    if _gravity_key.get(ctx.h.value) == h.digest():
+        return
+    # GM of the march that starts at radius[l]: np.interp exactly as shape.py:156-157 calls it (the radius profile
+    # decreases with the index; the reference passes it to np.interp as it is)
+    GM_layer = f64(np.array([np.interp(r, radius, GMp) for r in radius]))
+    m = _lib.GravityModel()
+    m.n_layers, m.radius, m.GM_layer = len(radius), ptr(radius), ptr(GM_layer)
+    m.n_J, m.Jn, m.RJ, m.omega_m = len(Jn), ptr(Jn), float(RJ), float(omega_m)
+    m.n_vw, m.vwlat, m.vwdat = len(vwlat), ptr(vwlat), ptr(vwdat)
+    m.latstep, m.max_lat = float(latstep), float(max_lat)
+    ctx.use_own_stream()
+    ctx.check(ctx.lib.rb_set_gravity_model(ctx.h, C.byref(m)))
+    _gravity_key[ctx.h.value] = h.digest()
 LIMB = {'shape': 0, 'sec': 1}
 
 
-def build_geometry_desc(L, n0, n1, Req, Rpol, orientation, gtype, limb):
+def build_geometry_desc(L, n0, n1, Req, Rpol, orientation, gtype, limb, gravity_model=None, radius=None):
+    if gtype == 'gravity':
+        if gravity_model is None:
+            raise ValueError("gtype 'gravity' needs the gravity model of the planet (GM profile, Jn, RJ, omega_m, zonal winds)")
+        set_gravity_model(radius, **gravity_model)
     if gtype not in GTYPE:
         raise NotImplementedError("gtype '{}' is not built (ellipse / circle / sphere only)".format(gtype))
     g = GeometryDesc()
@@ -303,14 +333,14 @@ def build_geometry_desc(L, n0, n1, Req, Rpol, orientation, gtype, limb):
     return g
 
 
-def compute_ds(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None):
+def compute_ds(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None, gravity_model=None):
     """raypath.compute_ds for a batch of impact points.  Returns ds[R][L-1], nseg[R], (tip, rotate, rNorm)."""
     ctx = ctx or _lib.get_context()
     ctx.use_own_stream()
     radius = f64(radius)
     b = f64(np.atleast_2d(b))
     R, L = b.shape[0], radius.shape[0]
-    g = build_geometry_desc(L, refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb)
+    g = build_geometry_desc(L, refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb, gravity_model, radius)
     g.radius = ptr(radius)
     ds = np.empty((R, L - 1))
     nseg = np.empty(R, dtype=np.int32)
@@ -319,7 +349,7 @@ def compute_ds(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='
     return ds, nseg, aspect
 
 
-def compute_ray_fields(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None):
+def compute_ray_fields(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None, gravity_model=None):
     """Per step of every ray: Ray.r4ds (km) and the planetocentric latitude / longitude (deg) of the point the step starts
     at (raypath.py:186-187, 224).  Returns fields[R][3][L-1]."""
     ctx = ctx or _lib.get_context()
@@ -327,7 +357,7 @@ def compute_ray_fields(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0),
     radius = f64(radius)
     b = f64(np.atleast_2d(b))
     R, L = b.shape[0], radius.shape[0]
-    g = build_geometry_desc(L, refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb)
+    g = build_geometry_desc(L, refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb, gravity_model, radius)
     g.radius = ptr(radius)
     out = np.empty((R, 3, L - 1))
     ctx.check(ctx.lib.rb_compute_ray_fields(ctx.h, C.byref(g), R, ptr(b), ptr(out)))
@@ -341,7 +371,7 @@ def compute_ray_fields(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0),
 TAU_CUT = 50.0
 
 
-def geometry_prefetch(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None):
+def geometry_prefetch(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None, gravity_model=None):
     """Start the ray geometry of the next rt_batch(b=<the same array>, same geometry) now so that it overlaps
     the absorption kernel (rb_geometry_prefetch).  `radius` and `b` must be the very arrays (same memory) later
     given to rt_batch and must stay unchanged until then; returns the (radius, b) pair to pass on."""
@@ -349,24 +379,27 @@ def geometry_prefetch(radius, refr_index, b, Req, Rpol, orientation=(0.0, 0.0), 
     ctx.use_own_stream()
     radius = f64(radius)
     b = f64(np.atleast_2d(b))
-    g = build_geometry_desc(radius.shape[0], refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb)
+    g = build_geometry_desc(radius.shape[0], refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb, gravity_model,
+                            radius)
     g.radius = ptr(radius)
     ctx.check(ctx.lib.rb_geometry_prefetch(ctx.h, C.byref(g), b.shape[0], ptr(b)))
     return radius, b
 
 
-def geometry_prefetch_dev(radius_t, n0, n1, b_t, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None):
+def geometry_prefetch_dev(radius_t, n0, n1, b_t, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape', ctx=None, gravity_model=None):
     """Device-resident variant of geometry_prefetch (torch CUDA tensors; pairs with rt_batch_dev)."""
     import torch
     ctx = ctx or _lib.get_context()
-    g = build_geometry_desc(radius_t.shape[0], n0, n1, Req, Rpol, orientation, gtype, limb)
+    g = build_geometry_desc(radius_t.shape[0], n0, n1, Req, Rpol, orientation, gtype, limb, gravity_model,
+                            radius_t.cpu().numpy() if gtype == 'gravity' else None)
     g.radius = radius_t.data_ptr()
     ctx.set_stream(torch.cuda.current_stream(b_t.device).cuda_stream)
     ctx.check(ctx.lib.rb_geometry_prefetch_dev(ctx.h, C.byref(g), b_t.shape[0], b_t.data_ptr()))
 
 
 def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape',
-             disc_average=False, out_f32=False, tau_cut=TAU_CUT, want_intW=False, profile_ray=-1, ctx=None, out=None):
+             disc_average=False, out_f32=False, tau_cut=TAU_CUT, want_intW=False, profile_ray=-1, ctx=None, out=None,
+             gravity_model=None):
     """Brightness.single over a batch of rays: Tb[R][F] (+ integrated_W, + profiles of one ray)."""
     resident = isinstance(alpha_slab, ResidentSlab)
     ctx = ctx or (alpha_slab.ctx if resident else _lib.get_context())
@@ -381,7 +414,7 @@ def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 
     R, L, F = b.shape[0], radius.shape[0], alpha_slab.shape[1]
     if alpha_slab.shape[0] != L or T.shape[0] != L:
         raise ValueError('alpha slab must be [L][F] with L = number of layers')
-    g = build_geometry_desc(L, refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb)
+    g = build_geometry_desc(L, refr_index[0], refr_index[1], Req, Rpol, orientation, gtype, limb, gravity_model, radius)
     g.radius = ptr(radius)
     rt = RtDesc()
     rt.n_freqs, rt.alpha, rt.T = F, (None if resident else ptr(alpha_slab)), ptr(T)
@@ -406,12 +439,13 @@ def rt_batch(radius, refr_index, b, alpha_slab, T, Req, Rpol, orientation=(0.0, 
 
 
 def rt_batch_dev(radius_t, n0, n1, b_t, alpha_t, T_t, Req, Rpol, orientation=(0.0, 0.0), gtype='ellipse', limb='shape',
-                 disc_average=False, out_f32=True, tau_cut=TAU_CUT, ctx=None, out=None):
+                 disc_average=False, out_f32=True, tau_cut=TAU_CUT, ctx=None, out=None, gravity_model=None):
     """Device-resident variant (torch CUDA tensors, async on the current stream)."""
     import torch
     ctx = ctx or _lib.get_context()
     R, L, F = b_t.shape[0], radius_t.shape[0], alpha_t.shape[1]
-    g = build_geometry_desc(L, n0, n1, Req, Rpol, orientation, gtype, limb)
+    g = build_geometry_desc(L, n0, n1, Req, Rpol, orientation, gtype, limb, gravity_model,
+                            radius_t.cpu().numpy() if gtype == 'gravity' else None)
     g.radius = radius_t.data_ptr()
     rt = RtDesc()
     rt.n_freqs, rt.alpha, rt.T = F, alpha_t.data_ptr(), T_t.data_ptr()

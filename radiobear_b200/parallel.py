@@ -429,10 +429,9 @@ def run_points_sharded(planet, pts, atm, alpha, out_f32=True, rows=None):
         # page-locked result image
         full = ex.begin(parts[-1][1], (F,), np.float32 if out_f32 else np.float64, pin=True)
         if e > s:
-            engine.rt_batch(radius=atm.property[cfg.LP['R']], refr_index=nidx_of(atm), b=np.asarray(pts[s:e], dtype=np.float64),
-                            alpha_slab=alpha.rt_slab(), T=atm.gas[cfg.C['T']], Req=cfg.Req, Rpol=cfg.Rpol,
-                            orientation=[float(cfg.orientation[0]), float(cfg.orientation[1])], gtype=cfg.gtype,
-                            limb=getattr(cfg, 'limb', 'shape'), out_f32=out_f32, out=full[s:e])
+            from . import raypath
+            engine.rt_batch(b=np.asarray(pts[s:e], dtype=np.float64), alpha_slab=alpha.rt_slab(), T=atm.gas[cfg.C['T']],
+                            out_f32=out_f32, out=full[s:e], **raypath._geometry_args(atm, cfg.orientation, None))
         return ex.finish()
     radius = torch.as_tensor(np.ascontiguousarray(atm.property[cfg.LP['R']]), device=dev)
     nidx = atm.property[cfg.LP['N']]
@@ -440,9 +439,11 @@ def run_points_sharded(planet, pts, atm, alpha, out_f32=True, rows=None):
     slab_t = torch.as_tensor(np.ascontiguousarray(alpha.slab), device=dev)
     if e > s:
         b_t = torch.as_tensor(np.array(pts[s:e], dtype=np.float64), device=dev)      # private writable copy
+        from . import raypath
         local = engine.rt_batch_dev(radius, nidx[0], nidx[1], b_t, slab_t, T_t, cfg.Req, cfg.Rpol,
                                     [float(cfg.orientation[0]), float(cfg.orientation[1])], cfg.gtype,
-                                    getattr(cfg, 'limb', 'shape'), out_f32=out_f32)
+                                    getattr(cfg, 'limb', 'shape'), out_f32=out_f32,
+                                    gravity_model=raypath._geometry_args(atm, cfg.orientation, None).get('gravity_model'))
     else:
         local = torch.empty((0, F), dtype=torch.float32 if out_f32 else torch.float64, device=dev)
     # several nodes / no shared memory: gather over NCCL, rank 0 copies to pinned host memory

@@ -39,9 +39,14 @@ def _geometry_args(atm, orientation, gtype):
         gtype = cfg.gtype
     if orientation is None:
         orientation = cfg.orientation
-    return dict(radius=atm.property[LP['R']], refr_index=atm.property[LP['N']], Req=cfg.Req, Rpol=cfg.Rpol,
+    args = dict(radius=atm.property[LP['R']], refr_index=atm.property[LP['N']], Req=cfg.Req, Rpol=cfg.Rpol,
                 orientation=[float(orientation[0]), float(orientation[1])], gtype=gtype,
                 limb=getattr(cfg, 'limb', 'shape'))
+    if gtype == 'gravity':
+        # what Shape._calcGeoid / _gravity read from the planet (shape.py:141-221)
+        args['gravity_model'] = dict(GM_profile=atm.property[LP['GM']], Jn=cfg.Jn, RJ=cfg.RJ, omega_m=cfg.omega_m,
+                                     vwlat=cfg.vwlat, vwdat=cfg.vwdat)
+    return args
 
 
 def compute_ds_batch(atm, b, orientation=None, gtype=None):

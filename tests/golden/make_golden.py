@@ -8,7 +8,7 @@ scratch work directory bootstrapped the way scripts/initial_planet_setup.py:12-3
 
     python tests/golden/make_golden.py [section ...]
 
-sections: atm fileio plugins plugins_nh3_extra plugins_nh3_full plugins_notrunc alpha rays ray_fields tb neptune uranus image
+sections: atm fileio plugins plugins_nh3_extra plugins_nh3_full plugins_notrunc alpha rays ray_fields gravity tb neptune uranus image
           image_full ring c3_full c5_saturn   (default: all; the last four take ~10 min each on 8 cores)
 
 Every array is float64 exactly as the reference produced it; nothing is post-processed.
@@ -379,6 +379,51 @@ def sec_ray_fields():
     save('ray_fields.npz', b=np.array(blist), **out)
 
 
+def _w_gravity_ray(b):
+    import radiobear as rb
+    j = _W.get('jg') or planet('jupiter')
+    _W['jg'] = j
+    ray = _quiet(rb.raypath.compute_ds, j.atmos[0], list(b), j.config.orientation, gtype='gravity')
+    return np.array(ray.ds), np.array(ray.r4ds)
+
+
+def sec_gravity():
+    """gtype='gravity' (Shape._calcGeoid / _gravity, shape.py:141-221).  The reference builds a scipy orthopoly1d object
+    for every Legendre evaluation and marches 0.01 deg at a time, so a mid-latitude ray costs hours; pinned here are
+    (a) the shape itself -- rmag, gamma, r, n of calcShape at latitudes up to 0.3 deg (30 march steps) on three layers
+    -- and (b) two complete rays close to the equatorial plane (a few march steps per shape)."""
+    import radiobear as rb
+    j = planet('jupiter')
+    atm = j.atmos[0]
+    req = atm.property[atm.config.LP['R']]
+    geoid = rb.shape.Shape('gravity')
+    lats = [0.0, 0.004, 0.01, 0.0100001, 0.05, -0.03, 0.2, -0.25, 0.3]
+    layers = [0, 300, 999]
+    rows = []
+    for l in layers:
+        for lat in lats:
+            rmag = _quiet(geoid.calcShape, atm, req[l], lat, 17.0)
+            rows.append([l, lat, rmag, geoid.gamma] + list(geoid.r) + list(geoid.n))
+    blist = [[0.3, 0.001], [-0.6, 0.002]]
+    with _pool(len(blist), _w_gravity_init, None) as pool:
+        res = pool.map(_w_gravity_ray, blist)
+    S = len(req) - 1
+    ds = np.full((len(blist), S), -2.0)
+    r4 = np.zeros((len(blist), S))
+    nn = []
+    for k, (d, r) in enumerate(res):
+        ds[k, :len(d)] = d
+        r4[k, :len(r)] = r
+        nn.append(len(d))
+    save('gravity.npz', shape_rows=np.array(rows), shape_dlng=17.0, b=np.array(blist), ds=ds, r4ds=r4, nseg=np.array(nn),
+         Jn=np.array(j.config.Jn, dtype=float), RJ=j.config.RJ, omega_m=j.config.omega_m,
+         vwlat=np.array(j.config.vwlat, dtype=float), vwdat=np.array(j.config.vwdat, dtype=float))
+
+
+def _w_gravity_init(_):
+    _W.clear()
+
+
 def sec_tb():
     """End-to-end Tb: the reference's own known-answer case (scripts/benchmark.py:10-24), the Jupiter
     default disc spectrum '1:100:5' (config C1), point rays and a limb profile (config C3 subset)."""
@@ -655,7 +700,7 @@ def sec_fileio():
 
 
 SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins_nh3_full': sec_plugins_nh3_full, 'plugins_h2_orton': sec_plugins_h2_orton, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
-            'rays': sec_rays, 'ray_fields': sec_ray_fields, 'tb': sec_tb, 'neptune': sec_neptune, 'uranus': sec_uranus, 'image': sec_image,
+            'rays': sec_rays, 'ray_fields': sec_ray_fields, 'gravity': sec_gravity, 'tb': sec_tb, 'neptune': sec_neptune, 'uranus': sec_uranus, 'image': sec_image,
             'image_full': sec_image_full, 'ring': sec_ring, 'c3_full': sec_c3_full, 'c5_saturn': sec_c5_saturn}
 
 if __name__ == '__main__':

@@ -70,3 +70,31 @@ def test_neptune_c2_run():
     rv = p.run(list(n['freqs']), b='disc')
     assert np.max(np.abs(np.asarray(p.Tb) - n['tb'])) < 1e-4
     assert p.alpha[0].ordered_constituents == [str(x) for x in n['ordered_constituents']]
+
+
+def test_planet_run_with_the_gravity_shape():
+    """config gtype = 'gravity' through the executive: Planet.run and raypath.compute_ds take the geoid of
+    shape.py:141-221 (its model read from the planet's config: Jn, RJ, omega_m, GM profile, zonal winds); an image
+    request (>= 512 rays, prefetched geometry) gives the same pixels as a list of points; Brightness.single works."""
+    from radiobear_b200 import raypath
+    j = make_planet('jupiter', 'atm_jupiter.npz')
+    e = make_planet('jupiter', 'atm_jupiter.npz')
+    j.config.gtype = 'gravity'
+    pts = [[0.0, 0.0], [0.3, 0.2], [0.6, -0.4]]
+    rg = j.run([2.0, 10.0, 30.0], b=pts, reuse_override='false')
+    re_ = e.run([2.0, 10.0, 30.0], b=pts, reuse_override='false')
+    assert rg.header['gtype'] == '# gtype: gravity' and rg.Tb.shape == (3, 3) and np.isfinite(rg.Tb).all()
+    tb_g = np.array(rg.Tb, dtype=float)                              # (Planet.run hands out the same Data object every call)
+    d = np.abs(tb_g - np.asarray(re_.Tb, dtype=float))
+    assert 1e-4 < d[1:].max() < 5.0                                  # another shape: close, not equal
+    ray = raypath.compute_ds(j.atmos[0], pts[1], j.config.orientation)
+    ell = raypath.compute_ds(e.atmos[0], pts[1], e.config.orientation)
+    assert len(ray.ds) == len(ell.ds) == len(ray.r4ds) and abs(ray.r4ds[0] - ell.r4ds[0]) > 1.0
+    img = np.array(j.run([10.0], b=0.05, reuse_override='false').Tb)  # 61 x 61 image through the batched path
+    grid = np.array(j.b).reshape(61, 61, 2)
+    pick = [(30, 30), (36, 34), (22, 42), (2, 2)]
+    one = j.run([10.0], b=[list(grid[iy, ix]) for iy, ix in pick], reuse_override='false')
+    assert np.allclose([img[iy, ix] for iy, ix in pick], np.asarray(one.Tb)[:, 0], rtol=0, atol=1e-4)
+    assert img[2, 2] == np.float32(2.725)
+    tb1 = j.bright.single(pts[1], [10.0], j.atmos[0], j.alpha[0], j.config.orientation)
+    assert abs(tb1[0] - tb_g[1, 1]) < 1e-3 and j.bright.travel.r4ds is not None

@@ -78,7 +78,9 @@ def test_compute_ds_secant_and_sphere(eng):
     for i in range(6):
         o = ro.compute_ds(ga['radius'], ga['refr_index'], g['b'][i], ga['Req'], ga['Rpol'], ga['orientation'], 'sphere')
         assert nseg[i] == len(o['ds']) and np.max(relerr(ds[i], o['ds'])) < 1e-8
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):                 # shape.py:107 calls a name-mangled method: broken upstream
+        eng.compute_ds(b=g['b'][:1], **dict(geom(a), gtype='reference'))
+    with pytest.raises(ValueError):                           # 'gravity' without the planet's gravity model
         eng.compute_ds(b=g['b'][:1], **dict(geom(a), gtype='gravity'))
 
 
@@ -478,3 +480,73 @@ def test_ray_fields_r4ds_and_doppler():
             assert len(ray.ds) == n == len(ray.r4ds) == len(ray.doppler) == len(ray.layer4ds)
             assert np.max(np.abs(np.array(ray.r4ds) / g['r4ds_' + name][k, :n] - 1.0)) < 1e-10
             assert np.max(np.abs(np.array(ray.doppler) - g['doppler_' + name][k, :n])) < 1e-12
+
+
+def _gravity_setup(name, fn):
+    import os
+    from conftest import GOLDEN
+    from radiobear_b200.atmosphere import Atmosphere
+    from oracle import ray_oracle as ro
+    g = golden('ray_fields.npz')
+    atm = Atmosphere.from_npz(os.path.join(GOLDEN, fn), name)
+    atm.config.vwlat, atm.config.vwdat = list(g['vwlat_' + name]), list(g['vwdat_' + name])   # config.zonal table
+    cfg = atm.config
+    req, GM = atm.property[cfg.LP['R']], atm.property[cfg.LP['GM']]
+    tab = ro.GeoidTable(req, GM, cfg.Jn, cfg.RJ, cfg.omega_m, cfg.vwlat, cfg.vwdat, max_abs_lat=60.0)
+    return atm, tab
+
+
+@pytest.mark.parametrize('name,fn', [('jupiter', 'atm_jupiter.npz'), ('neptune', 'atm_neptune.npz')])
+def test_gravity_geoid_rays_vs_oracle(eng, name, fn):
+    """gtype='gravity' (Shape._calcGeoid / _gravity, shape.py:141-221): the device's shape table + vector ray march
+    against the oracle's restatement -- path lengths, segment counts, the NaN tail of a limb ray, Ray.r4ds -- and Tb
+    through the integration.  (tests/test_oracle_golden.py pins the oracle to rays the reference itself computed.)"""
+    from radiobear_b200 import raypath
+    from oracle import ray_oracle as ro
+    atm, tab = _gravity_setup(name, fn)
+    cfg = atm.config
+    req, nr = atm.property[cfg.LP['R']], atm.property[cfg.LP['N']]
+    S = len(req) - 1
+    pts = [[0.0, 0.0], [0.3, 0.2], [0.6, -0.4], [-0.85, 0.3], [0.2, 0.7], [0.99, 0.05], [1.2, 0.1]]
+    args = raypath._geometry_args(atm, cfg.orientation, 'gravity')
+    ds, nseg, aspect = eng.compute_ds(b=np.array(pts), **args)
+    fields = eng.compute_ray_fields(b=np.array(pts), **args)
+    n_nan = 0
+    for k, b in enumerate(pts):
+        ref = ro.compute_ds(req, nr, b, cfg.Req, cfg.Rpol, cfg.orientation, 'gravity', 'shape', gravity=dict(table=tab))
+        if ref['ds'] is None:
+            assert nseg[k] == -1
+            continue
+        n = len(ref['ds'])
+        assert nseg[k] == n, (b, nseg[k], n)
+        bad = np.isnan(ref['ds'])
+        assert np.array_equal(np.isnan(ds[k, :n]), bad)
+        n_nan += int(bad.any())
+        assert np.max(np.abs(ds[k, :n][~bad] / ref['ds'][~bad] - 1.0)) < 1e-8, b
+        ok = ~np.isnan(ref['r4ds'])
+        assert np.max(np.abs(fields[k, 0, :n][ok] / ref['r4ds'][ok] - 1.0)) < 1e-11
+    assert n_nan >= 1                                         # the grazing ray goes below its tangent shell
+    if name == 'jupiter':
+        # the two rays the reference itself computed (tests/golden/make_golden.py section gravity)
+        gg = golden('gravity.npz')
+        gds, gn, _ = eng.compute_ds(b=gg['b'], **args)
+        gf = eng.compute_ray_fields(b=gg['b'], **args)
+        for k in range(len(gg['b'])):
+            n = int(gg['nseg'][k])
+            assert gn[k] == n
+            assert np.max(np.abs(gds[k, :n] / gg['ds'][k, :n] - 1.0)) < 1e-8
+            assert np.max(np.abs(gf[k, 0, :n] / gg['r4ds'][k, :n] - 1.0)) < 1e-11
+    # the shape differs from the ellipse by kilometres; the integration takes the gravity segments as they are
+    e_ds, e_n, _ = eng.compute_ds(b=np.array(pts[:3]), **raypath._geometry_args(atm, cfg.orientation, 'ellipse'))
+    assert np.max(np.abs(ds[1, :e_n[1]] / e_ds[1, :e_n[1]] - 1.0)) > 1e-4
+    a = golden(fn)
+    freqs = [2.0, 10.0, 30.0]
+    slab = _slab(eng, a, freqs) if name == 'jupiter' else None
+    if slab is not None:
+        C = keymap(a['C_keys'])
+        T = a['gas'][C['T']]
+        got = eng.rt_batch(b=np.array(pts[:3]), alpha_slab=slab, T=T, **args)['Tb']
+        want = eng.rt_integrate(ds[:3], nseg[:3], slab, T)
+        assert np.max(np.abs(got - want)) < 1e-9
+        ell = eng.rt_batch(b=np.array(pts[:3]), alpha_slab=slab, T=T, **raypath._geometry_args(atm, cfg.orientation, 'ellipse'))['Tb']
+        assert 1e-4 < np.max(np.abs(got - ell)) < 5.0

@@ -336,3 +336,34 @@ def test_c5_saturn_oracle_rows():
         col = g['gas'][:, g['layers'][k]]
         out = ao.FORMALISMS['nh3_dbs_sjs'](g['freqs'], col[C['T']], col[C['P']], col, C, {}, units='invcm')
         assert np.max(relerr(out, g['alpha'][k])) < 1e-12
+
+
+def test_gravity_geoid_oracle_vs_reference():
+    """gtype='gravity' (shape.py:141-221): the oracle's scalar restatement reproduces the reference's calcShape (27
+    samples up to 0.3 deg on three layers) and two complete near-equatorial rays (the only ones the reference can
+    afford: it builds a scipy polynomial object per Legendre evaluation); the all-layers table the GPU tests use agrees
+    with the scalar march."""
+    from conftest import golden, keymap
+    from oracle import ray_oracle as ro
+    a, g = golden('atm_jupiter.npz'), golden('gravity.npz')
+    LP = keymap(a['LP_keys'])
+    req, GM, nr = a['property'][LP['R']], a['property'][LP['GM']], a['property'][LP['N']]
+    model = dict(GM=GM, Jn=g['Jn'], RJ=float(g['RJ']), omega_m=float(g['omega_m']), vwlat=g['vwlat'], vwdat=g['vwdat'])
+    S = ro.Geoid(req, GM, g['Jn'], float(g['RJ']), float(g['omega_m']), g['vwlat'], g['vwdat'])
+    T = ro.GeoidTable(req, GM, g['Jn'], float(g['RJ']), float(g['omega_m']), g['vwlat'], g['vwdat'], max_abs_lat=1.0)
+    for row in g['shape_rows']:
+        l, lat = int(row[0]), row[1]
+        for G in (S, T):
+            rm = G.calc(req[l], lat, float(g['shape_dlng']))
+            assert abs(rm / row[2] - 1.0) < 1e-13 and abs(G.gamma - row[3]) < 1e-15
+            assert np.max(np.abs(G.r - row[4:7])) < 1e-8 and np.max(np.abs(G.n - row[7:10])) < 1e-14
+        nsp, k = T.kindex(lat)
+        assert k == len(np.arange(0.0, lat + nsp * 0.01, nsp * 0.01)) - 1
+    b, n = list(g['b'][0]), int(g['nseg'][0])
+    with np.errstate(invalid='ignore'):
+        ray = ro.compute_ds(req, nr, b, float(a['Req']), float(a['Rpol']), a['orientation'], 'gravity', 'shape', gravity=model)
+        fast = ro.compute_ds(req, nr, b, float(a['Req']), float(a['Rpol']), a['orientation'], 'gravity', 'shape',
+                             gravity=dict(table=T))
+    assert len(ray['ds']) == n == len(fast['ds'])
+    assert np.max(np.abs(ray['ds'] / g['ds'][0, :n] - 1.0)) < 1e-12 and np.max(np.abs(ray['r4ds'] / g['r4ds'][0, :n] - 1.0)) < 1e-13
+    assert np.max(np.abs(fast['ds'] / g['ds'][0, :n] - 1.0)) < 1e-8
