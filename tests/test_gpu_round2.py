@@ -203,3 +203,33 @@ def test_widely_separated_frequency_pair(eng, c4):
         eng.set_rt_tuning(-1, True)
     assert np.array_equal(np.isnan(one), np.isnan(two)) and np.isfinite(one).any()
     assert np.nanmax(np.abs(one - two)) < 1e-9
+
+
+def test_degenerate_ray_lists(eng, c4):
+    """The compacted, ordered ray list at its edges: a request with no hit at all, one hit among sky, exactly one and
+    exactly two super-blocks of rays, 513 rays, and 40 001 random points through the host copy-out pipeline -- against
+    the plain ray order / the one-frequency kernel."""
+    a, slab, T = c4['a'], c4['slab'], c4['T']
+    rng = np.random.default_rng(5)
+    sky = np.stack([rng.uniform(1.05, 1.4, 1000), rng.uniform(-0.2, 0.2, 1000)], axis=1)
+    out = eng.rt_batch(b=sky, alpha_slab=slab, T=T, **geom(a))['Tb']
+    assert out.shape == (1000, 64) and np.all(out == 2.725)
+    one = sky.copy()
+    one[777] = [0.25, 0.5]
+    out = eng.rt_batch(b=one, alpha_slab=slab, T=T, **geom(a))['Tb']
+    assert np.all(np.delete(out, 777, axis=0) == 2.725) and np.all(out[777] > 50.0)
+    th, rad = rng.uniform(0, 2 * np.pi, 40001), np.sqrt(rng.uniform(0, 1.1, 40001))
+    pts = np.stack([rad * np.cos(th), rad * np.sin(th) * 0.935], axis=1)
+    try:
+        eng.set_rt_tuning(0, False)
+        ref = eng.rt_batch(b=pts, alpha_slab=slab, T=T, **geom(a))['Tb'].copy()
+    finally:
+        eng.set_rt_tuning(-1, True)
+    for n in (513, 8192, 16384, 40001):
+        got = eng.rt_batch(b=np.ascontiguousarray(pts[:n]), alpha_slab=slab, T=T, **geom(a))['Tb']
+        assert got.shape == (n, 64) and np.array_equal(np.isnan(got), np.isnan(ref[:n]))
+        assert np.array_equal(got == 2.725, ref[:n] == 2.725)
+        assert np.nanmax(np.abs(got - ref[:n])) < 1e-9, n
+    f32 = eng.rt_batch(b=pts, alpha_slab=slab, T=T, out_f32=True, **geom(a))['Tb']
+    big = eng.rt_batch(b=pts, alpha_slab=slab, T=T, **geom(a))['Tb']
+    assert np.array_equal(f32, big.astype(np.float32), equal_nan=True)
