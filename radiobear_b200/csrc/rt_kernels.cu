@@ -1044,6 +1044,15 @@ __device__ double c_small[4] = {
     -kSmallE * (kSmallK1 + kSmallM),                                  // a1
     0.5 * kSmallE,                                                    // a2
     0.0};
+// The same polynomial with the square completed, E/2 [(tau - m - k1)^2 + (2 - k1^2)], as the pair kernel evaluates it:
+// one DADD and one DFMA that read two registers each (the Horner form is two DFMAs with three register operands, which
+// the register file feeds at 2/3 of the pipe rate -- tools/probe_pipes.py); the factor E/2 is applied to the
+// accumulators once, when the ray leaves the small-tau phase.
+__device__ double c_small2[4] = {
+    -(kSmallM + kSmallK1),                                            // cb: u = tau + cb
+    2.0 - kSmallK1 * kSmallK1,                                        // cd: p = u^2 + cd
+    0.5 * kSmallE,                                                    // a2
+    0.0};
 // mixed-precision kernel: -2^23 log2 e and the rounding constant 2^52 + 2^51 with 0x3F000000 folded into its low word
 __device__ double c_mxc[2] = {-1.4426950408889634074 * 8388608.0, 6755399441055744.0 + 1056964608.0};
 #if RB_EXP_DEG == 2
@@ -1733,6 +1742,15 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
   int nf = 0, ns = 0;        // rb_count_steps: segments taken by the pair loops (two steps each) / single steps
   int ia = 0;                // steps in phase A (both frequencies counted)
   bool small = true;
+  // the small-tau phase accumulates its weights without the factor E/2 of the polynomial (see c_small2): applied once,
+  // when the ray leaves the phase (or ends inside it)
+  auto end_small = [&]() {
+    if (RB_EXP_SMALL_LOG > 0 && small) {
+      const double a2 = pin(c_small2 + 2);
+      iWA *= a2; TbA *= a2; iWB *= a2; TbB *= a2;
+    }
+    small = false;
+  };
 
   // e^-tau * dd for a step known to be below the threshold (the table path of rt_integrate_rays_kernel);
   // ndraw = fma(tau, cA, cM) (the caller may have it from the tau_cut test)
@@ -1847,8 +1865,9 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
           nf -= 2;                                           // counted step by step in ns
         };
         if (RB_EXP_SMALL_LOG > 0 && small) {
-          const double sa0 = pin(c_small + 0), sa1 = pin(c_small + 1 + vz), sa2 = pin(c_small + 2);
-#define RB_PAIR_WA(T, DD) (fma(fma((T), sa2, sa1), (T), sa0) * (DD))
+          const double scb = pin(c_small2 + 0 + vz), scd = pin(c_small2 + 1);
+          auto wa = [&](double t, double dd) { const double u_ = t + scb; return fma(u_, u_, scd) * dd; };
+#define RB_PAIR_WA(T, DD) wa((T), (DD))
 #pragma unroll 1
           while (dpa <= dlast) {
             d1 = lds_f64<256>(dpa); d2 = lds_f64<512>(dpa);
@@ -1874,7 +1893,7 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
           dpa += 512; qpa += 2 * kRowB;
         small_exit_0:
           ia += 2 * (int)((dpa - dbase) >> 8);
-          small = false;
+          end_small();
           finish_group(d0, d1, d2, qpa);
           d0 = d2; dpa += 512; qpa += 2 * kRowB;
         small_done:;
@@ -1919,6 +1938,8 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
         nf += u;
       }
       // one segment at a time: the chunk remainder, and the frequency that is left alone after its partner stopped
+      // (these steps take the table exponential: a ray still in the small-tau phase leaves it here)
+      if (u < m && mode != 0) end_small();
 #pragma unroll 1
       for (; u < m && mode != 0; ++u) {
         const double dcur = dsb[u * 32];
@@ -1966,6 +1987,7 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
 #else
   cp_async_wait<0>();
 #endif
+  end_small();              // a ray that ended inside the small-tau phase
   if (k.step_counter) {   // measurement aid (bench.py): executed (ray, freq, segment) steps, one atomic per warp
     unsigned long long done = 2ull * (unsigned long long)nf + (unsigned long long)ns;
     unsigned long long done_a = (unsigned long long)ia;
