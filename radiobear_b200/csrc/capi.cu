@@ -83,6 +83,7 @@ int rb_create(int device, rb_context** out) {
   }
   if (const char* e = getenv("RB_RT_PAIRS")) ctx->rt_pairs = atoi(e) < 0 ? -1 : (atoi(e) ? 1 : 0);
   if (const char* e = getenv("RB_RT_COMPACT")) ctx->rt_compact = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("RB_RT_TILES")) ctx->rt_tiles = atoi(e) ? 1 : 0;
   for (int i = 0; i < 3; ++i)
     for (int r = 0; r < rb_context::kEvRing; ++r)
       for (int j = 0; j < 2; ++j) RB_CUDA(ctx, cudaEventCreate(&ctx->ev[i][r][j]));
@@ -748,7 +749,7 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full_in, const rb_rt
     // chunks complete evenly in time.
     pg.shift = rb_progress_shift(R);
     for (int c = 0; c <= nch; ++c) pg.cut[c] = (int)cut_at(c);
-    const unsigned fgroups = (unsigned)(prep.pairs ? (F + kPairFreqs - 1) / kPairFreqs : (F + 7) / 8);
+    const unsigned fgroups = (unsigned)prep.fgroups;
     // value the counter of a chunk of `len` ray tiles ends at: one count per CTA (len * fgroups); compacted launches
     // start the counters at their deficit so that they end at kProgressTarget (rt_progress_init_kernel)
     RB_CUDA(ctx, cudaMemsetAsync(p_flags, 0, kMaxProgressChunks * sizeof(unsigned), user));

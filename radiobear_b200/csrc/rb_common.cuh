@@ -42,6 +42,7 @@ struct rb_context {
   int rt_precision = 0;  // RB_RT_F64 / RB_RT_MIXED: arithmetic of the rays-major integration (rb_set_rt_precision)
   int rt_pairs = -1;     // rb_set_rt_tuning: two frequencies per thread (-1 automatic)
   int rt_compact = 1;    // rb_set_rt_tuning: integrate the compacted list of rays that hit the planet
+  int rt_tiles = 0;      // RB_RT_TILES: pair kernel with one frequency pair x four ray tiles per CTA (0: four pairs x one tile)
   bool smem_opted[4] = {false, false, false, false};  // kernels opted into > 48 KB of dynamic shared memory
   int alpha_newton = -1; // Newton steps of the line reciprocal (RB_RCP_NEWTON), read once per context
   unsigned long long* step_counter = nullptr;  // device counters of integrated segment-steps (measurement aid)
@@ -199,6 +200,8 @@ struct RtPrep {
   bool use_rays = false;       // rays-major kernel (R >= 512, point rays) or the lanes = frequency kernel
   bool mixed = false;          // rays-major kernel in mixed precision (operand rows of rt_prepare_mixed_kernel)
   bool pairs = false;          // FP64 rays-major kernel with two frequencies per thread (pair operand rows)
+  bool tiles = false;          // ... in the decomposition where the warps of a CTA share the frequency pair, not the rays
+  int fgroups = 0;             // frequency groups = CTAs (pair kernel, tiles: warps) that integrate one ray tile
   const void* prep = nullptr;  // operand slab of the rays-major kernel
 };
 int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt /*device pointers*/, int64_t R_total, bool profile,

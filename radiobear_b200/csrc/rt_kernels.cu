@@ -1136,12 +1136,14 @@ struct RayTile {
   bool dead;           // whole CTA beyond the end of the compacted list
   int first_r, last_r; // compacted launch: ray index of the first / last ray of the tile
 };
-__device__ __forceinline__ RayTile map_ray_tile(const RtK& k) {
+// (tiles_per_cta > 1: the CTA's warps take consecutive tiles, `sub` = this warp's)
+__device__ __forceinline__ RayTile map_ray_tile(const RtK& k, unsigned tiles_per_cta = 1, unsigned sub = 0) {
   RayTile m;
   m.dead = false;
   m.first_r = m.last_r = 0;
-  m.by = blockIdx.x / k.fgroups;
-  m.fg = blockIdx.x - m.by * k.fgroups;
+  const unsigned bcta = blockIdx.x / k.fgroups;
+  m.fg = blockIdx.x - bcta * k.fgroups;
+  m.by = bcta * tiles_per_cta + sub;
   if (k.cidx) {
     const int nc = *k.ncomp;
     const unsigned ntile = (unsigned)((nc + 31) >> 5);
@@ -1159,11 +1161,12 @@ __device__ __forceinline__ RayTile map_ray_tile(const RtK& k) {
       m.last_r = (int)__reduce_max_sync(0xffffffffu, m.in ? (unsigned)m.r : 0u);
     }
   } else {
+    m.dead = m.by >= k.ntiles;
     unsigned tile = m.by + (unsigned)k.progress.shift;
     if (tile >= k.ntiles) tile -= k.ntiles;
     m.tile = tile;
     m.t = m.r = (long long)tile * 32 + threadIdx.x;
-    m.in = m.r < k.R;
+    m.in = !m.dead && m.r < k.R;
   }
   return m;
 }
@@ -1187,11 +1190,12 @@ __device__ __forceinline__ unsigned progress_touched(const RtProgress& pg, int n
 
 // this CTA's results are in global memory: count it in its chunk(s) (the host's copy stream waits on the counters
 // with a stream memory operation and then copies the chunk device -> host)
-__device__ __forceinline__ void progress_report(const RtK& k, const RayTile& m, int tid) {
+// (per_warp: the warp is the unit that finished a tile -- rt_integrate_pairs_kernel<true>)
+__device__ __forceinline__ void progress_report(const RtK& k, const RayTile& m, int tid, bool per_warp = false) {
   if (!k.progress.done) return;
   __threadfence();
-  __syncthreads();
-  if (tid != 0) return;
+  if (per_warp) { __syncwarp(); if (threadIdx.x != 0) return; }
+  else { __syncthreads(); if (tid != 0) return; }
   if (k.cidx) {
     unsigned mask = progress_touched(k.progress, (int)k.ntiles, m.first_r >> 5, m.last_r >> 5);
     for (; mask; mask &= mask - 1) atomicAdd(k.progress.done + (__ffs(mask) - 1), 1u);
@@ -1547,6 +1551,22 @@ static_assert(kPChunk % 4 == 0 && kPChunk >= 8, "pair kernel: trips of four segm
 static_assert(RB_RT_RING ? kPStages >= 3 : kPStages == 2, "ring: at least three buffers; barrier version: two");
 constexpr int kPairRow = 3;                          // double2 per (segment, pair)
 constexpr int kPairThreads = 32 * kPairWarps;
+// Decomposition "tiles" (rt_integrate_pairs_kernel<true>): the warps of a CTA share the FREQUENCY PAIR and each takes
+// its own ray tile (four tiles that are neighbours in the ordered list), staging its own ds chunks; nothing is shared
+// but the exponential table, so there is no CTA barrier in the loop and the warps of a CTA -- same frequencies, nearly
+// the same rays -- finish together.  The ds tiles are then fetched once per frequency pair instead of once per eight
+// frequencies (16 GB instead of 8 GB from L2 per C4 launch: 14 % of the crossbar), in chunks of kTChunk segments.
+// Measured on B200 (C4, same bits): 3.36 ms against 3.10 ms for the shared-rays decomposition -- the barrier waits it
+// removes cost no issue slots, the extra copy instructions and chunk turns (8 segments instead of 32) do.  Kept as a
+// run-time option (RB_RT_TILES=1), off by default.
+#ifndef RB_RTT_CHUNK
+#define RB_RTT_CHUNK 8
+#endif
+constexpr int kTChunk = RB_RTT_CHUNK;
+static_assert(kTChunk % 4 == 0 && kTChunk >= 8, "tiles decomposition: trips of four segments");
+constexpr size_t kTilesWarpBytes = 2 * ((kTChunk + 1) * 32 * sizeof(double) + kTChunk * 3 * sizeof(double2));
+constexpr size_t kTilesSmemBytes = kPairWarps * kTilesWarpBytes;
+static_assert(kRtSlackBytes >= (size_t)(kTChunk + 1) * 32 * sizeof(double) + 256, "ds slab slack covers one over-read chunk");
 constexpr int kPairTileQ = kPChunk * kPairWarps * kPairRow;    // double2 per operand tile
 constexpr int kPairRound = kPairThreads * 16;        // bytes one round of 16-byte copies of the whole CTA moves
 constexpr size_t kPairStageBytes = kPTileDs * sizeof(double) + kPairTileQ * sizeof(double2);
@@ -1562,18 +1582,18 @@ static_assert(kRtSlackBytes >= kChunk * 8 * sizeof(double4), "operand slack cove
 // pair operands:  prep2[fg][i][p] = { asum_a, asum_b }, { a'_a, T_i+1 a'_a }, { a'_b, T_i+1 a'_b },
 //   a = kPairFreqs fg + 2 p, b = a + 1; asum = (a_i + a_i+1) kHalfCm, a' = a_i+1 kHalfCm; zero for f >= F
 __global__ void rt_prepare_pairs_kernel(const double* __restrict__ alpha, const double* __restrict__ T, int L, int F,
-                                        int ngroups, double2* __restrict__ prep2) {
+                                        int ngroups, int pw /* pairs per row */, double2* __restrict__ prep2) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int Lm1 = L - 1;
-  if (idx >= ngroups * Lm1 * kPairWarps) return;
-  const int p = idx % kPairWarps;
-  const int i = (idx / kPairWarps) % Lm1;
-  const int fg = (idx / kPairWarps) / Lm1;
+  if (idx >= ngroups * Lm1 * pw) return;
+  const int p = idx % pw;
+  const int i = (idx / pw) % Lm1;
+  const int fg = (idx / pw) / Lm1;
   const double kHalfCm = 0.5 * kKmToCm;
   double v[2][3];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int f = fg * kPairFreqs + 2 * p + h;
+    const int f = fg * 2 * pw + 2 * p + h;
     v[h][0] = v[h][1] = v[h][2] = 0.0;
     if (f < F) {
       const double a0 = alpha[(size_t)i * F + f], a1 = alpha[(size_t)(i + 1) * F + f];
@@ -1630,21 +1650,30 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 }
 #endif
 
+template <bool TILES>
 __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_kernel(const __grid_constant__ RtK k) {
-  // dynamic shared memory: [ table | ds tiles x kStages | pair operand tiles x kStages ]
+  static_assert(!(TILES && RB_RT_RING), "the tiles decomposition stages with cp.async");
+  // TILES = false: the CTA's warps are kPairWarps frequency pairs on one ray tile (shared staging buffers);
+  // TILES = true:  the CTA's warps are kPairWarps ray tiles on one frequency pair (private staging buffers per warp)
+  constexpr int kCh = TILES ? kTChunk : kPChunk;                 // segments per staged chunk
+  constexpr int kSt = TILES ? 2 : kPStages;                      // staging buffers
+  constexpr int kRowPairs = TILES ? 1 : kPairWarps;              // frequency pairs per operand row
+  constexpr int kTileD = (kCh + 1) * 32;                         // doubles per ds buffer
+  constexpr int kTileQ = kCh * kRowPairs * kPairRow;             // double2 per operand buffer
+  // dynamic shared memory: [ table | ds buffers x kSt | operand buffers x kSt ]  (TILES: the last two per warp)
   extern __shared__ __align__(16) unsigned char s_raw[];
   double* const s_tab = reinterpret_cast<double*>(s_raw);
-  double* const s_ds = s_tab + kExpTabDoubles;
-  double2* const s_q = reinterpret_cast<double2*>(s_ds + kPStages * kPTileDs);
+  double* const s_ds = s_tab + kExpTabDoubles + (TILES ? threadIdx.y * (kSt * (kTileD + 2 * kTileQ)) : 0);
+  double2* const s_q = reinterpret_cast<double2*>(s_ds + kSt * kTileD);
   const int tid = threadIdx.y * 32 + threadIdx.x;
 
   const int S = k.L - 1;
-  const RayTile rt_ = map_ray_tile(k);
-  if (rt_.dead) return;
+  const RayTile rt_ = TILES ? map_ray_tile(k, kPairWarps, threadIdx.y) : map_ray_tile(k);
+  if (!TILES && rt_.dead) return;
   const unsigned tile = rt_.tile;
   const long long tpos = rt_.t;
   const long long r = rt_.r;
-  const int fA = rt_.fg * kPairFreqs + 2 * threadIdx.y;
+  const int fA = rt_.fg * (2 * kRowPairs) + 2 * (TILES ? 0 : (int)threadIdx.y);
   const bool validA = rt_.in && (fA < k.F), validB = rt_.in && (fA + 1 < k.F);
   const int n = validA ? k.nseg[tpos] : -1;
   const bool nanray = validA && k.nanflag[tpos] != 0;
@@ -1699,26 +1728,44 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
   }
   __syncthreads();                                           // table landed, s_ctl[1] published
 #else
-  // copy plan (see rt_integrate_rays_kernel): ds chunk 33 x 256 B, operand chunk kChunk x 384 B, 16-byte pieces
-  const char* src_ds = reinterpret_cast<const char*>(k.ds + (size_t)tile * S * 32) + tid * 16;
-  const char* src_q = reinterpret_cast<const char*>(k.prep2 + (size_t)rt_.fg * S * kPairWarps * kPairRow) + tid * 16;
-  const unsigned dst_ds = (unsigned)__cvta_generic_to_shared(s_ds) + tid * 16;
-  const unsigned dst_q = (unsigned)__cvta_generic_to_shared(s_q) + tid * 16;
+  // copy plan (see rt_integrate_rays_kernel): a ds chunk is (kCh + 1) x 256 B, an operand chunk kCh x kRowPairs x 48 B,
+  // both contiguous in global memory, moved in 16-byte pieces by the threads that share the buffers (TILES: the warp)
+  constexpr int kCopyThreads = TILES ? 32 : kPairThreads;
+  const int ctid = TILES ? (int)threadIdx.x : tid;
+  const char* src_ds = reinterpret_cast<const char*>(k.ds + (size_t)tile * S * 32) + ctid * 16;
+  const char* src_q = reinterpret_cast<const char*>(k.prep2 + (size_t)rt_.fg * S * kRowPairs * kPairRow) + ctid * 16;
+  const unsigned dst_ds = (unsigned)__cvta_generic_to_shared(s_ds) + ctid * 16;
+  const unsigned dst_q = (unsigned)__cvta_generic_to_shared(s_q) + ctid * 16;
   auto issue = [&](int c) {
-    const unsigned bd = (c & 1) ? (unsigned)(kPTileDs * sizeof(double)) : 0u;
-    const unsigned bq = (c & 1) ? (unsigned)(kPairTileQ * sizeof(double2)) : 0u;
-    constexpr int kDsRounds = (kPChunk * 32 * (int)sizeof(double)) / kPairRound;
-    cp_rounds<kDsRounds, kPairRound>(dst_ds + bd, src_ds);
-    cp_rounds<(kPairTileQ * (int)sizeof(double2)) / kPairRound, kPairRound>(dst_q + bq, src_q);
-    if (tid < 16) cp_async16_at<kDsRounds * kPairRound>(dst_ds + bd, src_ds);
+    const unsigned bd = (c & 1) ? (unsigned)(kTileD * sizeof(double)) : 0u;
+    const unsigned bq = (c & 1) ? (unsigned)(kTileQ * sizeof(double2)) : 0u;
+    constexpr int kRound = kCopyThreads * 16;
+    constexpr int kDsBytes = kTileD * (int)sizeof(double), kQBytes = kTileQ * (int)sizeof(double2);
+    cp_rounds<kDsBytes / kRound, kRound>(dst_ds + bd, src_ds);
+    if (ctid * 16 < kDsBytes % kRound) cp_async16_at<(kDsBytes / kRound) * kRound>(dst_ds + bd, src_ds);
+    cp_rounds<kQBytes / kRound, kRound>(dst_q + bq, src_q);
+    if (ctid * 16 < kQBytes % kRound) cp_async16_at<(kQBytes / kRound) * kRound>(dst_q + bq, src_q);
     cp_async_commit();
-    src_ds += kPChunk * 32 * sizeof(double);
-    src_q += kPairTileQ * sizeof(double2);
+    src_ds += kCh * 32 * sizeof(double);
+    src_q += kTileQ * sizeof(double2);
   };
-  const bool any_live = __syncthreads_or(mode != 0);
-  if (any_live) {
+  bool any_live;
+  if (TILES) {
+    // the table is the one thing the warps share: all threads fetch it, then every warp is on its own
     for (int q = tid; q < kExpTabDoubles / 2; q += kPairThreads) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
-    issue(0);
+    any_live = __any_sync(0xffffffffu, mode != 0);
+    if (any_live) issue(0); else cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (!any_live) {                                           // nothing to integrate in this warp's tile
+      mode = 0;
+    }
+  } else {
+    any_live = __syncthreads_or(mode != 0);
+    if (any_live) {
+      for (int q = tid; q < kExpTabDoubles / 2; q += kPairThreads) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
+      issue(0);
+    }
   }
 #endif
 
@@ -1799,8 +1846,8 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
 
   // shared-window addresses of this thread's ds column / operand rows in stage 0
   const unsigned ds_a0 = (unsigned)__cvta_generic_to_shared(s_ds + threadIdx.x);
-  const unsigned q_a0 = (unsigned)__cvta_generic_to_shared(s_q + threadIdx.y * kPairRow);
-  constexpr unsigned kRowB = kPairWarps * kPairRow * sizeof(double2);   // bytes between the operand rows of two segments
+  const unsigned q_a0 = (unsigned)__cvta_generic_to_shared(s_q + (TILES ? 0 : threadIdx.y) * kPairRow);
+  constexpr unsigned kRowB = kRowPairs * kPairRow * sizeof(double2);   // bytes between the operand rows of two segments
   constexpr int small_hi = (int)(((0x3FFull - (RB_EXP_SMALL_LOG > 0 ? RB_EXP_SMALL_LOG : 1)) << 20));
 
   for (int c = 0; any_live; ++c) {
@@ -1818,26 +1865,33 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
     bool wrote_zero = false;
 #else
     cp_async_wait<0>();
-    if (!__syncthreads_or(mode != 0)) break;
+    if (TILES) {
+      // this warp's pieces of chunk c have landed (every lane waited for its own); the vote also tells whether any of
+      // its rays is still going, and that all lanes are done with the buffer chunk c + 1 goes into
+      __syncwarp();
+      if (!__any_sync(0xffffffffu, mode != 0)) break;
+    } else {
+      if (!__syncthreads_or(mode != 0)) break;
+    }
     issue(c + 1);
 #endif
     if (mode != 0) {
-      double* dsb = s_ds + (c % kPStages) * kPTileDs + threadIdx.x;
-      const double2* qb = s_q + (c % kPStages) * kPairTileQ + threadIdx.y * kPairRow;
-      const int zrow = steps - c * kPChunk;
+      double* dsb = s_ds + (c % kSt) * kTileD + threadIdx.x;
+      const double2* qb = s_q + (c % kSt) * kTileQ + (TILES ? 0 : threadIdx.y) * kPairRow;
+      const int zrow = steps - c * kCh;
 #if RB_RT_RING
-      wrote_zero = zrow <= kPChunk;
+      wrote_zero = zrow <= kCh;
 #endif
-      if (zrow <= kPChunk) dsb[zrow * 32] = 0.0;             // nothing lies below the last node
-      const int m = min(kPChunk, steps - i);
+      if (zrow <= kCh) dsb[zrow * 32] = 0.0;                 // nothing lies below the last node
+      const int m = min(kCh, steps - i);
       int u = 0;
       if (mode == 3 && m >= 4) {
         // Trips of 2 x (two segments x two frequencies).  The optical depths are updated in place; a group the
         // fast loops cannot finish (it leaves the small-tau range / a frequency crosses tau_cut inside it) is
         // handed, with its four optical depths, to finish_group, which takes it one step at a time.
-        const unsigned dbase = ds_a0 + (unsigned)((c % kPStages) * kPTileDs * sizeof(double));
+        const unsigned dbase = ds_a0 + (unsigned)((c % kSt) * kTileD * sizeof(double));
         unsigned dpa = dbase;
-        unsigned qpa = q_a0 + (unsigned)((c % kPStages) * kPairTileQ * sizeof(double2));
+        unsigned qpa = q_a0 + (unsigned)((c % kSt) * kTileQ * sizeof(double2));
         const unsigned dlast = dbase + 256u * (unsigned)(m - 4);   // last trip start with four segments left
         double d0 = lds_f64<0>(dpa), d1, d2, d3, tA0, tB0;
         double2 s0, s1;
@@ -1944,7 +1998,7 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
       for (; u < m && mode != 0; ++u) {
         const double dcur = dsb[u * 32];
         const double dd = dcur + dsb[(u + 1) * 32];
-        const double2* qr = qb + (size_t)u * kPairWarps * kPairRow;
+        const double2* qr = qb + (size_t)u * kRowPairs * kPairRow;
         const double2 s0 = qr[0];
         if (mode & 1) { tauA = fma(s0.x, dcur, tauA); step_known(0, tauA, dd, qr[1]); }
         if (mode & 2) { tauB = fma(s0.y, dcur, tauB); step_known(1, tauB, dd, qr[2]); }
@@ -2010,7 +2064,8 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
     else reinterpret_cast<double*>(k.out_Tb)[o] = vout;
     if (k.out_intW) k.out_intW[o] = (n < 0) ? 0.0 : wout;
   }
-  progress_report(k, rt_, tid);
+  if (TILES && rt_.dead) return;                             // a warp beyond the end of the list has no tile to report
+  progress_report(k, rt_, tid, TILES);
 }
 
 // ====================================================================================================
@@ -2397,10 +2452,12 @@ int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total,
   out->use_rays = !profile && !rt->disc_average && R_total >= 512;
   out->mixed = out->use_rays && have_pairs && ctx->rt_precision == RB_RT_MIXED;
   out->pairs = false;
+  out->tiles = false;
   out->prep = nullptr;
-  if (!out->use_rays) return RB_OK;
   const int F = rt->n_freqs;
   const int ngroups = (F + 7) / 8;
+  out->fgroups = ngroups;
+  if (!out->use_rays) return RB_OK;
   const int nel = ngroups * (L - 1) * 8;
   void* scratch;
   if (out->mixed) {
@@ -2418,11 +2475,14 @@ int rb_rt_prepare(rb_context* ctx, int L, const rb_rt_desc* rt, int64_t R_total,
     ctx->launches += 1;
   }
   out->pairs = choose_pairs(ctx, F);
+  out->tiles = out->pairs && ctx->rt_tiles == 1 && !RB_RT_RING;
+  out->fgroups = out->pairs ? (out->tiles ? (F + 1) / 2 : (F + kPairFreqs - 1) / kPairFreqs) : ngroups;
   if (out->pairs) {
-    const int ng2 = (F + kPairFreqs - 1) / kPairFreqs;
-    const int nel2 = ng2 * (L - 1) * kPairWarps;
+    const int pw = out->tiles ? 1 : kPairWarps;               // frequency pairs per operand row
+    const int ng2 = out->fgroups;
+    const int nel2 = ng2 * (L - 1) * pw;
     RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)nel2 * kPairRow * sizeof(double2) + kRtSlackBytes, &scratch));
-    rt_prepare_pairs_kernel<<<(nel2 + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ng2, (double2*)scratch);
+    rt_prepare_pairs_kernel<<<(nel2 + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ng2, pw, (double2*)scratch);
   } else {
     RB_TRY(rb_ensure(ctx, RB_BUF_PREP, (size_t)ngroups * (L - 1) * 8 * sizeof(double4) + kRtSlackBytes, &scratch));
     rt_prepare_kernel<<<(nel + 255) / 256, 256, 0, ctx->stream>>>(rt->alpha, rt->T, L, F, ngroups, (double4*)scratch);
@@ -2529,9 +2589,10 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     // of a ray tile adjacent in launch order; operands prepared by rb_rt_prepare
     k.step_counter = ctx->step_counter;
     if (progress) k.progress = *progress;
-    k.fgroups = (unsigned)(prep.pairs ? (k.F + kPairFreqs - 1) / kPairFreqs : (k.F + 7) / 8);
+    k.fgroups = (unsigned)prep.fgroups;
     k.ntiles = (unsigned)((g.R + 31) / 32);
-    const unsigned long long nblocks = (unsigned long long)k.fgroups * k.ntiles;
+    const unsigned long long nblocks =
+        (unsigned long long)k.fgroups * (prep.tiles ? (k.ntiles + kPairWarps - 1) / kPairWarps : k.ntiles);
     if (nblocks > 2147483647ULL) return rb_fail(ctx, RB_ERR_INVALID, "rt: too many (ray tile, frequency group) blocks for one launch");
     dim3 block(32, prep.pairs ? kPairWarps : 8), grid((unsigned)nblocks);
     if (prep.mixed) {
@@ -2552,12 +2613,20 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
       if (!progress) RB_TRY(rb_launch_fill_miss(ctx, g, k.F, out_Tb, out_intW, k.out_f32));
     }
     k.exp_tab = ctx->exp_tab;
-    if (prep.pairs) {
+    if (prep.pairs && prep.tiles) {
+      k.prep2 = (const double2*)prep.prep;
+      constexpr size_t smem = kExpTabDoubles * sizeof(double) + kTilesSmemBytes;
+      static_assert(smem <= 227 * 1024, "shared memory limit");
+#if !RB_RT_RING
+      RB_TRY(opt_in_smem(ctx, rt_integrate_pairs_kernel<true>, smem, 0));
+      rt_integrate_pairs_kernel<true><<<grid, block, smem, ctx->stream>>>(k);
+#endif
+    } else if (prep.pairs) {
       k.prep2 = (const double2*)prep.prep;
       constexpr size_t smem = kExpTabDoubles * sizeof(double) + kPairsSmemBytes;
       static_assert(smem <= 227 * 1024, "shared memory limit");
-      RB_TRY(opt_in_smem(ctx, rt_integrate_pairs_kernel, smem, 1));
-      rt_integrate_pairs_kernel<<<grid, block, smem, ctx->stream>>>(k);
+      RB_TRY(opt_in_smem(ctx, rt_integrate_pairs_kernel<false>, smem, 1));
+      rt_integrate_pairs_kernel<false><<<grid, block, smem, ctx->stream>>>(k);
     } else {
       k.prep = (const double4*)prep.prep;
       constexpr size_t smem = kExpTabDoubles * sizeof(double) + kRaysSmemBytes;
