@@ -335,7 +335,17 @@ def alpha_c5(ctx, dev, reps=5, full=False, world=1, rank=0):
     assert L % world == 0
     g_t = torch.tensor(gas[:, lo:hi], **t64).contiguous()
     f_t, T_t, P_t = torch.tensor(freqs, **t64), torch.tensor(gas[C['T']][lo:hi], **t64), torch.tensor(P[lo:hi], **t64)
-    out = torch.empty((L, F), **t64)                 # the full slab; this rank's block of layers is out[lo:hi]
+    # the full slab; this rank's block of layers is out[lo:hi].  N > 1: a symmetric allocation, so that the absorption
+    # kernel can store its values straight into every GPU's copy over NVLink (the all_gather inside the kernel);
+    # RB_BENCH_ALPHA_GATHER=nccl (or no symmetric memory) keeps the kernel + NCCL all_gather pair
+    sym = None
+    if world > 1 and os.environ.get('RB_BENCH_ALPHA_GATHER', 'kernel') == 'kernel':
+        sym = parallel.symmetric_slab(L, F, dev)
+        ok = torch.tensor([1 if sym.usable else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            sym = None
+    out = sym.tensor if sym is not None else torch.empty((L, F), **t64)
     local = out[lo:hi]
     forms = [('nh3', 'nh3_dbs_sjs')]
     ms, ms_k = [], []
@@ -347,10 +357,16 @@ def alpha_c5(ctx, dev, reps=5, full=False, world=1, rank=0):
             torch.cuda.synchronize()
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-            engine.alpha_layers_dev(f_t, T_t, P_t, g_t, C, formalisms=forms, out=local, freqs_host=freqs, ctx=ctx)
-            e1.record()
-            if world > 1:
-                dist.all_gather_into_tensor(out, local)      # in place: block r of the output is rank r's input
+            if sym is not None:
+                engine.alpha_layers_dev(f_t, T_t, P_t, g_t, C, formalisms=forms, freqs_host=freqs, ctx=ctx,
+                                        scatter=(sym.ptrs, lo))
+                e1.record()
+                sym.barrier()                                # everybody's stores have landed everywhere
+            else:
+                engine.alpha_layers_dev(f_t, T_t, P_t, g_t, C, formalisms=forms, out=local, freqs_host=freqs, ctx=ctx)
+                e1.record()
+                if world > 1:
+                    dist.all_gather_into_tensor(out, local)  # in place: block r of the output is rank r's input
             e2.record()
             torch.cuda.synchronize()
             if i >= 2:
@@ -378,8 +394,12 @@ def alpha_c5(ctx, dev, reps=5, full=False, world=1, rank=0):
                 ', full catalog: 415 + 1301 + 4198 lines' if full else ', shipped catalog: 415 + 201 + 198 lines'),
             'metric': 'alpha layer*freq*line/s',
             'value': evals / t, 'ms': t * 1e3, 'kernel_ms': t_kernel * 1e3, 'n_gpus': world,
-            'sharding': 'none' if world == 1 else 'contiguous blocks of layers per rank + one all_gather (NCCL) in place into the '
-                        '[L][F] slab: every rank ends with the full slab',
+            'sharding': 'none' if world == 1 else (
+                'contiguous blocks of layers per rank; the kernel stores every value into the [L][F] slab of all GPUs over '
+                'NVLink (symmetric memory) + one device-side barrier: every rank ends with the full slab' if sym is not None else
+                'contiguous blocks of layers per rank + one all_gather (NCCL) in place into the [L][F] slab: every rank ends '
+                'with the full slab'),
+            'gather': 'none' if world == 1 else ('in-kernel peer stores' if sym is not None else 'nccl all_gather'),
             'line_evals': evals, 'max_rel_err_vs_oracle': rel,
             'fp64_tflops_algorithmic': flops / t / 1e12,
             'flops_per_line_eval': '10 (Ben-Reuven) / 8 (Gross) + 1 reciprocal (SURVEY 8d)',

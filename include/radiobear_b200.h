@@ -175,6 +175,15 @@ typedef struct rb_alpha_desc {
  * A single plugin call (constituents/<gas>/<formalism>.alpha, alpha.py:210) is n_layers = 1.   */
 int rb_alpha_layers(rb_context* ctx, const rb_alpha_desc* desc, double* out_total, double* out_cube);
 int rb_alpha_layers_dev(rb_context* ctx, const rb_alpha_desc* desc, double* out_total, double* out_cube);
+/* Layer-sharded absorption over the GPUs of one NVSwitch domain (one process per GPU): desc describes THIS rank's block
+ * of layers (device pointers, like rb_alpha_layers_dev); peer_slabs[n_peers] are the device addresses of the full
+ * [L_total][F] slab on every GPU, this one included, as mapped into this process (a symmetric / peer-accessible
+ * allocation, e.g. torch.distributed._symmetric_memory); the kernel stores every value it computes into row
+ * first_row + l of all of them, so the all_gather of the blocks happens inside the kernel, over
+ * NVLink, behind the line sums.  The caller synchronises the ranks afterwards (a barrier with system-scope release /
+ * acquire, e.g. the symmetric-memory barrier) before anybody reads the slab. */
+int rb_alpha_layers_dev_scatter(rb_context* ctx, const rb_alpha_desc* desc, int32_t n_peers, const uint64_t* peer_slabs,
+                                int64_t first_row);
 /* Alpha.total_layer_alpha on a cached per-constituent cube (get_alpha='memory'/'file', alpha.py:151-192,
  * 224-225): out_total[l][f] = sum_c scale[c][l] * cube[l][f][c]; when out_cube != NULL it receives the scaled
  * cube (what a following save_alpha stores).  scale may be NULL (all ones).  Host pointers. */

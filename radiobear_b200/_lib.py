@@ -99,6 +99,7 @@ def load():
         'rb_alpha_layers': (C.c_int, [vp, C.POINTER(AlphaDesc), vp, vp]),
         'rb_alpha_layers_dev': (C.c_int, [vp, C.POINTER(AlphaDesc), vp, vp]),
         'rb_alpha_scale_sum': (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp]),
+        'rb_alpha_layers_dev_scatter': (C.c_int, [vp, C.POINTER(AlphaDesc), i32, C.POINTER(C.c_uint64), i64]),
         'rb_alpha_layers_resident': (C.c_int, [vp, C.POINTER(AlphaDesc), i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         'rb_alpha_rescale_resident': (C.c_int, [vp, vp, C.POINTER(C.c_uint64)]),
         'rb_alpha_resident_info': (C.c_int, [vp, vp, C.POINTER(C.c_uint64), vp, C.POINTER(C.c_uint64)]),
@@ -128,7 +129,7 @@ EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error'
                     'rb_synchronize',
                     'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_kernel_timed_count',
                     'rb_set_rt_chunks', 'rb_set_rt_precision', 'rb_get_rt_precision', 'rb_set_rt_tuning', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
-                    'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_alpha_layers_resident', 'rb_alpha_rescale_resident',
+                    'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_alpha_layers_dev_scatter', 'rb_alpha_layers_resident', 'rb_alpha_rescale_resident',
                     'rb_alpha_resident_info', 'rb_alpha_fetch', 'rb_rt_batch_resident', 'rb_compute_ds', 'rb_compute_ray_fields', 'rb_set_gravity_model', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
                     'rb_probe_fp64_peak', 'rb_probe_rcp', 'rb_probe_fp64_mix']
 

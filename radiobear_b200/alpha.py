@@ -193,7 +193,17 @@ class Alpha:
                 # one process per GPU: this rank's block of layers (or of frequencies), then one all_gather (every
                 # rank traces rays with the full slab afterwards)
                 cl = common['cloud']
-                if self.shard_axis == 'freqs':
+                slab = None
+                if self.shard_axis == 'layers':
+                    if isinstance(scale, dict):                    # validated against all layers before it is cut
+                        self.get_layer_scale(scale, L)
+                    # NCCL ranks on one NVSwitch domain: the all_gather happens inside the absorption kernel
+                    slab = parallel.alpha_layers_scatter(fr, atm.gas[C['T']], atm.gas[C['P']], atm.gas, C, cl,
+                                                         atm.config.Cl, self.formalisms(), self.other_dict, utils.alphaUnit,
+                                                         scale, self.truncate_strength, self.truncate_freq)
+                if slab is not None:
+                    pass
+                elif self.shard_axis == 'freqs':
                     def block(lo, hi):
                         return engine.alpha_layers(fr[lo:hi], atm.gas[C['T']], atm.gas[C['P']], atm.gas, C, **common)
                 else:
@@ -204,7 +214,8 @@ class Alpha:
                             self.get_layer_scale(scale, L)
                         return engine.alpha_layers(fr, atm.gas[C['T']][lo:hi], atm.gas[C['P']][lo:hi],
                                                    np.ascontiguousarray(atm.gas[:, lo:hi]), C, **kw)
-                slab = parallel.alpha_layers_sharded(block, L, len(fr), axis=self.shard_axis)
+                if slab is None:
+                    slab = parallel.alpha_layers_sharded(block, L, len(fr), axis=self.shard_axis)
             elif os.environ.get('RB_ALPHA_RESIDENT', '1') == '0':     # A/B switch: results through host memory
                 out = engine.alpha_layers(fr, atm.gas[C['T']], atm.gas[C['P']], atm.gas, C, want_cube=to_cache, **common)
                 slab, cube = out if to_cache else (out, None)

@@ -63,6 +63,12 @@ struct AlphaK {
   const double* scale;
   double* out_total;
   double* out_cube;
+  // layer-sharded multi-GPU runs: this rank's layers are rows [peer_row0, peer_row0 + L) of a full slab that every GPU
+  // holds; the epilogue stores each value into all of them over NVLink (peer pointers of a symmetric allocation)
+  // instead of into out_total -- the all_gather happens inside the kernel, tile by tile behind the line sums
+  double* peer_out[RB_MAX_PEERS];
+  int n_peer;
+  long long peer_row0;
   const double* cat[RB_NUM_CATALOGS];
   int ncat[RB_NUM_CATALOGS];
   // which families are present and the constituent slot each one fills (-1 = absent)
@@ -787,7 +793,14 @@ __global__ void __launch_bounds__(kThreads, FPT >= 4 ? RB_ALPHA_FPT4_CTAS : 2) a
         total += v;
       }
     }
-    k.out_total[o] = total;
+    if (k.n_peer > 0) {
+      const size_t op = (size_t)(k.peer_row0 + l) * k.F + fidx[j];
+#pragma unroll
+      for (int p = 0; p < RB_MAX_PEERS; ++p)
+        if (p < k.n_peer) k.peer_out[p][op] = total;
+    } else {
+      k.out_total[o] = total;
+    }
   }
   }  // trips
 }
@@ -811,7 +824,7 @@ int family_of(int form) {
 // d holds DEVICE pointers; freqs are also needed on the host for the class scan, so the caller
 // passes a host copy through ctx scratch (see capi.cu).
 int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_freqs, double* out_total,
-                    double* out_cube) {
+                    double* out_cube, int n_peer, double* const* peer_out, long long peer_row0) {
   AlphaK k{};
   k.L = d->n_layers; k.F = d->n_freqs; k.C = d->n_constituents;
   if (k.L <= 0 || k.F <= 0) return rb_fail(ctx, RB_ERR_INVALID, "alpha: n_layers and n_freqs must be positive");
@@ -830,6 +843,12 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   }
   k.cloud_flags = d->cloud_flags; k.h2state = d->h2state; k.coshape = d->coshape; k.units = d->units;
   k.scale = d->scale; k.out_total = out_total; k.out_cube = out_cube;
+  k.n_peer = 0; k.peer_row0 = peer_row0;
+  if (n_peer > 0) {
+    if (n_peer > RB_MAX_PEERS || !peer_out) return rb_fail(ctx, RB_ERR_INVALID, "alpha: 1..%d peer slabs", RB_MAX_PEERS);
+    k.n_peer = n_peer;
+    for (int p = 0; p < n_peer; ++p) k.peer_out[p] = peer_out[p];
+  }
   k.nh3_form = 0; k.slot_nh3 = k.slot_h2s = k.slot_ph3 = k.slot_h2o = k.slot_h2 = k.slot_cld = k.slot_co = -1;
   for (int c = 0; c < k.C; ++c) {
     const int fm = d->formalism[c];

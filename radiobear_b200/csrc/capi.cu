@@ -322,6 +322,25 @@ int rb_alpha_layers(rb_context* ctx, const rb_alpha_desc* d, double* out_total, 
   return alpha_layers_host(ctx, d, out_total, out_cube, false, false);
 }
 
+int rb_alpha_layers_dev_scatter(rb_context* ctx, const rb_alpha_desc* d, int32_t n_peers, const uint64_t* peer_slabs,
+                                int64_t first_row) {
+  static const double dummy = 0.0;
+  RB_TRY(check_alpha_desc(ctx, d, &dummy));
+  if (n_peers < 1 || n_peers > RB_MAX_PEERS || !peer_slabs || first_row < 0)
+    return rb_fail(ctx, RB_ERR_INVALID, "alpha scatter: 1..%d peer slabs, first_row >= 0", RB_MAX_PEERS);
+  RB_CUDA(ctx, cudaSetDevice(ctx->device));
+  double* peers[RB_MAX_PEERS];
+  for (int p = 0; p < n_peers; ++p) {
+    if (!peer_slabs[p]) return rb_fail(ctx, RB_ERR_INVALID, "alpha scatter: null peer slab %d", p);
+    peers[p] = (double*)(uintptr_t)peer_slabs[p];
+  }
+  if (d->freqs_host) return rb_launch_alpha(ctx, d, d->freqs_host, nullptr, nullptr, n_peers, peers, first_row);
+  std::vector<double> hf(d->n_freqs);
+  RB_CUDA(ctx, cudaMemcpyAsync(hf.data(), d->freqs, sizeof(double) * d->n_freqs, cudaMemcpyDeviceToHost, ctx->stream));
+  RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return rb_launch_alpha(ctx, d, hf.data(), nullptr, nullptr, n_peers, peers, first_row);
+}
+
 int rb_alpha_layers_resident(rb_context* ctx, const rb_alpha_desc* d, int32_t keep_cube, uint64_t* out_slab_generation,
                              uint64_t* out_cube_generation) {
   static const double dummy = 0.0;

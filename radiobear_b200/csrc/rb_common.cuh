@@ -98,6 +98,7 @@ enum {
 // The rays-major integration kernel prefetches whole 32-segment chunks of the ds slab and of the operand
 // slab without bounds checks (the rows it may over-read are never consumed); both buffers carry this slack.
 constexpr size_t kRtSlackBytes = 128 * 256;
+#define RB_MAX_PEERS 8   // GPUs of one NVSwitch domain a layer-sharded absorption run stores into
 // Compaction of the rays that hit the planet (ray_compact_kernel): within super-blocks of kSortBlock consecutive rays
 // the list is ordered by projected radius, so that the 32 rays of a tile (= the lanes of a warp of the layer march and
 // of the integration) have nearly the same path: they change phase and finish together.  A tile of the list may then
@@ -143,7 +144,7 @@ int rb_ensure(rb_context* ctx, int which, size_t bytes, void** out);
 // ---- kernel launchers implemented in the .cu files ---------------------------------------------
 // d holds DEVICE pointers; h_freqs is a host copy of d->freqs (frequency-class scan)
 int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_freqs, double* out_total,
-                    double* out_cube);
+                    double* out_cube, int n_peer = 0, double* const* peer_out = nullptr, long long peer_row0 = 0);
 
 int rb_launch_alpha_scale_sum(rb_context* ctx, const double* cube, const double* scale, int L, int F, int C,
                               double* total, double* out_cube);

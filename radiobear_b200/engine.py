@@ -245,8 +245,12 @@ def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formal
 
 def alpha_layers_dev(freqs_t, T_t, P_t, gas_t, gas_dict, cloud_t=None, cloud_dict=None, formalisms=(), other_dicts=None,
                      units='invcm', scale_t=None, want_cube=False, truncate_strength=None, truncate_freq=None, ctx=None,
-                     out=None, freqs_host=None):
-    """Device-resident variant: torch float64 CUDA tensors in, slab[L][F] CUDA tensor out (async)."""
+                     out=None, freqs_host=None, scatter=None):
+    """Device-resident variant: torch float64 CUDA tensors in, slab[L][F] CUDA tensor out (async).
+
+    scatter = (peer_ptrs, first_row): a layer-sharded run -- the inputs describe this rank's block of layers and the
+    kernel stores its values into rows first_row.. of the full slab on every GPU (device addresses `peer_ptrs`, e.g.
+    `torch.distributed._symmetric_memory` buffer_ptrs) instead of into `out`; returns None."""
     import torch
     ctx = ctx or _lib.get_context()
     L, F = T_t.shape[0], freqs_t.shape[0]
@@ -266,9 +270,14 @@ def alpha_layers_dev(freqs_t, T_t, P_t, gas_t, gas_dict, cloud_t=None, cloud_dic
     if freqs_host is not None:
         freqs_host = f64(freqs_host)
         d.freqs_host = ptr(freqs_host)
+    ctx.set_stream(torch.cuda.current_stream(T_t.device).cuda_stream)
+    if scatter is not None:
+        ptrs, first_row = scatter
+        arr = (C.c_uint64 * len(ptrs))(*[int(x) for x in ptrs])
+        ctx.check(ctx.lib.rb_alpha_layers_dev_scatter(ctx.h, C.byref(d), len(ptrs), arr, int(first_row)))
+        return None
     total = out if out is not None else torch.empty((L, F), dtype=torch.float64, device=T_t.device)
     cube = torch.empty((L, F, len(formalisms)), dtype=torch.float64, device=T_t.device) if want_cube else None
-    ctx.set_stream(torch.cuda.current_stream(T_t.device).cuda_stream)
     ctx.check(ctx.lib.rb_alpha_layers_dev(ctx.h, C.byref(d), total.data_ptr(), cube.data_ptr() if want_cube else None))
     return (total, cube) if want_cube else total
 

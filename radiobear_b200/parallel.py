@@ -158,6 +158,84 @@ def alpha_layers_sharded(compute_block, L, F, axis='layers', group=None):
     return full.cpu().numpy() if full.is_cuda else full.numpy()
 
 
+class SymmetricSlab:
+    """A [L][F] float64 slab that exists at the same place on every GPU of the process group and that every rank can
+    store into directly over NVLink (torch.distributed._symmetric_memory): the target of the in-kernel all_gather of
+    layer-sharded absorption runs (`engine.alpha_layers_dev(..., scatter=...)`).  `usable` is False when the symmetric
+    allocation or the rendezvous is not available (gloo, no peer access); callers then fall back to all_gather."""
+
+    def __init__(self, L, F, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.usable, self.tensor, self.handle, self.ptrs = False, None, None, None
+        self.shape = (int(L), int(F))
+        try:
+            import torch.distributed._symmetric_memory as symm
+            if dist.get_backend(group) != 'nccl':
+                return
+            grp = group if group is not None else dist.group.WORLD
+            self.tensor = symm.empty((int(L), int(F)), dtype=torch.float64, device=device)
+            self.handle = symm.rendezvous(self.tensor, grp)
+            self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            self.usable = len(self.ptrs) == dist.get_world_size(group) and all(self.ptrs)
+        except Exception as e:                                  # noqa: BLE001 -- any failure means "use the collective"
+            self.error = repr(e)
+            self.usable = False
+
+    def barrier(self):
+        """All ranks' stores into every copy of the slab are complete and visible (device-side barrier with system-scope
+        release / acquire on the current stream)."""
+        self.handle.barrier(channel=0)
+
+
+_SLABS = {}
+
+
+def symmetric_slab(L, F, device, group=None):
+    key = (int(L), int(F), str(device))
+    if key not in _SLABS:
+        _SLABS[key] = SymmetricSlab(L, F, device, group)
+    return _SLABS[key]
+
+
+def alpha_layers_scatter(freqs, T, P, gas, gas_dict, cloud, cloud_dict, formalisms, other_dicts, units, scale,
+                         truncate_strength, truncate_freq, group=None):
+    """Layer-sharded absorption with the all_gather inside the kernel: every rank computes its block of layers from
+    device-resident inputs and stores the values into the full [L][F] slab of every GPU over NVLink
+    (`SymmetricSlab`, `rb_alpha_layers_dev_scatter`); one device-side barrier, then the slab is copied to the host.
+    Returns the numpy [L][F] slab, or None when the ranks cannot set up the symmetric slab (the caller then uses
+    alpha_layers_sharded)."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    if dist.get_backend(group) != 'nccl' or not torch.cuda.is_available():
+        return None
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    L, F = len(T), len(freqs)
+    sym = symmetric_slab(L, F, dev, group)
+    ok = torch.tensor([1 if sym.usable else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        return None
+    lo, hi = partition_even(L, world)[rank]
+    t64 = dict(dtype=torch.float64, device=dev)
+    if hi > lo:
+        fr = np.ascontiguousarray(freqs, dtype=np.float64)
+        sm = engine.scale_matrix(slice_scale(scale, lo, hi), [c for c, _ in formalisms], hi - lo)
+        engine.alpha_layers_dev(
+            torch.tensor(fr, **t64), torch.tensor(np.ascontiguousarray(T[lo:hi]), **t64),
+            torch.tensor(np.ascontiguousarray(P[lo:hi]), **t64), torch.tensor(np.ascontiguousarray(gas[:, lo:hi]), **t64),
+            gas_dict, None if cloud is None else torch.tensor(np.ascontiguousarray(cloud[:, lo:hi]), **t64), cloud_dict,
+            formalisms=formalisms, other_dicts=other_dicts, units=units,
+            scale_t=None if sm is None else torch.tensor(np.ascontiguousarray(sm), **t64),
+            truncate_strength=truncate_strength, truncate_freq=truncate_freq, freqs_host=fr, scatter=(sym.ptrs, lo))
+    sym.barrier()                       # every rank's rows are in every copy
+    out = sym.tensor.cpu().numpy()
+    sym.barrier()                       # nobody overwrites a copy that is still being read
+    return out
+
+
 def slice_scale(scale, lo, hi):
     """The part of a `scale` request (number / per-layer list / dict of per-layer lists, alpha.py:235-259) that belongs
     to layers [lo, hi)."""

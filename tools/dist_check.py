@@ -33,6 +33,22 @@ def main():
             ok = ok and same
         else:
             ok = ok and rv.Tb is None
+    # absorption sharded by layer blocks (the all_gather inside the kernel over symmetric memory, else NCCL) and by
+    # frequency blocks against the replicated computation, with a per-constituent scale
+    from radiobear_b200.alpha import Alpha
+    from radiobear_b200 import parallel
+    L = atm.gas.shape[1]
+    sc = {'nh3': list(np.linspace(0.5, 1.5, L)), 'h2o': [2.0] * L}
+    ref = Alpha(config=atm.config, verbose=False, shard=False)
+    ref.get_layers(fl, atm, scale=sc)
+    for axis in ('layers', 'freqs'):
+        a = Alpha(config=atm.config, verbose=False, shard=True, shard_axis=axis)
+        a.get_layers(fl, atm, scale=sc)
+        same = np.array_equal(a.layers, ref.layers)
+        if rank == 0:
+            used = parallel.symmetric_slab(L, len(fl), torch.device('cuda', local)).usable if axis == 'layers' else False
+            print('alpha sharded by', axis, 'identical to the replicated slab:', same, '(in-kernel gather: {})'.format(used))
+        ok = ok and same
     flag = torch.tensor([1 if ok else 0], device='cuda')
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
