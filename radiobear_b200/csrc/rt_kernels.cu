@@ -806,6 +806,9 @@ struct RtK {
   RtProgress progress;    // optional per-chunk completion counters (rays-major kernel only)
   const double2* prep2;   // [F/16][L-1][8][3] pair operands (rt_integrate_pairs_kernel, see rt_prepare_pairs_kernel)
   unsigned fgroups, ntiles;  // rays-major launches are 1-D: block = tile * fgroups + frequency group
+  unsigned nparts;           // launch order: the tile list in nparts parts, inside a part frequency group by frequency
+                             // group (see rb_launch_integrate); 0: block = tile * fgroups + frequency group
+  unsigned tile_blocks;      // upper bound of the CTAs per frequency group (the grid holds nparts more per group)
   const int* cidx;        // compacted launch: list position -> ray index (null: ds / nseg / nanflag are per ray index)
   const int* ncomp;       // compacted launch: length of the list
   const double* ds;     // [S][Rpad]
@@ -1141,13 +1144,27 @@ __device__ __forceinline__ RayTile map_ray_tile(const RtK& k, unsigned tiles_per
   RayTile m;
   m.dead = false;
   m.first_r = m.last_r = 0;
-  const unsigned bcta = blockIdx.x / k.fgroups;
-  m.fg = blockIdx.x - bcta * k.fgroups;
+  unsigned bcta;
+  bool beyond = false;
+  if (k.nparts) {
+    // CTAs (tile blocks) that exist: known on the device only for a compacted launch
+    const unsigned nt = k.cidx ? ((unsigned)((*k.ncomp + 31) >> 5) + tiles_per_cta - 1) / tiles_per_cta : k.tile_blocks;
+    const unsigned cs = (nt + k.nparts - 1) / k.nparts;        // tile blocks per part
+    const unsigned per = cs * k.fgroups;
+    const unsigned part = per ? blockIdx.x / per : k.nparts;
+    const unsigned local = blockIdx.x - part * per;
+    m.fg = cs ? local / cs : 0;
+    bcta = part * cs + (local - m.fg * cs);
+    beyond = part >= k.nparts || bcta >= nt;
+  } else {
+    bcta = blockIdx.x / k.fgroups;
+    m.fg = blockIdx.x - bcta * k.fgroups;
+  }
   m.by = bcta * tiles_per_cta + sub;
   if (k.cidx) {
     const int nc = *k.ncomp;
     const unsigned ntile = (unsigned)((nc + 31) >> 5);
-    m.dead = m.by >= ntile;
+    m.dead = beyond || m.by >= ntile;
     unsigned tile = m.by + (k.progress.done ? (unsigned)k.ncomp[1] : 0u);
     if (tile >= ntile) tile -= ntile;
     m.tile = tile;
@@ -1161,7 +1178,7 @@ __device__ __forceinline__ RayTile map_ray_tile(const RtK& k, unsigned tiles_per
       m.last_r = (int)__reduce_max_sync(0xffffffffu, m.in ? (unsigned)m.r : 0u);
     }
   } else {
-    m.dead = m.by >= k.ntiles;
+    m.dead = beyond || m.by >= k.ntiles;
     unsigned tile = m.by + (unsigned)k.progress.shift;
     if (tile >= k.ntiles) tile -= k.ntiles;
     m.tile = tile;
@@ -2591,8 +2608,19 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     if (progress) k.progress = *progress;
     k.fgroups = (unsigned)prep.fgroups;
     k.ntiles = (unsigned)((g.R + 31) / 32);
-    const unsigned long long nblocks =
-        (unsigned long long)k.fgroups * (prep.tiles ? (k.ntiles + kPairWarps - 1) / kPairWarps : k.ntiles);
+    k.tile_blocks = prep.tiles ? (k.ntiles + kPairWarps - 1) / kPairWarps : k.ntiles;
+    // Launch order: frequency group by frequency group (the low-frequency groups integrate twice as many layers as
+    // the others: they go first, and the CTAs that are resident together do the same kind of work) instead of the
+    // frequency groups of a ray tile next to each other -- measured on C4: 3.10 -> 2.93 ms on one GPU, 0.48 -> 0.40 ms
+    // for a rank's share on eight, although every ds tile then comes from DRAM once per frequency group.  With the
+    // copy-out pipeline the tile list is cut into parts that are launched one after the other, so that the copy chunks
+    // still complete in order.  RB_RT_PARTS: 0 = the old order, n = n parts.
+    {
+      const char* e = getenv("RB_RT_PARTS");
+      k.nparts = e ? (unsigned)atoi(e) : (progress ? 12u : 1u);
+      if (k.nparts > k.tile_blocks) k.nparts = k.tile_blocks ? k.tile_blocks : 1u;
+    }
+    const unsigned long long nblocks = (unsigned long long)k.fgroups * (k.tile_blocks + k.nparts);
     if (nblocks > 2147483647ULL) return rb_fail(ctx, RB_ERR_INVALID, "rt: too many (ray tile, frequency group) blocks for one launch");
     dim3 block(32, prep.pairs ? kPairWarps : 8), grid((unsigned)nblocks);
     if (prep.mixed) {
