@@ -69,6 +69,7 @@ struct AlphaK {
   double* peer_out[RB_MAX_PEERS];
   int n_peer;
   long long peer_row0;
+  const int* order;   // launch order of the layers (alpha_order_kernel) or null: CTA y computes layer order[y]
   const double* cat[RB_NUM_CATALOGS];
   int ncat[RB_NUM_CATALOGS];
   // which families are present and the constituent slot each one fills (-1 = absent)
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, FPT >= 4 ? RB_ALPHA_FPT4_CTAS : 2) a
   extern __shared__ __align__(16) double smem[];
   __shared__ double s_pow[PW_COUNT];
 
-  const int l = blockIdx.y;
+  const int l = k.order ? k.order[blockIdx.y] : (int)blockIdx.y;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -805,6 +806,35 @@ __global__ void __launch_bounds__(kThreads, FPT >= 4 ? RB_ALPHA_FPT4_CTAS : 2) a
   }  // trips
 }
 
+// Launch order of the layers: the NH3 formalisms evaluate 1014 lines per frequency in the 400..2000 bar blend, 814
+// below it and 200 above, so the CTAs of a launch differ in length by a factor of five; longest first (a counting sort
+// of the layers by pressure class, layer order kept inside a class) leaves the short ones for the tail of the launch.
+__global__ void alpha_order_kernel(const double* __restrict__ P, int L, int* __restrict__ order) {
+  __shared__ int s_cnt[3], s_base[3];
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  auto cls = [](double p) { return (p >= 400.0 && p <= 2000.0) ? 0 : (p < 400.0 ? 1 : 2); };
+  for (int l = threadIdx.x; l < L; l += blockDim.x) atomicAdd(&s_cnt[cls(P[l])], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) { s_base[0] = 0; s_base[1] = s_cnt[0]; s_base[2] = s_cnt[0] + s_cnt[1]; }
+  __syncthreads();
+  // stable placement: thread t handles the contiguous layer range [t * per, (t + 1) * per)
+  const int per = (L + blockDim.x - 1) / blockDim.x;
+  const int l0 = threadIdx.x * per, l1 = min(L, l0 + per);
+  int mine[3] = {0, 0, 0};
+  for (int l = l0; l < l1; ++l) ++mine[cls(P[l])];
+  __shared__ int s_scan[3][1024];
+  for (int c = 0; c < 3; ++c) s_scan[c][threadIdx.x] = mine[c];
+  __syncthreads();
+  if (threadIdx.x < 3) {                                     // exclusive scan per class (1024 entries, once per launch)
+    int acc = s_base[threadIdx.x];
+    for (int t = 0; t < (int)blockDim.x; ++t) { const int v = s_scan[threadIdx.x][t]; s_scan[threadIdx.x][t] = acc; acc += v; }
+  }
+  __syncthreads();
+  int pos[3] = {s_scan[0][threadIdx.x], s_scan[1][threadIdx.x], s_scan[2][threadIdx.x]};
+  for (int l = l0; l < l1; ++l) order[pos[cls(P[l])]++] = l;
+}
+
 int family_of(int form) {
   switch (form) {
     case RB_F_NH3_HS: case RB_F_NH3_DBS: case RB_F_NH3_SJS: case RB_F_NH3_HS_SJS: case RB_F_NH3_DBS_SJS:
@@ -959,6 +989,14 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   RB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   dim3 grid(nblk_x, k.L);
   if (k.L > 65535) return rb_fail(ctx, RB_ERR_INVALID, "alpha: n_layers > 65535 not supported");
+  k.order = nullptr;
+  if (k.slot_nh3 >= 0 && k.L >= 2 * ctx->num_sms && !getenv("RB_ALPHA_NO_ORDER")) {
+    void* p_order;
+    RB_TRY(rb_ensure(ctx, RB_BUF_ORDER, (size_t)k.L * sizeof(int), &p_order));
+    alpha_order_kernel<<<1, 1024, 0, ctx->stream>>>(k.P, k.L, (int*)p_order);
+    ctx->launches += 1;
+    k.order = (const int*)p_order;
+  }
   RB_CUDA(ctx, rb_time_begin(ctx, 0));
   kern<<<grid, kThreads, smem_bytes, ctx->stream>>>(k);
   RB_CUDA(ctx, cudaGetLastError());
