@@ -45,10 +45,10 @@ UNIT = 'pixel*freq/s'
 # rt_integrate_pairs_kernel (two frequencies per thread), per executed (ray, freq, segment) step (DESIGN.md 3.3;
 # counted in the SASS of the two hot loops, profiles/r2_sass_rt_integrate_pairs.txt: 8 steps per trip):
 #   table phase      6.5 DFMA + 2 DMUL + 2 DADD = 10.5 FP64 instructions, 17 flops   (ds_i + ds_i+1 is shared by the pair)
-#   small-tau phase (tau < 2^-11)  4.5 DFMA + 1 DMUL + 1 DADD = 6.5 FP64 instructions, 11 flops
+#   small-tau phase (tau < 2^-11)  4 DFMA + 1 DMUL + 1.5 DADD = 6.5 FP64 instructions, 10.5 flops
 RT_FLOPS_PER_STEP = 17.0
 RT_FP64_INSTR_PER_STEP = 10.5
-RT_FLOPS_PER_SMALL_STEP = 11.0
+RT_FLOPS_PER_SMALL_STEP = 10.5
 RT_FP64_INSTR_PER_SMALL_STEP = 6.5
 # dram__bytes_read.sum + dram__bytes_write.sum of one rt_integrate_pairs_kernel launch of this workload at N=1
 RT_DRAM_BYTES_N1 = 1008942848
