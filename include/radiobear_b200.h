@@ -86,6 +86,15 @@ int rb_get_rt_precision(const rb_context* ctx);
  *             Environment: RB_RT_COMPACT.
  * Kept as a call for A/B measurements and for the tests that compare the decompositions. */
 int rb_set_rt_tuning(rb_context* ctx, int pairs, int compact);
+/* Streamed ray trace (results do not depend on it).  A geometry started ahead of its consumer with
+ * rb_geometry_prefetch[_dev] can publish its progress per (tile of 32 rays, chunk of 32 segments); the FP64 pair
+ * integration of the following rb_rt_batch* call then starts as soon as the list of hitting rays exists and follows the
+ * running trace chunk by chunk instead of waiting for its end.  The trace is a chain of ~1000 dependent steps per ray
+ * however few rays there are, so this pays for small requests (a rank's rows of an image shared by several GPUs).
+ *   mode : 1 = always, 0 = never, -1 = automatic (requests of at most 200 000 rays).
+ * Environment: RB_RT_STREAM_GEOMETRY = 0 / 1.  Replaces nothing in the reference (raypath.py:108-273 and
+ * brightness.py:30-126 run one after the other there). */
+int rb_set_rt_stream_geometry(rb_context* ctx, int mode);
 /* Measurement aid: count the (ray, freq, segment) steps the integration kernel actually executes (the
  * tau_cut early exit skips the rest).  enable = 1 resets and starts counting, 0 stops; the count is returned
  * (after synchronising the context stream). */

@@ -93,6 +93,7 @@ def load():
         'rb_set_rt_precision': (C.c_int, [vp, C.c_int]),
         'rb_get_rt_precision': (C.c_int, [vp]),
         'rb_set_rt_tuning': (C.c_int, [vp, C.c_int, C.c_int]),
+        'rb_set_rt_stream_geometry': (C.c_int, [vp, C.c_int]),
         'rb_count_steps': (i64, [vp, C.c_int]),
         'rb_count_small_steps': (i64, [vp]),
         'rb_set_catalog': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -128,7 +129,7 @@ def load():
 EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error', 'rb_set_stream', 'rb_use_own_stream',
                     'rb_synchronize',
                     'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_kernel_timed_count',
-                    'rb_set_rt_chunks', 'rb_set_rt_precision', 'rb_get_rt_precision', 'rb_set_rt_tuning', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
+                    'rb_set_rt_chunks', 'rb_set_rt_precision', 'rb_get_rt_precision', 'rb_set_rt_tuning', 'rb_set_rt_stream_geometry', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
                     'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_alpha_layers_dev_scatter', 'rb_alpha_layers_resident', 'rb_alpha_rescale_resident',
                     'rb_alpha_resident_info', 'rb_alpha_fetch', 'rb_rt_batch_resident', 'rb_compute_ds', 'rb_compute_ray_fields', 'rb_set_gravity_model', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
                     'rb_probe_fp64_peak', 'rb_probe_rcp', 'rb_probe_fp64_mix']
@@ -218,6 +219,11 @@ class Context:
         if precision not in RT_PRECISIONS:
             raise ValueError("rt precision must be one of {}".format(sorted(RT_PRECISIONS)))
         self.check(self.lib.rb_set_rt_precision(self.h, RT_PRECISIONS[precision]))
+
+    def set_rt_stream_geometry(self, mode=-1):
+        """Integration follows a prefetched trace that is still running: 1 always, 0 never, -1 automatic
+        (include/radiobear_b200.h: rb_set_rt_stream_geometry)."""
+        self.check(self.lib.rb_set_rt_stream_geometry(self.h, int(mode)))
 
     def set_rt_tuning(self, pairs=-1, compact=True):
         """Work decomposition of the FP64 ray integration (results are bit-identical): pairs -1 auto / 0 / 1,

@@ -104,6 +104,7 @@ void rb_destroy(rb_context* ctx) {
     if (ctx->grav.gamma) cudaFree(ctx->grav.gamma);
     if (ctx->step_counter_buf) cudaFree(ctx->step_counter_buf);
     if (ctx->ticket.done) cudaEventDestroy(ctx->ticket.done);
+    if (ctx->ticket.mid) cudaEventDestroy(ctx->ticket.mid);
     for (int i = 0; i < 3; ++i)
       for (int r = 0; r < rb_context::kEvRing; ++r)
         for (int j = 0; j < 2; ++j)
@@ -217,6 +218,13 @@ int rb_set_rt_tuning(rb_context* ctx, int pairs, int compact) {
   if (compact != ctx->rt_compact) drop_ticket(ctx);        // a prefetched geometry has the other indexing
   ctx->rt_pairs = pairs;
   ctx->rt_compact = compact;
+  return RB_OK;
+}
+
+int rb_set_rt_stream_geometry(rb_context* ctx, int mode) {
+  if (!ctx) return RB_ERR_INVALID;
+  if (mode < -1 || mode > 1) return rb_fail(ctx, RB_ERR_INVALID, "rt stream geometry: mode must be -1 / 0 / 1");
+  ctx->rt_stream = mode < 0 ? 2 : mode;
   return RB_OK;
 }
 
@@ -463,15 +471,33 @@ static bool same_geometry(const rb_geometry_desc& a, const rb_geometry_desc& b) 
 
 // true (and the ticket is consumed, ctx->stream made to wait for it) when the prefetched geometry is the one
 // this call needs; any other state drops the ticket: the caller is about to overwrite the ds buffers
-static bool take_ticket(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const void* b) {
+// (streamed: a hit on a trace that publishes its progress is NOT waited for here -- the caller decides with
+//  join_streamed_ticket whether its integration can follow the running trace)
+static bool take_ticket(rb_context* ctx, const rb_geometry_desc* g, int64_t R, const void* b, bool* streamed = nullptr) {
   auto& t = ctx->ticket;
+  if (streamed) *streamed = false;
   if (!t.valid) return false;
   const bool hit = g && t.R == R && t.b == b && same_geometry(t.g, *g);
-  cudaStreamWaitEvent(ctx->stream, t.done, 0);   // hit: the geometry is ready; miss: it no longer writes the buffers
   t.valid = false;
+  if (hit && t.streamed && streamed) { *streamed = true; return true; }
+  cudaStreamWaitEvent(ctx->stream, t.done, 0);   // hit: the geometry is ready; miss: it no longer writes the buffers
   return hit;
 }
 static void drop_ticket(rb_context* ctx) { take_ticket(ctx, nullptr, -1, nullptr); }
+
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWaitValue32Fn stream_wait_value();
+// follow == true: ctx->stream continues once the list of hitting rays exists and every CTA of the trace has started
+// (the integration then waits chunk by chunk on the device: RtLaunch::prog); false: once the trace has ended
+static int join_streamed_ticket(rb_context* ctx, bool follow) {
+  auto& t = ctx->ticket;
+  if (!follow) { RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, t.done, 0)); return RB_OK; }
+  RB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, t.mid, 0));
+  if (stream_wait_value()((CUstream)ctx->stream, (CUdeviceptr)(uintptr_t)t.started, t.started_target,
+                          CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+    return rb_fail(ctx, RB_ERR_CUDA, "rt: cuStreamWaitValue32 failed");
+  return RB_OK;
+}
 
 // The ds buffer of a ray request: the tiled FP64 slab, followed -- when the context integrates in mixed
 // precision -- by the float slab of the same tiling (each with its over-read slack).
@@ -492,6 +518,16 @@ static void bind_ds(const rb_context* ctx, RtLaunch& L, void* p_ds, void* p_n) {
 // rb_set_rt_tuning / RB_RT_COMPACT=0 switch it off (A/B measurements, tests of the plain path).
 static bool want_compact(const rb_context* ctx, int64_t R) {
   return ctx->rt_compact == 1 && R >= 512 && R < 2000000000LL && ctx->rt_precision == RB_RT_F64;
+}
+// RB_RT_STREAM_GEOMETRY=0/1 (default: requests of at most kStreamMaxRays rays)
+constexpr int64_t kStreamMaxRays = 200000;
+static bool want_stream(rb_context* ctx, int64_t R) {
+  if (ctx->rt_stream < 0) {
+    const char* e = getenv("RB_RT_STREAM_GEOMETRY");
+    ctx->rt_stream = e ? (atoi(e) ? 1 : 0) : 2;
+  }
+  if (ctx->rt_precision != RB_RT_F64 || ctx->rt_tiles) return false;
+  return ctx->rt_stream == 1 || (ctx->rt_stream == 2 && R <= kStreamMaxRays);
 }
 static int bind_compact(rb_context* ctx, RtLaunch& L) {
   L.compact = want_compact(ctx, L.R) && L.gtype != RB_GTYPE_GRAVITY;   // the gravity march walks the plain ray order
@@ -547,6 +583,21 @@ static int geometry_prefetch(rb_context* ctx, const rb_geometry_desc* g, int64_t
   }
   bind_ds(ctx, L, p_ds, p_n);
   RB_TRY(bind_compact(ctx, L));
+  // Small requests (a rank's rows of an image shared by 4 or 8 GPUs): the trace is a chain of ~1000 dependent steps
+  // per ray whatever the number of rays, so let the integration start behind it (RtLaunch::prog)
+  t.streamed = false;
+  if (L.compact && want_stream(ctx, R) && stream_wait_value()) {
+    const size_t npub = (S + kGeoPub - 1) / kGeoPub, nprog = (size_t)(L.Rpad / 32) * npub;
+    void* p_g;
+    RB_TRY(rb_ensure(ctx, RB_BUF_PROG, (nprog + 1) * sizeof(int), &p_g));
+    if (!t.mid) RB_CUDA(ctx, cudaEventCreateWithFlags(&t.mid, cudaEventDisableTiming));
+    L.prog = (int32_t*)p_g;
+    L.mid_event = t.mid;
+    t.streamed = true;
+    t.prog = L.prog;
+    t.started = L.prog + nprog;
+    t.started_target = (unsigned)((R + 127) / 128);          // CTAs of ray_geometry_kernel
+  }
   ctx->stream = sG;
   const int status = rb_launch_geometry(ctx, L);
   ctx->stream = user;
@@ -682,7 +733,6 @@ static bool tracing() { static int t = -1; if (t < 0) t = getenv("RB_TRACE") ? 1
 #define RB_TRACE_AT(label) do { if (tracing()) fprintf(stderr, "[rb_trace] %-28s %.3f ms\n", label, now_ms() - trace_t0); } while (0)
 
 // cuStreamWaitValue32 through the runtime's driver entry point lookup (the library links no libcuda)
-typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 static StreamWaitValue32Fn stream_wait_value() {
   static StreamWaitValue32Fn fn = nullptr;
   static bool looked = false;
@@ -724,12 +774,21 @@ static int choose_chunks(const rb_context* ctx, int64_t R, bool rays_path, bool 
 }
 
 static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full_in, const rb_rt_desc* rd, void* d_out, double* d_intW,
-                           void* h_out, double* h_intW, bool have_geometry) {
+                           void* h_out, double* h_intW, bool have_geometry, bool streamed) {
   RtLaunch full = full_in;
   const int64_t R = full.R;
   const size_t S = full.L - 1, F = rd->n_freqs, esz = rd->out_f32 ? 4 : 8;
   RtPrep prep;
   RB_TRY(rb_rt_prepare(ctx, full.L, rd, R, false, full.dsf != nullptr, &prep));
+  // a prefetched trace that publishes its progress: the FP64 pair kernel can follow it while it runs; every other
+  // consumer waits for its end
+  const bool follow = streamed && full.compact && prep.use_rays && prep.pairs && !prep.tiles;
+  if (streamed) RB_TRY(join_streamed_ticket(ctx, follow));
+  if (follow) full.prog = ctx->ticket.prog;
+  struct Rejoin {   // whatever follows on the context stream comes after the end of the trace
+    rb_context* c; bool on;
+    ~Rejoin() { if (on) cudaStreamWaitEvent(c->stream, c->ticket.done, 0); }
+  } rejoin{ctx, follow};
   if (full.compact && !prep.use_rays) {
     // a disc-averaged request over >= 512 rays: the lanes = frequency kernel walks the plain ray order
     full.compact = false;
@@ -862,8 +921,9 @@ int rb_rt_batch_dev(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc
   L.radius = g->radius; L.b = b;
   bind_ds(ctx, L, p_ds, p_n);
   RB_TRY(bind_compact(ctx, L));
-  const bool have_geometry = take_ticket(ctx, g, R, b);
-  return run_rt_pipeline(ctx, L, rt, out_Tb, out_intW, nullptr, nullptr, have_geometry);
+  bool streamed;
+  const bool have_geometry = take_ticket(ctx, g, R, b, &streamed);
+  return run_rt_pipeline(ctx, L, rt, out_Tb, out_intW, nullptr, nullptr, have_geometry, streamed);
 }
 
 static int rt_batch_host(rb_context* ctx, const rb_geometry_desc* g, const rb_rt_desc* rt, int64_t R, const double* b,
@@ -899,7 +959,8 @@ static int rt_batch_host(rb_context* ctx, const rb_geometry_desc* g, const rb_rt
   if (out_intW) RB_TRY(rb_ensure(ctx, RB_BUF_INTW, (size_t)R * F * 8, &p_iw));
   cudaStream_t s = ctx->stream;
   const double trace_t0 = now_ms();
-  const bool have_geometry = take_ticket(ctx, g, R, b);      // radius and b were staged by the prefetch
+  bool streamed;
+  const bool have_geometry = take_ticket(ctx, g, R, b, &streamed);   // radius and b were staged by the prefetch
   if (!have_geometry) {
     RB_CUDA(ctx, cudaMemcpyAsync(p_rad, g->radius, nL * 8, cudaMemcpyHostToDevice, s));
     RB_CUDA(ctx, cudaMemcpyAsync(p_b, b, (size_t)R * 16, cudaMemcpyHostToDevice, s));
@@ -912,7 +973,7 @@ static int rt_batch_host(rb_context* ctx, const rb_geometry_desc* g, const rb_rt
   RB_TRY(bind_compact(ctx, L));
   rb_rt_desc rd = *rt;
   rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
-  RB_TRY(run_rt_pipeline(ctx, L, &rd, p_tb, (double*)p_iw, out_Tb, out_intW, have_geometry));
+  RB_TRY(run_rt_pipeline(ctx, L, &rd, p_tb, (double*)p_iw, out_Tb, out_intW, have_geometry, streamed));
   RB_TRACE_AT("pipeline enqueued");
   if (profile_ray >= 0) {
     // re-run the selected ray alone with the profile-writing variant (Brightness.tau/.W/.Tb_lyr)

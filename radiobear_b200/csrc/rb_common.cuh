@@ -42,8 +42,9 @@ struct rb_context {
   int rt_precision = 0;  // RB_RT_F64 / RB_RT_MIXED: arithmetic of the rays-major integration (rb_set_rt_precision)
   int rt_pairs = -1;     // rb_set_rt_tuning: two frequencies per thread (-1 automatic)
   int rt_compact = 1;    // rb_set_rt_tuning: integrate the compacted list of rays that hit the planet
+  int rt_stream = -1;    // RB_RT_STREAM_GEOMETRY: integrate behind a trace that is still running (-1: small requests)
   int rt_tiles = 0;      // RB_RT_TILES: pair kernel with one frequency pair x four ray tiles per CTA (0: four pairs x one tile)
-  bool smem_opted[4] = {false, false, false, false};  // kernels opted into > 48 KB of dynamic shared memory
+  bool smem_opted[5] = {false, false, false, false, false};  // kernels opted into > 48 KB of dynamic shared memory
   int alpha_newton = -1; // Newton steps of the line reciprocal (RB_RCP_NEWTON), read once per context
   unsigned long long* step_counter = nullptr;  // device counters of integrated segment-steps (measurement aid)
   unsigned long long* step_counter_buf = nullptr;  // their allocation (rb_count_steps)
@@ -55,6 +56,11 @@ struct rb_context {
     const void* b = nullptr;
     rb_geometry_desc g{};
     cudaEvent_t done = nullptr;
+    cudaEvent_t mid = nullptr;     // list of hitting rays and progress counters are ready, the trace starts
+    bool streamed = false;         // the trace publishes its progress (RtLaunch::prog)
+    int32_t* prog = nullptr;       // its progress counters, the counter of started CTAs and that counter's final value
+    int32_t* started = nullptr;
+    unsigned started_target = 0;
   } ticket;
   // device-resident absorption (rb_alpha_layers_resident / rb_alpha_rescale_resident): the slab and the
   // per-constituent cube stay in RB_BUF_RES_TOTAL / RB_BUF_RES_CUBE between calls; generations count overwrites
@@ -92,7 +98,7 @@ inline cudaError_t rb_time_end(rb_context* ctx, int which) {
 enum {
   RB_BUF_FREQS = 0, RB_BUF_T, RB_BUF_P, RB_BUF_GAS, RB_BUF_CLOUD, RB_BUF_SCALE, RB_BUF_TOTAL, RB_BUF_CUBE,
   RB_BUF_RADIUS, RB_BUF_B, RB_BUF_DS, RB_BUF_NSEG, RB_BUF_TB, RB_BUF_INTW, RB_BUF_PROFILE, RB_BUF_MISC, RB_BUF_PREP,
-  RB_BUF_FLAGS, RB_BUF_CIDX, RB_BUF_ZQ, RB_BUF_BLKCNT, RB_BUF_DR2, RB_BUF_RES_TOTAL, RB_BUF_RES_CUBE, RB_BUF_ORDER
+  RB_BUF_FLAGS, RB_BUF_CIDX, RB_BUF_ZQ, RB_BUF_BLKCNT, RB_BUF_DR2, RB_BUF_RES_TOTAL, RB_BUF_RES_CUBE, RB_BUF_ORDER, RB_BUF_PROG
 };
 
 // The rays-major integration kernel prefetches whole 32-segment chunks of the ds slab and of the operand
@@ -172,7 +178,12 @@ struct RtLaunch {
   int32_t* ncomp;   // device scalar: length of the list
   double* zq;       // device [R]: findEdge depth per ray, NaN = misses the planet
   int32_t* blkcnt;  // device [ceil(R / 256)]
+  // streamed geometry (see rt_kernels.cu, "streamed geometry"): per (tile of the list, chunk of 32 segments) the number
+  // of rays whose trace has passed the chunk; the integration starts while the trace is still running
+  int32_t* prog;    // device [Rpad / 32][kGeoPubChunksMax] or null
+  cudaEvent_t mid_event;   // recorded on the launching stream right before ray_geometry_kernel (or null)
 };
+constexpr int kGeoPub = 32;             // segments per published chunk (= the staging chunk of the pair kernel)
 int rb_launch_geometry(rb_context* ctx, const RtLaunch& g);
 int rb_launch_gravity_geometry(rb_context* ctx, const RtLaunch& g, double* out_fields);
 int rb_build_geoid_table(rb_context* ctx, int L, int K, int nJ, int nvw, const double* d_radius, const double* d_GM,

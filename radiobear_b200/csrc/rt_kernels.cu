@@ -50,6 +50,13 @@ struct GeoK {
   double* zq;    // [R] edge depth found by findEdge, NaN for a ray that misses
   int* blkcnt;   // [ceil(R / kEdgeThreads)] hits per block of rays
   const double* dr2;  // [L-1] R_l+1^2 - R_l^2 (layer_dr2_kernel)
+  // Streamed geometry: the integration of a tile may start while its rays are still being traced.  Every ray counts
+  // itself into prog[tile][c] once its rows 0 .. 32 (c + 1) are in global memory (fence, then a relaxed atomic); the
+  // integration CTA waits (one thread, acquire load) until all rays of its tile have counted before it copies chunk c.
+  // A ray that ends counts into all remaining chunks.  In this mode the rows from the last used segment on are written
+  // as 0 (the integration walks all S - 1 steps: it does not know the segment count before the trace has ended).
+  int* prog;          // [tiles][npub] or null
+  int npub;           // chunks per tile
 };
 
 __device__ __forceinline__ void rot2planet(const GeoK& g, double x, double y, double z, double& ox, double& oy,
@@ -235,6 +242,10 @@ __global__ void __launch_bounds__(kSortThreads) ray_compact_kernel(const __grid_
 //  restart arithmetic, and 743 rays of the C4 image differed in the last bits of ds)
 __global__ void __launch_bounds__(128, RB_GEO_CTAS) ray_geometry_kernel(const __grid_constant__ GeoK g) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // streamed trace: count the CTAs that have started.  The integration that waits on g.prog is released (stream
+  // memory operation on this counter) only when every CTA of the trace is resident or done, so that its waiting CTAs
+  // can never keep a CTA of the trace off the machine.
+  if (g.prog && threadIdx.x == 0) atomicAdd(g.prog + (size_t)(g.Rpad / 32) * g.npub, 1);
   const int S = g.L - 1;
   const bool COMPACT = g.cidx != nullptr;
   long long r = t;
@@ -336,7 +347,13 @@ __global__ void __launch_bounds__(128, RB_GEO_CTAS) ray_geometry_kernel(const __
   double shape2 = shape * shape;
   bool outward = !(rd0 < 0.0);                               // only possible after a reflection (below)
   int cool = 0;                                              // careful steps to take before speculating again
+  int pubc = 0;                                              // streamed geometry: chunks published so far
   while (layer < S) {
+    if (g.prog && layer >= (pubc + 1) * kGeoPub + 1) {       // rows 0 .. 32 (pubc + 1) are written
+      __threadfence();
+      atomicAdd(g.prog + (size_t)(t >> 5) * g.npub + pubc, 1);
+      ++pubc;
+    }
     // Speculative block of kSpec segments: the plain recurrence with every exceptional condition (ray leaves,
     // NaN below the tangent shell, y == 0, grazing incidence) folded into one flag that nothing waits for until
     // the end of the block -- no branch sits between two segments of the chain.  A flagged block is discarded
@@ -449,6 +466,14 @@ __global__ void __launch_bounds__(128, RB_GEO_CTAS) ray_geometry_kernel(const __
   if (outf && count >= 1) outf[(size_t)(count - 1) * kDsStride] = 0.0f;
   // Brightness.single uses ds[0 .. n-2] (brightness.py:65); a NaN there makes every frequency NaN
   g.nanflag[o] = (first_nan >= 0 && first_nan <= count - 2) ? 1 : 0;
+  if (g.prog) {
+    // nothing lies below the last used segment: zeros from row count - 1 on (a NaN ray keeps its NaN rows), then the
+    // ray counts into every chunk it has not published yet
+    if (first_nan < 0)
+      for (int l = max(count - 1, 0); l < S; ++l) out[(size_t)l * kDsStride] = 0.0;
+    __threadfence();
+    for (; pubc < g.npub; ++pubc) atomicAdd(g.prog + (size_t)(t >> 5) * g.npub + pubc, 1);
+  }
 }
 
 // ---- descriptive ray fields of the compute_ds API (Ray.r4ds, and the latitude / longitude Ray.doppler is made of) ---
@@ -806,6 +831,8 @@ struct RtK {
   RtProgress progress;    // optional per-chunk completion counters (rays-major kernel only)
   const double2* prep2;   // [F/16][L-1][8][3] pair operands (rt_integrate_pairs_kernel, see rt_prepare_pairs_kernel)
   unsigned fgroups, ntiles;  // rays-major launches are 1-D: block = tile * fgroups + frequency group
+  const int* geo_prog;       // streamed geometry: [tiles][geo_npub] rays past each chunk (see GeoK::prog), or null
+  int geo_npub;
   unsigned nparts;           // launch order: the tile list in nparts parts, inside a part frequency group by frequency
                              // group (see rb_launch_integrate); 0: block = tile * fgroups + frequency group
   unsigned tile_blocks;      // upper bound of the CTAs per frequency group (the grid holds nparts more per group)
@@ -1667,7 +1694,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 }
 #endif
 
-template <bool TILES>
+template <bool TILES, bool STREAM = false>
 __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_kernel(const __grid_constant__ RtK k) {
   static_assert(!(TILES && RB_RT_RING), "the tiles decomposition stages with cp.async");
   // TILES = false: the CTA's warps are kPairWarps frequency pairs on one ray tile (shared staging buffers);
@@ -1692,9 +1719,24 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
   const long long r = rt_.r;
   const int fA = rt_.fg * (2 * kRowPairs) + 2 * (TILES ? 0 : (int)threadIdx.y);
   const bool validA = rt_.in && (fA < k.F), validB = rt_.in && (fA + 1 < k.F);
-  const int n = validA ? k.nseg[tpos] : -1;
-  const bool nanray = validA && k.nanflag[tpos] != 0;
+  // Streamed geometry (GeoK::prog): the trace of this tile may still be running.  Segment count and NaN flag are read
+  // at the end; until then every ray walks all S - 1 steps (the trace writes zeros from the last used segment on)
+  // and chunk c of the tile is copied only after all its rays have counted themselves past it.
+  constexpr bool streamed = !TILES && STREAM;
+  int n = validA ? (streamed ? S : k.nseg[tpos]) : -1;
+  bool nanray = validA && !streamed && k.nanflag[tpos] != 0;
   const int steps = (validA && !nanray) ? n - 1 : 0;        // brightness.py:65: i = 0 .. len(ds)-2
+  auto geo_wait = [&](int c) {                               // one thread: chunk c of this tile is complete
+    if (c >= k.geo_npub) return;
+    const int geo_lanes = min(32, *k.ncomp - (int)tile * 32);
+    const int* p = k.geo_prog + (size_t)tile * k.geo_npub + c;
+    int v;
+    unsigned spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+      if (++spins > (1u << 26)) __trap();                    // a trace that never comes: fail, do not hang
+    } while (v < geo_lanes);
+  };
 
   // bit 0: frequency a is live, bit 1: frequency b (a ghost b beyond F rides along with zero operands)
   int mode = (steps > 0) ? 3 : 0;
@@ -1778,6 +1820,7 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
       mode = 0;
     }
   } else {
+    if (streamed && tid == 0) geo_wait(0);
     any_live = __syncthreads_or(mode != 0);
     if (any_live) {
       for (int q = tid; q < kExpTabDoubles / 2; q += kPairThreads) cp_async16(s_tab + 2 * q, k.exp_tab + 2 * q);
@@ -1888,6 +1931,7 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
       __syncwarp();
       if (!__any_sync(0xffffffffu, mode != 0)) break;
     } else {
+      if (streamed && tid == 0) geo_wait(c + 1);             // the chunk about to be copied (the others wait at the barrier)
       if (!__syncthreads_or(mode != 0)) break;
     }
     issue(c + 1);
@@ -2059,6 +2103,13 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
   cp_async_wait<0>();
 #endif
   end_small();              // a ray that ended inside the small-tau phase
+  if (streamed) {
+    // the trace of the whole tile has ended (every ray counts into the last chunk when it ends): segment counts and
+    // NaN flags are final
+    if (tid == 0) geo_wait(k.geo_npub - 1);
+    __syncthreads();
+    if (validA) { n = k.nseg[tpos]; nanray = k.nanflag[tpos] != 0; }
+  }
   if (k.step_counter) {   // measurement aid (bench.py): executed (ray, freq, segment) steps, one atomic per warp
     unsigned long long done = 2ull * (unsigned long long)nf + (unsigned long long)ns;
     unsigned long long done_a = (unsigned long long)ia;
@@ -2415,6 +2466,12 @@ int rb_launch_geometry(rb_context* ctx, const RtLaunch& g) {
     ray_edge_kernel<<<eblocks, kEdgeThreads, 0, ctx->stream>>>(k);
     ray_compact_kernel<<<(unsigned)((g.R + kSortBlock - 1) / kSortBlock), kSortThreads, 0, ctx->stream>>>(k);
     ctx->launches += 2;
+    if (g.prog) {
+      k.prog = g.prog;
+      k.npub = (g.L - 1 + kGeoPub - 1) / kGeoPub;
+      RB_CUDA(ctx, cudaMemsetAsync(g.prog, 0, ((size_t)(g.Rpad / 32) * k.npub + 1) * sizeof(int), ctx->stream));
+    }
+    if (g.mid_event) RB_CUDA(ctx, cudaEventRecord(g.mid_event, ctx->stream));
   }
   ray_geometry_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(k);
   RB_CUDA(ctx, cudaGetLastError());
@@ -2638,6 +2695,12 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
       // sky pixels first: the compacted launch never visits them (the copy-out pipeline has filled them already,
       // before its copy stream was released: rb_launch_fill_miss)
       k.cidx = g.cidx; k.ncomp = g.ncomp;
+      if (g.prog && prep.pairs && !prep.tiles && !RB_RT_RING && kPChunk == kGeoPub) {
+        k.geo_prog = g.prog;
+        k.geo_npub = (k.L - 1 + kGeoPub - 1) / kGeoPub;
+      } else if (g.prog) {
+        return rb_fail(ctx, RB_ERR_INVALID, "rt: a streamed trace needs the FP64 pair kernel");
+      }
       if (!progress) RB_TRY(rb_launch_fill_miss(ctx, g, k.F, out_Tb, out_intW, k.out_f32));
     }
     k.exp_tab = ctx->exp_tab;
@@ -2653,8 +2716,13 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
       k.prep2 = (const double2*)prep.prep;
       constexpr size_t smem = kExpTabDoubles * sizeof(double) + kPairsSmemBytes;
       static_assert(smem <= 227 * 1024, "shared memory limit");
-      RB_TRY(opt_in_smem(ctx, rt_integrate_pairs_kernel<false>, smem, 1));
-      rt_integrate_pairs_kernel<false><<<grid, block, smem, ctx->stream>>>(k);
+      if (k.geo_prog) {
+        RB_TRY(opt_in_smem(ctx, rt_integrate_pairs_kernel<false, true>, smem, 4));
+        rt_integrate_pairs_kernel<false, true><<<grid, block, smem, ctx->stream>>>(k);
+      } else {
+        RB_TRY(opt_in_smem(ctx, rt_integrate_pairs_kernel<false>, smem, 1));
+        rt_integrate_pairs_kernel<false><<<grid, block, smem, ctx->stream>>>(k);
+      }
     } else {
       k.prep = (const double4*)prep.prep;
       constexpr size_t smem = kExpTabDoubles * sizeof(double) + kRaysSmemBytes;

@@ -38,6 +38,12 @@ def set_rt_tuning(pairs=-1, compact=True, ctx=None):
     (ctx or _lib.get_context()).set_rt_tuning(pairs, compact)
 
 
+def set_rt_stream_geometry(mode=-1, ctx=None):
+    """Let the integration of rt_batch follow a prefetched ray trace while it is still running
+    (rb_set_rt_stream_geometry): 1 always, 0 never, -1 automatic (small requests).  Results do not depend on it."""
+    (ctx or _lib.get_context()).set_rt_stream_geometry(mode)
+
+
 UNITS = {'invcm': 0, 'dBperkm': 1}
 COSHAPE = {'voigt': 0, 'vvw': 1, 'diff': 2}
 

@@ -233,3 +233,42 @@ def test_degenerate_ray_lists(eng, c4):
     f32 = eng.rt_batch(b=pts, alpha_slab=slab, T=T, out_f32=True, **geom(a))['Tb']
     big = eng.rt_batch(b=pts, alpha_slab=slab, T=T, **geom(a))['Tb']
     assert np.array_equal(f32, big.astype(np.float32), equal_nan=True)
+
+
+def test_integration_follows_a_running_trace(eng, c4):
+    """rb_set_rt_stream_geometry: the pair kernel starts behind a prefetched trace that still runs and waits chunk by
+    chunk on the trace's progress counters.  Same bits as the trace-then-integrate order: image rows with sky, NaN limb
+    ring and the disc centre; ragged frequency counts; every consumer that cannot follow (one frequency: lanes =
+    frequency kernel, disc average, a request that misses the ticket) waits for the end of the trace."""
+    a, b, slab, T = c4['a'], c4['b'], c4['slab'], c4['T']
+    g = geom(a)
+    radius = np.ascontiguousarray(g.pop('radius'), dtype=np.float64)
+    pre = lambda pts: eng.geometry_prefetch(radius, g['refr_index'], pts, g['Req'], g['Rpol'], g['orientation'], g['gtype'], g['limb'])
+    rows = np.ascontiguousarray(b[601 * 270:601 * 330])           # 60 image rows through the centre: 36 060 rays
+    edge = np.ascontiguousarray(b[601 * 108:601 * 136])           # sky rows, then rows that graze the limb
+    try:
+        res = {}
+        for mode in (0, 1):
+            eng.set_rt_stream_geometry(mode)
+            out = []
+            for pts in (rows, edge):
+                pre(pts)
+                got = eng.rt_batch(radius=radius, b=pts, alpha_slab=slab, T=T, want_intW=True, **g)
+                out += [got['Tb'].copy(), got['integrated_W'].copy()]
+            for nf in (1, 2, 3, 17):
+                pre(edge)
+                out.append(eng.rt_batch(radius=radius, b=edge, alpha_slab=np.ascontiguousarray(slab[:, :nf]), T=T, **g)['Tb'].copy())
+            pre(rows)
+            out.append(eng.rt_batch(radius=radius, b=rows, alpha_slab=slab, T=T, out_f32=True, **g)['Tb'].copy())
+            pre(rows)                                              # ticket missed: other points
+            out.append(eng.rt_batch(radius=radius, b=edge, alpha_slab=slab, T=T, **g)['Tb'].copy())
+            pre(rows)                                              # followed twice in a row (counters are reset per trace)
+            out.append(eng.rt_batch(radius=radius, b=rows, alpha_slab=slab, T=T, tau_cut=0.3, **g)['Tb'].copy())
+            res[mode] = out
+        for x, y in zip(res[0], res[1]):
+            assert x.shape == y.shape and np.array_equal(x, y, equal_nan=True)
+        assert np.isnan(res[1][2]).any() and (res[1][2] == 2.725).any() and np.nanmax(res[1][0]) > 100.0
+        ref = c4['cube'].reshape(-1, 64)
+        assert np.array_equal(res[1][0], ref[601 * 270:601 * 330], equal_nan=True)
+    finally:
+        eng.set_rt_stream_geometry(-1)
