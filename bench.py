@@ -506,14 +506,40 @@ def run_gpu(args):
     orient = [float(cfg.orientation[0]), float(cfg.orientation[1])]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    # N > 1: the absorption slab is computed once per step by all ranks together -- every rank its block of layers,
+    # stored by the kernel into the [L][F] slab of every GPU over NVLink (symmetric memory), one device-side barrier --
+    # instead of N times redundantly.  Two slabs alternate so that a rank that runs ahead never overwrites the slab a
+    # slower rank still integrates with.  RB_BENCH_STEP_ALPHA=replicated keeps every rank computing all layers.
+    syms = None
+    if world > 1 and os.environ.get('RB_BENCH_STEP_ALPHA', 'sharded') == 'sharded':
+        syms = [parallel.SymmetricSlab(L, F, dev) for _ in range(2)]
+        ok = torch.tensor([1 if all(s.usable for s in syms) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            syms = None
+    if syms is not None:
+        lo, hi = parallel.partition_even(L, world)[rank]
+        T_blk, P_blk, gas_blk = T_t[lo:hi].contiguous(), P_t[lo:hi].contiguous(), gas_t[:, lo:hi].contiguous()
+    step_no = [0]
+
     def step():
         # geometry first, on the library's side stream: it does not depend on the absorption and overlaps it
         engine.geometry_prefetch_dev(radius_t, nidx[0], nidx[1], b_t, cfg.Req, cfg.Rpol, orient, cfg.gtype, cfg.limb, ctx=ctx)
-        engine.alpha_layers_dev(freqs_t, T_t, P_t, gas_t, cfg.C, formalisms=forms, other_dicts=other,
-                                truncate_strength=cfg.truncate_strength, out=slab_t, freqs_host=freqs, ctx=ctx)
-        engine.rt_batch_dev(radius_t, nidx[0], nidx[1], b_t, slab_t, T_t, cfg.Req, cfg.Rpol, orient, cfg.gtype, cfg.limb,
+        if syms is not None:
+            sym = syms[step_no[0] & 1]
+            step_no[0] += 1
+            engine.alpha_layers_dev(freqs_t, T_blk, P_blk, gas_blk, cfg.C, formalisms=forms, other_dicts=other,
+                                    truncate_strength=cfg.truncate_strength, freqs_host=freqs, ctx=ctx,
+                                    scatter=(sym.ptrs, lo))
+            sym.barrier()                   # every rank's layers are in every GPU's slab
+            slab = sym.tensor
+        else:
+            slab = slab_t
+            engine.alpha_layers_dev(freqs_t, T_t, P_t, gas_t, cfg.C, formalisms=forms, other_dicts=other,
+                                    truncate_strength=cfg.truncate_strength, out=slab_t, freqs_host=freqs, ctx=ctx)
+        engine.rt_batch_dev(radius_t, nidx[0], nidx[1], b_t, slab, T_t, cfg.Req, cfg.Rpol, orient, cfg.gtype, cfg.limb,
                             out_f32=True, tau_cut=engine.TAU_CUT, out=tb_t, ctx=ctx)
-        return tb_t                         # N > 1: the image stays row-sharded in HBM, no data-path collective
+        return tb_t                         # N > 1: the image stays row-sharded in HBM
 
     def barrier():
         if world > 1:
@@ -532,6 +558,10 @@ def run_gpu(args):
         dist.all_reduce(counts)
     n_on, n_nan, n_all = [int(x) for x in counts.tolist()]
 
+    sharding_note = ('image rows balanced by on-disc pixels; output stays row-sharded in HBM; ' +
+                     ('absorption: layer blocks, all_gather inside the kernel over NVLink (symmetric memory) + one device-side '
+                      'barrier per step; ' if syms is not None else 'absorption replicated on every rank (no collective); ') +
+                     'e2e: every rank copies its rows into one shared pinned host image')
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -705,7 +735,7 @@ def run_gpu(args):
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64' if precision == 'f64' else 'f64 optical depth + f32 weights (mixed)', 'data': 'synthetic image grid over the Jupiter default atmosphere fixture',
             'config': {'workload': WORKLOAD, 'pixels': 'on-disc', 'on_disc_pixels': n_on, 'nan_limb_pixels': n_nan,
-                       'all_pixels': n_all, 'layers': L, 'freqs': F, 'sharding': 'image rows balanced by on-disc pixels; output stays row-sharded in HBM (no collective); e2e: every rank copies its rows into one shared pinned host image',
+                       'all_pixels': n_all, 'layers': L, 'freqs': F, 'sharding': sharding_note,
                        'l2': 'flushed between timed steps (256 MiB write, untimed); ds slab (0.94 GB) exceeds L2',
                        'tb_dtype_out': 'f32', 'tau_cut': engine.TAU_CUT, 'rt_precision': precision,
                        **({'emulated_rank0_share_of_world': emulate} if emulate else {})},

@@ -809,29 +809,47 @@ __global__ void __launch_bounds__(kThreads, FPT >= 4 ? RB_ALPHA_FPT4_CTAS : 2) a
 // Launch order of the layers: the NH3 formalisms evaluate 1014 lines per frequency in the 400..2000 bar blend, 814
 // below it and 200 above, so the CTAs of a launch differ in length by a factor of five; longest first (a counting sort
 // of the layers by pressure class, layer order kept inside a class) leaves the short ones for the tail of the launch.
-__global__ void alpha_order_kernel(const double* __restrict__ P, int L, int* __restrict__ order) {
-  __shared__ int s_cnt[3], s_base[3];
-  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
+__global__ void __launch_bounds__(1024) alpha_order_kernel(const double* __restrict__ P, int L, int* __restrict__ order) {
   auto cls = [](double p) { return (p >= 400.0 && p <= 2000.0) ? 0 : (p < 400.0 ? 1 : 2); };
-  for (int l = threadIdx.x; l < L; l += blockDim.x) atomicAdd(&s_cnt[cls(P[l])], 1);
-  __syncthreads();
-  if (threadIdx.x == 0) { s_base[0] = 0; s_base[1] = s_cnt[0]; s_base[2] = s_cnt[0] + s_cnt[1]; }
-  __syncthreads();
-  // stable placement: thread t handles the contiguous layer range [t * per, (t + 1) * per)
+  // stable placement: thread t handles the contiguous layer range [t * per, (t + 1) * per); an exclusive scan of the
+  // per-thread class counts (warp shuffles, then the 32 warp totals) gives every thread its write positions
   const int per = (L + blockDim.x - 1) / blockDim.x;
-  const int l0 = threadIdx.x * per, l1 = min(L, l0 + per);
+  const int l0 = min(L, (int)threadIdx.x * per), l1 = min(L, l0 + per);
   int mine[3] = {0, 0, 0};
   for (int l = l0; l < l1; ++l) ++mine[cls(P[l])];
-  __shared__ int s_scan[3][1024];
-  for (int c = 0; c < 3; ++c) s_scan[c][threadIdx.x] = mine[c];
-  __syncthreads();
-  if (threadIdx.x < 3) {                                     // exclusive scan per class (1024 entries, once per launch)
-    int acc = s_base[threadIdx.x];
-    for (int t = 0; t < (int)blockDim.x; ++t) { const int v = s_scan[threadIdx.x][t]; s_scan[threadIdx.x][t] = acc; acc += v; }
+  __shared__ int s_warp[3][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  int incl[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    int v = mine[c];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += u;
+    }
+    incl[c] = v;
+    if (lane == 31) s_warp[c][warp] = v;
   }
   __syncthreads();
-  int pos[3] = {s_scan[0][threadIdx.x], s_scan[1][threadIdx.x], s_scan[2][threadIdx.x]};
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int v = lane < nwarps ? s_warp[c][lane] : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += u;
+      }
+      s_warp[c][lane] = v;                                   // inclusive over the warps
+    }
+  }
+  __syncthreads();
+  const int tot0 = s_warp[0][nwarps - 1], tot1 = s_warp[1][nwarps - 1];
+  const int base[3] = {0, tot0, tot0 + tot1};
+  int pos[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) pos[c] = base[c] + (warp ? s_warp[c][warp - 1] : 0) + incl[c] - mine[c];
   for (int l = l0; l < l1; ++l) order[pos[cls(P[l])]++] = l;
 }
 

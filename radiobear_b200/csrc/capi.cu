@@ -105,6 +105,7 @@ void rb_destroy(rb_context* ctx) {
     if (ctx->step_counter_buf) cudaFree(ctx->step_counter_buf);
     if (ctx->ticket.done) cudaEventDestroy(ctx->ticket.done);
     if (ctx->ticket.mid) cudaEventDestroy(ctx->ticket.mid);
+    for (auto e : ctx->fill_ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 3; ++i)
       for (int r = 0; r < rb_context::kEvRing; ++r)
         for (int j = 0; j < 2; ++j)
@@ -841,6 +842,7 @@ static int run_rt_pipeline(rb_context* ctx, const RtLaunch& full_in, const rb_rt
     }
     RB_CUDA(ctx, cudaEventRecord(ev[0], user));             // counters are set; the copy stream may start waiting
     RB_CUDA(ctx, cudaStreamWaitEvent(sC, ev[0], 0));
+    if (full.compact) RB_TRY(rb_join_fill_miss(ctx, sC));   // (the sky fill runs on its own stream)
     RB_TRY(rb_launch_integrate(ctx, full, rd, prep, &pg, d_out, d_intW, -1, nullptr, nullptr, nullptr));
     auto copy_tiles = [&](int64_t t0, int64_t t1) -> int {   // memory-order tiles [t0, t1)
       const int64_t r0 = t0 * 32, r1 = (t1 * 32 < R) ? t1 * 32 : R;

@@ -37,6 +37,7 @@ struct rb_context {
   int ev_slot = 0;  // slot of the launch being timed
   // ray-chunk pipeline (geometry of chunk c+1 overlaps integration of chunk c and the D2H of chunk c-1)
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fill_ev[2] = {nullptr, nullptr};   // fork / join of the sky fill (rb_launch_fill_miss)
   std::vector<cudaEvent_t> pipe_ev;
   int rt_chunks = 0;  // 0 = automatic
   int rt_precision = 0;  // RB_RT_F64 / RB_RT_MIXED: arithmetic of the rays-major integration (rb_set_rt_precision)
@@ -190,6 +191,7 @@ int rb_build_geoid_table(rb_context* ctx, int L, int K, int nJ, int nvw, const d
                          const double* d_Jn, const double* d_vwlat, const double* d_vwdat, double RJ, double omega_m,
                          double latstep);
 int rb_launch_fill_miss(rb_context* ctx, const RtLaunch& g, int F, void* out_Tb, double* out_intW, int out_f32);
+int rb_join_fill_miss(rb_context* ctx, cudaStream_t stream);
 int rb_launch_ray_fields(rb_context* ctx, const RtLaunch& g, double* out);
 int rb_launch_ds_transpose(rb_context* ctx, const RtLaunch& g, double* out_ds_raymajor /*[R][L-1] device*/);
 int rb_launch_ds_to_slab(rb_context* ctx, const double* ds_raymajor, int64_t R, int64_t Rpad, int S, const int* nseg,

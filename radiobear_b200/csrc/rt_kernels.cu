@@ -833,6 +833,7 @@ struct RtK {
   unsigned fgroups, ntiles;  // rays-major launches are 1-D: block = tile * fgroups + frequency group
   const int* geo_prog;       // streamed geometry: [tiles][geo_npub] rays past each chunk (see GeoK::prog), or null
   int geo_npub;
+  int fg_reverse;            // launch the frequency groups last to first (behind a running trace: rb_launch_integrate)
   unsigned nparts;           // launch order: the tile list in nparts parts, inside a part frequency group by frequency
                              // group (see rb_launch_integrate); 0: block = tile * fgroups + frequency group
   unsigned tile_blocks;      // upper bound of the CTAs per frequency group (the grid holds nparts more per group)
@@ -1182,6 +1183,7 @@ __device__ __forceinline__ RayTile map_ray_tile(const RtK& k, unsigned tiles_per
     const unsigned local = blockIdx.x - part * per;
     m.fg = cs ? local / cs : 0;
     bcta = part * cs + (local - m.fg * cs);
+    if (k.fg_reverse && m.fg < k.fgroups) m.fg = k.fgroups - 1 - m.fg;
     beyond = part >= k.nparts || bcta >= nt;
   } else {
     bcta = blockIdx.x / k.fgroups;
@@ -1285,6 +1287,29 @@ __global__ void rt_fill_miss_kernel(const double* __restrict__ zq, long long R, 
   if (out_f32) reinterpret_cast<float*>(out_Tb)[idx] = (float)kTcmb;
   else reinterpret_cast<double*>(out_Tb)[idx] = kTcmb;
   if (out_intW) out_intW[idx] = 0.0;
+}
+// the same with four frequencies per thread and 16-byte stores (F a multiple of 4, outputs 16-byte aligned)
+__global__ void rt_fill_miss4_kernel(const double* __restrict__ zq, long long R, int F4, void* out_Tb, double* out_intW,
+                                     int out_f32) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = R * F4;
+  if (idx >= n) return;
+  const long long r = n < 0x7fffffffLL ? (long long)((unsigned)idx / (unsigned)F4) : idx / F4;
+  const double z = zq[r];
+  if (z == z) return;
+  if (out_f32) {
+    const float t = (float)kTcmb;
+    reinterpret_cast<float4*>(out_Tb)[idx] = make_float4(t, t, t, t);
+  } else {
+    double2* o = reinterpret_cast<double2*>(out_Tb) + 2 * idx;
+    o[0] = make_double2(kTcmb, kTcmb);
+    o[1] = make_double2(kTcmb, kTcmb);
+  }
+  if (out_intW) {
+    double2* w = reinterpret_cast<double2*>(out_intW) + 2 * idx;
+    w[0] = make_double2(0.0, 0.0);
+    w[1] = make_double2(0.0, 0.0);
+  }
 }
 
 // thread = (ray, frequency); lanes = 32 consecutive rays; the CTA's 8 warps are the 8 frequencies of one
@@ -1726,16 +1751,22 @@ __global__ void __launch_bounds__(kPairThreads, RB_RTP_CTAS) rt_integrate_pairs_
   int n = validA ? (streamed ? S : k.nseg[tpos]) : -1;
   bool nanray = validA && !streamed && k.nanflag[tpos] != 0;
   const int steps = (validA && !nanray) ? n - 1 : 0;        // brightness.py:65: i = 0 .. len(ds)-2
+  bool geo_done = false;                                     // (thread 0) the trace of this tile has ended
   auto geo_wait = [&](int c) {                               // one thread: chunk c of this tile is complete
-    if (c >= k.geo_npub) return;
+    if (geo_done || c >= k.geo_npub) return;
     const int geo_lanes = min(32, *k.ncomp - (int)tile * 32);
-    const int* p = k.geo_prog + (size_t)tile * k.geo_npub + c;
+    const int* base = k.geo_prog + (size_t)tile * k.geo_npub;
     int v;
+    // every ray counts into the last chunk when its trace ends: once that counter is full nothing is left to wait
+    // for (the usual case for all but the first CTAs of a launch)
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(base + k.geo_npub - 1) : "memory");
+    if (v >= geo_lanes) { geo_done = true; return; }
     unsigned spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(base + c) : "memory");
+      if (v >= geo_lanes) break;
       if (++spins > (1u << 26)) __trap();                    // a trace that never comes: fail, do not hang
-    } while (v < geo_lanes);
+    }
   };
 
   // bit 0: frequency a is live, bit 1: frequency b (a ghost b beyond F rides along with zero operands)
@@ -2601,11 +2632,31 @@ int rb_launch_gravity_geometry(rb_context* ctx, const RtLaunch& g, double* out_f
   return RB_OK;
 }
 
+// The sky fill only needs the classification of the rays (zq) and touches no output element the integration writes:
+// it runs on a side stream beside the integration (memory-bound next to an FP64-bound kernel).  Whoever reads the
+// outputs waits with rb_join_fill_miss.
 int rb_launch_fill_miss(rb_context* ctx, const RtLaunch& g, int F, void* out_Tb, double* out_intW, int out_f32) {
+  if (!ctx->aux[1]) RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[1], cudaStreamNonBlocking));
+  for (auto& e : ctx->fill_ev)
+    if (!e) RB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaStream_t user = ctx->stream, side = ctx->aux[1];
+  RB_CUDA(ctx, cudaEventRecord(ctx->fill_ev[0], user));
+  RB_CUDA(ctx, cudaStreamWaitEvent(side, ctx->fill_ev[0], 0));
+  struct Restore { rb_context* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, user};
+  ctx->stream = side;
   const long long nout = (long long)g.R * F;
-  rt_fill_miss_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, ctx->stream>>>(g.zq, g.R, F, out_Tb, out_intW, out_f32);
+  const bool aligned = (((uintptr_t)out_Tb | (uintptr_t)out_intW) & 15) == 0;
+  if (F % 4 == 0 && aligned)
+    rt_fill_miss4_kernel<<<(unsigned)((nout / 4 + 255) / 256), 256, 0, ctx->stream>>>(g.zq, g.R, F / 4, out_Tb, out_intW, out_f32);
+  else
+    rt_fill_miss_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, ctx->stream>>>(g.zq, g.R, F, out_Tb, out_intW, out_f32);
   RB_CUDA(ctx, cudaGetLastError());
+  RB_CUDA(ctx, cudaEventRecord(ctx->fill_ev[1], side));
   ctx->launches += 1;
+  return RB_OK;
+}
+int rb_join_fill_miss(rb_context* ctx, cudaStream_t stream) {
+  RB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->fill_ev[1], 0));
   return RB_OK;
 }
 
@@ -2631,6 +2682,7 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
                         const RtProgress* progress, void* out_Tb,
                         double* out_intW, int64_t profile_ray, double* out_tau, double* out_W, double* out_Tblyr) {
   RtK k{};
+  bool fill_pending = false;
   k.L = g.L; k.F = rt->n_freqs; k.R = g.R; k.Rpad = g.Rpad;
   k.alpha = rt->alpha; k.T = rt->T; k.ds = g.ds; k.nseg = g.nseg; k.nanflag = g.nanflag;
   k.out_Tb = out_Tb; k.out_intW = out_intW; k.out_f32 = rt->out_f32; k.disc = rt->disc_average;
@@ -2698,10 +2750,16 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
       if (g.prog && prep.pairs && !prep.tiles && !RB_RT_RING && kPChunk == kGeoPub) {
         k.geo_prog = g.prog;
         k.geo_npub = (k.L - 1 + kGeoPub - 1) / kGeoPub;
+        // RB_RT_STREAM_ORDER=1 launches the frequency groups last to first (the high frequencies reach tau_cut in the
+        // upper half of the atmosphere: their CTAs need only the chunks the trace publishes first).  Measured on rank
+        // shares of C4 (1/8, 1/4, 1/2 of the image): 0.63 -> 0.70, 1.01 -> 1.09, 1.80 -> 1.89 ms -- the long
+        // low-frequency CTAs then form the tail of the launch, which costs more than the earlier start gains.
+        const char* e = getenv("RB_RT_STREAM_ORDER");
+        k.fg_reverse = e ? atoi(e) : 0;
       } else if (g.prog) {
         return rb_fail(ctx, RB_ERR_INVALID, "rt: a streamed trace needs the FP64 pair kernel");
       }
-      if (!progress) RB_TRY(rb_launch_fill_miss(ctx, g, k.F, out_Tb, out_intW, k.out_f32));
+      if (!progress) { RB_TRY(rb_launch_fill_miss(ctx, g, k.F, out_Tb, out_intW, k.out_f32)); fill_pending = true; }
     }
     k.exp_tab = ctx->exp_tab;
     if (prep.pairs && prep.tiles) {
@@ -2732,6 +2790,7 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     }
   }
   RB_CUDA(ctx, cudaGetLastError());
+  if (fill_pending) RB_TRY(rb_join_fill_miss(ctx, ctx->stream));
   RB_CUDA(ctx, rb_time_end(ctx, 2));
   ctx->launches += 1;
   return RB_OK;
