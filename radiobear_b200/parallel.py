@@ -23,9 +23,9 @@ def row_weights(grid, q, floor=1.0):
     return w + floor
 
 
-def partition_rows(grid, q, n):
+def partition_rows(grid, q, n, floor=1.0):
     """n contiguous [start, stop) row blocks with (nearly) equal summed weight."""
-    w = row_weights(grid, q)
+    w = row_weights(grid, q, floor)
     cum = np.concatenate(([0.0], np.cumsum(w)))
     total = cum[-1]
     cuts = [0]
@@ -469,13 +469,33 @@ def host_exchange():
     return _EXCHANGE
 
 
-def point_blocks(npts, cfg, rows, world):
+_ROW_BLOCKS = {}
+
+
+# Host-output runs move every pixel of a row to the host, sky included, while only the on-disc pixels cost device time:
+# a row weighs its on-disc pixels plus this fraction of all its pixels (measured on 8 B200 behind shared PCIe uplinks:
+# the ranks holding the sky rows at the top and bottom of a disc image were copying 2.4 times the bytes of the others).
+ROW_COPY_WEIGHT = 0.3
+
+
+def point_blocks(npts, cfg, rows, world, host_output=True):
     """[start, stop) blocks of the flat point list for every rank: whole image rows balanced by on-disc
-    pixels when `rows` = (grid of row y values, pixels per row) is given, else an even split."""
+    pixels (plus, for results that go to the host, the pixels to copy) when `rows` = (grid of row y values, pixels
+    per row) is given, else an even split.
+    (A pure function of its arguments, asked for twice per Planet.run: the last few answers are kept.)"""
     if rows is not None:
+        import os
         grid, ncol = rows
-        rparts = partition_rows(grid, cfg.Rpol / cfg.Req if cfg.gtype == 'ellipse' else 1.0, world)
-        return [(a * ncol, b * ncol) for a, b in rparts]
+        q = cfg.Rpol / cfg.Req if cfg.gtype == 'ellipse' else 1.0
+        floor = 1.0 + (float(os.environ.get('RB_ROW_COPY_WEIGHT', ROW_COPY_WEIGHT)) * ncol if host_output else 0.0)
+        key = (np.asarray(grid, dtype=np.float64).tobytes(), int(ncol), float(q), int(world), floor)
+        blocks = _ROW_BLOCKS.get(key)
+        if blocks is None:
+            blocks = [(a * ncol, b * ncol) for a, b in partition_rows(grid, q, world, floor)]
+            if len(_ROW_BLOCKS) >= 8:
+                _ROW_BLOCKS.pop(next(iter(_ROW_BLOCKS)))
+            _ROW_BLOCKS[key] = blocks
+        return list(blocks)
     return partition_even(npts, world)
 
 
