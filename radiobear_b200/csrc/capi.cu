@@ -106,6 +106,7 @@ void rb_destroy(rb_context* ctx) {
     if (ctx->ticket.done) cudaEventDestroy(ctx->ticket.done);
     if (ctx->ticket.mid) cudaEventDestroy(ctx->ticket.mid);
     for (auto e : ctx->fill_ev) if (e) cudaEventDestroy(e);
+    if (ctx->fill_stream) cudaStreamDestroy(ctx->fill_stream);
     for (int i = 0; i < 3; ++i)
       for (int r = 0; r < rb_context::kEvRing; ++r)
         for (int j = 0; j < 2; ++j)

@@ -2636,12 +2636,32 @@ int rb_launch_gravity_geometry(rb_context* ctx, const RtLaunch& g, double* out_f
 // it runs on a side stream beside the integration (memory-bound next to an FP64-bound kernel).  Whoever reads the
 // outputs waits with rb_join_fill_miss.
 int rb_launch_fill_miss(rb_context* ctx, const RtLaunch& g, int F, void* out_Tb, double* out_intW, int out_f32) {
-  if (!ctx->aux[1]) RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[1], cudaStreamNonBlocking));
+  // RB_FILL_STREAM: 0 = on the context stream, ahead of the integration; 1 = side stream; 2 = side stream of the
+  // highest priority (its CTAs get SM slots ahead of the thousands of integration CTAs launched right after it, so
+  // the copy-out stream, which waits for the fill, is released at the start of the integration and not in its middle)
+  if (ctx->fill_mode < 0) {
+    const char* e = getenv("RB_FILL_STREAM");
+    ctx->fill_mode = e ? atoi(e) : 2;
+    if (ctx->fill_mode < 0 || ctx->fill_mode > 2) ctx->fill_mode = 2;
+  }
   for (auto& e : ctx->fill_ev)
     if (!e) RB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  cudaStream_t user = ctx->stream, side = ctx->aux[1];
-  RB_CUDA(ctx, cudaEventRecord(ctx->fill_ev[0], user));
-  RB_CUDA(ctx, cudaStreamWaitEvent(side, ctx->fill_ev[0], 0));
+  cudaStream_t user = ctx->stream, side = user;
+  if (ctx->fill_mode == 1) {
+    if (!ctx->aux[1]) RB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[1], cudaStreamNonBlocking));
+    side = ctx->aux[1];
+  } else if (ctx->fill_mode == 2) {
+    if (!ctx->fill_stream) {
+      int lo = 0, hi = 0;
+      RB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      RB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->fill_stream, cudaStreamNonBlocking, hi));
+    }
+    side = ctx->fill_stream;
+  }
+  if (side != user) {
+    RB_CUDA(ctx, cudaEventRecord(ctx->fill_ev[0], user));
+    RB_CUDA(ctx, cudaStreamWaitEvent(side, ctx->fill_ev[0], 0));
+  }
   struct Restore { rb_context* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, user};
   ctx->stream = side;
   const long long nout = (long long)g.R * F;
