@@ -51,8 +51,9 @@ RT_FP64_INSTR_PER_STEP = 10.5
 RT_FLOPS_PER_SMALL_STEP = 10.5
 RT_FP64_INSTR_PER_SMALL_STEP = 6.5
 # dram__bytes_read.sum + dram__bytes_write.sum of one rt_integrate_pairs_kernel launch of this workload at N=1
-RT_DRAM_BYTES_N1 = 1008942848
-RT_DRAM_SOURCE = 'ncu --set full, profiles/r2_rt_integrate_pairs_ncu_full.txt (0.946 GB read + 0.063 GB written)'
+RT_DRAM_BYTES_N1 = 1032517000 + 64695296
+RT_DRAM_SOURCE = ('ncu --set full, profiles/r2_final_rt_integrate_pairs_ncu_full.txt (1.033 GB read + 0.065 GB written; the tile list '
+                  'launched in one part instead of L2-sized parts reads 4.40 GB: profiles/r2_final_rt_kernels_one_part_ncu_full.txt)')
 RT_DRAM_BYTES_N1_MIXED = 645195776
 RT_DRAM_SOURCE_MIXED = 'ncu --set full, profiles/r1_mixed_rt_integrate_rays_mixed_ncu_full.txt (0.505 GB read + 0.140 GB written)'
 # SASS instructions (cuobjdump, hot loops) and shared-memory wavefronts (128 B/clk/SM data pipe) per executed segment-step

@@ -836,6 +836,7 @@ struct RtK {
   int fg_reverse;            // launch the frequency groups last to first (behind a running trace: rb_launch_integrate)
   unsigned nparts;           // launch order: the tile list in nparts parts, inside a part frequency group by frequency
                              // group (see rb_launch_integrate); 0: block = tile * fgroups + frequency group
+  unsigned part_tiles;       // != 0: the device cuts the list into parts of about part_tiles tile blocks (<= nparts parts)
   unsigned tile_blocks;      // upper bound of the CTAs per frequency group (the grid holds nparts more per group)
   const int* cidx;        // compacted launch: list position -> ray index (null: ds / nseg / nanflag are per ray index)
   const int* ncomp;       // compacted launch: length of the list
@@ -1177,14 +1178,17 @@ __device__ __forceinline__ RayTile map_ray_tile(const RtK& k, unsigned tiles_per
   if (k.nparts) {
     // CTAs (tile blocks) that exist: known on the device only for a compacted launch
     const unsigned nt = k.cidx ? ((unsigned)((*k.ncomp + 31) >> 5) + tiles_per_cta - 1) / tiles_per_cta : k.tile_blocks;
-    const unsigned cs = (nt + k.nparts - 1) / k.nparts;        // tile blocks per part
+    // (part_tiles: parts of about that many tile blocks, at most k.nparts of them -- the host sized the grid for
+    //  k.nparts without knowing how many rays hit)
+    const unsigned np = k.part_tiles ? min(k.nparts, max(1u, (nt + k.part_tiles / 2) / k.part_tiles)) : k.nparts;
+    const unsigned cs = (nt + np - 1) / np;                    // tile blocks per part
     const unsigned per = cs * k.fgroups;
-    const unsigned part = per ? blockIdx.x / per : k.nparts;
+    const unsigned part = per ? blockIdx.x / per : np;
     const unsigned local = blockIdx.x - part * per;
     m.fg = cs ? local / cs : 0;
     bcta = part * cs + (local - m.fg * cs);
     if (k.fg_reverse && m.fg < k.fgroups) m.fg = k.fgroups - 1 - m.fg;
-    beyond = part >= k.nparts || bcta >= nt;
+    beyond = part >= np || bcta >= nt;
   } else {
     bcta = blockIdx.x / k.fgroups;
     m.fg = blockIdx.x - bcta * k.fgroups;
@@ -2743,10 +2747,24 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
     // frequency groups of a ray tile next to each other -- measured on C4: 3.10 -> 2.93 ms on one GPU, 0.48 -> 0.40 ms
     // for a rank's share on eight, although every ds tile then comes from DRAM once per frequency group.  With the
     // copy-out pipeline the tile list is cut into parts that are launched one after the other, so that the copy chunks
-    // still complete in order.  RB_RT_PARTS: 0 = the old order, n = n parts.
+    // still complete in order.  Device-resident outputs: parts of ~80 MB of ds tiles, which stay in L2 (126 MB) for
+    // the eight frequency groups of the part -- C4 in one part reads 4.4 GB from DRAM for 0.94 GB of ds (2.895 ms),
+    // in 12 parts 2.915 ms (profiles/r2_ab_parts.txt).  RB_RT_PARTS: 0 = the old order, n = n parts.
     {
       const char* e = getenv("RB_RT_PARTS");
-      k.nparts = e ? (unsigned)atoi(e) : (progress ? 12u : 1u);
+      const unsigned long long tile_bytes = (unsigned long long)(k.L - 1) * 256ull * (prep.tiles ? kPairWarps : 1);
+      k.part_tiles = 0;
+      if (e || progress) {
+        k.nparts = e ? (unsigned)atoi(e) : 12u;
+      } else if (g.prog) {
+        k.nparts = 1;                                          // behind a running trace: measured in one part (N = 2 / 4 / 8)
+      } else {
+        // (a compacted launch knows its number of tiles on the device only: k.nparts is the bound for a list of all rays)
+        k.part_tiles = (unsigned)(80000000ull / tile_bytes);
+        if (k.part_tiles < 1) k.part_tiles = 1;
+        k.nparts = (k.tile_blocks + k.part_tiles / 2) / k.part_tiles;
+        if (k.nparts < 1) k.nparts = 1;
+      }
       if (k.nparts > k.tile_blocks) k.nparts = k.tile_blocks ? k.tile_blocks : 1u;
     }
     const unsigned long long nblocks = (unsigned long long)k.fgroups * (k.tile_blocks + k.nparts);
