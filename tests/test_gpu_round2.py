@@ -272,3 +272,42 @@ def test_integration_follows_a_running_trace(eng, c4):
         assert np.array_equal(res[1][0], ref[601 * 270:601 * 330], equal_nan=True)
     finally:
         eng.set_rt_stream_geometry(-1)
+
+
+def test_launch_order_changes_no_bit(eng, c4):
+    """The integration's launch order (rb_launch_integrate: frequency group by frequency group inside parts of the
+    tile list; device-resident outputs get L2-sized parts whose number is chosen on the device, RB_RT_PARTS overrides,
+    0 = the frequency groups of a tile adjacent) decides which CTAs run together, not what they compute: the full C4
+    cube through the device-pointer entry is bit-identical for every order, and equals the host-output cube (12 parts
+    under the copy-out pipeline)."""
+    import os
+    import torch
+    a, b, slab, T = c4['a'], c4['b'], c4['slab'], c4['T']
+    g = geom(a)
+    dev = torch.device('cuda', 0)
+    t64 = dict(dtype=torch.float64, device=dev)
+    radius_t = torch.tensor(np.ascontiguousarray(g['radius'], dtype=np.float64), **t64)
+    b_t, slab_t, T_t = torch.tensor(b, **t64), torch.tensor(np.ascontiguousarray(slab), **t64), torch.tensor(np.ascontiguousarray(T), **t64)
+    out_t = torch.empty((len(b), slab.shape[1]), **t64)
+    n = g['refr_index']
+    before = os.environ.pop('RB_RT_PARTS', None)
+    try:
+        cubes = {}
+        for parts in (None, '0', '1', '5', '37'):
+            if parts is None:
+                os.environ.pop('RB_RT_PARTS', None)
+            else:
+                os.environ['RB_RT_PARTS'] = parts
+            out_t.fill_(-1.0)
+            eng.rt_batch_dev(radius_t, float(n[0]), float(n[1]), b_t, slab_t, T_t, g['Req'], g['Rpol'],
+                             [float(g['orientation'][0]), float(g['orientation'][1])], g['gtype'], g['limb'],
+                             out_f32=False, tau_cut=eng.TAU_CUT, out=out_t)
+            torch.cuda.synchronize()
+            cubes[parts] = out_t.cpu().numpy()
+        ref = c4['cube'].reshape(-1, 64)
+        for parts, cube in cubes.items():
+            assert np.array_equal(cube, ref, equal_nan=True), parts
+    finally:
+        os.environ.pop('RB_RT_PARTS', None)
+        if before is not None:
+            os.environ['RB_RT_PARTS'] = before
