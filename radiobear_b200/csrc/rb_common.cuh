@@ -39,7 +39,7 @@ struct rb_context {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t fill_ev[2] = {nullptr, nullptr};   // fork / join of the sky fill (rb_launch_fill_miss)
   cudaStream_t fill_stream = nullptr;            // highest-priority stream of the sky fill (RB_FILL_STREAM=2)
-  int fill_mode = -1;                            // RB_FILL_STREAM, read once per context
+  int fill_mode = 2;                             // RB_FILL_STREAM of the last sky fill
   std::vector<cudaEvent_t> pipe_ev;
   int rt_chunks = 0;  // 0 = automatic
   int rt_precision = 0;  // RB_RT_F64 / RB_RT_MIXED: arithmetic of the rays-major integration (rb_set_rt_precision)

@@ -2643,8 +2643,8 @@ int rb_launch_fill_miss(rb_context* ctx, const RtLaunch& g, int F, void* out_Tb,
   // RB_FILL_STREAM: 0 = on the context stream, ahead of the integration; 1 = side stream; 2 = side stream of the
   // highest priority (its CTAs get SM slots ahead of the thousands of integration CTAs launched right after it, so
   // the copy-out stream, which waits for the fill, is released at the start of the integration and not in its middle)
-  if (ctx->fill_mode < 0) {
-    const char* e = getenv("RB_FILL_STREAM");
+  {
+    const char* e = getenv("RB_FILL_STREAM");                 // (read per call: tests switch it)
     ctx->fill_mode = e ? atoi(e) : 2;
     if (ctx->fill_mode < 0 || ctx->fill_mode > 2) ctx->fill_mode = 2;
   }

@@ -311,3 +311,24 @@ def test_launch_order_changes_no_bit(eng, c4):
         os.environ.pop('RB_RT_PARTS', None)
         if before is not None:
             os.environ['RB_RT_PARTS'] = before
+
+
+def test_sky_fill_stream_changes_no_bit(eng, c4):
+    """The sky pixels of a compacted launch are written by rt_fill_miss on the context stream (RB_FILL_STREAM=0), a side
+    stream (1) or a side stream of the highest priority (2, the default: the fill must not queue behind the integration
+    CTAs, the copy-out stream waits for it).  Host-output pipeline and single-launch path: same cube, sky exactly 2.725 K."""
+    import os
+    a, b, slab, T = c4['a'], c4['b'], c4['slab'], c4['T']
+    ref = c4['cube'].reshape(-1, 64)
+    before = os.environ.pop('RB_FILL_STREAM', None)
+    try:
+        for mode in ('0', '1', '2'):
+            os.environ['RB_FILL_STREAM'] = mode
+            got = eng.rt_batch(b=b, alpha_slab=slab, T=T, **geom(a))['Tb']
+            assert np.array_equal(got, ref, equal_nan=True), mode
+            part = eng.rt_batch(b=b[:8000], alpha_slab=slab, T=T, **geom(a))['Tb']      # below the chunked pipeline: one launch
+            assert np.array_equal(part, ref[:8000], equal_nan=True) and (part == 2.725).all(), mode
+    finally:
+        os.environ.pop('RB_FILL_STREAM', None)
+        if before is not None:
+            os.environ['RB_FILL_STREAM'] = before
