@@ -176,6 +176,10 @@ typedef struct rb_alpha_desc {
   int32_t units;                           /* RB_UNITS_* (parameters.py:4-8) */
   const double* scale;                     /* [C][L] per-constituent per-layer scale or NULL (alpha.py:151-192, 235-259) */
   const double* freqs_host;                /* _dev calls only: optional HOST copy of freqs (saves one small D2H + sync) */
+  int32_t freqs_per_layer;                 /* 1: freqs (and freqs_host) is [L][F], row l = the frequencies layer l is
+                                              evaluated at -- Doppler-shifted absorption, where every step of a ray sees
+                                              f / doppler (brightness.py:80-92).  0: one list [F] for all layers.  Not
+                                              with h2_orton (its table is prepared per frequency list). */
 } rb_alpha_desc;
 
 /* Alpha.get_layers (alpha.py:261-305): total absorption for every (layer, freq).
@@ -281,6 +285,10 @@ typedef struct rb_rt_desc {
   int32_t out_f32;          /* 1: out_Tb is float32 (Data.Tb dtype, data_handling.py:46-47) else float64 */
   double tau_cut;           /* stop a ray once tau > tau_cut (exp(-tau) no longer representable in the sums);
                                <= 0 disables.  The reference integrates every layer. */
+  const double* alpha0;     /* NULL, or a second [L][F] slab: dtau of step i becomes (alpha0[i] + alpha[i+1]) ds_i / 2 while
+                               the weights keep alpha[i+1] -- the Doppler form of brightness.py:80-96, where the upper node
+                               of a step is evaluated at its own shifted frequency (a0 there) instead of re-using the lower
+                               node of the step before.  rb_rt_integrate[_profile] only (requests below 512 rays). */
 } rb_rt_desc;
 
 /* Brightness.single over a batch of rays (brightness.py:30-126): geometry + tau/W/Tb integration.
@@ -314,6 +322,11 @@ int rb_geometry_prefetch_dev(rb_context* ctx, const rb_geometry_desc* geom, int6
  *   ds : [R][S] km host, nseg[R]; layer4ds is implicit 0..nseg-1 (raypath.py:222-225).          */
 int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int64_t n_rays, int32_t n_seg,
                     const double* ds, const int32_t* nseg, void* out_Tb, double* out_integrated_W);
+/* The same with the profile outputs of rb_rt_batch for one ray (Brightness.tau / .W / .Tb_lyr, brightness.py:118-120):
+ * profile_ray >= 0 and out_tau / out_W / out_Tb_lyr each [F][S], or -1 / NULL. */
+int rb_rt_integrate_profile(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int64_t n_rays, int32_t n_seg,
+                            const double* ds, const int32_t* nseg, void* out_Tb, double* out_integrated_W,
+                            int64_t profile_ray, double* out_tau, double* out_W, double* out_Tb_lyr);
 
 /* ---- measurement probes (bench.py / tests) ------------------------------------------------- */
 /* Sustained FP64 FMA rate of the device in TFLOP/s (2 flops per DFMA, 16 independent chains per thread,

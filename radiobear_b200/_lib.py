@@ -38,7 +38,7 @@ class AlphaDesc(C.Structure):
                 ('gas', C.c_void_p), ('gas_rows', C.c_int32), ('gas_col', C.c_int32 * RB_NUM_GAS),
                 ('cloud', C.c_void_p), ('cloud_rows', C.c_int32), ('cloud_col', C.c_int32 * RB_NUM_CLD),
                 ('cloud_flags', C.c_uint32), ('h2state', C.c_int32), ('coshape', C.c_int32),
-                ('units', C.c_int32), ('scale', C.c_void_p), ('freqs_host', C.c_void_p)]
+                ('units', C.c_int32), ('scale', C.c_void_p), ('freqs_host', C.c_void_p), ('freqs_per_layer', C.c_int32)]
 
 
 class GeometryDesc(C.Structure):
@@ -55,7 +55,7 @@ class GravityModel(C.Structure):
 
 class RtDesc(C.Structure):
     _fields_ = [('n_freqs', C.c_int32), ('alpha', C.c_void_p), ('T', C.c_void_p),
-                ('disc_average', C.c_int32), ('out_f32', C.c_int32), ('tau_cut', C.c_double)]
+                ('disc_average', C.c_int32), ('out_f32', C.c_int32), ('tau_cut', C.c_double), ('alpha0', C.c_void_p)]
 
 
 class RadiobearB200Error(RuntimeError):
@@ -114,6 +114,7 @@ def load():
         'rb_geometry_prefetch': (C.c_int, [vp, C.POINTER(GeometryDesc), i64, vp]),
         'rb_geometry_prefetch_dev': (C.c_int, [vp, C.POINTER(GeometryDesc), i64, vp]),
         'rb_rt_integrate': (C.c_int, [vp, C.POINTER(RtDesc), i32, i64, i32, vp, vp, vp, vp]),
+        'rb_rt_integrate_profile': (C.c_int, [vp, C.POINTER(RtDesc), i32, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp]),
         'rb_probe_fp64_peak': (C.c_int, [vp, C.c_int, C.POINTER(dbl)]),
         'rb_probe_rcp': (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
         'rb_probe_fp64_mix': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(dbl)]),
@@ -131,7 +132,7 @@ EXPORTED_SYMBOLS = ['rb_abi_version', 'rb_create', 'rb_destroy', 'rb_last_error'
                     'rb_launch_count', 'rb_enable_timing', 'rb_last_kernel_ms', 'rb_kernel_ms_history', 'rb_kernel_timed_count',
                     'rb_set_rt_chunks', 'rb_set_rt_precision', 'rb_get_rt_precision', 'rb_set_rt_tuning', 'rb_set_rt_stream_geometry', 'rb_count_steps', 'rb_count_small_steps', 'rb_set_catalog', 'rb_alpha_layers',
                     'rb_alpha_layers_dev', 'rb_alpha_scale_sum', 'rb_alpha_layers_dev_scatter', 'rb_alpha_layers_resident', 'rb_alpha_rescale_resident',
-                    'rb_alpha_resident_info', 'rb_alpha_fetch', 'rb_rt_batch_resident', 'rb_compute_ds', 'rb_compute_ray_fields', 'rb_set_gravity_model', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate',
+                    'rb_alpha_resident_info', 'rb_alpha_fetch', 'rb_rt_batch_resident', 'rb_compute_ds', 'rb_compute_ray_fields', 'rb_set_gravity_model', 'rb_geometry_prefetch', 'rb_geometry_prefetch_dev', 'rb_rt_batch', 'rb_rt_batch_dev', 'rb_rt_integrate', 'rb_rt_integrate_profile',
                     'rb_probe_fp64_peak', 'rb_probe_rcp', 'rb_probe_fp64_mix']
 
 _EXC = {RB_ERR_INVALID: ValueError, RB_ERR_CUDA: RadiobearB200Error, RB_ERR_NOMEM: MemoryError,

@@ -162,6 +162,7 @@ class Alpha:
         """Compute (or re-scale cached) absorption for all layers: sets .layers[F, L], .P, .freqs."""
         self.reset_layers()
         self.freqs = freqs
+        self._scale = scale
         C = atm.config.C
         self.P = atm.gas[C['P']]
         L = atm.gas.shape[1]
@@ -231,6 +232,19 @@ class Alpha:
             # the device copy of what the memory cache now holds (None when the cube went through the host path)
             self._dev_cube = (res, self.memory.alpha_data) if (save_alpha == 'memory' and res is not None) else None
             del self.tosave
+
+    def layers_at(self, freq_matrix, atm, scale=None):
+        """Total absorption slab[L][F] with every layer evaluated at its own frequencies freq_matrix[L][F] -- what the
+        Doppler branch of Brightness.single asks for step by step (brightness.py:83-92: one plugin sweep per step and
+        frequency at f / doppler); here one kernel launch (rb_alpha_desc::freqs_per_layer).  `scale` as in get_layers
+        (default: the scale of the last get_layers call)."""
+        C = atm.config.C
+        if scale is None:
+            scale = getattr(self, '_scale', False)
+        return engine.alpha_layers(np.asarray(freq_matrix, dtype=np.float64), atm.gas[C['T']], atm.gas[C['P']], atm.gas, C,
+                                   cloud=atm.cloud if np.size(atm.cloud) else None, cloud_dict=atm.config.Cl,
+                                   formalisms=self.formalisms(), other_dicts=self.other_dict, units=utils.alphaUnit,
+                                   scale=scale, truncate_strength=self.truncate_strength, truncate_freq=self.truncate_freq)
 
     def get_single_layer(self, freqs, layer, atm, lscale=1.0, units='invcm'):
         """Total absorption of one layer (alpha.py:218-233)."""

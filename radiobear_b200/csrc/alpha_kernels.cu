@@ -54,6 +54,7 @@ struct AlphaK {
   int L, F, C;
   int form[RB_MAX_CONSTITUENTS];
   const double* freqs;
+  int freq_stride;   // 0: freqs[F] for every layer; F: freqs[L][F] (rb_alpha_desc::freqs_per_layer)
   const double* T;
   const double* P;
   const double* gas[RB_NUM_GAS];     // row pointers (nullptr = absent -> mixing ratio 0)
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, FPT >= 4 ? RB_ALPHA_FPT4_CTAS : 2) a
   for (int j = 0; j < FPT; ++j) {
     fidx[j] = (g * FPT + j) * 32 + lane;
     valid[j] = (g < k.ngroups) && (fidx[j] < k.F);
-    f[j] = valid[j] ? k.freqs[fidx[j]] : 1.0;
+    f[j] = valid[j] ? k.freqs[(size_t)l * k.freq_stride + fidx[j]] : 1.0;   // (freq_stride = F: per-layer frequencies)
     x[j] = f[j] * f[j];
   }
   double s_low[FPT], s_sjs[FPT], s_h2s[FPT], s_ph3[FPT], s_h2o[FPT], s_co[FPT];
@@ -879,6 +880,7 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   if (k.C <= 0 || k.C > RB_MAX_CONSTITUENTS)
     return rb_fail(ctx, RB_ERR_INVALID, "alpha: n_constituents must be 1..%d", RB_MAX_CONSTITUENTS);
   k.freqs = d->freqs; k.T = d->T; k.P = d->P;
+  k.freq_stride = d->freqs_per_layer ? d->n_freqs : 0;
   for (int i = 0; i < RB_NUM_GAS; ++i) {
     const int c = d->gas_col[i];
     if (c >= d->gas_rows) return rb_fail(ctx, RB_ERR_INVALID, "alpha: gas_col[%d]=%d out of range", i, c);
@@ -932,6 +934,7 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   if (k.slot_h2o >= 0) RB_TRY(need_cat(RB_CAT_H2O, "h2o"));
   if (k.slot_co >= 0) RB_TRY(need_cat(RB_CAT_CO, "co"));
   if (k.slot_h2 >= 0 && k.h2_form == RB_F_H2_ORTON) {
+    if (d->freqs_per_layer) return rb_fail(ctx, RB_ERR_UNSUPPORTED, "alpha: h2_orton with per-layer frequencies");
     RB_TRY(need_cat(RB_CAT_H2_ORTON, "h2_orton"));
     if (ctx->cat_n[RB_CAT_H2_ORTON] != k.F)
       return rb_fail(ctx, RB_ERR_INVALID, "alpha: the h2_orton table was prepared for %d frequencies, the call has %d",
@@ -939,7 +942,8 @@ int rb_launch_alpha(rb_context* ctx, const rb_alpha_desc* d, const double* h_fre
   }
 
   // frequency classes
-  for (int i = 0; i < k.F; ++i) {
+  const long long n_hf = (long long)k.F * (d->freqs_per_layer ? k.L : 1);   // per-layer lists: the union of all rows
+  for (long long i = 0; i < n_hf; ++i) {
     const double f = h_freqs[i];
     if (f <= 30.0) k.any_lo = 1; else k.any_hi = 1;
     if (f <= 26.0) k.any_S = 1; else if (f >= 34.0) k.any_J = 1; else k.any_I = 1;

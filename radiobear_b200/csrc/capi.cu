@@ -269,8 +269,9 @@ int rb_alpha_layers_dev(rb_context* ctx, const rb_alpha_desc* d, double* out_tot
   RB_CUDA(ctx, cudaSetDevice(ctx->device));
   // the frequency-class scan needs the (tiny) frequency list on the host
   if (d->freqs_host) return rb_launch_alpha(ctx, d, d->freqs_host, out_total, out_cube);
-  std::vector<double> hf(d->n_freqs);
-  RB_CUDA(ctx, cudaMemcpyAsync(hf.data(), d->freqs, sizeof(double) * d->n_freqs, cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t n_hf = (size_t)d->n_freqs * (d->freqs_per_layer ? (size_t)d->n_layers : 1);
+  std::vector<double> hf(n_hf);
+  RB_CUDA(ctx, cudaMemcpyAsync(hf.data(), d->freqs, sizeof(double) * n_hf, cudaMemcpyDeviceToHost, ctx->stream));
   RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return rb_launch_alpha(ctx, d, hf.data(), out_total, out_cube);
 }
@@ -284,12 +285,13 @@ static int alpha_layers_host(rb_context* ctx, const rb_alpha_desc* d, double* ou
   rb_alpha_desc dd = *d;
   void *p_f, *p_T, *p_P, *p_gas = nullptr, *p_cloud = nullptr, *p_scale = nullptr, *p_tot, *p_cube = nullptr;
   const bool want_cube = resident ? keep_cube : (out_cube != nullptr);
-  RB_TRY(rb_ensure(ctx, RB_BUF_FREQS, F * 8, &p_f));
+  const size_t n_f = F * (d->freqs_per_layer ? L : 1);       // per-layer frequency lists: [L][F]
+  RB_TRY(rb_ensure(ctx, RB_BUF_FREQS, n_f * 8, &p_f));
   RB_TRY(rb_ensure(ctx, RB_BUF_T, L * 8, &p_T));
   RB_TRY(rb_ensure(ctx, RB_BUF_P, L * 8, &p_P));
   RB_TRY(rb_ensure(ctx, resident ? RB_BUF_RES_TOTAL : RB_BUF_TOTAL, L * F * 8, &p_tot));
   cudaStream_t s = ctx->stream;
-  RB_CUDA(ctx, cudaMemcpyAsync(p_f, d->freqs, F * 8, cudaMemcpyHostToDevice, s));
+  RB_CUDA(ctx, cudaMemcpyAsync(p_f, d->freqs, n_f * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_T, d->T, L * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_P, d->P, L * 8, cudaMemcpyHostToDevice, s));
   if (d->gas && d->gas_rows > 0) {
@@ -345,8 +347,9 @@ int rb_alpha_layers_dev_scatter(rb_context* ctx, const rb_alpha_desc* d, int32_t
     peers[p] = (double*)(uintptr_t)peer_slabs[p];
   }
   if (d->freqs_host) return rb_launch_alpha(ctx, d, d->freqs_host, nullptr, nullptr, n_peers, peers, first_row);
-  std::vector<double> hf(d->n_freqs);
-  RB_CUDA(ctx, cudaMemcpyAsync(hf.data(), d->freqs, sizeof(double) * d->n_freqs, cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t n_hf = (size_t)d->n_freqs * (d->freqs_per_layer ? (size_t)d->n_layers : 1);
+  std::vector<double> hf(n_hf);
+  RB_CUDA(ctx, cudaMemcpyAsync(hf.data(), d->freqs, sizeof(double) * n_hf, cudaMemcpyDeviceToHost, ctx->stream));
   RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return rb_launch_alpha(ctx, d, hf.data(), nullptr, nullptr, n_peers, peers, first_row);
 }
@@ -712,10 +715,12 @@ int rb_compute_ray_fields(rb_context* ctx, const rb_geometry_desc* g, int64_t R,
   return RB_OK;
 }
 
-static int check_rt(rb_context* ctx, const rb_rt_desc* rt, const void* out_Tb) {
+static int check_rt(rb_context* ctx, const rb_rt_desc* rt, const void* out_Tb, bool allow_alpha0 = false) {
   if (!rt || !out_Tb) return rb_fail(ctx, RB_ERR_INVALID, "rt: null descriptor / output");
   if (rt->n_freqs <= 0) return rb_fail(ctx, RB_ERR_INVALID, "rt: n_freqs must be positive");
   if (!rt->alpha || !rt->T) return rb_fail(ctx, RB_ERR_INVALID, "rt: alpha / T must not be null");
+  if (rt->alpha0 && !allow_alpha0)
+    return rb_fail(ctx, RB_ERR_UNSUPPORTED, "rt: alpha0 (Doppler form: one absorption slab pair per ray) goes through rb_rt_integrate");
   return RB_OK;
 }
 
@@ -1018,23 +1023,27 @@ int rb_rt_batch_resident(rb_context* ctx, const rb_geometry_desc* g, const rb_rt
   return rt_batch_host(ctx, g, rt, R, b, out_Tb, out_intW, profile_ray, out_tau, out_W, out_Tblyr, true);
 }
 
-int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int64_t R, int32_t n_seg, const double* ds,
-                    const int32_t* nseg, void* out_Tb, double* out_intW) {
+int rb_rt_integrate_profile(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int64_t R, int32_t n_seg,
+                            const double* ds, const int32_t* nseg, void* out_Tb, double* out_intW, int64_t profile_ray,
+                            double* out_tau, double* out_W, double* out_Tblyr) {
   if (!ctx) return RB_ERR_INVALID;
-  RB_TRY(check_rt(ctx, rt, out_Tb));
+  RB_TRY(check_rt(ctx, rt, out_Tb, true));
   if (!ds || !nseg || R <= 0) return rb_fail(ctx, RB_ERR_INVALID, "rt_integrate: null pointer / no rays");
   if (n_layers < 2 || n_seg != n_layers - 1) return rb_fail(ctx, RB_ERR_INVALID, "rt_integrate: n_seg must be n_layers - 1");
+  if (profile_ray >= R || (profile_ray >= 0 && (!out_tau || !out_W || !out_Tblyr)))
+    return rb_fail(ctx, RB_ERR_INVALID, "rt_integrate: profile_ray out of range / profile outputs missing");
   RB_CUDA(ctx, cudaSetDevice(ctx->device));
   drop_ticket(ctx);
   RtLaunch L{};
   L.L = n_layers; L.R = R; L.Rpad = (R + 31) & ~(int64_t)31;
   const size_t nL = n_layers, S = n_seg, F = rt->n_freqs;
   const size_t esz = rt->out_f32 ? 4 : 8;
-  void *p_in, *p_ds, *p_n, *p_alpha, *p_T, *p_tb, *p_iw = nullptr;
+  void *p_in, *p_ds, *p_n, *p_alpha, *p_alpha0 = nullptr, *p_T, *p_tb, *p_iw = nullptr, *p_prof = nullptr;
   RB_TRY(rb_ensure(ctx, RB_BUF_MISC, (size_t)R * S * 8, &p_in));
   RB_TRY(rb_ensure(ctx, RB_BUF_DS, S * L.Rpad * 8 + kRtSlackBytes, &p_ds));
   RB_TRY(rb_ensure(ctx, RB_BUF_NSEG, (size_t)L.Rpad * 8, &p_n));
   RB_TRY(rb_ensure(ctx, RB_BUF_TOTAL, nL * F * 8, &p_alpha));
+  if (rt->alpha0) RB_TRY(rb_ensure(ctx, RB_BUF_ALPHA0, nL * F * 8, &p_alpha0));
   RB_TRY(rb_ensure(ctx, RB_BUF_T, nL * 8, &p_T));
   RB_TRY(rb_ensure(ctx, RB_BUF_TB, (size_t)R * F * esz, &p_tb));
   if (out_intW) RB_TRY(rb_ensure(ctx, RB_BUF_INTW, (size_t)R * F * 8, &p_iw));
@@ -1042,18 +1051,43 @@ int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int
   RB_CUDA(ctx, cudaMemcpyAsync(p_in, ds, (size_t)R * S * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_n, nseg, (size_t)R * 4, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_alpha, rt->alpha, nL * F * 8, cudaMemcpyHostToDevice, s));
+  if (rt->alpha0) RB_CUDA(ctx, cudaMemcpyAsync(p_alpha0, rt->alpha0, nL * F * 8, cudaMemcpyHostToDevice, s));
   RB_CUDA(ctx, cudaMemcpyAsync(p_T, rt->T, nL * 8, cudaMemcpyHostToDevice, s));
   L.ds = (double*)p_ds; L.nseg = (int32_t*)p_n; L.nanflag = (int32_t*)p_n + L.Rpad;
   RB_TRY(rb_launch_ds_to_slab(ctx, (const double*)p_in, R, L.Rpad, (int)S, L.nseg, L.nanflag, (double*)p_ds));
   rb_rt_desc rd = *rt;
-  rd.alpha = (const double*)p_alpha; rd.T = (const double*)p_T;
+  rd.alpha = (const double*)p_alpha; rd.alpha0 = (const double*)p_alpha0; rd.T = (const double*)p_T;
   RtPrep prep;
   RB_TRY(rb_rt_prepare(ctx, L.L, &rd, R, false, false, &prep));
   RB_TRY(rb_launch_integrate(ctx, L, &rd, prep, nullptr, p_tb, (double*)p_iw, -1, nullptr, nullptr, nullptr));
   RB_CUDA(ctx, cudaMemcpyAsync(out_Tb, p_tb, (size_t)R * F * esz, cudaMemcpyDeviceToHost, s));
   if (out_intW) RB_CUDA(ctx, cudaMemcpyAsync(out_intW, p_iw, (size_t)R * F * 8, cudaMemcpyDeviceToHost, s));
+  if (profile_ray >= 0) {
+    // the selected ray once more, alone, with the profile-writing variant (Brightness.tau / .W / .Tb_lyr)
+    RB_TRY(rb_ensure(ctx, RB_BUF_PROFILE, 3 * F * S * 8 + F * 8, &p_prof));
+    RB_CUDA(ctx, cudaMemsetAsync(p_prof, 0, 3 * F * S * 8 + F * 8, s));
+    RtLaunch L1 = L;
+    L1.R = 1; L1.Rpad = 32;
+    L1.nanflag = L.nseg + 32;
+    RB_CUDA(ctx, cudaMemcpyAsync(p_n, nseg + profile_ray, 4, cudaMemcpyHostToDevice, s));
+    RB_TRY(rb_launch_ds_to_slab(ctx, (const double*)p_in + (size_t)profile_ray * S, 1, 32, (int)S, L1.nseg, L1.nanflag,
+                                (double*)p_ds));
+    double* pp = (double*)p_prof;
+    rd.out_f32 = 0;
+    RtPrep prof_prep;
+    RB_TRY(rb_rt_prepare(ctx, L.L, &rd, 1, true, false, &prof_prep));
+    RB_TRY(rb_launch_integrate(ctx, L1, &rd, prof_prep, nullptr, pp + 3 * F * S, nullptr, 0, pp, pp + F * S, pp + 2 * F * S));
+    RB_CUDA(ctx, cudaMemcpyAsync(out_tau, pp, F * S * 8, cudaMemcpyDeviceToHost, s));
+    RB_CUDA(ctx, cudaMemcpyAsync(out_W, pp + F * S, F * S * 8, cudaMemcpyDeviceToHost, s));
+    RB_CUDA(ctx, cudaMemcpyAsync(out_Tblyr, pp + 2 * F * S, F * S * 8, cudaMemcpyDeviceToHost, s));
+  }
   RB_CUDA(ctx, cudaStreamSynchronize(s));
   return RB_OK;
+}
+
+int rb_rt_integrate(rb_context* ctx, const rb_rt_desc* rt, int32_t n_layers, int64_t R, int32_t n_seg, const double* ds,
+                    const int32_t* nseg, void* out_Tb, double* out_intW) {
+  return rb_rt_integrate_profile(ctx, rt, n_layers, R, n_seg, ds, nseg, out_Tb, out_intW, -1, nullptr, nullptr, nullptr);
 }
 
 }  // extern "C"

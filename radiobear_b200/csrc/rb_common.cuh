@@ -101,7 +101,8 @@ inline cudaError_t rb_time_end(rb_context* ctx, int which) {
 enum {
   RB_BUF_FREQS = 0, RB_BUF_T, RB_BUF_P, RB_BUF_GAS, RB_BUF_CLOUD, RB_BUF_SCALE, RB_BUF_TOTAL, RB_BUF_CUBE,
   RB_BUF_RADIUS, RB_BUF_B, RB_BUF_DS, RB_BUF_NSEG, RB_BUF_TB, RB_BUF_INTW, RB_BUF_PROFILE, RB_BUF_MISC, RB_BUF_PREP,
-  RB_BUF_FLAGS, RB_BUF_CIDX, RB_BUF_ZQ, RB_BUF_BLKCNT, RB_BUF_DR2, RB_BUF_RES_TOTAL, RB_BUF_RES_CUBE, RB_BUF_ORDER, RB_BUF_PROG
+  RB_BUF_FLAGS, RB_BUF_CIDX, RB_BUF_ZQ, RB_BUF_BLKCNT, RB_BUF_DR2, RB_BUF_RES_TOTAL, RB_BUF_RES_CUBE, RB_BUF_ORDER, RB_BUF_PROG,
+  RB_BUF_ALPHA0
 };
 
 // The rays-major integration kernel prefetches whole 32-segment chunks of the ds slab and of the operand

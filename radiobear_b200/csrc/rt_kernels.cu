@@ -831,6 +831,7 @@ struct RtK {
   RtProgress progress;    // optional per-chunk completion counters (rays-major kernel only)
   const double2* prep2;   // [F/16][L-1][8][3] pair operands (rt_integrate_pairs_kernel, see rt_prepare_pairs_kernel)
   unsigned fgroups, ntiles;  // rays-major launches are 1-D: block = tile * fgroups + frequency group
+  const double* alpha0;      // Doppler form (rb_rt_desc::alpha0): dtau_i = (alpha0[i] + alpha[i+1]) ds_i / 2, or null
   const int* geo_prog;       // streamed geometry: [tiles][geo_npub] rays past each chunk (see GeoK::prog), or null
   int geo_npub;
   int fg_reverse;            // launch the frequency groups last to first (behind a running trace: rb_launch_integrate)
@@ -880,7 +881,7 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
   if (PROFILE && fvalid && nmax > 0) {
     k.out_tau[(size_t)f * S] = 0.0; k.out_W[(size_t)f * S] = 0.0; k.out_Tblyr[(size_t)f * S] = 0.0;
   }
-  double a0 = k.alpha[f];
+  double a0 = k.alpha0 ? k.alpha0[f] : k.alpha[f];
   double T0 = k.T[0];
   // a ray stops once tau >= tau_cut, by the high words (the rule of the rays-major kernels; INFINITY disables it)
   const int cut_hi = __double2hiint(k.tau_cut);
@@ -911,7 +912,7 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
       }
     }
     if (!PROFILE && !live) break;
-    a0 = a1;
+    a0 = k.alpha0 ? k.alpha0[(size_t)(i + 1) * k.F + f] : a1;   // (Doppler: the upper node of the next step has its own value)
     T0 = T1;
   }
   if (!fvalid) return;
@@ -940,7 +941,7 @@ __global__ void __launch_bounds__(128) rt_integrate_kernel(const __grid_constant
 // operations in the same order as the sequential kernel, so the same bits.  Optional profile outputs
 // (Brightness.tau / .W / .Tb_lyr, brightness.py:118-120) as in rt_integrate_kernel<1, true, true>.
 constexpr int kDiscThreads = 256;
-constexpr size_t disc_smem_bytes(int L) { return 5 * (size_t)L * sizeof(double); }
+constexpr size_t disc_smem_bytes(int L) { return 6 * (size_t)L * sizeof(double); }
 __global__ void __launch_bounds__(kDiscThreads) rt_disc_kernel(const __grid_constant__ RtK k, int profile) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   double* const s_tau = reinterpret_cast<double*>(s_raw);     // [L] tau after step i at index i + 1
@@ -948,6 +949,7 @@ __global__ void __launch_bounds__(kDiscThreads) rt_disc_kernel(const __grid_cons
   double* const s_a = s_W + k.L;                              // [L] this frequency's column of the alpha slab
   double* const s_h = s_a + k.L;                              // [L] ds_i / 2 in cm
   double* const s_T = s_h + k.L;                              // [L]
+  double* const s_a0 = s_T + k.L;                             // [L] upper-node absorption of step i (alpha0, else = s_a)
   __shared__ int s_last;                                      // number of steps taken
   const int f = blockIdx.y;
   const long long r = blockIdx.x;
@@ -961,20 +963,19 @@ __global__ void __launch_bounds__(kDiscThreads) rt_disc_kernel(const __grid_cons
   // shared memory: a thread that walks global memory alone waits an L2 round trip per layer)
   for (int i = threadIdx.x; i <= nsteps && i < k.L; i += kDiscThreads) {
     s_a[i] = k.alpha[(size_t)i * k.F + f];
+    s_a0[i] = k.alpha0 ? k.alpha0[(size_t)i * k.F + f] : s_a[i];
     s_T[i] = k.T[i];
     if (i < nsteps) s_h[i] = ds[(size_t)i * kDsStride] * kKmToCm * 0.5;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double tau = 0.0, a0 = s_a[0];
+    double tau = 0.0;
     int i = 0;
     s_tau[0] = 0.0;
     for (; i < nsteps; ++i) {
       if (!(__double2hiint(tau) < cut_hi)) break;             // the rule of every integration kernel of this file
-      const double a1 = s_a[i + 1];
-      tau = tau + (a0 + a1) * s_h[i];
+      tau = tau + (s_a0[i] + s_a[i + 1]) * s_h[i];
       s_tau[i + 1] = tau;
-      a0 = a1;
     }
     s_last = i;
   }
@@ -2709,6 +2710,9 @@ int rb_launch_integrate(rb_context* ctx, const RtLaunch& g, const rb_rt_desc* rt
   bool fill_pending = false;
   k.L = g.L; k.F = rt->n_freqs; k.R = g.R; k.Rpad = g.Rpad;
   k.alpha = rt->alpha; k.T = rt->T; k.ds = g.ds; k.nseg = g.nseg; k.nanflag = g.nanflag;
+  k.alpha0 = rt->alpha0;
+  if (rt->alpha0 && prep.use_rays)
+    return rb_fail(ctx, RB_ERR_UNSUPPORTED, "rt: alpha0 (Doppler form) is built for requests below 512 rays");
   k.out_Tb = out_Tb; k.out_intW = out_intW; k.out_f32 = rt->out_f32; k.disc = rt->disc_average;
   k.tau_cut = (rt->tau_cut > 0.0) ? rt->tau_cut : INFINITY;
   k.profile_ray = profile_ray; k.out_tau = out_tau; k.out_W = out_W; k.out_Tblyr = out_Tblyr;

@@ -216,7 +216,11 @@ def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formal
     gas = f64(gas)
     if gas.ndim == 1:
         gas = np.ascontiguousarray(gas[:, None])
-    L, F = T.shape[0], freqs.shape[0]
+    # freqs[L][F]: every layer at its own frequencies (Doppler-shifted absorption, brightness.py:80-92)
+    per_layer = freqs.ndim == 2
+    L, F = T.shape[0], freqs.shape[-1]
+    if per_layer and freqs.shape[0] != L:
+        raise ValueError('per-layer frequencies: freqs must be [L][F]')
     if gas.shape[1] != L or P.shape[0] != L:
         raise ValueError('T, P and gas disagree on the number of layers')
     if cloud is not None:
@@ -230,12 +234,16 @@ def alpha_layers(freqs, T, P, gas, gas_dict, cloud=None, cloud_dict=None, formal
     ctx = ctx or _lib.get_context()
     ctx.use_own_stream()
     formalisms = list(formalisms)
-    prepare_catalogs(ctx, formalisms, truncate_strength, truncate_freq, freqs=freqs, other_dicts=other_dicts)
+    if per_layer and any(name == 'h2_orton' for _, name in formalisms):
+        raise NotImplementedError('h2_orton prepares its table per frequency list: no per-layer frequencies')
+    prepare_catalogs(ctx, formalisms, truncate_strength, truncate_freq, freqs=freqs[0] if per_layer else freqs,
+                     other_dicts=other_dicts)
     d = build_alpha_desc(formalisms, L, F, gas.shape[0], gas_dict, 0 if cloud is None else cloud.shape[0], cloud_dict,
                          other_dicts, units)
     sm = scale_matrix(scale, [c for c, _ in formalisms], L)
     sm = None if sm is None else f64(sm)
     d.freqs, d.T, d.P, d.gas = ptr(freqs), ptr(T), ptr(P), ptr(gas)
+    d.freqs_per_layer = 1 if per_layer else 0
     d.cloud = ptr(cloud)
     d.scale = ptr(sm)
     if _resident is not None:
@@ -472,8 +480,12 @@ def rt_batch_dev(radius_t, n0, n1, b_t, alpha_t, T_t, Req, Rpol, orientation=(0.
     return out
 
 
-def rt_integrate(ds, nseg, alpha_slab, T, disc_average=False, out_f32=False, tau_cut=TAU_CUT, want_intW=False, ctx=None):
-    """Integration only, for caller-supplied segments ds[R][L-1] (km)."""
+def rt_integrate(ds, nseg, alpha_slab, T, disc_average=False, out_f32=False, tau_cut=TAU_CUT, want_intW=False, ctx=None,
+                 alpha0_slab=None, profile_ray=-1):
+    """Integration only, for caller-supplied segments ds[R][L-1] (km).
+
+    alpha0_slab: the Doppler form -- dtau of step i is (alpha0[i] + alpha[i+1]) ds_i / 2 (rb_rt_desc::alpha0).
+    profile_ray >= 0: returns a dict with Tb, integrated_W and the profiles tau / W / Tb_lyr [F][L-1] of that ray."""
     ctx = ctx or _lib.get_context()
     ctx.use_own_stream()
     ds = f64(np.atleast_2d(ds))
@@ -484,7 +496,17 @@ def rt_integrate(ds, nseg, alpha_slab, T, disc_average=False, out_f32=False, tau
     rt = RtDesc()
     rt.n_freqs, rt.alpha, rt.T = F, ptr(alpha_slab), ptr(T)
     rt.disc_average, rt.out_f32, rt.tau_cut = int(bool(disc_average)), int(bool(out_f32)), float(tau_cut or 0.0)
+    if alpha0_slab is not None:
+        alpha0_slab = f64(alpha0_slab)
+        if alpha0_slab.shape != alpha_slab.shape:
+            raise ValueError('alpha0_slab must have the shape of alpha_slab')
+        rt.alpha0 = ptr(alpha0_slab)
     out = np.empty((R, F), dtype=np.float32 if out_f32 else np.float64)
-    intW = np.empty((R, F)) if want_intW else None
+    intW = np.empty((R, F)) if (want_intW or profile_ray >= 0) else None
+    if profile_ray >= 0:
+        tau, W, Tbl = np.zeros((F, S)), np.zeros((F, S)), np.zeros((F, S))
+        ctx.check(ctx.lib.rb_rt_integrate_profile(ctx.h, C.byref(rt), L, R, S, ptr(ds), ptr(nseg), ptr(out), ptr(intW),
+                                                  int(profile_ray), ptr(tau), ptr(W), ptr(Tbl)))
+        return {'Tb': out, 'integrated_W': intW, 'tau': tau, 'W': W, 'Tb_lyr': Tbl}
     ctx.check(ctx.lib.rb_rt_integrate(ctx.h, C.byref(rt), L, R, S, ptr(ds), ptr(nseg), ptr(out), ptr(intW)))
     return (out, intW) if want_intW else out

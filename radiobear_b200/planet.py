@@ -162,7 +162,8 @@ class Planet:
         self.set_b(b=b, block=block)
         self._pts = None
         local_pts = self._local_points()
-        if not reuse and local_pts is not None:
+        doppler = bool(getattr(self.config, 'Doppler', False))   # per-ray absorption: Brightness._doppler_ray, ray by ray
+        if not reuse and local_pts is not None and not doppler:
             # the ray geometry does not depend on the absorption: start it first, on its own stream
             self.bright.prefetch(local_pts, self.atmos[0], self.config.orientation)
         if not reuse:
@@ -189,7 +190,7 @@ class Planet:
                 which = None
             f32 = self.data_type == 'image'
             world, rank = parallel.world_rank()
-            if world > 1 and len(pts) >= 64 * world and which is None:
+            if world > 1 and len(pts) >= 64 * world and which is None and not doppler:
                 # one process per GPU: shard rows / points, gather to rank 0 (None on the other ranks)
                 rows = (pts[::self.imSize[0], 1], self.imSize[0]) if self.data_type == 'image' else None
                 Tb = parallel.run_points_sharded(self, pts, self.atmos[0], self.alpha[0], out_f32=f32, rows=rows)

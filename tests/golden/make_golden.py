@@ -9,7 +9,7 @@ scratch work directory bootstrapped the way scripts/initial_planet_setup.py:12-3
     python tests/golden/make_golden.py [section ...]
 
 sections: atm fileio plugins plugins_nh3_extra plugins_nh3_full plugins_notrunc alpha rays ray_fields gravity tb neptune uranus image
-          image_full ring c3_full c5_saturn   (default: all; the last four take ~10 min each on 8 cores)
+          image_full ring c3_full c5_saturn doppler   (default: all; image_full .. c5_saturn take ~10 min each on 8 cores)
 
 Every array is float64 exactly as the reference produced it; nothing is post-processed.
 Reference defects driven around: log-sweep strings and float image
@@ -681,6 +681,47 @@ FILEIO_CASES = [('spectrum', [[0.0, 0.0], [0.5, 0.25]], [[100.123, 200.5, 300.25
                 ('image', [[0, 0]] * 25, [[float(i * j) + 0.123 for i in range(4)] for j in range(3)])]
 
 
+def sec_doppler():
+    """Doppler-shifted absorption (brightness.py:80-96, config key `doppler`).  The branch calls `alpha.get_alpha`, the
+    name `Alpha.get_alpha_from_calc` (alpha.py:194) had in earlier versions; with today's class it raises AttributeError
+    (the reference prints "Doppler currently broken since the get_alpha call is different").  ONE change is made to run
+    it, here and not in the reference tree: the old name is restored as a method that returns the total absorption of
+    its single frequency -- the sum over constituents of get_alpha_from_calc's row, which is what the arithmetic under
+    the call expects (dtau = (a0 + a1) * ds / 2 with numbers).  Everything else is the reference's own loop.
+    Jupiter's rotation moves the frequencies by 4e-5 at most; omega_m is multiplied by 100 for the fixture so that the
+    branch changes Tb by far more than the comparison tolerance (the factor is stored)."""
+    from radiobear import alpha as ralpha
+
+    def get_alpha(self, freqs, T, P, gas, gas_dict, cloud, cloud_dict, units='invcm'):
+        return float(self.get_alpha_from_calc(freqs, T, P, gas, gas_dict, cloud, cloud_dict, units)[0].sum())
+    ralpha.Alpha.get_alpha = get_alpha
+    factor = 100.0
+    freqs = [4.0, 22.0, 23.9]
+    bpts = [[0.5, 0.0], [-0.8, 0.3], [0.0, 0.6], [1.2, 1.2]]
+    try:
+        j = planet('jupiter')
+        j.config.omega_m = j.config.omega_m * factor
+        out = {}
+        for flag in (False, True):
+            j.config.Doppler = flag
+            rv = j.run(freqs, b=bpts, reuse_override='False')
+            out[flag] = np.array(j.Tb, dtype=np.float64)
+        dop = [np.array(ray_doppler(j, b)) for b in bpts[:3]]
+        j.config.Doppler = True
+        j.run(freqs, b='disc', reuse_override='False')                 # b = (0, 0): delta_lng = 0, no shift
+        disc = np.array(j.Tb, dtype=np.float64)
+    finally:
+        del ralpha.Alpha.get_alpha
+    print('  Doppler - plain (K):', np.abs(out[True] - out[False]).max(axis=1))
+    save('doppler.npz', freqs=np.array(freqs), b=np.array(bpts), omega_factor=factor, tb_doppler=out[True],
+         tb_plain=out[False], tb_disc=disc, doppler0=dop[0], doppler1=dop[1], doppler2=dop[2])
+
+
+def ray_doppler(p, b):
+    from radiobear import raypath as ray
+    return ray.compute_ds(p.atmos[0], b, p.config.orientation, gtype=None, verbose=False).doppler
+
+
 def sec_fileio():
     """fileIO.FileIO.write (fileIO.py:19-107): the text a reference run writes for each output type."""
     from radiobear import fileIO, data_handling
@@ -701,7 +742,8 @@ def sec_fileio():
 
 SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins_nh3_full': sec_plugins_nh3_full, 'plugins_h2_orton': sec_plugins_h2_orton, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
             'rays': sec_rays, 'ray_fields': sec_ray_fields, 'gravity': sec_gravity, 'tb': sec_tb, 'neptune': sec_neptune, 'uranus': sec_uranus, 'image': sec_image,
-            'image_full': sec_image_full, 'ring': sec_ring, 'c3_full': sec_c3_full, 'c5_saturn': sec_c5_saturn}
+            'image_full': sec_image_full, 'ring': sec_ring, 'c3_full': sec_c3_full, 'c5_saturn': sec_c5_saturn,
+            'doppler': sec_doppler}
 
 if __name__ == '__main__':
     import warnings

@@ -28,13 +28,30 @@ def test_header_symbols_exported():
     assert lib.rb_abi_version() == 1
 
 
-def test_struct_layouts_match_header():
-    # sizes computed from the header by hand: see include/radiobear_b200.h
-    assert ctypes.sizeof(_lib.AlphaDesc) == 12 + 32 + 4 + 3 * 8 + 8 + 4 + 32 + 4 + 8 + 4 + 24 + 4 + 4 * 3 + 4 + 8 or \
-        ctypes.sizeof(_lib.AlphaDesc) % 8 == 0
-    assert _lib.AlphaDesc.freqs.offset == 48
-    assert _lib.GeometryDesc.radius.offset == 8
-    assert ctypes.sizeof(_lib.RtDesc) == 40
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors against the header itself: gcc compiles include/radiobear_b200.h and prints sizeof / offsetof."""
+    import subprocess
+    fields = {'rb_alpha_desc': (_lib.AlphaDesc, ['n_layers', 'formalism', 'freqs', 'gas_col', 'cloud', 'cloud_flags', 'units',
+                                                 'scale', 'freqs_host', 'freqs_per_layer']),
+              'rb_geometry_desc': (_lib.GeometryDesc, ['radius', 'n0', 'orientation', 'gtype', 'limb']),
+              'rb_rt_desc': (_lib.RtDesc, ['n_freqs', 'alpha', 'T', 'disc_average', 'out_f32', 'tau_cut', 'alpha0']),
+              'rb_gravity_model': (_lib.GravityModel, ['radius', 'GM_layer', 'n_J', 'Jn', 'RJ', 'n_vw', 'vwdat', 'latstep', 'max_lat'])}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "radiobear_b200.h"', 'int main(void) {']
+    for st, (_, names) in fields.items():
+        src.append('  printf("{0} %zu\\n", sizeof({0}));'.format(st))
+        for n in names:
+            src.append('  printf("{0}.{1} %zu\\n", offsetof({0}, {1}));'.format(st, n))
+    src += ['  return 0;', '}']
+    c = tmp_path / 'layout.c'
+    c.write_text('\n'.join(src))
+    exe = str(tmp_path / 'layout')
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(c), '-o', exe], check=True)
+    out = dict(line.split() for line in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    for st, (cls, names) in fields.items():
+        assert ctypes.sizeof(cls) == int(out[st]), st
+        for n in names:
+            assert getattr(cls, n).offset == int(out['{}.{}'.format(st, n)]), (st, n)
+    assert _lib.AlphaDesc.freqs.offset == 48 and ctypes.sizeof(_lib.RtDesc) == 48
 
 
 def test_no_gpu_means_loud_failure():

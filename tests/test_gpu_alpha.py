@@ -319,3 +319,38 @@ def test_resident_slab_and_retrieval_loop(tmp_path):
     with pytest.raises((ValueError, RuntimeError)):
         engine.rt_batch(b=pts, alpha_slab=h, T=atm.gas[atm.config.C['T']], radius=atm.property[atm.config.LP['R']],
                         refr_index=atm.property[atm.config.LP['N']], Req=atm.config.Req, Rpol=atm.config.Rpol)
+
+
+def test_per_layer_frequencies(eng):
+    """rb_alpha_desc::freqs_per_layer: every layer at its own frequency list (what the Doppler branch of
+    Brightness.single needs, brightness.py:83-92).  Row l of the result equals a one-layer call with that row's
+    frequencies -- bit for bit, it is the same kernel -- for lists that straddle the 30 GHz band switch and the 26 / 34 GHz
+    interpolation band differently from layer to layer, for both frequencies-per-lane paths; a constant matrix equals the
+    shared-list call; the oracle agrees; h2_orton (table prepared per list) refuses."""
+    from oracle import alpha_oracle as ao
+    a = golden('atm_jupiter.npz')
+    C, Cl = keymap(a['C_keys']), keymap(a['Cl_keys'])
+    kw = dict(formalisms=formalisms_of(a), other_dicts={'h2': {'h2state': 'e'}}, truncate_strength=TRUNC)
+    rng = np.random.default_rng(11)
+    lay = np.arange(0, 1000, 37)
+    gas, cloud = np.ascontiguousarray(a['gas'][:, lay]), np.ascontiguousarray(a['cloud'][:, lay])
+    T, P = gas[C['T']], gas[C['P']]
+    for F in (5, 70, 600):
+        base = np.sort(rng.uniform(1.0, 100.0, F))
+        fm = base[None, :] * (1.0 + 0.2 * rng.uniform(-1.0, 1.0, (len(lay), 1)))      # a different shift per layer
+        got = eng.alpha_layers(fm, T, P, gas, C, cloud=cloud, cloud_dict=Cl, **kw)
+        assert got.shape == (len(lay), F)
+        for i in (0, 7, len(lay) - 1):
+            one = eng.alpha_layers(fm[i], T[i:i + 1], P[i:i + 1], np.ascontiguousarray(gas[:, i:i + 1]), C,
+                                   cloud=np.ascontiguousarray(cloud[:, i:i + 1]), cloud_dict=Cl, **kw)
+            assert np.array_equal(got[i], one[0]), (F, i)
+        same = eng.alpha_layers(np.tile(base, (len(lay), 1)), T, P, gas, C, cloud=cloud, cloud_dict=Cl, **kw)
+        assert np.array_equal(same, eng.alpha_layers(base, T, P, gas, C, cloud=cloud, cloud_dict=Cl, **kw))
+    i = 9
+    ref = ao.get_layers(fm[i], gas, cloud, C, Cl, dict(formalisms_of(a)), other_dicts={'h2': {'h2state': 'e'}},
+                        truncate_strength=TRUNC, layers=[i])[:, 0]
+    assert np.max(relerr(got[i], ref)) < TIGHT
+    with pytest.raises(NotImplementedError):
+        eng.alpha_layers(fm, T, P, gas, C, formalisms=[('h2', 'h2_orton')], other_dicts={'h2': {'h2state': 'e'}})
+    with pytest.raises(ValueError):
+        eng.alpha_layers(fm[:3], T, P, gas, C, **kw)

@@ -98,3 +98,38 @@ def test_planet_run_with_the_gravity_shape():
     assert img[2, 2] == np.float32(2.725)
     tb1 = j.bright.single(pts[1], [10.0], j.atmos[0], j.alpha[0], j.config.orientation)
     assert abs(tb1[0] - tb_g[1, 1]) < 1e-3 and j.bright.travel.r4ds is not None
+
+
+def test_doppler_shifted_absorption():
+    """config Doppler (brightness.py:80-96): the reference's branch, run with its renamed `alpha.get_alpha` call
+    restored (tests/golden/make_golden.py section `doppler`, omega_m x 100).  Here: per-layer frequency lists in the
+    absorption kernel (two launches per ray) + the integration with the slab pair (rb_rt_desc::alpha0)."""
+    d = golden('doppler.npz')
+    j = make_planet('jupiter', 'atm_jupiter.npz')
+    g = golden('ray_fields.npz')
+    j.config.vwlat, j.config.vwdat = list(g['vwlat_jupiter']), list(g['vwdat_jupiter'])      # config.zonal table
+    j.config.omega_m = j.config.omega_m * float(d['omega_factor'])
+    freqs, bpts = [float(x) for x in d['freqs']], [[float(x), float(y)] for x, y in d['b']]
+    j.config.Doppler = False
+    j.run(freqs, b=bpts, reuse_override='False')
+    plain = np.asarray(j.Tb, dtype=np.float64)
+    assert np.max(np.abs(plain - d['tb_plain'])) < 1e-4
+    j.config.Doppler = True
+    rv = j.run(freqs, b=bpts, reuse_override='False')
+    got = np.asarray(j.Tb, dtype=np.float64)
+    assert rv.Tb.shape == (4, 3)
+    assert np.max(np.abs(got - d['tb_doppler'])) < 1e-4, np.abs(got - d['tb_doppler'])
+    assert np.max(np.abs(got - plain)[:2]) > 0.1                     # the branch does something
+    assert np.max(np.abs(got[2] - plain[2])) < 1e-9                  # central meridian: no line-of-sight velocity
+    assert (got[3] == 2.725).all()
+    j.run(freqs, b='disc', reuse_override='False')                   # b = (0, 0): doppler = 1, E2 weighting
+    assert np.max(np.abs(np.asarray(j.Tb, dtype=np.float64) - d['tb_disc'])) < 1e-4
+    # Brightness.single under Doppler: Tb and the profile attributes of the ray
+    j.alpha_layers(freqs, j.atmos)
+    Tb = j.bright.single(bpts[1], freqs, j.atmos[0], j.alpha[0], j.config.orientation)
+    assert np.max(np.abs(np.array(Tb) - d['tb_doppler'][1])) < 1e-4
+    B = j.bright
+    n = len(B.travel.ds)
+    assert B.tau.shape == (3, n) and B.W.shape == (3, n) and B.Tb_lyr.shape == (3, n)
+    assert np.all(np.diff(B.tau, axis=1) >= 0) and np.max(np.abs(B.Tb_lyr[:, -1] / B.integrated_W - np.array(Tb))) < 1e-9
+    assert np.max(np.abs(np.array(B.travel.doppler) - d['doppler1'])) < 1e-12

@@ -367,3 +367,36 @@ def test_gravity_geoid_oracle_vs_reference():
     assert len(ray['ds']) == n == len(fast['ds'])
     assert np.max(np.abs(ray['ds'] / g['ds'][0, :n] - 1.0)) < 1e-12 and np.max(np.abs(ray['r4ds'] / g['r4ds'][0, :n] - 1.0)) < 1e-13
     assert np.max(np.abs(fast['ds'] / g['ds'][0, :n] - 1.0)) < 1e-8
+
+
+def test_doppler_branch_oracle_vs_reference():
+    """Brightness.single with config Doppler (brightness.py:80-96), the reference's branch run with its renamed
+    `alpha.get_alpha` call restored (tests/golden/make_golden.py section `doppler`; omega_m x 100 so that the branch
+    moves Tb by 0.02-0.3 K).  The oracle walks the same steps with the oracle absorption at the shifted frequencies;
+    one ray completely (998 steps x 2 absorption evaluations), and the no-shift cases (central meridian, disc average,
+    sky) against the plain run."""
+    a = golden('atm_jupiter.npz')
+    d = golden('doppler.npz')
+    C, Cl, LP = keymap(a['C_keys']), keymap(a['Cl_keys']), keymap(a['LP_keys'])
+    freqs = d['freqs']
+    kw = dict(other_dicts={'h2': {'h2state': str(a['h2state'])}}, truncate_strength=TRUNC)
+    fa = dict(formalisms_of(a))
+
+    def alpha_at(layer, fv):
+        return ao.get_layers(fv, a['gas'], a['cloud'], C, Cl, fa, layers=[layer], **kw)[:, 0]
+    assert np.max(np.abs(d['tb_doppler'] - d['tb_plain'])[:2]) > 0.1 and float(d['omega_factor']) == 100.0
+    assert np.array_equal(d['tb_doppler'][2], d['tb_plain'][2]) or np.max(np.abs(d['tb_doppler'][2] - d['tb_plain'][2])) < 1e-9
+    assert (d['tb_doppler'][3] == 2.725).all()
+    k = 1                                                      # b = (-0.8, 0.3)
+    ray = ro.compute_ds(a['property'][LP['R']], a['property'][LP['N']], d['b'][k], float(a['Req']), float(a['Rpol']),
+                        a['orientation'], 'ellipse', 'shape')
+    dop = d['doppler%d' % k]
+    assert len(dop) == len(ray['ds'])
+    Tb = rto.integrate_ray_doppler(ray['ds'], ray['layer4ds'], dop, freqs, alpha_at, a['gas'][C['T']])
+    assert np.max(np.abs(Tb - d['tb_doppler'][k])) < 1e-6
+    # doppler == 1 everywhere reduces to the plain loop
+    slab = ao.get_layers(freqs, a['gas'], a['cloud'], C, Cl, fa, **kw)
+    plain = rto.integrate_ray(ray['ds'], ray['layer4ds'], slab, a['gas'][C['T']])
+    same = rto.integrate_ray_doppler(ray['ds'], ray['layer4ds'], np.ones_like(dop), freqs, lambda l, fv: slab[:, l], a['gas'][C['T']])
+    assert np.array_equal(plain, same)
+    assert np.max(np.abs(plain - d['tb_plain'][k])) < 1e-6
