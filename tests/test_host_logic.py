@@ -291,3 +291,56 @@ def test_fileio_read_back_round_trip(tmp_path):
             assert np.allclose(out.b, np.asarray(b), atol=1e-3)
     assert len(io.flist(None, 'dat')) == 4 and io.flist(1, 'dat') == [sorted(io.flist(None, 'dat'))[1]]
     assert len(io.read(None, tag='dat', file_type='spectrum')) == 2
+
+
+def test_doppler_host_logic_builds_the_steps_the_reference_takes(monkeypatch):
+    """Brightness._doppler_ray without a GPU: trace, absorption and integration are replaced by recorders, the host
+    logic in between must ask for exactly what brightness.py:83-92 evaluates -- step i: the lower node (layer i + 1) at
+    f / doppler[i], the upper node (layer i) at f / doppler[i + 1] -- and hand the integration the slab pair in the
+    roles rb_rt_desc::alpha0 defines.  Checked by integrating the recorded slabs with the oracle's plain loop formula
+    against oracle.rt_oracle.integrate_ray_doppler on a synthetic absorption law."""
+    import os
+    from conftest import GOLDEN
+    from oracle import rt_oracle as rto
+    from radiobear_b200 import brightness, raypath
+
+    atm = Atmosphere.from_npz(os.path.join(GOLDEN, 'atm_jupiter.npz'), 'jupiter')
+    L = atm.gas.shape[1]
+    n = 37
+    rng = np.random.default_rng(5)
+    ray = raypath.Ray()
+    ray.update(ds=list(rng.uniform(5.0, 60.0, n)), layer4ds=list(range(n)), doppler=list(1.0 + 0.01 * rng.uniform(-1, 1, n)))
+    monkeypatch.setattr(raypath, 'compute_ds', lambda a, b, o=None, gtype=None, verbose=False: ray)
+    T = atm.gas[atm.config.C['T']]
+
+    def law(layer, fv):                                       # any smooth function of (layer, frequency)
+        return 1e-7 * (1.0 + layer) ** 1.5 * (np.asarray(fv) / 10.0) ** 2
+
+    class FakeAlpha:
+        config = atm.config
+
+        def layers_at(self, fm, a):
+            assert fm.shape == (L, 3)
+            return np.array([law(l, fm[l]) for l in range(L)])
+    seen = {}
+
+    def fake_integrate(ds, nseg, alpha_slab, Tl, disc_average=False, tau_cut=0.0, want_intW=False, alpha0_slab=None,
+                       profile_ray=-1, **kw):
+        seen.update(ds=np.array(ds), nseg=list(nseg), a1=alpha_slab, a0=alpha0_slab)
+        return np.zeros((1, 3)), np.zeros((1, 3))
+    monkeypatch.setattr(brightness.engine, 'rt_integrate', fake_integrate)
+    freqs = [4.0, 22.0, 23.9]
+    B = brightness.Brightness(config=atm.config, verbose=False)
+    B._doppler_ray([0.3, 0.1], freqs, atm, FakeAlpha(), None, False, False)
+    assert seen['nseg'] == [n] and seen['ds'].shape == (1, L - 1) and np.array_equal(seen['ds'][0, :n], ray.ds)
+    # the kernel's recurrence on the recorded slabs (rb_rt_desc::alpha0): dtau_i = (a0[i] + a1[i+1]) ds_i / 2, W from a1[i+1]
+    tau, W, Tb, iW = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3)
+    for i in range(n - 1):
+        h = ray.ds[i] * 1e5 / 2.0
+        tau = tau + (seen['a0'][i] + seen['a1'][i + 1]) * h
+        Wn = seen['a1'][i + 1] * np.exp(-tau)
+        iW = iW + (Wn + W) * h
+        Tb = Tb + (T[i + 1] * Wn + T[i] * W) * h
+        W = Wn
+    ref = rto.integrate_ray_doppler(ray.ds, ray.layer4ds, ray.doppler, freqs, law, T)
+    assert np.max(np.abs(Tb / iW - ref)) < 1e-9

@@ -15,6 +15,10 @@ def main():
     atm, freqs, grid = bench.workload()
     p = Planet('jupiter', atmosphere=atm, verbose=False)
     fl = list(freqs)
+    from radiobear_b200 import _lib
+    ctx = _lib.get_context(0)
+    if os.environ.get('RB_AB_TIMING'):
+        ctx.enable_timing(True)
     for _ in range(4):
         p.run(fl, b=bench.BSTEP, reuse_override='false')
     torch.cuda.synchronize()
@@ -23,6 +27,8 @@ def main():
         t0 = time.perf_counter()
         p.run(fl, b=bench.BSTEP, reuse_override='false')
         ts.append(1e3 * (time.perf_counter() - t0))
+    if os.environ.get('RB_AB_TIMING'):
+        print('   device families inside Planet.run (ms):', {w: round(float(np.median(ctx.kernel_ms_history(w, 16))), 4) for w in ('alpha', 'geometry', 'rt')})
     # the link: one 93 MB device -> pinned host copy
     n = 361201 * 64
     d = torch.empty(n, dtype=torch.float32, device='cuda')
