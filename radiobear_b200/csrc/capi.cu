@@ -773,7 +773,7 @@ static int choose_chunks(const rb_context* ctx, int64_t R, bool rays_path, bool 
   int n = ctx->rt_chunks;
   if (n <= 0) {
     // Planet.run of C4 on one GPU (361 201 rays, 93 MB out): 4 / 6 / 8 / 12 / 16 chunks 4.08 / 3.97 / 3.93 / 3.86 / 3.88 ms
-    // (tools/gpu_session_r2aj.sh); a rank's share on 2-8 GPUs was tuned with 6
+    // (tools/sessions/gpu_session_r2aj.sh); a rank's share on 2-8 GPUs was tuned with 6
     const char* e = getenv("RB_RT_CHUNKS");
     n = e ? atoi(e) : (R >= 200000 ? 12 : 6);
   }

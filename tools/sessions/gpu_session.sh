@@ -1,4 +1,4 @@
-# One GPU-box session (gpurun --timeout 900 -- "bash tools/gpu_session.sh"): GPU test suite, smoke, both bench arms,
+# One GPU-box session (gpurun --timeout 900 -- "bash tools/sessions/gpu_session.sh"): GPU test suite, smoke, both bench arms,
 # ncu --set full of the mixed integration kernel and the ncu launch list of bench.py; everything lands in gpurun_out/.
 mkdir -p gpurun_out
 ( timeout 540 python -m pytest tests -m gpu -x -q --tb=short; echo "pytest exit $?" ) > gpurun_out/pytest_gpu.log 2>&1

@@ -1,4 +1,4 @@
-# bench.py at N ranks (torchrun), NCCL_DEBUG=INFO on stderr:  bash tools/gpu_session_scale.sh N
+# bench.py at N ranks (torchrun), NCCL_DEBUG=INFO on stderr:  bash tools/sessions/gpu_session_scale.sh N
 N=$1
 mkdir -p gpurun_out
 NCCL_DEBUG=INFO timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench exit $? lines $(wc -l < gpurun_out/r2_bench_n$N.json)"
