@@ -240,6 +240,12 @@ __global__ void __launch_bounds__(kSortThreads) ray_compact_kernel(const __grid_
 // (one kernel for the plain and the compacted launch -- g.cidx selects -- so that both run the very same instructions
 //  per ray: two template instantiations were contracted into FMAs differently by the compiler in the start-up and
 //  restart arithmetic, and 743 rays of the C4 image differed in the last bits of ds)
+// RB_GEO_FUSED = 2 / 1: the layer march with one / two latencies taken out of the dependent chain of every segment (see the
+// speculative block).  Built and measured (profiles/r2_ab_geometry_chain.txt): 0.52 / 0.54 ms against 0.48 ms on C4 and
+// slower on a rank's share of eight GPUs too -- the extra FP64 instructions and spills cost more than the latencies save.  Off.
+#ifndef RB_GEO_FUSED
+#define RB_GEO_FUSED 0
+#endif
 __global__ void __launch_bounds__(128, RB_GEO_CTAS) ray_geometry_kernel(const __grid_constant__ GeoK g) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   // streamed trace: count the CTAs that have started.  The integration that waits on g.prog is released (stream
@@ -363,6 +369,41 @@ __global__ void __launch_bounds__(128, RB_GEO_CTAS) ray_geometry_kernel(const __
       const double X0 = X, sq0 = sq, sh0 = shape2;
       double dsv[kSpec];
       bool bad = false;
+#if RB_GEO_FUSED
+      // The chain with two latencies taken out of every segment (X' -> sqrt -> y^2 -> X'' instead of
+      // X' -> sqrt -> y -> y^2 -> shape2 -> X''):
+      //   y^2 = (c0 - sy sqrt(X'))^2 = (c0^2 + sy^2 X') - 2 c0 sy sqrt(X')          one FMA behind the square root
+      //   X'' = X' + shape2 dR2' = (X' + dR2') + y^2 (inve dR2')                     one FMA behind y^2
+      // (the bracketed terms depend on X' only and run beside the square root).  Rounding differs from the plain form
+      // by a few 1e-16 of |r|^2 resp. X; shape2 itself is only needed as the state the block ends with.
+#if RB_GEO_FUSED == 1
+      const double c02 = c0 * c0, sy2 = sy * sy, m2 = -2.0 * c0 * sy;
+#endif
+      double Xn = fma(shape2, g.dr2[layer], X);
+#pragma unroll
+      for (int j = 0; j < kSpec; ++j) {
+        const double sqn = sqrt_seeded(Xn);
+        const double inve = rcp_seeded_scaled(Xn + perp2, -e2);
+        const double ds = sq - sqn;
+        const double yn = fma(-sy, sqn, c0);
+#if RB_GEO_FUSED == 1
+        const double yy = fma(m2, sqn, fma(sy2, Xn, c02));
+#else
+        const double yy = yn * yn;                             // RB_GEO_FUSED == 2: only the second of the two
+#endif
+        const double syy = sy * yn;
+        const double d = fma(g.q, -sqn - syy, syy);
+        bad |= !(ds >= 0.0) | (yn == 0.0) | !(d <= 0.0);
+        dsv[j] = ds;
+        X = Xn; sq = sqn;
+        if (j + 1 < kSpec) {
+          const double dn = g.dr2[layer + j + 1];
+          Xn = fma(yy, inve * dn, Xn + dn);
+        } else {
+          shape2 = fma(yy, inve, 1.0);
+        }
+      }
+#else
 #pragma unroll
       for (int j = 0; j < kSpec; ++j) {
         const double Xn = fma(shape2, g.dr2[layer + j], X);
@@ -377,6 +418,7 @@ __global__ void __launch_bounds__(128, RB_GEO_CTAS) ray_geometry_kernel(const __
         shape2 = fma(yn * yn, inve, 1.0);
         X = Xn; sq = sqn;
       }
+#endif
       if (!bad) {
 #pragma unroll
         for (int j = 0; j < kSpec; ++j) {
