@@ -344,3 +344,28 @@ def test_doppler_host_logic_builds_the_steps_the_reference_takes(monkeypatch):
         W = Wn
     ref = rto.integrate_ray_doppler(ray.ds, ray.layer4ds, ray.doppler, freqs, law, T)
     assert np.max(np.abs(Tb / iW - ref)) < 1e-9
+
+
+def test_point_blocks_weigh_the_pixels_to_copy_for_host_output():
+    """parallel.point_blocks: whole image rows per rank; results that go to the host weigh every pixel of a row (all of
+    them are copied) next to its on-disc pixels (device work), so the ranks holding the sky rows get fewer rows than with
+    the on-disc weight alone; the answer is cached and handed out as a fresh list."""
+    grid = set_utils.image_grid(0.005)
+    ncol = len(grid)
+    cfg = type('Cfg', (), dict(Rpol=66854.0, Req=71492.0, gtype='ellipse'))()
+    for world in (2, 4, 8):
+        host = parallel.point_blocks(ncol * ncol, cfg, (grid, ncol), world)
+        dev = parallel.point_blocks(ncol * ncol, cfg, (grid, ncol), world, host_output=False)
+        for parts in (host, dev):
+            assert parts[0][0] == 0 and parts[-1][1] == ncol * ncol
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            assert all(a % ncol == 0 and b % ncol == 0 for a, b in parts)
+        rows_host = [(b - a) // ncol for a, b in host]
+        rows_dev = [(b - a) // ncol for a, b in dev]
+        assert max(rows_host) < max(rows_dev) or world == 2       # the sky-row blocks at both ends shrink
+        assert rows_host[0] <= rows_dev[0] and rows_host[-1] <= rows_dev[-1]
+        again = parallel.point_blocks(ncol * ncol, cfg, (grid, ncol), world)
+        assert again == host and again is not host
+        again.append('x')                                          # a caller's list: the cache must not see this
+        assert parallel.point_blocks(ncol * ncol, cfg, (grid, ncol), world) == host
+    assert parallel.point_blocks(10, cfg, None, 4) == parallel.partition_even(10, 4)
