@@ -3,6 +3,8 @@
 API mirror of Brightness.single (brightness.py:30-126).  `single` is the R = 1 case of `batch`,
 which runs geometry + integration for any number of impact points in two kernel launches.
 """
+import os.path
+
 import numpy as np
 
 from . import engine
@@ -122,3 +124,70 @@ class Brightness:
                 if w < 0.96:
                     print("Weight correction at {:.2f} is {:.4f} (showing below 0.96)".format(f, w))
         return self.Tb
+
+    # ---- profile tables of the last ray (brightness.py:128-250): the text formats the reference's users read back ----
+    def _table(self, filename, columns, tight=False):
+        """One row per segment: repr(P) <tab> z (2 decimals) <tab> one repr(value) per frequency.  `columns[i][j]` is
+        frequency i at segment j.  `tight` is the weight file's variant (no tab before 'GHz' or the line end)."""
+        nF, n = len(self.freqs), len(self.P)
+        lines = ['#P  \tz  \t' + ''.join('{:.2f}\t'.format(f) for f in self.freqs)]
+        for j in range(n):
+            lines.append('{}\t{:.2f}\t'.format(repr(self.P[j]), self.z[j])
+                         + ''.join('{}\t'.format(repr(columns[i][j])) for i in range(nF)))
+        if tight:
+            lines = [ln.strip() for ln in lines]
+        with open(filename, 'w') as fp:
+            fp.write(lines[0] + 'GHz\n')
+            for ln in lines[1:]:
+                fp.write(ln + '\n')
+        return '{} ({} x {})'.format(filename, nF, n)
+
+    def saveAlpha(self, filename=None, path='.'):
+        """Absorption of the layers the ray crossed, [segment][frequency] (brightness.py:166-183); the only one of the
+        four tables that honours `path` in the reference, and it returns nothing."""
+        self._table(os.path.join(path, 'alpha.out' if filename is None else filename), self.alpha.layers)
+
+    def saveWeight(self, norm=False, filename=None, path='.'):
+        """Weighting functions, optionally each divided by its maximum (brightness.py:185-208).  Written to the working
+        directory like the reference does (`path` is accepted and unused there)."""
+        W = self.W
+        if norm:
+            W = [np.asarray(w) / np.max(w) for w in W]
+        else:
+            W = [np.asarray(w) / 1.0 for w in W]
+        return self._table('wgt.out' if filename is None else filename, W, tight=True)
+
+    def saveTau(self, filename=None, path='.'):
+        """Optical depth down to each segment (brightness.py:210-228); working directory, see saveWeight -- but `path`
+        is joined (and the result dropped) there, so path=None raises TypeError here too."""
+        filename = 'tau.out' if filename is None else filename
+        os.path.join(path, filename)
+        return self._table(filename, self.tau)
+
+    def saveTblayer(self, filename=None, path='.'):
+        """Brightness accumulated down to each segment (brightness.py:230-250); working directory, see saveTau."""
+        filename = 'tblayer.out' if filename is None else filename
+        os.path.join(path, filename)
+        return self._table(filename, self.Tb_lyr)
+
+    def savertm(self, tag=None, path=None):
+        """All four tables (brightness.py:128-149).  The reference hands (filename, path) to saveWeight, whose first
+        parameter is `norm`: with a tag the weights come out normalised, and the file is named `path` ('wgt.out' when
+        path is None -- and then saveTau raises TypeError; a directory raises IsADirectoryError).  Kept as it is, so that
+        the same call leaves the same files and the same exception (tests/golden/rtm_tables.npz)."""
+        name = (lambda kind: None) if tag is None else (lambda kind: '{}_{}.out'.format(kind, tag))
+        self.saveAlpha(name('alpha'), self.config.output_directory)
+        self.saveWeight(norm=name('wgt') is not None, filename=path)
+        self.saveTau(name('tau'), path)
+        self.saveTblayer(name('tblayer'), path)
+
+    def saveit(self):
+        """One file per frequency: pressure, absorption, weight, optical depth, brightness per segment
+        (brightness.py:151-164)."""
+        for i, f in enumerate(self.freqs):
+            filename = 'pawtt_{:.3f}.out'.format(f)
+            print("{}:  Pressure, alpha, weight, tau, Tb".format(filename))
+            with open(filename, 'w') as fp:
+                for j in range(len(self.P)):
+                    cols = (self.P[j], self.alpha.layers[i][j], self.W[i][j], self.tau[i][j], self.Tb_lyr[i][j])
+                    fp.write('\t'.join(repr(c) for c in cols) + '\n')

@@ -42,16 +42,33 @@ class Data:
             out.append('Tb = ' + ' '.join('{:6.1f}'.format(x) for x in np.atleast_1d(self.Tb[i])) + '  K')
         return '\n'.join(out) + '\n'
 
-    def show(self, include=('header', 'start', 'stop', 'f', 'b', 'Tb'), indent=1):
+    def show(self, include=('header', 'start', 'stop', 'f', 'b', 'Tb', 'log'), indent=1):
         tab = indent * '\t'
         for v in include:
-            if v not in self.allowed_parameters:
+            if v == 'log':
+                self.show_log(indent=indent)
+            elif v not in self.allowed_parameters:
                 continue
-            if v == 'header':
-                print('{}<<<Header>>>'.format(tab))
-                for k, h in (self.header or {}).items():
-                    print('{}\t{:20s}     {}'.format(tab, k, h))
+            elif v == 'header':
+                self.show_header(indent=indent)
             elif v == 'f':
                 print('{}<<<freq>>> {} {}'.format(tab, self.f, self.freqUnit))
             else:
                 print('{}<<<{}>>>  {}'.format(tab, v, getattr(self, v)))
+
+    def show_header(self, indent=1):
+        """data_handling.py:67-74."""
+        print('{}<<<Header>>>'.format(indent * '\t'))
+        for k, h in self.header.items():
+            print('{}{:20s}     {}'.format((indent + 1) * '\t', k, h))
+        print()
+
+    def show_log(self, indent=1):
+        """Close the run's log and print the file (data_handling.py:76-85)."""
+        if self.log is not None:
+            self.log.close()
+        print('{}<<<Log>>>  {}'.format(indent * '\t', self.logfile))
+        with open(self.logfile) as fp:
+            for line in fp:
+                print(line.strip())
+        print("-----------------------------------\n")

@@ -32,6 +32,25 @@ def computeAspect(Q, f=1.0):
     return tip, rotate
 
 
+def _about_x_then(tip, rotate, v, x_last):
+    ct, st, cr, sr = np.cos(tip), np.sin(tip), np.cos(rotate), np.sin(rotate)
+    about_z = np.array([[ct, -st, 0.0], [st, ct, 0.0], [0.0, 0.0, 1.0]])
+    about_x = np.array([[1.0, 0.0, 0.0], [0.0, cr, -sr], [0.0, sr, cr]])
+    v = np.asarray(v, dtype=np.float64)
+    return about_x @ (about_z @ v) if x_last else about_z @ (about_x @ v)
+
+
+def rotate2planet(rotate, tip, b):
+    """Observer frame -> planet frame: about z by `tip`, then about x by `rotate` (raypath.py:47-51; the order the ray
+    trace kernel applies to the impact vector)."""
+    return _about_x_then(tip, rotate, b, True)
+
+
+def rotate2obs(rotate, tip, b):
+    """The two rotations in the other order (raypath.py:54-57); rotate2obs(-rotate, -tip, .) undoes rotate2planet."""
+    return _about_x_then(tip, rotate, b, False)
+
+
 def _geometry_args(atm, orientation, gtype):
     cfg = atm.config
     LP = cfg.LP

@@ -8,7 +8,7 @@ scratch work directory bootstrapped the way scripts/initial_planet_setup.py:12-3
 
     python tests/golden/make_golden.py [section ...]
 
-sections: atm fileio plugins plugins_nh3_extra plugins_nh3_full plugins_notrunc alpha rays ray_fields gravity tb neptune uranus image
+sections: atm fileio rtm_tables plugins plugins_nh3_extra plugins_nh3_full plugins_notrunc alpha rays ray_fields gravity tb neptune uranus image
           image_full ring c3_full c5_saturn doppler   (default: all; image_full .. c5_saturn take ~10 min each on 8 cores)
 
 Every array is float64 exactly as the reference produced it; nothing is post-processed.
@@ -722,6 +722,22 @@ def ray_doppler(p, b):
     return ray.compute_ds(p.atmos[0], b, p.config.orientation, gtype=None, verbose=False).doppler
 
 
+def data_show(d):
+    """What Data.show / show_header / show_log print (data_handling.py:51-85) for the last FILEIO case with a log file."""
+    import contextlib
+    import io
+    with open('show_case.log', 'w') as fp:
+        fp.write('  first line  \nsecond\n')
+    d.set('logfile', 'show_case.log')
+    d.set('start', 'START')
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        d.show()
+        d.show(include=['f', 'nonsense', 'type'], indent=0)
+        d.show_header(indent=2)
+    return buf.getvalue()
+
+
 def sec_fileio():
     """fileIO.FileIO.write (fileIO.py:19-107): the text a reference run writes for each output type."""
     from radiobear import fileIO, data_handling
@@ -737,10 +753,66 @@ def sec_fileio():
         fn = fileIO.FileIO().write('fileio_case.dat', d)
         out['case{}'.format(n)] = np.array(open(fn).read())
         out['type{}'.format(n)] = np.array(typ)
+    out['show'] = np.array(data_show(d))
     save('fileio.npz', **out)
 
 
-SECTIONS = {'atm': sec_atm, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins_nh3_full': sec_plugins_nh3_full, 'plugins_h2_orton': sec_plugins_h2_orton, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
+def rtm_state(B):
+    """Side attributes of a finished Brightness.single call (brightness.py:114-123), seeded, 3 freqs x 7 segments,
+    set on a Brightness instance of either implementation."""
+    rng = np.random.default_rng(11)
+    nF, n = 3, 7
+    B.freqs = [1.0, 22.235, 100.5]
+    B.P = np.geomspace(0.01, 3000.0, n) * (1.0 + 0.1 * rng.random(n))
+    B.z = np.linspace(250.123, -800.987, n)
+    B.tau = np.cumsum(rng.random((nF, n)) * 3.0, axis=1)
+    B.W = rng.random((nF, n)) * np.exp(-B.tau)
+    B.Tb_lyr = np.cumsum(rng.random((nF, n)) * 60.0, axis=1)
+    B.alpha = type('A', (), {})()
+    B.alpha.layers = rng.random((nF, n + 1)) * 1e-5
+    return B
+
+
+RTM_CALLS = [('savertm', (), {}), ('savertm', (None, '.'), {}), ('savertm', ('t1', '.'), {}), ('savertm', ('t2', 'wgt_path.out'), {}),
+             ('saveWeight', (True,), {}), ('saveWeight', (False, 'w.out', 'nowhere'), {}), ('saveTau', ('tau2.out', 'nowhere'), {}),
+             ('saveit', (), {})]
+
+
+def rtm_run(B, outdir):
+    """Run RTM_CALLS in an empty working directory -> {'<call index>/<relative file name>': text, 'ret<i>': repr}."""
+    out = {}
+    here = os.getcwd()
+    for n, (name, a, kw) in enumerate(RTM_CALLS):
+        d = tempfile.mkdtemp(prefix='rtm_', dir=outdir)
+        os.mkdir(os.path.join(d, 'Output'))
+        B.config = type('C', (), {'output_directory': 'Output'})()
+        os.chdir(d)
+        try:
+            ret = repr(getattr(B, name)(*a, **kw))
+        except Exception as e:                                  # savertm's default path=None fails in saveTau
+            ret = 'raised ' + type(e).__name__
+        finally:
+            os.chdir(here)
+        out['ret{}'.format(n)] = np.array(ret)
+        for root, _, files in os.walk(d):
+            for fn in files:
+                rel = os.path.relpath(os.path.join(root, fn), d)
+                out['{}/{}'.format(n, rel)] = np.array(open(os.path.join(root, fn)).read())
+    return out
+
+
+def sec_rtm_tables():
+    """Brightness.savertm / saveAlpha / saveWeight / saveTau / saveTblayer / saveit (brightness.py:128-250): the files
+    (names, locations, bytes) and return values the reference leaves for a fixed state."""
+    import gc
+    from radiobear import brightness
+    B = rtm_state(object.__new__(brightness.Brightness))
+    out = rtm_run(B, os.getcwd())
+    gc.collect()
+    save('rtm_tables.npz', **out)
+
+
+SECTIONS = {'atm': sec_atm, 'rtm_tables': sec_rtm_tables, 'fileio': sec_fileio, 'plugins_nh3_extra': sec_plugins_nh3_extra, 'plugins_nh3_full': sec_plugins_nh3_full, 'plugins_h2_orton': sec_plugins_h2_orton, 'plugins': sec_plugins, 'plugins_notrunc': sec_plugins_notrunc, 'alpha': sec_alpha,
             'rays': sec_rays, 'ray_fields': sec_ray_fields, 'gravity': sec_gravity, 'tb': sec_tb, 'neptune': sec_neptune, 'uranus': sec_uranus, 'image': sec_image,
             'image_full': sec_image_full, 'ring': sec_ring, 'c3_full': sec_c3_full, 'c5_saturn': sec_c5_saturn,
             'doppler': sec_doppler}

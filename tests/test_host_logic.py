@@ -179,6 +179,13 @@ def test_fileio_text_formats_match_reference(tmp_path):
         d.set('header', {'z': '# z line', 'a': '# a line', 'data-type': '#* type:  ' + typ})
         fn = fileIO.FileIO(directory=str(tmp_path)).write(str(tmp_path / 'out{}.dat'.format(n)), d)
         assert open(fn).read() == str(g['case{}'.format(n)])
+    from make_golden import data_show
+    here = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        assert data_show(d) == str(g['show'])                   # Data.show / show_header / show_log
+    finally:
+        os.chdir(here)
 
 
 def test_bench_reference_arm_contract():
@@ -369,3 +376,36 @@ def test_point_blocks_weigh_the_pixels_to_copy_for_host_output():
         again.append('x')                                          # a caller's list: the cache must not see this
         assert parallel.point_blocks(ncol * ncol, cfg, (grid, ncol), world) == host
     assert parallel.point_blocks(10, cfg, None, 4) == parallel.partition_even(10, 4)
+
+
+def test_brightness_profile_tables_match_reference(tmp_path):
+    """Brightness.savertm / saveAlpha / saveWeight / saveTau / saveTblayer / saveit (brightness.py:128-250): same file
+    names, locations, bytes, return values and exceptions as the reference for the same state of the last ray."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    from make_golden import rtm_state, rtm_run, RTM_CALLS
+    from radiobear_b200 import brightness
+    g = golden('rtm_tables.npz')
+    here = os.getcwd()
+    try:
+        got = rtm_run(rtm_state(object.__new__(brightness.Brightness)), str(tmp_path))
+    finally:
+        os.chdir(here)
+    assert sorted(got) == sorted(g.files) and len(RTM_CALLS) == 8
+    for k in g.files:
+        assert str(got[k]) == str(g[k]), k
+
+
+def test_frame_rotations_of_the_ray_module():
+    """raypath.rotate2planet / rotate2obs (raypath.py:47-57) against the oracle's rotation matrices; one undoes the other
+    with the angles negated."""
+    from radiobear_b200 import raypath
+    from oracle import ray_oracle as ro
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        tip, rot = rng.uniform(-1.5, 1.5, 2)
+        v = rng.normal(size=3)
+        p = raypath.rotate2planet(rot, tip, v)
+        assert np.array_equal(p, ro.rotX(rot, ro.rotZ(tip, v)))
+        assert np.array_equal(raypath.rotate2obs(rot, tip, v), ro.rotZ(tip, ro.rotX(rot, v)))
+        assert np.max(np.abs(raypath.rotate2obs(-rot, -tip, p) - v)) < 1e-14
