@@ -180,5 +180,6 @@ class FileIO(object):
     def show(self, property='all'):
         for filename, d in getattr(self, 'data', {}).items():
             print(filename)
-            d.show(include=d.allowed_parameters if property == 'all' else
-                   ([property] if isinstance(property, str) else property))
+            keys = d.allowed_parameters if property == 'all' else ([property] if isinstance(property, str) else property)
+            # the log of the run is printed when the file's header names one that is still there
+            d.show(include=[k for k in keys if k != 'log' or (d.logfile and os.path.isfile(str(d.logfile)))])

@@ -67,6 +67,8 @@ class Planet:
             self.log = rblog.LogIt('{}/{}_{}.log'.format(self.config.log_directory, self.planet,
                                                          start.strftime("%Y%m%d_%H%M%S")))
             self.log.add(self.planet + ' start ' + str(start), self.verbose)
+            for entry in (self.planet, config_file, self.config.show(print_it=False)):     # planet.py:47-52
+                self.log.add(entry, False)
         else:
             self.log = None
         self.data_return = data_handling.Data()
@@ -170,6 +172,10 @@ class Planet:
             self.freqs = freqs
             self.freqUnit = utils.proc_unit(freqUnit)
             self.scale, self.get_alpha, self.save_alpha = scale, get_alpha, save_alpha
+            if self.log is not None:                                                      # planet.py:103-110
+                unit = utils.proc_unit(freqUnit)
+                self.log.add('{} at {} frequencies ({} - {} {})'.format(self.planet, len(freqs), freqs[0], freqs[-1], unit)
+                             if self.verbose else '{} at {} {}'.format(self.planet, freqs[0], unit), self.verbose)
             self.alpha_layers(freqs=self.freqs, atmos=self.atmos, scale=scale, get_alpha=get_alpha,
                               save_alpha=save_alpha)
             if self.verbose:
@@ -205,6 +211,9 @@ class Planet:
                                             self.config.orientation, out_f32=f32)
                     Tb[sel] = res['Tb']
         runStop = datetime.datetime.now()
+        if self.log is not None:
+            self.log.add('Run start ' + str(runStart), False)
+            self.log.add('Run stop ' + str(runStop), False)
         if self.data_type == 'image' and Tb is not None:
             ncol, nrow = self.imSize[0], len(self.b) // self.imSize[0]
             Tb = Tb.reshape(nrow, ncol, F)

@@ -133,3 +133,52 @@ def test_doppler_shifted_absorption():
     assert B.tau.shape == (3, n) and B.W.shape == (3, n) and B.Tb_lyr.shape == (3, n)
     assert np.all(np.diff(B.tau, axis=1) >= 0) and np.max(np.abs(B.Tb_lyr[:, -1] / B.integrated_W - np.array(Tb))) < 1e-9
     assert np.max(np.abs(np.array(B.travel.doppler) - d['doppler1'])) < 1e-12
+
+
+def test_log_output_files_and_profile_tables(tmp_path, capsys):
+    """write_log_file / write_output_files through Planet.run (planet.py:45-52, 103-146) and the profile tables of the
+    last ray (Brightness.saveAlpha / saveWeight / saveTau / saveTblayer, brightness.py:166-250): files land where the
+    reference puts them, read back to the values the run returned."""
+    from radiobear_b200.atmosphere import Atmosphere
+    from radiobear_b200.planet import Planet
+    atm = Atmosphere.from_npz(os.path.join(GOLDEN, 'atm_jupiter.npz'), 'jupiter')
+    j = Planet('jupiter', atmosphere=atm, verbose=False, write_log_file=True, write_output_files=True,
+               log_directory=str(tmp_path / 'Logs'), output_directory=str(tmp_path / 'Output'))
+    freqs = [2.0, 22.0]
+    rv = j.run(freqs, b=[[0.0, 0.0], [0.4, 0.3]])
+    tb = np.array(rv.Tb, dtype=np.float64)
+    outs = os.listdir(tmp_path / 'Output')
+    assert len(outs) == 1 and outs[0].startswith('Jupiter_spectrum_') and outs[0].endswith('.dat')
+    back = j.fIO.read(file_type='spectrum')
+    d = list(back.values())[0]
+    assert np.allclose(d.f, freqs) and np.max(np.abs(d.Tb - tb)) < 1e-3
+    rv.show(include=['log'])                                         # closes the log and prints it
+    text = capsys.readouterr().out
+    assert '<<<Log>>>' in text and 'Run start ' in text and 'Run stop ' in text and 'Run parameters:' in text
+    assert 'Jupiter at 2.0 GHz' in text                              # verbose False: the short frequency line
+    # the profile tables of one ray
+    B = j.bright
+    Tb1 = B.single([0.4, 0.3], freqs, j.atmos[0], j.alpha[0], j.config.orientation)
+    assert np.max(np.abs(np.array(Tb1) - tb[1])) < 1e-3
+    here = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        B.saveAlpha('alpha.out', str(tmp_path))
+        assert B.saveTau() == 'tau.out (2 x {})'.format(len(B.P))
+        B.saveTblayer()
+        B.saveWeight(norm=True)
+        B.saveit()
+        def table(fn):
+            rows = [ln.replace('np.float64(', '').replace(')', '').split() for ln in open(fn) if not ln.startswith('#')]
+            return np.array(rows, dtype=np.float64)
+        n = len(B.P)
+        t = table('tau.out')
+        assert t.shape == (n, 4) and np.array_equal(t[:, 0], B.P) and np.array_equal(t[:, 2:], B.tau.T)
+        assert np.array_equal(table('tblayer.out')[:, 2:], B.Tb_lyr.T)
+        assert np.array_equal(table('alpha.out')[:, 2:], np.asarray(j.alpha[0].layers)[:, :n].T)
+        w = table('wgt.out')[:, 2:]
+        assert np.allclose(w.max(axis=0), 1.0) and np.allclose(w * B.W.max(axis=1), B.W.T, rtol=1e-14, atol=0)
+        p = table('pawtt_22.000.out')
+        assert p.shape == (n, 5) and np.array_equal(p[:, 3], B.tau[1]) and np.array_equal(p[:, 4], B.Tb_lyr[1])
+    finally:
+        os.chdir(here)

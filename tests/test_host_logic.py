@@ -409,3 +409,30 @@ def test_frame_rotations_of_the_ray_module():
         assert np.array_equal(p, ro.rotX(rot, ro.rotZ(tip, v)))
         assert np.array_equal(raypath.rotate2obs(rot, tip, v), ro.rotZ(tip, ro.rotX(rot, v)))
         assert np.max(np.abs(raypath.rotate2obs(-rot, -tip, p) - v)) < 1e-14
+
+
+def test_planet_run_writes_log_and_output_file(tmp_path, monkeypatch, capsys):
+    """Host side of Planet.run with write_log_file / write_output_files (planet.py:45-52, 103-146): absorption and
+    integration replaced by recorders; the log holds what the reference logs, the spectrum file reads back."""
+    from radiobear_b200.planet import Planet
+    from conftest import GOLDEN
+    atm = Atmosphere.from_npz(os.path.join(GOLDEN, 'atm_jupiter.npz'), 'jupiter')
+    j = Planet('jupiter', atmosphere=atm, verbose=False, write_log_file=True, write_output_files=True,
+               log_directory=str(tmp_path / 'Logs'), output_directory=str(tmp_path / 'Output'))
+    want = np.array([[500.25, 140.5], [480.125, 139.75]])
+    monkeypatch.setattr(j, 'alpha_layers', lambda **kw: None)
+    monkeypatch.setattr(j.bright, 'prefetch', lambda *a, **kw: None)
+    monkeypatch.setattr(j.bright, 'batch', lambda pts, *a, **kw: {'Tb': want.copy()})
+    rv = j.run([2.0, 22.0], b=[[0.0, 0.0], [0.4, 0.3]])
+    outs = os.listdir(tmp_path / 'Output')
+    assert len(outs) == 1 and outs[0].startswith('Jupiter_spectrum_') and outs[0].endswith('.dat')
+    d = list(j.fIO.read(file_type='spectrum').values())[0]
+    assert np.allclose(d.f, [2.0, 22.0]) and np.max(np.abs(d.Tb - want)) < 1e-3
+    assert rv.header['log-file:'] == '#* logfile: ' + j.log.logfile
+    capsys.readouterr()
+    rv.show(include=['log'])
+    text = capsys.readouterr().out
+    for piece in ('<<<Log>>>', 'Jupiter start ', 'config.par', 'Run parameters:', 'Jupiter at 2.0 GHz', 'Run start ', 'Run stop '):
+        assert piece in text, piece
+    j.fIO.show()                                                     # header + values of the file read back; no log key
+    assert outs[0] in capsys.readouterr().out
