@@ -99,3 +99,55 @@ def is_number(x):
 
 def as_float_list(x):
     return [float(v) for v in np.atleast_1d(x)]
+
+
+# radio band names by lower / upper edge in GHz (utils.py:79-82)
+rfBands = {'HF': (0.003, 0.03), 'VHF': (0.03, 0.3), 'UHF': (0.3, 1.0), 'L': (1.0, 2.0), 'S': (2.0, 4.0), 'C': (4.0, 8.0),
+           'X': (8.0, 12.0), 'Ku': (12.0, 18.0), 'K': (18.0, 26.5), 'Ka': (26.5, 40.0), 'Q': (40.0, 50.0), 'V': (50.0, 75.0),
+           'W': (75.0, 110.0)}
+get_data_from = data_line                                       # the reference's name (utils.py:152)
+
+
+def getRFband(freq, unit='GHz'):
+    """Band letter of a frequency, None outside 3 MHz - 110 GHz (utils.py:105-111)."""
+    ghz = freq * Units[unit] / Units['GHz']
+    return next((name for name, (lo, hi) in rfBands.items() if lo <= ghz < hi), None)
+
+
+def invertDictionary(dic, reverse=False):
+    """value -> key map and its sorted keys (utils.py:114-120)."""
+    inverse = {v: k for k, v in dic.items()}
+    return inverse, sorted(inverse, reverse=reverse)
+
+
+def rb_path(add_path=None):
+    """Directory of the package, optionally joined with a sub-path (utils.py:25-30)."""
+    import os
+    here = os.path.dirname(__file__)
+    return here if add_path is None else os.path.join(here, add_path)
+
+
+def ls(directory='Output', tag='dat', show=True, returnList=False):
+    """Numbered list of the non-hidden files of a directory whose name contains `tag` (utils.py:123-136)."""
+    import os
+    files = [os.path.join(directory, name) for name in os.listdir(directory)
+             if name[0] != '.' and (tag is None or (isinstance(tag, str) and tag in name))]
+    if show:
+        for i, name in enumerate(files):
+            print('{}:  {}'.format(i, name))
+    return files if returnList else None
+
+
+def get_expected_number_of_entries(fp):
+    """Most frequent number of floats per data line of an open table; ValueError when the other line lengths together
+    occur more than half as often (utils.py:163-182).  Rewinds the file."""
+    counts = {}
+    for line in fp:
+        vals = data_line(line)
+        if vals is not None:
+            counts[len(vals)] = counts.get(len(vals), 0) + 1
+    fp.seek(0)
+    by_count, ordered = invertDictionary(counts, reverse=True)
+    if len(ordered) > 1 and 2 * sum(ordered[1:]) > ordered[0]:
+        raise ValueError("Not enough data lines in file: {}".format(ordered))
+    return by_count[ordered[0]]

@@ -436,3 +436,32 @@ def test_planet_run_writes_log_and_output_file(tmp_path, monkeypatch, capsys):
         assert piece in text, piece
     j.fIO.show()                                                     # header + values of the file read back; no log key
     assert outs[0] in capsys.readouterr().out
+
+
+def test_small_utilities_against_the_live_reference(tmp_path):
+    """utils.getRFband / invertDictionary / ls / get_expected_number_of_entries (utils.py:105-182) give what the
+    reference's give (build container only: the reference is imported)."""
+    import sys
+    import io
+    if not os.path.isdir('/root/reference/radiobear'):
+        pytest.skip('reference not present')
+    sys.path.insert(0, '/root/reference')
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ref_utils', '/root/reference/radiobear/utils.py')
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    for f, u in [(0.001, 'GHz'), (1.0, 'GHz'), (1.9999, 'GHz'), (22.0, 'GHz'), (26.5, 'GHz'), (109.0, 'GHz'), (110.0, 'GHz'), (1400.0, 'MHz')]:
+        assert utils.getRFband(f, u) == ref.getRFband(f, u)
+    d = {'a': 3, 'b': 1, 'c': 2}
+    assert utils.invertDictionary(d) == ref.invertDictionary(d) and utils.invertDictionary(d, True) == ref.invertDictionary(d, True)
+    for name in ('x.dat', 'y.dat', '.hidden.dat', 'z.txt'):
+        (tmp_path / name).write_text('')
+    for tag in ('dat', None, 'txt'):
+        assert sorted(utils.ls(str(tmp_path), tag, show=False, returnList=True)) == \
+            sorted(ref.ls(str(tmp_path), tag, show=False, returnList=True))
+    table = '# comment\n1 2 3 4\n5 6 7 8\n1 2\nbad line here x\n9 9 9 9\n'
+    assert utils.get_expected_number_of_entries(io.StringIO(table)) == ref.get_expected_number_of_entries(io.StringIO(table)) == 4
+    bad = '10 20 30\n' * 3 + '10 20\n' * 2 + '10 20 30 40\n'
+    for mod in (utils, ref):
+        with pytest.raises(ValueError):
+            mod.get_expected_number_of_entries(io.StringIO(bad))
