@@ -345,7 +345,7 @@ def build_geometry_desc(L, n0, n1, Req, Rpol, orientation, gtype, limb, gravity_
             raise ValueError("gtype 'gravity' needs the gravity model of the planet (GM profile, Jn, RJ, omega_m, zonal winds)")
         set_gravity_model(radius, **gravity_model)
     if gtype not in GTYPE:
-        raise NotImplementedError("gtype '{}' is not built (ellipse / circle / sphere only)".format(gtype))
+        raise NotImplementedError("gtype '{}' is not built (ellipse / circle / sphere / gravity; 'reference' raises in the reference too, shape.py:107)".format(gtype))
     g = GeometryDesc()
     g.n_layers = L
     g.n0, g.n1 = float(n0), float(n1)
