@@ -254,9 +254,38 @@ class Alpha:
                                    np.ascontiguousarray(atm.gas[:, sl]), C,
                                    cloud=np.ascontiguousarray(atm.cloud[:, sl]) if np.size(atm.cloud) else None,
                                    cloud_dict=atm.config.Cl, formalisms=self.formalisms(), other_dicts=self.other_dict,
-                                   units=units, scale=None if isinstance(lscale, dict) else lscale,
+                                   units=units, scale=self._one_layer_scale(lscale),
                                    truncate_strength=self.truncate_strength, truncate_freq=self.truncate_freq)
         return slab[0]
+
+    def _one_layer_scale(self, lscale):
+        """The scale of one layer as the reference hands it around (a number, or {constituent: number}, the value
+        get_layer_scale builds per layer, alpha.py:235-259) -> the request form of a one-layer absorption call.  Names
+        that are not constituents are ignored like in total_layer_alpha (alpha.py:182-184)."""
+        if isinstance(lscale, dict):
+            return {k: [float(v)] for k, v in lscale.items() if k in self.ordered_constituents}
+        return lscale
+
+    def total_layer_alpha(self, absorb, lscale):
+        """Scale-sum of one layer's per-constituent absorption absorb[F][C] (the array get_alpha_from_calc returns,
+        columns in ordered_constituents order) -> total[F] (alpha.py:151-192).  `lscale`: a number for all constituents
+        or {constituent: number}; constituents that are not named keep their value, names that are not constituents are
+        ignored like in the reference.  Device scale-sum (rb_alpha_scale_sum, L = 1)."""
+        absorb = np.ascontiguousarray(absorb, dtype=np.float64)
+        if absorb.ndim != 2:
+            raise ValueError('absorb must be [F][C], got shape {}'.format(absorb.shape))
+        ncon = absorb.shape[1]
+        if utils.isanynum(lscale):
+            m = np.full((ncon, 1), float(lscale))
+        else:
+            m = np.ones((ncon, 1))
+            for j, name in enumerate(list(self.ordered_constituents)[:ncon]):
+                if name in lscale:
+                    m[j, 0] = float(lscale[name])
+        total, scaled = engine.alpha_scale_sum(absorb[None], m, want_cube=True)
+        if getattr(self, '_save_alpha_memfil', False):             # the reference's per-layer cache list
+            self.tosave.append(scaled[0])
+        return total[0]
 
     def get_alpha_from_calc(self, freqs, T, P, gas, gas_dict, cloud, cloud_dict, units='invcm'):
         """Per-constituent absorption of one (T, P, X) point -> [F][C] (alpha.py:194-216)."""

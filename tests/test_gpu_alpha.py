@@ -189,6 +189,24 @@ def test_alpha_object_api(tmp_path):
     assert np.max(relerr(one, al['layers'][:, 500])) < TIGHT
     with pytest.raises(ValueError):
         A.get_layers(list(al['freqs']), atm, scale={'bogus': [1.0] * 1000})
+    # one layer the way alpha.py:218-233 does it: per-constituent absorption, then the scale-sum of that layer
+    C = atm.config.C
+    freqs = list(al['freqs'])
+    absorb = A.get_alpha_from_calc(freqs, atm.gas[C['T']][500], atm.gas[C['P']][500], atm.gas[:, 500], C,
+                                   atm.cloud[:, 500] if np.size(atm.cloud) else None, atm.config.Cl)
+    assert absorb.shape == (8, len(A.ordered_constituents)) and np.nanmax(relerr(absorb, al['cube'][500])) < TIGHT
+    A.freqs = freqs
+    assert np.max(relerr(A.total_layer_alpha(absorb, 1.0), al['layers'][:, 500])) < TIGHT
+    assert np.max(relerr(A.total_layer_alpha(absorb, 2.5), 2.5 * absorb.sum(axis=1))) < 1e-14
+    j_nh3, j_h2o = A.ordered_constituents.index('nh3'), A.ordered_constituents.index('h2o')
+    w = np.ones(absorb.shape[1])
+    w[j_nh3], w[j_h2o] = 0.5, 2.0
+    lscale = {'nh3': 0.5, 'h2o': 2.0, 'not_a_constituent': 7.0}
+    assert np.max(relerr(A.total_layer_alpha(absorb, lscale), (absorb * w).sum(axis=1))) < 1e-14
+    assert np.max(relerr(A.get_single_layer(freqs, 500, atm, lscale), (absorb * w).sum(axis=1))) < TIGHT
+    A._save_alpha_memfil, A.tosave = True, []                       # the reference's per-layer cache list
+    A.total_layer_alpha(absorb, lscale)
+    assert len(A.tosave) == 1 and np.max(relerr(A.tosave[0], absorb * w)) < 1e-15
 
 
 @pytest.mark.parametrize('name', ['nh3_kd', 'nh3_sjsd', 'nh3_bg'])
