@@ -300,6 +300,13 @@ class Atmosphere:
                         y[j] = 1e-20
         return gas
 
+    @staticmethod
+    def is_present(c, tiny=1.0E-30):
+        """(does any entry of the profile exceed `tiny`, the profile with everything at or below it raised to `tiny`)
+        -- for log plots (atm_base.py:196-204)."""
+        floor = np.maximum(np.asarray(c, dtype=np.float64), tiny)
+        return bool((floor > tiny).any()), list(floor)
+
     def tweak(self):
         """Run the user's tweak module: modify(gas, cloud, C, Cl) -> (comment, gas, cloud)
         (atm_modify.py:12-21)."""
