@@ -552,3 +552,31 @@ def test_check_reuse_against_the_live_reference():
     # a numpy array as per-layer scale: the reference's isanynum lets float(array)'s TypeError through; here it compares
     arr = type('S', (), dict(freqs=f0, scale=np.array([1.0, 2.0, 3.0]), get_alpha='none', save_alpha='none'))()
     assert mine(arr, f0, np.array([1.0, 2.0, 3.0]), 'none', 'none') and not mine(arr, f0, np.array([1.0, 2.0, 3.5]), 'none', 'none')
+
+
+def test_total_layer_alpha_builds_the_layer_scale_the_reference_applies(monkeypatch):
+    """Alpha.total_layer_alpha / the {constituent: number} scale of get_single_layer (alpha.py:151-192, 218-233): the
+    host side (scale column per constituent, unknown names ignored, per-layer cache list) with the device scale-sum
+    replaced by its definition, against the reference's method on the same array."""
+    from radiobear_b200 import alpha as rbalpha
+    ref_alpha = _reference_module('alpha').Alpha
+
+    def scale_sum(cube, scale_mat=None, want_cube=False, ctx=None):           # rb_alpha_scale_sum, stated in numpy
+        cube = np.asarray(cube, dtype=np.float64)
+        scaled = cube * (1.0 if scale_mat is None else np.asarray(scale_mat).T[:, None, :])
+        return (scaled.sum(axis=2), scaled) if want_cube else scaled.sum(axis=2)
+    monkeypatch.setattr(engine, 'alpha_scale_sum', scale_sum)
+    rng = np.random.default_rng(9)
+    names = ['h2', 'h2o', 'h2s', 'nh3', 'ph3']
+    absorb = rng.random((6, 5)) * 1e-5
+    mine = object.__new__(rbalpha.Alpha)
+    ref = object.__new__(ref_alpha)
+    for obj in (mine, ref):
+        obj.ordered_constituents, obj.freqs, obj._save_alpha_memfil, obj.tosave = names, np.arange(6.0), True, []
+    for lscale in (1.0, 2.5, 3, {'nh3': 0.5, 'h2o': 2.0}, {'ph3': 0.0, 'bogus': 9.0}, {}):
+        got, want = mine.total_layer_alpha(absorb.copy(), lscale), ref.total_layer_alpha(absorb.copy(), lscale)
+        assert got.shape == want.shape and np.max(relerr(got, want)) < 1e-15, lscale
+        assert np.max(relerr(mine.tosave[-1], ref.tosave[-1])) == 0.0
+    assert mine._one_layer_scale({'nh3': 0.5, 'bogus': 2.0}) == {'nh3': [0.5]} and mine._one_layer_scale(2.0) == 2.0
+    with pytest.raises(ValueError):
+        mine.total_layer_alpha(absorb[0], 1.0)
