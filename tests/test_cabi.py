@@ -70,3 +70,16 @@ def test_product_never_imports_oracle():
             if fn.endswith('.py'):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), fn
+
+
+def test_integration_doc_structs_match_the_binding():
+    """The ctypes structures INTEGRATION.md shows a maintainer are the ones radiobear_b200/_lib.py binds (which the
+    layout test above checks against the header compiled with gcc): same field names, same order."""
+    import re
+    from radiobear_b200 import _lib
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    shown = {m.group(1): re.findall(r"\('(\w+)'", m.group(2))
+             for m in re.finditer(r"class (\w+)\(C\.Structure\):.*?_fields_ = \[(.*?)\]\n", text, re.S)}
+    assert shown, 'INTEGRATION.md lost its binding stub'
+    for name, fields in shown.items():
+        assert fields == [f[0] for f in getattr(_lib, name)._fields_], name
