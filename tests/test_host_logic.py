@@ -580,3 +580,38 @@ def test_total_layer_alpha_builds_the_layer_scale_the_reference_applies(monkeypa
     assert mine._one_layer_scale({'nh3': 0.5, 'bogus': 2.0}) == {'nh3': [0.5]} and mine._one_layer_scale(2.0) == 2.0
     with pytest.raises(ValueError):
         mine.total_layer_alpha(absorb[0], 1.0)
+
+
+def test_committed_bench_lines_carry_the_contract():
+    """The bench lines measured on B200 and committed under profiles/ (the round's final N = 1 / 2 / 4 / 8 runs): every
+    key the measurement contract names, the roofline on the binding resource with hbm beside it, sane relations between
+    the numbers (kernel time <= step time <= Planet.run time, achieved <= peak, bytes moved <= HBM peak x time)."""
+    import json
+    seen = 0
+    for name in ('r2_final2_bench_n1.json', 'r2_final_bench_n1.json', 'r2_final_bench_n2.json', 'r2_final_bench_n4.json',
+                 'r2_final_bench_n8.json'):
+        path = os.path.join(ROOT, 'profiles', name)
+        lines = [ln for ln in open(path) if ln.startswith('{')]
+        d = json.loads(lines[-1])
+        seen += 1
+        for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                  'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches', 'roofline'):
+            assert k in d, (name, k)
+        assert d['unit'] == 'pixel*freq/s' and d['dtype'] == 'f64' and d['vs_baseline'] is None and d['warmup'] >= 3
+        assert 'C4' in d['config']['workload'] and 'l2' in d['config'] and d['gpu_launches'] > 0
+        assert d['clocks']['sm_mhz'] >= 0.9 * d['clocks']['sm_max_mhz']
+        assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+        e = d['e2e']
+        assert e['h2d_bytes_per_step'] > 0 and e['d2h_bytes_per_step'] > 0 and e['value'] < d['value']
+        assert abs(d['value'] - d['config']['on_disc_pixels'] * d['config']['freqs'] / (d['ms_per_step'] * 1e-3)) < 1e-6 * d['value']
+        r = d['roofline']
+        assert r['bound'] == 'fp64' and r['unit'] == 'TFLOP/s' and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+        assert 0.3 < r['frac'] < 1.0 and r['ms_per_launch'] * r['launches_per_step'] <= d['ms_per_step'] * 1.001
+        h = r['hbm']
+        assert h['peak'] == 6453.4 and abs(h['frac'] - h['achieved'] / h['peak']) < 1e-9 and h['frac'] < 1.0
+        if d['n_gpus'] == 1:
+            c = d['cpu_baseline']
+            assert c['kind'] == 'port' and c['cores'] >= 1 and c['value'] > 0 and 'sample' in c
+            assert r['traffic'] >= h['algorithmic_bytes'] and r['traffic'] < 1.2 * h['algorithmic_bytes']
+            assert r['traffic'] / (r['ms_per_launch'] * 1e-3) < h['peak'] * 1e9
+    assert seen == 5
