@@ -730,7 +730,7 @@ def run_gpu(args):
                                           'issue-bound, see issue / smem'}}
             roofline.update(common)
         cores = 1
-        cpu_v, cpu_desc, _ = cpu_sample(cores, n_pix_per_core=int(os.environ.get('RB_BENCH_CPU_PIXELS', '160')), n_lay_per_core=128) if world == 1 else (None, None, None)
+        cpu_v, cpu_desc, _ = cpu_sample(cores, n_pix_per_core=int(os.environ.get('RB_BENCH_CPU_PIXELS', '256')), n_lay_per_core=128) if world == 1 else (None, None, None)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
